@@ -1,0 +1,260 @@
+/*
+ * mo_b200.h -- C-ABI of libmo_b200.so, the B200 (sm_100a) implementation of MatrixOne's per-block batch
+ * operators and vector-distance kernels.
+ *
+ * PART 1 is the reference's cgo surface, byte for byte the same prototypes as /root/reference/cgo/mo.h:24-73
+ * (Bitmap_*, {SignedInt,UnsignedInt,Float}_Vec*, Numeric_Vec*, Logic_Vec*, XCall), so the Go side
+ * (pkg/common/bitmap/cbitmap.go:33-50, pkg/sql/plan/function/cxcall.go:78-83) binds to it unchanged.
+ * Rules kept from cgo/README.md:12-16: only fixed-width ints, float/double and pointers cross the boundary.
+ *
+ * Every pointer argument may be either a HOST pointer (pageable or pinned; the library stages it through the
+ * calling thread's stream) or a DEVICE pointer obtained from MoB200_DeviceAlloc (zero-copy, the resident path).
+ * The library classifies each pointer with cudaPointerGetAttributes.  All pointers of one call must live on the
+ * same side unless stated otherwise.  Buffers stay owned by the caller (cgo/README.md:21-23).
+ *
+ * PART 2 declares the XCall argument block (reference cgo/xcall.h:24-31) and the funcIds this library adds
+ * (>= 100; ids 0..3 keep the reference meaning, cgo/mo.c:49-52).
+ *
+ * PART 3 is the residency/runtime extension (device + pinned allocation, copies, stream adoption, timers).
+ */
+#ifndef _MO_B200_H_
+#define _MO_B200_H_
+
+#include <stdint.h>
+#include <stdbool.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ======================================================================================================
+ * PART 1 -- reference ABI (cgo/mo.h)
+ * ==================================================================================================== */
+
+/* Bitmap ops -- replaces cgo/mo.c:19-47 (bodies in cgo/bitmap.h:47-149).  LSB-first uint64 words, set = NULL. */
+void Bitmap_Add(uint64_t *p, uint64_t pos);
+void Bitmap_Remove(uint64_t *p, uint64_t pos);
+bool Bitmap_Contains(uint64_t *p, uint64_t pos);
+bool Bitmap_IsEmpty(uint64_t *p, uint64_t nbits);
+uint64_t Bitmap_Count(uint64_t *p, uint64_t nbits);
+void Bitmap_And(uint64_t *dst, uint64_t *a, uint64_t *b, uint64_t nbits);
+void Bitmap_Or(uint64_t *dst, uint64_t *a, uint64_t *b, uint64_t nbits);
+void Bitmap_Not(uint64_t *dst, uint64_t *a, uint64_t nbits);
+
+/* Vector arithmetic -- replaces cgo/arith.c:316-580.  flag&1: a is scalar, flag&2: b is scalar
+ * (cgo/mo_impl.h:37-38).  Rows whose bit is set in `nulls` are skipped (r[i] untouched).
+ * Return codes as cgo/mo_impl.h:26-35 (see MO_RC_* below); overflow-flag quirks of arith.c are reproduced. */
+int32_t SignedInt_VecAdd(void *r, void *a, void *b, uint64_t n, uint64_t *nulls, int32_t flag, int32_t szof);
+int32_t UnsignedInt_VecAdd(void *r, void *a, void *b, uint64_t n, uint64_t *nulls, int32_t flag, int32_t szof);
+int32_t Float_VecAdd(void *r, void *a, void *b, uint64_t n, uint64_t *nulls, int32_t flag, int32_t szof);
+
+int32_t SignedInt_VecSub(void *r, void *a, void *b, uint64_t n, uint64_t *nulls, int32_t flag, int32_t szof);
+int32_t UnsignedInt_VecSub(void *r, void *a, void *b, uint64_t n, uint64_t *nulls, int32_t flag, int32_t szof);
+int32_t Float_VecSub(void *r, void *a, void *b, uint64_t n, uint64_t *nulls, int32_t flag, int32_t szof);
+
+int32_t SignedInt_VecMul(void *r, void *a, void *b, uint64_t n, uint64_t *nulls, int32_t flag, int32_t szof);
+int32_t UnsignedInt_VecMul(void *r, void *a, void *b, uint64_t n, uint64_t *nulls, int32_t flag, int32_t szof);
+int32_t Float_VecMul(void *r, void *a, void *b, uint64_t n, uint64_t *nulls, int32_t flag, int32_t szof);
+
+int32_t Float_VecDiv(void *r, void *a, void *b, uint64_t n, uint64_t *nulls, int32_t flag, int32_t szof);
+int32_t Float_VecIntegerDiv(void *r, void *a, void *b, uint64_t n, uint64_t *nulls, int32_t flag, int32_t szof);
+
+int32_t SignedInt_VecMod(void *r, void *a, void *b, uint64_t n, uint64_t *nulls, int32_t flag, int32_t szof);
+int32_t UnsignedInt_VecMod(void *r, void *a, void *b, uint64_t n, uint64_t *nulls, int32_t flag, int32_t szof);
+int32_t Float_VecMod(void *r, void *a, void *b, uint64_t n, uint64_t *nulls, int32_t flag, int32_t szof);
+
+/* Compare -- replaces cgo/compare.c:153-383.  r is bool[n] (1 byte each); `type` is a types.T id (MO_T_*). */
+int32_t Numeric_VecEq(void *r, void *a, void *b, uint64_t n, uint64_t *nulls, int32_t flag, int32_t type);
+int32_t Numeric_VecNe(void *r, void *a, void *b, uint64_t n, uint64_t *nulls, int32_t flag, int32_t type);
+int32_t Numeric_VecGt(void *r, void *a, void *b, uint64_t n, uint64_t *nulls, int32_t flag, int32_t type);
+int32_t Numeric_VecGe(void *r, void *a, void *b, uint64_t n, uint64_t *nulls, int32_t flag, int32_t type);
+int32_t Numeric_VecLt(void *r, void *a, void *b, uint64_t n, uint64_t *nulls, int32_t flag, int32_t type);
+int32_t Numeric_VecLe(void *r, void *a, void *b, uint64_t n, uint64_t *nulls, int32_t flag, int32_t type);
+
+/* Three-valued logic -- replaces cgo/logic.c:33-221.  The caller pre-fills rnulls = anulls | bnulls;
+ * And/Or clear the bits where the other operand dominates. */
+int32_t Logic_VecAnd(void *r, void *a, void *b, uint64_t n, uint64_t *anulls, uint64_t *bnulls, uint64_t *rnulls, int32_t flag);
+int32_t Logic_VecOr(void *r, void *a, void *b, uint64_t n, uint64_t *anulls, uint64_t *bnulls, uint64_t *rnulls, int32_t flag);
+int32_t Logic_VecXor(void *r, void *a, void *b, uint64_t n, uint64_t *nulls, int32_t flag);
+int32_t Logic_VecNot(void *r, void *a, uint64_t n, uint64_t *nulls, int32_t flag);
+
+/* XCall -- replaces cgo/mo.c:54-68.  runtimeId: 0 = "C", 1 = "CUDA" (cgo/xcall.h:44-45); this library runs every
+ * funcId on the GPU for BOTH runtime ids (there is no CPU implementation inside it).  errStr is the reference's
+ * 256-byte Pascal string: errStr[0] = length, text from errStr[1] (cgo/cuda/cuda.cpp:45-58, cxcall.go:76-89).
+ * args -> xcall_args_t[]: index 0 = result vector, 1..k = inputs.  Unknown funcId returns -1. */
+int32_t XCall(int64_t runtimeId, int64_t funcId, uint8_t *errStr, uint64_t *args, uint64_t len);
+
+/* ======================================================================================================
+ * PART 2 -- XCall argument block, type ids, return codes, funcIds
+ * ==================================================================================================== */
+
+/* cgo/xcall.h:24-31; filled by Vector.FillRawPtrLen, pkg/container/vector/vector.go:5161-5172 */
+typedef struct mo_xcall_args_t {
+    uint64_t *pnulls;  /* nulls bitmap words or NULL */
+    uint64_t nullCnt;  /* bitmap length IN BITS (field misnamed in the reference) */
+    uint8_t *pdata;    /* fixed-width values, or 24-byte varlena cells */
+    uint64_t dataSz;   /* bytes; typeSize*1 for a const vector */
+    uint8_t *parea;    /* varlena payload area or NULL */
+    uint64_t areaSz;
+} mo_xcall_args_t;
+
+#define MO_VARLENA_SZ 24         /* cgo/xcall.h:33 */
+#define MO_VARLENA_INLINE_SZ 23
+
+#define MO_RUNTIME_C 0
+#define MO_RUNTIME_CUDA 1
+
+/* return codes, cgo/mo_impl.h:26-35 */
+#define MO_RC_SUCCESS 0
+#define MO_RC_INTERNAL_ERROR 20101
+#define MO_RC_DIVISION_BY_ZERO 20200
+#define MO_RC_OUT_OF_RANGE 20201
+#define MO_RC_DATA_TRUNCATED 20202
+#define MO_RC_INVALID_ARGUMENT 20203
+
+/* types.T ids, pkg/container/types/types.go:35-67 == cgo/compare.c:20-38 */
+#define MO_T_BOOL 10
+#define MO_T_INT8 20
+#define MO_T_INT16 21
+#define MO_T_INT32 22
+#define MO_T_INT64 23
+#define MO_T_UINT8 25
+#define MO_T_UINT16 26
+#define MO_T_UINT32 27
+#define MO_T_UINT64 28
+#define MO_T_FLOAT32 30
+#define MO_T_FLOAT64 31
+#define MO_T_DATE 50
+#define MO_T_TIME 51
+#define MO_T_DATETIME 52
+#define MO_T_TIMESTAMP 53
+
+/* reference funcIds, cgo/mo.c:49-52 == cxcall.go:33-38.  args: [0] f64 result, [1] vec col, [2] vec col
+ * (varlena cells; either side may be const: dataSz == 24).  Semantics of cgo/xcall.c:23-134:
+ * float diff, squares accumulated in double, optional sqrt. */
+#define MO_XCALL_L2DISTANCE_F32 0
+#define MO_XCALL_L2DISTANCE_F64 1
+#define MO_XCALL_L2DISTANCE_SQ_F32 2
+#define MO_XCALL_L2DISTANCE_SQ_F64 3
+
+/* --- new: row-wise distances with the Go semantics of pkg/vectorindex/metric/distance_func.go (accumulator type =
+ * element type, 8-way unrolled association), i.e. what the SQL builtins l2_distance / l2_distance_sq / inner_product /
+ * cosine_distance / cosine_similarity compute (pkg/vectorize/moarray/external.go:171-260).  Same 3-arg layout as
+ * ids 0..3, result float64[len].  Bit-exact with the Go loops.  dim mismatch -> MO_RC_INVALID_ARGUMENT. */
+#define MO_XCALL_GO_L2_F32 100
+#define MO_XCALL_GO_L2_F64 101
+#define MO_XCALL_GO_L2SQ_F32 102
+#define MO_XCALL_GO_L2SQ_F64 103
+#define MO_XCALL_GO_IP_F32 104
+#define MO_XCALL_GO_IP_F64 105
+#define MO_XCALL_GO_COSDIST_F32 106
+#define MO_XCALL_GO_COSDIST_F64 107
+#define MO_XCALL_GO_COSSIM_F32 108
+#define MO_XCALL_GO_COSSIM_F64 109
+
+/* --- new: single-column aggregates (aggexec sumavg2.go / count2.go / minmax2.go semantics, no group-by = H0).
+ * funcId = MO_XCALL_AGG(op, T).  args: [0] result: pdata -> one 8-byte value (int64 / uint64 / float64, or the
+ * column type for MIN/MAX, zero-extended), pnulls -> 1-word bitmap, bit 0 set when the result is NULL
+ * (all-null input); [1] the column (fixed width, pnulls optional).  len = rows.
+ * SUM over signed ints returns MO_RC_OUT_OF_RANGE exactly when the serial Go loop would (int64OfCheck). */
+#define MO_AGG_SUM 0
+#define MO_AGG_COUNT 1   /* COUNT(col): non-null rows; result int64 */
+#define MO_AGG_MIN 2
+#define MO_AGG_MAX 3
+#define MO_AGG_AVG 4     /* result float64 = sum/cnt, NULL when cnt == 0 */
+#define MO_XCALL_AGG(op, T) (0x1000 + ((op) << 8) + (T))
+
+/* --- new: fused TPC-H Q6 shape  SUM(a*b) WHERE d in [d_lo,d_hi) AND b BETWEEN b_lo AND b_hi AND c < c_hi
+ * args: [0] result f64 (+ 1-word nulls bitmap, bit0 = no row qualified) ; [1] d int32/DATE col ; [2] b f64 col
+ * (discount) ; [3] c f64 col (quantity) ; [4] a f64 col (extendedprice) ; [5] params: pdata -> mo_q6_params_t.
+ * Optional second result word: if args[0].dataSz >= 16 the qualifying row count (int64) is written at pdata+8. */
+#define MO_XCALL_Q6_FILTER_SUM 0x2000
+typedef struct mo_q6_params_t {
+    int32_t date_lo, date_hi;  /* date_lo <= d < date_hi */
+    double disc_lo, disc_hi;   /* disc_lo <= b <= disc_hi (BETWEEN) */
+    double qty_hi;             /* c < qty_hi */
+} mo_q6_params_t;
+
+/* --- new: fused TPC-H Q1 shape: filter d <= cutoff, group by two 1-byte keys, 8 aggregates (q1.sql:5-12).
+ * args: [0] result: pdata -> mo_q1_result_t ; [1] shipdate int32 ; [2] quantity f64 ; [3] extendedprice f64 ;
+ * [4] discount f64 ; [5] tax f64 ; [6] returnflag ; [7] linestatus ; [8] params: pdata -> int32 cutoff.
+ * Key columns: dataSz == len -> packed uint8 column; dataSz == 24*len -> MatrixOne varlena cells (inline char(1)). */
+#define MO_XCALL_Q1_GROUP_AGG 0x2001
+#define MO_Q1_MAX_GROUPS 8
+typedef struct mo_q1_group_t {
+    uint8_t returnflag, linestatus; uint8_t pad[6];
+    int64_t first_row;      /* global row index of the first qualifying row of the group (first-seen order) */
+    double sum_qty, sum_base_price, sum_disc_price, sum_charge, avg_qty, avg_price, avg_disc;
+    double sum_disc;        /* numerator of avg_disc (partials for a cross-GPU reduce) */
+    int64_t count_order;
+} mo_q1_group_t;
+typedef struct mo_q1_result_t {
+    int64_t ngroups;        /* groups sorted by first_row (= reference first-seen group-id order) */
+    mo_q1_group_t groups[MO_Q1_MAX_GROUPS];
+} mo_q1_result_t;
+
+/* --- new: brute-force top-k (GoBruteForceIndex.Search, pkg/vectorindex/brute_force/brute_force.go:248-341).
+ * args: [0] result keys int64[nq*k] ; [1] result distances f64[nq*k] ; [2] dataset f32 row-major (dataSz = n*dim*4)
+ * ; [3] queries f32 row-major (dataSz = nq*dim*4) ; [4] params: pdata -> mo_search_params_t.  len = nq.
+ * Distances are bit-exact with the Go metric functions; ties between equal distances resolve to the lower row id. */
+#define MO_XCALL_BRUTEFORCE_TOPK_F32 0x3000
+/* IVF-flat probe (IvfflatSearchIndex.Search, pkg/vectorindex/ivfflat/search.go:509-630):
+ * args as above plus [5] centroids f32 (nlist*dim) ; [6] list offsets int64[nlist+1] into a list-ordered dataset ;
+ * [7] row ids int64[n] (original pk of each list-ordered row). */
+#define MO_XCALL_IVF_TOPK_F32 0x3001
+typedef struct mo_search_params_t {
+    int64_t n, dim, nq;
+    int32_t k;        /* RuntimeConfig.Limit */
+    int32_t metric;   /* MO_METRIC_* */
+    int32_t nprobe;   /* IVF only */
+    int32_t sqrt_out; /* DistanceTransformIvfflat: sqrt on the final k (user asked l2_distance) */
+    int64_t nlist;    /* IVF only */
+    int64_t key_base; /* added to row ordinals (dataset shard offset in a multi-GPU run) */
+} mo_search_params_t;
+#define MO_METRIC_L2 0      /* metric/types.go MetricType: both L2 variants search with L2sq (distance_func.go:507-524) */
+#define MO_METRIC_IP 1
+#define MO_METRIC_COS 2
+#define MO_METRIC_L1 3
+#define MO_METRIC_L2SQ 4
+
+/* merge of per-shard top-k lists (MergeTop / hnsw sub-index merge, pkg/vectorindex/hnsw/search.go:89-135):
+ * args: [0] out keys int64[nq*k] ; [1] out dist f64[nq*k] ; [2] in keys int64[nshards*nq*k] ; [3] in dist f64[...] ;
+ * [4] params mo_search_params_t (n = nshards, nq, k). */
+#define MO_XCALL_TOPK_MERGE 0x3002
+
+/* ======================================================================================================
+ * PART 3 -- runtime / residency extension
+ * ==================================================================================================== */
+int32_t MoB200_Init(int32_t device);          /* idempotent; device < 0 -> $MO_B200_DEVICE, $LOCAL_RANK or 0 */
+const char *MoB200_Version(void);
+int32_t MoB200_DeviceCount(void);
+int32_t MoB200_DeviceAlloc(uint64_t bytes, void **dptr);
+int32_t MoB200_DeviceFree(void *dptr);
+int32_t MoB200_HostAlloc(uint64_t bytes, void **hptr);  /* pinned host memory (replaces malloc.CAllocator) */
+int32_t MoB200_HostFree(void *hptr);
+int32_t MoB200_HostRegister(void *hptr, uint64_t bytes);
+int32_t MoB200_HostUnregister(void *hptr);
+int32_t MoB200_Upload(void *dst_dev, const void *src_host, uint64_t bytes);   /* on the calling thread's stream, synchronous */
+int32_t MoB200_Download(void *dst_host, const void *src_dev, uint64_t bytes);
+int32_t MoB200_Memset(void *dst_dev, int32_t value, uint64_t bytes);
+int32_t MoB200_Sync(void);                    /* synchronize the calling thread's stream */
+int32_t MoB200_SetStream(void *cuda_stream);  /* adopt an external cudaStream_t for the calling thread (NULL = own) */
+int32_t MoB200_TimerStart(void);              /* CUDA event on the calling thread's stream */
+int32_t MoB200_TimerStop(float *ms);          /* records, synchronizes, returns elapsed milliseconds */
+uint64_t MoB200_KernelLaunchCount(void);      /* kernels launched by this library since load (all threads) */
+int32_t MoB200_LastError(char *buf, uint64_t buflen);  /* thread-local last error text */
+int32_t MoB200_FlushL2(void);                 /* write a >L2-sized scratch buffer (bench hygiene) */
+int32_t MoB200_SetTuning(const char *name, int32_t value);  /* kernel-variant knobs used by tools/tune.py; returns 0 if known */
+
+/* synthetic column generators used by bench.py / tests (counter-based, reproducible on the host: see
+ * matrixone_b200/datagen.py).  All write DEVICE memory, rows [row0, row0+n). */
+int32_t MoB200_GenLineitem(uint64_t seed, uint64_t row0, uint64_t n, int32_t *shipdate, double *quantity,
+                           double *extendedprice, double *discount, double *tax, uint8_t *returnflag, uint8_t *linestatus);
+int32_t MoB200_GenInt64(uint64_t seed, uint64_t row0, uint64_t n, int64_t *out, uint64_t *nulls, uint32_t null_per_mille);
+int32_t MoB200_GenVectorsF32(uint64_t seed, uint64_t row0, uint64_t n, int64_t dim, float *out,
+                             const float *centers, int64_t ncenters, float sigma);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* _MO_B200_H_ */

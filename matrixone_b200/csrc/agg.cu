@@ -1,0 +1,428 @@
+// agg.cu -- single-column aggregates without group-by (the reference's H0 path: Group.buildOneBatch ->
+// agg.BulkFill, pkg/sql/colexec/group/exec2.go:305-315) : SUM / AVG / COUNT / MIN / MAX over a fixed-width
+// column + nulls bitmap.  Semantics: pkg/sql/colexec/aggexec/sumavg2.go:133-199,254-353, count2.go:120-146,
+// minmax2.go:49-80.
+//
+// HBM-bound streaming reduction: every thread issues 4 independent 128-bit L1-bypassing loads per iteration
+// (grid = 148 SMs x CTAS_PER_SM persistent CTAs, grid-stride), the nulls word for 64 rows is a warp-broadcast
+// load, partials are combined by warp shuffles -> shared memory -> one per-CTA record; the last CTA to finish
+// (atomicInc ticket) folds the per-CTA records in index order, so results are run-to-run deterministic.
+//
+// Algorithmic bytes: sizeof(T) per row (+ 1/8 byte per row with a nulls bitmap).
+#include "common.cuh"
+#include <cstring>
+#include <cmath>
+
+using namespace mob;
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kCtasPerSm = 4;
+constexpr int kUnroll = 4;
+
+enum Kind { K_SUM_SIGNED = 0, K_SUM_UNSIGNED = 1, K_SUM_FLOAT = 2, K_MIN = 3, K_MAX = 4 };
+
+// Per-CTA / final record.  Meaning of the words depends on Kind:
+//  SUM_SIGNED  : w0,w1 = sum of non-negative values (lo,hi) ; w2,w3 = sum of magnitudes of negative values (lo,hi)
+//  SUM_UNSIGNED: w0,w1 = sum (lo,hi)
+//  SUM_FLOAT   : d = sum (double)
+//  MIN / MAX   : w0 = value bits (zero-extended), w1 = smallest row index of a non-null row (floats: NaN rule)
+//  all         : cnt = non-null rows
+struct Rec { uint64_t w0, w1, w2, w3; double d; uint64_t cnt; uint64_t pad0, pad1; };
+
+__device__ __forceinline__ void add128(uint64_t &lo, uint64_t &hi, uint64_t x) { lo += x; hi += (lo < x); }
+__device__ __forceinline__ void add128p(uint64_t &lo, uint64_t &hi, uint64_t lo2, uint64_t hi2) {
+    lo += lo2; hi += hi2 + (lo < lo2);
+}
+
+template <typename T> struct Bits { };
+template <typename T> __device__ __forceinline__ uint64_t to_bits(T v) { uint64_t r = 0; memcpy(&r, &v, sizeof(T)); return r; }
+template <typename T> __device__ __forceinline__ T from_bits(uint64_t b) { T v; memcpy(&v, &b, sizeof(T)); return v; }
+
+template <typename T, int KIND>
+struct Acc {
+    uint64_t w0 = 0, w1 = 0, w2 = 0, w3 = 0, cnt = 0;
+    double d = 0.0;
+    T mm;
+    bool has = false;
+    uint64_t first = ~0ull;
+
+    __device__ __forceinline__ void add(T v, uint64_t row) {
+        cnt++;
+        if (KIND == K_SUM_SIGNED) {
+            int64_t x = (int64_t)v;
+            uint64_t p = x >= 0 ? (uint64_t)x : 0ull;
+            uint64_t m = x < 0 ? (0ull - (uint64_t)x) : 0ull;
+            add128(w0, w1, p);
+            add128(w2, w3, m);
+        } else if (KIND == K_SUM_UNSIGNED) {
+            add128(w0, w1, (uint64_t)v);
+        } else if (KIND == K_SUM_FLOAT) {
+            d = d + (double)v;  // sums[g] += float64(val), sumavg2.go:153
+        } else {
+            if (!has) { has = true; mm = v; first = row; }
+            else if (KIND == K_MIN ? (v < mm) : (v > mm)) mm = v;       // strict compare, minmax2.go:73
+            else if (mm != mm && !(v != v)) { /* running value NaN but not the global first row: Go would never hold it */ mm = v; }
+        }
+    }
+    __device__ __forceinline__ void merge(const Rec &r) {
+        if (r.cnt == 0) return;
+        if (KIND == K_SUM_SIGNED) { add128p(w0, w1, r.w0, r.w1); add128p(w2, w3, r.w2, r.w3); }
+        else if (KIND == K_SUM_UNSIGNED) { add128p(w0, w1, r.w0, r.w1); }
+        else if (KIND == K_SUM_FLOAT) { d = d + r.d; }
+        else {
+            T v = from_bits<T>(r.w0);
+            if (!has) { has = true; mm = v; first = r.w1; }
+            else {
+                if (r.w1 < first) first = r.w1;
+                if (KIND == K_MIN ? (v < mm) : (v > mm)) mm = v;
+                else if (mm != mm && !(v != v)) mm = v;
+            }
+        }
+        cnt += r.cnt;
+    }
+    __device__ __forceinline__ Rec rec() const {
+        Rec r; r.w0 = w0; r.w1 = w1; r.w2 = w2; r.w3 = w3; r.d = d; r.cnt = cnt; r.pad0 = r.pad1 = 0;
+        if (KIND == K_MIN || KIND == K_MAX) { r.w0 = has ? to_bits<T>(mm) : 0; r.w1 = first; }
+        return r;
+    }
+};
+
+__device__ __forceinline__ Rec shfl_rec(const Rec &r, int o) {
+    Rec q;
+    q.w0 = __shfl_xor_sync(0xffffffffu, r.w0, o); q.w1 = __shfl_xor_sync(0xffffffffu, r.w1, o);
+    q.w2 = __shfl_xor_sync(0xffffffffu, r.w2, o); q.w3 = __shfl_xor_sync(0xffffffffu, r.w3, o);
+    q.d = __shfl_xor_sync(0xffffffffu, r.d, o); q.cnt = __shfl_xor_sync(0xffffffffu, r.cnt, o);
+    q.pad0 = q.pad1 = 0;
+    return q;
+}
+
+// Combine two records in a FIXED order (a then b): used by every tree level so the association is data independent.
+template <typename T, int KIND>
+__device__ __forceinline__ Rec combine(const Rec &a, const Rec &b) {
+    Acc<T, KIND> x;
+    x.merge(a); x.merge(b);
+    return x.rec();
+}
+
+template <typename T, int KIND>
+__device__ Rec block_reduce(Rec r) {
+    __shared__ Rec sm[kThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Rec q = shfl_rec(r, o);
+        // lower lane first keeps (a,b) order identical on both partners for the commutative-but-not-associative fp add
+        r = (lane & o) ? combine<T, KIND>(q, r) : combine<T, KIND>(r, q);
+    }
+    if (lane == 0) sm[warp] = r;
+    __syncthreads();
+    if (warp == 0) {
+        Rec z; z.w0 = z.w1 = z.w2 = z.w3 = 0; z.d = 0; z.cnt = 0; z.pad0 = z.pad1 = 0;
+        r = lane < kThreads / 32 ? sm[lane] : z;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            Rec q = shfl_rec(r, o);
+            r = (lane & o) ? combine<T, KIND>(q, r) : combine<T, KIND>(r, q);
+        }
+    }
+    __syncthreads();
+    return r;  // valid in warp 0
+}
+
+// col must be 16-byte aligned for the vector path (vec = true); rows are [0, n).
+template <typename T, int KIND>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
+agg_kernel(const T *__restrict__ col, const uint64_t *__restrict__ nulls, uint64_t n, bool vec,
+           Rec *__restrict__ partials, Rec *__restrict__ out, unsigned *ticket) {
+    constexpr int V = 16 / sizeof(T);  // rows per 128-bit load
+    Acc<T, KIND> acc;
+    const uint64_t tid = blockIdx.x * (uint64_t)kThreads + threadIdx.x;
+    const uint64_t nthreads = (uint64_t)gridDim.x * kThreads;
+    uint64_t done = 0;
+    if (vec) {
+        const uint64_t nvec = n / V;
+        const int4 *p = reinterpret_cast<const int4 *>(col);
+        uint64_t v = tid;
+        for (; v + (kUnroll - 1) * nthreads < nvec; v += kUnroll * nthreads) {
+            int4 x[kUnroll];
+#pragma unroll
+            for (int k = 0; k < kUnroll; k++) x[k] = ld_stream16(p + v + k * nthreads);
+#pragma unroll
+            for (int k = 0; k < kUnroll; k++) {
+                const uint64_t row0 = (v + k * nthreads) * V;
+                uint32_t nb = nulls ? (uint32_t)((__ldg(nulls + (row0 >> 6)) >> (row0 & 63)) & ((1u << V) - 1u)) : 0u;
+                if (V == 16 && nulls) nb = (uint32_t)((__ldg(nulls + (row0 >> 6)) >> (row0 & 63)) & 0xffffu);
+                T e[V];
+                memcpy(e, &x[k], 16);
+#pragma unroll
+                for (int j = 0; j < V; j++)
+                    if (!((nb >> j) & 1u)) acc.add(e[j], row0 + j);
+            }
+        }
+        for (; v < nvec; v += nthreads) {
+            int4 x = ld_stream16(p + v);
+            const uint64_t row0 = v * V;
+            uint32_t nb = nulls ? (uint32_t)((__ldg(nulls + (row0 >> 6)) >> (row0 & 63)) & (V == 16 ? 0xffffu : ((1u << V) - 1u))) : 0u;
+            T e[V];
+            memcpy(e, &x, 16);
+#pragma unroll
+            for (int j = 0; j < V; j++)
+                if (!((nb >> j) & 1u)) acc.add(e[j], row0 + j);
+        }
+        done = nvec * V;
+    }
+    // scalar tail (and the whole column when it is not 16-byte aligned)
+    for (uint64_t i = done + tid; i < n; i += nthreads)
+        if (!bm_test(nulls, i)) acc.add(col[i], i);
+
+    Rec r = block_reduce<T, KIND>(acc.rec());
+    __shared__ bool last;
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = r;
+        __threadfence();
+        unsigned t = atomicInc(ticket, gridDim.x - 1);  // wraps to 0 after the last CTA: reusable without a memset
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        Acc<T, KIND> f;
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += kThreads) f.merge(partials[b]);  // fixed index order per thread
+        Rec fr = block_reduce<T, KIND>(f.rec());
+        if (threadIdx.x == 0) {
+            if ((KIND == K_MIN || KIND == K_MAX) && fr.cnt) {
+                // Go rule (minmax2.go:69-75): the first non-null value initialises; a NaN there is never replaced
+                T fv = col[fr.w1];
+                if (fv != fv) fr.w0 = to_bits<T>(fv);
+            }
+            *out = fr;
+        }
+    }
+}
+
+// ---- exact serial-order overflow check for SUM over signed ints (slow path, rare) ---------------------------------
+// Go errors at the first row whose running sum leaves int64 (int64OfCheck, sumavg2.go:89-94).  Each thread summarises a
+// contiguous segment as (total, max prefix, min prefix) in 128-bit; segments are then folded in row order.
+struct Seg { __int128 total, maxp, minp; };
+
+template <typename T>
+__global__ void prefix_seg_kernel(const T *__restrict__ col, const uint64_t *__restrict__ nulls, uint64_t n, uint64_t seg_rows, Seg *segs) {
+    uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    uint64_t r0 = s * seg_rows, r1 = r0 + seg_rows;
+    if (r1 > n) r1 = n;
+    __int128 tot = 0, mx = 0, mn = 0;
+    for (uint64_t i = r0; i < r1; i++) {
+        if (bm_test(nulls, i)) continue;
+        tot += (__int128)(int64_t)col[i];
+        if (tot > mx) mx = tot;
+        if (tot < mn) mn = tot;
+    }
+    segs[s].total = tot; segs[s].maxp = mx; segs[s].minp = mn;
+}
+__global__ void prefix_fold_kernel(const Seg *segs, uint64_t nseg, int32_t *overflow) {
+    __int128 run = 0; int32_t ov = 0;
+    const __int128 hi = (__int128)INT64_MAX, lo = (__int128)INT64_MIN;
+    for (uint64_t s = 0; s < nseg; s++) {
+        if (run + segs[s].maxp > hi || run + segs[s].minp < lo) { ov = 1; break; }
+        run += segs[s].total;
+    }
+    *overflow = ov;
+}
+
+template <typename T, int KIND>
+int launch_agg(ThreadCtx &t, const void *dcol, const uint64_t *dnulls, uint64_t n, Rec *hrec) {
+    int grid = num_sms() * kCtasPerSm;
+    uint64_t work = (n + (16 / sizeof(T)) * kThreads - 1) / ((16 / sizeof(T)) * kThreads);
+    if ((uint64_t)grid > work) grid = work ? (int)work : 1;
+    Rec *partials = (Rec *)arena_alloc(t, sizeof(Rec) * (size_t)(grid + 1));
+    if (!partials) return MO_RC_INTERNAL_ERROR;
+    Rec *out = partials + grid;
+    bool vec = (((uintptr_t)dcol) & 15) == 0;
+    agg_kernel<T, KIND><<<grid, kThreads, 0, t.stream>>>((const T *)dcol, dnulls, n, vec, partials, out, t.ctrl);
+    MOB_LAUNCH_CHECK();
+    return read_back(t, hrec, out, sizeof(Rec));
+}
+
+template <typename T>
+int signed_prefix_overflow(ThreadCtx &t, const void *dcol, const uint64_t *dnulls, uint64_t n, int32_t *ov) {
+    const uint64_t nseg_target = (uint64_t)num_sms() * 256;
+    uint64_t seg_rows = (n + nseg_target - 1) / nseg_target;
+    if (seg_rows < 64) seg_rows = 64;
+    uint64_t nseg = (n + seg_rows - 1) / seg_rows;
+    Seg *segs = (Seg *)arena_alloc(t, sizeof(Seg) * nseg + 16);
+    if (!segs) return MO_RC_INTERNAL_ERROR;
+    int32_t *dov = (int32_t *)(segs + nseg);
+    prefix_seg_kernel<T><<<(unsigned)((nseg + 255) / 256), 256, 0, t.stream>>>((const T *)dcol, dnulls, n, seg_rows, segs);
+    MOB_LAUNCH_CHECK();
+    prefix_fold_kernel<<<1, 1, 0, t.stream>>>(segs, nseg, dov);
+    MOB_LAUNCH_CHECK();
+    return read_back(t, ov, dov, 4);
+}
+
+template <typename T>
+int run_sum_signed(ThreadCtx &t, const void *dcol, const uint64_t *dnulls, uint64_t n, int64_t *sum, uint64_t *cnt) {
+    Rec r;
+    int rc = launch_agg<T, K_SUM_SIGNED>(t, dcol, dnulls, n, &r);
+    if (rc) return rc;
+    *cnt = r.cnt;
+    // total = pos - negmag, exact in 128 bits
+    unsigned __int128 pos = ((unsigned __int128)r.w1 << 64) | r.w0, neg = ((unsigned __int128)r.w3 << 64) | r.w2;
+    __int128 total = (__int128)pos - (__int128)neg;
+    *sum = (int64_t)total;
+    const unsigned __int128 lim_pos = (unsigned __int128)INT64_MAX, lim_neg = (unsigned __int128)1 << 63;
+    if (pos <= lim_pos && neg <= lim_neg) return MO_RC_SUCCESS;  // no prefix can leave int64: every prefix lies in [-neg, pos]
+    int32_t ov = 0;
+    rc = signed_prefix_overflow<T>(t, dcol, dnulls, n, &ov);
+    if (rc) return rc;
+    return ov ? MO_RC_OUT_OF_RANGE : MO_RC_SUCCESS;
+}
+
+template <typename T>
+int run_sum_unsigned(ThreadCtx &t, const void *dcol, const uint64_t *dnulls, uint64_t n, uint64_t *sum, uint64_t *cnt) {
+    Rec r;
+    int rc = launch_agg<T, K_SUM_UNSIGNED>(t, dcol, dnulls, n, &r);
+    if (rc) return rc;
+    *cnt = r.cnt; *sum = r.w0;
+    return r.w1 ? MO_RC_OUT_OF_RANGE : MO_RC_SUCCESS;  // prefixes are monotone: overflow iff the exact total exceeds 2^64-1
+}
+
+template <typename T>
+int run_sum_float(ThreadCtx &t, const void *dcol, const uint64_t *dnulls, uint64_t n, double *sum, uint64_t *cnt) {
+    Rec r;
+    int rc = launch_agg<T, K_SUM_FLOAT>(t, dcol, dnulls, n, &r);
+    if (rc) return rc;
+    *cnt = r.cnt; *sum = r.d;
+    return MO_RC_SUCCESS;
+}
+
+template <typename T, int KIND>
+int run_minmax(ThreadCtx &t, const void *dcol, const uint64_t *dnulls, uint64_t n, uint64_t *bits, uint64_t *cnt) {
+    Rec r;
+    int rc = launch_agg<T, KIND>(t, dcol, dnulls, n, &r);
+    if (rc) return rc;
+    *cnt = r.cnt; *bits = r.w0;
+    return MO_RC_SUCCESS;
+}
+
+int type_size(int T) {
+    switch (T) {
+    case MO_T_BOOL: case MO_T_INT8: case MO_T_UINT8: return 1;
+    case MO_T_INT16: case MO_T_UINT16: return 2;
+    case MO_T_INT32: case MO_T_UINT32: case MO_T_FLOAT32: case MO_T_DATE: return 4;
+    case MO_T_INT64: case MO_T_UINT64: case MO_T_FLOAT64: case MO_T_TIME: case MO_T_DATETIME: case MO_T_TIMESTAMP: return 8;
+    }
+    return 0;
+}
+
+__global__ void popcount_kernel(const uint64_t *p, uint64_t nbits, unsigned long long *out) {
+    // count set bits among the first nbits (last word masked, cgo/bitmap.h:110-131)
+    uint64_t nw = (nbits + 63) >> 6;
+    unsigned long long c = 0;
+    for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < nw; w += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t v = p[w];
+        if (w == nw - 1 && (nbits & 63)) v &= ((1ull << (nbits & 63)) - 1ull);
+        c += __popcll(v);
+    }
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+}  // namespace
+
+namespace mob {
+
+int bitmap_count_device(ThreadCtx &t, const uint64_t *dp, uint64_t nbits, uint64_t *count) {
+    if (nbits == 0 || !dp) { *count = 0; return MO_RC_SUCCESS; }
+    unsigned long long *dout = (unsigned long long *)arena_alloc(t, 8);
+    if (!dout) return MO_RC_INTERNAL_ERROR;
+    MOB_CUDA_TRY(cudaMemsetAsync(dout, 0, 8, t.stream));
+    uint64_t nw = (nbits + 63) >> 6;
+    int grid = (int)((nw + 255) / 256);
+    if (grid > num_sms() * 8) grid = num_sms() * 8;
+    popcount_kernel<<<grid, 256, 0, t.stream>>>(dp, nbits, dout);
+    MOB_LAUNCH_CHECK();
+    return read_back(t, count, dout, 8);
+}
+
+// XCall family MO_XCALL_AGG(op, T): args[0] = result, args[1] = column.  See include/mo_b200.h.
+int xcall_agg(int op, int T, mo_xcall_args_t *args, uint64_t len) {
+    ThreadCtx &t = tctx();
+    if (!t.ready) return MO_RC_INTERNAL_ERROR;
+    const int sz = type_size(T);
+    if (!sz || T == MO_T_BOOL && op != MO_AGG_COUNT && op != MO_AGG_MIN && op != MO_AGG_MAX) { set_error("agg: unsupported type %d", T); return MO_RC_INVALID_ARGUMENT; }
+    if (!args[0].pdata || args[0].dataSz < 8) { set_error("agg: result vector must hold 8 bytes"); return MO_RC_INVALID_ARGUMENT; }
+    if (args[1].dataSz < (uint64_t)sz * len) { set_error("agg: column shorter than len"); return MO_RC_INVALID_ARGUMENT; }
+    Stager st(t);
+    const void *dcol = st.in(args[1].pdata, (size_t)sz * len);
+    const uint64_t *dnulls = (const uint64_t *)st.in(args[1].pnulls, args[1].pnulls ? ((len + 63) / 64) * 8 : 0);
+    if (st.failed) { st.finish(); return MO_RC_INTERNAL_ERROR; }
+
+    uint64_t bits = 0, cnt = 0; int rc = MO_RC_SUCCESS; bool isnull = false;
+    const bool is_signed = T >= MO_T_INT8 && T <= MO_T_INT64, is_unsigned = T >= MO_T_UINT8 && T <= MO_T_UINT64;
+    const bool is_float = T == MO_T_FLOAT32 || T == MO_T_FLOAT64;
+    if (len == 0) { isnull = (op != MO_AGG_COUNT); }
+    else if (op == MO_AGG_COUNT) {
+        uint64_t nn = 0;
+        rc = bitmap_count_device(t, dnulls, dnulls ? len : 0, &nn);
+        bits = len - nn;
+    } else if (op == MO_AGG_SUM || op == MO_AGG_AVG) {
+        double dsum = 0; int64_t isum = 0; uint64_t usum = 0;
+        if (is_signed) {
+            switch (sz) {
+            case 1: rc = run_sum_signed<int8_t>(t, dcol, dnulls, len, &isum, &cnt); break;
+            case 2: rc = run_sum_signed<int16_t>(t, dcol, dnulls, len, &isum, &cnt); break;
+            case 4: rc = run_sum_signed<int32_t>(t, dcol, dnulls, len, &isum, &cnt); break;
+            default: rc = run_sum_signed<int64_t>(t, dcol, dnulls, len, &isum, &cnt); break;
+            }
+            memcpy(&bits, &isum, 8); dsum = (double)isum;
+        } else if (is_unsigned) {
+            switch (sz) {
+            case 1: rc = run_sum_unsigned<uint8_t>(t, dcol, dnulls, len, &usum, &cnt); break;
+            case 2: rc = run_sum_unsigned<uint16_t>(t, dcol, dnulls, len, &usum, &cnt); break;
+            case 4: rc = run_sum_unsigned<uint32_t>(t, dcol, dnulls, len, &usum, &cnt); break;
+            default: rc = run_sum_unsigned<uint64_t>(t, dcol, dnulls, len, &usum, &cnt); break;
+            }
+            bits = usum; dsum = (double)usum;
+        } else if (is_float) {
+            if (sz == 4) rc = run_sum_float<float>(t, dcol, dnulls, len, &dsum, &cnt);
+            else rc = run_sum_float<double>(t, dcol, dnulls, len, &dsum, &cnt);
+            memcpy(&bits, &dsum, 8);
+        } else { set_error("sum: unsupported type %d", T); rc = MO_RC_INVALID_ARGUMENT; }
+        isnull = cnt == 0;
+        if (op == MO_AGG_AVG && !isnull) { double avg = dsum / (double)cnt; memcpy(&bits, &avg, 8); }  // sumavg2.go:331
+    } else if (op == MO_AGG_MIN || op == MO_AGG_MAX) {
+#define MM(TT) (op == MO_AGG_MIN ? run_minmax<TT, K_MIN>(t, dcol, dnulls, len, &bits, &cnt) : run_minmax<TT, K_MAX>(t, dcol, dnulls, len, &bits, &cnt))
+        switch (T) {
+        case MO_T_BOOL: case MO_T_UINT8: rc = MM(uint8_t); break;
+        case MO_T_INT8: rc = MM(int8_t); break;
+        case MO_T_INT16: rc = MM(int16_t); break;
+        case MO_T_UINT16: rc = MM(uint16_t); break;
+        case MO_T_INT32: case MO_T_DATE: rc = MM(int32_t); break;
+        case MO_T_UINT32: rc = MM(uint32_t); break;
+        case MO_T_INT64: case MO_T_TIME: case MO_T_DATETIME: case MO_T_TIMESTAMP: rc = MM(int64_t); break;
+        case MO_T_UINT64: rc = MM(uint64_t); break;
+        case MO_T_FLOAT32: rc = MM(float); break;
+        case MO_T_FLOAT64: rc = MM(double); break;
+        default: rc = MO_RC_INVALID_ARGUMENT;
+        }
+#undef MM
+        isnull = cnt == 0;
+    } else { set_error("agg: unknown op %d", op); rc = MO_RC_INVALID_ARGUMENT; }
+
+    // write the result (host memory directly; device memory through the stream)
+    if (rc == MO_RC_SUCCESS || rc == MO_RC_OUT_OF_RANGE) {
+        uint64_t nullword = isnull ? 1ull : 0ull;
+        if (is_device_ptr(args[0].pdata)) cudaMemcpyAsync(args[0].pdata, &bits, 8, cudaMemcpyHostToDevice, t.stream);
+        else memcpy(args[0].pdata, &bits, 8);
+        if (args[0].pnulls) {
+            if (is_device_ptr(args[0].pnulls)) cudaMemcpyAsync(args[0].pnulls, &nullword, 8, cudaMemcpyHostToDevice, t.stream);
+            else memcpy(args[0].pnulls, &nullword, 8);
+        }
+    }
+    int frc = st.finish();
+    return rc ? rc : frc;
+}
+
+}  // namespace mob

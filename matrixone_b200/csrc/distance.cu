@@ -1,0 +1,313 @@
+// distance.cu -- row-wise vector distances over MatrixOne varlena columns, behind XCall.
+//
+//   ids 0..3   (reference ids, cgo/mo.c:49-52): semantics of cgo/xcall.c:23-134 -- float diff, squares summed in
+//              double, optional sqrt; dim taken from the first cell of arg 1; rows null in the result bitmap skipped.
+//              This replaces cgo/cuda/mocl.cu:4-86 (one thread per row, uncoalesced, += into global memory).
+//   ids 100..109 (new): the Go metric functions of pkg/vectorindex/metric/distance_func.go as wrapped by
+//              pkg/vectorize/moarray/external.go:171-260 (what l2_distance / inner_product / cosine_distance /
+//              cosine_similarity evaluate per row).  BIT-EXACT: the accumulator has the element type and the
+//              8-way (cosine: 4-way) unrolled association of the Go source is reproduced operation by operation.
+//
+// Mapping: one warp per row.  Lane l computes the partial sums of chunks l, l+32, ... (a chunk = 8 consecutive
+// elements = 2 x 128-bit loads per operand, so a warp instruction reads 512 contiguous bytes of the row); the
+// serial "sum += chunk" chain of the Go loop is then replayed in chunk order with warp shuffles (every lane keeps
+// the same running sum).  3 KB rows stream at HBM rate: algorithmic bytes per row = 2 * dim * sizeof(T) (one side
+// const: dim * sizeof(T)) + 24 per varlena cell + 8 for the result.
+#include "common.cuh"
+#include <cstring>
+
+using namespace mob;
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr unsigned FULL = 0xffffffffu;
+
+enum Kind { K_XC_L2 = 0, K_XC_L2SQ, K_GO_L2, K_GO_L2SQ, K_GO_IP, K_GO_COSDIST, K_GO_COSSIM };
+constexpr unsigned ST_DIM = 1u, ST_AREA = 2u, ST_ZERO = 4u;
+
+struct Ref { const uint8_t *ptr; uint32_t len; bool ok; };
+
+// varlena decode, cgo/xcall.h:47-61 (== pkg/container/types/bytes.go:61-115)
+__device__ __forceinline__ Ref varlena_ref(const uint8_t *cells, uint64_t i, const uint8_t *area, uint64_t areaSz) {
+    const uint8_t *c = cells + 24 * i;
+    Ref r; r.ok = true;
+    const uint8_t b0 = c[0];
+    if (b0 <= MO_VARLENA_INLINE_SZ) { r.ptr = c + 1; r.len = b0; }
+    else {
+        uint32_t off, len;
+        memcpy(&off, c + 4, 4); memcpy(&len, c + 8, 4);
+        r.ptr = area + off; r.len = len;
+        if (!area || (uint64_t)off + len > areaSz) r.ok = false;
+    }
+    return r;
+}
+
+template <typename T, int N>
+__device__ __forceinline__ void load_elems(const uint8_t *p, T *out, bool aligned, bool stream) {
+    if (aligned) {
+#pragma unroll
+        for (int i = 0; i < (int)(N * sizeof(T)) / 16; i++) {
+            int4 v = stream ? ld_stream16(p + 16 * i) : __ldg(reinterpret_cast<const int4 *>(p + 16 * i));
+            memcpy(reinterpret_cast<char *>(out) + 16 * i, &v, 16);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            T v; uint8_t b[sizeof(T)];
+#pragma unroll
+            for (int k = 0; k < (int)sizeof(T); k++) b[k] = p[i * sizeof(T) + k];
+            memcpy(&v, b, sizeof(T)); out[i] = v;
+        }
+    }
+}
+template <typename T> __device__ __forceinline__ T load1(const uint8_t *p) {
+    T v; uint8_t b[sizeof(T)];
+#pragma unroll
+    for (int k = 0; k < (int)sizeof(T); k++) b[k] = p[k];
+    memcpy(&v, b, sizeof(T)); return v;
+}
+
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+
+// replay "sum = sum + c[l]" for l = 0..m-1 in lane order; all lanes end with the same sum
+template <typename T>
+__device__ __forceinline__ T chain(T sum, T c, int m) {
+    if (m == 32) {
+#pragma unroll
+        for (int l = 0; l < 32; l++) sum = add_rn(sum, __shfl_sync(FULL, c, l));
+    } else {
+        for (int l = 0; l < m; l++) sum = add_rn(sum, __shfl_sync(FULL, c, l));
+    }
+    return sum;
+}
+
+// L2DistanceSq, distance_func.go:59-95
+template <typename T>
+__device__ T go_l2sq(const uint8_t *p, const uint8_t *q, int dim, int lane, bool al, bool sp, bool sq) {
+    const int nch = dim >> 3;
+    T sum = 0;
+    for (int base = 0; base < nch; base += 32) {
+        const int c = base + lane;
+        T s = 0;
+        if (c < nch) {
+            T a[8], b[8], t[8];
+            load_elems<T, 8>(p + (size_t)c * 8 * sizeof(T), a, al, sp);
+            load_elems<T, 8>(q + (size_t)c * 8 * sizeof(T), b, al, sq);
+#pragma unroll
+            for (int j = 0; j < 8; j++) { T d = sub_rn(a[j], b[j]); t[j] = mul_rn(d, d); }
+            s = add_rn(add_rn(add_rn(add_rn(t[0], t[1]), add_rn(t[2], t[3])), add_rn(t[4], t[5])), add_rn(t[6], t[7]));
+        }
+        sum = chain(sum, s, min(32, nch - base));
+    }
+    for (int i = nch << 3; i < dim; i++) {  // remainder loop, distance_func.go:88-92
+        T d = sub_rn(load1<T>(p + (size_t)i * sizeof(T)), load1<T>(q + (size_t)i * sizeof(T)));
+        sum = add_rn(sum, mul_rn(d, d));
+    }
+    return sum;
+}
+
+// InnerProduct, distance_func.go:172-205 (returns -sum)
+template <typename T>
+__device__ T go_ip(const uint8_t *p, const uint8_t *q, int dim, int lane, bool al, bool sp, bool sq) {
+    const int nch = dim >> 3;
+    T sum = 0;
+    for (int base = 0; base < nch; base += 32) {
+        const int c = base + lane;
+        T s = 0;
+        if (c < nch) {
+            T a[8], b[8];
+            load_elems<T, 8>(p + (size_t)c * 8 * sizeof(T), a, al, sp);
+            load_elems<T, 8>(q + (size_t)c * 8 * sizeof(T), b, al, sq);
+            s = add_rn(mul_rn(a[0], b[0]), mul_rn(a[1], b[1]));
+#pragma unroll
+            for (int j = 2; j < 8; j++) s = add_rn(s, mul_rn(a[j], b[j]));
+        }
+        sum = chain(sum, s, min(32, nch - base));
+    }
+    for (int i = nch << 3; i < dim; i++)
+        sum = add_rn(sum, mul_rn(load1<T>(p + (size_t)i * sizeof(T)), load1<T>(q + (size_t)i * sizeof(T))));
+    return -sum;
+}
+
+// shared accumulation of CosineDistance / CosineSimilarity, distance_func.go:216-262
+template <typename T>
+__device__ void go_cos_parts(const uint8_t *p, const uint8_t *q, int dim, int lane, bool al, bool sp, bool sq, T &dp, T &n1, T &n2) {
+    const int nch = dim >> 2;
+    dp = 0; n1 = 0; n2 = 0;
+    for (int base = 0; base < nch; base += 32) {
+        const int c = base + lane;
+        T s0 = 0, s1 = 0, s2 = 0;
+        if (c < nch) {
+            T a[4], b[4];
+            if (sizeof(T) == 4) { load_elems<T, 4>(p + (size_t)c * 4 * sizeof(T), a, al, sp); load_elems<T, 4>(q + (size_t)c * 4 * sizeof(T), b, al, sq); }
+            else { load_elems<T, 4>(p + (size_t)c * 4 * sizeof(T), a, al, sp); load_elems<T, 4>(q + (size_t)c * 4 * sizeof(T), b, al, sq); }
+            s0 = add_rn(add_rn(add_rn(mul_rn(a[0], b[0]), mul_rn(a[1], b[1])), mul_rn(a[2], b[2])), mul_rn(a[3], b[3]));
+            s1 = add_rn(add_rn(add_rn(mul_rn(a[0], a[0]), mul_rn(a[1], a[1])), mul_rn(a[2], a[2])), mul_rn(a[3], a[3]));
+            s2 = add_rn(add_rn(add_rn(mul_rn(b[0], b[0]), mul_rn(b[1], b[1])), mul_rn(b[2], b[2])), mul_rn(b[3], b[3]));
+        }
+        const int m = min(32, nch - base);
+        dp = chain(dp, s0, m); n1 = chain(n1, s1, m); n2 = chain(n2, s2, m);
+    }
+    for (int i = nch << 2; i < dim; i++) {
+        T x = load1<T>(p + (size_t)i * sizeof(T)), y = load1<T>(q + (size_t)i * sizeof(T));
+        dp = add_rn(dp, mul_rn(x, y)); n1 = add_rn(n1, mul_rn(x, x)); n2 = add_rn(n2, mul_rn(y, y));
+    }
+}
+
+// xcall.c:55-75: float diff, (double)(diff*diff) accumulated in double
+template <typename T>
+__device__ double xc_l2sq(const uint8_t *p, const uint8_t *q, int dim, int lane, bool al, bool sp, bool sq) {
+    constexpr int V = 16 / sizeof(T);
+    double s = 0.0;
+    const int nv = dim / V;
+    for (int v = lane; v < nv; v += 32) {
+        T a[V], b[V];
+        load_elems<T, V>(p + (size_t)v * 16, a, al, sp);
+        load_elems<T, V>(q + (size_t)v * 16, b, al, sq);
+#pragma unroll
+        for (int j = 0; j < V; j++) { T d = sub_rn(a[j], b[j]); s = __dadd_rn(s, (double)mul_rn(d, d)); }
+    }
+    for (int i = nv * V + lane; i < dim; i += 32) {
+        T d = sub_rn(load1<T>(p + (size_t)i * sizeof(T)), load1<T>(q + (size_t)i * sizeof(T)));
+        s = __dadd_rn(s, (double)mul_rn(d, d));
+    }
+    return warp_sum_f64(s);
+}
+
+template <typename T, int KIND>
+__global__ void __launch_bounds__(kThreads)
+rowdist_kernel(double *__restrict__ res, const uint64_t *__restrict__ rnulls, uint64_t n,
+               const uint8_t *__restrict__ cells1, const uint8_t *__restrict__ area1, uint64_t area1Sz, bool const1,
+               const uint8_t *__restrict__ cells2, const uint8_t *__restrict__ area2, uint64_t area2Sz, bool const2,
+               unsigned *status) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t)kThreads + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * kThreads) >> 5;
+    int xc_dim = 0;
+    if (KIND == K_XC_L2 || KIND == K_XC_L2SQ) {  // dim = c1.len / sizeof(T) from the FIRST cell of arg 1, xcall.c:40,55
+        Ref r0 = varlena_ref(cells1, 0, area1, area1Sz);
+        xc_dim = r0.ok ? (int)(r0.len / sizeof(T)) : 0;
+    }
+    unsigned st = 0;
+    for (uint64_t i = warp; i < n; i += nwarps) {
+        if (bm_test(rnulls, i)) continue;
+        Ref a = varlena_ref(cells1, const1 ? 0 : i, area1, area1Sz);
+        Ref b = varlena_ref(cells2, const2 ? 0 : i, area2, area2Sz);
+        if (!a.ok || !b.ok) { st |= ST_AREA; continue; }
+        int dim;
+        if (KIND == K_XC_L2 || KIND == K_XC_L2SQ) {
+            dim = xc_dim;
+            if ((uint64_t)dim * sizeof(T) > a.len || (uint64_t)dim * sizeof(T) > b.len) { st |= ST_DIM; continue; }  // would read out of bounds
+        } else {
+            if (a.len != b.len) { st |= ST_DIM; continue; }  // moerr.NewArrayInvalidOpNoCtx, external.go:182-184
+            dim = (int)(a.len / sizeof(T));
+        }
+        const bool al = ((((uintptr_t)a.ptr) | ((uintptr_t)b.ptr)) & 15) == 0;
+        const bool sa = !const1, sb = !const2;  // const side is re-read by every row: keep it cached
+        double out;
+        if (KIND == K_XC_L2 || KIND == K_XC_L2SQ) {
+            double s = xc_l2sq<T>(a.ptr, b.ptr, dim, lane, al, sa, sb);
+            out = KIND == K_XC_L2 ? sqrt(s) : s;
+        } else if (KIND == K_GO_L2SQ) {
+            out = (double)go_l2sq<T>(a.ptr, b.ptr, dim, lane, al, sa, sb);
+        } else if (KIND == K_GO_L2) {
+            out = (double)(T)sqrt((double)go_l2sq<T>(a.ptr, b.ptr, dim, lane, al, sa, sb));  // distance_func.go:35-42
+        } else if (KIND == K_GO_IP) {
+            out = (double)go_ip<T>(a.ptr, b.ptr, dim, lane, al, sa, sb);
+        } else {
+            T dp, n1, n2;
+            go_cos_parts<T>(a.ptr, b.ptr, dim, lane, al, sa, sb, dp, n1, n2);
+            const double den = sqrt((double)n1) * sqrt((double)n2);
+            if (KIND == K_GO_COSDIST) {
+                if (dim == 0) out = 0.0;
+                else if (den == 0.0) out = (double)(T)1.0;        // distance_func.go:268-271
+                else {
+                    double sim = (double)dp / den;
+                    sim = sim > 1.0 ? 1.0 : (sim < -1.0 ? -1.0 : sim);
+                    out = (double)(T)(1.0 - sim);
+                }
+            } else {
+                if (dim == 0) out = 0.0;
+                else if (den == 0.0) { st |= ST_ZERO; continue; }   // "one of the vector is zero", distance_func.go:342-345
+                else {
+                    double sim = (double)dp / den;
+                    sim = sim > 1.0 ? 1.0 : (sim < -1.0 ? -1.0 : sim);
+                    double c = (double)(T)sim;
+                    const float f = (float)c;                        // moarray.CosineSimilarity snap, external.go:252-257
+                    if (f == 1.0f) c = 1.0; else if (f == -1.0f) c = -1.0;
+                    out = c;
+                }
+            }
+        }
+        if (lane == 0) res[i] = out;
+    }
+    st = __reduce_or_sync(FULL, st);
+    if (lane == 0 && st) atomicOr(status, st);
+}
+
+template <typename T, int KIND>
+int run_rowdist(mo_xcall_args_t *args, uint64_t len) {
+    ThreadCtx &t = tctx();
+    if (!t.ready) return MO_RC_INTERNAL_ERROR;
+    if (len == 0) return MO_RC_SUCCESS;
+    if (!args[0].pdata || args[0].dataSz < 8 * len) { set_error("distance: result vector shorter than len"); return MO_RC_INVALID_ARGUMENT; }
+    const bool c1 = args[1].dataSz == MO_VARLENA_SZ, c2 = args[2].dataSz == MO_VARLENA_SZ;   // const detection, xcall.c:38-39
+    if ((!c1 && args[1].dataSz < 24 * len) || (!c2 && args[2].dataSz < 24 * len)) { set_error("distance: argument vector shorter than len"); return MO_RC_INVALID_ARGUMENT; }
+    Stager st(t);
+    const uint8_t *cells1 = (const uint8_t *)st.in(args[1].pdata, args[1].dataSz);
+    const uint8_t *cells2 = (const uint8_t *)st.in(args[2].pdata, args[2].dataSz);
+    const uint8_t *area1 = (const uint8_t *)st.in(args[1].parea, args[1].areaSz);
+    const uint8_t *area2 = (const uint8_t *)st.in(args[2].parea, args[2].areaSz);
+    const uint64_t *rn = (const uint64_t *)st.in(args[0].pnulls, args[0].pnulls ? ((len + 63) / 64) * 8 : 0);
+    double *res = (double *)st.out(args[0].pdata, 8 * len, args[0].pnulls != nullptr);
+    unsigned *dstatus = (unsigned *)st.tmp(4);
+    if (st.failed) { st.finish(); return MO_RC_INTERNAL_ERROR; }
+    MOB_CUDA_TRY(cudaMemsetAsync(dstatus, 0, 4, t.stream));
+    uint64_t blocks = (len * 32 + kThreads - 1) / kThreads;
+    const uint64_t cap = (uint64_t)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    rowdist_kernel<T, KIND><<<(unsigned)blocks, kThreads, 0, t.stream>>>(res, rn, len, cells1, area1, args[1].areaSz, c1,
+                                                                         cells2, area2, args[2].areaSz, c2, dstatus);
+    MOB_LAUNCH_CHECK();
+    unsigned status = 0;
+    int rc = read_back(t, &status, dstatus, 4);
+    int frc = st.finish();
+    if (rc) return rc;
+    if (frc) return frc;
+    if (status & ST_AREA) { set_error("distance: varlena cell points outside its area"); return MO_RC_INVALID_ARGUMENT; }
+    if (status & ST_DIM) { set_error("distance: vector dimension not matched"); return MO_RC_INVALID_ARGUMENT; }
+    if (status & ST_ZERO) { set_error("cosine similarity: one of the vector is zero"); return MO_RC_INTERNAL_ERROR; }
+    return MO_RC_SUCCESS;
+}
+
+}  // namespace
+
+namespace mob {
+
+int xcall_rowdist(int64_t funcId, mo_xcall_args_t *args, uint64_t len) {
+    switch (funcId) {
+    case MO_XCALL_L2DISTANCE_F32: return run_rowdist<float, K_XC_L2>(args, len);
+    case MO_XCALL_L2DISTANCE_F64: return run_rowdist<double, K_XC_L2>(args, len);
+    case MO_XCALL_L2DISTANCE_SQ_F32: return run_rowdist<float, K_XC_L2SQ>(args, len);
+    case MO_XCALL_L2DISTANCE_SQ_F64: return run_rowdist<double, K_XC_L2SQ>(args, len);
+    case MO_XCALL_GO_L2_F32: return run_rowdist<float, K_GO_L2>(args, len);
+    case MO_XCALL_GO_L2_F64: return run_rowdist<double, K_GO_L2>(args, len);
+    case MO_XCALL_GO_L2SQ_F32: return run_rowdist<float, K_GO_L2SQ>(args, len);
+    case MO_XCALL_GO_L2SQ_F64: return run_rowdist<double, K_GO_L2SQ>(args, len);
+    case MO_XCALL_GO_IP_F32: return run_rowdist<float, K_GO_IP>(args, len);
+    case MO_XCALL_GO_IP_F64: return run_rowdist<double, K_GO_IP>(args, len);
+    case MO_XCALL_GO_COSDIST_F32: return run_rowdist<float, K_GO_COSDIST>(args, len);
+    case MO_XCALL_GO_COSDIST_F64: return run_rowdist<double, K_GO_COSDIST>(args, len);
+    case MO_XCALL_GO_COSSIM_F32: return run_rowdist<float, K_GO_COSSIM>(args, len);
+    case MO_XCALL_GO_COSSIM_F64: return run_rowdist<double, K_GO_COSSIM>(args, len);
+    }
+    return -1;
+}
+
+}  // namespace mob

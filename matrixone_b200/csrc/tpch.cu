@@ -1,0 +1,547 @@
+// tpch.cu -- fused scan -> filter -> project -> aggregate kernels for the two OLAP shapes BASELINE.json names.
+//
+// The reference runs these as an operator chain that materialises a vector per expression node and compacts every
+// column after each conjunct (table_scan -> filter -> projection -> group: pkg/sql/colexec/filter/filter.go:87-153,
+// pkg/sql/colexec/group/exec2.go:296-367, aggexec/sumavg2.go:133-199).  Here each shape is ONE pass over the
+// columns: every byte is read from HBM exactly once, nothing is written but a few hundred bytes of partials.
+//
+//   Q6  SUM(price*disc) WHERE date in [lo,hi) AND disc BETWEEN a AND b AND qty < c     28 B/row   (q6.sql:50-61)
+//   Q1  filter date <= cutoff, group by (returnflag, linestatus), 8 aggregates          38 B/row packed keys,
+//                                                                                        84 B/row varlena keys (q1.sql:1-21)
+//
+// Mapping: a "pair" is two consecutive rows.  Lane l of a warp owns pair (w*32 + l), so one warp instruction reads
+// 64 consecutive rows: 256 B of the int32 column (LDG.64/lane) and 512 B of each float64 column (LDG.128/lane) --
+// whole 32-byte sectors, nothing fetched twice.  kUnroll pairs are in flight per thread; grid = 148 x CTAs/SM
+// persistent CTAs, grid-stride.  Products are rounded exactly as the reference's separate multiply / add nodes do
+// (__dmul_rn/__dadd_rn, no FMA contraction), so only the summation ORDER differs from the serial Go loop.
+// Reduction: registers -> warp shuffles -> shared memory -> per-CTA record; the last CTA (atomicInc ticket) folds
+// the records in CTA-index order => bitwise run-to-run deterministic for a fixed grid.
+#include "common.cuh"
+#include <cstring>
+
+using namespace mob;
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// =========================================================================================================
+// Q6
+// =========================================================================================================
+struct Q6Rec { double sum; unsigned long long cnt; };
+
+template <int UNROLL, int CTAS>
+__global__ void __launch_bounds__(kThreads, CTAS)
+q6_kernel(const int32_t *__restrict__ sd, const double *__restrict__ disc, const double *__restrict__ qty,
+          const double *__restrict__ price, uint64_t n, mo_q6_params_t P, Q6Rec *__restrict__ partials,
+          Q6Rec *__restrict__ out, unsigned *ticket) {
+    const uint64_t npairs = n >> 1;
+    const uint64_t tid = blockIdx.x * (uint64_t)kThreads + threadIdx.x;
+    const uint64_t nthreads = (uint64_t)gridDim.x * kThreads;
+    double s0 = 0.0, s1 = 0.0;
+    unsigned cnt = 0;  // a thread sees < 2^32 rows
+
+    auto row = [&](int32_t d, double di, double q, double pr, double &s) {
+        bool ok = (d >= P.date_lo) & (d < P.date_hi) & (di >= P.disc_lo) & (di <= P.disc_hi) & (q < P.qty_hi);
+        double prod = __dmul_rn(pr, di);             // projection node l_extendedprice * l_discount
+        s = __dadd_rn(s, ok ? prod : 0.0);           // SUM node; +0.0 leaves s unchanged (s is never -0.0)
+        cnt += ok;
+    };
+
+    uint64_t p = tid;
+    for (; p + (UNROLL - 1) * nthreads < npairs; p += UNROLL * nthreads) {
+        int2 d[UNROLL]; int4 a[UNROLL], b[UNROLL], c[UNROLL];
+#pragma unroll
+        for (int k = 0; k < UNROLL; k++) {
+            const uint64_t q = p + k * nthreads;
+            d[k] = ld_stream8(sd + 2 * q);
+            a[k] = ld_stream16(disc + 2 * q);
+            b[k] = ld_stream16(qty + 2 * q);
+            c[k] = ld_stream16(price + 2 * q);
+        }
+#pragma unroll
+        for (int k = 0; k < UNROLL; k++) {
+            double di[2], qq[2], pr[2];
+            memcpy(di, &a[k], 16); memcpy(qq, &b[k], 16); memcpy(pr, &c[k], 16);
+            row(d[k].x, di[0], qq[0], pr[0], s0);
+            row(d[k].y, di[1], qq[1], pr[1], s1);
+        }
+    }
+    for (; p < npairs; p += nthreads) {
+        int2 d = ld_stream8(sd + 2 * p);
+        int4 a = ld_stream16(disc + 2 * p), b = ld_stream16(qty + 2 * p), c = ld_stream16(price + 2 * p);
+        double di[2], qq[2], pr[2];
+        memcpy(di, &a, 16); memcpy(qq, &b, 16); memcpy(pr, &c, 16);
+        row(d.x, di[0], qq[0], pr[0], s0);
+        row(d.y, di[1], qq[1], pr[1], s1);
+    }
+    if ((n & 1) && tid == 0) row(sd[n - 1], disc[n - 1], qty[n - 1], price[n - 1], s0);  // odd tail row
+
+    // ---- deterministic reduction
+    double s = __dadd_rn(s0, s1);
+    unsigned long long c64 = cnt;
+    s = warp_sum_f64(s);
+    c64 = warp_sum(c64);
+    __shared__ double ss[kThreads / 32];
+    __shared__ unsigned long long sc[kThreads / 32];
+    __shared__ bool last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { ss[warp] = s; sc[warp] = c64; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0; unsigned long long tc = 0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; w++) { t = __dadd_rn(t, ss[w]); tc += sc[w]; }
+        partials[blockIdx.x].sum = t; partials[blockIdx.x].cnt = tc;
+        __threadfence();
+        unsigned tk = atomicInc(ticket, gridDim.x - 1);
+        last = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        double t = 0.0; unsigned long long tc = 0;
+        for (unsigned bIdx = threadIdx.x; bIdx < gridDim.x; bIdx += kThreads) { t = __dadd_rn(t, partials[bIdx].sum); tc += partials[bIdx].cnt; }
+        t = warp_sum_f64(t); tc = warp_sum(tc);
+        __syncthreads();
+        if (lane == 0) { ss[warp] = t; sc[warp] = tc; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double f = 0.0; unsigned long long fc = 0;
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; w++) { f = __dadd_rn(f, ss[w]); fc += sc[w]; }
+            out->sum = f; out->cnt = fc;
+        }
+    }
+}
+
+// =========================================================================================================
+// Q1
+// =========================================================================================================
+constexpr int kQ1Vals = 5;  // sum_qty, sum_price, sum_disc_price, sum_charge, sum_disc
+struct Q1Slot { unsigned long long first_row; unsigned long long cnt; double v[kQ1Vals]; unsigned key; unsigned used; };
+struct Q1Rec { Q1Slot slot[MO_Q1_MAX_GROUPS]; unsigned overflow; unsigned pad; };
+constexpr unsigned kEmptyKey = 0xffffffffu;
+
+// KEYMODE 0: packed uint8 columns; 1: MatrixOne varlena cells (24 B, inline: bs[0]=len, bs[1..]=bytes; cgo/xcall.h:33-61)
+template <int G, int UNROLL, int CTAS, int KEYMODE>
+__global__ void __launch_bounds__(kThreads, CTAS)
+q1_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty, const double *__restrict__ price,
+          const double *__restrict__ disc, const double *__restrict__ tax, const uint8_t *__restrict__ rf,
+          const uint8_t *__restrict__ ls, uint64_t n, int32_t cutoff, Q1Rec *__restrict__ partials,
+          Q1Rec *__restrict__ out, unsigned *ticket) {
+    __shared__ unsigned dict[G];      // CTA-local key -> slot dictionary, slots handed out first-come
+    __shared__ unsigned s_overflow;
+    if (threadIdx.x < G) dict[threadIdx.x] = kEmptyKey;
+    if (threadIdx.x == 0) s_overflow = 0;
+    __syncthreads();
+
+    double acc[G][kQ1Vals];
+    unsigned cnt[G];
+    unsigned long long first[G];
+    unsigned dk[G];  // register copy of the dictionary
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        cnt[g] = 0; first[g] = ~0ull; dk[g] = kEmptyKey;
+#pragma unroll
+        for (int j = 0; j < kQ1Vals; j++) acc[g][j] = 0.0;
+    }
+
+    auto find_slot = [&](unsigned key) -> int {
+        int slot = -1;
+#pragma unroll
+        for (int g = 0; g < G; g++) if (dk[g] == key) slot = g;
+        if (slot >= 0) return slot;
+        // miss: claim or find the key in the shared dictionary, then refresh the register copy
+#pragma unroll 1
+        for (int g = 0; g < G; g++) {
+            unsigned prev = atomicCAS(&dict[g], kEmptyKey, key);
+            if (prev == kEmptyKey || prev == key) { slot = g; break; }
+        }
+#pragma unroll
+        for (int g = 0; g < G; g++) dk[g] = ((volatile unsigned *)dict)[g];
+        if (slot < 0) s_overflow = 1;
+        return slot;
+    };
+
+    auto row = [&](uint64_t r, int32_t d, double q, double pr, double di, double tx, unsigned key) {
+        if (d > cutoff) return;                       // l_shipdate <= cutoff
+        int slot = find_slot(key);
+        if (slot < 0) return;
+        double t1 = __dsub_rn(1.0, di);               // 1 - l_discount
+        double t2 = __dmul_rn(pr, t1);                // l_extendedprice * (1 - l_discount)
+        double t3 = __dadd_rn(1.0, tx);               // 1 + l_tax
+        double t4 = __dmul_rn(t2, t3);                // ... * (1 + l_tax)
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            const bool m = (slot == g);
+            acc[g][0] = __dadd_rn(acc[g][0], m ? q : 0.0);
+            acc[g][1] = __dadd_rn(acc[g][1], m ? pr : 0.0);
+            acc[g][2] = __dadd_rn(acc[g][2], m ? t2 : 0.0);
+            acc[g][3] = __dadd_rn(acc[g][3], m ? t4 : 0.0);
+            acc[g][4] = __dadd_rn(acc[g][4], m ? di : 0.0);
+            if (m && cnt[g] == 0) first[g] = r;   // a thread visits its rows in increasing order
+            cnt[g] += m;
+        }
+    };
+
+    auto load_keys = [&](uint64_t pair, unsigned &k0, unsigned &k1) {
+        if (KEYMODE == 0) {
+            unsigned short a = __ldg(reinterpret_cast<const unsigned short *>(rf) + pair);
+            unsigned short b = __ldg(reinterpret_cast<const unsigned short *>(ls) + pair);
+            k0 = (a & 0xffu) | ((b & 0xffu) << 8);
+            k1 = (a >> 8) | ((b >> 8) << 8);
+        } else {
+            // head 8 bytes of each 24-byte cell hold len + first chars; empty string (len 0) keys as 0
+            const uint64_t r0 = 2 * pair;
+            uint2 a0 = __ldg(reinterpret_cast<const uint2 *>(rf + 24 * r0)), a1 = __ldg(reinterpret_cast<const uint2 *>(rf + 24 * (r0 + 1)));
+            uint2 b0 = __ldg(reinterpret_cast<const uint2 *>(ls + 24 * r0)), b1 = __ldg(reinterpret_cast<const uint2 *>(ls + 24 * (r0 + 1)));
+            auto ch = [](uint2 h) -> unsigned { return (h.x & 0xffu) ? ((h.x >> 8) & 0xffu) : 0u; };
+            k0 = ch(a0) | (ch(b0) << 8);
+            k1 = ch(a1) | (ch(b1) << 8);
+        }
+    };
+
+    const uint64_t npairs = n >> 1;
+    const uint64_t tid = blockIdx.x * (uint64_t)kThreads + threadIdx.x;
+    const uint64_t nthreads = (uint64_t)gridDim.x * kThreads;
+    uint64_t p = tid;
+    for (; p + (UNROLL - 1) * nthreads < npairs; p += UNROLL * nthreads) {
+        int2 d[UNROLL]; int4 a[UNROLL], b[UNROLL], c[UNROLL], e[UNROLL]; unsigned k0[UNROLL], k1[UNROLL];
+#pragma unroll
+        for (int k = 0; k < UNROLL; k++) {
+            const uint64_t q = p + k * nthreads;
+            d[k] = ld_stream8(sd + 2 * q);
+            a[k] = ld_stream16(qty + 2 * q);
+            b[k] = ld_stream16(price + 2 * q);
+            c[k] = ld_stream16(disc + 2 * q);
+            e[k] = ld_stream16(tax + 2 * q);
+            load_keys(q, k0[k], k1[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < UNROLL; k++) {
+            const uint64_t q = p + k * nthreads;
+            double qq[2], pr[2], di[2], tx[2];
+            memcpy(qq, &a[k], 16); memcpy(pr, &b[k], 16); memcpy(di, &c[k], 16); memcpy(tx, &e[k], 16);
+            row(2 * q, d[k].x, qq[0], pr[0], di[0], tx[0], k0[k]);
+            row(2 * q + 1, d[k].y, qq[1], pr[1], di[1], tx[1], k1[k]);
+        }
+    }
+    for (; p < npairs; p += nthreads) {
+        int2 d = ld_stream8(sd + 2 * p);
+        int4 a = ld_stream16(qty + 2 * p), b = ld_stream16(price + 2 * p), c = ld_stream16(disc + 2 * p), e = ld_stream16(tax + 2 * p);
+        unsigned k0, k1; load_keys(p, k0, k1);
+        double qq[2], pr[2], di[2], tx[2];
+        memcpy(qq, &a, 16); memcpy(pr, &b, 16); memcpy(di, &c, 16); memcpy(tx, &e, 16);
+        row(2 * p, d.x, qq[0], pr[0], di[0], tx[0], k0);
+        row(2 * p + 1, d.y, qq[1], pr[1], di[1], tx[1], k1);
+    }
+    if ((n & 1) && tid == 0) {
+        const uint64_t r = n - 1;
+        unsigned key;
+        if (KEYMODE == 0) key = rf[r] | ((unsigned)ls[r] << 8);
+        else key = (rf[24 * r] ? rf[24 * r + 1] : 0u) | ((ls[24 * r] ? (unsigned)ls[24 * r + 1] : 0u) << 8);
+        row(r, sd[r], qty[r], price[r], disc[r], tax[r], key);
+    }
+    __syncthreads();  // dictionary final
+
+    // ---- CTA reduction.  Register slots are indexed by the CTA dictionary, identical for every thread of the CTA.
+    __shared__ double sv[kThreads / 32][G][kQ1Vals];
+    __shared__ unsigned long long scnt[kThreads / 32][G], sfirst[kThreads / 32][G];
+    __shared__ bool last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        unsigned long long c64 = cnt[g], f = first[g];
+        c64 = warp_sum(c64);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { unsigned long long of = __shfl_xor_sync(0xffffffffu, f, o); f = of < f ? of : f; }
+#pragma unroll
+        for (int j = 0; j < kQ1Vals; j++) {
+            double v = warp_sum_f64(acc[g][j]);
+            if (lane == 0) sv[warp][g][j] = v;
+        }
+        if (lane == 0) { scnt[warp][g] = c64; sfirst[warp][g] = f; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Q1Rec &R = partials[blockIdx.x];
+        for (int g = 0; g < G; g++) {
+            Q1Slot s; s.cnt = 0; s.first_row = ~0ull; s.key = dict[g]; s.used = dict[g] != kEmptyKey;
+            for (int j = 0; j < kQ1Vals; j++) s.v[j] = 0.0;
+            for (int w = 0; w < kThreads / 32; w++) {
+                s.cnt += scnt[w][g];
+                if (sfirst[w][g] < s.first_row) s.first_row = sfirst[w][g];
+                for (int j = 0; j < kQ1Vals; j++) s.v[j] = __dadd_rn(s.v[j], sv[w][g][j]);
+            }
+            R.slot[g] = s;
+        }
+        for (int g = G; g < MO_Q1_MAX_GROUPS; g++) { Q1Slot z; memset(&z, 0, sizeof z); z.key = kEmptyKey; R.slot[g] = z; }
+        R.overflow = s_overflow; R.pad = 0;
+        __threadfence();
+        unsigned tk = atomicInc(ticket, gridDim.x - 1);
+        last = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        // fold CTA records in CTA-index order (MergeGroup: re-hash partial keys + BatchMerge, mergeGroup.go:132-247)
+        __threadfence();
+        Q1Rec F; memset(&F, 0, sizeof F);
+        for (int g = 0; g < MO_Q1_MAX_GROUPS; g++) { F.slot[g].key = kEmptyKey; F.slot[g].first_row = ~0ull; }
+        for (unsigned bIdx = 0; bIdx < gridDim.x; bIdx++) {
+            const Q1Rec &R = partials[bIdx];
+            if (R.overflow) F.overflow = 1;
+            for (int g = 0; g < G; g++) {
+                const Q1Slot &s = R.slot[g];
+                if (!s.used || s.cnt == 0) continue;
+                int dst = -1;
+                for (int x = 0; x < MO_Q1_MAX_GROUPS; x++) {
+                    if (F.slot[x].key == s.key) { dst = x; break; }
+                    if (F.slot[x].key == kEmptyKey) { dst = x; F.slot[x].key = s.key; F.slot[x].used = 1; break; }
+                }
+                if (dst < 0) { F.overflow = 1; continue; }
+                Q1Slot &D = F.slot[dst];
+                D.cnt += s.cnt;
+                if (s.first_row < D.first_row) D.first_row = s.first_row;
+                for (int j = 0; j < kQ1Vals; j++) D.v[j] = __dadd_rn(D.v[j], s.v[j]);
+            }
+        }
+        *out = F;
+    }
+}
+
+void q1_finalize(const Q1Rec &F, mo_q1_result_t *res) {
+    memset(res, 0, sizeof *res);
+    int order[MO_Q1_MAX_GROUPS], ng = 0;
+    for (int g = 0; g < MO_Q1_MAX_GROUPS; g++) if (F.slot[g].used && F.slot[g].cnt) order[ng++] = g;
+    for (int i = 1; i < ng; i++)  // first-seen (row) order == the reference's group-id order
+        for (int j = i; j > 0 && F.slot[order[j]].first_row < F.slot[order[j - 1]].first_row; j--) { int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t; }
+    res->ngroups = ng;
+    for (int i = 0; i < ng; i++) {
+        const Q1Slot &s = F.slot[order[i]];
+        mo_q1_group_t &o = res->groups[i];
+        o.returnflag = (uint8_t)(s.key & 0xff); o.linestatus = (uint8_t)((s.key >> 8) & 0xff);
+        o.first_row = (int64_t)s.first_row;
+        o.sum_qty = s.v[0]; o.sum_base_price = s.v[1]; o.sum_disc_price = s.v[2]; o.sum_charge = s.v[3]; o.sum_disc = s.v[4];
+        o.count_order = (int64_t)s.cnt;
+        const double c = (double)s.cnt;   // avg = float64(sum)/float64(cnt), sumavg2.go:331
+        o.avg_qty = s.v[0] / c; o.avg_price = s.v[1] / c; o.avg_disc = s.v[4] / c;
+    }
+}
+
+int g_q6_variant = 0, g_q1_variant = 0;  // tuning knobs (MoB200_SetTuning)
+
+}  // namespace
+
+namespace mob {
+
+int tuning_set(const char *name, int value) {
+    if (!strcmp(name, "q6_variant")) { g_q6_variant = value; return 0; }
+    if (!strcmp(name, "q1_variant")) { g_q1_variant = value; return 0; }
+    return -1;
+}
+
+// chunk of rows processed per launch when inputs are staged from the host (bounds device scratch)
+static const uint64_t kHostChunkRows = 32ull << 20;
+
+static bool aligned_to(const void *p, uintptr_t a) { return (((uintptr_t)p) & (a - 1)) == 0; }
+
+static int launch_q6(ThreadCtx &t, const int32_t *sd, const double *disc, const double *qty, const double *price,
+                     uint64_t n, const mo_q6_params_t &P, Q6Rec *hrec) {
+    if (!aligned_to(sd, 8) || !aligned_to(disc, 16) || !aligned_to(qty, 16) || !aligned_to(price, 16)) {
+        set_error("q6: columns must be 16-byte aligned (int32 column 8-byte)"); return MO_RC_INVALID_ARGUMENT;
+    }
+    int variant = g_q6_variant;
+    int ctas = (variant == 1 || variant == 3) ? 2 : 4;
+    int grid = num_sms() * ctas;
+    uint64_t work = (n / 2 + kThreads - 1) / kThreads;
+    if ((uint64_t)grid > work) grid = work ? (int)work : 1;
+    Q6Rec *partials = (Q6Rec *)arena_alloc(t, sizeof(Q6Rec) * (size_t)(grid + 1));
+    if (!partials) return MO_RC_INTERNAL_ERROR;
+    Q6Rec *out = partials + grid;
+    switch (variant) {
+    case 1: q6_kernel<4, 2><<<grid, kThreads, 0, t.stream>>>(sd, disc, qty, price, n, P, partials, out, t.ctrl); break;
+    case 2: q6_kernel<2, 4><<<grid, kThreads, 0, t.stream>>>(sd, disc, qty, price, n, P, partials, out, t.ctrl); break;
+    case 3: q6_kernel<8, 2><<<grid, kThreads, 0, t.stream>>>(sd, disc, qty, price, n, P, partials, out, t.ctrl); break;
+    default: q6_kernel<4, 4><<<grid, kThreads, 0, t.stream>>>(sd, disc, qty, price, n, P, partials, out, t.ctrl); break;
+    }
+    MOB_LAUNCH_CHECK();
+    return read_back(t, hrec, out, sizeof(Q6Rec));
+}
+
+int xcall_q6(mo_xcall_args_t *args, uint64_t len) {
+    ThreadCtx &t = tctx();
+    if (!t.ready) return MO_RC_INTERNAL_ERROR;
+    if (!args[5].pdata || args[5].dataSz < sizeof(mo_q6_params_t)) { set_error("q6: params missing"); return MO_RC_INVALID_ARGUMENT; }
+    if (!args[0].pdata || args[0].dataSz < 8) { set_error("q6: result must hold 8 bytes"); return MO_RC_INVALID_ARGUMENT; }
+    if (args[1].dataSz < 4 * len || args[2].dataSz < 8 * len || args[3].dataSz < 8 * len || args[4].dataSz < 8 * len) {
+        set_error("q6: column shorter than len"); return MO_RC_INVALID_ARGUMENT;
+    }
+    for (int i = 1; i <= 4; i++) if (args[i].pnulls) { set_error("q6: nullable columns are not supported by the fused kernel"); return MO_RC_INVALID_ARGUMENT; }
+    mo_q6_params_t P;
+    if (is_device_ptr(args[5].pdata)) { int rc = read_back(t, &P, args[5].pdata, sizeof P); if (rc) return rc; }
+    else memcpy(&P, args[5].pdata, sizeof P);
+
+    const bool dev = is_device_ptr(args[1].pdata);
+    for (int i = 2; i <= 4; i++) if (is_device_ptr(args[i].pdata) != dev) { set_error("q6: columns must all be host or all device"); return MO_RC_INVALID_ARGUMENT; }
+
+    double sum = 0.0; unsigned long long cnt = 0; bool any = false;
+    int rc = MO_RC_SUCCESS;
+    if (dev || len == 0) {
+        if (len) {
+            Q6Rec r;
+            rc = launch_q6(t, (const int32_t *)args[1].pdata, (const double *)args[2].pdata, (const double *)args[3].pdata,
+                           (const double *)args[4].pdata, len, P, &r);
+            sum = r.sum; cnt = r.cnt; any = r.cnt != 0;
+        }
+        arena_reset(t);
+    } else {
+        // host-resident columns: stream block ranges through the arena; partial sums are merged in chunk order
+        // exactly like per-pipeline partials in MergeGroup (BatchMerge, sumavg2.go:222-236)
+        for (uint64_t r0 = 0; r0 < len && rc == MO_RC_SUCCESS; r0 += kHostChunkRows) {
+            uint64_t m = len - r0 < kHostChunkRows ? len - r0 : kHostChunkRows;
+            Stager st(t);
+            const int32_t *d_sd = (const int32_t *)st.in(args[1].pdata + 4 * r0, 4 * m);
+            const double *d_di = (const double *)st.in(args[2].pdata + 8 * r0, 8 * m);
+            const double *d_q = (const double *)st.in(args[3].pdata + 8 * r0, 8 * m);
+            const double *d_p = (const double *)st.in(args[4].pdata + 8 * r0, 8 * m);
+            if (st.failed) { st.finish(); return MO_RC_INTERNAL_ERROR; }
+            Q6Rec r;
+            rc = launch_q6(t, d_sd, d_di, d_q, d_p, m, P, &r);
+            if (rc == MO_RC_SUCCESS && r.cnt) { sum = any ? sum + r.sum : r.sum; any = true; cnt += r.cnt; }
+            int frc = st.finish();
+            if (!rc) rc = frc;
+        }
+    }
+    if (rc) return rc;
+    uint64_t nullword = any ? 0ull : 1ull;
+    int64_t c64 = (int64_t)cnt;
+    if (is_device_ptr(args[0].pdata)) {
+        MOB_CUDA_TRY(cudaMemcpyAsync(args[0].pdata, &sum, 8, cudaMemcpyHostToDevice, t.stream));
+        if (args[0].dataSz >= 16) MOB_CUDA_TRY(cudaMemcpyAsync(args[0].pdata + 8, &c64, 8, cudaMemcpyHostToDevice, t.stream));
+        MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));
+    } else {
+        memcpy(args[0].pdata, &sum, 8);
+        if (args[0].dataSz >= 16) memcpy(args[0].pdata + 8, &c64, 8);
+    }
+    if (args[0].pnulls) {
+        if (is_device_ptr(args[0].pnulls)) { MOB_CUDA_TRY(cudaMemcpyAsync(args[0].pnulls, &nullword, 8, cudaMemcpyHostToDevice, t.stream)); MOB_CUDA_TRY(cudaStreamSynchronize(t.stream)); }
+        else memcpy(args[0].pnulls, &nullword, 8);
+    }
+    return MO_RC_SUCCESS;
+}
+
+template <int KEYMODE>
+static int launch_q1(ThreadCtx &t, const int32_t *sd, const double *qty, const double *price, const double *disc, const double *tax,
+                     const uint8_t *rf, const uint8_t *ls, uint64_t n, int32_t cutoff, Q1Rec *hrec) {
+    if (!aligned_to(sd, 8) || !aligned_to(qty, 16) || !aligned_to(price, 16) || !aligned_to(disc, 16) || !aligned_to(tax, 16) ||
+        !aligned_to(rf, KEYMODE ? 8 : 2) || !aligned_to(ls, KEYMODE ? 8 : 2)) {
+        set_error("q1: columns must be 16-byte aligned (int32 column 8-byte, key columns 2/8-byte)"); return MO_RC_INVALID_ARGUMENT;
+    }
+    for (int attempt = 0; attempt < 2; attempt++) {
+        const bool wide = attempt == 1 || g_q1_variant == 2;
+        int ctas = 2;
+        int grid = num_sms() * ctas;
+        uint64_t work = (n / 2 + kThreads - 1) / kThreads;
+        if ((uint64_t)grid > work) grid = work ? (int)work : 1;
+        Q1Rec *partials = (Q1Rec *)arena_alloc(t, sizeof(Q1Rec) * (size_t)(grid + 1));
+        if (!partials) return MO_RC_INTERNAL_ERROR;
+        Q1Rec *out = partials + grid;
+        if (!wide) {
+            if (g_q1_variant == 1) q1_kernel<4, 4, 2, KEYMODE><<<grid, kThreads, 0, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl);
+            else q1_kernel<4, 2, 2, KEYMODE><<<grid, kThreads, 0, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl);
+        } else {
+            q1_kernel<8, 2, 2, KEYMODE><<<grid, kThreads, 0, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl);
+        }
+        MOB_LAUNCH_CHECK();
+        int rc = read_back(t, hrec, out, sizeof(Q1Rec));
+        if (rc) return rc;
+        if (!hrec->overflow) return MO_RC_SUCCESS;
+        if (wide) break;  // more than MO_Q1_MAX_GROUPS distinct keys
+    }
+    set_error("q1: more than %d distinct group keys; the fused small-cardinality kernel does not apply", MO_Q1_MAX_GROUPS);
+    return MO_RC_INVALID_ARGUMENT;
+}
+
+static void q1_merge_rec(Q1Rec &F, const Q1Rec &R, bool &first) {
+    if (first) { F = R; first = false; return; }
+    for (int g = 0; g < MO_Q1_MAX_GROUPS; g++) {
+        const Q1Slot &s = R.slot[g];
+        if (!s.used || s.cnt == 0) continue;
+        int dst = -1;
+        for (int x = 0; x < MO_Q1_MAX_GROUPS; x++) {
+            if (F.slot[x].used && F.slot[x].key == s.key) { dst = x; break; }
+            if (!F.slot[x].used || F.slot[x].key == kEmptyKey) { dst = x; F.slot[x].key = s.key; F.slot[x].used = 1; F.slot[x].cnt = 0; F.slot[x].first_row = ~0ull; for (int j = 0; j < kQ1Vals; j++) F.slot[x].v[j] = 0; break; }
+        }
+        if (dst < 0) { F.overflow = 1; continue; }
+        Q1Slot &D = F.slot[dst];
+        D.cnt += s.cnt;
+        if (s.first_row < D.first_row) D.first_row = s.first_row;
+        for (int j = 0; j < kQ1Vals; j++) D.v[j] = D.v[j] + s.v[j];
+    }
+}
+
+int xcall_q1(mo_xcall_args_t *args, uint64_t len) {
+    ThreadCtx &t = tctx();
+    if (!t.ready) return MO_RC_INTERNAL_ERROR;
+    if (!args[0].pdata || args[0].dataSz < sizeof(mo_q1_result_t)) { set_error("q1: result buffer too small"); return MO_RC_INVALID_ARGUMENT; }
+    if (!args[8].pdata || args[8].dataSz < 4) { set_error("q1: cutoff param missing"); return MO_RC_INVALID_ARGUMENT; }
+    if (args[1].dataSz < 4 * len) { set_error("q1: shipdate shorter than len"); return MO_RC_INVALID_ARGUMENT; }
+    for (int i = 2; i <= 5; i++) if (args[i].dataSz < 8 * len) { set_error("q1: column %d shorter than len", i); return MO_RC_INVALID_ARGUMENT; }
+    for (int i = 1; i <= 7; i++) if (args[i].pnulls) { set_error("q1: nullable columns are not supported by the fused kernel"); return MO_RC_INVALID_ARGUMENT; }
+    int keymode;
+    if (args[6].dataSz == len && args[7].dataSz == len) keymode = 0;
+    else if (args[6].dataSz == 24 * len && args[7].dataSz == 24 * len) keymode = 1;
+    else { set_error("q1: key columns must be packed uint8 (len bytes) or varlena cells (24*len bytes)"); return MO_RC_INVALID_ARGUMENT; }
+    int32_t cutoff;
+    if (is_device_ptr(args[8].pdata)) { int rc = read_back(t, &cutoff, args[8].pdata, 4); if (rc) return rc; }
+    else memcpy(&cutoff, args[8].pdata, 4);
+    const bool dev = is_device_ptr(args[1].pdata);
+    for (int i = 2; i <= 7; i++) if (is_device_ptr(args[i].pdata) != dev) { set_error("q1: columns must all be host or all device"); return MO_RC_INVALID_ARGUMENT; }
+    const uint64_t ksz = keymode ? 24 : 1;
+
+    Q1Rec F; memset(&F, 0, sizeof F); bool first = true; int rc = MO_RC_SUCCESS;
+    for (int g = 0; g < MO_Q1_MAX_GROUPS; g++) F.slot[g].key = kEmptyKey;
+    if (dev || len == 0) {
+        if (len) {
+            Q1Rec R;
+            rc = keymode ? launch_q1<1>(t, (const int32_t *)args[1].pdata, (const double *)args[2].pdata, (const double *)args[3].pdata, (const double *)args[4].pdata, (const double *)args[5].pdata, args[6].pdata, args[7].pdata, len, cutoff, &R)
+                         : launch_q1<0>(t, (const int32_t *)args[1].pdata, (const double *)args[2].pdata, (const double *)args[3].pdata, (const double *)args[4].pdata, (const double *)args[5].pdata, args[6].pdata, args[7].pdata, len, cutoff, &R);
+            if (!rc) q1_merge_rec(F, R, first);
+        }
+        arena_reset(t);
+    } else {
+        for (uint64_t r0 = 0; r0 < len && rc == MO_RC_SUCCESS; r0 += kHostChunkRows) {
+            uint64_t m = len - r0 < kHostChunkRows ? len - r0 : kHostChunkRows;
+            Stager st(t);
+            const int32_t *d_sd = (const int32_t *)st.in(args[1].pdata + 4 * r0, 4 * m);
+            const double *d_q = (const double *)st.in(args[2].pdata + 8 * r0, 8 * m);
+            const double *d_p = (const double *)st.in(args[3].pdata + 8 * r0, 8 * m);
+            const double *d_d = (const double *)st.in(args[4].pdata + 8 * r0, 8 * m);
+            const double *d_t = (const double *)st.in(args[5].pdata + 8 * r0, 8 * m);
+            const uint8_t *d_rf = (const uint8_t *)st.in(args[6].pdata + ksz * r0, ksz * m);
+            const uint8_t *d_ls = (const uint8_t *)st.in(args[7].pdata + ksz * r0, ksz * m);
+            if (st.failed) { st.finish(); return MO_RC_INTERNAL_ERROR; }
+            Q1Rec R;
+            rc = keymode ? launch_q1<1>(t, d_sd, d_q, d_p, d_d, d_t, d_rf, d_ls, m, cutoff, &R)
+                         : launch_q1<0>(t, d_sd, d_q, d_p, d_d, d_t, d_rf, d_ls, m, cutoff, &R);
+            if (!rc) {
+                for (int g = 0; g < MO_Q1_MAX_GROUPS; g++) if (R.slot[g].used && R.slot[g].cnt) R.slot[g].first_row += r0;
+                q1_merge_rec(F, R, first);
+            }
+            int frc = st.finish();
+            if (!rc) rc = frc;
+        }
+    }
+    if (rc) return rc;
+    if (F.overflow) { set_error("q1: too many groups"); return MO_RC_INVALID_ARGUMENT; }
+    mo_q1_result_t res;
+    q1_finalize(F, &res);
+    if (is_device_ptr(args[0].pdata)) {
+        MOB_CUDA_TRY(cudaMemcpyAsync(args[0].pdata, &res, sizeof res, cudaMemcpyHostToDevice, t.stream));
+        MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));
+    } else memcpy(args[0].pdata, &res, sizeof res);
+    return MO_RC_SUCCESS;
+}
+
+}  // namespace mob

@@ -1,0 +1,213 @@
+"""Reference-facing operator calls over the C-ABI (what the Go side would do through cgo, written in Python).
+
+Each function only marshals arguments into mo_xcall_args_t blocks (Vector.FillRawPtrLen layout) and calls XCall /
+the mo.h entry points of libmo_b200.so.  Inputs may be numpy arrays (host path: the library stages them) or
+DeviceBuffer objects (resident path).  Names follow the reference:
+
+  q6_filter_sum / q1_group_agg     the fused TableScan->Filter->Projection->Group pipelines of TPC-H Q6 / Q1
+  agg_sum / agg_count / agg_min / agg_max / agg_avg      aggexec sumAvgExec / countColumnExec / minMaxExecFixed (H0)
+  BruteForceIndex                  brute_force.NewBruteForceIndex / .Search / .Destroy (brute_force.go:65-84,248-341)
+  IvfflatSearchIndex               ivfflat.IvfflatSearchIndex.Search (ivfflat/search.go:509-630)
+  topk_merge                       MergeTop / hnsw sub-index merge
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .vector import DeviceBuffer, Vector, xcall
+
+
+def _vec(x, length=None, itemsize=None):
+    """numpy array / DeviceBuffer / (DeviceBuffer, nbytes) -> Vector"""
+    if isinstance(x, Vector):
+        return x
+    if isinstance(x, DeviceBuffer):
+        return Vector(data_ptr=x.ptr, data_nbytes=x.nbytes, length=length)
+    a = np.ascontiguousarray(x)
+    return Vector(data=a, length=length if length is not None else a.shape[0])
+
+
+def _params_vec(struct):
+    buf = np.frombuffer(bytes(struct), dtype=np.uint8).copy()
+    return Vector(data=buf, length=1, const=True)
+
+
+# ------------------------------------------------------------------------------------------------ aggregates
+def _agg(op, T, col, nulls=None, length=None):
+    n = length if length is not None else (col.nbytes // np.dtype(capi.NP_OF_T[T]).itemsize if isinstance(col, DeviceBuffer) else len(col))
+    res = np.zeros(1, dtype=np.uint64)
+    rn = np.zeros(1, dtype=np.uint64)
+    rv = Vector(data=res, nulls=rn, length=1)
+    cv = _vec(col, n)
+    if nulls is not None:
+        if isinstance(nulls, DeviceBuffer):
+            cv.nulls_ptr = nulls.ptr
+        else:
+            cv.nulls = np.ascontiguousarray(nulls, dtype=np.uint64)
+    cv.length = n
+    rc, msg = xcall(capi.XCALL_AGG(op, T), [rv, cv], n, raise_on_error=False)
+    if rc not in (0, capi.RC_OUT_OF_RANGE):
+        raise capi.MoError(rc, msg)
+    return rc, res, bool(rv.nulls[0] & np.uint64(1))
+
+
+def agg_sum(T, col, nulls=None, length=None):
+    """SUM(col): returns (rc, value, is_null); value int64 / uint64 / float64 per SumReturnType (sumavg2.go:69-87)."""
+    rc, res, isnull = _agg(capi.AGG_SUM, T, col, nulls, length)
+    if T in (capi.T_FLOAT32, capi.T_FLOAT64):
+        v = res.view(np.float64)[0]
+    elif capi.T_UINT8 <= T <= capi.T_UINT64:
+        v = int(res[0])
+    else:
+        v = int(res.view(np.int64)[0])
+    return rc, v, isnull
+
+
+def agg_avg(T, col, nulls=None, length=None):
+    rc, res, isnull = _agg(capi.AGG_AVG, T, col, nulls, length)
+    return rc, float(res.view(np.float64)[0]), isnull
+
+
+def agg_count(T, col, nulls=None, length=None):
+    rc, res, _ = _agg(capi.AGG_COUNT, T, col, nulls, length)
+    return int(res.view(np.int64)[0])
+
+
+def _minmax(op, T, col, nulls, length):
+    rc, res, isnull = _agg(op, T, col, nulls, length)
+    dt = np.dtype(capi.NP_OF_T[T])
+    return res.view(np.uint8)[:dt.itemsize].view(dt)[0], isnull
+
+
+def agg_min(T, col, nulls=None, length=None):
+    return _minmax(capi.AGG_MIN, T, col, nulls, length)
+
+
+def agg_max(T, col, nulls=None, length=None):
+    return _minmax(capi.AGG_MAX, T, col, nulls, length)
+
+
+# ------------------------------------------------------------------------------------------------ TPC-H shapes
+def q6_filter_sum(shipdate, discount, quantity, extendedprice, n, date_lo, date_hi, disc_lo, disc_hi, qty_hi):
+    """SUM(l_extendedprice*l_discount) WHERE ... (q6.sql).  Returns (sum, qualifying_rows, is_null)."""
+    res = np.zeros(2, dtype=np.float64)
+    rn = np.zeros(1, dtype=np.uint64)
+    rv = Vector(data=res, nulls=rn, length=1)
+    p = capi.Q6Params(date_lo, date_hi, disc_lo, disc_hi, qty_hi)
+    xcall(capi.XCALL_Q6_FILTER_SUM, [rv, _vec(shipdate, n), _vec(discount, n), _vec(quantity, n), _vec(extendedprice, n), _params_vec(p)], n)
+    return float(res[0]), int(res.view(np.int64)[1]), bool(rv.nulls[0] & np.uint64(1))
+
+
+def q1_group_agg(shipdate, quantity, extendedprice, discount, tax, returnflag, linestatus, n, cutoff):
+    """TPC-H Q1 grouped aggregates (q1.sql).  returnflag/linestatus: packed uint8 columns or varlena cell buffers.
+    Returns a list of dicts in first-seen group order."""
+    res = np.zeros(C.sizeof(capi.Q1Result), dtype=np.uint8)
+    rv = Vector(data=res, length=1)
+    cut = Vector(data=np.asarray([cutoff], dtype=np.int32), length=1, const=True)
+    xcall(capi.XCALL_Q1_GROUP_AGG, [rv, _vec(shipdate, n), _vec(quantity, n), _vec(extendedprice, n), _vec(discount, n), _vec(tax, n),
+                                     _vec(returnflag, n), _vec(linestatus, n), cut], n)
+    r = capi.Q1Result.from_buffer_copy(res.tobytes())
+    out = []
+    for g in range(r.ngroups):
+        s = r.groups[g]
+        out.append({k: getattr(s, k) for k in ("returnflag", "linestatus", "first_row", "sum_qty", "sum_base_price", "sum_disc_price",
+                                               "sum_charge", "avg_qty", "avg_price", "avg_disc", "sum_disc", "count_order")})
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ vector search
+def _search_params(n, dim, nq, k, metric, nprobe=0, sqrt_out=0, nlist=0, key_base=0):
+    return capi.SearchParams(n, dim, nq, k, metric, nprobe, sqrt_out, nlist, key_base)
+
+
+class BruteForceIndex:
+    """brute_force.GoBruteForceIndex: NewBruteForceIndex(dataset, dim, metric) keeps the dataset RESIDENT in HBM
+    (the reference keeps it in C-malloc memory, brute_force.go:104-123); Search returns (keys int64[nq*limit],
+    distances float64[nq*limit]) row-major, ascending, keys = row ordinals (+ key_base)."""
+
+    def __init__(self, dataset, dim, metric=capi.METRIC_L2, key_base=0, lib=None):
+        self.lib = lib or capi.load_library()
+        self.dim, self.metric, self.key_base = int(dim), int(metric), int(key_base)
+        if isinstance(dataset, DeviceBuffer):
+            self.buf, self.owned = dataset, False
+            self.n = dataset.nbytes // (4 * self.dim)
+        else:
+            ds = np.ascontiguousarray(dataset, dtype=np.float32)
+            self.n = ds.shape[0]
+            self.buf, self.owned = DeviceBuffer.from_numpy(ds, self.lib), True
+
+    def search(self, queries, limit, out_device=False):
+        if isinstance(queries, DeviceBuffer):
+            nq = queries.nbytes // (4 * self.dim)
+            qv = Vector(data_ptr=queries.ptr, data_nbytes=queries.nbytes, length=nq)
+        else:
+            q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dim)
+            nq = q.shape[0]
+            qv = Vector(data=q.reshape(-1), length=nq)
+        if limit == 0 or nq == 0:
+            return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.float64)
+        keys = np.zeros(nq * limit, dtype=np.int64)
+        dists = np.zeros(nq * limit, dtype=np.float64)
+        p = _search_params(self.n, self.dim, nq, limit, self.metric, key_base=self.key_base)
+        dv = Vector(data_ptr=self.buf.ptr, data_nbytes=self.n * self.dim * 4, length=self.n)
+        xcall(capi.XCALL_BRUTEFORCE_TOPK_F32, [Vector(data=keys, length=nq), Vector(data=dists, length=nq), dv, qv, _params_vec(p)], nq)
+        return keys, dists
+
+    def destroy(self):
+        if self.owned and self.buf is not None:
+            self.buf.free()
+        self.buf = None
+
+
+class IvfflatSearchIndex:
+    """ivfflat.IvfflatSearchIndex: centroids + list-ordered entries resident in HBM.  build() takes the entry matrix
+    and its list assignment (what the index tables hold) and lays the lists out contiguously."""
+
+    def __init__(self, data, assign, centroids, metric=capi.METRIC_L2, lib=None):
+        self.lib = lib or capi.load_library()
+        data = np.ascontiguousarray(data, dtype=np.float32)
+        centroids = np.ascontiguousarray(centroids, dtype=np.float32)
+        self.n, self.dim = data.shape
+        self.nlist = centroids.shape[0]
+        self.metric = int(metric)
+        order = np.argsort(assign, kind="stable")   # stable: rows of a list stay in table order
+        counts = np.bincount(assign, minlength=self.nlist)
+        self.offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        self.row_ids = order.astype(np.int64)
+        self.d_data = DeviceBuffer.from_numpy(data[order], self.lib)
+        self.d_cent = DeviceBuffer.from_numpy(centroids, self.lib)
+        self.d_off = DeviceBuffer.from_numpy(self.offsets, self.lib)
+        self.d_ids = DeviceBuffer.from_numpy(self.row_ids, self.lib)
+
+    def search(self, queries, limit, nprobe, sqrt_out=False):
+        q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dim)
+        nq = q.shape[0]
+        keys = np.zeros(nq * limit, dtype=np.int64)
+        dists = np.zeros(nq * limit, dtype=np.float64)
+        p = _search_params(self.n, self.dim, nq, limit, self.metric, nprobe=nprobe, sqrt_out=int(sqrt_out), nlist=self.nlist)
+        xcall(capi.XCALL_IVF_TOPK_F32, [
+            Vector(data=keys, length=nq), Vector(data=dists, length=nq),
+            Vector(data_ptr=self.d_data.ptr, data_nbytes=self.d_data.nbytes, length=self.n),
+            Vector(data=q.reshape(-1), length=nq), _params_vec(p),
+            Vector(data_ptr=self.d_cent.ptr, data_nbytes=self.d_cent.nbytes, length=self.nlist),
+            Vector(data_ptr=self.d_off.ptr, data_nbytes=self.d_off.nbytes, length=self.nlist + 1),
+            Vector(data_ptr=self.d_ids.ptr, data_nbytes=self.d_ids.nbytes, length=self.n)], nq)
+        return keys, dists
+
+    def destroy(self):
+        for b in (self.d_data, self.d_cent, self.d_off, self.d_ids):
+            b.free()
+
+
+def topk_merge(keys_shards, dists_shards, nq, k):
+    """merge [nshards, nq, k] per-shard results (final keys, float64 distances) into the global top-k."""
+    ks = np.ascontiguousarray(keys_shards, dtype=np.int64).reshape(-1)
+    ds = np.ascontiguousarray(dists_shards, dtype=np.float64).reshape(-1)
+    nsh = ks.shape[0] // (nq * k)
+    keys = np.zeros(nq * k, dtype=np.int64)
+    dists = np.zeros(nq * k, dtype=np.float64)
+    p = _search_params(nsh, 0, nq, k, 0)
+    xcall(capi.XCALL_TOPK_MERGE, [Vector(data=keys, length=nq), Vector(data=dists, length=nq), Vector(data=ks, length=nq),
+                                  Vector(data=ds, length=nq), _params_vec(p)], nq)
+    return keys, dists
