@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""bench.py -- the measurement contract.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload q6|q1|sum|bruteforce]
+
+Default workload = BASELINE.json configs[1]: TPC-H Q6 (3-predicate filter + SUM, fp64) over SF100 synthetic lineitem
+columns (600 037 902 rows, 28 B/row = 16.8 GB) on one B200.  A "step" is one pass of the fused scan->filter->agg over
+the rank's columns (+ the NCCL exchange of partial aggregates when N > 1).  One JSON line is printed by rank 0.
+
+  value        rows/s, whole job, columns RESIDENT in HBM when the timed region starts (CUDA events, max over ranks)
+  e2e          the same metric through the C-ABI call with HOST (pinned) column buffers: H2D copies inside the timed region
+  roofline     algorithmic bytes per launch / CUDA-event duration of the dominant kernel, against MEASURED_PEAKS.json
+  cpu_baseline the oracle port (C restatement of the Go operator chain) on the host cores, bounded sample
+  --impl reference   times that CPU implementation alone (rank 0), same metric / config / unit
+
+Multi-GPU: weak scaling -- every rank owns an SF100-sized, disjoint row range of an N x SF100 table (block ranges, the
+reference's buildScanParallelRun split); partial (sum, count) records are exchanged with NCCL all_gather and merged.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SF100_ROWS = 600_037_902
+WORKLOADS = {
+    "q6": dict(name="tpch_q6_sf100_fp64", metric="scan+filter+agg rows/sec (TPC-H Q6, fp64)", bytes_per_row=28.0, rows=SF100_ROWS),
+    "q1": dict(name="tpch_q1_sf100_fp64_packed_keys", metric="scan+filter+group-agg rows/sec (TPC-H Q1, fp64)", bytes_per_row=38.0, rows=SF100_ROWS),
+    "sum": dict(name="int64_sum_10m_rows", metric="int64 SUM rows/sec", bytes_per_row=8.0, rows=10_000_000),
+    "bruteforce": dict(name="bruteforce_l2_top10_1Mx768_10k_queries", metric="ANN top-k qps (768-d, brute-force L2 top-10)", bytes_per_row=None, rows=1_000_000),
+}
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    """nvidia-smi clocks during the timed region (B200_PROFILING.md recipe)"""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# =====================================================================================================================
+# CPU reference arm / cpu_baseline: the oracle port on the host cores
+# =====================================================================================================================
+def cpu_reference(workload, sample_rows, steps, warmup, threads):
+    import oracle_lib as O
+    from matrixone_b200 import datagen
+    if workload == "q6":
+        cols = datagen.lineitem(10, 0, sample_rows)
+        P = datagen.q6_params()
+        fn = lambda: O.q6(cols, sample_rows, P, nthreads=threads)
+    elif workload == "q1":
+        cols = datagen.lineitem(10, 0, sample_rows)
+        fn = lambda: O.q1(cols, sample_rows, datagen.Q1_CUTOFF, nthreads=threads)
+    elif workload == "sum":
+        v, _ = datagen.int64_column(1, 0, sample_rows)
+        s = np.zeros(1, dtype=np.int64); nul = np.zeros(1, dtype=np.uint8)
+        fn = lambda: O.go().og_sum_int64_mt(O.p(v), None, sample_rows, threads, O.p(s), O.p(nul))
+    else:
+        raise SystemExit("cpu reference for workload %s: use --workload q6|q1|sum" % workload)
+    for _ in range(warmup):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    dt = time.perf_counter() - t0
+    return sample_rows * steps / dt, dt / steps
+
+
+def run_reference_arm(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    wl = WORKLOADS[args.workload]
+    threads = os.cpu_count() or 1
+    sample = min(wl["rows"], 1 << 25)
+    steps = max(1, args.steps)
+    warmup = max(1, min(args.warmup, 2))
+    value, sec_per_step = cpu_reference(args.workload, sample, steps, warmup, threads)
+    line = {
+        "impl": "reference", "metric": wl["metric"], "value": value, "unit": "rows/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if args.workload != "sum" else "int64",
+        "data": "synthetic", "config": {"workload": wl["name"], "rows_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": "rows/s", "cores": threads, "kind": "port",
+                         "sample": "first %d rows of the workload per step; oracle/oracle_go.c operator chain (filter conjunct by conjunct + Shrink, projection, aggexec fill) on %d pthreads over 8192-row blocks" % (sample, threads)},
+        "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# =====================================================================================================================
+# our arm
+# =====================================================================================================================
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="q6", choices=sorted(WORKLOADS))
+    ap.add_argument("--rows", type=int, default=0, help="override rows per GPU (testing only; the default is the BASELINE config)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--queries", type=int, default=10_000)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    os.environ.setdefault("MO_B200_DEVICE", str(local))
+    from matrixone_b200 import capi, datagen, ops
+    from matrixone_b200.vector import DeviceBuffer, PinnedArray, Vector, xcall
+    lib = capi.load_library()
+    capi.check(lib.MoB200_Init(local), lib)
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier_sync():
+        capi.check(lib.MoB200_Sync(), lib)
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    wl = WORKLOADS[args.workload]
+    n = args.rows or wl["rows"]
+    W = max(3, args.warmup)
+    K = max(1, args.steps)
+    row0 = rank * n                      # this rank's disjoint block range of the N x SF100 table
+    result = {}
+
+    # ---------------------------------------------------------------------------------------------- workload set-up
+    if args.workload in ("q6", "q1"):
+        names = ["shipdate", "quantity", "extendedprice", "discount"] + (["tax", "returnflag", "linestatus"] if args.workload == "q1" else [])
+        size = {"shipdate": 4, "returnflag": 1, "linestatus": 1}
+        bufs = {k: DeviceBuffer(size.get(k, 8) * n, lib) for k in names}
+        ptr = lambda k: bufs[k].ptr if k in bufs else None
+        capi.check(lib.MoB200_GenLineitem(10, row0, n, ptr("shipdate"), ptr("quantity"), ptr("extendedprice"), ptr("discount"), ptr("tax"),
+                                          ptr("returnflag"), ptr("linestatus")), lib)
+        P = datagen.q6_params()
+        if args.workload == "q6":
+            def step(cols=bufs):
+                return ops.q6_filter_sum(cols["shipdate"], cols["discount"], cols["quantity"], cols["extendedprice"], n, *P)
+            rec_bytes = 16
+            def pack(res):
+                return np.asarray([res[0]], dtype=np.float64).tobytes() + np.asarray([res[1]], dtype=np.int64).tobytes()
+        else:
+            def step(cols=bufs):
+                return ops.q1_group_agg(cols["shipdate"], cols["quantity"], cols["extendedprice"], cols["discount"], cols["tax"],
+                                        cols["returnflag"], cols["linestatus"], n, datagen.Q1_CUTOFF)
+            rec_bytes = 8 * 64
+            def pack(res):
+                out = np.zeros(64, dtype=np.float64)
+                for i, g in enumerate(res[:8]):
+                    out[i * 8:(i + 1) * 8] = [g["returnflag"] + 256 * g["linestatus"], g["sum_qty"], g["sum_base_price"], g["sum_disc_price"],
+                                              g["sum_charge"], g["sum_disc"], g["count_order"], g["first_row"]]
+                return out.tobytes()
+        units = n
+        unit_name = "rows/s"
+        alg_bytes = wl["bytes_per_row"] * n
+        h2d_bytes = int(alg_bytes)
+    elif args.workload == "sum":
+        dv = DeviceBuffer(8 * n, lib)
+        capi.check(lib.MoB200_GenInt64(1, (row0 // 64) * 64, n, dv.ptr, None, 0), lib)
+        bufs = {"col": dv}
+        def step(cols=bufs):
+            return ops.agg_sum(capi.T_INT64, cols["col"], None, n)
+        rec_bytes = 16
+        pack = lambda res: np.asarray([res[1], 0], dtype=np.int64).tobytes()
+        units, unit_name, alg_bytes, h2d_bytes = n, "rows/s", 8.0 * n, 8 * n
+    else:  # bruteforce: dataset rows sharded across ranks, every rank sees all queries
+        dim, nq, k = 768, args.queries, 10
+        n_local = n // world if world > 1 else n
+        ds = DeviceBuffer(4 * n_local * dim, lib)
+        capi.check(lib.MoB200_GenVectorsF32(20, rank * n_local, n_local, dim, ds.ptr, None, 0, 1.0), lib)
+        dq = DeviceBuffer(4 * nq * dim, lib)
+        capi.check(lib.MoB200_GenVectorsF32(21, 0, nq, dim, dq.ptr, None, 0, 1.0), lib)
+        idx = ops.BruteForceIndex(ds, dim, capi.METRIC_L2, key_base=rank * n_local, lib=lib)
+        bufs = {"queries": dq}
+        def step(cols=bufs):
+            return idx.search(cols["queries"], k)
+        rec_bytes = nq * k * 16
+        pack = lambda res: res[0].tobytes() + res[1].tobytes()
+        units, unit_name = nq, "queries/s"
+        alg_bytes = None
+        h2d_bytes = 4 * nq * dim
+        n = n_local
+
+    gather_buf = None
+    if dist is not None:
+        import torch
+        send = torch.zeros(rec_bytes, dtype=torch.uint8, device="cuda")
+        gather_buf = torch.zeros(rec_bytes * world, dtype=torch.uint8, device="cuda")
+
+    def exchange(res):
+        """the reduce seam (MergeGroup / MergeTop): all ranks receive every rank's partial record"""
+        if dist is None:
+            return
+        import torch
+        send.copy_(torch.frombuffer(bytearray(pack(res)), dtype=torch.uint8))
+        dist.all_gather_into_tensor(gather_buf, send)
+        if args.workload == "bruteforce":
+            allk = gather_buf.cpu().numpy()
+            per = rec_bytes
+            nq_, k_ = args.queries, 10
+            ks = np.stack([np.frombuffer(allk[r * per:r * per + nq_ * k_ * 8].tobytes(), dtype=np.int64) for r in range(world)])
+            dsx = np.stack([np.frombuffer(allk[r * per + nq_ * k_ * 8:(r + 1) * per].tobytes(), dtype=np.float64) for r in range(world)])
+            ops.topk_merge(ks, dsx, nq_, k_)          # k-way merge kernel on every rank
+
+    # ---------------------------------------------------------------------------------------------- resident timing
+    for _ in range(W):
+        exchange(step())
+    barrier_sync()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.MoB200_KernelLaunchCount()
+    kernel_ms = []
+    kms = C.c_float()
+    capi.check(lib.MoB200_TimerStart(), lib)
+    t_wall0 = time.perf_counter()
+    for _ in range(K):
+        res = step()
+        lib.MoB200_LastKernelMs(C.byref(kms)); kernel_ms.append(kms.value)
+        exchange(res)
+    ms = C.c_float()
+    capi.check(lib.MoB200_TimerStop(C.byref(ms)), lib)
+    barrier_sync()
+    wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    launches = lib.MoB200_KernelLaunchCount() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = max_over_ranks(max(ms.value, 0.0))
+    ms_per_step = total_ms / K
+    value = units * world * K / (total_ms * 1e-3)
+    kern_ms = statistics.mean(kernel_ms)
+
+    # ---------------------------------------------------------------------------------------------- e2e: host buffers
+    e2e = None
+    if not args.no_e2e and args.workload in ("q6", "q1", "sum"):
+        try:
+            avail = 0
+            for ln in open("/proc/meminfo"):
+                if ln.startswith("MemAvailable"):
+                    avail = int(ln.split()[1]) * 1024
+            need = sum(b.nbytes for b in bufs.values())
+            n_e2e = n
+            if avail and need * world * 1.5 > avail:
+                n_e2e = max(1 << 20, int(n * (avail / (need * world * 1.5))) // 8192 * 8192)
+            host = {}
+            dts = {"shipdate": np.int32, "returnflag": np.uint8, "linestatus": np.uint8, "col": np.int64}
+            for kname, b in bufs.items():
+                dt = np.dtype(dts.get(kname, np.float64))
+                pa = PinnedArray((n_e2e,), dt, lib)
+                capi.check(lib.MoB200_Download(pa.ptr, b.ptr, n_e2e * dt.itemsize), lib)
+                host[kname] = pa
+            n_saved = n
+            ke = min(K, 5)
+            hcols = {kname: pa.array for kname, pa in host.items()}
+            n = n_e2e     # step() closes over n
+            for _ in range(1):
+                exchange(step(hcols))
+            barrier_sync()
+            t0 = time.perf_counter()
+            for _ in range(ke):
+                exchange(step(hcols))
+            barrier_sync()
+            dt_e = max_over_ranks(time.perf_counter() - t0)
+            n = n_saved
+            per_row = need / n_saved
+            e2e = {"value": n_e2e * world * ke / dt_e, "unit": unit_name, "h2d_bytes_per_step": int(per_row * n_e2e), "d2h_bytes_per_step": rec_bytes,
+                   "steps": ke, "rows_per_gpu": n_e2e, "host_memory": "pinned (MoB200_HostAlloc)", "timer": "wall clock around the C-ABI calls, max over ranks"}
+            for pa in host.values():
+                pa.free()
+        except Exception as ex:  # report, never fake
+            e2e = {"value": None, "unit": unit_name, "error": str(ex)[:200]}
+    elif args.workload == "bruteforce":
+        qhost = bufs["queries"].to_numpy(np.float32)
+        t0 = time.perf_counter()
+        ke = min(K, 3)
+        for _ in range(ke):
+            exchange(step({"queries": qhost}))
+        barrier_sync()
+        dt_e = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": units * ke / dt_e, "unit": unit_name, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": rec_bytes, "steps": ke,
+               "note": "dataset resident (index built once, as the reference keeps it in memory); queries from host, keys+distances to host"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---------------------------------------------------------------------------------------------- roofline + cpu baseline
+    peak, peak_src = measured_peaks()
+    if alg_bytes is not None:
+        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "kernel": {"q6": "q6_kernel", "q1": "q1_kernel", "sum": "agg_kernel"}[args.workload], "kernel_ms": kern_ms,
+                    "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src}
+    else:
+        flop = 3.0 * args.queries * n * 768
+        fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12      # nominal fp32 FMA peak, TFLOP/s (no measured fp32 figure in MEASURED_PEAKS.json)
+        ach = flop / (kern_ms * 1e-3) / 1e12
+        roofline = {"bound": "fp32-fma", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak, "traffic": None,
+                    "kernel": "bf_topk_kernel", "kernel_ms": kern_ms, "peak_source": "nominal 148 SM x 128 FMA/clk x 1.965 GHz (exact fp32 path, no tensor cores)"}
+    cpu_baseline = None
+    if not args.no_cpu and world == 1 and args.workload in ("q6", "q1", "sum"):
+        threads = os.cpu_count() or 1
+        sample = min(n, 1 << 25)
+        v, sec = cpu_reference(args.workload, sample, 3, 1, threads)
+        cpu_baseline = {"value": v, "unit": "rows/s", "cores": threads, "kind": "port",
+                        "sample": "first %d rows, 3 passes after 1 warm-up; oracle/oracle_go.c operator chain on %d pthreads" % (sample, threads)}
+
+    line = {
+        "metric": wl["metric"], "value": value, "unit": unit_name, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak" if args.workload != "bruteforce" else "strong", "vs_baseline": None,
+        "dtype": {"q6": "f64", "q1": "f64", "sum": "int64", "bruteforce": "f32"}[args.workload], "data": "synthetic",
+        "config": {"workload": wl["name"], "rows_per_gpu": n, "l2": "inputs (%.1f GB per GPU) are larger than the 126 MB L2; no flush needed" % ((alg_bytes or 4.0 * n * 768) / 1e9),
+                   "parallelism": "block-range shards x%d, NCCL all_gather of partial aggregates" % world if world > 1 else "1 GPU",
+                   "timer": "CUDA events on the library stream (MoB200_TimerStart/Stop), max over ranks", "wall_ms_rank0": wall_ms},
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -242,6 +242,7 @@ int32_t MoB200_SetStream(void *cuda_stream);  /* adopt an external cudaStream_t 
 int32_t MoB200_TimerStart(void);              /* CUDA event on the calling thread's stream */
 int32_t MoB200_TimerStop(float *ms);          /* records, synchronizes, returns elapsed milliseconds */
 uint64_t MoB200_KernelLaunchCount(void);      /* kernels launched by this library since load (all threads) */
+int32_t MoB200_LastKernelMs(float *ms);       /* device time of the dominant kernel of the calling thread's last call (CUDA events) */
 int32_t MoB200_LastError(char *buf, uint64_t buflen);  /* thread-local last error text */
 int32_t MoB200_FlushL2(void);                 /* write a >L2-sized scratch buffer (bench hygiene) */
 int32_t MoB200_SetTuning(const char *name, int32_t value);  /* kernel-variant knobs used by tools/tune.py; returns 0 if known */

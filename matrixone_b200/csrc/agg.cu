@@ -240,7 +240,9 @@ int launch_agg(ThreadCtx &t, const void *dcol, const uint64_t *dnulls, uint64_t 
     if (!partials) return MO_RC_INTERNAL_ERROR;
     Rec *out = partials + grid;
     bool vec = (((uintptr_t)dcol) & 15) == 0;
+    cudaEventRecord(t.kev0, t.stream);
     agg_kernel<T, KIND><<<grid, kThreads, 0, t.stream>>>((const T *)dcol, dnulls, n, vec, partials, out, t.ctrl);
+    cudaEventRecord(t.kev1, t.stream);
     MOB_LAUNCH_CHECK();
     return read_back(t, hrec, out, sizeof(Rec));
 }

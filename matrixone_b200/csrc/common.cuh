@@ -22,6 +22,7 @@ struct ThreadCtx {
     bool own_stream = true;
     bool ready = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t kev0 = nullptr, kev1 = nullptr;  // bracket the dominant kernel of the last call (MoB200_LastKernelMs)
     std::vector<ArenaBlock> blocks;  // device scratch arena (bump allocated, reset per call)
     size_t cur_block = 0, cur_off = 0;
     char *pinned = nullptr;          // small pinned staging (scalar results, status words)

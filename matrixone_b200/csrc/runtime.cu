@@ -71,7 +71,8 @@ ThreadCtx &tctx() {
         }
         if (cudaSetDevice(g_device) != cudaSuccess) { snprintf(t.err, sizeof t.err, "cudaSetDevice failed"); return t; }
         if (cudaStreamCreateWithFlags(&t.stream, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreate(&t.ev0) != cudaSuccess || cudaEventCreate(&t.ev1) != cudaSuccess) {
+            cudaEventCreate(&t.ev0) != cudaSuccess || cudaEventCreate(&t.ev1) != cudaSuccess ||
+            cudaEventCreate(&t.kev0) != cudaSuccess || cudaEventCreate(&t.kev1) != cudaSuccess) {
             snprintf(t.err, sizeof t.err, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
             return t;
         }
@@ -284,6 +285,13 @@ int32_t MoB200_TimerStop(float *ms) {
     return MO_RC_SUCCESS;
 }
 uint64_t MoB200_KernelLaunchCount(void) { return g_launches.load(); }
+
+int32_t MoB200_LastKernelMs(float *ms) {
+    REQUIRE_CTX(t);
+    MOB_CUDA_TRY(cudaEventSynchronize(t.kev1));
+    MOB_CUDA_TRY(cudaEventElapsedTime(ms, t.kev0, t.kev1));
+    return MO_RC_SUCCESS;
+}
 
 int32_t MoB200_LastError(char *buf, uint64_t buflen) {
     ThreadCtx &t = tctx();

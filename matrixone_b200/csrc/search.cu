@@ -348,7 +348,9 @@ int launch_bf(ThreadCtx &t, const WorkDesc *ditems, int nitems, int dim, int k, 
         MOB_CUDA_TRY(cudaFuncSetAttribute(bf_topk_kernel<METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SearchSmem)));
         attr_set = true;
     }
+    cudaEventRecord(t.kev0, t.stream);
     bf_topk_kernel<METRIC><<<nitems, kThreads, sizeof(SearchSmem), t.stream>>>(ditems, dim, k, part_d, part_i);
+    cudaEventRecord(t.kev1, t.stream);
     MOB_LAUNCH_CHECK();
     return MO_RC_SUCCESS;
 }

@@ -359,12 +359,14 @@ static int launch_q6(ThreadCtx &t, const int32_t *sd, const double *disc, const 
     Q6Rec *partials = (Q6Rec *)arena_alloc(t, sizeof(Q6Rec) * (size_t)(grid + 1));
     if (!partials) return MO_RC_INTERNAL_ERROR;
     Q6Rec *out = partials + grid;
+    cudaEventRecord(t.kev0, t.stream);
     switch (variant) {
     case 1: q6_kernel<4, 2><<<grid, kThreads, 0, t.stream>>>(sd, disc, qty, price, n, P, partials, out, t.ctrl); break;
     case 2: q6_kernel<2, 4><<<grid, kThreads, 0, t.stream>>>(sd, disc, qty, price, n, P, partials, out, t.ctrl); break;
     case 3: q6_kernel<8, 2><<<grid, kThreads, 0, t.stream>>>(sd, disc, qty, price, n, P, partials, out, t.ctrl); break;
     default: q6_kernel<4, 4><<<grid, kThreads, 0, t.stream>>>(sd, disc, qty, price, n, P, partials, out, t.ctrl); break;
     }
+    cudaEventRecord(t.kev1, t.stream);
     MOB_LAUNCH_CHECK();
     return read_back(t, hrec, out, sizeof(Q6Rec));
 }
@@ -447,12 +449,14 @@ static int launch_q1(ThreadCtx &t, const int32_t *sd, const double *qty, const d
         Q1Rec *partials = (Q1Rec *)arena_alloc(t, sizeof(Q1Rec) * (size_t)(grid + 1));
         if (!partials) return MO_RC_INTERNAL_ERROR;
         Q1Rec *out = partials + grid;
+        cudaEventRecord(t.kev0, t.stream);
         if (!wide) {
             if (g_q1_variant == 1) q1_kernel<4, 4, 2, KEYMODE><<<grid, kThreads, 0, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl);
             else q1_kernel<4, 2, 2, KEYMODE><<<grid, kThreads, 0, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl);
         } else {
             q1_kernel<8, 2, 2, KEYMODE><<<grid, kThreads, 0, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl);
         }
+        cudaEventRecord(t.kev1, t.stream);
         MOB_LAUNCH_CHECK();
         int rc = read_back(t, hrec, out, sizeof(Q1Rec));
         if (rc) return rc;

@@ -1,0 +1,118 @@
+"""GPU parity: brute-force top-k, IVF-flat probe and top-k merge against the oracle restatement of
+GoBruteForceIndex.Search / IvfflatSearchIndex.Search.  Distances bit-exact; keys equal wherever the oracle's distances
+are not tied."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from matrixone_b200 import capi, datagen, ops
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_topk(keys, dists, okeys, odists, nq, k):
+    keys = keys.reshape(nq, k); dists = dists.reshape(nq, k); okeys = okeys.reshape(nq, k); odists = odists.reshape(nq, k)
+    assert (dists == odists).all(), np.abs(dists - odists).max()          # bit-exact distances, ascending
+    for q in range(nq):
+        same = keys[q] == okeys[q]
+        if not same.all():            # only allowed where distances tie
+            for j in np.flatnonzero(~same):
+                assert (odists[q] == odists[q][j]).sum() > 1, (q, j)
+
+
+@pytest.mark.parametrize("n,dim,nq,k", [(1000, 16, 7, 1), (1000, 16, 7, 5), (1000, 16, 7, 50), (5000, 128, 130, 10),
+                                        (777, 768, 65, 10), (3000, 100, 3, 64), (64, 8, 1, 10), (100, 30, 5, 3), (200, 7, 9, 4)])
+@pytest.mark.parametrize("metric", [capi.METRIC_L2, capi.METRIC_IP, capi.METRIC_COS, capi.METRIC_L1])
+def test_bruteforce_topk_matches_oracle(gpu, n, dim, nq, k, metric):
+    rng = np.random.default_rng(n + dim + k)
+    ds = rng.standard_normal((n, dim)).astype(np.float32); qs = rng.standard_normal((nq, dim)).astype(np.float32)
+    idx = ops.BruteForceIndex(ds, dim, metric)
+    keys, dists = idx.search(qs, k)
+    okeys, odists = O.bruteforce(ds, qs, k, metric)
+    _check_topk(keys, dists, okeys, odists, nq, k)
+    idx.destroy()
+
+
+def test_self_match_exact_zero_and_front_padding(gpu):
+    """brute_force_test.go:76-146 (key == i, distance == 0.0) and brute_force.go:319-331 (front padding with -1 / 0)"""
+    ds = datagen.vectors_f32(20, 0, 10_000, 128)
+    idx = ops.BruteForceIndex(ds, 128)
+    keys, dists = idx.search(ds[:2000], 3)
+    keys = keys.reshape(-1, 3); dists = dists.reshape(-1, 3)
+    assert (keys[:, 0] == np.arange(2000)).all() and (dists[:, 0] == 0.0).all() and (np.diff(dists, axis=1) >= 0).all()
+    idx.destroy()
+    small = ops.BruteForceIndex(ds[:2], 128)
+    keys, dists = small.search(ds[:1], 5)
+    assert list(keys[:3]) == [-1, -1, -1] and list(dists[:3]) == [0.0, 0.0, 0.0] and keys[3] == 0 and dists[3] == 0.0
+    assert small.search(ds[:1], 0)[0].size == 0
+    with pytest.raises(capi.MoError):
+        small.search(ds[:1], 65)           # beyond the fused kernel's k limit: loud error, no fallback
+    small.destroy()
+
+
+def test_ties_resolve_to_lower_row_id(gpu):
+    ds = np.zeros((300, 8), dtype=np.float32); ds[:, 0] = np.arange(300) % 3      # many exact ties
+    idx = ops.BruteForceIndex(ds, 8)
+    keys, dists = idx.search(np.zeros((1, 8), dtype=np.float32), 10)
+    assert list(keys) == [0, 3, 6, 9, 12, 15, 18, 21, 24, 27] and (dists == 0).all()
+    okeys, odists = O.bruteforce(ds, np.zeros((1, 8), dtype=np.float32), 10)
+    assert (odists == dists).all()
+    idx.destroy()
+
+
+def test_topk_merge_of_shards_equals_global(gpu):
+    """dataset sharded by rows (the multi-GPU layout): per-shard top-k + merge == global top-k"""
+    rng = np.random.default_rng(12)
+    n, dim, nq, k = 6000, 64, 50, 10
+    ds = rng.standard_normal((n, dim)).astype(np.float32); qs = rng.standard_normal((nq, dim)).astype(np.float32)
+    gk, gd = O.bruteforce(ds, qs, k)
+    sk, sd = [], []
+    for s in range(4):
+        lo, hi = s * 1500, (s + 1) * 1500
+        idx = ops.BruteForceIndex(ds[lo:hi], dim, key_base=lo)
+        a, b = idx.search(qs, k)
+        sk.append(a); sd.append(b); idx.destroy()
+    mk, md = ops.topk_merge(np.stack(sk), np.stack(sd), nq, k)
+    _check_topk(mk, md, gk, gd, nq, k)
+    # a shard with fewer than k rows contributes front-padded lists; the merge must skip the padding
+    idx = ops.BruteForceIndex(ds[:4], dim); a, b = idx.search(qs, k); idx.destroy()
+    idx = ops.BruteForceIndex(ds[4:n], dim, key_base=4); c, d = idx.search(qs, k); idx.destroy()
+    mk, md = ops.topk_merge(np.stack([a, c]), np.stack([b, d]), nq, k)
+    _check_topk(mk, md, gk, gd, nq, k)
+
+
+@pytest.mark.parametrize("metric,sqrt_out", [(capi.METRIC_L2, False), (capi.METRIC_L2, True), (capi.METRIC_IP, False), (capi.METRIC_COS, False)])
+def test_ivf_probe_matches_oracle(gpu, metric, sqrt_out):
+    nlist, dim, n, nq, k, nprobe = 64, 96, 20_000, 150, 10, 8
+    centers = datagen.vectors_f32(30, 0, nlist, dim) * 4
+    data = datagen.vectors_f32(31, 0, n, dim, centers, 1.0)
+    qs = datagen.vectors_f32(32, 0, nq, dim, centers, 1.0)
+    assign = np.zeros(n, dtype=np.int32)
+    O.go().og_assign_centroids_f32(O.p(data), n, dim, O.p(centers), nlist, metric, O.p(assign))
+    okeys = np.zeros(nq * k, dtype=np.int64); odists = np.zeros(nq * k)
+    O.go().og_ivf_search_f32(O.p(data), O.p(assign), n, dim, O.p(centers), nlist, O.p(qs), nq, nprobe, k, metric, int(sqrt_out), 8, O.p(okeys), O.p(odists))
+    idx = ops.IvfflatSearchIndex(data, assign, centers, metric)
+    keys, dists = idx.search(qs, k, nprobe, sqrt_out)
+    _check_topk(keys, dists, okeys, odists, nq, k)
+    # nprobe == nlist degenerates to brute force
+    keys, dists = idx.search(qs[:10], k, nlist, sqrt_out)
+    bk, bd = O.bruteforce(data, qs[:10], k, metric)
+    if sqrt_out:
+        bd = np.sqrt(bd)
+    _check_topk(keys, dists, bk, bd, 10, k)
+    idx.destroy()
+
+
+def test_ivf_empty_lists_and_small_index(gpu):
+    dim = 16
+    centers = np.eye(8, dim, dtype=np.float32) * 10
+    centers[np.arange(8), (np.arange(8) + 1) % dim] = 0.37 * np.arange(8, dtype=np.float32)    # break centroid-distance ties
+    data =np.repeat(centers[:2], 3, axis=0) + 0.01 * np.arange(6, dtype=np.float32)[:, None]      # only lists 0 and 1 have rows
+    assign = np.asarray([0, 0, 0, 1, 1, 1], dtype=np.int32)
+    idx = ops.IvfflatSearchIndex(data, assign, centers)
+    qs = centers[[0, 5]]
+    keys, dists = idx.search(qs, 4, 2)
+    okeys = np.zeros(8, dtype=np.int64); odists = np.zeros(8)
+    O.go().og_ivf_search_f32(O.p(data), O.p(assign), 6, dim, O.p(centers), 8, O.p(qs), 2, 2, 4, 0, 0, 1, O.p(okeys), O.p(odists))
+    assert (dists == odists).all() and (keys == okeys).all()
+    idx.destroy()
