@@ -122,6 +122,7 @@ constexpr int kQ1Vals = 5;  // sum_qty, sum_price, sum_disc_price, sum_charge, s
 struct Q1Slot { unsigned long long first_row; unsigned long long cnt; double v[kQ1Vals]; unsigned key; unsigned used; };
 struct Q1Rec { Q1Slot slot[MO_Q1_MAX_GROUPS]; unsigned overflow; unsigned pad; };
 constexpr unsigned kEmptyKey = 0xffffffffu;
+constexpr int kQ1MaxGrid = 1024;  // upper bound on the grid (the last-CTA fold keeps a [grid][8] byte map in shared memory)
 
 // KEYMODE 0: packed uint8 columns; 1: MatrixOne varlena cells (24 B, inline: bs[0]=len, bs[1..]=bytes; cgo/xcall.h:33-61)
 template <int G, int UNROLL, int CTAS, int KEYMODE>
@@ -174,14 +175,15 @@ q1_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty, const 
         double t4 = __dmul_rn(t2, t3);                // ... * (1 + l_tax)
 #pragma unroll
         for (int g = 0; g < G; g++) {
-            const bool m = (slot == g);
-            acc[g][0] = __dadd_rn(acc[g][0], m ? q : 0.0);
-            acc[g][1] = __dadd_rn(acc[g][1], m ? pr : 0.0);
-            acc[g][2] = __dadd_rn(acc[g][2], m ? t2 : 0.0);
-            acc[g][3] = __dadd_rn(acc[g][3], m ? t4 : 0.0);
-            acc[g][4] = __dadd_rn(acc[g][4], m ? di : 0.0);
-            if (m && cnt[g] == 0) first[g] = r;   // a thread visits its rows in increasing order
-            cnt[g] += m;
+            if (slot == g) {   // short body: compiled to predicated DADDs, no selects, no divergence cost beyond the issue slot
+                acc[g][0] = __dadd_rn(acc[g][0], q);
+                acc[g][1] = __dadd_rn(acc[g][1], pr);
+                acc[g][2] = __dadd_rn(acc[g][2], t2);
+                acc[g][3] = __dadd_rn(acc[g][3], t4);
+                acc[g][4] = __dadd_rn(acc[g][4], di);
+                if (cnt[g] == 0) first[g] = r;   // a thread visits its rows in increasing order
+                cnt[g] += 1;
+            }
         }
     };
 
@@ -283,30 +285,55 @@ q1_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty, const 
         last = (tk == gridDim.x - 1);
     }
     __syncthreads();
-    if (last && threadIdx.x == 0) {
-        // fold CTA records in CTA-index order (MergeGroup: re-hash partial keys + BatchMerge, mergeGroup.go:132-247)
+    if (last) {
+        // Fold the CTA records (MergeGroup: re-hash partial keys + BatchMerge, mergeGroup.go:132-247) with the whole CTA:
+        //  1. one thread per CTA record maps its local slots to final slots (shared dictionary, atomicCAS);
+        //  2. one thread per (final slot, value) sums that value over the CTA records IN CTA-INDEX ORDER, so the result
+        //     is bitwise deterministic although the dictionary slot order is not (the host sorts groups by first_row).
         __threadfence();
-        Q1Rec F; memset(&F, 0, sizeof F);
-        for (int g = 0; g < MO_Q1_MAX_GROUPS; g++) { F.slot[g].key = kEmptyKey; F.slot[g].first_row = ~0ull; }
-        for (unsigned bIdx = 0; bIdx < gridDim.x; bIdx++) {
+        __shared__ unsigned fdict[MO_Q1_MAX_GROUPS];
+        __shared__ unsigned char inv[kQ1MaxGrid][MO_Q1_MAX_GROUPS];   // [cta][final slot] -> local slot or 0xff
+        __shared__ unsigned f_overflow;
+        if (threadIdx.x < MO_Q1_MAX_GROUPS) fdict[threadIdx.x] = kEmptyKey;
+        if (threadIdx.x == 0) f_overflow = 0;
+        for (unsigned i = threadIdx.x; i < gridDim.x * MO_Q1_MAX_GROUPS; i += kThreads) inv[i / MO_Q1_MAX_GROUPS][i % MO_Q1_MAX_GROUPS] = 0xff;
+        __syncthreads();
+        for (unsigned bIdx = threadIdx.x; bIdx < gridDim.x; bIdx += kThreads) {
             const Q1Rec &R = partials[bIdx];
-            if (R.overflow) F.overflow = 1;
+            if (R.overflow) f_overflow = 1;
+#pragma unroll
             for (int g = 0; g < G; g++) {
-                const Q1Slot &s = R.slot[g];
-                if (!s.used || s.cnt == 0) continue;
+                if (!R.slot[g].used || R.slot[g].cnt == 0) continue;
+                const unsigned key = R.slot[g].key;
                 int dst = -1;
                 for (int x = 0; x < MO_Q1_MAX_GROUPS; x++) {
-                    if (F.slot[x].key == s.key) { dst = x; break; }
-                    if (F.slot[x].key == kEmptyKey) { dst = x; F.slot[x].key = s.key; F.slot[x].used = 1; break; }
+                    const unsigned prev = atomicCAS(&fdict[x], kEmptyKey, key);
+                    if (prev == kEmptyKey || prev == key) { dst = x; break; }
                 }
-                if (dst < 0) { F.overflow = 1; continue; }
-                Q1Slot &D = F.slot[dst];
-                D.cnt += s.cnt;
-                if (s.first_row < D.first_row) D.first_row = s.first_row;
-                for (int j = 0; j < kQ1Vals; j++) D.v[j] = __dadd_rn(D.v[j], s.v[j]);
+                if (dst < 0) f_overflow = 1; else inv[bIdx][dst] = (unsigned char)g;
             }
         }
-        *out = F;
+        __syncthreads();
+        if (threadIdx.x < MO_Q1_MAX_GROUPS * 8) {
+            const int sl = threadIdx.x >> 3, j = threadIdx.x & 7;
+            Q1Slot &D = out->slot[sl];
+            if (j < kQ1Vals) {
+                double a = 0.0;
+                for (unsigned bIdx = 0; bIdx < gridDim.x; bIdx++) { const unsigned g = inv[bIdx][sl]; if (g != 0xff) a = __dadd_rn(a, partials[bIdx].slot[g].v[j]); }
+                D.v[j] = a;
+            } else if (j == 5) {
+                unsigned long long c = 0;
+                for (unsigned bIdx = 0; bIdx < gridDim.x; bIdx++) { const unsigned g = inv[bIdx][sl]; if (g != 0xff) c += partials[bIdx].slot[g].cnt; }
+                D.cnt = c;
+            } else if (j == 6) {
+                unsigned long long f = ~0ull;
+                for (unsigned bIdx = 0; bIdx < gridDim.x; bIdx++) { const unsigned g = inv[bIdx][sl]; if (g != 0xff) { const unsigned long long r = partials[bIdx].slot[g].first_row; f = r < f ? r : f; } }
+                D.first_row = f;
+            } else {
+                D.key = fdict[sl]; D.used = fdict[sl] != kEmptyKey;
+                if (sl == 0) { out->overflow = f_overflow; out->pad = 0; }
+            }
+        }
     }
 }
 
@@ -446,6 +473,7 @@ static int launch_q1(ThreadCtx &t, const int32_t *sd, const double *qty, const d
         int grid = num_sms() * ctas;
         uint64_t work = (n / 2 + kThreads - 1) / kThreads;
         if ((uint64_t)grid > work) grid = work ? (int)work : 1;
+        if (grid > kQ1MaxGrid) grid = kQ1MaxGrid;
         Q1Rec *partials = (Q1Rec *)arena_alloc(t, sizeof(Q1Rec) * (size_t)(grid + 1));
         if (!partials) return MO_RC_INTERNAL_ERROR;
         Q1Rec *out = partials + grid;

@@ -95,7 +95,8 @@ def test_sum_float_within_1e5_and_deterministic(gpu, n):
         assert rc == 0 and isnull == bool(nul[0])
         if not isnull:
             assert abs(got - s[0]) <= 1e-5 * abs(s[0]) + 1e-9      # tolerance stated by north_star: 1e-5 relative
-            kahan = O.go().og_kahan_sum(O.p(v.astype(np.float64)[~np.unpackbits(nulls.view(np.uint8), bitorder="little")[:n].astype(bool)].copy()), int(c[0]))
+            live = np.ascontiguousarray(v.astype(np.float64)[~np.unpackbits(nulls.view(np.uint8), bitorder="little")[:n].astype(bool)])
+            kahan = O.go().og_kahan_sum(O.p(live), int(c[0]))
             assert abs(got - kahan) <= 1e-9 * abs(kahan) + 1e-9    # and far tighter against a compensated sum
             assert ops.agg_sum(T, v, nulls)[1] == got              # bitwise run-to-run determinism
             rca, avg, _ = ops.agg_avg(T, v, nulls)

@@ -139,3 +139,24 @@ def test_full_size_properties_block_additivity(gpu):
     assert ns == full[1] and abs(want - full[0]) <= 1e-10 * abs(want)
     for b in bufs.values():
         b.free()
+
+
+def test_kernel_variants_agree(gpu):
+    """every tuning variant (tools/tune.py) computes the same counts and 1e-12-equal sums"""
+    n = 300_000
+    cols = datagen.lineitem(13, 0, n)
+    P = datagen.q6_params()
+    base = None
+    try:
+        for var in (0, 1, 2, 3):
+            gpu.MoB200_SetTuning(b"q6_variant", var)
+            r = ops.q6_filter_sum(cols["shipdate"], cols["discount"], cols["quantity"], cols["extendedprice"], n, *P)
+            base = base or r
+            assert r[1] == base[1] and abs(r[0] - base[0]) <= 1e-12 * abs(base[0])
+        want = O.q1(cols, n, datagen.Q1_CUTOFF)
+        for var in (0, 1, 2):
+            gpu.MoB200_SetTuning(b"q1_variant", var)
+            _check_q1(ops.q1_group_agg(cols["shipdate"], cols["quantity"], cols["extendedprice"], cols["discount"], cols["tax"],
+                                       cols["returnflag"], cols["linestatus"], n, datagen.Q1_CUTOFF), want)
+    finally:
+        gpu.MoB200_SetTuning(b"q6_variant", 0); gpu.MoB200_SetTuning(b"q1_variant", 0)
