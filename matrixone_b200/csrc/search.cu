@@ -129,6 +129,7 @@ bf_topk_kernel(const WorkDesc *__restrict__ items, int dim, int k, float *__rest
     };
 
     for (int64_t row0 = W.row_begin; row0 < W.row_end; row0 += TX) {
+        __syncwarp();   // the per-query insertion loop below diverges; make sure every warp starts a tile converged
         float acc[4][4];
 #pragma unroll
         for (int a = 0; a < 4; a++)

@@ -130,7 +130,11 @@ __global__ void __launch_bounds__(kThreads, CTAS)
 q1_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty, const double *__restrict__ price,
           const double *__restrict__ disc, const double *__restrict__ tax, const uint8_t *__restrict__ rf,
           const uint8_t *__restrict__ ls, uint64_t n, int32_t cutoff, Q1Rec *__restrict__ partials,
-          Q1Rec *__restrict__ out, unsigned *ticket) {
+          Q1Rec *__restrict__ out, unsigned *ticket, unsigned long long *dbg) {
+    auto stamp = [&](int k) { if (dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[blockIdx.x * 16 + k] = t; } };
+    stamp(0);
+    __shared__ unsigned s_slow;
+    if (threadIdx.x == 0) s_slow = 0;
     __shared__ unsigned dict[G];      // CTA-local key -> slot dictionary, slots handed out first-come
     __shared__ unsigned s_overflow;
     if (threadIdx.x < G) dict[threadIdx.x] = kEmptyKey;
@@ -148,34 +152,52 @@ q1_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty, const 
         for (int j = 0; j < kQ1Vals; j++) acc[g][j] = 0.0;
     }
 
-    auto find_slot = [&](unsigned key) -> int {
+    const int lane = threadIdx.x & 31;
+    // Control flow below is WARP-UNIFORM: every lane of a warp runs the same iterations and the dictionary slow path is
+    // taken by the whole warp together (ballot + one elected lane doing the CAS).  A first version let lanes diverge inside
+    // the insert loop; some warps then never reconverged and ran ~8x slower to the end of the kernel (profiles/r01_q1_*).
+    auto find_slot = [&](unsigned key, bool valid) -> int {
         int slot = -1;
 #pragma unroll
         for (int g = 0; g < G; g++) if (dk[g] == key) slot = g;
-        if (slot >= 0) return slot;
-        // miss: claim or find the key in the shared dictionary, then refresh the register copy
+        bool settled = !valid || slot >= 0;   // a lane is settled once its key has been looked up in the shared dictionary
+        unsigned miss = __ballot_sync(0xffffffffu, !settled);
+        while (miss) {
+            const int leader = __ffs(miss) - 1;
+            const unsigned lkey = __shfl_sync(0xffffffffu, key, leader);
+            if (lane == leader) {   // claim or find lkey in the shared dictionary
+                if (dbg) atomicAdd(&s_slow, 1u);
+                bool ok = false;
 #pragma unroll 1
-        for (int g = 0; g < G; g++) {
-            unsigned prev = atomicCAS(&dict[g], kEmptyKey, key);
-            if (prev == kEmptyKey || prev == key) { slot = g; break; }
-        }
+                for (int g = 0; g < G; g++) {
+                    const unsigned prev = atomicCAS(&dict[g], kEmptyKey, lkey);
+                    if (prev == kEmptyKey || prev == lkey) { ok = true; break; }
+                }
+                if (!ok) s_overflow = 1;
+            }
+            __syncwarp();
 #pragma unroll
-        for (int g = 0; g < G; g++) dk[g] = ((volatile unsigned *)dict)[g];
-        if (slot < 0) s_overflow = 1;
+            for (int g = 0; g < G; g++) dk[g] = ((volatile unsigned *)dict)[g];
+            slot = -1;
+#pragma unroll
+            for (int g = 0; g < G; g++) if (dk[g] == key) slot = g;
+            if (key == lkey || slot >= 0) settled = true;   // lkey lanes are settled either way (slot found, or dictionary full)
+            miss = __ballot_sync(0xffffffffu, !settled);
+        }
         return slot;
     };
 
-    auto row = [&](uint64_t r, int32_t d, double q, double pr, double di, double tx, unsigned key) {
-        if (d > cutoff) return;                       // l_shipdate <= cutoff
-        int slot = find_slot(key);
-        if (slot < 0) return;
-        double t1 = __dsub_rn(1.0, di);               // 1 - l_discount
-        double t2 = __dmul_rn(pr, t1);                // l_extendedprice * (1 - l_discount)
-        double t3 = __dadd_rn(1.0, tx);               // 1 + l_tax
-        double t4 = __dmul_rn(t2, t3);                // ... * (1 + l_tax)
+    // every lane calls row(); `inb` = the row exists, the shipdate filter is folded into `valid`
+    auto row = [&](uint64_t r, bool inb, int32_t d, double q, double pr, double di, double tx, unsigned key) {
+        const bool valid = inb && d <= cutoff;        // l_shipdate <= cutoff
+        const int slot = find_slot(key, valid);
+        const double t1 = __dsub_rn(1.0, di);         // 1 - l_discount
+        const double t2 = __dmul_rn(pr, t1);          // l_extendedprice * (1 - l_discount)
+        const double t3 = __dadd_rn(1.0, tx);         // 1 + l_tax
+        const double t4 = __dmul_rn(t2, t3);          // ... * (1 + l_tax)
 #pragma unroll
         for (int g = 0; g < G; g++) {
-            if (slot == g) {   // short body: compiled to predicated DADDs, no selects, no divergence cost beyond the issue slot
+            if (valid && slot == g) {   // short body: predicated DADDs
                 acc[g][0] = __dadd_rn(acc[g][0], q);
                 acc[g][1] = __dadd_rn(acc[g][1], pr);
                 acc[g][2] = __dadd_rn(acc[g][2], t2);
@@ -207,12 +229,13 @@ q1_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty, const 
     const uint64_t npairs = n >> 1;
     const uint64_t tid = blockIdx.x * (uint64_t)kThreads + threadIdx.x;
     const uint64_t nthreads = (uint64_t)gridDim.x * kThreads;
-    uint64_t p = tid;
-    for (; p + (UNROLL - 1) * nthreads < npairs; p += UNROLL * nthreads) {
+    const uint64_t wbase = tid - lane;   // first pair of this warp: loop bounds depend on it only => uniform per warp
+    uint64_t pw = wbase;
+    for (; pw + 31 + (UNROLL - 1) * nthreads < npairs; pw += UNROLL * nthreads) {   // all 32 lanes x UNROLL pairs in range
         int2 d[UNROLL]; int4 a[UNROLL], b[UNROLL], c[UNROLL], e[UNROLL]; unsigned k0[UNROLL], k1[UNROLL];
 #pragma unroll
         for (int k = 0; k < UNROLL; k++) {
-            const uint64_t q = p + k * nthreads;
+            const uint64_t q = pw + lane + k * nthreads;
             d[k] = ld_stream8(sd + 2 * q);
             a[k] = ld_stream16(qty + 2 * q);
             b[k] = ld_stream16(price + 2 * q);
@@ -222,36 +245,54 @@ q1_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty, const 
         }
 #pragma unroll
         for (int k = 0; k < UNROLL; k++) {
-            const uint64_t q = p + k * nthreads;
+            const uint64_t q = pw + lane + k * nthreads;
             double qq[2], pr[2], di[2], tx[2];
             memcpy(qq, &a[k], 16); memcpy(pr, &b[k], 16); memcpy(di, &c[k], 16); memcpy(tx, &e[k], 16);
-            row(2 * q, d[k].x, qq[0], pr[0], di[0], tx[0], k0[k]);
-            row(2 * q + 1, d[k].y, qq[1], pr[1], di[1], tx[1], k1[k]);
+            row(2 * q, true, d[k].x, qq[0], pr[0], di[0], tx[0], k0[k]);
+            row(2 * q + 1, true, d[k].y, qq[1], pr[1], di[1], tx[1], k1[k]);
         }
     }
-    for (; p < npairs; p += nthreads) {
-        int2 d = ld_stream8(sd + 2 * p);
-        int4 a = ld_stream16(qty + 2 * p), b = ld_stream16(price + 2 * p), c = ld_stream16(disc + 2 * p), e = ld_stream16(tax + 2 * p);
-        unsigned k0, k1; load_keys(p, k0, k1);
+    for (; pw < npairs; pw += nthreads) {   // ragged end: same code, lanes past the end carry inb = false
+        const uint64_t q = pw + lane;
+        const bool inb = q < npairs;
+        int2 d = make_int2(0, 0); int4 a = make_int4(0, 0, 0, 0), b = a, c = a, e = a; unsigned k0 = 0, k1 = 0;
+        if (inb) {
+            d = ld_stream8(sd + 2 * q);
+            a = ld_stream16(qty + 2 * q); b = ld_stream16(price + 2 * q); c = ld_stream16(disc + 2 * q); e = ld_stream16(tax + 2 * q);
+            load_keys(q, k0, k1);
+        }
         double qq[2], pr[2], di[2], tx[2];
         memcpy(qq, &a, 16); memcpy(pr, &b, 16); memcpy(di, &c, 16); memcpy(tx, &e, 16);
-        row(2 * p, d.x, qq[0], pr[0], di[0], tx[0], k0);
-        row(2 * p + 1, d.y, qq[1], pr[1], di[1], tx[1], k1);
+        row(2 * q, inb, d.x, qq[0], pr[0], di[0], tx[0], k0);
+        row(2 * q + 1, inb, d.y, qq[1], pr[1], di[1], tx[1], k1);
     }
-    if ((n & 1) && tid == 0) {
+    if (tid < 32) {   // odd tail row: handled by warp 0 of CTA 0, lane 0 carries it
+        const bool has = (n & 1) && lane == 0;
         const uint64_t r = n - 1;
-        unsigned key;
-        if (KEYMODE == 0) key = rf[r] | ((unsigned)ls[r] << 8);
-        else key = (rf[24 * r] ? rf[24 * r + 1] : 0u) | ((ls[24 * r] ? (unsigned)ls[24 * r + 1] : 0u) << 8);
-        row(r, sd[r], qty[r], price[r], disc[r], tax[r], key);
+        unsigned key = 0; int32_t dd = 0; double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+        if (has) {
+            if (KEYMODE == 0) key = rf[r] | ((unsigned)ls[r] << 8);
+            else key = (rf[24 * r] ? rf[24 * r + 1] : 0u) | ((ls[24 * r] ? (unsigned)ls[24 * r + 1] : 0u) << 8);
+            dd = sd[r]; v0 = qty[r]; v1 = price[r]; v2 = disc[r]; v3 = tax[r];
+        }
+        row(r, has, dd, v0, v1, v2, v3, key);
+    }
+    stamp(1);
+    if (dbg && (threadIdx.x & 31) == 0) {
+        unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
+        unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        dbg[blockIdx.x * 16 + 8 + (threadIdx.x >> 5)] = tt;
+        if (threadIdx.x == 0) dbg[blockIdx.x * 16 + 5] = sm;
     }
     __syncthreads();  // dictionary final
+    stamp(2);
+    if (dbg && threadIdx.x == 0) dbg[blockIdx.x * 16 + 7] = s_slow;
 
     // ---- CTA reduction.  Register slots are indexed by the CTA dictionary, identical for every thread of the CTA.
     __shared__ double sv[kThreads / 32][G][kQ1Vals];
     __shared__ unsigned long long scnt[kThreads / 32][G], sfirst[kThreads / 32][G];
     __shared__ bool last;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warp = threadIdx.x >> 5;
 #pragma unroll
     for (int g = 0; g < G; g++) {
         unsigned long long c64 = cnt[g], f = first[g];
@@ -284,6 +325,7 @@ q1_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty, const 
         unsigned tk = atomicInc(ticket, gridDim.x - 1);
         last = (tk == gridDim.x - 1);
     }
+    stamp(3);
     __syncthreads();
     if (last) {
         // Fold the CTA records (MergeGroup: re-hash partial keys + BatchMerge, mergeGroup.go:132-247) with the whole CTA:
@@ -334,6 +376,8 @@ q1_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty, const 
                 if (sl == 0) { out->overflow = f_overflow; out->pad = 0; }
             }
         }
+        __syncthreads();
+        stamp(4);
     }
 }
 
@@ -357,14 +401,22 @@ void q1_finalize(const Q1Rec &F, mo_q1_result_t *res) {
 }
 
 int g_q6_variant = 0, g_q1_variant = 0;  // tuning knobs (MoB200_SetTuning)
+unsigned long long *g_q1_dbg = nullptr;   // optional per-CTA phase timestamps (MoB200_SetTuning("q1_debug", 1))
 
 }  // namespace
 
 namespace mob {
 
+unsigned long long *q1_debug_buffer() { return g_q1_dbg; }
+
 int tuning_set(const char *name, int value) {
     if (!strcmp(name, "q6_variant")) { g_q6_variant = value; return 0; }
     if (!strcmp(name, "q1_variant")) { g_q1_variant = value; return 0; }
+    if (!strcmp(name, "q1_debug")) {
+        if (value && !g_q1_dbg) { if (cudaMalloc((void **)&g_q1_dbg, 8 * 16 * 1024) != cudaSuccess) return -1; cudaMemset(g_q1_dbg, 0, 8 * 16 * 1024); }
+        if (!value && g_q1_dbg) { cudaFree(g_q1_dbg); g_q1_dbg = nullptr; }
+        return 0;
+    }
     return -1;
 }
 
@@ -479,10 +531,10 @@ static int launch_q1(ThreadCtx &t, const int32_t *sd, const double *qty, const d
         Q1Rec *out = partials + grid;
         cudaEventRecord(t.kev0, t.stream);
         if (!wide) {
-            if (g_q1_variant == 1) q1_kernel<4, 4, 2, KEYMODE><<<grid, kThreads, 0, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl);
-            else q1_kernel<4, 2, 2, KEYMODE><<<grid, kThreads, 0, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl);
+            if (g_q1_variant == 1) q1_kernel<4, 4, 2, KEYMODE><<<grid, kThreads, 0, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg);
+            else q1_kernel<4, 2, 2, KEYMODE><<<grid, kThreads, 0, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg);
         } else {
-            q1_kernel<8, 2, 2, KEYMODE><<<grid, kThreads, 0, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl);
+            q1_kernel<8, 2, 2, KEYMODE><<<grid, kThreads, 0, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg);
         }
         cudaEventRecord(t.kev1, t.stream);
         MOB_LAUNCH_CHECK();
