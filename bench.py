@@ -176,8 +176,8 @@ def main():
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     os.environ.setdefault("MO_B200_DEVICE", str(local))
-    from matrixone_b200 import capi, datagen, ops
-    from matrixone_b200.vector import DeviceBuffer, PinnedArray, Vector, xcall
+    from matrixone_b200 import capi, datagen, ops, shard
+    from matrixone_b200.vector import DeviceBuffer, PinnedArray
     lib = capi.load_library()
     capi.check(lib.MoB200_Init(local), lib)
 
@@ -222,20 +222,16 @@ def main():
         if args.workload == "q6":
             def step(cols=bufs):
                 return ops.q6_filter_sum(cols["shipdate"], cols["discount"], cols["quantity"], cols["extendedprice"], n, *P)
-            rec_bytes = 16
-            def pack(res):
-                return np.asarray([res[0]], dtype=np.float64).tobytes() + np.asarray([res[1]], dtype=np.int64).tobytes()
+            rec_bytes = shard.Q6_REC_BYTES
+            pack = lambda res: shard.pack_q6(res[0], res[1])
+            merge = lambda buf: shard.merge_q6(buf, world)
         else:
             def step(cols=bufs):
                 return ops.q1_group_agg(cols["shipdate"], cols["quantity"], cols["extendedprice"], cols["discount"], cols["tax"],
                                         cols["returnflag"], cols["linestatus"], n, datagen.Q1_CUTOFF)
-            rec_bytes = 8 * 64
-            def pack(res):
-                out = np.zeros(64, dtype=np.float64)
-                for i, g in enumerate(res[:8]):
-                    out[i * 8:(i + 1) * 8] = [g["returnflag"] + 256 * g["linestatus"], g["sum_qty"], g["sum_base_price"], g["sum_disc_price"],
-                                              g["sum_charge"], g["sum_disc"], g["count_order"], g["first_row"]]
-                return out.tobytes()
+            rec_bytes = shard.Q1_REC_BYTES
+            pack = lambda res: shard.pack_q1(res, row0)
+            merge = lambda buf: shard.merge_q1(buf, world)
         units = n
         unit_name = "rows/s"
         alg_bytes = wl["bytes_per_row"] * n
@@ -248,6 +244,7 @@ def main():
             return ops.agg_sum(capi.T_INT64, cols["col"], None, n)
         rec_bytes = 16
         pack = lambda res: np.asarray([res[1], 0], dtype=np.int64).tobytes()
+        merge = lambda buf: int(np.frombuffer(bytes(buf), dtype=np.int64).reshape(world, 2)[:, 0].sum())
         units, unit_name, alg_bytes, h2d_bytes = n, "rows/s", 8.0 * n, 8 * n
     else:  # bruteforce: dataset rows sharded across ranks, every rank sees all queries
         dim, nq, k = 768, args.queries, 10
@@ -261,7 +258,8 @@ def main():
         def step(cols=bufs):
             return idx.search(cols["queries"], k)
         rec_bytes = nq * k * 16
-        pack = lambda res: res[0].tobytes() + res[1].tobytes()
+        pack = lambda res: shard.pack_topk(res[0], res[1])
+        merge = lambda buf: ops.topk_merge(*shard.unpack_topk(buf, world, nq, k), nq, k)   # k-way merge kernel on every rank
         units, unit_name = nq, "queries/s"
         alg_bytes = None
         h2d_bytes = 4 * nq * dim
@@ -280,13 +278,7 @@ def main():
         import torch
         send.copy_(torch.frombuffer(bytearray(pack(res)), dtype=torch.uint8))
         dist.all_gather_into_tensor(gather_buf, send)
-        if args.workload == "bruteforce":
-            allk = gather_buf.cpu().numpy()
-            per = rec_bytes
-            nq_, k_ = args.queries, 10
-            ks = np.stack([np.frombuffer(allk[r * per:r * per + nq_ * k_ * 8].tobytes(), dtype=np.int64) for r in range(world)])
-            dsx = np.stack([np.frombuffer(allk[r * per + nq_ * k_ * 8:(r + 1) * per].tobytes(), dtype=np.float64) for r in range(world)])
-            ops.topk_merge(ks, dsx, nq_, k_)          # k-way merge kernel on every rank
+        return merge(gather_buf.cpu().numpy().tobytes())
 
     # ---------------------------------------------------------------------------------------------- resident timing
     for _ in range(W):

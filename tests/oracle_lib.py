@@ -166,6 +166,6 @@ def q1(cols, n, cutoff, nthreads=1):
         s = sums[g * 7:(g + 1) * 7]; c = cnts[g * 4:(g + 1) * 4]
         out.append({"returnflag": int(keys[g]) & 0xff, "linestatus": (int(keys[g]) >> 8) & 0xff, "first_row": int(first[g]),
                     "sum_qty": s[0], "sum_base_price": s[1], "sum_disc_price": s[2], "sum_charge": s[3],
-                    "avg_qty": s[4] / c[0], "avg_price": s[5] / c[1], "avg_disc": s[6] / c[2], "count_order": int(c[3])})
+                    "avg_qty": s[4] / c[0], "avg_price": s[5] / c[1], "avg_disc": s[6] / c[2], "sum_disc": s[6], "count_order": int(c[3])})
     out.sort(key=lambda g: g["first_row"])
     return out
