@@ -187,7 +187,11 @@ q1_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty, const 
         return slot;
     };
 
-    // every lane calls row(); `inb` = the row exists, the shipdate filter is folded into `valid`
+    // every lane calls row(); `inb` = the row exists, the shipdate filter is folded into `valid`.
+    // Group dispatch without branches: acc[g][j] = fma(v_j, ind_g, acc[g][j]) with ind_g = 1.0 for the row's slot and 0.0 for
+    // the others.  fma(v, 1.0, a) == RN(v + a) (bit-identical to the reference's add) and fma(v, 0.0, a) == a for finite v,
+    // so all 32 lanes stay active (the branchy form ran at ~14 active lanes, profiles/r01_ncu_summary.md).  Rows holding
+    // Inf/NaN would poison the other groups through 0 * Inf, so a warp that sees one takes the exact predicated path.
     auto row = [&](uint64_t r, bool inb, int32_t d, double q, double pr, double di, double tx, unsigned key) {
         const bool valid = inb && d <= cutoff;        // l_shipdate <= cutoff
         const int slot = find_slot(key, valid);
@@ -195,17 +199,33 @@ q1_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty, const 
         const double t2 = __dmul_rn(pr, t1);          // l_extendedprice * (1 - l_discount)
         const double t3 = __dadd_rn(1.0, tx);         // 1 + l_tax
         const double t4 = __dmul_rn(t2, t3);          // ... * (1 + l_tax)
+        const bool finite = (fabs(t4) + fabs(q)) < INFINITY;   // false for any Inf/NaN among q, pr, di, tx (and on overflow)
+        if (__any_sync(0xffffffffu, valid && !finite)) {
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                if (valid && slot == g) {
+                    acc[g][0] = __dadd_rn(acc[g][0], q);
+                    acc[g][1] = __dadd_rn(acc[g][1], pr);
+                    acc[g][2] = __dadd_rn(acc[g][2], t2);
+                    acc[g][3] = __dadd_rn(acc[g][3], t4);
+                    acc[g][4] = __dadd_rn(acc[g][4], di);
+                    if (cnt[g] == 0) first[g] = r;
+                    cnt[g] += 1;
+                }
+            }
+            return;
+        }
 #pragma unroll
         for (int g = 0; g < G; g++) {
-            if (valid && slot == g) {   // short body: predicated DADDs
-                acc[g][0] = __dadd_rn(acc[g][0], q);
-                acc[g][1] = __dadd_rn(acc[g][1], pr);
-                acc[g][2] = __dadd_rn(acc[g][2], t2);
-                acc[g][3] = __dadd_rn(acc[g][3], t4);
-                acc[g][4] = __dadd_rn(acc[g][4], di);
-                if (cnt[g] == 0) first[g] = r;   // a thread visits its rows in increasing order
-                cnt[g] += 1;
-            }
+            const bool m = valid && slot == g;
+            const double ind = __hiloint2double(m ? 0x3ff00000 : 0, 0);   // 1.0 or 0.0
+            acc[g][0] = __fma_rn(q, ind, acc[g][0]);
+            acc[g][1] = __fma_rn(pr, ind, acc[g][1]);
+            acc[g][2] = __fma_rn(t2, ind, acc[g][2]);
+            acc[g][3] = __fma_rn(t4, ind, acc[g][3]);
+            acc[g][4] = __fma_rn(di, ind, acc[g][4]);
+            if (m && cnt[g] == 0) first[g] = r;       // a thread visits its rows in increasing order
+            cnt[g] += m;
         }
     };
 

@@ -160,3 +160,26 @@ def test_kernel_variants_agree(gpu):
                                        cols["returnflag"], cols["linestatus"], n, datagen.Q1_CUTOFF), want)
     finally:
         gpu.MoB200_SetTuning(b"q6_variant", 0); gpu.MoB200_SetTuning(b"q1_variant", 0)
+
+
+def test_q1_non_finite_values_stay_inside_their_group(gpu):
+    """the branch-free group dispatch multiplies by 0/1 indicators; rows holding Inf/NaN must take the exact path so that
+    only their own group is affected, exactly like the reference's per-group `sums[g] += v`"""
+    n = 20_000
+    cols = {k: v.copy() for k, v in datagen.lineitem(14, 0, n).items()}
+    sel = np.flatnonzero((cols["returnflag"] == ord("A")) & (cols["shipdate"] <= datagen.Q1_CUTOFF))
+    cols["quantity"][sel[5]] = np.inf
+    cols["tax"][sel[9]] = np.nan
+    cols["extendedprice"][sel[11]] = 1e308; cols["tax"][sel[11]] = 0.08      # finite inputs, product overflows to +Inf
+    want = O.q1(cols, n, datagen.Q1_CUTOFF)
+    got = ops.q1_group_agg(cols["shipdate"], cols["quantity"], cols["extendedprice"], cols["discount"], cols["tax"],
+                           cols["returnflag"], cols["linestatus"], n, datagen.Q1_CUTOFF)
+    assert [(g["returnflag"], g["linestatus"], g["count_order"]) for g in got] == [(g["returnflag"], g["linestatus"], g["count_order"]) for g in want]
+    for g, w in zip(got, want):
+        for k in ("sum_qty", "sum_base_price", "sum_disc_price", "sum_charge", "avg_qty", "avg_price", "avg_disc"):
+            if np.isfinite(w[k]):
+                assert abs(g[k] - w[k]) <= 1e-11 * abs(w[k]), (chr(g["returnflag"]), k)
+            else:
+                assert (np.isnan(g[k]) and np.isnan(w[k])) or g[k] == w[k], (chr(g["returnflag"]), k, g[k], w[k])
+    a = [g for g in got if g["returnflag"] == ord("A")][0]
+    assert np.isinf(a["sum_qty"]) and np.isnan(a["sum_charge"])
