@@ -124,39 +124,38 @@ struct Q1Rec { Q1Slot slot[MO_Q1_MAX_GROUPS]; unsigned overflow; unsigned pad; }
 constexpr unsigned kEmptyKey = 0xffffffffu;
 constexpr int kQ1MaxGrid = 1024;  // upper bound on the grid (the last-CTA fold keeps a [grid][8] byte map in shared memory)
 
-// KEYMODE 0: packed uint8 columns; 1: MatrixOne varlena cells (24 B, inline: bs[0]=len, bs[1..]=bytes; cgo/xcall.h:33-61)
-template <int G, int UNROLL, int CTAS, int KEYMODE>
-__global__ void __launch_bounds__(kThreads, CTAS)
-q1_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty, const double *__restrict__ price,
-          const double *__restrict__ disc, const double *__restrict__ tax, const uint8_t *__restrict__ rf,
-          const uint8_t *__restrict__ ls, uint64_t n, int32_t cutoff, Q1Rec *__restrict__ partials,
-          Q1Rec *__restrict__ out, unsigned *ticket, unsigned long long *dbg) {
-    auto stamp = [&](int k) { if (dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[blockIdx.x * 16 + k] = t; } };
-    stamp(0);
-    __shared__ unsigned s_slow;
-    if (threadIdx.x == 0) s_slow = 0;
-    __shared__ unsigned dict[G];      // CTA-local key -> slot dictionary, slots handed out first-come
-    __shared__ unsigned s_overflow;
-    if (threadIdx.x < G) dict[threadIdx.x] = kEmptyKey;
-    if (threadIdx.x == 0) s_overflow = 0;
-    __syncthreads();
+// Shared state of one CTA: key -> slot dictionary (slots handed out first-come) + flags
+struct Q1Shared {
+    unsigned dict[MO_Q1_MAX_GROUPS];
+    unsigned overflow;
+    unsigned slow;   // debug: dictionary slow-path entries
+};
 
+// Per-thread aggregation state (registers).  Control flow of every method is WARP-UNIFORM: all 32 lanes call row() together
+// and the dictionary slow path is taken by the whole warp (ballot + one elected lane doing the CAS).  A first version let
+// lanes diverge inside the insert loop; some warps then never reconverged and ran ~8x slower to the end of the kernel.
+template <int G>
+struct Q1Thread {
     double acc[G][kQ1Vals];
     unsigned cnt[G];
     unsigned long long first[G];
     unsigned dk[G];  // register copy of the dictionary
+    Q1Shared *S;
+    int32_t cutoff;
+    int lane;
+    bool dbg;
+
+    __device__ __forceinline__ void init(Q1Shared *s, int32_t cut, bool debug) {
+        S = s; cutoff = cut; lane = threadIdx.x & 31; dbg = debug;
 #pragma unroll
-    for (int g = 0; g < G; g++) {
-        cnt[g] = 0; first[g] = ~0ull; dk[g] = kEmptyKey;
+        for (int g = 0; g < G; g++) {
+            cnt[g] = 0; first[g] = ~0ull; dk[g] = kEmptyKey;
 #pragma unroll
-        for (int j = 0; j < kQ1Vals; j++) acc[g][j] = 0.0;
+            for (int j = 0; j < kQ1Vals; j++) acc[g][j] = 0.0;
+        }
     }
 
-    const int lane = threadIdx.x & 31;
-    // Control flow below is WARP-UNIFORM: every lane of a warp runs the same iterations and the dictionary slow path is
-    // taken by the whole warp together (ballot + one elected lane doing the CAS).  A first version let lanes diverge inside
-    // the insert loop; some warps then never reconverged and ran ~8x slower to the end of the kernel (profiles/r01_q1_*).
-    auto find_slot = [&](unsigned key, bool valid) -> int {
+    __device__ __forceinline__ int find_slot(unsigned key, bool valid) {
         int slot = -1;
 #pragma unroll
         for (int g = 0; g < G; g++) if (dk[g] == key) slot = g;
@@ -166,18 +165,18 @@ q1_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty, const 
             const int leader = __ffs(miss) - 1;
             const unsigned lkey = __shfl_sync(0xffffffffu, key, leader);
             if (lane == leader) {   // claim or find lkey in the shared dictionary
-                if (dbg) atomicAdd(&s_slow, 1u);
+                if (dbg) atomicAdd(&S->slow, 1u);
                 bool ok = false;
 #pragma unroll 1
                 for (int g = 0; g < G; g++) {
-                    const unsigned prev = atomicCAS(&dict[g], kEmptyKey, lkey);
+                    const unsigned prev = atomicCAS(&S->dict[g], kEmptyKey, lkey);
                     if (prev == kEmptyKey || prev == lkey) { ok = true; break; }
                 }
-                if (!ok) s_overflow = 1;
+                if (!ok) S->overflow = 1;
             }
             __syncwarp();
 #pragma unroll
-            for (int g = 0; g < G; g++) dk[g] = ((volatile unsigned *)dict)[g];
+            for (int g = 0; g < G; g++) dk[g] = ((volatile unsigned *)S->dict)[g];
             slot = -1;
 #pragma unroll
             for (int g = 0; g < G; g++) if (dk[g] == key) slot = g;
@@ -185,14 +184,14 @@ q1_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty, const 
             miss = __ballot_sync(0xffffffffu, !settled);
         }
         return slot;
-    };
+    }
 
-    // every lane calls row(); `inb` = the row exists, the shipdate filter is folded into `valid`.
-    // Group dispatch without branches: acc[g][j] = fma(v_j, ind_g, acc[g][j]) with ind_g = 1.0 for the row's slot and 0.0 for
-    // the others.  fma(v, 1.0, a) == RN(v + a) (bit-identical to the reference's add) and fma(v, 0.0, a) == a for finite v,
-    // so all 32 lanes stay active (the branchy form ran at ~14 active lanes, profiles/r01_ncu_summary.md).  Rows holding
-    // Inf/NaN would poison the other groups through 0 * Inf, so a warp that sees one takes the exact predicated path.
-    auto row = [&](uint64_t r, bool inb, int32_t d, double q, double pr, double di, double tx, unsigned key) {
+    // `inb` = the row exists; the shipdate filter is folded into `valid`.
+    // Group dispatch without branches: acc[g][j] = fma(v_j, ind_g, acc[g][j]) with ind_g = 1.0 for the row's slot and 0.0 for the
+    // others.  fma(v, 1.0, a) == RN(v + a) (bit-identical to the reference's add) and fma(v, 0.0, a) == a for finite v, so all 32
+    // lanes stay active.  Rows holding Inf/NaN would poison the other groups through 0 * Inf, so a warp that sees one takes the
+    // exact predicated path.
+    __device__ __forceinline__ void row(uint64_t r, bool inb, int32_t d, double q, double pr, double di, double tx, unsigned key) {
         const bool valid = inb && d <= cutoff;        // l_shipdate <= cutoff
         const int slot = find_slot(key, valid);
         const double t1 = __dsub_rn(1.0, di);         // 1 - l_discount
@@ -227,78 +226,24 @@ q1_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty, const 
             if (m && cnt[g] == 0) first[g] = r;       // a thread visits its rows in increasing order
             cnt[g] += m;
         }
-    };
+    }
+};
 
-    auto load_keys = [&](uint64_t pair, unsigned &k0, unsigned &k1) {
-        if (KEYMODE == 0) {
-            unsigned short a = __ldg(reinterpret_cast<const unsigned short *>(rf) + pair);
-            unsigned short b = __ldg(reinterpret_cast<const unsigned short *>(ls) + pair);
-            k0 = (a & 0xffu) | ((b & 0xffu) << 8);
-            k1 = (a >> 8) | ((b >> 8) << 8);
-        } else {
-            // head 8 bytes of each 24-byte cell hold len + first chars; empty string (len 0) keys as 0
-            const uint64_t r0 = 2 * pair;
-            uint2 a0 = __ldg(reinterpret_cast<const uint2 *>(rf + 24 * r0)), a1 = __ldg(reinterpret_cast<const uint2 *>(rf + 24 * (r0 + 1)));
-            uint2 b0 = __ldg(reinterpret_cast<const uint2 *>(ls + 24 * r0)), b1 = __ldg(reinterpret_cast<const uint2 *>(ls + 24 * (r0 + 1)));
-            auto ch = [](uint2 h) -> unsigned { return (h.x & 0xffu) ? ((h.x >> 8) & 0xffu) : 0u; };
-            k0 = ch(a0) | (ch(b0) << 8);
-            k1 = ch(a1) | (ch(b1) << 8);
-        }
-    };
+// key of one row: packed uint8 columns (KEYMODE 0) or MatrixOne varlena cells (KEYMODE 1: 24 B, inline: bs[0]=len,
+// bs[1..]=bytes; cgo/xcall.h:33-61); an empty string keys as 0
+template <int KEYMODE>
+__device__ __forceinline__ unsigned q1_key_scalar(const uint8_t *rf, const uint8_t *ls, uint64_t r) {
+    if (KEYMODE == 0) return rf[r] | ((unsigned)ls[r] << 8);
+    return (rf[24 * r] ? rf[24 * r + 1] : 0u) | ((ls[24 * r] ? (unsigned)ls[24 * r + 1] : 0u) << 8);
+}
 
-    const uint64_t npairs = n >> 1;
-    const uint64_t tid = blockIdx.x * (uint64_t)kThreads + threadIdx.x;
-    const uint64_t nthreads = (uint64_t)gridDim.x * kThreads;
-    const uint64_t wbase = tid - lane;   // first pair of this warp: loop bounds depend on it only => uniform per warp
-    uint64_t pw = wbase;
-    for (; pw + 31 + (UNROLL - 1) * nthreads < npairs; pw += UNROLL * nthreads) {   // all 32 lanes x UNROLL pairs in range
-        int2 d[UNROLL]; int4 a[UNROLL], b[UNROLL], c[UNROLL], e[UNROLL]; unsigned k0[UNROLL], k1[UNROLL];
-#pragma unroll
-        for (int k = 0; k < UNROLL; k++) {
-            const uint64_t q = pw + lane + k * nthreads;
-            d[k] = ld_stream8(sd + 2 * q);
-            a[k] = ld_stream16(qty + 2 * q);
-            b[k] = ld_stream16(price + 2 * q);
-            c[k] = ld_stream16(disc + 2 * q);
-            e[k] = ld_stream16(tax + 2 * q);
-            load_keys(q, k0[k], k1[k]);
-        }
-#pragma unroll
-        for (int k = 0; k < UNROLL; k++) {
-            const uint64_t q = pw + lane + k * nthreads;
-            double qq[2], pr[2], di[2], tx[2];
-            memcpy(qq, &a[k], 16); memcpy(pr, &b[k], 16); memcpy(di, &c[k], 16); memcpy(tx, &e[k], 16);
-            row(2 * q, true, d[k].x, qq[0], pr[0], di[0], tx[0], k0[k]);
-            row(2 * q + 1, true, d[k].y, qq[1], pr[1], di[1], tx[1], k1[k]);
-        }
-    }
-    for (; pw < npairs; pw += nthreads) {   // ragged end: same code, lanes past the end carry inb = false
-        const uint64_t q = pw + lane;
-        const bool inb = q < npairs;
-        int2 d = make_int2(0, 0); int4 a = make_int4(0, 0, 0, 0), b = a, c = a, e = a; unsigned k0 = 0, k1 = 0;
-        if (inb) {
-            d = ld_stream8(sd + 2 * q);
-            a = ld_stream16(qty + 2 * q); b = ld_stream16(price + 2 * q); c = ld_stream16(disc + 2 * q); e = ld_stream16(tax + 2 * q);
-            load_keys(q, k0, k1);
-        }
-        double qq[2], pr[2], di[2], tx[2];
-        memcpy(qq, &a, 16); memcpy(pr, &b, 16); memcpy(di, &c, 16); memcpy(tx, &e, 16);
-        row(2 * q, inb, d.x, qq[0], pr[0], di[0], tx[0], k0);
-        row(2 * q + 1, inb, d.y, qq[1], pr[1], di[1], tx[1], k1);
-    }
-    if (tid < 32) {   // odd tail row: handled by warp 0 of CTA 0, lane 0 carries it
-        const bool has = (n & 1) && lane == 0;
-        const uint64_t r = n - 1;
-        unsigned key = 0; int32_t dd = 0; double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-        if (has) {
-            if (KEYMODE == 0) key = rf[r] | ((unsigned)ls[r] << 8);
-            else key = (rf[24 * r] ? rf[24 * r + 1] : 0u) | ((ls[24 * r] ? (unsigned)ls[24 * r + 1] : 0u) << 8);
-            dd = sd[r]; v0 = qty[r]; v1 = price[r]; v2 = disc[r]; v3 = tax[r];
-        }
-        row(r, has, dd, v0, v1, v2, v3, key);
-    }
+// CTA reduction + last-CTA fold, shared by both kernels.  kT = threads per CTA.
+template <int G, int kT>
+__device__ void q1_epilogue(Q1Thread<G> &T, Q1Shared &S, Q1Rec *__restrict__ partials, Q1Rec *__restrict__ out, unsigned *ticket,
+                            unsigned long long *dbg) {
+    auto stamp = [&](int k) { if (dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[blockIdx.x * 16 + k] = t; } };
     stamp(1);
-    if (dbg && (threadIdx.x & 31) == 0) {
+    if (dbg && (threadIdx.x & 31) == 0 && (threadIdx.x >> 5) < 8) {
         unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
         unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
         dbg[blockIdx.x * 16 + 8 + (threadIdx.x >> 5)] = tt;
@@ -306,22 +251,22 @@ q1_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty, const 
     }
     __syncthreads();  // dictionary final
     stamp(2);
-    if (dbg && threadIdx.x == 0) dbg[blockIdx.x * 16 + 7] = s_slow;
-
-    // ---- CTA reduction.  Register slots are indexed by the CTA dictionary, identical for every thread of the CTA.
-    __shared__ double sv[kThreads / 32][G][kQ1Vals];
-    __shared__ unsigned long long scnt[kThreads / 32][G], sfirst[kThreads / 32][G];
+    if (dbg && threadIdx.x == 0) dbg[blockIdx.x * 16 + 7] = S.slow;
+    // Register slots are indexed by the CTA dictionary, identical for every thread of the CTA.
+    constexpr int kW = kT / 32;
+    __shared__ double sv[kW][G][kQ1Vals];
+    __shared__ unsigned long long scnt[kW][G], sfirst[kW][G];
     __shared__ bool last;
-    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int g = 0; g < G; g++) {
-        unsigned long long c64 = cnt[g], f = first[g];
+        unsigned long long c64 = T.cnt[g], f = T.first[g];
         c64 = warp_sum(c64);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { unsigned long long of = __shfl_xor_sync(0xffffffffu, f, o); f = of < f ? of : f; }
 #pragma unroll
         for (int j = 0; j < kQ1Vals; j++) {
-            double v = warp_sum_f64(acc[g][j]);
+            double v = warp_sum_f64(T.acc[g][j]);
             if (lane == 0) sv[warp][g][j] = v;
         }
         if (lane == 0) { scnt[warp][g] = c64; sfirst[warp][g] = f; }
@@ -330,9 +275,9 @@ q1_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty, const 
     if (threadIdx.x == 0) {
         Q1Rec &R = partials[blockIdx.x];
         for (int g = 0; g < G; g++) {
-            Q1Slot s; s.cnt = 0; s.first_row = ~0ull; s.key = dict[g]; s.used = dict[g] != kEmptyKey;
+            Q1Slot s; s.cnt = 0; s.first_row = ~0ull; s.key = S.dict[g]; s.used = S.dict[g] != kEmptyKey;
             for (int j = 0; j < kQ1Vals; j++) s.v[j] = 0.0;
-            for (int w = 0; w < kThreads / 32; w++) {
+            for (int w = 0; w < kW; w++) {
                 s.cnt += scnt[w][g];
                 if (sfirst[w][g] < s.first_row) s.first_row = sfirst[w][g];
                 for (int j = 0; j < kQ1Vals; j++) s.v[j] = __dadd_rn(s.v[j], sv[w][g][j]);
@@ -340,7 +285,7 @@ q1_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty, const 
             R.slot[g] = s;
         }
         for (int g = G; g < MO_Q1_MAX_GROUPS; g++) { Q1Slot z; memset(&z, 0, sizeof z); z.key = kEmptyKey; R.slot[g] = z; }
-        R.overflow = s_overflow; R.pad = 0;
+        R.overflow = S.overflow; R.pad = 0;
         __threadfence();
         unsigned tk = atomicInc(ticket, gridDim.x - 1);
         last = (tk == gridDim.x - 1);
@@ -358,9 +303,9 @@ q1_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty, const 
         __shared__ unsigned f_overflow;
         if (threadIdx.x < MO_Q1_MAX_GROUPS) fdict[threadIdx.x] = kEmptyKey;
         if (threadIdx.x == 0) f_overflow = 0;
-        for (unsigned i = threadIdx.x; i < gridDim.x * MO_Q1_MAX_GROUPS; i += kThreads) inv[i / MO_Q1_MAX_GROUPS][i % MO_Q1_MAX_GROUPS] = 0xff;
+        for (unsigned i = threadIdx.x; i < gridDim.x * MO_Q1_MAX_GROUPS; i += kT) inv[i / MO_Q1_MAX_GROUPS][i % MO_Q1_MAX_GROUPS] = 0xff;
         __syncthreads();
-        for (unsigned bIdx = threadIdx.x; bIdx < gridDim.x; bIdx += kThreads) {
+        for (unsigned bIdx = threadIdx.x; bIdx < gridDim.x; bIdx += kT) {
             const Q1Rec &R = partials[bIdx];
             if (R.overflow) f_overflow = 1;
 #pragma unroll
@@ -399,6 +344,187 @@ q1_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty, const 
         __syncthreads();
         stamp(4);
     }
+}
+
+// ---- variant A: direct register-staged loads (pairs of rows, UNROLL pairs in flight per thread) -------------------------
+template <int G, int UNROLL, int CTAS, int KEYMODE>
+__global__ void __launch_bounds__(kThreads, CTAS)
+q1_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty, const double *__restrict__ price,
+          const double *__restrict__ disc, const double *__restrict__ tax, const uint8_t *__restrict__ rf,
+          const uint8_t *__restrict__ ls, uint64_t n, int32_t cutoff, Q1Rec *__restrict__ partials,
+          Q1Rec *__restrict__ out, unsigned *ticket, unsigned long long *dbg) {
+    if (dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[blockIdx.x * 16] = t; }
+    __shared__ Q1Shared S;
+    if (threadIdx.x < MO_Q1_MAX_GROUPS) S.dict[threadIdx.x] = kEmptyKey;
+    if (threadIdx.x == 0) { S.overflow = 0; S.slow = 0; }
+    __syncthreads();
+    Q1Thread<G> T;
+    T.init(&S, cutoff, dbg != nullptr);
+    const int lane = threadIdx.x & 31;
+
+    auto load_keys = [&](uint64_t pair, unsigned &k0, unsigned &k1) {
+        if (KEYMODE == 0) {
+            unsigned short a = __ldg(reinterpret_cast<const unsigned short *>(rf) + pair);
+            unsigned short b = __ldg(reinterpret_cast<const unsigned short *>(ls) + pair);
+            k0 = (a & 0xffu) | ((b & 0xffu) << 8);
+            k1 = (a >> 8) | ((b >> 8) << 8);
+        } else {
+            const uint64_t r0 = 2 * pair;   // head 8 bytes of each 24-byte cell hold len + first chars
+            uint2 a0 = __ldg(reinterpret_cast<const uint2 *>(rf + 24 * r0)), a1 = __ldg(reinterpret_cast<const uint2 *>(rf + 24 * (r0 + 1)));
+            uint2 b0 = __ldg(reinterpret_cast<const uint2 *>(ls + 24 * r0)), b1 = __ldg(reinterpret_cast<const uint2 *>(ls + 24 * (r0 + 1)));
+            auto ch = [](uint2 h) -> unsigned { return (h.x & 0xffu) ? ((h.x >> 8) & 0xffu) : 0u; };
+            k0 = ch(a0) | (ch(b0) << 8);
+            k1 = ch(a1) | (ch(b1) << 8);
+        }
+    };
+
+    const uint64_t npairs = n >> 1;
+    const uint64_t tid = blockIdx.x * (uint64_t)kThreads + threadIdx.x;
+    const uint64_t nthreads = (uint64_t)gridDim.x * kThreads;
+    const uint64_t wbase = tid - lane;   // first pair of this warp: loop bounds depend on it only => uniform per warp
+    uint64_t pw = wbase;
+    for (; pw + 31 + (UNROLL - 1) * nthreads < npairs; pw += UNROLL * nthreads) {   // all 32 lanes x UNROLL pairs in range
+        int2 d[UNROLL]; int4 a[UNROLL], b[UNROLL], c[UNROLL], e[UNROLL]; unsigned k0[UNROLL], k1[UNROLL];
+#pragma unroll
+        for (int k = 0; k < UNROLL; k++) {
+            const uint64_t q = pw + lane + k * nthreads;
+            d[k] = ld_stream8(sd + 2 * q);
+            a[k] = ld_stream16(qty + 2 * q);
+            b[k] = ld_stream16(price + 2 * q);
+            c[k] = ld_stream16(disc + 2 * q);
+            e[k] = ld_stream16(tax + 2 * q);
+            load_keys(q, k0[k], k1[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < UNROLL; k++) {
+            const uint64_t q = pw + lane + k * nthreads;
+            double qq[2], pr[2], di[2], tx[2];
+            memcpy(qq, &a[k], 16); memcpy(pr, &b[k], 16); memcpy(di, &c[k], 16); memcpy(tx, &e[k], 16);
+            T.row(2 * q, true, d[k].x, qq[0], pr[0], di[0], tx[0], k0[k]);
+            T.row(2 * q + 1, true, d[k].y, qq[1], pr[1], di[1], tx[1], k1[k]);
+        }
+    }
+    for (; pw < npairs; pw += nthreads) {   // ragged end: same code, lanes past the end carry inb = false
+        const uint64_t q = pw + lane;
+        const bool inb = q < npairs;
+        int2 d = make_int2(0, 0); int4 a = make_int4(0, 0, 0, 0), b = a, c = a, e = a; unsigned k0 = 0, k1 = 0;
+        if (inb) {
+            d = ld_stream8(sd + 2 * q);
+            a = ld_stream16(qty + 2 * q); b = ld_stream16(price + 2 * q); c = ld_stream16(disc + 2 * q); e = ld_stream16(tax + 2 * q);
+            load_keys(q, k0, k1);
+        }
+        double qq[2], pr[2], di[2], tx[2];
+        memcpy(qq, &a, 16); memcpy(pr, &b, 16); memcpy(di, &c, 16); memcpy(tx, &e, 16);
+        T.row(2 * q, inb, d.x, qq[0], pr[0], di[0], tx[0], k0);
+        T.row(2 * q + 1, inb, d.y, qq[1], pr[1], di[1], tx[1], k1);
+    }
+    if (tid < 32) {   // odd tail row: handled by warp 0 of CTA 0, lane 0 carries it
+        const bool has = (n & 1) && lane == 0;
+        const uint64_t r = n - 1;
+        unsigned key = 0; int32_t dd = 0; double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+        if (has) { key = q1_key_scalar<KEYMODE>(rf, ls, r); dd = sd[r]; v0 = qty[r]; v1 = price[r]; v2 = disc[r]; v3 = tax[r]; }
+        T.row(r, has, dd, v0, v1, v2, v3, key);
+    }
+    q1_epilogue<G, kThreads>(T, S, partials, out, ticket, dbg);
+}
+
+// ---- variant B: cp.async-staged tiles (packed keys only) ----------------------------------------------------------------
+// Each warp owns a ring of kStages tiles of 64 rows in shared memory.  The 64-row slices of the seven columns are copied with
+// per-lane cp.async (LDGSTS): 8 B/lane for the int32 column, 16 B/lane for each float64 column, 4 B/lane (half a warp) for each
+// key column -- every copy instruction covers whole 32-byte sectors.  Bytes in flight per SM = warps x kStages x 2432 B,
+// independent of the register file, so the loads of tile i+kStages-1 are in the air while tile i is reduced: the register
+// version above could keep only ~78 KB per SM in flight and stalled on HBM latency (profiles/r01_ncu_summary.md).
+// No CTA barriers in the steady state: a warp waits for ITS oldest copy group (cp.async.wait_group) and __syncwarp()s.
+constexpr int kTileRows = 64;
+constexpr int kTileBytes = kTileRows * 38;   // 256 (shipdate) + 4 x 512 + 2 x 64 = 2432
+constexpr int kStagedThreads = 512;
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int G, int kStages>
+__global__ void __launch_bounds__(kStagedThreads, 1)
+q1_staged_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty, const double *__restrict__ price,
+                 const double *__restrict__ disc, const double *__restrict__ tax, const uint8_t *__restrict__ rf,
+                 const uint8_t *__restrict__ ls, uint64_t n, int32_t cutoff, Q1Rec *__restrict__ partials,
+                 Q1Rec *__restrict__ out, unsigned *ticket, unsigned long long *dbg) {
+    extern __shared__ __align__(16) unsigned char ring[];   // [warp][stage][kTileBytes]
+    if (dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[blockIdx.x * 16] = t; }
+    __shared__ Q1Shared S;
+    if (threadIdx.x < MO_Q1_MAX_GROUPS) S.dict[threadIdx.x] = kEmptyKey;
+    if (threadIdx.x == 0) { S.overflow = 0; S.slow = 0; }
+    __syncthreads();
+    Q1Thread<G> T;
+    T.init(&S, cutoff, dbg != nullptr);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int kWarps = kStagedThreads / 32;
+    unsigned char *wring = ring + (size_t)warp * kStages * kTileBytes;
+    const uint64_t ntiles = n / kTileRows;
+    const uint64_t gw = blockIdx.x * (uint64_t)kWarps + warp, nw = (uint64_t)gridDim.x * kWarps;
+
+    auto issue = [&](uint64_t tile, int stage) {   // all lanes; one commit group per tile
+        unsigned char *s = wring + stage * kTileBytes;
+        const uint64_t r0 = tile * kTileRows;
+        cp_async8(s + lane * 8, sd + r0 + lane * 2);
+        cp_async16(s + 256 + lane * 16, qty + r0 + lane * 2);
+        cp_async16(s + 768 + lane * 16, price + r0 + lane * 2);
+        cp_async16(s + 1280 + lane * 16, disc + r0 + lane * 2);
+        cp_async16(s + 1792 + lane * 16, tax + r0 + lane * 2);
+        if (lane < 16) { cp_async4(s + 2304 + lane * 4, rf + r0 + lane * 4); cp_async4(s + 2368 + lane * 4, ls + r0 + lane * 4); }
+        cp_async_commit();
+    };
+
+    // prologue: kStages - 1 tiles in flight (empty groups keep the group arithmetic uniform when tiles run out)
+    uint64_t next = gw;
+#pragma unroll
+    for (int s = 0; s < kStages - 1; s++) {
+        if (next < ntiles) issue(next, s); else cp_async_commit();
+        next += nw;
+    }
+    int stage = 0;
+    for (uint64_t tile = gw; tile < ntiles; tile += nw) {
+        // refill the slot consumed in the previous iteration, then wait for the oldest group
+        const int fill = (stage + kStages - 1) % kStages;
+        if (next < ntiles) issue(next, fill); else cp_async_commit();
+        next += nw;
+        cp_async_wait<kStages - 1>();
+        __syncwarp();
+        const unsigned char *s = wring + stage * kTileBytes;
+        const uint64_t r0 = tile * kTileRows;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {   // lane handles rows lane and lane + 32 of the tile: conflict-free LDS
+            const int rl = lane + 32 * h;
+            const int32_t d = *reinterpret_cast<const int32_t *>(s + rl * 4);
+            const double q = *reinterpret_cast<const double *>(s + 256 + rl * 8);
+            const double pr = *reinterpret_cast<const double *>(s + 768 + rl * 8);
+            const double di = *reinterpret_cast<const double *>(s + 1280 + rl * 8);
+            const double tx = *reinterpret_cast<const double *>(s + 1792 + rl * 8);
+            const unsigned key = (unsigned)s[2304 + rl] | ((unsigned)s[2368 + rl] << 8);
+            T.row(r0 + rl, true, d, q, pr, di, tx, key);
+        }
+        __syncwarp();   // every lane is done with this slot before any lane's next cp.async overwrites it
+        stage = (stage + 1) % kStages;
+    }
+    cp_async_wait<0>();
+    // rows past the last full tile (< 64): warp 0 of CTA 0, direct loads
+    if (blockIdx.x == 0 && warp == 0) {
+        for (uint64_t r = ntiles * kTileRows + lane; r - lane < n; r += 32) {
+            const bool has = r < n;
+            unsigned key = 0; int32_t dd = 0; double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+            if (has) { key = q1_key_scalar<0>(rf, ls, r); dd = sd[r]; v0 = qty[r]; v1 = price[r]; v2 = disc[r]; v3 = tax[r]; }
+            T.row(r, has, dd, v0, v1, v2, v3, key);
+        }
+    }
+    q1_epilogue<G, kStagedThreads>(T, S, partials, out, ticket, dbg);
 }
 
 void q1_finalize(const Q1Rec &F, mo_q1_result_t *res) {
@@ -539,20 +665,38 @@ static int launch_q1(ThreadCtx &t, const int32_t *sd, const double *qty, const d
         !aligned_to(rf, KEYMODE ? 8 : 2) || !aligned_to(ls, KEYMODE ? 8 : 2)) {
         set_error("q1: columns must be 16-byte aligned (int32 column 8-byte, key columns 2/8-byte)"); return MO_RC_INVALID_ARGUMENT;
     }
+    // variant: 0 = auto (cp.async-staged kernel for packed keys, register kernel otherwise), 1 = register kernel, 2 = register
+    // kernel with 8 group slots, 3 = staged with 3 stages, 4 = staged with 5 stages
+    const bool can_stage = KEYMODE == 0 && aligned_to(sd, 16) && aligned_to(rf, 16) && aligned_to(ls, 16) && n >= kTileRows;
     for (int attempt = 0; attempt < 2; attempt++) {
         const bool wide = attempt == 1 || g_q1_variant == 2;
-        int ctas = 2;
-        int grid = num_sms() * ctas;
-        uint64_t work = (n / 2 + kThreads - 1) / kThreads;
+        const bool staged = can_stage && !wide && g_q1_variant != 1;
+        int grid = num_sms() * (staged ? 1 : 2);
+        const int threads = staged ? kStagedThreads : kThreads;
+        uint64_t work = staged ? (n / kTileRows + (kStagedThreads / 32) - 1) / (kStagedThreads / 32) : (n / 2 + kThreads - 1) / kThreads;
         if ((uint64_t)grid > work) grid = work ? (int)work : 1;
         if (grid > kQ1MaxGrid) grid = kQ1MaxGrid;
+        (void)threads;
         Q1Rec *partials = (Q1Rec *)arena_alloc(t, sizeof(Q1Rec) * (size_t)(grid + 1));
         if (!partials) return MO_RC_INTERNAL_ERROR;
         Q1Rec *out = partials + grid;
         cudaEventRecord(t.kev0, t.stream);
-        if (!wide) {
-            if (g_q1_variant == 1) q1_kernel<4, 4, 2, KEYMODE><<<grid, kThreads, 0, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg);
-            else q1_kernel<4, 2, 2, KEYMODE><<<grid, kThreads, 0, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg);
+        if (staged) {
+            const int stages = g_q1_variant == 3 ? 3 : (g_q1_variant == 4 ? 5 : 4);
+            const size_t smem = (size_t)(kStagedThreads / 32) * stages * kTileBytes;
+            static bool attr_done[3] = {false, false, false};
+            if (!attr_done[stages - 3]) {
+                cudaError_t e = stages == 3 ? cudaFuncSetAttribute(q1_staged_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                              : stages == 4 ? cudaFuncSetAttribute(q1_staged_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                            : cudaFuncSetAttribute(q1_staged_kernel<4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) { set_error("q1: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return MO_RC_INTERNAL_ERROR; }
+                attr_done[stages - 3] = true;
+            }
+            if (stages == 3) q1_staged_kernel<4, 3><<<grid, kStagedThreads, smem, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg);
+            else if (stages == 4) q1_staged_kernel<4, 4><<<grid, kStagedThreads, smem, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg);
+            else q1_staged_kernel<4, 5><<<grid, kStagedThreads, smem, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg);
+        } else if (!wide) {
+            q1_kernel<4, 2, 2, KEYMODE><<<grid, kThreads, 0, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg);
         } else {
             q1_kernel<8, 2, 2, KEYMODE><<<grid, kThreads, 0, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg);
         }

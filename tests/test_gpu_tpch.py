@@ -154,7 +154,7 @@ def test_kernel_variants_agree(gpu):
             base = base or r
             assert r[1] == base[1] and abs(r[0] - base[0]) <= 1e-12 * abs(base[0])
         want = O.q1(cols, n, datagen.Q1_CUTOFF)
-        for var in (0, 1, 2):
+        for var in (0, 1, 2, 3, 4):
             gpu.MoB200_SetTuning(b"q1_variant", var)
             _check_q1(ops.q1_group_agg(cols["shipdate"], cols["quantity"], cols["extendedprice"], cols["discount"], cols["tax"],
                                        cols["returnflag"], cols["linestatus"], n, datagen.Q1_CUTOFF), want)

@@ -65,7 +65,7 @@ def main():
                 report("q6", ms, best, 28.0 * n, variant=var, rows=n, Grows_per_s=round(n / ms / 1e6, 2))
             lib.MoB200_SetTuning(b"q6_variant", 0)
         if "q1" in which:
-            for var in (0, 1, 2):
+            for var in (0, 1, 3, 4):
                 lib.MoB200_SetTuning(b"q1_variant", var)
                 ms, best = timed(lambda: ops.q1_group_agg(b["shipdate"], b["quantity"], b["extendedprice"], b["discount"], b["tax"],
                                                           b["returnflag"], b["linestatus"], n, datagen.Q1_CUTOFF))
