@@ -164,16 +164,16 @@ struct Q1Thread {
         while (miss) {
             const int leader = __ffs(miss) - 1;
             const unsigned lkey = __shfl_sync(0xffffffffu, key, leader);
-            if (lane == leader) {   // claim or find lkey in the shared dictionary
-                if (dbg) atomicAdd(&S->slow, 1u);
-                bool ok = false;
-#pragma unroll 1
-                for (int g = 0; g < G; g++) {
-                    const unsigned prev = atomicCAS(&S->dict[g], kEmptyKey, lkey);
-                    if (prev == kEmptyKey || prev == lkey) { ok = true; break; }
-                }
-                if (!ok) S->overflow = 1;
+            // Claim or find lkey in the shared dictionary.  EVERY lane issues the same idempotent CAS sequence (same address,
+            // same value): an elected-lane `if (lane == leader) { loop }` left the warp split in two groups for the rest of
+            // the kernel (ncu: 16.0 active threads per instruction, profiles/r01_ncu_summary.md), doubling the issue cost.
+            bool ok = false;
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const unsigned prev = ok ? lkey : atomicCAS(&S->dict[g], kEmptyKey, lkey);
+                ok = ok || prev == kEmptyKey || prev == lkey;
             }
+            if (!ok) S->overflow = 1;
             __syncwarp();
 #pragma unroll
             for (int g = 0; g < G; g++) dk[g] = ((volatile unsigned *)S->dict)[g];
@@ -201,16 +201,15 @@ struct Q1Thread {
         const bool finite = (fabs(t4) + fabs(q)) < INFINITY;   // false for any Inf/NaN among q, pr, di, tx (and on overflow)
         if (__any_sync(0xffffffffu, valid && !finite)) {
 #pragma unroll
-            for (int g = 0; g < G; g++) {
-                if (valid && slot == g) {
-                    acc[g][0] = __dadd_rn(acc[g][0], q);
-                    acc[g][1] = __dadd_rn(acc[g][1], pr);
-                    acc[g][2] = __dadd_rn(acc[g][2], t2);
-                    acc[g][3] = __dadd_rn(acc[g][3], t4);
-                    acc[g][4] = __dadd_rn(acc[g][4], di);
-                    if (cnt[g] == 0) first[g] = r;
-                    cnt[g] += 1;
-                }
+            for (int g = 0; g < G; g++) {   // selects, not branches: lanes must not diverge here either
+                const bool m = valid && slot == g;
+                acc[g][0] = m ? __dadd_rn(acc[g][0], q) : acc[g][0];
+                acc[g][1] = m ? __dadd_rn(acc[g][1], pr) : acc[g][1];
+                acc[g][2] = m ? __dadd_rn(acc[g][2], t2) : acc[g][2];
+                acc[g][3] = m ? __dadd_rn(acc[g][3], t4) : acc[g][3];
+                acc[g][4] = m ? __dadd_rn(acc[g][4], di) : acc[g][4];
+                if (m && cnt[g] == 0) first[g] = r;
+                cnt[g] += m;
             }
             return;
         }
@@ -355,8 +354,8 @@ q1_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty, const 
           Q1Rec *__restrict__ out, unsigned *ticket, unsigned long long *dbg) {
     if (dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[blockIdx.x * 16] = t; }
     __shared__ Q1Shared S;
-    if (threadIdx.x < MO_Q1_MAX_GROUPS) S.dict[threadIdx.x] = kEmptyKey;
-    if (threadIdx.x == 0) { S.overflow = 0; S.slow = 0; }
+    S.dict[threadIdx.x & (MO_Q1_MAX_GROUPS - 1)] = kEmptyKey;   // all threads write (same values): no lane-dependent branch
+    S.overflow = 0; S.slow = 0;
     __syncthreads();
     Q1Thread<G> T;
     T.init(&S, cutoff, dbg != nullptr);
@@ -460,8 +459,8 @@ q1_staged_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty,
     extern __shared__ __align__(16) unsigned char ring[];   // [warp][stage][kTileBytes]
     if (dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[blockIdx.x * 16] = t; }
     __shared__ Q1Shared S;
-    if (threadIdx.x < MO_Q1_MAX_GROUPS) S.dict[threadIdx.x] = kEmptyKey;
-    if (threadIdx.x == 0) { S.overflow = 0; S.slow = 0; }
+    S.dict[threadIdx.x & (MO_Q1_MAX_GROUPS - 1)] = kEmptyKey;   // all threads write (same values): no lane-dependent branch
+    S.overflow = 0; S.slow = 0;
     __syncthreads();
     Q1Thread<G> T;
     T.init(&S, cutoff, dbg != nullptr);
@@ -479,7 +478,9 @@ q1_staged_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty,
         cp_async16(s + 768 + lane * 16, price + r0 + lane * 2);
         cp_async16(s + 1280 + lane * 16, disc + r0 + lane * 2);
         cp_async16(s + 1792 + lane * 16, tax + r0 + lane * 2);
-        if (lane < 16) { cp_async4(s + 2304 + lane * 4, rf + r0 + lane * 4); cp_async4(s + 2368 + lane * 4, ls + r0 + lane * 4); }
+        // keys: lanes 0-15 copy the returnflag slice, lanes 16-31 the linestatus slice (address select, no branch); the
+        // linestatus area follows the returnflag area so one destination expression serves both
+        cp_async4(s + 2304 + lane * 4, (lane < 16 ? rf + r0 + lane * 4 : ls + r0 + (lane - 16) * 4));
         cp_async_commit();
     };
 
@@ -665,8 +666,8 @@ static int launch_q1(ThreadCtx &t, const int32_t *sd, const double *qty, const d
         !aligned_to(rf, KEYMODE ? 8 : 2) || !aligned_to(ls, KEYMODE ? 8 : 2)) {
         set_error("q1: columns must be 16-byte aligned (int32 column 8-byte, key columns 2/8-byte)"); return MO_RC_INVALID_ARGUMENT;
     }
-    // variant: 0 = auto (cp.async-staged kernel for packed keys, register kernel otherwise), 1 = register kernel, 2 = register
-    // kernel with 8 group slots, 3 = staged with 3 stages, 4 = staged with 5 stages
+    // variant: 0 = auto (cp.async-staged kernel, 3 stages, for packed keys; register kernel otherwise), 1 = register kernel,
+    // 2 = register kernel with 8 group slots, 3 = staged with 4 stages, 4 = staged with 5 stages
     const bool can_stage = KEYMODE == 0 && aligned_to(sd, 16) && aligned_to(rf, 16) && aligned_to(ls, 16) && n >= kTileRows;
     for (int attempt = 0; attempt < 2; attempt++) {
         const bool wide = attempt == 1 || g_q1_variant == 2;
@@ -682,7 +683,7 @@ static int launch_q1(ThreadCtx &t, const int32_t *sd, const double *qty, const d
         Q1Rec *out = partials + grid;
         cudaEventRecord(t.kev0, t.stream);
         if (staged) {
-            const int stages = g_q1_variant == 3 ? 3 : (g_q1_variant == 4 ? 5 : 4);
+            const int stages = g_q1_variant == 3 ? 4 : (g_q1_variant == 4 ? 5 : 3);   // 3 stages measured best (tools/tune.py q1)
             const size_t smem = (size_t)(kStagedThreads / 32) * stages * kTileBytes;
             static bool attr_done[3] = {false, false, false};
             if (!attr_done[stages - 3]) {

@@ -95,11 +95,13 @@ def test_q1_matches_oracle_packed_and_varlena_keys(gpu, n):
     _check_q1(got, want)
     rf = varlena_char1_column(cols["returnflag"]); ls = varlena_char1_column(cols["linestatus"])    # MatrixOne varlena layout
     got_v = ops.q1_group_agg(cols["shipdate"], cols["quantity"], cols["extendedprice"], cols["discount"], cols["tax"], rf, ls, n, datagen.Q1_CUTOFF)
-    assert got_v == got
+    _check_q1(got_v, want)       # varlena keys run the register kernel, packed keys the cp.async-staged one: same values to 1e-11
     bufs = dev_lineitem(gpu, 11, n)
     got_d = ops.q1_group_agg(bufs["shipdate"], bufs["quantity"], bufs["extendedprice"], bufs["discount"], bufs["tax"],
                              bufs["returnflag"], bufs["linestatus"], n, datagen.Q1_CUTOFF)
-    assert got_d == got
+    assert got_d == got           # resident vs staged-from-host: same kernel, same grid => bitwise equal
+    assert got_d == ops.q1_group_agg(bufs["shipdate"], bufs["quantity"], bufs["extendedprice"], bufs["discount"], bufs["tax"],
+                                     bufs["returnflag"], bufs["linestatus"], n, datagen.Q1_CUTOFF)   # run-to-run deterministic
     for b in bufs.values():
         b.free()
 
