@@ -50,7 +50,7 @@ def env_int(name, default):
 
 class ClockSampler:
     """nvidia-smi clocks during the timed region (B200_PROFILING.md recipe)"""
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
@@ -59,7 +59,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -70,7 +70,9 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """t_begin / t_end: wall-clock (time.time()) bounds of the timed region; samples outside are dropped"""
+        import datetime
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -84,6 +86,10 @@ class ClockSampler:
             if len(f) < 9:
                 continue
             try:
+                if t_begin is not None:
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    if ts < t_begin - 0.02 or ts > t_end + 0.02:
+                        continue
                 sm.append(float(f[1])); mx.append(float(f[2]))
             except ValueError:
                 continue
@@ -162,7 +168,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="q6", choices=sorted(WORKLOADS))
@@ -281,12 +287,15 @@ def main():
         return merge(gather_buf.cpu().numpy().tobytes())
 
     # ---------------------------------------------------------------------------------------------- resident timing
-    for _ in range(W):
-        exchange(step())
-    barrier_sync()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()          # started before the warm-up: nvidia-smi needs ~100 ms to deliver its first sample
+    for _ in range(W):
+        exchange(step())
+    if rank == 0:
+        time.sleep(0.25)
+    barrier_sync()
+    t_region0 = time.time()
     launches0 = lib.MoB200_KernelLaunchCount()
     kernel_ms = []
     kms = C.c_float()
@@ -301,7 +310,7 @@ def main():
     barrier_sync()
     wall_ms = (time.perf_counter() - t_wall0) * 1e3
     launches = lib.MoB200_KernelLaunchCount() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_region0, time.time()) if rank == 0 else None
     total_ms = max_over_ranks(max(ms.value, 0.0))
     ms_per_step = total_ms / K
     value = units * world * K / (total_ms * 1e-3)
@@ -399,4 +408,20 @@ def main():
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    # stdout carries exactly ONE JSON line: library chatter (NCCL version banners, torchrun notices) is sent to stderr by
+    # pointing fd 1 at fd 2 for the run and printing the result line to the saved descriptor.
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    _buf = []
+    _print = print
+
+    def print(*a, **k):  # noqa: A001  (only the JSON line goes through here)
+        _buf.append(" ".join(str(x) for x in a))
+
+    rc = main()
+    sys.stdout.flush()
+    os.dup2(_real_stdout, 1)
+    for line in _buf:
+        os.write(1, (line + "\n").encode())
+    sys.exit(rc)
