@@ -426,6 +426,10 @@ int bruteforce_topk_device(ThreadCtx &t, const float *ddata, int64_t n, int dim,
     return MO_RC_SUCCESS;
 }
 
+bool tc_search_applicable(int64_t n, int dim, int64_t nq, int k, int metric);
+int bruteforce_topk_tc_device(ThreadCtx &t, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq, int k,
+                              int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d, float *dbg_scores);
+
 int xcall_bruteforce(mo_xcall_args_t *args, uint64_t len) {
     ThreadCtx &t = tctx();
     if (!t.ready) return MO_RC_INTERNAL_ERROR;
@@ -444,7 +448,10 @@ int xcall_bruteforce(mo_xcall_args_t *args, uint64_t len) {
     int64_t *ok = (int64_t *)st.out(args[0].pdata, (size_t)P.nq * P.k * 8);
     double *od = (double *)st.out(args[1].pdata, (size_t)P.nq * P.k * 8);
     if (st.failed) { st.finish(); return MO_RC_INTERNAL_ERROR; }
-    rc = bruteforce_topk_device(t, ddata, P.n, (int)P.dim, dq, P.nq, P.k, P.metric, P.key_base, P.sqrt_out, ok, od);
+    if (tc_search_applicable(P.n, (int)P.dim, P.nq, P.k, P.metric))
+        rc = bruteforce_topk_tc_device(t, ddata, P.n, (int)P.dim, dq, P.nq, P.k, P.key_base, P.sqrt_out, ok, od, nullptr);
+    else
+        rc = bruteforce_topk_device(t, ddata, P.n, (int)P.dim, dq, P.nq, P.k, P.metric, P.key_base, P.sqrt_out, ok, od);
     int frc = st.finish();
     return rc ? rc : frc;
 }

@@ -1,0 +1,515 @@
+// tcsearch.cu -- tensor-core candidate generation for batched brute-force search (tcgen05 + TMEM + TMA, sm_100a).
+//
+// The exact kernel in search.cu replays the Go distance loop (3 fp32 ops per element pair, ~33 T lane-ops/s ceiling on this
+// part).  For large query batches the L2 distance is a dense contraction, so candidates are generated on the 5th-gen tensor
+// cores and only the survivors are re-scored exactly:
+//
+//   1. split_kernel:   x (fp32) = hi + lo with hi = bf16(x), lo = bf16(x - hi); operands are stored K-concatenated,
+//                      A' = [q_hi | q_hi | q_lo], B' = [x_hi | x_lo | x_hi]  (K' = 3*dim, padded to a multiple of 64), so ONE
+//                      bf16 GEMM yields q_hi.x_hi + q_hi.x_lo + q_lo.x_hi = q.x up to ~2^-16 relative (the lo.lo term is
+//                      dropped); squared norms are computed in fp64 and rounded to fp32.
+//   2. tc_candidates_kernel: persistent, warp-specialised.  CTA tile 128 queries x 256 rows, K' streamed in 64-element
+//                      (128-byte, SWIZZLE_128B) slabs by TMA through a 4-stage mbarrier ring; one elected thread issues
+//                      tcgen05.mma.cta_group::1.kind::f16 (M128 N256 K16) into one of two 256-column TMEM accumulators; four
+//                      epilogue warps read the other accumulator with tcgen05.ld (each thread = one query row), form
+//                      d~ = |q|^2 + |x|^2 - 2 q.x and keep the KP smallest per (query, row range) in a thread-private shared-memory list.
+//   3. rescore (search.cu path): the approximate lists of all ranges are merged per query, the best KR candidates are
+//                      re-scored with the bit-exact Go-order distance, sorted by (distance, id), and the top k returned.
+//   4. proof of completeness: a row that was never a candidate has d~ >= t, the smallest "list-full threshold" of its
+//                      range; with |d~ - d| <= eps (eps from the split error bound), d_k(exact) + eps < t proves no such
+//                      row can enter the top k.  Queries that fail the test (near-ties, tiny lists) are re-run on the exact
+//                      kernel, so results are ALWAYS the exact answer.
+//
+// Work per launch: 2 * Q * N * K' flop on the tensor pipe (K' = 2304 for dim 768) + exact re-scoring of Q * KR rows.
+#include "common.cuh"
+#include "godist.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cstring>
+#include <cmath>
+#include <vector>
+
+using namespace mob;
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int KP = 16;                      // candidates kept per (query, row range)
+constexpr int kTcThreads = 256;             // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warp 3 idle, warps 4-7 epilogue
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
+
+struct TcSmem {
+    unsigned char a[STAGES][A_STAGE_BYTES];   // 1024-byte aligned (SWIZZLE_128B atoms)
+    unsigned char b[STAGES][B_STAGE_BYTES];
+    float ld[KP][BM];                         // per-query sorted candidate list, [rank][query row]
+    int li[KP][BM];
+    float xn[2][BN];                          // |x|^2 of the current tile's rows (double buffered with the accumulators)
+    unsigned long long full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
+    unsigned tmem_base;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    while (!mbar_try_wait(bar, parity)) { }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, unsigned long long *bar, void *dst, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(unsigned long long *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(unsigned tmem_d, unsigned long long desc_a, unsigned long long desc_b, unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = TMEM lane = query row)
+__device__ __forceinline__ void tc_ld32(unsigned taddr, float *v) {
+    unsigned r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+// start>>4 | LBO(=1, ignored for swizzled K-major)<<16 | SBO(=1024 B: 8 rows x 128 B)>>4 <<32 | version 1 <<46 | layout 2 <<61
+__device__ __forceinline__ unsigned long long make_desc(unsigned smem_addr) {
+    return (unsigned long long)((smem_addr & 0x3ffff) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (UMMA::InstrDescriptor): D=F32 (bit 4), A=BF16 (bit 7), B=BF16 (bit 10), K-major both, N>>3 at 17, M>>4 at 24
+constexpr unsigned kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
+
+struct TcUnit { int m0; int n_begin; int n_end; int range; };   // one work unit: 128 queries x rows [n_begin, n_end)
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                     const TcUnit *__restrict__ units, int nunits, int kprime /* K' */, int nq, int n,
+                     const float *__restrict__ qnorm, const float *__restrict__ xnorm,
+                     float *__restrict__ part_d, int *__restrict__ part_i, float *__restrict__ part_thr,
+                     float *__restrict__ dbg_scores) {
+    extern __shared__ unsigned char smem_raw[];
+    // SWIZZLE_128B atoms need 1024-byte alignment in the shared window: align by hand (the launch adds 1024 spare bytes)
+    TcSmem &S = *reinterpret_cast<TcSmem *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = kprime / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&S.tmem_full[a], 1); mbar_init(&S.tmem_empty[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {   // TMEM: 512 columns = two 128 x 256 fp32 accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S.tmem_base)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem_base = S.tmem_base;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0; unsigned phase = 0;
+            for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+                const TcUnit U = units[u];
+                for (int n0 = U.n_begin; n0 < U.n_end; n0 += BN) {
+                    for (int kb = 0; kb < nkb; kb++) {
+                        mbar_wait(&S.empty[stage], phase ^ 1);
+                        mbar_expect_tx(&S.full[stage], A_STAGE_BYTES + B_STAGE_BYTES);
+                        tma_load_2d(&map_a, &S.full[stage], S.a[stage], kb * BK, U.m0);
+                        tma_load_2d(&map_b, &S.full[stage], S.b[stage], kb * BK, n0);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            int stage = 0; unsigned phase = 0; unsigned tile = 0;
+            for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+                const TcUnit U = units[u];
+                for (int n0 = U.n_begin; n0 < U.n_end; n0 += BN, tile++) {
+                    const unsigned acc = tile & 1;
+                    mbar_wait(&S.tmem_empty[acc], ((tile >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const unsigned tmem_d = tmem_base + acc * BN;
+                    for (int kb = 0; kb < nkb; kb++) {
+                        mbar_wait(&S.full[stage], phase);
+                        tc_fence_after();
+                        const unsigned long long da = make_desc(smem_u32(S.a[stage])), db = make_desc(smem_u32(S.b[stage]));
+#pragma unroll
+                        for (int k = 0; k < BK / 16; k++)   // +32 bytes (= 2 in the >>4 address field) per K16 step inside the 128-B swizzle atom
+                            tc_mma_bf16(tmem_d, da + 2 * k, db + 2 * k, kIdesc, (kb | k) != 0);
+                        tc_commit(&S.empty[stage]);          // frees the smem slot once these MMAs have read it
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    tc_commit(&S.tmem_full[acc]);            // accumulator complete -> epilogue
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: thread e = query row of the tile = TMEM lane =====
+        const int e = threadIdx.x - 128;
+        const int ew = warp - 4;                              // TMEM lane quarter 32*ew .. 32*ew+31
+        unsigned tile = 0;
+        for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+            const TcUnit U = units[u];
+            const int q = U.m0 + e;
+            const float qn = q < nq ? qnorm[q] : 0.f;
+            int cnt = 0; float thr = INFINITY;
+            for (int n0 = U.n_begin; n0 < U.n_end; n0 += BN, tile++) {
+                const unsigned acc = tile & 1;
+                // |x|^2 of this tile's rows -> shared (2 per thread); named barrier over the 128 epilogue threads
+                for (int j = e; j < BN; j += 128) S.xn[acc][j] = (n0 + j < n) ? xnorm[n0 + j] : INFINITY;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                mbar_wait(&S.tmem_full[acc], (tile >> 1) & 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < BN; c += 32) {
+                    float v[32];
+                    tc_ld32(tmem_base + ((unsigned)(32 * ew) << 16) + acc * BN + c, v);
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float d = (qn + S.xn[acc][c + j]) - 2.0f * v[j];   // +inf for rows past the end
+                        if (dbg_scores && q < nq && n0 + c + j < n) dbg_scores[(size_t)q * n + n0 + c + j] = d;
+                        if (d < thr) {
+                            const int id = n0 + c + j;
+                            int pos;
+                            if (cnt < KP) pos = cnt++;
+                            else pos = KP - 1;
+                            while (pos > 0 && d < S.ld[pos - 1][e]) { S.ld[pos][e] = S.ld[pos - 1][e]; S.li[pos][e] = S.li[pos - 1][e]; pos--; }
+                            S.ld[pos][e] = d; S.li[pos][e] = id;
+                            if (cnt == KP) thr = S.ld[KP - 1][e];
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.tmem_empty[acc]);   // 4 arrivals (one per epilogue warp) release the accumulator
+            }
+            if (q < nq) {
+                const size_t base = ((size_t)U.range * nq + q) * KP;
+                for (int j = 0; j < KP; j++) { part_d[base + j] = j < cnt ? S.ld[j][e] : INFINITY; part_i[base + j] = j < cnt ? S.li[j][e] : -1; }
+                part_thr[(size_t)U.range * nq + q] = thr;       // every row of this range that is NOT listed has d~ >= thr
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+}
+
+// ---- operand preparation -------------------------------------------------------------------------------------------------
+// mode 0: A' = [hi | hi | lo] (queries), mode 1: B' = [hi | lo | hi] (dataset).  One warp per row; pads K' with zeros.
+__global__ void split_kernel(const float *__restrict__ x, int64_t n, int dim, int kprime, int mode, __nv_bfloat16 *__restrict__ out,
+                             float *__restrict__ norm, float *__restrict__ absmax) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n; r += nwarps) {
+        const float *p = x + r * dim;
+        __nv_bfloat16 *o = out + r * kprime;
+        double s = 0.0; float am = 0.f;
+        for (int j = lane; j < dim; j += 32) {
+            const float v = p[j];
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+            o[j] = hi;
+            o[dim + j] = mode == 0 ? hi : lo;
+            o[2 * dim + j] = mode == 0 ? lo : hi;
+            s += (double)v * (double)v;
+            am = fmaxf(am, fabsf(v));
+        }
+        for (int j = 3 * dim + lane; j < kprime; j += 32) o[j] = __float2bfloat16_rn(0.f);
+        s = warp_sum_f64(s);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, off));
+        if (lane == 0) { norm[r] = (float)s; if (absmax) absmax[r] = am; }
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_map(CUtensorMap *map, void *base, uint64_t rows, uint64_t kprime, uint32_t box_rows) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        cudaDriverEntryPointQueryResult qres;
+        void *p = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p) {
+            set_error("cuTensorMapEncodeTiled entry point not available"); return MO_RC_INTERNAL_ERROR;
+        }
+        fn = (EncodeTiledFn)p;
+    }
+    const cuuint64_t gdim[2] = {kprime, rows};              // innermost first
+    const cuuint64_t gstride[1] = {kprime * 2};             // bytes, dims 1..
+    const cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};  // 64 bf16 = 128 B = the swizzle span
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return MO_RC_INTERNAL_ERROR; }
+    return MO_RC_SUCCESS;
+}
+
+// ---- post-processing: merge approximate lists, exact re-score, final order + completeness proof -----------------------------
+constexpr int KR = 32;   // candidates re-scored exactly per query
+
+// one thread per query: R-way merge of the (ascending) approximate lists -> KR best candidate ids; t_excl = smallest approximate
+// distance any row NOT among them can have (first unconsumed entry of every list, and the list-full threshold of every range)
+__global__ void tc_merge_kernel(int nq, int R, const float *__restrict__ part_d, const int *__restrict__ part_i,
+                                const float *__restrict__ part_thr, int *__restrict__ cand, float *__restrict__ t_excl) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    unsigned char head[64];
+    for (int r = 0; r < R; r++) head[r] = 0;
+    for (int j = 0; j < KR; j++) {
+        int best = -1; float bd = INFINITY;
+        for (int r = 0; r < R; r++) {
+            if (head[r] >= KP) continue;
+            const size_t idx = ((size_t)r * nq + q) * KP + head[r];
+            if (part_i[idx] < 0) { head[r] = KP; continue; }
+            const float d = part_d[idx];
+            if (best < 0 || d < bd) { best = r; bd = d; }
+        }
+        if (best < 0) { cand[(size_t)q * KR + j] = -1; continue; }
+        cand[(size_t)q * KR + j] = part_i[((size_t)best * nq + q) * KP + head[best]];
+        head[best]++;
+    }
+    float t = INFINITY;
+    for (int r = 0; r < R; r++) {
+        t = fminf(t, part_thr[(size_t)r * nq + q]);
+        if (head[r] < KP) { const size_t idx = ((size_t)r * nq + q) * KP + head[r]; if (part_i[idx] >= 0) t = fminf(t, part_d[idx]); }
+    }
+    t_excl[q] = t;
+}
+
+// one warp per (query, candidate): the bit-exact Go-order L2sq (godist.cuh)
+__global__ void tc_rescore_kernel(const float *__restrict__ data, const float *__restrict__ queries, int dim, int nq,
+                                  const int *__restrict__ cand, float *__restrict__ exact) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t p = w; p < (int64_t)nq * KR; p += nw) {
+        const int id = cand[p];
+        float d = INFINITY;
+        if (id >= 0) {
+            const uint8_t *a = reinterpret_cast<const uint8_t *>(queries + (p / KR) * dim), *b = reinterpret_cast<const uint8_t *>(data + (int64_t)id * dim);
+            const bool al = ((((uintptr_t)a) | ((uintptr_t)b)) & 15) == 0;
+            d = godist::go_l2sq<float>(a, b, dim, lane, al, false, true);
+        }
+        if (lane == 0) exact[p] = d;
+    }
+}
+
+__global__ void tc_max_kernel(const float *__restrict__ v, int64_t n, float *out) {   // max of non-negative floats
+    float m = 0.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, v[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int *>(out), __float_as_int(m));
+}
+
+// one thread per query: order the KR exact candidates by (distance, id), emit the top k with the reference's front padding, and
+// prove completeness:  every excluded row has approximate distance >= t_excl, |approx - real| <= eps_tc, |real - go| <= eps_go,
+// so d_k + eps_tc + eps_go < t_excl  =>  no excluded row can displace the k-th result.  flag = 1 when the proof fails.
+__global__ void tc_final_kernel(int nq, int k, int64_t n_rows, int dim, const int *__restrict__ cand, const float *__restrict__ exact,
+                                const float *__restrict__ t_excl, const float *__restrict__ qnorm, const float *__restrict__ xnorm_max,
+                                int64_t key_base, int sqrt_out, int64_t *__restrict__ out_k, double *__restrict__ out_d, int *__restrict__ flags) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    float d[KR]; int id[KR]; int m = 0;
+    for (int j = 0; j < KR; j++) {
+        const int c = cand[(size_t)q * KR + j];
+        if (c < 0) continue;
+        const float v = exact[(size_t)q * KR + j];
+        int pos = m++;
+        while (pos > 0 && (v < d[pos - 1] || (v == d[pos - 1] && c < id[pos - 1]))) { d[pos] = d[pos - 1]; id[pos] = id[pos - 1]; pos--; }
+        d[pos] = v; id[pos] = c;
+    }
+    const int total = m < k ? m : k;
+    const int pad = k - total;
+    int64_t *ok = out_k + (size_t)q * k; double *od = out_d + (size_t)q * k;
+    for (int j = 0; j < pad; j++) { ok[j] = -1; od[j] = 0.0; }
+    for (int j = 0; j < total; j++) { ok[pad + j] = (int64_t)id[j] + key_base; od[pad + j] = sqrt_out ? sqrt((double)d[j]) : (double)d[j]; }
+    const float t = t_excl[q];
+    bool proven;
+    if (t == INFINITY) proven = true;                       // nothing was excluded (every row of every range is listed)
+    else if (m < k) proven = false;
+    else {
+        const float qn = qnorm[q], xm = *xnorm_max;
+        const float eps_tc = 1.220703125e-4f * sqrtf(qn * xm) + 4.76837158203125e-7f * (qn + xm);   // 2^-13 |q||x| + 2^-21 (|q|^2+|x|^2)
+        const float eps_go = (float)dim * 1.1920928955078125e-7f * t;                                  // dim * 2^-23 * distance scale
+        proven = d[k - 1] + eps_tc + eps_go < t;
+    }
+    flags[q] = proven ? 0 : 1;
+}
+
+__global__ void gather_rows_kernel(const float *__restrict__ src, const int *__restrict__ idx, int m, int dim, float *__restrict__ dst) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < (int64_t)m * dim; e += (int64_t)gridDim.x * blockDim.x)
+        dst[e] = src[(int64_t)idx[e / dim] * dim + e % dim];
+}
+__global__ void scatter_results_kernel(const int64_t *__restrict__ sk, const double *__restrict__ sd, const int *__restrict__ idx, int m, int k,
+                                       int64_t *__restrict__ out_k, double *__restrict__ out_d) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < m * k; e += gridDim.x * blockDim.x) {
+        const int q = idx[e / k];
+        out_k[(size_t)q * k + e % k] = sk[e]; out_d[(size_t)q * k + e % k] = sd[e];
+    }
+}
+
+}  // namespace
+
+namespace mob {
+
+// Tensor-core candidate pass.  Outputs (device): part_d/part_i [R][nq][KP] approximate (distance, local row id) lists, part_thr [R][nq].
+// Returns the number of row ranges R and the per-list length KP through out params.
+int tc_candidates_device(ThreadCtx &t, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq,
+                         float **part_d, int **part_i, float **part_thr, int *R_out, int *kp_out, float *dbg_scores,
+                         float **qnorm_out, float **xnorm_out, float **qabs_out, float **xabs_out) {
+    const int kprime = ((3 * dim + BK - 1) / BK) * BK;
+    __nv_bfloat16 *a = (__nv_bfloat16 *)arena_alloc(t, (size_t)nq * kprime * 2 + 1024);
+    __nv_bfloat16 *b = (__nv_bfloat16 *)arena_alloc(t, (size_t)n * kprime * 2 + 1024);
+    float *qn = (float *)arena_alloc(t, (size_t)nq * 4), *xn = (float *)arena_alloc(t, (size_t)n * 4);
+    float *qa = (float *)arena_alloc(t, (size_t)nq * 4), *xa = (float *)arena_alloc(t, (size_t)n * 4);
+    if (!a || !b || !qn || !xn || !qa || !xa) return MO_RC_INTERNAL_ERROR;
+    split_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(dq, nq, dim, kprime, 0, a, qn, qa);
+    MOB_LAUNCH_CHECK();
+    split_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(ddata, n, dim, kprime, 1, b, xn, xa);
+    MOB_LAUNCH_CHECK();
+    CUtensorMap map_a, map_b;
+    int rc = make_map(&map_a, a, (uint64_t)nq, (uint64_t)kprime, BM);
+    if (rc) return rc;
+    rc = make_map(&map_b, b, (uint64_t)n, (uint64_t)kprime, BN);
+    if (rc) return rc;
+    // work units: (query tile, row range); ranges sized so that units ~ a whole number of waves over the SMs
+    const int mt = (int)((nq + BM - 1) / BM);
+    const int64_t ntiles = (n + BN - 1) / BN;
+    int R = (int)((8ll * num_sms() + mt - 1) / mt);
+    if (R > ntiles) R = (int)ntiles;
+    if (R < 1) R = 1;
+    const int64_t tiles_per = (ntiles + R - 1) / R;
+    R = (int)((ntiles + tiles_per - 1) / tiles_per);
+    std::vector<TcUnit> units;
+    for (int r = 0; r < R; r++)
+        for (int m = 0; m < mt; m++) {
+            TcUnit u; u.m0 = m * BM; u.n_begin = (int)(r * tiles_per * BN); u.n_end = (int)((r + 1) * tiles_per * BN < n ? (r + 1) * tiles_per * BN : n); u.range = r;
+            if (u.n_begin < u.n_end) units.push_back(u);
+        }
+    TcUnit *dunits = (TcUnit *)arena_alloc(t, sizeof(TcUnit) * units.size());
+    *part_d = (float *)arena_alloc(t, sizeof(float) * (size_t)R * nq * KP);
+    *part_i = (int *)arena_alloc(t, sizeof(int) * (size_t)R * nq * KP);
+    *part_thr = (float *)arena_alloc(t, sizeof(float) * (size_t)R * nq);
+    if (!dunits || !*part_d || !*part_i || !*part_thr) return MO_RC_INTERNAL_ERROR;
+    MOB_CUDA_TRY(cudaMemcpyAsync(dunits, units.data(), sizeof(TcUnit) * units.size(), cudaMemcpyHostToDevice, t.stream));
+    MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));
+    static bool attr = false;
+    const size_t smem = sizeof(TcSmem) + 1024;
+    if (!attr) { MOB_CUDA_TRY(cudaFuncSetAttribute(tc_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    int grid = num_sms();
+    if (grid > (int)units.size()) grid = (int)units.size();
+    cudaEventRecord(t.kev0, t.stream);
+    tc_candidates_kernel<<<grid, kTcThreads, smem, t.stream>>>(map_a, map_b, dunits, (int)units.size(), kprime, (int)nq, (int)n, qn, xn,
+                                                                *part_d, *part_i, *part_thr, dbg_scores);
+    cudaEventRecord(t.kev1, t.stream);
+    MOB_LAUNCH_CHECK();
+    *R_out = R; *kp_out = KP;
+    *qnorm_out = qn; *xnorm_out = xn; *qabs_out = qa; *xabs_out = xa;
+    return MO_RC_SUCCESS;
+}
+
+int bruteforce_topk_device(ThreadCtx &t, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq, int k, int metric,
+                           int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d);
+
+int g_search_mode = 0;          // 0 = auto, 1 = exact kernel only, 2 = force the tensor-core path (MoB200_SetTuning("search_mode"))
+int g_last_tc_fallbacks = -1;   // queries of the last tensor-core search that failed the completeness proof and were re-run exactly
+
+bool tc_search_applicable(int64_t n, int dim, int64_t nq, int k, int metric) {
+    if (g_search_mode == 1) return false;
+    const bool shape_ok = (metric == MO_METRIC_L2 || metric == MO_METRIC_L2SQ) && k >= 1 && k <= KP && dim >= 16 && n >= BN && n < (1ll << 31) - BN;
+    if (g_search_mode == 2) return shape_ok;
+    return shape_ok && nq >= 256 && n >= 16384 && dim >= 64;   // below this the exact kernel wins (operand split + launch overheads)
+}
+
+// Brute-force top-k through the tensor-core candidate pass; results are the exact answer (see file header).
+int bruteforce_topk_tc_device(ThreadCtx &t, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq, int k,
+                              int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d, float *dbg_scores) {
+    float *part_d, *part_thr, *qn, *xn, *qa, *xa; int *part_i; int R = 0, kp = 0;
+    int rc = tc_candidates_device(t, ddata, n, dim, dq, nq, &part_d, &part_i, &part_thr, &R, &kp, dbg_scores, &qn, &xn, &qa, &xa);
+    if (rc) return rc;
+    if (R > 64) { set_error("tc search: too many row ranges"); return MO_RC_INTERNAL_ERROR; }
+    int *cand = (int *)arena_alloc(t, sizeof(int) * (size_t)nq * KR);
+    float *exact = (float *)arena_alloc(t, sizeof(float) * (size_t)nq * KR);
+    float *t_excl = (float *)arena_alloc(t, sizeof(float) * (size_t)nq + 16);
+    int *flags = (int *)arena_alloc(t, sizeof(int) * (size_t)nq);
+    if (!cand || !exact || !t_excl || !flags) return MO_RC_INTERNAL_ERROR;
+    float *xmax = t_excl + nq;
+    MOB_CUDA_TRY(cudaMemsetAsync(xmax, 0, 4, t.stream));
+    tc_max_kernel<<<num_sms() * 2, 256, 0, t.stream>>>(xn, n, xmax);
+    MOB_LAUNCH_CHECK();
+    tc_merge_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, t.stream>>>((int)nq, R, part_d, part_i, part_thr, cand, t_excl);
+    MOB_LAUNCH_CHECK();
+    tc_rescore_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(ddata, dq, dim, (int)nq, cand, exact);
+    MOB_LAUNCH_CHECK();
+    tc_final_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, t.stream>>>((int)nq, k, n, dim, cand, exact, t_excl, qn, xmax, key_base, sqrt_out, out_k, out_d, flags);
+    MOB_LAUNCH_CHECK();
+    std::vector<int> hflags((size_t)nq);
+    MOB_CUDA_TRY(cudaMemcpyAsync(hflags.data(), flags, sizeof(int) * (size_t)nq, cudaMemcpyDeviceToHost, t.stream));
+    MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));
+    std::vector<int> redo;
+    for (int64_t q = 0; q < nq; q++) if (hflags[(size_t)q]) redo.push_back((int)q);
+    g_last_tc_fallbacks = (int)redo.size();
+    if (!redo.empty()) {   // queries whose completeness could not be proven: exact kernel, results scattered back
+        const int m = (int)redo.size();
+        int *didx = (int *)arena_alloc(t, sizeof(int) * (size_t)m);
+        float *sub = (float *)arena_alloc(t, sizeof(float) * (size_t)m * dim);
+        int64_t *sk = (int64_t *)arena_alloc(t, sizeof(int64_t) * (size_t)m * k);
+        double *sd = (double *)arena_alloc(t, sizeof(double) * (size_t)m * k);
+        if (!didx || !sub || !sk || !sd) return MO_RC_INTERNAL_ERROR;
+        MOB_CUDA_TRY(cudaMemcpyAsync(didx, redo.data(), sizeof(int) * (size_t)m, cudaMemcpyHostToDevice, t.stream));
+        MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));
+        gather_rows_kernel<<<num_sms() * 4, 256, 0, t.stream>>>(dq, didx, m, dim, sub);
+        MOB_LAUNCH_CHECK();
+        rc = bruteforce_topk_device(t, ddata, n, dim, sub, m, k, MO_METRIC_L2SQ, key_base, sqrt_out, sk, sd);
+        if (rc) return rc;
+        scatter_results_kernel<<<(unsigned)((m * k + 255) / 256), 256, 0, t.stream>>>(sk, sd, didx, m, k, out_k, out_d);
+        MOB_LAUNCH_CHECK();
+    }
+    return MO_RC_SUCCESS;
+}
+
+}  // namespace mob

@@ -116,3 +116,40 @@ def test_ivf_empty_lists_and_small_index(gpu):
     O.go().og_ivf_search_f32(O.p(data), O.p(assign), 6, dim, O.p(centers), 8, O.p(qs), 2, 2, 4, 0, 0, 1, O.p(okeys), O.p(odists))
     assert (dists == odists).all() and (keys == okeys).all()
     idx.destroy()
+
+
+@pytest.mark.parametrize("n,dim,nq,k", [(20_000, 128, 300, 10), (9_000, 768, 257, 10), (5_000, 100, 130, 5), (70_000, 64, 1000, 16), (300, 32, 40, 3)])
+def test_tensor_core_candidate_path_is_exact(gpu, n, dim, nq, k):
+    """tcgen05 candidate generation + exact re-scoring + completeness proof (csrc/tcsearch.cu): the results must be the exact
+    answer (bit-exact distances), and the tensor path itself must be doing the work (few proof failures -> few fallbacks)."""
+    ds = datagen.vectors_f32(40, 0, n, dim); qs = datagen.vectors_f32(41, 0, nq, dim)
+    qs[:7] = ds[[0, 5, n // 2, n - 1, 17, 100, 255]]          # self matches: exact distance 0
+    okeys, odists = O.bruteforce(ds, qs, k)
+    try:
+        gpu.MoB200_SetTuning(b"search_mode", 2)
+        idx = ops.BruteForceIndex(ds, dim)
+        keys, dists = idx.search(qs, k)
+        fallbacks = gpu.MoB200_SetTuning(b"get_tc_fallbacks", 0)
+        idx.destroy()
+    finally:
+        gpu.MoB200_SetTuning(b"search_mode", 0)
+    _check_topk(keys, dists, okeys, odists, nq, k)
+    assert dists.reshape(nq, k)[:7, 0].tolist() == [0.0] * 7
+    assert 0 <= fallbacks <= max(2, nq // 20), fallbacks
+
+
+def test_tensor_core_path_near_ties_fall_back_to_exact(gpu):
+    """many exactly tied rows defeat the completeness proof: those queries are re-run on the exact kernel, results stay exact"""
+    n, dim, nq, k = 4096, 64, 256, 10
+    ds = np.zeros((n, dim), dtype=np.float32); ds[:, 0] = np.arange(n) % 7
+    qs = np.zeros((nq, dim), dtype=np.float32); qs[:, 1] = np.arange(nq) % 3
+    okeys, odists = O.bruteforce(ds, qs, k)
+    try:
+        gpu.MoB200_SetTuning(b"search_mode", 2)
+        idx = ops.BruteForceIndex(ds, dim)
+        keys, dists = idx.search(qs, k)
+        fallbacks = gpu.MoB200_SetTuning(b"get_tc_fallbacks", 0)
+        idx.destroy()
+    finally:
+        gpu.MoB200_SetTuning(b"search_mode", 0)
+    assert (dists == odists).all() and fallbacks > 0
