@@ -421,6 +421,7 @@ int tc_candidates_device(ThreadCtx &t, const float *ddata, int64_t n, int dim, c
     const int64_t ntiles = (n + BN - 1) / BN;
     int R = (int)((8ll * num_sms() + mt - 1) / mt);
     if (R > ntiles) R = (int)ntiles;
+    if (R > 64) R = 64;   // the merge kernel keeps one list head per range in a 64-entry array
     if (R < 1) R = 1;
     const int64_t tiles_per = (ntiles + R - 1) / R;
     R = (int)((ntiles + tiles_per - 1) / tiles_per);

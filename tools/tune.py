@@ -125,15 +125,21 @@ def main():
             x.free()
     if "bf" in which:
         dim = 768
-        for rows, nq in ((200_000, 2048), (1_000_000, 1024)):
+        for rows, nq in ((200_000, 2048), (1_000_000, 1024), (1_000_000, 10_000)):
             ds = DeviceBuffer(4 * rows * dim, lib)
             capi.check(lib.MoB200_GenVectorsF32(20, 0, rows, dim, ds.ptr, None, 0, 1.0), lib)
             dq = DeviceBuffer(4 * nq * dim, lib)
             capi.check(lib.MoB200_GenVectorsF32(21, 0, nq, dim, dq.ptr, None, 0, 1.0), lib)
             idx = ops.BruteForceIndex(ds, dim, lib=lib)
-            ms, best = timed(lambda: idx.search(dq, 10), reps=3, warm=1)
-            flop = 3.0 * rows * nq * dim
-            report("bruteforce_l2_top10", ms, best, None, rows=rows, queries=nq, qps=round(nq / ms * 1e3, 1), TFLOPs_3op=round(flop / ms / 1e9, 2))
+            import time
+            for mode, name in ((1, "exact"), (2, "tensor_core")):
+                lib.MoB200_SetTuning(b"search_mode", mode)
+                ms, best = timed(lambda: idx.search(dq, 10), reps=3, warm=1)
+                t0 = time.perf_counter(); idx.search(dq, 10); wall = (time.perf_counter() - t0) * 1e3
+                flop = (3.0 if mode == 1 else 2.0 * 3) * rows * nq * dim
+                report("bruteforce_l2_top10_" + name, ms, best, None, rows=rows, queries=nq, kernel_qps=round(nq / ms * 1e3, 1), call_wall_ms=round(wall, 2),
+                       call_qps=round(nq / wall * 1e3, 1), TFLOPs=round(flop / ms / 1e9, 2), fallbacks=lib.MoB200_SetTuning(b"get_tc_fallbacks", 0))
+            lib.MoB200_SetTuning(b"search_mode", 0)
             ds.free(); dq.free()
 
 
