@@ -379,11 +379,18 @@ def main():
                     "kernel": {"q6": "q6_kernel", "q1": "q1_kernel", "sum": "agg_kernel"}[args.workload], "kernel_ms": kern_ms,
                     "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src}
     else:
-        flop = 3.0 * args.queries * n * 768
-        fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12      # nominal fp32 FMA peak, TFLOP/s (no measured fp32 figure in MEASURED_PEAKS.json)
+        # dominant kernel = tc_candidates_kernel: one bf16 GEMM with K' = 3 * dim (hi/lo operand split), 2 * Q * N * K' flop
+        flop = 2.0 * args.queries * n * (3 * 768)
+        tpeak, tsrc = 1709.9, "fallback"
+        try:
+            mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            tpeak, tsrc = float(mp["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst: the kernel is timed alone)"
+        except Exception:
+            tpeak, tsrc = 1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s)"
         ach = flop / (kern_ms * 1e-3) / 1e12
-        roofline = {"bound": "fp32-fma", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak, "traffic": None,
-                    "kernel": "bf_topk_kernel", "kernel_ms": kern_ms, "peak_source": "nominal 148 SM x 128 FMA/clk x 1.965 GHz (exact fp32 path, no tensor cores)"}
+        roofline = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": None,
+                    "kernel": "tc_candidates_kernel (tcgen05 bf16, K' = 2304)", "kernel_ms": kern_ms, "algorithmic_flop_per_launch": flop, "peak_source": tsrc,
+                    "tc_fallback_queries": int(lib.MoB200_SetTuning(b"get_tc_fallbacks", 0))}
     cpu_baseline = None
     if not args.no_cpu and world == 1 and args.workload in ("q6", "q1", "sum"):
         threads = os.cpu_count() or 1

@@ -239,7 +239,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 // ---- operand preparation -------------------------------------------------------------------------------------------------
 // mode 0: A' = [hi | hi | lo] (queries), mode 1: B' = [hi | lo | hi] (dataset).  One warp per row; pads K' with zeros.
 __global__ void split_kernel(const float *__restrict__ x, int64_t n, int dim, int kprime, int mode, __nv_bfloat16 *__restrict__ out,
-                             float *__restrict__ norm, float *__restrict__ absmax) {
+                             float *__restrict__ norm, float *__restrict__ absmax, int *__restrict__ nonfinite) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t r = warp; r < n; r += nwarps) {
@@ -255,6 +255,7 @@ __global__ void split_kernel(const float *__restrict__ x, int64_t n, int dim, in
             o[2 * dim + j] = mode == 0 ? lo : hi;
             s += (double)v * (double)v;
             am = fmaxf(am, fabsf(v));
+            if (!(fabsf(v) <= 3.0e38f)) *nonfinite = 1;   // Inf / NaN: the caller falls back to the exact kernel
         }
         for (int j = 3 * dim + lane; j < kprime; j += 32) o[j] = __float2bfloat16_rn(0.f);
         s = warp_sum_f64(s);
@@ -373,7 +374,9 @@ __global__ void tc_final_kernel(int nq, int k, int64_t n_rows, int dim, const in
     else if (m < k) proven = false;
     else {
         const float qn = qnorm[q], xm = *xnorm_max;
-        const float eps_tc = 1.220703125e-4f * sqrtf(qn * xm) + 4.76837158203125e-7f * (qn + xm);   // 2^-13 |q||x| + 2^-21 (|q|^2+|x|^2)
+        // |2 q.x error| <= 2 * (3 * 2^-16 [dropped lo.lo + bf16 residuals] + 144 * 2^-23 [fp32 accumulation over K'/16 MMA steps]) * |q||x|
+        //               < 2^-12.8 |q||x|; 2^-12 is used.  Norm / final-formula rounding: 2^-21 (|q|^2 + |x|^2).
+        const float eps_tc = 2.44140625e-4f * sqrtf(qn * xm) + 4.76837158203125e-7f * (qn + xm);
         const float eps_go = (float)dim * 1.1920928955078125e-7f * t;                                  // dim * 2^-23 * distance scale
         proven = d[k - 1] + eps_tc + eps_go < t;
     }
@@ -407,10 +410,16 @@ int tc_candidates_device(ThreadCtx &t, const float *ddata, int64_t n, int dim, c
     float *qn = (float *)arena_alloc(t, (size_t)nq * 4), *xn = (float *)arena_alloc(t, (size_t)n * 4);
     float *qa = (float *)arena_alloc(t, (size_t)nq * 4), *xa = (float *)arena_alloc(t, (size_t)n * 4);
     if (!a || !b || !qn || !xn || !qa || !xa) return MO_RC_INTERNAL_ERROR;
-    split_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(dq, nq, dim, kprime, 0, a, qn, qa);
+    int *dnonfinite = (int *)arena_alloc(t, 4);
+    if (!dnonfinite) return MO_RC_INTERNAL_ERROR;
+    MOB_CUDA_TRY(cudaMemsetAsync(dnonfinite, 0, 4, t.stream));
+    split_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(dq, nq, dim, kprime, 0, a, qn, qa, dnonfinite);
     MOB_LAUNCH_CHECK();
-    split_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(ddata, n, dim, kprime, 1, b, xn, xa);
+    split_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(ddata, n, dim, kprime, 1, b, xn, xa, dnonfinite);
     MOB_LAUNCH_CHECK();
+    int hnonfinite = 0;
+    { int rcx = read_back(t, &hnonfinite, dnonfinite, 4); if (rcx) return rcx; }
+    if (hnonfinite) { *R_out = 0; return MO_RC_SUCCESS; }   // R == 0 tells the caller to use the exact kernel
     CUtensorMap map_a, map_b;
     int rc = make_map(&map_a, a, (uint64_t)nq, (uint64_t)kprime, BM);
     if (rc) return rc;
@@ -472,6 +481,10 @@ int bruteforce_topk_tc_device(ThreadCtx &t, const float *ddata, int64_t n, int d
     float *part_d, *part_thr, *qn, *xn, *qa, *xa; int *part_i; int R = 0, kp = 0;
     int rc = tc_candidates_device(t, ddata, n, dim, dq, nq, &part_d, &part_i, &part_thr, &R, &kp, dbg_scores, &qn, &xn, &qa, &xa);
     if (rc) return rc;
+    if (R == 0) {   // non-finite inputs: the error bound of the tensor-core pass does not apply
+        g_last_tc_fallbacks = (int)nq;
+        return bruteforce_topk_device(t, ddata, n, dim, dq, nq, k, MO_METRIC_L2SQ, key_base, sqrt_out, out_k, out_d);
+    }
     if (R > 64) { set_error("tc search: too many row ranges"); return MO_RC_INTERNAL_ERROR; }
     int *cand = (int *)arena_alloc(t, sizeof(int) * (size_t)nq * KR);
     float *exact = (float *)arena_alloc(t, sizeof(float) * (size_t)nq * KR);

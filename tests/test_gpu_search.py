@@ -153,3 +153,19 @@ def test_tensor_core_path_near_ties_fall_back_to_exact(gpu):
     finally:
         gpu.MoB200_SetTuning(b"search_mode", 0)
     assert (dists == odists).all() and fallbacks > 0
+
+
+def test_tensor_core_path_non_finite_inputs_use_exact_kernel(gpu):
+    n, dim, nq, k = 4096, 64, 256, 5
+    ds = datagen.vectors_f32(42, 0, n, dim); qs = datagen.vectors_f32(43, 0, nq, dim)
+    ds[77, 3] = np.inf
+    okeys, odists = O.bruteforce(ds, qs, k)
+    try:
+        gpu.MoB200_SetTuning(b"search_mode", 2)
+        idx = ops.BruteForceIndex(ds, dim)
+        keys, dists = idx.search(qs, k)
+        assert gpu.MoB200_SetTuning(b"get_tc_fallbacks", 0) == nq
+        idx.destroy()
+    finally:
+        gpu.MoB200_SetTuning(b"search_mode", 0)
+    _check_topk(keys, dists, okeys, odists, nq, k)
