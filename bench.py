@@ -114,9 +114,22 @@ def measured_peaks():
 # =====================================================================================================================
 # CPU reference arm / cpu_baseline: the oracle port on the host cores
 # =====================================================================================================================
-def cpu_reference(workload, sample_rows, steps, warmup, threads):
+def cpu_reference(workload, sample_rows, steps, warmup, threads, dataset=None, queries=None):
     import oracle_lib as O
     from matrixone_b200 import datagen
+    if workload == "bruteforce":
+        # GoBruteForceIndex.Search on the FULL dataset (per-query work must not shrink), one query per host thread per step
+        dim = 768
+        ds = dataset if dataset is not None else datagen.vectors_f32(20, 0, sample_rows, dim)
+        qs = queries if queries is not None else datagen.vectors_f32(21, 0, threads, dim)
+        nq = qs.shape[0]
+        for _ in range(warmup):
+            O.bruteforce(ds, qs[:max(1, nq // 4)], 10, 0, threads)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.bruteforce(ds, qs, 10, 0, threads)
+        dt = time.perf_counter() - t0
+        return nq * steps / dt, dt / steps
     if workload == "q6":
         cols = datagen.lineitem(10, 0, sample_rows)
         P = datagen.q6_params()
@@ -148,7 +161,19 @@ def run_reference_arm(args):
     sample = min(wl["rows"], 1 << 25)
     steps = max(1, args.steps)
     warmup = max(1, min(args.warmup, 2))
+    if args.workload == "bruteforce":
+        steps, warmup = min(steps, 3), 1
     value, sec_per_step = cpu_reference(args.workload, sample, steps, warmup, threads)
+    unit = "queries/s" if args.workload == "bruteforce" else "rows/s"
+    if args.workload == "bruteforce":
+        line = {"impl": "reference", "metric": wl["metric"], "value": value, "unit": unit, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+                "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": wl["name"], "rows": sample, "queries_per_step": threads},
+                "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": "port",
+                                 "sample": "full 1 M x 768 dataset, %d queries per step (one per host thread); oracle/oracle_go.c GoBruteForceIndex.Search (metric.L2DistanceSq + FastMaxHeap)" % threads},
+                "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
     line = {
         "impl": "reference", "metric": wl["metric"], "value": value, "unit": "rows/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if args.workload != "sum" else "int64",
@@ -392,6 +417,13 @@ def main():
                     "kernel": "tc_candidates_kernel (tcgen05 bf16, K' = 2304)", "kernel_ms": kern_ms, "algorithmic_flop_per_launch": flop, "peak_source": tsrc,
                     "tc_fallback_queries": int(lib.MoB200_SetTuning(b"get_tc_fallbacks", 0))}
     cpu_baseline = None
+    if not args.no_cpu and world == 1 and args.workload == "bruteforce":
+        threads = os.cpu_count() or 1
+        hds = ds.to_numpy(np.float32).reshape(n, 768)
+        hqs = bufs["queries"].to_numpy(np.float32).reshape(-1, 768)[:threads]
+        v, sec = cpu_reference("bruteforce", n, 1, 1, threads, hds, hqs)
+        cpu_baseline = {"value": v, "unit": "queries/s", "cores": threads, "kind": "port",
+                        "sample": "full dataset, %d queries (one per host thread), 1 pass after a quarter-size warm-up; oracle/oracle_go.c GoBruteForceIndex.Search" % hqs.shape[0]}
     if not args.no_cpu and world == 1 and args.workload in ("q6", "q1", "sum"):
         threads = os.cpu_count() or 1
         sample = min(n, 1 << 25)
