@@ -38,6 +38,7 @@ WORKLOADS = {
     "q1": dict(name="tpch_q1_sf100_fp64_packed_keys", metric="scan+filter+group-agg rows/sec (TPC-H Q1, fp64)", bytes_per_row=38.0, rows=SF100_ROWS),
     "sum": dict(name="int64_sum_10m_rows", metric="int64 SUM rows/sec", bytes_per_row=8.0, rows=10_000_000),
     "bruteforce": dict(name="bruteforce_l2_top10_1Mx768_10k_queries", metric="ANN top-k qps (768-d, brute-force L2 top-10)", bytes_per_row=None, rows=1_000_000),
+    "ivf": dict(name="ivfflat_l2_top10_10Mx768_nlist1024_nprobe32_10k_queries", metric="ANN top-k qps (768-d, IVF-flat nlist=1024 nprobe=32 top-10)", bytes_per_row=None, rows=10_000_000),
 }
 
 
@@ -277,6 +278,32 @@ def main():
         pack = lambda res: np.asarray([res[1], 0], dtype=np.int64).tobytes()
         merge = lambda buf: int(np.frombuffer(bytes(buf), dtype=np.int64).reshape(world, 2)[:, 0].sum())
         units, unit_name, alg_bytes, h2d_bytes = n, "rows/s", 8.0 * n, 8 * n
+    elif args.workload == "ivf":
+        # BASELINE config 5: entries = mixture of 1024 Gaussians, centroids = the generating means, assignment by argmin L2sq
+        # (Productl2).  Lists are sharded across ranks (every rank holds whole lists of a contiguous row slice of the table and
+        # the full centroid table); each rank answers every query over its lists; per-rank top-k are gathered and merged.
+        dim, nq, k, nlist, nprobe = 768, args.queries, 10, 1024, 32
+        n_local = n // world
+        centers = datagen.vectors_f32(30, 0, nlist, dim) * np.float32(4.0)
+        dcent = DeviceBuffer.from_numpy(centers, lib)
+        raw = DeviceBuffer(4 * n_local * dim, lib)
+        capi.check(lib.MoB200_GenVectorsF32(31, rank * n_local, n_local, dim, raw.ptr, dcent.ptr, nlist, 1.0), lib)
+        ivf = ops.IvfflatSearchIndex.build(raw, n_local, centers, capi.METRIC_L2, lib)
+        ivf.row_ids += rank * n_local                      # global primary keys
+        ivf.d_ids.free(); ivf.d_ids = DeviceBuffer.from_numpy(ivf.row_ids, lib)
+        raw.free(); dcent.free()
+        dq = DeviceBuffer(4 * nq * dim, lib)
+        capi.check(lib.MoB200_GenVectorsF32(32, 0, nq, dim, dq.ptr, ivf.d_cent.ptr, nlist, 1.0), lib)
+        bufs = {"queries": dq}
+        def step(cols=bufs):
+            return ivf.search(cols["queries"], k, nprobe)
+        rec_bytes = nq * k * 16
+        pack = lambda res: shard.pack_topk(res[0], res[1])
+        merge = lambda buf: ops.topk_merge(*shard.unpack_topk(buf, world, nq, k), nq, k)
+        units, unit_name = nq, "queries/s"
+        alg_bytes = None
+        h2d_bytes = 4 * nq * dim
+        n = n_local
     else:  # bruteforce: dataset rows sharded across ranks, every rank sees all queries
         dim, nq, k = 768, args.queries, 10
         n_local = n // world if world > 1 else n
@@ -380,7 +407,7 @@ def main():
                 pa.free()
         except Exception as ex:  # report, never fake
             e2e = {"value": None, "unit": unit_name, "error": str(ex)[:200]}
-    elif args.workload == "bruteforce":
+    elif args.workload in ("bruteforce", "ivf"):
         qhost = bufs["queries"].to_numpy(np.float32)
         t0 = time.perf_counter()
         ke = min(K, 3)
@@ -398,7 +425,16 @@ def main():
 
     # ---------------------------------------------------------------------------------------------- roofline + cpu baseline
     peak, peak_src = measured_peaks()
-    if alg_bytes is not None:
+    if args.workload == "ivf":
+        # the list scan is the same exact fp32 kernel as the brute force; work = 3 flop per element pair over the probed lists
+        pairs = float(args.queries) * 32 * (n / 1024.0)
+        flop = 3.0 * pairs * 768
+        fp32_peak = 148 * 114.4 * 1.965e9 / 1e12     # measured lane-op rate of this B200 (tools/microbench: 114.4 lane-ops/clk/SM)
+        ach = flop / (kern_ms * 1e-3) / 1e12
+        roofline = {"bound": "fp32-alu", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak, "traffic": None,
+                    "kernel": "bf_topk_kernel over (list, query-tile) work items", "kernel_ms": kern_ms,
+                    "peak_source": "tools/microbench.cu on this pool's B200: 114.4 fp32 lane-ops/clk/SM x 148 SM x 1.965 GHz (exact 3-op form, no FMA)"}
+    elif alg_bytes is not None:
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                     "kernel": {"q6": "q6_kernel", "q1": "q1_kernel", "sum": "agg_kernel"}[args.workload], "kernel_ms": kern_ms,
@@ -433,8 +469,8 @@ def main():
 
     line = {
         "metric": wl["metric"], "value": value, "unit": unit_name, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "weak" if args.workload != "bruteforce" else "strong", "vs_baseline": None,
-        "dtype": {"q6": "f64", "q1": "f64", "sum": "int64", "bruteforce": "f32"}[args.workload], "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak" if args.workload not in ("bruteforce", "ivf") else "strong", "vs_baseline": None,
+        "dtype": {"q6": "f64", "q1": "f64", "sum": "int64", "bruteforce": "f32", "ivf": "f32"}[args.workload], "data": "synthetic",
         "config": {"workload": wl["name"], "rows_per_gpu": n, "l2": "inputs (%.1f GB per GPU) are larger than the 126 MB L2; no flush needed" % ((alg_bytes or 4.0 * n * 768) / 1e9),
                    "parallelism": "block-range shards x%d, NCCL all_gather of partial aggregates" % world if world > 1 else "1 GPU",
                    "timer": "CUDA events on the library stream (MoB200_TimerStart/Stop), max over ranks", "wall_ms_rank0": wall_ms},

@@ -255,6 +255,7 @@ int32_t MoB200_GenLineitem(uint64_t seed, uint64_t row0, uint64_t n, int32_t *sh
 int32_t MoB200_GenInt64(uint64_t seed, uint64_t row0, uint64_t n, int64_t *out, uint64_t *nulls, uint32_t null_per_mille);
 int32_t MoB200_GenVectorsF32(uint64_t seed, uint64_t row0, uint64_t n, int64_t dim, float *out,
                              const float *centers, int64_t ncenters, float sigma);
+int32_t MoB200_GatherRowsF32(float *dst, const float *src, const int64_t *idx, uint64_t m, int64_t dim);  /* device pointers */
 
 #ifdef __cplusplus
 }

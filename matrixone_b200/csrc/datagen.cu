@@ -78,6 +78,12 @@ __global__ void gen_vectors_kernel(uint64_t seed, uint64_t row0, uint64_t n, int
     }
 }
 
+__global__ void gather_rows_f32_kernel(const float *__restrict__ src, const int64_t *__restrict__ idx, uint64_t m, int64_t dim, float *__restrict__ dst) {
+    const uint64_t total = m * (uint64_t)dim;
+    for (uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; e < total; e += (uint64_t)gridDim.x * blockDim.x)
+        dst[e] = src[(uint64_t)idx[e / (uint64_t)dim] * (uint64_t)dim + e % (uint64_t)dim];
+}
+
 }  // namespace
 
 extern "C" {
@@ -110,6 +116,17 @@ int32_t MoB200_GenVectorsF32(uint64_t seed, uint64_t row0, uint64_t n, int64_t d
     if (!t.ready) return MO_RC_INTERNAL_ERROR;
     if (n == 0) return MO_RC_SUCCESS;
     gen_vectors_kernel<<<num_sms() * 16, 256, 0, t.stream>>>(seed, row0, n, dim, out, centers, ncenters, sigma);
+    MOB_LAUNCH_CHECK();
+    MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));
+    return MO_RC_SUCCESS;
+}
+
+// dst[i] = src[idx[i]] for whole rows (device pointers): lays an IVF dataset out list by list (ivfflat index build)
+int32_t MoB200_GatherRowsF32(float *dst, const float *src, const int64_t *idx, uint64_t m, int64_t dim) {
+    ThreadCtx &t = tctx();
+    if (!t.ready) return MO_RC_INTERNAL_ERROR;
+    if (m == 0) return MO_RC_SUCCESS;
+    gather_rows_f32_kernel<<<num_sms() * 16, 256, 0, t.stream>>>(src, idx, m, dim, dst);
     MOB_LAUNCH_CHECK();
     MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));
     return MO_RC_SUCCESS;

@@ -166,30 +166,59 @@ class IvfflatSearchIndex:
 
     def __init__(self, data, assign, centroids, metric=capi.METRIC_L2, lib=None):
         self.lib = lib or capi.load_library()
-        data = np.ascontiguousarray(data, dtype=np.float32)
         centroids = np.ascontiguousarray(centroids, dtype=np.float32)
-        self.n, self.dim = data.shape
-        self.nlist = centroids.shape[0]
+        self.nlist, self.dim = centroids.shape
         self.metric = int(metric)
+        assign = np.asarray(assign)
         order = np.argsort(assign, kind="stable")   # stable: rows of a list stay in table order
         counts = np.bincount(assign, minlength=self.nlist)
         self.offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
         self.row_ids = order.astype(np.int64)
-        self.d_data = DeviceBuffer.from_numpy(data[order], self.lib)
+        self.n = len(order)
+        self.d_ids = DeviceBuffer.from_numpy(self.row_ids, self.lib)
+        if isinstance(data, DeviceBuffer):          # resident entries: lay them out list by list on the device
+            self.d_data = DeviceBuffer(4 * self.n * self.dim, self.lib)
+            capi.check(self.lib.MoB200_GatherRowsF32(self.d_data.ptr, data.ptr, self.d_ids.ptr, self.n, self.dim), self.lib)
+        else:
+            data = np.ascontiguousarray(data, dtype=np.float32)
+            self.d_data = DeviceBuffer.from_numpy(data[order], self.lib)
         self.d_cent = DeviceBuffer.from_numpy(centroids, self.lib)
         self.d_off = DeviceBuffer.from_numpy(self.offsets, self.lib)
-        self.d_ids = DeviceBuffer.from_numpy(self.row_ids, self.lib)
+
+    @classmethod
+    def build(cls, data_dev, n, centroids, metric=capi.METRIC_L2, lib=None, chunk=500_000):
+        """index build on resident entries: centroid assignment = Productl2 (brute-force Search(limit=1) against the
+        centroids, pkg/sql/colexec/productl2/product_l2.go:317-407) run chunk by chunk, then the list-ordered layout"""
+        lib = lib or capi.load_library()
+        centroids = np.ascontiguousarray(centroids, dtype=np.float32)
+        dim = centroids.shape[1]
+        cidx = BruteForceIndex(centroids, dim, metric, lib=lib)
+        assign = np.empty(n, dtype=np.int32)
+        for r0 in range(0, n, chunk):
+            m = min(chunk, n - r0)
+            view = DeviceBuffer.__new__(DeviceBuffer)
+            view.lib, view.nbytes, view.ptr = lib, 4 * m * dim, data_dev.ptr + 4 * r0 * dim
+            keys, _ = cidx.search(view, 1)
+            view.ptr = None
+            assign[r0:r0 + m] = keys
+        cidx.destroy()
+        return cls(data_dev, assign, centroids, metric, lib)
 
     def search(self, queries, limit, nprobe, sqrt_out=False):
-        q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dim)
-        nq = q.shape[0]
+        if isinstance(queries, DeviceBuffer):
+            nq = queries.nbytes // (4 * self.dim)
+            qvec = Vector(data_ptr=queries.ptr, data_nbytes=queries.nbytes, length=nq)
+        else:
+            q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dim)
+            nq = q.shape[0]
+            qvec = Vector(data=q.reshape(-1), length=nq)
         keys = np.zeros(nq * limit, dtype=np.int64)
         dists = np.zeros(nq * limit, dtype=np.float64)
         p = _search_params(self.n, self.dim, nq, limit, self.metric, nprobe=nprobe, sqrt_out=int(sqrt_out), nlist=self.nlist)
         xcall(capi.XCALL_IVF_TOPK_F32, [
             Vector(data=keys, length=nq), Vector(data=dists, length=nq),
             Vector(data_ptr=self.d_data.ptr, data_nbytes=self.d_data.nbytes, length=self.n),
-            Vector(data=q.reshape(-1), length=nq), _params_vec(p),
+            qvec, _params_vec(p),
             Vector(data_ptr=self.d_cent.ptr, data_nbytes=self.d_cent.nbytes, length=self.nlist),
             Vector(data_ptr=self.d_off.ptr, data_nbytes=self.d_off.nbytes, length=self.nlist + 1),
             Vector(data_ptr=self.d_ids.ptr, data_nbytes=self.d_ids.nbytes, length=self.n)], nq)
