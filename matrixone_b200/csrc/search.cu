@@ -18,6 +18,7 @@
 // query block (Q x dim x 4 B = 30 MB at the BASELINE shape) stays L2 resident.
 // Work per launch: Q*N*dim element-pairs, 3 fp32 ops each (sub, mul, add) => 3*Q*N*dim flop; bytes N*dim*4 + Q*dim*4.
 #include "common.cuh"
+#include "search_internal.cuh"
 #include <cstring>
 #include <cfloat>
 #include <cmath>
@@ -426,10 +427,6 @@ int bruteforce_topk_device(ThreadCtx &t, const float *ddata, int64_t n, int dim,
     return MO_RC_SUCCESS;
 }
 
-bool tc_search_applicable(int64_t n, int dim, int64_t nq, int k, int metric);
-int bruteforce_topk_tc_device(ThreadCtx &t, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq, int k,
-                              int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d, float *dbg_scores);
-
 int xcall_bruteforce(mo_xcall_args_t *args, uint64_t len) {
     ThreadCtx &t = tctx();
     if (!t.ready) return MO_RC_INTERNAL_ERROR;
@@ -449,7 +446,7 @@ int xcall_bruteforce(mo_xcall_args_t *args, uint64_t len) {
     double *od = (double *)st.out(args[1].pdata, (size_t)P.nq * P.k * 8);
     if (st.failed) { st.finish(); return MO_RC_INTERNAL_ERROR; }
     if (tc_search_applicable(P.n, (int)P.dim, P.nq, P.k, P.metric))
-        rc = bruteforce_topk_tc_device(t, ddata, P.n, (int)P.dim, dq, P.nq, P.k, P.key_base, P.sqrt_out, ok, od, nullptr);
+        rc = bruteforce_topk_tc_device(t, ddata, P.n, (int)P.dim, dq, P.nq, P.k, P.key_base, P.sqrt_out, ok, od);
     else
         rc = bruteforce_topk_device(t, ddata, P.n, (int)P.dim, dq, P.nq, P.k, P.metric, P.key_base, P.sqrt_out, ok, od);
     int frc = st.finish();
@@ -494,13 +491,26 @@ __global__ void ivf_count_kernel(const int64_t *probes, int64_t npairs, int *cnt
     }
 }
 __global__ void ivf_fill_kernel(const int64_t *probes, int64_t npairs, int nprobe, const int *start, int *cursor,
-                                int32_t *bucket_q, int64_t *bucket_slot) {
+                                int32_t *bucket_q, int64_t *bucket_slot, int32_t *pair_pos) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npairs; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t l = probes[i];
-        if (l < 0) continue;
+        if (l < 0) { pair_pos[i] = -1; continue; }
         const int pos = start[l] + atomicAdd(&cursor[l], 1);
         bucket_q[pos] = (int32_t)(i / nprobe);
         bucket_slot[pos] = i;
+        pair_pos[i] = pos;
+    }
+}
+
+__global__ void ivf_gather_queries_kernel(const float *__restrict__ src, const int *__restrict__ idx, int m, int dim, float *__restrict__ dst) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < (int64_t)m * dim; e += (int64_t)gridDim.x * blockDim.x)
+        dst[e] = src[(int64_t)idx[e / dim] * dim + e % dim];
+}
+__global__ void ivf_scatter_kernel(const int64_t *__restrict__ sk, const double *__restrict__ sd, const int *__restrict__ idx, int m, int k,
+                                   int64_t *__restrict__ out_k, double *__restrict__ out_d) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < m * k; e += gridDim.x * blockDim.x) {
+        const int q = idx[e / k];
+        out_k[(size_t)q * k + e % k] = sk[e]; out_d[(size_t)q * k + e % k] = sd[e];
     }
 }
 
@@ -542,68 +552,107 @@ int xcall_ivf(mo_xcall_args_t *args, uint64_t len) {
     if (is_device_ptr(args[6].pdata)) { MOB_CUDA_TRY(cudaMemcpyAsync(offsets.data(), args[6].pdata, offsets.size() * 8, cudaMemcpyDeviceToHost, t.stream)); MOB_CUDA_TRY(cudaStreamSynchronize(t.stream)); }
     else memcpy(offsets.data(), args[6].pdata, offsets.size() * 8);
 
-    auto fail = [&](int code) { st.finish(); return code; };
-    // 1. probes[q][rank] = list id, ascending centroid distance
-    const int64_t npairs = P.nq * nprobe;
-    int64_t *probes = (int64_t *)st.tmp((size_t)npairs * 8);
-    double *probe_d = (double *)st.tmp((size_t)npairs * 8);
-    if (st.failed) return fail(MO_RC_INTERNAL_ERROR);
-    rc = bruteforce_topk_device(t, dcent, P.nlist, dim, dq, P.nq, nprobe, P.metric, 0, 0, probes, probe_d);
-    if (rc) return fail(rc);
-    // 2. invert: list -> (query, slot) buckets
-    int *cnt = (int *)st.tmp((size_t)P.nlist * 4 * 3);
-    int32_t *bucket_q = (int32_t *)st.tmp((size_t)npairs * 4);
-    int64_t *bucket_slot = (int64_t *)st.tmp((size_t)npairs * 8);
-    if (st.failed) return fail(MO_RC_INTERNAL_ERROR);
-    int *dstart = cnt + P.nlist, *cursor = cnt + 2 * P.nlist;
-    MOB_CUDA_TRY(cudaMemsetAsync(cnt, 0, (size_t)P.nlist * 4 * 3, t.stream));
-    ivf_count_kernel<<<num_sms() * 4, 256, 0, t.stream>>>(probes, npairs, cnt);
+    IvfPlan plan;
+    rc = ivf_make_plan(t, dcent, P.nlist, dim, dq, P.nq, nprobe, P.metric, plan);
+    if (rc) { st.finish(); return rc; }
+    if (tc_ivf_applicable(P.n, dim, P.nq, P.k, nprobe, P.metric)) {
+        std::vector<int> redo;
+        rc = ivf_tc_scan(t, plan, ddata, P.n, dim, dq, P.nq, offsets, drowids, P.k, P.sqrt_out, ok, od, redo);
+        if (!rc && !redo.empty()) {   // queries whose completeness could not be proven: exact scan, scattered back
+            const int m = (int)redo.size();
+            int *didx = (int *)st.tmp(sizeof(int) * (size_t)m);
+            float *sub = (float *)st.tmp(sizeof(float) * (size_t)m * dim);
+            int64_t *sk = (int64_t *)st.tmp(sizeof(int64_t) * (size_t)m * P.k);
+            double *sd = (double *)st.tmp(sizeof(double) * (size_t)m * P.k);
+            if (st.failed) { st.finish(); return MO_RC_INTERNAL_ERROR; }
+            MOB_CUDA_TRY(cudaMemcpyAsync(didx, redo.data(), sizeof(int) * (size_t)m, cudaMemcpyHostToDevice, t.stream));
+            MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));
+            ivf_gather_queries_kernel<<<num_sms() * 4, 256, 0, t.stream>>>(dq, didx, m, dim, sub);
+            MOB_LAUNCH_CHECK();
+            IvfPlan sp;
+            rc = ivf_make_plan(t, dcent, P.nlist, dim, sub, m, nprobe, P.metric, sp);
+            if (!rc) rc = ivf_exact_scan(t, sp, ddata, P.n, dim, sub, m, offsets, drowids, P.k, P.metric, P.sqrt_out, sk, sd);
+            if (!rc) { ivf_scatter_kernel<<<(unsigned)((m * P.k + 255) / 256), 256, 0, t.stream>>>(sk, sd, didx, m, P.k, ok, od); MOB_LAUNCH_CHECK(); }
+        }
+    } else {
+        rc = ivf_exact_scan(t, plan, ddata, P.n, dim, dq, P.nq, offsets, drowids, P.k, P.metric, P.sqrt_out, ok, od);
+    }
+    int frc = st.finish();
+    return rc ? rc : frc;
+}
+
+// 1. probes[q][rank] = list id by ascending centroid distance (findCentroids, ivfflat/search.go:292-311): the exact top-nprobe kernel
+// 2. invert: list -> bucket of (query, slot) pairs
+int ivf_make_plan(ThreadCtx &t, const float *dcent, int64_t nlist, int dim, const float *dq, int64_t nq, int nprobe, int metric, IvfPlan &plan) {
+    plan.nprobe = nprobe;
+    plan.npairs = nq * nprobe;
+    const int64_t npairs = plan.npairs;
+    plan.probes = (int64_t *)arena_alloc(t, (size_t)npairs * 8);
+    double *probe_d = (double *)arena_alloc(t, (size_t)npairs * 8);
+    int *cnt = (int *)arena_alloc(t, (size_t)nlist * 4 * 3);
+    plan.bucket_q = (int32_t *)arena_alloc(t, (size_t)npairs * 4);
+    plan.bucket_slot = (int64_t *)arena_alloc(t, (size_t)npairs * 8);
+    plan.pair_pos = (int32_t *)arena_alloc(t, (size_t)npairs * 4);
+    if (!plan.probes || !probe_d || !cnt || !plan.bucket_q || !plan.bucket_slot || !plan.pair_pos) return MO_RC_INTERNAL_ERROR;
+    int rc = bruteforce_topk_device(t, dcent, nlist, dim, dq, nq, nprobe, metric, 0, 0, plan.probes, probe_d);
+    if (rc) return rc;
+    int *dstart = cnt + nlist, *cursor = cnt + 2 * nlist;
+    MOB_CUDA_TRY(cudaMemsetAsync(cnt, 0, (size_t)nlist * 4 * 3, t.stream));
+    ivf_count_kernel<<<num_sms() * 4, 256, 0, t.stream>>>(plan.probes, npairs, cnt);
     MOB_LAUNCH_CHECK();
-    std::vector<int> hcnt((size_t)P.nlist), hstart((size_t)P.nlist);
-    MOB_CUDA_TRY(cudaMemcpyAsync(hcnt.data(), cnt, (size_t)P.nlist * 4, cudaMemcpyDeviceToHost, t.stream));
+    plan.hcnt.assign((size_t)nlist, 0); plan.hstart.assign((size_t)nlist, 0);
+    MOB_CUDA_TRY(cudaMemcpyAsync(plan.hcnt.data(), cnt, (size_t)nlist * 4, cudaMemcpyDeviceToHost, t.stream));
     MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));
     int run = 0;
-    for (int64_t l = 0; l < P.nlist; l++) { hstart[(size_t)l] = run; run += hcnt[(size_t)l]; }
-    MOB_CUDA_TRY(cudaMemcpyAsync(dstart, hstart.data(), (size_t)P.nlist * 4, cudaMemcpyHostToDevice, t.stream));
-    ivf_fill_kernel<<<num_sms() * 4, 256, 0, t.stream>>>(probes, npairs, nprobe, dstart, cursor, bucket_q, bucket_slot);
+    for (int64_t l = 0; l < nlist; l++) { plan.hstart[(size_t)l] = run; run += plan.hcnt[(size_t)l]; }
+    MOB_CUDA_TRY(cudaMemcpyAsync(dstart, plan.hstart.data(), (size_t)nlist * 4, cudaMemcpyHostToDevice, t.stream));
+    ivf_fill_kernel<<<num_sms() * 4, 256, 0, t.stream>>>(plan.probes, npairs, nprobe, dstart, cursor, plan.bucket_q, plan.bucket_slot, plan.pair_pos);
     MOB_LAUNCH_CHECK();
-    // 3. work items: (list, 64-query tile)
+    MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));   // hstart (pageable host memory) must stay valid until the copy above is done
+    return MO_RC_SUCCESS;
+}
+
+// 3. (list, 64-query tile) work items through the exact kernel; 4. merge the nprobe partial lists of each query, local row -> primary
+// key through row_ids, optional sqrt (DistanceTransformIvfflat)
+int ivf_exact_scan(ThreadCtx &t, const IvfPlan &plan, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq,
+                   const std::vector<int64_t> &offsets, const int64_t *drowids, int k, int metric, int sqrt_out, int64_t *ok, double *od) {
+    const int64_t nlist = (int64_t)offsets.size() - 1;
+    const int64_t npairs = plan.npairs;
     float *xnorm = nullptr, *qnorm = nullptr;
-    if (P.metric == MO_METRIC_COS) {
-        xnorm = (float *)st.tmp(sizeof(float) * (size_t)(P.n > 0 ? P.n : 1));
-        qnorm = (float *)st.tmp(sizeof(float) * (size_t)P.nq);
-        if (st.failed) return fail(MO_RC_INTERNAL_ERROR);
-        if (P.n > 0) { cos_norm_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(ddata, P.n, dim, xnorm); MOB_LAUNCH_CHECK(); }
-        cos_norm_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(dq, P.nq, dim, qnorm); MOB_LAUNCH_CHECK();
+    if (metric == MO_METRIC_COS) {
+        xnorm = (float *)arena_alloc(t, sizeof(float) * (size_t)(n > 0 ? n : 1));
+        qnorm = (float *)arena_alloc(t, sizeof(float) * (size_t)nq);
+        if (!xnorm || !qnorm) return MO_RC_INTERNAL_ERROR;
+        if (n > 0) { cos_norm_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(ddata, n, dim, xnorm); MOB_LAUNCH_CHECK(); }
+        cos_norm_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(dq, nq, dim, qnorm); MOB_LAUNCH_CHECK();
     }
     std::vector<WorkDesc> items;
-    for (int64_t l = 0; l < P.nlist; l++) {
-        const int c = hcnt[(size_t)l];
+    for (int64_t l = 0; l < nlist; l++) {
+        const int c = plan.hcnt[(size_t)l];
         if (c == 0 || offsets[(size_t)l + 1] <= offsets[(size_t)l]) continue;
         for (int q0 = 0; q0 < c; q0 += TQ) {
             WorkDesc w;
-            w.data = ddata; w.n = P.n; w.row_begin = offsets[(size_t)l]; w.row_end = offsets[(size_t)l + 1];
-            w.queries = dq; w.nq_total = P.nq; w.qidx = bucket_q + hstart[(size_t)l] + q0; w.q0 = 0;
+            w.data = ddata; w.n = n; w.row_begin = offsets[(size_t)l]; w.row_end = offsets[(size_t)l + 1];
+            w.queries = dq; w.nq_total = nq; w.qidx = plan.bucket_q + plan.hstart[(size_t)l] + q0; w.q0 = 0;
             w.nq_local = c - q0 < TQ ? c - q0 : TQ;
-            w.slot_of = bucket_slot + hstart[(size_t)l] + q0; w.range = 0; w.xnorm = xnorm; w.qnorm = qnorm;
+            w.slot_of = plan.bucket_slot + plan.hstart[(size_t)l] + q0; w.range = 0; w.xnorm = xnorm; w.qnorm = qnorm;
             items.push_back(w);
         }
     }
-    float *part_d = (float *)st.tmp(sizeof(float) * (size_t)(npairs * P.k));
-    int32_t *part_i = (int32_t *)st.tmp(sizeof(int32_t) * (size_t)(npairs * P.k));
-    WorkDesc *ditems = (WorkDesc *)st.tmp(sizeof(WorkDesc) * (items.size() ? items.size() : 1));
-    if (st.failed) return fail(MO_RC_INTERNAL_ERROR);
-    MOB_CUDA_TRY(cudaMemsetAsync(part_i, 0xff, sizeof(int32_t) * (size_t)(npairs * P.k), t.stream));   // -1 = empty slot
+    float *part_d = (float *)arena_alloc(t, sizeof(float) * (size_t)(npairs * k));
+    int32_t *part_i = (int32_t *)arena_alloc(t, sizeof(int32_t) * (size_t)(npairs * k));
+    WorkDesc *ditems = (WorkDesc *)arena_alloc(t, sizeof(WorkDesc) * (items.size() ? items.size() : 1));
+    if (!part_d || !part_i || !ditems) return MO_RC_INTERNAL_ERROR;
+    MOB_CUDA_TRY(cudaMemsetAsync(part_i, 0xff, sizeof(int32_t) * (size_t)(npairs * k), t.stream));   // -1 = empty slot
     if (!items.empty()) {
         MOB_CUDA_TRY(cudaMemcpyAsync(ditems, items.data(), sizeof(WorkDesc) * items.size(), cudaMemcpyHostToDevice, t.stream));
         MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));
-        rc = launch_bf_metric(t, P.metric, ditems, (int)items.size(), dim, P.k, part_d, part_i);
-        if (rc) return fail(rc);
+        int rc = launch_bf_metric(t, metric, ditems, (int)items.size(), dim, k, part_d, part_i);
+        if (rc) return rc;
     }
-    // 4. merge the nprobe partial lists of each query; local row -> primary key through row_ids; optional sqrt
-    topk_merge_kernel<<<(unsigned)((P.nq + 127) / 128), 128, 0, t.stream>>>(P.nq, P.k, nprobe, P.nq, part_d, part_i, nullptr, nullptr, drowids, 0, P.sqrt_out, 1, ok, od);
+    topk_merge_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, t.stream>>>(nq, k, plan.nprobe, nq, part_d, part_i, nullptr, nullptr, drowids, 0, sqrt_out, 1, ok, od);
     MOB_LAUNCH_CHECK();
-    return st.finish();
+    return MO_RC_SUCCESS;
 }
 
 }  // namespace mob

@@ -1,0 +1,34 @@
+// search_internal.cuh -- declarations shared by search.cu (exact kernels) and tcsearch.cu (tensor-core candidate pass)
+#pragma once
+#include "common.cuh"
+#include <vector>
+
+namespace mob {
+
+// IVF probe plan: which lists every query scans, inverted into per-list buckets of (query, slot) pairs
+struct IvfPlan {
+    int nprobe = 0;
+    int64_t npairs = 0;            // nq * nprobe
+    int64_t *probes = nullptr;     // [nq][nprobe] list ids by ascending centroid distance (-1 = none)       (device)
+    int32_t *bucket_q = nullptr;   // [npairs] query of every bucket entry, entries of one list are contiguous  (device)
+    int64_t *bucket_slot = nullptr;// [npairs] q * nprobe + rank of every bucket entry                          (device)
+    int32_t *pair_pos = nullptr;   // [npairs] inverse map: position of pair (q, rank) in the buckets, -1 = none (device)
+    std::vector<int> hcnt, hstart; // per list: bucket size / first position                                    (host)
+};
+
+int bruteforce_topk_device(ThreadCtx &t, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq, int k, int metric,
+                           int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d);
+int ivf_make_plan(ThreadCtx &t, const float *dcent, int64_t nlist, int dim, const float *dq, int64_t nq, int nprobe, int metric, IvfPlan &plan);
+int ivf_exact_scan(ThreadCtx &t, const IvfPlan &plan, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq,
+                   const std::vector<int64_t> &offsets, const int64_t *drowids, int k, int metric, int sqrt_out, int64_t *ok, double *od);
+
+bool tc_search_applicable(int64_t n, int dim, int64_t nq, int k, int metric);
+int bruteforce_topk_tc_device(ThreadCtx &t, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq, int k,
+                              int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d);
+bool tc_ivf_applicable(int64_t n, int dim, int64_t nq, int k, int nprobe, int metric);
+// returns the queries whose completeness proof failed in `redo` (their rows of ok/od are still filled with best-effort results)
+int ivf_tc_scan(ThreadCtx &t, const IvfPlan &plan, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq,
+                const std::vector<int64_t> &offsets, const int64_t *drowids, int k, int sqrt_out, int64_t *ok, double *od,
+                std::vector<int> &redo);
+
+}  // namespace mob

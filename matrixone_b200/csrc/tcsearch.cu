@@ -23,6 +23,7 @@
 // Work per launch: 2 * Q * N * K' flop on the tensor pipe (K' = 2304 for dim 768) + exact re-scoring of Q * KR rows.
 #include "common.cuh"
 #include "godist.cuh"
+#include "search_internal.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cstring>
@@ -113,14 +114,14 @@ __device__ __forceinline__ unsigned long long make_desc(unsigned smem_addr) {
 // instruction descriptor (UMMA::InstrDescriptor): D=F32 (bit 4), A=BF16 (bit 7), B=BF16 (bit 10), K-major both, N>>3 at 17, M>>4 at 24
 constexpr unsigned kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
 
-struct TcUnit { int m0; int n_begin; int n_end; int range; };   // one work unit: 128 queries x rows [n_begin, n_end)
+// one work unit: up to 128 rows of the A' operand (queries) x dataset rows [n_begin, n_end); lists are written at out_base + row
+struct TcUnit { int a_row0; int a_valid; int n_begin; int n_end; long long out_base; };
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                     const TcUnit *__restrict__ units, int nunits, int kprime /* K' */, int nq, int n,
+                     const TcUnit *__restrict__ units, int nunits, int kprime /* K' */,
                      const float *__restrict__ qnorm, const float *__restrict__ xnorm,
-                     float *__restrict__ part_d, int *__restrict__ part_i, float *__restrict__ part_thr,
-                     float *__restrict__ dbg_scores) {
+                     float *__restrict__ part_d, int *__restrict__ part_i, float *__restrict__ part_thr) {
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B atoms need 1024-byte alignment in the shared window: align by hand (the launch adds 1024 spare bytes)
     TcSmem &S = *reinterpret_cast<TcSmem *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -152,7 +153,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     for (int kb = 0; kb < nkb; kb++) {
                         mbar_wait(&S.empty[stage], phase ^ 1);
                         mbar_expect_tx(&S.full[stage], A_STAGE_BYTES + B_STAGE_BYTES);
-                        tma_load_2d(&map_a, &S.full[stage], S.a[stage], kb * BK, U.m0);
+                        tma_load_2d(&map_a, &S.full[stage], S.a[stage], kb * BK, U.a_row0);
                         tma_load_2d(&map_b, &S.full[stage], S.b[stage], kb * BK, n0);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
@@ -191,13 +192,13 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         unsigned tile = 0;
         for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
             const TcUnit U = units[u];
-            const int q = U.m0 + e;
-            const float qn = q < nq ? qnorm[q] : 0.f;
+            const bool valid_row = e < U.a_valid;
+            const float qn = valid_row ? qnorm[U.a_row0 + e] : 0.f;
             int cnt = 0; float thr = INFINITY;
             for (int n0 = U.n_begin; n0 < U.n_end; n0 += BN, tile++) {
                 const unsigned acc = tile & 1;
                 // |x|^2 of this tile's rows -> shared (2 per thread); named barrier over the 128 epilogue threads
-                for (int j = e; j < BN; j += 128) S.xn[acc][j] = (n0 + j < n) ? xnorm[n0 + j] : INFINITY;
+                for (int j = e; j < BN; j += 128) S.xn[acc][j] = (n0 + j < U.n_end) ? xnorm[n0 + j] : INFINITY;
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 mbar_wait(&S.tmem_full[acc], (tile >> 1) & 1);
                 tc_fence_after();
@@ -208,7 +209,6 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
                         const float d = (qn + S.xn[acc][c + j]) - 2.0f * v[j];   // +inf for rows past the end
-                        if (dbg_scores && q < nq && n0 + c + j < n) dbg_scores[(size_t)q * n + n0 + c + j] = d;
                         if (d < thr) {
                             const int id = n0 + c + j;
                             int pos;
@@ -224,10 +224,10 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&S.tmem_empty[acc]);   // 4 arrivals (one per epilogue warp) release the accumulator
             }
-            if (q < nq) {
-                const size_t base = ((size_t)U.range * nq + q) * KP;
+            if (valid_row) {
+                const size_t base = (size_t)(U.out_base + e) * KP;
                 for (int j = 0; j < KP; j++) { part_d[base + j] = j < cnt ? S.ld[j][e] : INFINITY; part_i[base + j] = j < cnt ? S.li[j][e] : -1; }
-                part_thr[(size_t)U.range * nq + q] = thr;       // every row of this range that is NOT listed has d~ >= thr
+                part_thr[U.out_base + e] = thr;                  // every row of this unit that is NOT listed has d~ >= thr
             }
         }
     }
@@ -239,7 +239,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 // ---- operand preparation -------------------------------------------------------------------------------------------------
 // mode 0: A' = [hi | hi | lo] (queries), mode 1: B' = [hi | lo | hi] (dataset).  One warp per row; pads K' with zeros.
 __global__ void split_kernel(const float *__restrict__ x, int64_t n, int dim, int kprime, int mode, __nv_bfloat16 *__restrict__ out,
-                             float *__restrict__ norm, float *__restrict__ absmax, int *__restrict__ nonfinite) {
+                             float *__restrict__ norm, float *__restrict__ absmax, int *__restrict__ nonfinite) {  // absmax optional
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t r = warp; r < n; r += nwarps) {
@@ -294,29 +294,35 @@ constexpr int KR = 32;   // candidates re-scored exactly per query
 
 // one thread per query: R-way merge of the (ascending) approximate lists -> KR best candidate ids; t_excl = smallest approximate
 // distance any row NOT among them can have (first unconsumed entry of every list, and the list-full threshold of every range)
+// list (q, r) lives at index  pos_map ? pos_map[q * R + r] (-1 = no such list)  :  r * nq + q
 __global__ void tc_merge_kernel(int nq, int R, const float *__restrict__ part_d, const int *__restrict__ part_i,
-                                const float *__restrict__ part_thr, int *__restrict__ cand, float *__restrict__ t_excl) {
+                                const float *__restrict__ part_thr, const int *__restrict__ pos_map, int *__restrict__ cand, float *__restrict__ t_excl) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
+    auto lst = [&](int r) -> long long { return pos_map ? (long long)pos_map[(size_t)q * R + r] : (long long)r * nq + q; };
     unsigned char head[64];
     for (int r = 0; r < R; r++) head[r] = 0;
     for (int j = 0; j < KR; j++) {
         int best = -1; float bd = INFINITY;
         for (int r = 0; r < R; r++) {
             if (head[r] >= KP) continue;
-            const size_t idx = ((size_t)r * nq + q) * KP + head[r];
+            const long long L = lst(r);
+            if (L < 0) { head[r] = KP; continue; }
+            const size_t idx = (size_t)L * KP + head[r];
             if (part_i[idx] < 0) { head[r] = KP; continue; }
             const float d = part_d[idx];
             if (best < 0 || d < bd) { best = r; bd = d; }
         }
         if (best < 0) { cand[(size_t)q * KR + j] = -1; continue; }
-        cand[(size_t)q * KR + j] = part_i[((size_t)best * nq + q) * KP + head[best]];
+        cand[(size_t)q * KR + j] = part_i[(size_t)lst(best) * KP + head[best]];
         head[best]++;
     }
     float t = INFINITY;
     for (int r = 0; r < R; r++) {
-        t = fminf(t, part_thr[(size_t)r * nq + q]);
-        if (head[r] < KP) { const size_t idx = ((size_t)r * nq + q) * KP + head[r]; if (part_i[idx] >= 0) t = fminf(t, part_d[idx]); }
+        const long long L = lst(r);
+        if (L < 0) continue;
+        t = fminf(t, part_thr[L]);
+        if (head[r] < KP) { const size_t idx = (size_t)L * KP + head[r]; if (part_i[idx] >= 0) t = fminf(t, part_d[idx]); }
     }
     t_excl[q] = t;
 }
@@ -351,13 +357,15 @@ __global__ void tc_max_kernel(const float *__restrict__ v, int64_t n, float *out
 // so d_k + eps_tc + eps_go < t_excl  =>  no excluded row can displace the k-th result.  flag = 1 when the proof fails.
 __global__ void tc_final_kernel(int nq, int k, int64_t n_rows, int dim, const int *__restrict__ cand, const float *__restrict__ exact,
                                 const float *__restrict__ t_excl, const float *__restrict__ qnorm, const float *__restrict__ xnorm_max,
-                                int64_t key_base, int sqrt_out, int64_t *__restrict__ out_k, double *__restrict__ out_d, int *__restrict__ flags) {
+                                const int64_t *__restrict__ id_map, int64_t key_base, int sqrt_out, int64_t *__restrict__ out_k,
+                                double *__restrict__ out_d, int *__restrict__ flags) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
-    float d[KR]; int id[KR]; int m = 0;
+    float d[KR]; int64_t id[KR]; int m = 0;
     for (int j = 0; j < KR; j++) {
-        const int c = cand[(size_t)q * KR + j];
-        if (c < 0) continue;
+        const int lc = cand[(size_t)q * KR + j];
+        if (lc < 0) continue;
+        const int64_t c = id_map ? id_map[lc] : (int64_t)lc + key_base;   // final key; ties are ordered by it
         const float v = exact[(size_t)q * KR + j];
         int pos = m++;
         while (pos > 0 && (v < d[pos - 1] || (v == d[pos - 1] && c < id[pos - 1]))) { d[pos] = d[pos - 1]; id[pos] = id[pos - 1]; pos--; }
@@ -367,7 +375,7 @@ __global__ void tc_final_kernel(int nq, int k, int64_t n_rows, int dim, const in
     const int pad = k - total;
     int64_t *ok = out_k + (size_t)q * k; double *od = out_d + (size_t)q * k;
     for (int j = 0; j < pad; j++) { ok[j] = -1; od[j] = 0.0; }
-    for (int j = 0; j < total; j++) { ok[pad + j] = (int64_t)id[j] + key_base; od[pad + j] = sqrt_out ? sqrt((double)d[j]) : (double)d[j]; }
+    for (int j = 0; j < total; j++) { ok[pad + j] = id[j]; od[pad + j] = sqrt_out ? sqrt((double)d[j]) : (double)d[j]; }
     const float t = t_excl[q];
     bool proven;
     if (t == INFINITY) proven = true;                       // nothing was excluded (every row of every range is listed)
@@ -381,6 +389,24 @@ __global__ void tc_final_kernel(int nq, int k, int64_t n_rows, int dim, const in
         proven = d[k - 1] + eps_tc + eps_go < t;
     }
     flags[q] = proven ? 0 : 1;
+}
+
+__global__ void tc_fill_kernel(float *thr, int *ids, int64_t nlists) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nlists * KP; i += (int64_t)gridDim.x * blockDim.x) {
+        ids[i] = -1;
+        if (i < nlists) thr[i] = INFINITY;
+    }
+}
+// dst row g = src row idx[g] (rows of kprime bf16 = 16-byte multiples); also gathers the fp32 norms
+__global__ void gather_split_rows_kernel(const __nv_bfloat16 *__restrict__ src, const float *__restrict__ snorm, const int32_t *__restrict__ idx,
+                                         int64_t m, int kprime, __nv_bfloat16 *__restrict__ dst, float *__restrict__ dnorm) {
+    const int vec_per_row = kprime / 8;   // int4 = 8 bf16
+    const int4 *s4 = reinterpret_cast<const int4 *>(src); int4 *d4 = reinterpret_cast<int4 *>(dst);
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < m * vec_per_row; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t g = e / vec_per_row; const int v = (int)(e % vec_per_row);
+        d4[e] = s4[(int64_t)idx[g] * vec_per_row + v];
+        if (v == 0) dnorm[g] = snorm[idx[g]];
+    }
 }
 
 __global__ void gather_rows_kernel(const float *__restrict__ src, const int *__restrict__ idx, int m, int dim, float *__restrict__ dst) {
@@ -399,32 +425,110 @@ __global__ void scatter_results_kernel(const int64_t *__restrict__ sk, const dou
 
 namespace mob {
 
-// Tensor-core candidate pass.  Outputs (device): part_d/part_i [R][nq][KP] approximate (distance, local row id) lists, part_thr [R][nq].
-// Returns the number of row ranges R and the per-list length KP through out params.
-int tc_candidates_device(ThreadCtx &t, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq,
-                         float **part_d, int **part_i, float **part_thr, int *R_out, int *kp_out, float *dbg_scores,
-                         float **qnorm_out, float **xnorm_out, float **qabs_out, float **xabs_out) {
-    const int kprime = ((3 * dim + BK - 1) / BK) * BK;
-    __nv_bfloat16 *a = (__nv_bfloat16 *)arena_alloc(t, (size_t)nq * kprime * 2 + 1024);
-    __nv_bfloat16 *b = (__nv_bfloat16 *)arena_alloc(t, (size_t)n * kprime * 2 + 1024);
-    float *qn = (float *)arena_alloc(t, (size_t)nq * 4), *xn = (float *)arena_alloc(t, (size_t)n * 4);
-    float *qa = (float *)arena_alloc(t, (size_t)nq * 4), *xa = (float *)arena_alloc(t, (size_t)n * 4);
-    if (!a || !b || !qn || !xn || !qa || !xa) return MO_RC_INTERNAL_ERROR;
+int g_search_mode = 0;          // 0 = auto, 1 = exact kernel only, 2 = force the tensor-core path (MoB200_SetTuning("search_mode"))
+int g_last_tc_fallbacks = -1;   // queries of the last tensor-core search that failed the completeness proof and were re-run exactly
+
+struct TcOperand { __nv_bfloat16 *bf = nullptr; float *norm = nullptr; int kprime = 0; };
+
+// split an fp32 row-major matrix into the K-concatenated bf16 operand; *nonfinite (device flag) is raised on Inf/NaN
+static int tc_prepare(ThreadCtx &t, const float *x, int64_t n, int dim, int mode, int *dnonfinite, TcOperand &op) {
+    op.kprime = ((3 * dim + BK - 1) / BK) * BK;
+    op.bf = (__nv_bfloat16 *)arena_alloc(t, (size_t)(n > 0 ? n : 1) * op.kprime * 2 + 1024);
+    op.norm = (float *)arena_alloc(t, (size_t)(n > 0 ? n : 1) * 4);
+    if (!op.bf || !op.norm) return MO_RC_INTERNAL_ERROR;
+    if (n > 0) { split_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(x, n, dim, op.kprime, mode, op.bf, op.norm, nullptr, dnonfinite); MOB_LAUNCH_CHECK(); }
+    return MO_RC_SUCCESS;
+}
+
+// run the candidate kernel over `units`; lists are written at unit.out_base + row (nlists lists in total, pre-initialised empty)
+static int tc_run_units(ThreadCtx &t, const TcOperand &A, int64_t a_rows, const TcOperand &B, int64_t b_rows, const std::vector<TcUnit> &units,
+                        int64_t nlists, float **part_d, int **part_i, float **part_thr) {
+    CUtensorMap map_a, map_b;
+    int rc = make_map(&map_a, A.bf, (uint64_t)a_rows, (uint64_t)A.kprime, BM);
+    if (rc) return rc;
+    rc = make_map(&map_b, B.bf, (uint64_t)b_rows, (uint64_t)B.kprime, BN);
+    if (rc) return rc;
+    TcUnit *dunits = (TcUnit *)arena_alloc(t, sizeof(TcUnit) * (units.size() ? units.size() : 1));
+    *part_d = (float *)arena_alloc(t, sizeof(float) * (size_t)nlists * KP);
+    *part_i = (int *)arena_alloc(t, sizeof(int) * (size_t)nlists * KP);
+    *part_thr = (float *)arena_alloc(t, sizeof(float) * (size_t)nlists);
+    if (!dunits || !*part_d || !*part_i || !*part_thr) return MO_RC_INTERNAL_ERROR;
+    tc_fill_kernel<<<num_sms() * 4, 256, 0, t.stream>>>(*part_thr, *part_i, nlists);
+    MOB_LAUNCH_CHECK();
+    if (units.empty()) return MO_RC_SUCCESS;
+    MOB_CUDA_TRY(cudaMemcpyAsync(dunits, units.data(), sizeof(TcUnit) * units.size(), cudaMemcpyHostToDevice, t.stream));
+    MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));
+    static bool attr = false;
+    const size_t smem = sizeof(TcSmem) + 1024;
+    if (!attr) { MOB_CUDA_TRY(cudaFuncSetAttribute(tc_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    int grid = num_sms();
+    if (grid > (int)units.size()) grid = (int)units.size();
+    cudaEventRecord(t.kev0, t.stream);
+    tc_candidates_kernel<<<grid, kTcThreads, smem, t.stream>>>(map_a, map_b, dunits, (int)units.size(), A.kprime, A.norm, B.norm, *part_d, *part_i, *part_thr);
+    cudaEventRecord(t.kev1, t.stream);
+    MOB_LAUNCH_CHECK();
+    return MO_RC_SUCCESS;
+}
+
+// merge approximate lists -> exact re-score -> final order + proof; returns the queries whose proof failed
+static int tc_finish(ThreadCtx &t, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq, int k, int R, const int *pos_map,
+                     const float *part_d, const int *part_i, const float *part_thr, const float *qnorm, const float *xnorm,
+                     const int64_t *id_map, int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d, std::vector<int> &redo) {
+    int *cand = (int *)arena_alloc(t, sizeof(int) * (size_t)nq * KR);
+    float *exact = (float *)arena_alloc(t, sizeof(float) * (size_t)nq * KR);
+    float *t_excl = (float *)arena_alloc(t, sizeof(float) * (size_t)nq + 16);
+    int *flags = (int *)arena_alloc(t, sizeof(int) * (size_t)nq);
+    if (!cand || !exact || !t_excl || !flags) return MO_RC_INTERNAL_ERROR;
+    float *xmax = t_excl + nq;
+    MOB_CUDA_TRY(cudaMemsetAsync(xmax, 0, 4, t.stream));
+    tc_max_kernel<<<num_sms() * 2, 256, 0, t.stream>>>(xnorm, n, xmax);
+    MOB_LAUNCH_CHECK();
+    tc_merge_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, t.stream>>>((int)nq, R, part_d, part_i, part_thr, pos_map, cand, t_excl);
+    MOB_LAUNCH_CHECK();
+    tc_rescore_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(ddata, dq, dim, (int)nq, cand, exact);
+    MOB_LAUNCH_CHECK();
+    tc_final_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, t.stream>>>((int)nq, k, n, dim, cand, exact, t_excl, qnorm, xmax, id_map, key_base, sqrt_out, out_k, out_d, flags);
+    MOB_LAUNCH_CHECK();
+    std::vector<int> hflags((size_t)nq);
+    MOB_CUDA_TRY(cudaMemcpyAsync(hflags.data(), flags, sizeof(int) * (size_t)nq, cudaMemcpyDeviceToHost, t.stream));
+    MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));
+    redo.clear();
+    for (int64_t q = 0; q < nq; q++) if (hflags[(size_t)q]) redo.push_back((int)q);
+    return MO_RC_SUCCESS;
+}
+
+bool tc_search_applicable(int64_t n, int dim, int64_t nq, int k, int metric) {
+    if (g_search_mode == 1) return false;
+    const bool shape_ok = (metric == MO_METRIC_L2 || metric == MO_METRIC_L2SQ) && k >= 1 && k <= KP && dim >= 16 && n >= BN && n < (1ll << 31) - BN;
+    if (g_search_mode == 2) return shape_ok;
+    return shape_ok && nq >= 256 && n >= 16384 && dim >= 64;   // below this the exact kernel wins (operand split + launch overheads)
+}
+
+bool tc_ivf_applicable(int64_t n, int dim, int64_t nq, int k, int nprobe, int metric) {
+    if (g_search_mode == 1) return false;
+    const bool shape_ok = (metric == MO_METRIC_L2 || metric == MO_METRIC_L2SQ) && k >= 1 && k <= KP && dim >= 16 && n >= 1 && n < (1ll << 31) - BN &&
+                          nprobe <= 64 && nq * (int64_t)nprobe < (1ll << 31);
+    if (g_search_mode == 2) return shape_ok;
+    return shape_ok && nq * (int64_t)nprobe >= 8192 && dim >= 64;
+}
+
+// Brute-force top-k through the tensor-core candidate pass; results are the exact answer (see file header).
+int bruteforce_topk_tc_device(ThreadCtx &t, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq, int k,
+                              int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d) {
     int *dnonfinite = (int *)arena_alloc(t, 4);
     if (!dnonfinite) return MO_RC_INTERNAL_ERROR;
     MOB_CUDA_TRY(cudaMemsetAsync(dnonfinite, 0, 4, t.stream));
-    split_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(dq, nq, dim, kprime, 0, a, qn, qa, dnonfinite);
-    MOB_LAUNCH_CHECK();
-    split_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(ddata, n, dim, kprime, 1, b, xn, xa, dnonfinite);
-    MOB_LAUNCH_CHECK();
+    TcOperand A, B;
+    int rc = tc_prepare(t, dq, nq, dim, 0, dnonfinite, A);
+    if (!rc) rc = tc_prepare(t, ddata, n, dim, 1, dnonfinite, B);
+    if (rc) return rc;
     int hnonfinite = 0;
-    { int rcx = read_back(t, &hnonfinite, dnonfinite, 4); if (rcx) return rcx; }
-    if (hnonfinite) { *R_out = 0; return MO_RC_SUCCESS; }   // R == 0 tells the caller to use the exact kernel
-    CUtensorMap map_a, map_b;
-    int rc = make_map(&map_a, a, (uint64_t)nq, (uint64_t)kprime, BM);
+    rc = read_back(t, &hnonfinite, dnonfinite, 4);
     if (rc) return rc;
-    rc = make_map(&map_b, b, (uint64_t)n, (uint64_t)kprime, BN);
-    if (rc) return rc;
+    if (hnonfinite) {   // the error bound of the tensor-core pass does not apply to Inf/NaN inputs
+        g_last_tc_fallbacks = (int)nq;
+        return bruteforce_topk_device(t, ddata, n, dim, dq, nq, k, MO_METRIC_L2SQ, key_base, sqrt_out, out_k, out_d);
+    }
     // work units: (query tile, row range); ranges sized so that units ~ a whole number of waves over the SMs
     const int mt = (int)((nq + BM - 1) / BM);
     const int64_t ntiles = (n + BN - 1) / BN;
@@ -437,75 +541,17 @@ int tc_candidates_device(ThreadCtx &t, const float *ddata, int64_t n, int dim, c
     std::vector<TcUnit> units;
     for (int r = 0; r < R; r++)
         for (int m = 0; m < mt; m++) {
-            TcUnit u; u.m0 = m * BM; u.n_begin = (int)(r * tiles_per * BN); u.n_end = (int)((r + 1) * tiles_per * BN < n ? (r + 1) * tiles_per * BN : n); u.range = r;
+            TcUnit u; u.a_row0 = m * BM; u.a_valid = (int)(nq - u.a_row0 < BM ? nq - u.a_row0 : BM);
+            u.n_begin = (int)(r * tiles_per * BN); u.n_end = (int)((r + 1) * tiles_per * BN < n ? (r + 1) * tiles_per * BN : n);
+            u.out_base = (long long)r * nq + u.a_row0;
             if (u.n_begin < u.n_end) units.push_back(u);
         }
-    TcUnit *dunits = (TcUnit *)arena_alloc(t, sizeof(TcUnit) * units.size());
-    *part_d = (float *)arena_alloc(t, sizeof(float) * (size_t)R * nq * KP);
-    *part_i = (int *)arena_alloc(t, sizeof(int) * (size_t)R * nq * KP);
-    *part_thr = (float *)arena_alloc(t, sizeof(float) * (size_t)R * nq);
-    if (!dunits || !*part_d || !*part_i || !*part_thr) return MO_RC_INTERNAL_ERROR;
-    MOB_CUDA_TRY(cudaMemcpyAsync(dunits, units.data(), sizeof(TcUnit) * units.size(), cudaMemcpyHostToDevice, t.stream));
-    MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));
-    static bool attr = false;
-    const size_t smem = sizeof(TcSmem) + 1024;
-    if (!attr) { MOB_CUDA_TRY(cudaFuncSetAttribute(tc_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-    int grid = num_sms();
-    if (grid > (int)units.size()) grid = (int)units.size();
-    cudaEventRecord(t.kev0, t.stream);
-    tc_candidates_kernel<<<grid, kTcThreads, smem, t.stream>>>(map_a, map_b, dunits, (int)units.size(), kprime, (int)nq, (int)n, qn, xn,
-                                                                *part_d, *part_i, *part_thr, dbg_scores);
-    cudaEventRecord(t.kev1, t.stream);
-    MOB_LAUNCH_CHECK();
-    *R_out = R; *kp_out = KP;
-    *qnorm_out = qn; *xnorm_out = xn; *qabs_out = qa; *xabs_out = xa;
-    return MO_RC_SUCCESS;
-}
-
-int bruteforce_topk_device(ThreadCtx &t, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq, int k, int metric,
-                           int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d);
-
-int g_search_mode = 0;          // 0 = auto, 1 = exact kernel only, 2 = force the tensor-core path (MoB200_SetTuning("search_mode"))
-int g_last_tc_fallbacks = -1;   // queries of the last tensor-core search that failed the completeness proof and were re-run exactly
-
-bool tc_search_applicable(int64_t n, int dim, int64_t nq, int k, int metric) {
-    if (g_search_mode == 1) return false;
-    const bool shape_ok = (metric == MO_METRIC_L2 || metric == MO_METRIC_L2SQ) && k >= 1 && k <= KP && dim >= 16 && n >= BN && n < (1ll << 31) - BN;
-    if (g_search_mode == 2) return shape_ok;
-    return shape_ok && nq >= 256 && n >= 16384 && dim >= 64;   // below this the exact kernel wins (operand split + launch overheads)
-}
-
-// Brute-force top-k through the tensor-core candidate pass; results are the exact answer (see file header).
-int bruteforce_topk_tc_device(ThreadCtx &t, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq, int k,
-                              int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d, float *dbg_scores) {
-    float *part_d, *part_thr, *qn, *xn, *qa, *xa; int *part_i; int R = 0, kp = 0;
-    int rc = tc_candidates_device(t, ddata, n, dim, dq, nq, &part_d, &part_i, &part_thr, &R, &kp, dbg_scores, &qn, &xn, &qa, &xa);
+    float *part_d, *part_thr; int *part_i;
+    rc = tc_run_units(t, A, nq, B, n, units, (int64_t)R * nq, &part_d, &part_i, &part_thr);
     if (rc) return rc;
-    if (R == 0) {   // non-finite inputs: the error bound of the tensor-core pass does not apply
-        g_last_tc_fallbacks = (int)nq;
-        return bruteforce_topk_device(t, ddata, n, dim, dq, nq, k, MO_METRIC_L2SQ, key_base, sqrt_out, out_k, out_d);
-    }
-    if (R > 64) { set_error("tc search: too many row ranges"); return MO_RC_INTERNAL_ERROR; }
-    int *cand = (int *)arena_alloc(t, sizeof(int) * (size_t)nq * KR);
-    float *exact = (float *)arena_alloc(t, sizeof(float) * (size_t)nq * KR);
-    float *t_excl = (float *)arena_alloc(t, sizeof(float) * (size_t)nq + 16);
-    int *flags = (int *)arena_alloc(t, sizeof(int) * (size_t)nq);
-    if (!cand || !exact || !t_excl || !flags) return MO_RC_INTERNAL_ERROR;
-    float *xmax = t_excl + nq;
-    MOB_CUDA_TRY(cudaMemsetAsync(xmax, 0, 4, t.stream));
-    tc_max_kernel<<<num_sms() * 2, 256, 0, t.stream>>>(xn, n, xmax);
-    MOB_LAUNCH_CHECK();
-    tc_merge_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, t.stream>>>((int)nq, R, part_d, part_i, part_thr, cand, t_excl);
-    MOB_LAUNCH_CHECK();
-    tc_rescore_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(ddata, dq, dim, (int)nq, cand, exact);
-    MOB_LAUNCH_CHECK();
-    tc_final_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, t.stream>>>((int)nq, k, n, dim, cand, exact, t_excl, qn, xmax, key_base, sqrt_out, out_k, out_d, flags);
-    MOB_LAUNCH_CHECK();
-    std::vector<int> hflags((size_t)nq);
-    MOB_CUDA_TRY(cudaMemcpyAsync(hflags.data(), flags, sizeof(int) * (size_t)nq, cudaMemcpyDeviceToHost, t.stream));
-    MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));
     std::vector<int> redo;
-    for (int64_t q = 0; q < nq; q++) if (hflags[(size_t)q]) redo.push_back((int)q);
+    rc = tc_finish(t, ddata, n, dim, dq, nq, k, R, nullptr, part_d, part_i, part_thr, A.norm, B.norm, nullptr, key_base, sqrt_out, out_k, out_d, redo);
+    if (rc) return rc;
     g_last_tc_fallbacks = (int)redo.size();
     if (!redo.empty()) {   // queries whose completeness could not be proven: exact kernel, results scattered back
         const int m = (int)redo.size();
@@ -523,6 +569,51 @@ int bruteforce_topk_tc_device(ThreadCtx &t, const float *ddata, int64_t n, int d
         scatter_results_kernel<<<(unsigned)((m * k + 255) / 256), 256, 0, t.stream>>>(sk, sd, didx, m, k, out_k, out_d);
         MOB_LAUNCH_CHECK();
     }
+    return MO_RC_SUCCESS;
+}
+
+// IVF list scan on the tensor cores: the queries probing a list are gathered (as split bf16 rows) next to each other, so
+// a (list, 128-query tile) pair is one work unit of the same candidate kernel; every (query, probe rank) pair owns one list.
+int ivf_tc_scan(ThreadCtx &t, const IvfPlan &plan, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq,
+                const std::vector<int64_t> &offsets, const int64_t *drowids, int k, int sqrt_out, int64_t *ok, double *od,
+                std::vector<int> &redo) {
+    const int64_t nlist = (int64_t)offsets.size() - 1;
+    int *dnonfinite = (int *)arena_alloc(t, 4);
+    if (!dnonfinite) return MO_RC_INTERNAL_ERROR;
+    MOB_CUDA_TRY(cudaMemsetAsync(dnonfinite, 0, 4, t.stream));
+    TcOperand Aq, B, A;
+    int rc = tc_prepare(t, dq, nq, dim, 0, dnonfinite, Aq);
+    if (!rc) rc = tc_prepare(t, ddata, n, dim, 1, dnonfinite, B);
+    if (rc) return rc;
+    int hnonfinite = 0;
+    rc = read_back(t, &hnonfinite, dnonfinite, 4);
+    if (rc) return rc;
+    if (hnonfinite) { redo.resize((size_t)nq); for (int64_t q = 0; q < nq; q++) redo[(size_t)q] = (int)q; g_last_tc_fallbacks = (int)nq; return MO_RC_SUCCESS; }
+    // gathered A operand: one row per (query, probe rank) pair, pairs of a list contiguous
+    A.kprime = Aq.kprime;
+    A.bf = (__nv_bfloat16 *)arena_alloc(t, (size_t)plan.npairs * A.kprime * 2 + 1024);
+    A.norm = (float *)arena_alloc(t, (size_t)plan.npairs * 4);
+    if (!A.bf || !A.norm) return MO_RC_INTERNAL_ERROR;
+    gather_split_rows_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(Aq.bf, Aq.norm, plan.bucket_q, plan.npairs, A.kprime, A.bf, A.norm);
+    MOB_LAUNCH_CHECK();
+    std::vector<TcUnit> units;
+    for (int64_t l = 0; l < nlist; l++) {
+        const int c = plan.hcnt[(size_t)l];
+        if (c == 0 || offsets[(size_t)l + 1] <= offsets[(size_t)l]) continue;
+        for (int q0 = 0; q0 < c; q0 += BM) {
+            TcUnit u; u.a_row0 = plan.hstart[(size_t)l] + q0; u.a_valid = c - q0 < BM ? c - q0 : BM;
+            u.n_begin = (int)offsets[(size_t)l]; u.n_end = (int)offsets[(size_t)l + 1]; u.out_base = u.a_row0;
+            units.push_back(u);
+        }
+    }
+    float *part_d, *part_thr; int *part_i;
+    rc = tc_run_units(t, A, plan.npairs, B, n, units, plan.npairs, &part_d, &part_i, &part_thr);
+    if (rc) return rc;
+    // the approximate lists are indexed by bucket position; tc_finish walks them per query through pair_pos; the final keys are
+    // the primary keys row_ids[local row] and Aq.norm holds |q|^2 per query
+    rc = tc_finish(t, ddata, n, dim, dq, nq, k, plan.nprobe, plan.pair_pos, part_d, part_i, part_thr, Aq.norm, B.norm, drowids, 0, sqrt_out, ok, od, redo);
+    if (rc) return rc;
+    g_last_tc_fallbacks = (int)redo.size();
     return MO_RC_SUCCESS;
 }
 

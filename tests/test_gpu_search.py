@@ -169,3 +169,28 @@ def test_tensor_core_path_non_finite_inputs_use_exact_kernel(gpu):
     finally:
         gpu.MoB200_SetTuning(b"search_mode", 0)
     _check_topk(keys, dists, okeys, odists, nq, k)
+
+
+@pytest.mark.parametrize("sqrt_out", [False, True])
+@pytest.mark.parametrize("nlist,dim,n,nq,k,nprobe", [(64, 96, 20_000, 150, 10, 8), (32, 768, 6_000, 300, 10, 32), (16, 100, 3_000, 64, 5, 3)])
+def test_ivf_tensor_core_scan_is_exact(gpu, nlist, dim, n, nq, k, nprobe, sqrt_out):
+    """IVF list scan through the tcgen05 candidate kernel ((list, query-tile) units over gathered split operands): exact results"""
+    centers = datagen.vectors_f32(30, 0, nlist, dim) * 4
+    data = datagen.vectors_f32(31, 0, n, dim, centers, 1.0)
+    qs = datagen.vectors_f32(32, 0, nq, dim, centers, 1.0)
+    qs[:5] = data[[0, 7, n // 3, n - 1, 99]]
+    assign = np.zeros(n, dtype=np.int32)
+    O.go().og_assign_centroids_f32(O.p(data), n, dim, O.p(centers), nlist, 0, O.p(assign))
+    okeys = np.zeros(nq * k, dtype=np.int64); odists = np.zeros(nq * k)
+    O.go().og_ivf_search_f32(O.p(data), O.p(assign), n, dim, O.p(centers), nlist, O.p(qs), nq, nprobe, k, 0, int(sqrt_out), 8, O.p(okeys), O.p(odists))
+    idx = ops.IvfflatSearchIndex(data, assign, centers)
+    try:
+        gpu.MoB200_SetTuning(b"search_mode", 2)
+        keys, dists = idx.search(qs, k, nprobe, sqrt_out)
+        fallbacks = gpu.MoB200_SetTuning(b"get_tc_fallbacks", 0)
+    finally:
+        gpu.MoB200_SetTuning(b"search_mode", 0)
+        idx.destroy()
+    _check_topk(keys, dists, okeys, odists, nq, k)
+    assert dists.reshape(nq, k)[:5, 0].tolist() == [0.0] * 5
+    assert 0 <= fallbacks <= max(3, nq // 10), fallbacks
