@@ -426,14 +426,20 @@ def main():
     # ---------------------------------------------------------------------------------------------- roofline + cpu baseline
     peak, peak_src = measured_peaks()
     if args.workload == "ivf":
-        # the list scan is the same exact fp32 kernel as the brute force; work = 3 flop per element pair over the probed lists
+        # dominant kernel = tc_candidates_kernel over (list, 128-query tile) units: 2 * K' flop per (query, probed row) pair,
+        # K' = 3 * dim (hi/lo operand split); pairs = queries * nprobe * mean list length
         pairs = float(args.queries) * 32 * (n / 1024.0)
-        flop = 3.0 * pairs * 768
-        fp32_peak = 148 * 114.4 * 1.965e9 / 1e12     # measured lane-op rate of this B200 (tools/microbench: 114.4 lane-ops/clk/SM)
+        flop = 2.0 * pairs * (3 * 768)
+        try:
+            mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            tpeak, tsrc = float(mp["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst)"
+        except Exception:
+            tpeak, tsrc = 1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s)"
         ach = flop / (kern_ms * 1e-3) / 1e12
-        roofline = {"bound": "fp32-alu", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak, "traffic": None,
-                    "kernel": "bf_topk_kernel over (list, query-tile) work items", "kernel_ms": kern_ms,
-                    "peak_source": "tools/microbench.cu on this pool's B200: 114.4 fp32 lane-ops/clk/SM x 148 SM x 1.965 GHz (exact 3-op form, no FMA)"}
+        roofline = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": None,
+                    "kernel": "tc_candidates_kernel (tcgen05 bf16) over (list, query-tile) units", "kernel_ms": kern_ms, "algorithmic_flop_per_launch": flop,
+                    "peak_source": tsrc, "tc_fallback_queries": int(lib.MoB200_SetTuning(b"get_tc_fallbacks", 0)),
+                    "note": "useful flop only: tiles are padded to 128 queries x 256 rows, so the tensor pipe does more work than counted"}
     elif alg_bytes is not None:
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
