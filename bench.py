@@ -438,7 +438,8 @@ def main():
         ach = flop / (kern_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": None,
                     "kernel": "tc_candidates_kernel (tcgen05 bf16) over (list, query-tile) units", "kernel_ms": kern_ms, "algorithmic_flop_per_launch": flop,
-                    "peak_source": tsrc, "tc_fallback_queries": int(lib.MoB200_SetTuning(b"get_tc_fallbacks", 0)),
+                    "peak_source": tsrc, "tc_refined_queries": int(lib.MoB200_SetTuning(b"get_tc_refined", 0)),
+                    "tc_fallback_queries": int(lib.MoB200_SetTuning(b"get_tc_fallbacks", 0)),
                     "note": "useful flop only: tiles are padded to 128 queries x 256 rows, so the tensor pipe does more work than counted"}
     elif alg_bytes is not None:
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
@@ -457,6 +458,7 @@ def main():
         ach = flop / (kern_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": None,
                     "kernel": "tc_candidates_kernel (tcgen05 bf16, K' = 2304)", "kernel_ms": kern_ms, "algorithmic_flop_per_launch": flop, "peak_source": tsrc,
+                    "tc_refined_queries": int(lib.MoB200_SetTuning(b"get_tc_refined", 0)),
                     "tc_fallback_queries": int(lib.MoB200_SetTuning(b"get_tc_fallbacks", 0))}
     cpu_baseline = None
     if not args.no_cpu and world == 1 and args.workload == "bruteforce":

@@ -25,6 +25,8 @@ struct ThreadCtx {
     cudaEvent_t kev0 = nullptr, kev1 = nullptr;  // bracket the dominant kernel of the last call (MoB200_LastKernelMs)
     std::vector<ArenaBlock> blocks;  // device scratch arena (bump allocated, reset per call)
     size_t cur_block = 0, cur_off = 0;
+    int kev_prio = 0;                // priority of the kernel kev0/kev1 currently bracket within this call (reset with the arena)
+    uint64_t arena_epoch = 0;        // bumped by arena_reset: per-call caches of arena pointers key on it
     char *pinned = nullptr;          // small pinned staging (scalar results, status words)
     size_t pinned_sz = 0;
     unsigned *ctrl = nullptr;        // 64 device words, zero between calls ("last CTA done" tickets, atomicInc wraps)

@@ -127,7 +127,7 @@ void arena_reset(ThreadCtx &t) {
         if (cudaMalloc((void **)&p, total) == cudaSuccess) t.blocks.push_back({p, total});
         else cudaGetLastError();
     }
-    t.cur_block = 0; t.cur_off = 0;
+    t.cur_block = 0; t.cur_off = 0; t.arena_epoch++; t.kev_prio = 0;
 }
 
 const void *Stager::in(const void *p, size_t bytes) {

@@ -40,8 +40,8 @@ struct SearchSmem {
     int li[KMAX][TQ];
     float thr_d[TQ]; int thr_i[TQ]; int lcnt[TQ];
     float qnorm[TQ];
-    unsigned cand_meta[TQ * TX]; float cand_d[TQ * TX];
-    int cand_cnt;
+    unsigned char cand_row[TQ][TX + 4]; float cand_d[TQ][TX + 1];   // per-query candidate lists of the current tile (padded: bank-conflict free across queries)
+    int qcnt[TQ];
 };
 
 __device__ __forceinline__ bool lex_less(float d, int i, float d2, int i2) { return d < d2 || (d == d2 && i < i2); }
@@ -101,8 +101,7 @@ bf_topk_kernel(const WorkDesc *__restrict__ items, int dim, int k, float *__rest
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const bool al4 = (dim & 3) == 0 && ((((uintptr_t)W.data) | ((uintptr_t)W.queries)) & 15) == 0;
 
-    if (tid < TQ) { S.lcnt[tid] = 0; S.thr_d[tid] = INFINITY; S.thr_i[tid] = 0x7fffffff; }
-    if (tid == 0) S.cand_cnt = 0;
+    if (tid < TQ) { S.lcnt[tid] = 0; S.thr_d[tid] = INFINITY; S.thr_i[tid] = 0x7fffffff; S.qcnt[tid] = 0; }
     if (METRIC == MO_METRIC_COS && tid < TQ) {
         int64_t gq = tid < W.nq_local ? (W.qidx ? W.qidx[tid] : W.q0 + tid) : -1;
         S.qnorm[tid] = gq >= 0 ? W.qnorm[gq] : 0.f;
@@ -231,21 +230,21 @@ bf_topk_kernel(const WorkDesc *__restrict__ items, int dim, int k, float *__rest
                     else { double sim = (double)d / den; sim = sim > 1.0 ? 1.0 : (sim < -1.0 ? -1.0 : sim); d = (float)(1.0 - sim); }
                 }
                 if (lex_less(d, (int)row, td, ti)) {
-                    const int slot = atomicAdd(&S.cand_cnt, 1);
-                    S.cand_meta[slot] = ((unsigned)ql << 8) | (unsigned)rl;
-                    S.cand_d[slot] = d;
+                    const int slot = atomicAdd(&S.qcnt[ql], 1);
+                    S.cand_row[ql][slot] = (unsigned char)rl;
+                    S.cand_d[ql][slot] = d;
                 }
             }
         }
         __syncthreads();
-        const int nc = S.cand_cnt;
-        if (nc > 0 && tid < W.nq_local) {
+        // every query thread inserts its own candidates (lanes work in parallel; the slot order inside a list is arbitrary but
+        // the result is not: (distance, row) is a total order)
+        if (tid < W.nq_local) {
             const int ql = tid;
+            const int nc = S.qcnt[ql];
             int cnt = S.lcnt[ql];
             for (int c = 0; c < nc; c++) {
-                const unsigned m = S.cand_meta[c];
-                if ((int)(m >> 8) != ql) continue;
-                const float d = S.cand_d[c]; const int id = (int)(row0 + (m & 0xffu));
+                const float d = S.cand_d[ql][c]; const int id = (int)(row0 + S.cand_row[ql][c]);
                 int pos;
                 if (cnt < k) pos = cnt++;
                 else { if (!lex_less(d, id, S.ld[k - 1][ql], S.li[k - 1][ql])) continue; pos = k - 1; }
@@ -256,10 +255,9 @@ bf_topk_kernel(const WorkDesc *__restrict__ items, int dim, int k, float *__rest
             }
             S.lcnt[ql] = cnt;
             if (cnt >= k) { S.thr_d[ql] = S.ld[k - 1][ql]; S.thr_i[ql] = S.li[k - 1][ql]; }
+            S.qcnt[ql] = 0;
         }
         __syncthreads();
-        if (tid == 0) S.cand_cnt = 0;
-        // (the next tile's first __syncthreads orders this reset before any new push)
     }
 
     // ---- write the partial lists
@@ -350,9 +348,10 @@ int launch_bf(ThreadCtx &t, const WorkDesc *ditems, int nitems, int dim, int k, 
         MOB_CUDA_TRY(cudaFuncSetAttribute(bf_topk_kernel<METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SearchSmem)));
         attr_set = true;
     }
-    cudaEventRecord(t.kev0, t.stream);
+    const bool timed = t.kev_prio <= 1;   // a tensor-core candidate pass of the same call stays the reported kernel
+    if (timed) { t.kev_prio = 1; cudaEventRecord(t.kev0, t.stream); }
     bf_topk_kernel<METRIC><<<nitems, kThreads, sizeof(SearchSmem), t.stream>>>(ditems, dim, k, part_d, part_i);
-    cudaEventRecord(t.kev1, t.stream);
+    if (timed) cudaEventRecord(t.kev1, t.stream);
     MOB_LAUNCH_CHECK();
     return MO_RC_SUCCESS;
 }
@@ -518,6 +517,45 @@ __global__ void ivf_scatter_kernel(const int64_t *__restrict__ sk, const double 
 
 namespace mob {
 
+struct IvfJob {
+    const float *dcent; int64_t nlist; const float *ddata; int64_t n; int dim; const std::vector<int64_t> *offsets; const int64_t *drowids;
+    int k, nprobe, metric, sqrt_out;
+};
+
+// level 0: tensor-core candidate pass over whole lists (when the shape qualifies), level 1: the queries it could not prove, again on
+// the tensor cores but with every list cut into sub-ranges, level 2: whatever is still unproven through the exact kernel.
+// Each level answers its queries exactly or hands them down; results are scattered back into the caller's rows.
+static int ivf_search_level(ThreadCtx &t, const IvfJob &J, int level, const float *dq, int64_t nq, int64_t *ok, double *od) {
+    IvfPlan plan;
+    int rc = ivf_make_plan(t, J.dcent, J.nlist, J.dim, dq, nq, J.nprobe, J.metric, plan);
+    if (rc) return rc;
+    if (level >= 2 || !tc_ivf_applicable(J.n, J.dim, nq, J.k, J.nprobe, J.metric, level == 1)) {
+        if (level > 0) g_last_tc_fallbacks = (int)nq;
+        return ivf_exact_scan(t, plan, J.ddata, J.n, J.dim, dq, nq, *J.offsets, J.drowids, J.k, J.metric, J.sqrt_out, ok, od);
+    }
+    std::vector<int> redo;
+    bool nonfinite = false;
+    rc = ivf_tc_scan(t, plan, J.ddata, J.n, J.dim, dq, nq, *J.offsets, J.drowids, J.k, J.sqrt_out, level == 1, ok, od, redo, &nonfinite);
+    if (rc) return rc;
+    if (level == 0) { g_last_tc_refined = (int)redo.size(); g_last_tc_fallbacks = 0; }
+    if (redo.empty()) return MO_RC_SUCCESS;
+    const int m = (int)redo.size();
+    int *didx = (int *)arena_alloc(t, sizeof(int) * (size_t)m);
+    float *sub = (float *)arena_alloc(t, sizeof(float) * (size_t)m * J.dim);
+    int64_t *sk = (int64_t *)arena_alloc(t, sizeof(int64_t) * (size_t)m * J.k);
+    double *sd = (double *)arena_alloc(t, sizeof(double) * (size_t)m * J.k);
+    if (!didx || !sub || !sk || !sd) return MO_RC_INTERNAL_ERROR;
+    MOB_CUDA_TRY(cudaMemcpyAsync(didx, redo.data(), sizeof(int) * (size_t)m, cudaMemcpyHostToDevice, t.stream));
+    MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));
+    ivf_gather_queries_kernel<<<num_sms() * 4, 256, 0, t.stream>>>(dq, didx, m, J.dim, sub);
+    MOB_LAUNCH_CHECK();
+    rc = ivf_search_level(t, J, nonfinite ? 2 : level + 1, sub, m, sk, sd);
+    if (rc) return rc;
+    ivf_scatter_kernel<<<(unsigned)((m * J.k + 255) / 256), 256, 0, t.stream>>>(sk, sd, didx, m, J.k, ok, od);
+    MOB_LAUNCH_CHECK();
+    return MO_RC_SUCCESS;
+}
+
 // IvfflatSearchIndex.Search (pkg/vectorindex/ivfflat/search.go:509-630):
 //   findCentroids (:292-311)  = exact top-nprobe over the centroid table (same kernel, k = nprobe)
 //   list scan + ORDER BY LIMIT (:572-592) = exact top-k over the rows of the probed lists
@@ -552,31 +590,9 @@ int xcall_ivf(mo_xcall_args_t *args, uint64_t len) {
     if (is_device_ptr(args[6].pdata)) { MOB_CUDA_TRY(cudaMemcpyAsync(offsets.data(), args[6].pdata, offsets.size() * 8, cudaMemcpyDeviceToHost, t.stream)); MOB_CUDA_TRY(cudaStreamSynchronize(t.stream)); }
     else memcpy(offsets.data(), args[6].pdata, offsets.size() * 8);
 
-    IvfPlan plan;
-    rc = ivf_make_plan(t, dcent, P.nlist, dim, dq, P.nq, nprobe, P.metric, plan);
-    if (rc) { st.finish(); return rc; }
-    if (tc_ivf_applicable(P.n, dim, P.nq, P.k, nprobe, P.metric)) {
-        std::vector<int> redo;
-        rc = ivf_tc_scan(t, plan, ddata, P.n, dim, dq, P.nq, offsets, drowids, P.k, P.sqrt_out, ok, od, redo);
-        if (!rc && !redo.empty()) {   // queries whose completeness could not be proven: exact scan, scattered back
-            const int m = (int)redo.size();
-            int *didx = (int *)st.tmp(sizeof(int) * (size_t)m);
-            float *sub = (float *)st.tmp(sizeof(float) * (size_t)m * dim);
-            int64_t *sk = (int64_t *)st.tmp(sizeof(int64_t) * (size_t)m * P.k);
-            double *sd = (double *)st.tmp(sizeof(double) * (size_t)m * P.k);
-            if (st.failed) { st.finish(); return MO_RC_INTERNAL_ERROR; }
-            MOB_CUDA_TRY(cudaMemcpyAsync(didx, redo.data(), sizeof(int) * (size_t)m, cudaMemcpyHostToDevice, t.stream));
-            MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));
-            ivf_gather_queries_kernel<<<num_sms() * 4, 256, 0, t.stream>>>(dq, didx, m, dim, sub);
-            MOB_LAUNCH_CHECK();
-            IvfPlan sp;
-            rc = ivf_make_plan(t, dcent, P.nlist, dim, sub, m, nprobe, P.metric, sp);
-            if (!rc) rc = ivf_exact_scan(t, sp, ddata, P.n, dim, sub, m, offsets, drowids, P.k, P.metric, P.sqrt_out, sk, sd);
-            if (!rc) { ivf_scatter_kernel<<<(unsigned)((m * P.k + 255) / 256), 256, 0, t.stream>>>(sk, sd, didx, m, P.k, ok, od); MOB_LAUNCH_CHECK(); }
-        }
-    } else {
-        rc = ivf_exact_scan(t, plan, ddata, P.n, dim, dq, P.nq, offsets, drowids, P.k, P.metric, P.sqrt_out, ok, od);
-    }
+    IvfJob job{dcent, P.nlist, ddata, P.n, dim, &offsets, drowids, (int)P.k, nprobe, (int)P.metric, (int)P.sqrt_out};
+    g_last_tc_fallbacks = -1; g_last_tc_refined = -1;
+    rc = ivf_search_level(t, job, 0, dq, P.nq, ok, od);
     int frc = st.finish();
     return rc ? rc : frc;
 }

@@ -25,10 +25,13 @@ int ivf_exact_scan(ThreadCtx &t, const IvfPlan &plan, const float *ddata, int64_
 bool tc_search_applicable(int64_t n, int dim, int64_t nq, int k, int metric);
 int bruteforce_topk_tc_device(ThreadCtx &t, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq, int k,
                               int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d);
-bool tc_ivf_applicable(int64_t n, int dim, int64_t nq, int k, int nprobe, int metric);
+bool tc_ivf_applicable(int64_t n, int dim, int64_t nq, int k, int nprobe, int metric, bool refine);
 // returns the queries whose completeness proof failed in `redo` (their rows of ok/od are still filled with best-effort results)
 int ivf_tc_scan(ThreadCtx &t, const IvfPlan &plan, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq,
-                const std::vector<int64_t> &offsets, const int64_t *drowids, int k, int sqrt_out, int64_t *ok, double *od,
-                std::vector<int> &redo);
+                const std::vector<int64_t> &offsets, const int64_t *drowids, int k, int sqrt_out, bool refine, int64_t *ok, double *od,
+                std::vector<int> &redo, bool *nonfinite);   // *nonfinite: Inf/NaN input, the error bound does not apply, redo = all
+
+extern int g_last_tc_fallbacks;   // queries of the last tensor-core search that ended in the exact kernel
+extern int g_last_tc_refined;     // IVF: queries of the last search that needed the sub-range refine pass
 
 }  // namespace mob

@@ -294,13 +294,20 @@ constexpr int KR = 32;   // candidates re-scored exactly per query
 
 // one thread per query: R-way merge of the (ascending) approximate lists -> KR best candidate ids; t_excl = smallest approximate
 // distance any row NOT among them can have (first unconsumed entry of every list, and the list-full threshold of every range)
-// list (q, r) lives at index  pos_map ? pos_map[q * R + r] (-1 = no such list)  :  r * nq + q
+// list (q, r) lives at index  r * nq + q  without pos_map; with it (IVF) r = s * pos_cols + p names sub-range s of probe rank p:
+// index = s * pos_stride + pos_map[q * pos_cols + p]  (pos_map < 0 = no such list)
+constexpr int kMaxMergeLists = 256;
 __global__ void tc_merge_kernel(int nq, int R, const float *__restrict__ part_d, const int *__restrict__ part_i,
-                                const float *__restrict__ part_thr, const int *__restrict__ pos_map, int *__restrict__ cand, float *__restrict__ t_excl) {
+                                const float *__restrict__ part_thr, const int *__restrict__ pos_map, int pos_cols, long long pos_stride,
+                                int *__restrict__ cand, float *__restrict__ t_excl) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
-    auto lst = [&](int r) -> long long { return pos_map ? (long long)pos_map[(size_t)q * R + r] : (long long)r * nq + q; };
-    unsigned char head[64];
+    auto lst = [&](int r) -> long long {
+        if (!pos_map) return (long long)r * nq + q;
+        const int p = pos_map[(size_t)q * pos_cols + r % pos_cols];
+        return p < 0 ? -1ll : (long long)(r / pos_cols) * pos_stride + p;
+    };
+    unsigned char head[kMaxMergeLists];
     for (int r = 0; r < R; r++) head[r] = 0;
     for (int j = 0; j < KR; j++) {
         int best = -1; float bd = INFINITY;
@@ -426,23 +433,31 @@ __global__ void scatter_results_kernel(const int64_t *__restrict__ sk, const dou
 namespace mob {
 
 int g_search_mode = 0;          // 0 = auto, 1 = exact kernel only, 2 = force the tensor-core path (MoB200_SetTuning("search_mode"))
+int g_last_tc_refined = -1;
 int g_last_tc_fallbacks = -1;   // queries of the last tensor-core search that failed the completeness proof and were re-run exactly
 
 struct TcOperand { __nv_bfloat16 *bf = nullptr; float *norm = nullptr; int kprime = 0; };
 
 // split an fp32 row-major matrix into the K-concatenated bf16 operand; *nonfinite (device flag) is raised on Inf/NaN
 static int tc_prepare(ThreadCtx &t, const float *x, int64_t n, int dim, int mode, int *dnonfinite, TcOperand &op) {
+    // one API call may split the same matrix more than once (IVF refine pass): the operand lives in the call's arena, so it
+    // is reused while the arena epoch lasts.  A nonfinite input was already reported by the split that filled the cache.
+    struct Cached { const float *x = nullptr; int64_t n = 0; int dim = 0, mode = 0; uint64_t epoch = ~0ull; const ThreadCtx *t = nullptr; TcOperand op; };
+    static thread_local Cached cache[2];
+    Cached &c = cache[mode & 1];
+    if (c.t == &t && c.epoch == t.arena_epoch && c.x == x && c.n == n && c.dim == dim && c.mode == mode) { op = c.op; return MO_RC_SUCCESS; }
     op.kprime = ((3 * dim + BK - 1) / BK) * BK;
     op.bf = (__nv_bfloat16 *)arena_alloc(t, (size_t)(n > 0 ? n : 1) * op.kprime * 2 + 1024);
     op.norm = (float *)arena_alloc(t, (size_t)(n > 0 ? n : 1) * 4);
     if (!op.bf || !op.norm) return MO_RC_INTERNAL_ERROR;
     if (n > 0) { split_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(x, n, dim, op.kprime, mode, op.bf, op.norm, nullptr, dnonfinite); MOB_LAUNCH_CHECK(); }
+    c.x = x; c.n = n; c.dim = dim; c.mode = mode; c.epoch = t.arena_epoch; c.t = &t; c.op = op;
     return MO_RC_SUCCESS;
 }
 
 // run the candidate kernel over `units`; lists are written at unit.out_base + row (nlists lists in total, pre-initialised empty)
 static int tc_run_units(ThreadCtx &t, const TcOperand &A, int64_t a_rows, const TcOperand &B, int64_t b_rows, const std::vector<TcUnit> &units,
-                        int64_t nlists, float **part_d, int **part_i, float **part_thr) {
+                        int64_t nlists, float **part_d, int **part_i, float **part_thr, bool timed = true) {
     CUtensorMap map_a, map_b;
     int rc = make_map(&map_a, A.bf, (uint64_t)a_rows, (uint64_t)A.kprime, BM);
     if (rc) return rc;
@@ -463,16 +478,16 @@ static int tc_run_units(ThreadCtx &t, const TcOperand &A, int64_t a_rows, const 
     if (!attr) { MOB_CUDA_TRY(cudaFuncSetAttribute(tc_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     int grid = num_sms();
     if (grid > (int)units.size()) grid = (int)units.size();
-    cudaEventRecord(t.kev0, t.stream);
+    if (timed) { t.kev_prio = 2; cudaEventRecord(t.kev0, t.stream); }   // MoB200_LastKernelMs reports the first (whole-list) pass, not the refine pass
     tc_candidates_kernel<<<grid, kTcThreads, smem, t.stream>>>(map_a, map_b, dunits, (int)units.size(), A.kprime, A.norm, B.norm, *part_d, *part_i, *part_thr);
-    cudaEventRecord(t.kev1, t.stream);
+    if (timed) cudaEventRecord(t.kev1, t.stream);
     MOB_LAUNCH_CHECK();
     return MO_RC_SUCCESS;
 }
 
 // merge approximate lists -> exact re-score -> final order + proof; returns the queries whose proof failed
 static int tc_finish(ThreadCtx &t, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq, int k, int R, const int *pos_map,
-                     const float *part_d, const int *part_i, const float *part_thr, const float *qnorm, const float *xnorm,
+                     int pos_cols, long long pos_stride, const float *part_d, const int *part_i, const float *part_thr, const float *qnorm, const float *xnorm,
                      const int64_t *id_map, int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d, std::vector<int> &redo) {
     int *cand = (int *)arena_alloc(t, sizeof(int) * (size_t)nq * KR);
     float *exact = (float *)arena_alloc(t, sizeof(float) * (size_t)nq * KR);
@@ -483,7 +498,8 @@ static int tc_finish(ThreadCtx &t, const float *ddata, int64_t n, int dim, const
     MOB_CUDA_TRY(cudaMemsetAsync(xmax, 0, 4, t.stream));
     tc_max_kernel<<<num_sms() * 2, 256, 0, t.stream>>>(xnorm, n, xmax);
     MOB_LAUNCH_CHECK();
-    tc_merge_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, t.stream>>>((int)nq, R, part_d, part_i, part_thr, pos_map, cand, t_excl);
+    if (R > kMaxMergeLists) { set_error("tc search: %d candidate lists per query exceed the merge limit %d", R, kMaxMergeLists); return MO_RC_INTERNAL_ERROR; }
+    tc_merge_kernel<<<(unsigned)((nq + 63) / 64), 64, 0, t.stream>>>((int)nq, R, part_d, part_i, part_thr, pos_map, pos_cols, pos_stride, cand, t_excl);
     MOB_LAUNCH_CHECK();
     tc_rescore_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(ddata, dq, dim, (int)nq, cand, exact);
     MOB_LAUNCH_CHECK();
@@ -504,11 +520,11 @@ bool tc_search_applicable(int64_t n, int dim, int64_t nq, int k, int metric) {
     return shape_ok && nq >= 256 && n >= 16384 && dim >= 64;   // below this the exact kernel wins (operand split + launch overheads)
 }
 
-bool tc_ivf_applicable(int64_t n, int dim, int64_t nq, int k, int nprobe, int metric) {
+bool tc_ivf_applicable(int64_t n, int dim, int64_t nq, int k, int nprobe, int metric, bool refine) {
     if (g_search_mode == 1) return false;
     const bool shape_ok = (metric == MO_METRIC_L2 || metric == MO_METRIC_L2SQ) && k >= 1 && k <= KP && dim >= 16 && n >= 1 && n < (1ll << 31) - BN &&
                           nprobe <= 64 && nq * (int64_t)nprobe < (1ll << 31);
-    if (g_search_mode == 2) return shape_ok;
+    if (g_search_mode == 2 || refine) return shape_ok;
     return shape_ok && nq * (int64_t)nprobe >= 8192 && dim >= 64;
 }
 
@@ -550,7 +566,7 @@ int bruteforce_topk_tc_device(ThreadCtx &t, const float *ddata, int64_t n, int d
     rc = tc_run_units(t, A, nq, B, n, units, (int64_t)R * nq, &part_d, &part_i, &part_thr);
     if (rc) return rc;
     std::vector<int> redo;
-    rc = tc_finish(t, ddata, n, dim, dq, nq, k, R, nullptr, part_d, part_i, part_thr, A.norm, B.norm, nullptr, key_base, sqrt_out, out_k, out_d, redo);
+    rc = tc_finish(t, ddata, n, dim, dq, nq, k, R, nullptr, 0, 0, part_d, part_i, part_thr, A.norm, B.norm, nullptr, key_base, sqrt_out, out_k, out_d, redo);
     if (rc) return rc;
     g_last_tc_fallbacks = (int)redo.size();
     if (!redo.empty()) {   // queries whose completeness could not be proven: exact kernel, results scattered back
@@ -575,9 +591,21 @@ int bruteforce_topk_tc_device(ThreadCtx &t, const float *ddata, int64_t n, int d
 // IVF list scan on the tensor cores: the queries probing a list are gathered (as split bf16 rows) next to each other, so
 // a (list, 128-query tile) pair is one work unit of the same candidate kernel; every (query, probe rank) pair owns one list.
 int ivf_tc_scan(ThreadCtx &t, const IvfPlan &plan, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq,
-                const std::vector<int64_t> &offsets, const int64_t *drowids, int k, int sqrt_out, int64_t *ok, double *od,
-                std::vector<int> &redo) {
+                const std::vector<int64_t> &offsets, const int64_t *drowids, int k, int sqrt_out, bool refine, int64_t *ok, double *od,
+                std::vector<int> &redo, bool *nonfinite) {
+    *nonfinite = false;
     const int64_t nlist = (int64_t)offsets.size() - 1;
+    // refine pass (queries the first pass could not prove): every list is cut into sub-ranges of `chunk` rows, each keeping its own
+    // KP candidates, so the excluded-row threshold of a (query, list) pair moves far away from the k-th result
+    int split = 1; int64_t chunk = (int64_t)1 << 40;
+    if (refine) {
+        int64_t maxlen = 1;
+        for (int64_t l = 0; l < nlist; l++) if (plan.hcnt[(size_t)l] > 0 && offsets[(size_t)l + 1] - offsets[(size_t)l] > maxlen) maxlen = offsets[(size_t)l + 1] - offsets[(size_t)l];
+        split = (int)((maxlen + BN - 1) / BN);
+        const int cap = kMaxMergeLists / plan.nprobe > 0 ? kMaxMergeLists / plan.nprobe : 1;
+        if (split > cap) split = cap;
+        chunk = ((maxlen + split - 1) / split + BN - 1) / BN * BN;
+    }
     int *dnonfinite = (int *)arena_alloc(t, 4);
     if (!dnonfinite) return MO_RC_INTERNAL_ERROR;
     MOB_CUDA_TRY(cudaMemsetAsync(dnonfinite, 0, 4, t.stream));
@@ -588,7 +616,7 @@ int ivf_tc_scan(ThreadCtx &t, const IvfPlan &plan, const float *ddata, int64_t n
     int hnonfinite = 0;
     rc = read_back(t, &hnonfinite, dnonfinite, 4);
     if (rc) return rc;
-    if (hnonfinite) { redo.resize((size_t)nq); for (int64_t q = 0; q < nq; q++) redo[(size_t)q] = (int)q; g_last_tc_fallbacks = (int)nq; return MO_RC_SUCCESS; }
+    if (hnonfinite) { *nonfinite = true; redo.resize((size_t)nq); for (int64_t q = 0; q < nq; q++) redo[(size_t)q] = (int)q; return MO_RC_SUCCESS; }
     // gathered A operand: one row per (query, probe rank) pair, pairs of a list contiguous
     A.kprime = Aq.kprime;
     A.bf = (__nv_bfloat16 *)arena_alloc(t, (size_t)plan.npairs * A.kprime * 2 + 1024);
@@ -600,21 +628,22 @@ int ivf_tc_scan(ThreadCtx &t, const IvfPlan &plan, const float *ddata, int64_t n
     for (int64_t l = 0; l < nlist; l++) {
         const int c = plan.hcnt[(size_t)l];
         if (c == 0 || offsets[(size_t)l + 1] <= offsets[(size_t)l]) continue;
-        for (int q0 = 0; q0 < c; q0 += BM) {
-            TcUnit u; u.a_row0 = plan.hstart[(size_t)l] + q0; u.a_valid = c - q0 < BM ? c - q0 : BM;
-            u.n_begin = (int)offsets[(size_t)l]; u.n_end = (int)offsets[(size_t)l + 1]; u.out_base = u.a_row0;
-            units.push_back(u);
-        }
+        for (int q0 = 0; q0 < c; q0 += BM)
+            for (int s = 0; s < split; s++) {
+                TcUnit u; u.a_row0 = plan.hstart[(size_t)l] + q0; u.a_valid = c - q0 < BM ? c - q0 : BM;
+                const int64_t b = offsets[(size_t)l] + s * chunk, e = b + chunk < offsets[(size_t)l + 1] ? b + chunk : offsets[(size_t)l + 1];
+                if (b >= e) break;
+                u.n_begin = (int)b; u.n_end = (int)e; u.out_base = (long long)s * plan.npairs + u.a_row0;
+                units.push_back(u);
+            }
     }
     float *part_d, *part_thr; int *part_i;
-    rc = tc_run_units(t, A, plan.npairs, B, n, units, plan.npairs, &part_d, &part_i, &part_thr);
+    rc = tc_run_units(t, A, plan.npairs, B, n, units, plan.npairs * split, &part_d, &part_i, &part_thr, !refine);
     if (rc) return rc;
     // the approximate lists are indexed by bucket position; tc_finish walks them per query through pair_pos; the final keys are
     // the primary keys row_ids[local row] and Aq.norm holds |q|^2 per query
-    rc = tc_finish(t, ddata, n, dim, dq, nq, k, plan.nprobe, plan.pair_pos, part_d, part_i, part_thr, Aq.norm, B.norm, drowids, 0, sqrt_out, ok, od, redo);
-    if (rc) return rc;
-    g_last_tc_fallbacks = (int)redo.size();
-    return MO_RC_SUCCESS;
+    rc = tc_finish(t, ddata, n, dim, dq, nq, k, plan.nprobe * split, plan.pair_pos, plan.nprobe, plan.npairs, part_d, part_i, part_thr, Aq.norm, B.norm, drowids, 0, sqrt_out, ok, od, redo);
+    return rc;
 }
 
 }  // namespace mob

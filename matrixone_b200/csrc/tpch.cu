@@ -557,11 +557,12 @@ namespace mob {
 unsigned long long *q1_debug_buffer() { return g_q1_dbg; }
 
 extern int g_search_mode;
-extern int g_last_tc_fallbacks;
+extern int g_last_tc_fallbacks, g_last_tc_refined;
 
 int tuning_set(const char *name, int value) {
     if (!strcmp(name, "search_mode")) { g_search_mode = value; return 0; }
     if (!strcmp(name, "get_tc_fallbacks")) return g_last_tc_fallbacks;
+    if (!strcmp(name, "get_tc_refined")) return g_last_tc_refined;
     if (!strcmp(name, "q6_variant")) { g_q6_variant = value; return 0; }
     if (!strcmp(name, "q1_variant")) { g_q1_variant = value; return 0; }
     if (!strcmp(name, "q1_debug")) {

@@ -194,3 +194,34 @@ def test_ivf_tensor_core_scan_is_exact(gpu, nlist, dim, n, nq, k, nprobe, sqrt_o
     _check_topk(keys, dists, okeys, odists, nq, k)
     assert dists.reshape(nq, k)[:5, 0].tolist() == [0.0] * 5
     assert 0 <= fallbacks <= max(3, nq // 10), fallbacks
+
+
+@pytest.mark.gpu
+def test_ivf_refine_pass_resolves_crowded_lists(gpu):
+    """40 near-duplicates of the query inside one list: the whole-list pass keeps 16 candidates per (query, list) and cannot prove the
+    top-k complete; the sub-range refine pass (still on the tensor cores) can, and the answer equals the oracle's"""
+    nlist, dim, n, nq, k, nprobe = 4, 64, 8_000, 40, 16, 4
+    centers = datagen.vectors_f32(40, 0, nlist, dim) * 4
+    data = datagen.vectors_f32(41, 0, n, dim, centers, 1.0)
+    rng = np.random.default_rng(5)
+    base = data[123].copy()
+    dup_rows = np.arange(200, 200 + 40 * 150, 150)
+    data[dup_rows] = base + (rng.standard_normal((40, dim)) * 1e-4).astype(np.float32)
+    qs = datagen.vectors_f32(42, 0, nq, dim, centers, 1.0)
+    qs[0] = base
+    assign = np.zeros(n, dtype=np.int32)
+    O.go().og_assign_centroids_f32(O.p(data), n, dim, O.p(centers), nlist, 0, O.p(assign))
+    okeys = np.zeros(nq * k, dtype=np.int64); odists = np.zeros(nq * k)
+    O.go().og_ivf_search_f32(O.p(data), O.p(assign), n, dim, O.p(centers), nlist, O.p(qs), nq, nprobe, k, 0, 0, 8, O.p(okeys), O.p(odists))
+    idx = ops.IvfflatSearchIndex(data, assign, centers)
+    try:
+        gpu.MoB200_SetTuning(b"search_mode", 2)
+        keys, dists = idx.search(qs, k, nprobe, False)
+        refined = gpu.MoB200_SetTuning(b"get_tc_refined", 0)
+        fallbacks = gpu.MoB200_SetTuning(b"get_tc_fallbacks", 0)
+    finally:
+        gpu.MoB200_SetTuning(b"search_mode", 0)
+        idx.destroy()
+    _check_topk(keys, dists, okeys, odists, nq, k)
+    assert refined >= 1, refined
+    assert fallbacks <= refined
