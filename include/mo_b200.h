@@ -257,6 +257,13 @@ int32_t MoB200_GenVectorsF32(uint64_t seed, uint64_t row0, uint64_t n, int64_t d
                              const float *centers, int64_t ncenters, float sigma);
 int32_t MoB200_GatherRowsF32(float *dst, const float *src, const int64_t *idx, uint64_t m, int64_t dim);  /* device pointers */
 
+/* Index load hooks (brute_force.go:104-123 Load / ivfflat/search.go:216-290 LoadIndex build the reference's in-memory index once;
+ * Destroy frees it).  SearchPrepare splits a RESIDENT float32 dataset [n][dim] into the tensor-core operand of
+ * MO_XCALL_BRUTEFORCE_TOPK_F32 / MO_XCALL_IVF_TOPK_F32 once, instead of once per search; the rows must not change until
+ * SearchRelease(data).  Optional: searches return identical results with or without it.  Costs 6*dim bytes of HBM per row. */
+int32_t MoB200_SearchPrepare(const void *data, uint64_t n, int64_t dim);
+int32_t MoB200_SearchRelease(const void *data);
+
 #ifdef __cplusplus
 }
 #endif

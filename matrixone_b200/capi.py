@@ -99,6 +99,8 @@ PROTOTYPES = {
     "MoB200_GenInt64": (_i32, [_u64, _u64, _u64, _vp, _vp, C.c_uint32]),
     "MoB200_GenVectorsF32": (_i32, [_u64, _u64, _u64, _i64, _vp, _vp, _i64, C.c_float]),
     "MoB200_GatherRowsF32": (_i32, [_vp, _vp, _vp, _u64, _i64]),
+    "MoB200_SearchPrepare": (_i32, [_vp, _u64, _i64]),
+    "MoB200_SearchRelease": (_i32, [_vp]),
 }
 for _k in ("SignedInt", "UnsignedInt", "Float"):
     for _op in ("Add", "Sub", "Mul", "Mod"):

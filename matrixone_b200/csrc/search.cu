@@ -610,7 +610,10 @@ int ivf_make_plan(ThreadCtx &t, const float *dcent, int64_t nlist, int dim, cons
     plan.bucket_slot = (int64_t *)arena_alloc(t, (size_t)npairs * 8);
     plan.pair_pos = (int32_t *)arena_alloc(t, (size_t)npairs * 4);
     if (!plan.probes || !probe_d || !cnt || !plan.bucket_q || !plan.bucket_slot || !plan.pair_pos) return MO_RC_INTERNAL_ERROR;
-    int rc = bruteforce_topk_device(t, dcent, nlist, dim, dq, nq, nprobe, metric, 0, 0, plan.probes, probe_d);
+    // exact either way: the tensor-core pass proves its top-nprobe complete or re-runs the query through the exact kernel
+    int rc = tc_probe_applicable(nlist, dim, nq, nprobe, metric)
+                 ? bruteforce_topk_tc_device(t, dcent, nlist, dim, dq, nq, nprobe, 0, 0, plan.probes, probe_d, false)
+                 : bruteforce_topk_device(t, dcent, nlist, dim, dq, nq, nprobe, metric, 0, 0, plan.probes, probe_d);
     if (rc) return rc;
     int *dstart = cnt + nlist, *cursor = cnt + 2 * nlist;
     MOB_CUDA_TRY(cudaMemsetAsync(cnt, 0, (size_t)nlist * 4 * 3, t.stream));

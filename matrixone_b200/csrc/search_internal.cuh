@@ -23,8 +23,10 @@ int ivf_exact_scan(ThreadCtx &t, const IvfPlan &plan, const float *ddata, int64_
                    const std::vector<int64_t> &offsets, const int64_t *drowids, int k, int metric, int sqrt_out, int64_t *ok, double *od);
 
 bool tc_search_applicable(int64_t n, int dim, int64_t nq, int k, int metric);
+bool tc_probe_applicable(int64_t nlist, int dim, int64_t nq, int nprobe, int metric);
+// record_stats = false: a helper search inside another call (IVF centroid probe) leaves the fallback counter and kernel timer alone
 int bruteforce_topk_tc_device(ThreadCtx &t, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq, int k,
-                              int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d);
+                              int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d, bool record_stats = true);
 bool tc_ivf_applicable(int64_t n, int dim, int64_t nq, int k, int nprobe, int metric, bool refine);
 // returns the queries whose completeness proof failed in `redo` (their rows of ok/od are still filled with best-effort results)
 int ivf_tc_scan(ThreadCtx &t, const IvfPlan &plan, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq,

@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "godist.cuh"
 #include "search_internal.cuh"
+#include <mutex>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cstring>
@@ -43,8 +44,6 @@ constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
 struct TcSmem {
     unsigned char a[STAGES][A_STAGE_BYTES];   // 1024-byte aligned (SWIZZLE_128B atoms)
     unsigned char b[STAGES][B_STAGE_BYTES];
-    float ld[KP][BM];                         // per-query sorted candidate list, [rank][query row]
-    int li[KP][BM];
     float xn[2][BN];                          // |x|^2 of the current tile's rows (double buffered with the accumulators)
     unsigned long long full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
     unsigned tmem_base;
@@ -194,7 +193,13 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             const TcUnit U = units[u];
             const bool valid_row = e < U.a_valid;
             const float qn = valid_row ? qnorm[U.a_row0 + e] : 0.f;
-            int cnt = 0; float thr = INFINITY;
+            // the KP best (approximate distance, row) pairs of this query row live in REGISTERS, ascending; an insertion is a
+            // branch-free compare/select sweep (no shared-memory dependency chain, lanes of a warp insert at different ranks at
+            // the same cost).  Rows of the tile past a_valid never insert (thr = -inf).
+            float ld[KP]; int li[KP];
+#pragma unroll
+            for (int j = 0; j < KP; j++) { ld[j] = INFINITY; li[j] = -1; }
+            float thr = valid_row ? INFINITY : -INFINITY;
             for (int n0 = U.n_begin; n0 < U.n_end; n0 += BN, tile++) {
                 const unsigned acc = tile & 1;
                 // |x|^2 of this tile's rows -> shared (2 per thread); named barrier over the 128 epilogue threads
@@ -202,8 +207,9 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 mbar_wait(&S.tmem_full[acc], (tile >> 1) & 1);
                 tc_fence_after();
+                const int ncols = U.n_end - n0 < BN ? U.n_end - n0 : BN;
 #pragma unroll 1
-                for (int c = 0; c < BN; c += 32) {
+                for (int c = 0; c < ncols; c += 32) {
                     float v[32];
                     tc_ld32(tmem_base + ((unsigned)(32 * ew) << 16) + acc * BN + c, v);
 #pragma unroll
@@ -211,12 +217,15 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                         const float d = (qn + S.xn[acc][c + j]) - 2.0f * v[j];   // +inf for rows past the end
                         if (d < thr) {
                             const int id = n0 + c + j;
-                            int pos;
-                            if (cnt < KP) pos = cnt++;
-                            else pos = KP - 1;
-                            while (pos > 0 && d < S.ld[pos - 1][e]) { S.ld[pos][e] = S.ld[pos - 1][e]; S.li[pos][e] = S.li[pos - 1][e]; pos--; }
-                            S.ld[pos][e] = d; S.li[pos][e] = id;
-                            if (cnt == KP) thr = S.ld[KP - 1][e];
+#pragma unroll
+                            for (int p = KP - 1; p > 0; p--) {     // descending: ld[p - 1] is still the old value when read
+                                const bool shift = d < ld[p - 1];  // the old neighbour moves down to p
+                                const bool here = !shift && d < ld[p];
+                                li[p] = shift ? li[p - 1] : (here ? id : li[p]);
+                                ld[p] = shift ? ld[p - 1] : (here ? d : ld[p]);
+                            }
+                            if (d < ld[0]) { ld[0] = d; li[0] = id; }
+                            thr = ld[KP - 1];
                         }
                     }
                 }
@@ -226,8 +235,9 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             }
             if (valid_row) {
                 const size_t base = (size_t)(U.out_base + e) * KP;
-                for (int j = 0; j < KP; j++) { part_d[base + j] = j < cnt ? S.ld[j][e] : INFINITY; part_i[base + j] = j < cnt ? S.li[j][e] : -1; }
-                part_thr[U.out_base + e] = thr;                  // every row of this unit that is NOT listed has d~ >= thr
+#pragma unroll
+                for (int j = 0; j < KP; j++) { part_d[base + j] = ld[j]; part_i[base + j] = li[j]; }   // empty slots: (+inf, -1)
+                part_thr[U.out_base + e] = thr;                  // every row of this unit that is NOT listed has d~ >= thr (+inf: list not full)
             }
         }
     }
@@ -290,60 +300,77 @@ int make_map(CUtensorMap *map, void *base, uint64_t rows, uint64_t kprime, uint3
 }
 
 // ---- post-processing: merge approximate lists, exact re-score, final order + completeness proof -----------------------------
-constexpr int KR = 32;   // candidates re-scored exactly per query
+constexpr int KR = 32;      // candidates re-scored exactly per query (k <= KP)
+constexpr int KR_WIDE = 64; // ... and for KP < k <= KW (centroid probes with nprobe up to 32)
+constexpr int KW = 32;
 
-// one thread per query: R-way merge of the (ascending) approximate lists -> KR best candidate ids; t_excl = smallest approximate
-// distance any row NOT among them can have (first unconsumed entry of every list, and the list-full threshold of every range)
+// one warp per query: R-way merge of the (ascending) approximate lists -> KR best candidate ids; t_excl = smallest approximate
+// distance any row NOT among them can have (first unconsumed entry of every list, and the list-full threshold of every range).
+// Lane l owns lists l, l+32, ...; every round the warp picks the smallest head (ties: lower list number).
 // list (q, r) lives at index  r * nq + q  without pos_map; with it (IVF) r = s * pos_cols + p names sub-range s of probe rank p:
 // index = s * pos_stride + pos_map[q * pos_cols + p]  (pos_map < 0 = no such list)
 constexpr int kMaxMergeLists = 256;
+constexpr int kMergeSlots = kMaxMergeLists / 32;
 __global__ void tc_merge_kernel(int nq, int R, const float *__restrict__ part_d, const int *__restrict__ part_i,
                                 const float *__restrict__ part_thr, const int *__restrict__ pos_map, int pos_cols, long long pos_stride,
-                                int *__restrict__ cand, float *__restrict__ t_excl) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nq) return;
-    auto lst = [&](int r) -> long long {
-        if (!pos_map) return (long long)r * nq + q;
-        const int p = pos_map[(size_t)q * pos_cols + r % pos_cols];
-        return p < 0 ? -1ll : (long long)(r / pos_cols) * pos_stride + p;
-    };
-    unsigned char head[kMaxMergeLists];
-    for (int r = 0; r < R; r++) head[r] = 0;
-    for (int j = 0; j < KR; j++) {
-        int best = -1; float bd = INFINITY;
-        for (int r = 0; r < R; r++) {
-            if (head[r] >= KP) continue;
-            const long long L = lst(r);
-            if (L < 0) { head[r] = KP; continue; }
-            const size_t idx = (size_t)L * KP + head[r];
-            if (part_i[idx] < 0) { head[r] = KP; continue; }
-            const float d = part_d[idx];
-            if (best < 0 || d < bd) { best = r; bd = d; }
-        }
-        if (best < 0) { cand[(size_t)q * KR + j] = -1; continue; }
-        cand[(size_t)q * KR + j] = part_i[(size_t)lst(best) * KP + head[best]];
-        head[best]++;
-    }
+                                int kr, int *__restrict__ cand, float *__restrict__ t_excl) {
+    const int lane = threadIdx.x & 31;
+    const int q = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+    if (q >= nq) return;   // whole warps leave together
+    long long L[kMergeSlots]; int head[kMergeSlots]; float cur[kMergeSlots];
     float t = INFINITY;
-    for (int r = 0; r < R; r++) {
-        const long long L = lst(r);
-        if (L < 0) continue;
-        t = fminf(t, part_thr[L]);
-        if (head[r] < KP) { const size_t idx = (size_t)L * KP + head[r]; if (part_i[idx] >= 0) t = fminf(t, part_d[idx]); }
+#pragma unroll
+    for (int i = 0; i < kMergeSlots; i++) {
+        const int r = lane + 32 * i;
+        long long l = -1;
+        if (r < R) {
+            if (!pos_map) l = (long long)r * nq + q;
+            else { const int p = pos_map[(size_t)q * pos_cols + r % pos_cols]; l = p < 0 ? -1ll : (long long)(r / pos_cols) * pos_stride + p; }
+        }
+        L[i] = l; head[i] = 0; cur[i] = INFINITY;
+        if (l >= 0) {
+            t = fminf(t, part_thr[l]);
+            if (part_i[(size_t)l * KP] >= 0) cur[i] = part_d[(size_t)l * KP];
+        }
     }
-    t_excl[q] = t;
+    for (int j = 0; j < kr; j++) {
+        float bd = INFINITY; int br = 0x7fffffff;
+#pragma unroll
+        for (int i = 0; i < kMergeSlots; i++) if (cur[i] < bd) { bd = cur[i]; br = lane + 32 * i; }   // ascending i = ascending list number
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float od = __shfl_xor_sync(0xffffffffu, bd, o); const int orr = __shfl_xor_sync(0xffffffffu, br, o);
+            if (od < bd || (od == bd && orr < br)) { bd = od; br = orr; }
+        }
+        if (br == 0x7fffffff) { if (lane == 0) cand[(size_t)q * kr + j] = -1; continue; }   // every list is exhausted (warp-uniform)
+        if ((br & 31) == lane) {
+#pragma unroll
+            for (int i = 0; i < kMergeSlots; i++)
+                if (i == (br >> 5)) {
+                    const size_t idx = (size_t)L[i] * KP + head[i];
+                    cand[(size_t)q * kr + j] = part_i[idx];
+                    head[i]++;
+                    cur[i] = (head[i] < KP && part_i[idx + 1] >= 0) ? part_d[idx + 1] : INFINITY;
+                }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kMergeSlots; i++) t = fminf(t, cur[i]);   // first unconsumed entry of every list
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t = fminf(t, __shfl_xor_sync(0xffffffffu, t, o));
+    if (lane == 0) t_excl[q] = t;
 }
 
 // one warp per (query, candidate): the bit-exact Go-order L2sq (godist.cuh)
-__global__ void tc_rescore_kernel(const float *__restrict__ data, const float *__restrict__ queries, int dim, int nq,
+__global__ void tc_rescore_kernel(const float *__restrict__ data, const float *__restrict__ queries, int dim, int nq, int kr,
                                   const int *__restrict__ cand, float *__restrict__ exact) {
     const int lane = threadIdx.x & 31;
     const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t p = w; p < (int64_t)nq * KR; p += nw) {
+    for (int64_t p = w; p < (int64_t)nq * kr; p += nw) {
         const int id = cand[p];
         float d = INFINITY;
         if (id >= 0) {
-            const uint8_t *a = reinterpret_cast<const uint8_t *>(queries + (p / KR) * dim), *b = reinterpret_cast<const uint8_t *>(data + (int64_t)id * dim);
+            const uint8_t *a = reinterpret_cast<const uint8_t *>(queries + (p / kr) * dim), *b = reinterpret_cast<const uint8_t *>(data + (int64_t)id * dim);
             const bool al = ((((uintptr_t)a) | ((uintptr_t)b)) & 15) == 0;
             d = godist::go_l2sq<float>(a, b, dim, lane, al, false, true);
         }
@@ -362,18 +389,19 @@ __global__ void tc_max_kernel(const float *__restrict__ v, int64_t n, float *out
 // one thread per query: order the KR exact candidates by (distance, id), emit the top k with the reference's front padding, and
 // prove completeness:  every excluded row has approximate distance >= t_excl, |approx - real| <= eps_tc, |real - go| <= eps_go,
 // so d_k + eps_tc + eps_go < t_excl  =>  no excluded row can displace the k-th result.  flag = 1 when the proof fails.
+template <int KRT>
 __global__ void tc_final_kernel(int nq, int k, int64_t n_rows, int dim, const int *__restrict__ cand, const float *__restrict__ exact,
                                 const float *__restrict__ t_excl, const float *__restrict__ qnorm, const float *__restrict__ xnorm_max,
                                 const int64_t *__restrict__ id_map, int64_t key_base, int sqrt_out, int64_t *__restrict__ out_k,
                                 double *__restrict__ out_d, int *__restrict__ flags) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
-    float d[KR]; int64_t id[KR]; int m = 0;
-    for (int j = 0; j < KR; j++) {
-        const int lc = cand[(size_t)q * KR + j];
+    float d[KRT]; int64_t id[KRT]; int m = 0;
+    for (int j = 0; j < KRT; j++) {
+        const int lc = cand[(size_t)q * KRT + j];
         if (lc < 0) continue;
         const int64_t c = id_map ? id_map[lc] : (int64_t)lc + key_base;   // final key; ties are ordered by it
-        const float v = exact[(size_t)q * KR + j];
+        const float v = exact[(size_t)q * KRT + j];
         int pos = m++;
         while (pos > 0 && (v < d[pos - 1] || (v == d[pos - 1] && c < id[pos - 1]))) { d[pos] = d[pos - 1]; id[pos] = id[pos - 1]; pos--; }
         d[pos] = v; id[pos] = c;
@@ -438,6 +466,11 @@ int g_last_tc_fallbacks = -1;   // queries of the last tensor-core search that f
 
 struct TcOperand { __nv_bfloat16 *bf = nullptr; float *norm = nullptr; int kprime = 0; };
 
+// datasets split once by MoB200_SearchPrepare (index load); looked up by (pointer, rows, dim)
+struct PreparedOperand { const float *x; int64_t n; int dim; int device; TcOperand op; };
+static std::mutex g_prepared_mu;
+static std::vector<PreparedOperand> g_prepared;
+
 // split an fp32 row-major matrix into the K-concatenated bf16 operand; *nonfinite (device flag) is raised on Inf/NaN
 static int tc_prepare(ThreadCtx &t, const float *x, int64_t n, int dim, int mode, int *dnonfinite, TcOperand &op) {
     // one API call may split the same matrix more than once (IVF refine pass): the operand lives in the call's arena, so it
@@ -445,6 +478,10 @@ static int tc_prepare(ThreadCtx &t, const float *x, int64_t n, int dim, int mode
     struct Cached { const float *x = nullptr; int64_t n = 0; int dim = 0, mode = 0; uint64_t epoch = ~0ull; const ThreadCtx *t = nullptr; TcOperand op; };
     static thread_local Cached cache[2];
     Cached &c = cache[mode & 1];
+    if (mode == 1) {
+        std::lock_guard<std::mutex> lk(g_prepared_mu);
+        for (const PreparedOperand &e : g_prepared) if (e.x == x && e.n == n && e.dim == dim) { op = e.op; return MO_RC_SUCCESS; }
+    }
     if (c.t == &t && c.epoch == t.arena_epoch && c.x == x && c.n == n && c.dim == dim && c.mode == mode) { op = c.op; return MO_RC_SUCCESS; }
     op.kprime = ((3 * dim + BK - 1) / BK) * BK;
     op.bf = (__nv_bfloat16 *)arena_alloc(t, (size_t)(n > 0 ? n : 1) * op.kprime * 2 + 1024);
@@ -489,8 +526,9 @@ static int tc_run_units(ThreadCtx &t, const TcOperand &A, int64_t a_rows, const 
 static int tc_finish(ThreadCtx &t, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq, int k, int R, const int *pos_map,
                      int pos_cols, long long pos_stride, const float *part_d, const int *part_i, const float *part_thr, const float *qnorm, const float *xnorm,
                      const int64_t *id_map, int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d, std::vector<int> &redo) {
-    int *cand = (int *)arena_alloc(t, sizeof(int) * (size_t)nq * KR);
-    float *exact = (float *)arena_alloc(t, sizeof(float) * (size_t)nq * KR);
+    const int kr = k > KP ? KR_WIDE : KR;
+    int *cand = (int *)arena_alloc(t, sizeof(int) * (size_t)nq * kr);
+    float *exact = (float *)arena_alloc(t, sizeof(float) * (size_t)nq * kr);
     float *t_excl = (float *)arena_alloc(t, sizeof(float) * (size_t)nq + 16);
     int *flags = (int *)arena_alloc(t, sizeof(int) * (size_t)nq);
     if (!cand || !exact || !t_excl || !flags) return MO_RC_INTERNAL_ERROR;
@@ -499,11 +537,12 @@ static int tc_finish(ThreadCtx &t, const float *ddata, int64_t n, int dim, const
     tc_max_kernel<<<num_sms() * 2, 256, 0, t.stream>>>(xnorm, n, xmax);
     MOB_LAUNCH_CHECK();
     if (R > kMaxMergeLists) { set_error("tc search: %d candidate lists per query exceed the merge limit %d", R, kMaxMergeLists); return MO_RC_INTERNAL_ERROR; }
-    tc_merge_kernel<<<(unsigned)((nq + 63) / 64), 64, 0, t.stream>>>((int)nq, R, part_d, part_i, part_thr, pos_map, pos_cols, pos_stride, cand, t_excl);
+    tc_merge_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, t.stream>>>((int)nq, R, part_d, part_i, part_thr, pos_map, pos_cols, pos_stride, kr, cand, t_excl);
     MOB_LAUNCH_CHECK();
-    tc_rescore_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(ddata, dq, dim, (int)nq, cand, exact);
+    tc_rescore_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(ddata, dq, dim, (int)nq, kr, cand, exact);
     MOB_LAUNCH_CHECK();
-    tc_final_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, t.stream>>>((int)nq, k, n, dim, cand, exact, t_excl, qnorm, xmax, id_map, key_base, sqrt_out, out_k, out_d, flags);
+    if (kr == KR) tc_final_kernel<KR><<<(unsigned)((nq + 127) / 128), 128, 0, t.stream>>>((int)nq, k, n, dim, cand, exact, t_excl, qnorm, xmax, id_map, key_base, sqrt_out, out_k, out_d, flags);
+    else tc_final_kernel<KR_WIDE><<<(unsigned)((nq + 127) / 128), 128, 0, t.stream>>>((int)nq, k, n, dim, cand, exact, t_excl, qnorm, xmax, id_map, key_base, sqrt_out, out_k, out_d, flags);
     MOB_LAUNCH_CHECK();
     std::vector<int> hflags((size_t)nq);
     MOB_CUDA_TRY(cudaMemcpyAsync(hflags.data(), flags, sizeof(int) * (size_t)nq, cudaMemcpyDeviceToHost, t.stream));
@@ -515,9 +554,20 @@ static int tc_finish(ThreadCtx &t, const float *ddata, int64_t n, int dim, const
 
 bool tc_search_applicable(int64_t n, int dim, int64_t nq, int k, int metric) {
     if (g_search_mode == 1) return false;
-    const bool shape_ok = (metric == MO_METRIC_L2 || metric == MO_METRIC_L2SQ) && k >= 1 && k <= KP && dim >= 16 && n >= BN && n < (1ll << 31) - BN;
+    // k <= KP: one candidate list per (query, row range); KP < k <= KW ("wide", centroid probes): ranges of >= 128 rows, at least 8 of them
+    const bool shape_ok = (metric == MO_METRIC_L2 || metric == MO_METRIC_L2SQ) && k >= 1 && dim >= 16 && n < (1ll << 31) - BN &&
+                          (k <= KP ? n >= BN : (k <= KW && n >= 1024));
     if (g_search_mode == 2) return shape_ok;
     return shape_ok && nq >= 256 && n >= 16384 && dim >= 64;   // below this the exact kernel wins (operand split + launch overheads)
+}
+
+// centroid probe of an IVF search (findCentroids): many queries against a small table, k = nprobe
+bool tc_probe_applicable(int64_t nlist, int dim, int64_t nq, int nprobe, int metric) {
+    if (g_search_mode == 1) return false;
+    const bool shape_ok = (metric == MO_METRIC_L2 || metric == MO_METRIC_L2SQ) && nprobe >= 1 && dim >= 16 &&
+                          (nprobe <= KP ? nlist >= BN : (nprobe <= KW && nlist >= 1024));
+    if (g_search_mode == 2) return shape_ok;
+    return shape_ok && nq >= 1024 && dim >= 64;
 }
 
 bool tc_ivf_applicable(int64_t n, int dim, int64_t nq, int k, int nprobe, int metric, bool refine) {
@@ -530,7 +580,7 @@ bool tc_ivf_applicable(int64_t n, int dim, int64_t nq, int k, int nprobe, int me
 
 // Brute-force top-k through the tensor-core candidate pass; results are the exact answer (see file header).
 int bruteforce_topk_tc_device(ThreadCtx &t, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq, int k,
-                              int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d) {
+                              int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d, bool record_stats) {
     int *dnonfinite = (int *)arena_alloc(t, 4);
     if (!dnonfinite) return MO_RC_INTERNAL_ERROR;
     MOB_CUDA_TRY(cudaMemsetAsync(dnonfinite, 0, 4, t.stream));
@@ -542,7 +592,7 @@ int bruteforce_topk_tc_device(ThreadCtx &t, const float *ddata, int64_t n, int d
     rc = read_back(t, &hnonfinite, dnonfinite, 4);
     if (rc) return rc;
     if (hnonfinite) {   // the error bound of the tensor-core pass does not apply to Inf/NaN inputs
-        g_last_tc_fallbacks = (int)nq;
+        if (record_stats) g_last_tc_fallbacks = (int)nq;
         return bruteforce_topk_device(t, ddata, n, dim, dq, nq, k, MO_METRIC_L2SQ, key_base, sqrt_out, out_k, out_d);
     }
     // work units: (query tile, row range); ranges sized so that units ~ a whole number of waves over the SMs
@@ -550,25 +600,29 @@ int bruteforce_topk_tc_device(ThreadCtx &t, const float *ddata, int64_t n, int d
     const int64_t ntiles = (n + BN - 1) / BN;
     int R = (int)((8ll * num_sms() + mt - 1) / mt);
     if (R > ntiles) R = (int)ntiles;
-    if (R > 64) R = 64;   // the merge kernel keeps one list head per range in a 64-entry array
+    if (R > 64) R = 64;
     if (R < 1) R = 1;
-    const int64_t tiles_per = (ntiles + R - 1) / R;
-    R = (int)((ntiles + tiles_per - 1) / tiles_per);
+    int64_t range_rows = (ntiles + R - 1) / R * BN;
+    if (k > KP) {   // wide mode: R * KP candidates must comfortably exceed k -> short ranges (the MMA tile is masked beyond n_end)
+        range_rows = ((n + 63) / 64 + 127) / 128 * 128;
+        if (range_rows < 128) range_rows = 128;
+    }
+    R = (int)((n + range_rows - 1) / range_rows);
     std::vector<TcUnit> units;
     for (int r = 0; r < R; r++)
         for (int m = 0; m < mt; m++) {
             TcUnit u; u.a_row0 = m * BM; u.a_valid = (int)(nq - u.a_row0 < BM ? nq - u.a_row0 : BM);
-            u.n_begin = (int)(r * tiles_per * BN); u.n_end = (int)((r + 1) * tiles_per * BN < n ? (r + 1) * tiles_per * BN : n);
+            u.n_begin = (int)(r * range_rows); u.n_end = (int)((r + 1) * range_rows < n ? (r + 1) * range_rows : n);
             u.out_base = (long long)r * nq + u.a_row0;
             if (u.n_begin < u.n_end) units.push_back(u);
         }
     float *part_d, *part_thr; int *part_i;
-    rc = tc_run_units(t, A, nq, B, n, units, (int64_t)R * nq, &part_d, &part_i, &part_thr);
+    rc = tc_run_units(t, A, nq, B, n, units, (int64_t)R * nq, &part_d, &part_i, &part_thr, record_stats);
     if (rc) return rc;
     std::vector<int> redo;
     rc = tc_finish(t, ddata, n, dim, dq, nq, k, R, nullptr, 0, 0, part_d, part_i, part_thr, A.norm, B.norm, nullptr, key_base, sqrt_out, out_k, out_d, redo);
     if (rc) return rc;
-    g_last_tc_fallbacks = (int)redo.size();
+    if (record_stats) g_last_tc_fallbacks = (int)redo.size();
     if (!redo.empty()) {   // queries whose completeness could not be proven: exact kernel, results scattered back
         const int m = (int)redo.size();
         int *didx = (int *)arena_alloc(t, sizeof(int) * (size_t)m);
@@ -647,3 +701,50 @@ int ivf_tc_scan(ThreadCtx &t, const IvfPlan &plan, const float *ddata, int64_t n
 }
 
 }  // namespace mob
+
+extern "C" {
+
+// Index load: split a RESIDENT dataset into the tensor-core operand once instead of once per search.  The rows must not change
+// until MoB200_SearchRelease(data).  Datasets the tensor-core path cannot serve (dim < 16, Inf/NaN values) are left unprepared:
+// searches on them behave exactly as without this call.
+int32_t MoB200_SearchPrepare(const void *data, uint64_t n, int64_t dim) {
+    using namespace mob;
+    ThreadCtx &t = tctx();
+    if (!t.ready) return MO_RC_INTERNAL_ERROR;
+    if (!data || n == 0 || dim < 16 || n >= (1ull << 31) - BN) return MO_RC_SUCCESS;
+    if (!is_device_ptr(data)) { set_error("SearchPrepare: the dataset must be device memory"); return MO_RC_INVALID_ARGUMENT; }
+    MoB200_SearchRelease(data);
+    PreparedOperand e; e.x = (const float *)data; e.n = (int64_t)n; e.dim = (int)dim; e.device = 0;
+    e.op.kprime = ((3 * (int)dim + BK - 1) / BK) * BK;
+    MOB_CUDA_TRY(cudaMalloc((void **)&e.op.bf, (size_t)n * e.op.kprime * 2 + 1024));
+    if (cudaMalloc((void **)&e.op.norm, (size_t)n * 4) != cudaSuccess) { cudaFree(e.op.bf); set_error("SearchPrepare: out of device memory"); return MO_RC_INTERNAL_ERROR; }
+    int *dnonfinite = (int *)arena_alloc(t, 4);
+    int hnonfinite = 1;
+    int rc = dnonfinite ? MO_RC_SUCCESS : MO_RC_INTERNAL_ERROR;
+    if (!rc && cudaMemsetAsync(dnonfinite, 0, 4, t.stream) != cudaSuccess) rc = MO_RC_INTERNAL_ERROR;
+    if (!rc) {
+        split_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(e.x, e.n, e.dim, e.op.kprime, 1, e.op.bf, e.op.norm, nullptr, dnonfinite);
+        g_launches++;
+        if (cudaGetLastError() != cudaSuccess) rc = MO_RC_INTERNAL_ERROR;
+    }
+    if (!rc) rc = read_back(t, &hnonfinite, dnonfinite, 4);
+    arena_reset(t);
+    if (rc || hnonfinite) { cudaFree(e.op.bf); cudaFree(e.op.norm); return rc; }
+    std::lock_guard<std::mutex> lk(g_prepared_mu);
+    g_prepared.push_back(e);
+    return MO_RC_SUCCESS;
+}
+
+int32_t MoB200_SearchRelease(const void *data) {
+    using namespace mob;
+    std::lock_guard<std::mutex> lk(g_prepared_mu);
+    for (size_t i = 0; i < g_prepared.size(); i++)
+        if (g_prepared[i].x == data) {
+            cudaFree(g_prepared[i].op.bf); cudaFree(g_prepared[i].op.norm);
+            g_prepared.erase(g_prepared.begin() + (long)i);
+            return MO_RC_SUCCESS;
+        }
+    return MO_RC_SUCCESS;
+}
+
+}  // extern "C"

@@ -136,6 +136,13 @@ class BruteForceIndex:
             ds = np.ascontiguousarray(dataset, dtype=np.float32)
             self.n = ds.shape[0]
             self.buf, self.owned = DeviceBuffer.from_numpy(ds, self.lib), True
+        self._prepare()
+
+    def _prepare(self):
+        # Load: split the resident rows into the tensor-core operand once (L2 metrics; a no-op where it does not apply)
+        self.prepared = self.metric in (capi.METRIC_L2, capi.METRIC_L2SQ) and self.n > 0
+        if self.prepared:
+            capi.check(self.lib.MoB200_SearchPrepare(self.buf.ptr, self.n, self.dim), self.lib)
 
     def search(self, queries, limit, out_device=False):
         if isinstance(queries, DeviceBuffer):
@@ -155,6 +162,8 @@ class BruteForceIndex:
         return keys, dists
 
     def destroy(self):
+        if self.buf is not None and getattr(self, "prepared", False):
+            self.lib.MoB200_SearchRelease(self.buf.ptr)
         if self.owned and self.buf is not None:
             self.buf.free()
         self.buf = None
@@ -184,6 +193,9 @@ class IvfflatSearchIndex:
             self.d_data = DeviceBuffer.from_numpy(data[order], self.lib)
         self.d_cent = DeviceBuffer.from_numpy(centroids, self.lib)
         self.d_off = DeviceBuffer.from_numpy(self.offsets, self.lib)
+        self.prepared = self.metric in (capi.METRIC_L2, capi.METRIC_L2SQ) and self.n > 0
+        if self.prepared:   # LoadIndex: the list-ordered entries are split into the tensor-core operand once
+            capi.check(self.lib.MoB200_SearchPrepare(self.d_data.ptr, self.n, self.dim), self.lib)
 
     @classmethod
     def build(cls, data_dev, n, centroids, metric=capi.METRIC_L2, lib=None, chunk=500_000):
@@ -225,6 +237,8 @@ class IvfflatSearchIndex:
         return keys, dists
 
     def destroy(self):
+        if self.prepared:
+            self.lib.MoB200_SearchRelease(self.d_data.ptr)
         for b in (self.d_data, self.d_cent, self.d_off, self.d_ids):
             b.free()
 

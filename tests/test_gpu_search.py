@@ -118,7 +118,8 @@ def test_ivf_empty_lists_and_small_index(gpu):
     idx.destroy()
 
 
-@pytest.mark.parametrize("n,dim,nq,k", [(20_000, 128, 300, 10), (9_000, 768, 257, 10), (5_000, 100, 130, 5), (70_000, 64, 1000, 16), (300, 32, 40, 3)])
+@pytest.mark.parametrize("n,dim,nq,k", [(20_000, 128, 300, 10), (9_000, 768, 257, 10), (5_000, 100, 130, 5), (70_000, 64, 1000, 16), (300, 32, 40, 3),
+                                        (20_000, 96, 200, 32), (1_024, 64, 500, 25)])   # k > 16: the wide mode of centroid probes
 def test_tensor_core_candidate_path_is_exact(gpu, n, dim, nq, k):
     """tcgen05 candidate generation + exact re-scoring + completeness proof (csrc/tcsearch.cu): the results must be the exact
     answer (bit-exact distances), and the tensor path itself must be doing the work (few proof failures -> few fallbacks)."""
@@ -172,7 +173,8 @@ def test_tensor_core_path_non_finite_inputs_use_exact_kernel(gpu):
 
 
 @pytest.mark.parametrize("sqrt_out", [False, True])
-@pytest.mark.parametrize("nlist,dim,n,nq,k,nprobe", [(64, 96, 20_000, 150, 10, 8), (32, 768, 6_000, 300, 10, 32), (16, 100, 3_000, 64, 5, 3)])
+@pytest.mark.parametrize("nlist,dim,n,nq,k,nprobe", [(64, 96, 20_000, 150, 10, 8), (32, 768, 6_000, 300, 10, 32), (16, 100, 3_000, 64, 5, 3),
+                                                    (1024, 64, 30_000, 300, 10, 32), (300, 64, 9_000, 200, 4, 9)])   # probe itself on the tensor cores
 def test_ivf_tensor_core_scan_is_exact(gpu, nlist, dim, n, nq, k, nprobe, sqrt_out):
     """IVF list scan through the tcgen05 candidate kernel ((list, query-tile) units over gathered split operands): exact results"""
     centers = datagen.vectors_f32(30, 0, nlist, dim) * 4
