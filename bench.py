@@ -202,6 +202,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--queries", type=int, default=10_000)
+    ap.add_argument("--tune", action="append", default=[], metavar="NAME=VALUE",
+                    help="kernel-variant knob passed to MoB200_SetTuning (experiments only; the default run uses none)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -212,6 +214,9 @@ def main():
     from matrixone_b200.vector import DeviceBuffer, PinnedArray
     lib = capi.load_library()
     capi.check(lib.MoB200_Init(local), lib)
+    for kv in args.tune:
+        name, _, val = kv.partition("=")
+        lib.MoB200_SetTuning(name.encode(), int(val))
 
     dist = None
     if world > 1:
@@ -429,7 +434,8 @@ def main():
         # dominant kernel = tc_candidates_kernel over (list, 128-query tile) units: 2 * K' flop per (query, probed row) pair,
         # K' = 3 * dim (hi/lo operand split); pairs = queries * nprobe * mean list length
         pairs = float(args.queries) * 32 * (n / 1024.0)
-        flop = 2.0 * pairs * (3 * 768)
+        kused = int(lib.MoB200_SetTuning(b"get_tc_kused", 0)) or 3 * 768
+        flop = 2.0 * pairs * kused
         try:
             mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
             tpeak, tsrc = float(mp["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst)"
@@ -437,7 +443,7 @@ def main():
             tpeak, tsrc = 1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s)"
         ach = flop / (kern_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": None,
-                    "kernel": "tc_candidates_kernel (tcgen05 bf16) over (list, query-tile) units", "kernel_ms": kern_ms, "algorithmic_flop_per_launch": flop,
+                    "kernel": "tc_candidates_kernel (tcgen05 bf16, K = %d per pair) over (list, query-tile) units" % kused, "kernel_ms": kern_ms, "algorithmic_flop_per_launch": flop,
                     "peak_source": tsrc, "tc_refined_queries": int(lib.MoB200_SetTuning(b"get_tc_refined", 0)),
                     "tc_fallback_queries": int(lib.MoB200_SetTuning(b"get_tc_fallbacks", 0)),
                     "note": "useful flop only: tiles are padded to 128 queries x 256 rows, so the tensor pipe does more work than counted"}
@@ -448,7 +454,9 @@ def main():
                     "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src}
     else:
         # dominant kernel = tc_candidates_kernel: one bf16 GEMM with K' = 3 * dim (hi/lo operand split), 2 * Q * N * K' flop
-        flop = 2.0 * args.queries * n * (3 * 768)
+        # K elements the timed candidate pass multiplies per (query, row): 768 = hi.hi only (one-term level), 2304 = three-term product
+        kused = int(lib.MoB200_SetTuning(b"get_tc_kused", 0)) or 3 * 768
+        flop = 2.0 * args.queries * n * kused
         tpeak, tsrc = 1709.9, "fallback"
         try:
             mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -457,7 +465,7 @@ def main():
             tpeak, tsrc = 1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s)"
         ach = flop / (kern_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": None,
-                    "kernel": "tc_candidates_kernel (tcgen05 bf16, K' = 2304)", "kernel_ms": kern_ms, "algorithmic_flop_per_launch": flop, "peak_source": tsrc,
+                    "kernel": "tc_candidates_kernel (tcgen05 bf16, K = %d per pair)" % kused, "kernel_ms": kern_ms, "algorithmic_flop_per_launch": flop, "peak_source": tsrc,
                     "tc_refined_queries": int(lib.MoB200_SetTuning(b"get_tc_refined", 0)),
                     "tc_fallback_queries": int(lib.MoB200_SetTuning(b"get_tc_fallbacks", 0))}
     cpu_baseline = None

@@ -30,22 +30,36 @@
 #include <cstring>
 #include <cmath>
 #include <vector>
+#include <algorithm>
 
 using namespace mob;
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int BM = 128, BN = 256, BK = 64;
 constexpr int KP = 16;                      // candidates kept per (query, row range)
 constexpr int kTcThreads = 256;             // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warp 3 idle, warps 4-7 epilogue
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
-constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
 
-struct TcSmem {
-    unsigned char a[STAGES][A_STAGE_BYTES];   // 1024-byte aligned (SWIZZLE_128B atoms)
-    unsigned char b[STAGES][B_STAGE_BYTES];
+// PAIR = false: one CTA per unit, tcgen05.mma.cta_group::1, M = 128: the CTA stages the whole 256-row B tile (48 KB per k-block).
+// PAIR = true : a cluster of two CTAs (one TPC) per unit, tcgen05.mma.cta_group::2, M = 256: each CTA stages its own 128 query
+//               rows and HALF of the B tile (32 KB per k-block for the same flop per SM) -- the candidate pass is bound by
+//               L2 -> SM bytes, so this is worth up to 1.5x where there are enough queries to fill 256-row tiles.
+template <bool PAIR>
+struct TcCfg {
+    static constexpr int kStages = PAIR ? 6 : 4;
+    static constexpr int kBRows = PAIR ? BN / 2 : BN;            // B rows staged per CTA per k-block
+    static constexpr int kBStageBytes = kBRows * BK * 2;         // 16 / 32 KB
+    static constexpr int kTileM = PAIR ? 2 * BM : BM;            // query rows per unit
+};
+
+template <bool PAIR>
+struct TcSmemT {
+    unsigned char a[TcCfg<PAIR>::kStages][A_STAGE_BYTES];                 // 1024-byte aligned (SWIZZLE_128B atoms)
+    unsigned char b[TcCfg<PAIR>::kStages][TcCfg<PAIR>::kBStageBytes];
     float xn[2][BN];                          // |x|^2 of the current tile's rows (double buffered with the accumulators)
-    unsigned long long full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
+    float scratch[32][BM];                    // epilogue slow path: a thread's 32 distances of the current chunk, [column][thread]
+    unsigned long long full[TcCfg<PAIR>::kStages], empty[TcCfg<PAIR>::kStages], tmem_full[2], tmem_empty[2];
     unsigned tmem_base;
 };
 
@@ -88,21 +102,49 @@ __device__ __forceinline__ void tc_mma_bf16(unsigned tmem_d, unsigned long long 
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
-// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = TMEM lane = query row)
-__device__ __forceinline__ void tc_ld32(unsigned taddr, float *v) {
-    unsigned r[32];
+// ---- CTA-pair (cta_group::2) variants.  Barrier operands that live in the LEADER CTA (rank 0) are addressed through mapa.
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned mapa_rank(unsigned local_addr, unsigned rank) {
+    unsigned r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// both CTAs of the pair load into their OWN shared memory and signal the leader's barrier (cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap *map, unsigned bar_cluster_addr, void *dst, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(unsigned bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+// arrives on the barrier at the same shared-memory offset in both CTAs of the pair once the MMAs issued so far have completed
+__device__ __forceinline__ void tc_commit_pair(unsigned long long *bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((unsigned short)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(unsigned tmem_d, unsigned long long desc_a, unsigned long long desc_b, unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = TMEM lane = query row).  The load is asynchronous:
+// tc_ld32_issue starts it, tc_ld32_wait (tcgen05.wait::ld) makes the registers valid; the "+f" operands tie every later use of
+// v[] to the wait so the compiler cannot schedule arithmetic on them above it.
+__device__ __forceinline__ void tc_ld32_issue(unsigned taddr, float *v) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
         "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]), "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_ld32_wait(float *v) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+        : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]), "+f"(v[16]), "+f"(v[17]), "+f"(v[18]), "+f"(v[19]), "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23]), "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31])
+        :: "memory");
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
@@ -112,58 +154,78 @@ __device__ __forceinline__ unsigned long long make_desc(unsigned smem_addr) {
 }
 // instruction descriptor (UMMA::InstrDescriptor): D=F32 (bit 4), A=BF16 (bit 7), B=BF16 (bit 10), K-major both, N>>3 at 17, M>>4 at 24
 constexpr unsigned kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
+constexpr unsigned kIdescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)((2 * BM) >> 4) << 24);
 
-// one work unit: up to 128 rows of the A' operand (queries) x dataset rows [n_begin, n_end); lists are written at out_base + row
+// one work unit: up to kTileM rows of the A' operand (queries) x dataset rows [n_begin, n_end); lists are written at out_base + row
 struct TcUnit { int a_row0; int a_valid; int n_begin; int n_end; long long out_base; };
 
+template <bool PAIR>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                     const TcUnit *__restrict__ units, int nunits, int kprime /* K' */,
+                     const TcUnit *__restrict__ units, int nunits, int nkb /* 64-element k-blocks of K' to run */,
                      const float *__restrict__ qnorm, const float *__restrict__ xnorm,
                      float *__restrict__ part_d, int *__restrict__ part_i, float *__restrict__ part_thr) {
+    using Cfg = TcCfg<PAIR>;
+    constexpr int STAGES = Cfg::kStages;
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B atoms need 1024-byte alignment in the shared window: align by hand (the launch adds 1024 spare bytes)
-    TcSmem &S = *reinterpret_cast<TcSmem *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    TcSmemT<PAIR> &S = *reinterpret_cast<TcSmemT<PAIR> *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nkb = kprime / BK;
+    const unsigned rank = PAIR ? cluster_ctarank() : 0u;            // 0 = leader: issues the MMAs, owns the full / tmem_empty barriers
+    const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int nworkers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(&S.tmem_full[a], 1); mbar_init(&S.tmem_empty[a], 4); }
+        for (int a = 0; a < 2; a++) { mbar_init(&S.tmem_full[a], 1); mbar_init(&S.tmem_empty[a], PAIR ? 8 : 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == 2) {   // TMEM: 512 columns = two 128 x 256 fp32 accumulators
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S.tmem_base)) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (warp == 2) {   // TMEM: 512 columns = two 128 x 256 fp32 accumulators (per CTA)
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S.tmem_base)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S.tmem_base)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();   // the peer's barriers must be initialised before anything signals them
     tc_fence_after();
     const unsigned tmem_base = S.tmem_base;
 
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== TMA producer (one thread; in a pair both CTAs run it, each for its own rows) =====
         if (lane == 0) {
             int stage = 0; unsigned phase = 0;
-            for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+            for (int u = worker; u < nunits; u += nworkers) {
                 const TcUnit U = units[u];
                 for (int n0 = U.n_begin; n0 < U.n_end; n0 += BN) {
                     for (int kb = 0; kb < nkb; kb++) {
                         mbar_wait(&S.empty[stage], phase ^ 1);
-                        mbar_expect_tx(&S.full[stage], A_STAGE_BYTES + B_STAGE_BYTES);
-                        tma_load_2d(&map_a, &S.full[stage], S.a[stage], kb * BK, U.a_row0);
-                        tma_load_2d(&map_b, &S.full[stage], S.b[stage], kb * BK, n0);
+                        if (PAIR) {
+                            // the leader's barrier collects the bytes of all four loads (two per CTA)
+                            if (rank == 0) mbar_expect_tx(&S.full[stage], 2 * (A_STAGE_BYTES + Cfg::kBStageBytes));
+                            const unsigned bar = mapa_rank(smem_u32(&S.full[stage]), 0);
+                            tma_load_2d_pair(&map_a, bar, S.a[stage], kb * BK, U.a_row0 + (int)rank * BM);
+                            tma_load_2d_pair(&map_b, bar, S.b[stage], kb * BK, n0 + (int)rank * Cfg::kBRows);
+                        } else {
+                            mbar_expect_tx(&S.full[stage], A_STAGE_BYTES + Cfg::kBStageBytes);
+                            tma_load_2d(&map_a, &S.full[stage], S.a[stage], kb * BK, U.a_row0);
+                            tma_load_2d(&map_b, &S.full[stage], S.b[stage], kb * BK, n0);
+                        }
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
+        // ===== MMA issuer (one thread of the leader CTA) =====
+        if (lane == 0 && rank == 0) {
             int stage = 0; unsigned phase = 0; unsigned tile = 0;
-            for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+            for (int u = worker; u < nunits; u += nworkers) {
                 const TcUnit U = units[u];
                 for (int n0 = U.n_begin; n0 < U.n_end; n0 += BN, tile++) {
                     const unsigned acc = tile & 1;
@@ -175,24 +237,29 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                         tc_fence_after();
                         const unsigned long long da = make_desc(smem_u32(S.a[stage])), db = make_desc(smem_u32(S.b[stage]));
 #pragma unroll
-                        for (int k = 0; k < BK / 16; k++)   // +32 bytes (= 2 in the >>4 address field) per K16 step inside the 128-B swizzle atom
-                            tc_mma_bf16(tmem_d, da + 2 * k, db + 2 * k, kIdesc, (kb | k) != 0);
-                        tc_commit(&S.empty[stage]);          // frees the smem slot once these MMAs have read it
+                        for (int k = 0; k < BK / 16; k++) {  // +32 bytes (= 2 in the >>4 address field) per K16 step inside the 128-B swizzle atom
+                            if (PAIR) tc_mma_bf16_pair(tmem_d, da + 2 * k, db + 2 * k, kIdescPair, (kb | k) != 0);
+                            else tc_mma_bf16(tmem_d, da + 2 * k, db + 2 * k, kIdesc, (kb | k) != 0);
+                        }
+                        if (PAIR) tc_commit_pair(&S.empty[stage]); else tc_commit(&S.empty[stage]);   // frees the smem slot(s) once these MMAs have read them
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
-                    tc_commit(&S.tmem_full[acc]);            // accumulator complete -> epilogue
+                    if (PAIR) tc_commit_pair(&S.tmem_full[acc]); else tc_commit(&S.tmem_full[acc]);   // accumulator complete -> epilogue(s)
                 }
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: thread e = query row of the tile = TMEM lane =====
+        // ===== epilogue: thread e = query row of this CTA's half of the tile = TMEM lane =====
         const int e = threadIdx.x - 128;
         const int ew = warp - 4;                              // TMEM lane quarter 32*ew .. 32*ew+31
+        const int row_in_unit = (int)rank * BM + e;
+        const unsigned tmem_empty_leader0 = PAIR ? mapa_rank(smem_u32(&S.tmem_empty[0]), 0) : 0u;
+        const unsigned tmem_empty_leader1 = PAIR ? mapa_rank(smem_u32(&S.tmem_empty[1]), 0) : 0u;
         unsigned tile = 0;
-        for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+        for (int u = worker; u < nunits; u += nworkers) {
             const TcUnit U = units[u];
-            const bool valid_row = e < U.a_valid;
-            const float qn = valid_row ? qnorm[U.a_row0 + e] : 0.f;
+            const bool valid_row = row_in_unit < U.a_valid;
+            const float qn = valid_row ? qnorm[U.a_row0 + row_in_unit] : 0.f;
             // the KP best (approximate distance, row) pairs of this query row live in REGISTERS, ascending; an insertion is a
             // branch-free compare/select sweep (no shared-memory dependency chain, lanes of a warp insert at different ranks at
             // the same cost).  Rows of the tile past a_valid never insert (thr = -inf).
@@ -208,54 +275,83 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 mbar_wait(&S.tmem_full[acc], (tile >> 1) & 1);
                 tc_fence_after();
                 const int ncols = U.n_end - n0 < BN ? U.n_end - n0 : BN;
+                const unsigned trow = tmem_base + ((unsigned)(32 * ew) << 16) + acc * BN;
 #pragma unroll 1
                 for (int c = 0; c < ncols; c += 32) {
                     float v[32];
-                    tc_ld32(tmem_base + ((unsigned)(32 * ew) << 16) + acc * BN + c, v);
+                    tc_ld32_issue(trow + c, v);
+                    tc_ld32_wait(v);
+                    // fast path: 32 approximate distances and their minimum, branch-free (independent FADD/FFMA/FMNMX chains)
+                    float dmin = INFINITY;
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const float d = (qn + S.xn[acc][c + j]) - 2.0f * v[j];   // +inf for rows past the end
-                        if (d < thr) {
-                            const int id = n0 + c + j;
+                    for (int j4 = 0; j4 < 32; j4 += 4) {
+                        const float4 xn4 = *reinterpret_cast<const float4 *>(&S.xn[acc][c + j4]);   // +inf for rows past the end
+                        v[j4 + 0] = fmaf(-2.0f, v[j4 + 0], qn + xn4.x); v[j4 + 1] = fmaf(-2.0f, v[j4 + 1], qn + xn4.y);
+                        v[j4 + 2] = fmaf(-2.0f, v[j4 + 2], qn + xn4.z); v[j4 + 3] = fmaf(-2.0f, v[j4 + 3], qn + xn4.w);
+                        dmin = fminf(fminf(dmin, fminf(v[j4 + 0], v[j4 + 1])), fminf(v[j4 + 2], v[j4 + 3]));
+                    }
+                    // slow path (some element beats the list's worst entry): the insertion code exists ONCE -- the hits are walked
+                    // through a bit mask and fetched from a per-thread shared-memory column (dynamic register indexing is impossible,
+                    // and 32 unrolled copies of the sweep would not fit the instruction cache)
+                    if (dmin < thr) {
+                        unsigned hit = 0;
 #pragma unroll
-                            for (int p = KP - 1; p > 0; p--) {     // descending: ld[p - 1] is still the old value when read
-                                const bool shift = d < ld[p - 1];  // the old neighbour moves down to p
-                                const bool here = !shift && d < ld[p];
-                                li[p] = shift ? li[p - 1] : (here ? id : li[p]);
-                                ld[p] = shift ? ld[p - 1] : (here ? d : ld[p]);
+                        for (int j = 0; j < 32; j++) { S.scratch[j][e] = v[j]; hit |= (v[j] < thr) ? (1u << j) : 0u; }
+#pragma unroll 1
+                        while (hit) {
+                            const int j = __ffs((int)hit) - 1;
+                            hit &= hit - 1;
+                            const float d = S.scratch[j][e];
+                            if (d < thr) {   // thr may have dropped since the mask was taken
+                                const int id = n0 + c + j;
+#pragma unroll
+                                for (int p = KP - 1; p > 0; p--) {     // descending: ld[p - 1] is still the old value when read
+                                    const bool shift = d < ld[p - 1];  // the old neighbour moves down to p
+                                    const bool here = !shift && d < ld[p];
+                                    li[p] = shift ? li[p - 1] : (here ? id : li[p]);
+                                    ld[p] = shift ? ld[p - 1] : (here ? d : ld[p]);
+                                }
+                                if (d < ld[0]) { ld[0] = d; li[0] = id; }
+                                thr = ld[KP - 1];
                             }
-                            if (d < ld[0]) { ld[0] = d; li[0] = id; }
-                            thr = ld[KP - 1];
                         }
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&S.tmem_empty[acc]);   // 4 arrivals (one per epilogue warp) release the accumulator
+                if (lane == 0) {   // 4 (8 in a pair) arrivals, one per epilogue warp, release the accumulator to the MMA issuer
+                    if (PAIR) mbar_arrive_cluster(acc ? tmem_empty_leader1 : tmem_empty_leader0);
+                    else mbar_arrive(&S.tmem_empty[acc]);
+                }
             }
             if (valid_row) {
-                const size_t base = (size_t)(U.out_base + e) * KP;
+                const size_t base = (size_t)(U.out_base + row_in_unit) * KP;
 #pragma unroll
                 for (int j = 0; j < KP; j++) { part_d[base + j] = ld[j]; part_i[base + j] = li[j]; }   // empty slots: (+inf, -1)
-                part_thr[U.out_base + e] = thr;                  // every row of this unit that is NOT listed has d~ >= thr (+inf: list not full)
+                part_thr[U.out_base + row_in_unit] = thr;        // every row of this unit that is NOT listed has d~ >= thr (+inf: list not full)
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    if (PAIR) cluster_sync_all();   // the leader's MMAs read the peer's shared memory and signal its barriers: leave together
+    if (warp == 2) {
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
 }
 
 // ---- operand preparation -------------------------------------------------------------------------------------------------
 // mode 0: A' = [hi | hi | lo] (queries), mode 1: B' = [hi | lo | hi] (dataset).  One warp per row; pads K' with zeros.
 __global__ void split_kernel(const float *__restrict__ x, int64_t n, int dim, int kprime, int mode, __nv_bfloat16 *__restrict__ out,
-                             float *__restrict__ norm, float *__restrict__ absmax, int *__restrict__ nonfinite) {  // absmax optional
+                             float *__restrict__ norm, float *__restrict__ lonorm, int *__restrict__ nonfinite) {
+    // norm = |x|^2, lonorm = |x - hi|^2 (the part of x a hi-only product does not see); both accumulated in double
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t r = warp; r < n; r += nwarps) {
         const float *p = x + r * dim;
         __nv_bfloat16 *o = out + r * kprime;
-        double s = 0.0; float am = 0.f;
+        double s = 0.0, sl = 0.0;
         for (int j = lane; j < dim; j += 32) {
             const float v = p[j];
             const __nv_bfloat16 hi = __float2bfloat16_rn(v);
@@ -264,14 +360,13 @@ __global__ void split_kernel(const float *__restrict__ x, int64_t n, int dim, in
             o[dim + j] = mode == 0 ? hi : lo;
             o[2 * dim + j] = mode == 0 ? lo : hi;
             s += (double)v * (double)v;
-            am = fmaxf(am, fabsf(v));
+            const double l = (double)(v - __bfloat162float(hi));   // exact in fp32
+            sl += l * l;
             if (!(fabsf(v) <= 3.0e38f)) *nonfinite = 1;   // Inf / NaN: the caller falls back to the exact kernel
         }
         for (int j = 3 * dim + lane; j < kprime; j += 32) o[j] = __float2bfloat16_rn(0.f);
-        s = warp_sum_f64(s);
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, off));
-        if (lane == 0) { norm[r] = (float)s; if (absmax) absmax[r] = am; }
+        s = warp_sum_f64(s); sl = warp_sum_f64(sl);
+        if (lane == 0) { norm[r] = (float)s; lonorm[r] = (float)sl; }
     }
 }
 
@@ -392,6 +487,7 @@ __global__ void tc_max_kernel(const float *__restrict__ v, int64_t n, float *out
 template <int KRT>
 __global__ void tc_final_kernel(int nq, int k, int64_t n_rows, int dim, const int *__restrict__ cand, const float *__restrict__ exact,
                                 const float *__restrict__ t_excl, const float *__restrict__ qnorm, const float *__restrict__ xnorm_max,
+                                const float *__restrict__ qlonorm, const float *__restrict__ xlonorm_max, int one_term,
                                 const int64_t *__restrict__ id_map, int64_t key_base, int sqrt_out, int64_t *__restrict__ out_k,
                                 double *__restrict__ out_d, int *__restrict__ flags) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -419,7 +515,14 @@ __global__ void tc_final_kernel(int nq, int k, int64_t n_rows, int dim, const in
         const float qn = qnorm[q], xm = *xnorm_max;
         // |2 q.x error| <= 2 * (3 * 2^-16 [dropped lo.lo + bf16 residuals] + 144 * 2^-23 [fp32 accumulation over K'/16 MMA steps]) * |q||x|
         //               < 2^-12.8 |q||x|; 2^-12 is used.  Norm / final-formula rounding: 2^-21 (|q|^2 + |x|^2).
-        const float eps_tc = 2.44140625e-4f * sqrtf(qn * xm) + 4.76837158203125e-7f * (qn + xm);
+        float eps_tc = 2.44140625e-4f * sqrtf(qn * xm) + 4.76837158203125e-7f * (qn + xm);
+        if (one_term) {
+            // hi-only pass: q.x - qh.xh = qh.xL + qL.xh + qL.xL with qL = q - qh, xL = x - xh known exactly, so
+            // |error| <= |q||xL| + |qL||x| + 3 |qL||xL|  (|qh| <= |q| + |qL|); fp32 accumulation over dim/16 MMA steps < 2^-17 |q||x|
+            const float ql = qlonorm[q], xl = *xlonorm_max;
+            eps_tc = 2.002f * (sqrtf(qn * xl) + sqrtf(ql * xm) + 3.0f * sqrtf(ql * xl)) + 1.52587890625e-5f * sqrtf(qn * xm) +
+                     4.76837158203125e-7f * (qn + xm);
+        }
         const float eps_go = (float)dim * 1.1920928955078125e-7f * t;                                  // dim * 2^-23 * distance scale
         proven = d[k - 1] + eps_tc + eps_go < t;
     }
@@ -461,10 +564,15 @@ __global__ void scatter_results_kernel(const int64_t *__restrict__ sk, const dou
 namespace mob {
 
 int g_search_mode = 0;          // 0 = auto, 1 = exact kernel only, 2 = force the tensor-core path (MoB200_SetTuning("search_mode"))
+int g_tc_ladder_mode = 0;        // 0 = auto (one-term level first unless it has been failing), 1 = never, 2 = always (MoB200_SetTuning("tc_ladder"))
+int g_one_term_skip = 0;         // searches left before the one-term level is tried again
+int g_last_tc_kused = 0;         // K elements per (query, row) pair the timed candidate pass multiplied (dim = one term, 3*dim = three)
+int g_tc_range_mb = 0;         // L2 budget of one row range of the brute-force candidate pass, MB (0 = ignore the L2)
+int g_tc_pair_mode = 0;          // 0 = auto, 1 = single-CTA units only, 2 = CTA pairs wherever the brute-force path runs (MoB200_SetTuning("tc_pair"))
 int g_last_tc_refined = -1;
 int g_last_tc_fallbacks = -1;   // queries of the last tensor-core search that failed the completeness proof and were re-run exactly
 
-struct TcOperand { __nv_bfloat16 *bf = nullptr; float *norm = nullptr; int kprime = 0; };
+struct TcOperand { __nv_bfloat16 *bf = nullptr; float *norm = nullptr; float *lonorm = nullptr; int kprime = 0; };   // norm = |x|^2, lonorm = |x - bf16(x)|^2 per row
 
 // datasets split once by MoB200_SearchPrepare (index load); looked up by (pointer, rows, dim)
 struct PreparedOperand { const float *x; int64_t n; int dim; int device; TcOperand op; };
@@ -486,19 +594,21 @@ static int tc_prepare(ThreadCtx &t, const float *x, int64_t n, int dim, int mode
     op.kprime = ((3 * dim + BK - 1) / BK) * BK;
     op.bf = (__nv_bfloat16 *)arena_alloc(t, (size_t)(n > 0 ? n : 1) * op.kprime * 2 + 1024);
     op.norm = (float *)arena_alloc(t, (size_t)(n > 0 ? n : 1) * 4);
-    if (!op.bf || !op.norm) return MO_RC_INTERNAL_ERROR;
-    if (n > 0) { split_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(x, n, dim, op.kprime, mode, op.bf, op.norm, nullptr, dnonfinite); MOB_LAUNCH_CHECK(); }
+    op.lonorm = (float *)arena_alloc(t, (size_t)(n > 0 ? n : 1) * 4);
+    if (!op.bf || !op.norm || !op.lonorm) return MO_RC_INTERNAL_ERROR;
+    if (n > 0) { split_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(x, n, dim, op.kprime, mode, op.bf, op.norm, op.lonorm, dnonfinite); MOB_LAUNCH_CHECK(); }
     c.x = x; c.n = n; c.dim = dim; c.mode = mode; c.epoch = t.arena_epoch; c.t = &t; c.op = op;
     return MO_RC_SUCCESS;
 }
 
 // run the candidate kernel over `units`; lists are written at unit.out_base + row (nlists lists in total, pre-initialised empty)
 static int tc_run_units(ThreadCtx &t, const TcOperand &A, int64_t a_rows, const TcOperand &B, int64_t b_rows, const std::vector<TcUnit> &units,
-                        int64_t nlists, float **part_d, int **part_i, float **part_thr, bool timed = true) {
+                        int64_t nlists, float **part_d, int **part_i, float **part_thr, bool timed = true, bool pair = false, int nkb = 0) {
+    if (nkb <= 0 || nkb > A.kprime / BK) nkb = A.kprime / BK;   // 0 = the whole K' (three-term product)
     CUtensorMap map_a, map_b;
     int rc = make_map(&map_a, A.bf, (uint64_t)a_rows, (uint64_t)A.kprime, BM);
     if (rc) return rc;
-    rc = make_map(&map_b, B.bf, (uint64_t)b_rows, (uint64_t)B.kprime, BN);
+    rc = make_map(&map_b, B.bf, (uint64_t)b_rows, (uint64_t)B.kprime, pair ? TcCfg<true>::kBRows : TcCfg<false>::kBRows);
     if (rc) return rc;
     TcUnit *dunits = (TcUnit *)arena_alloc(t, sizeof(TcUnit) * (units.size() ? units.size() : 1));
     *part_d = (float *)arena_alloc(t, sizeof(float) * (size_t)nlists * KP);
@@ -511,12 +621,30 @@ static int tc_run_units(ThreadCtx &t, const TcOperand &A, int64_t a_rows, const 
     MOB_CUDA_TRY(cudaMemcpyAsync(dunits, units.data(), sizeof(TcUnit) * units.size(), cudaMemcpyHostToDevice, t.stream));
     MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));
     static bool attr = false;
-    const size_t smem = sizeof(TcSmem) + 1024;
-    if (!attr) { MOB_CUDA_TRY(cudaFuncSetAttribute(tc_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-    int grid = num_sms();
-    if (grid > (int)units.size()) grid = (int)units.size();
-    if (timed) { t.kev_prio = 2; cudaEventRecord(t.kev0, t.stream); }   // MoB200_LastKernelMs reports the first (whole-list) pass, not the refine pass
-    tc_candidates_kernel<<<grid, kTcThreads, smem, t.stream>>>(map_a, map_b, dunits, (int)units.size(), A.kprime, A.norm, B.norm, *part_d, *part_i, *part_thr);
+    const size_t smem1 = sizeof(TcSmemT<false>) + 1024, smem2 = sizeof(TcSmemT<true>) + 1024;
+    if (!attr) {
+        MOB_CUDA_TRY(cudaFuncSetAttribute(tc_candidates_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        MOB_CUDA_TRY(cudaFuncSetAttribute(tc_candidates_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        attr = true;
+    }
+    const int nunits = (int)units.size();
+    if (timed) { t.kev_prio = 2; g_last_tc_kused = nkb * BK; cudaEventRecord(t.kev0, t.stream); }   // MoB200_LastKernelMs reports the first (whole-list) pass, not the refine pass
+    if (!pair) {
+        int grid = num_sms();
+        if (grid > nunits) grid = nunits;
+        tc_candidates_kernel<false><<<grid, kTcThreads, smem1, t.stream>>>(map_a, map_b, dunits, nunits, nkb, A.norm, B.norm, *part_d, *part_i, *part_thr);
+    } else {
+        // clusters of two CTAs (one TPC each): one persistent pair per two SMs
+        int pairs = num_sms() / 2;
+        if (pairs > nunits) pairs = nunits;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * pairs)); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem2; cfg.stream = t.stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        const float *an = A.norm, *bn = B.norm; int kp = nkb;
+        MOB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_candidates_kernel<true>, map_a, map_b, (const TcUnit *)dunits, nunits, kp, an, bn, *part_d, *part_i, *part_thr));
+    }
     if (timed) cudaEventRecord(t.kev1, t.stream);
     MOB_LAUNCH_CHECK();
     return MO_RC_SUCCESS;
@@ -525,24 +653,27 @@ static int tc_run_units(ThreadCtx &t, const TcOperand &A, int64_t a_rows, const 
 // merge approximate lists -> exact re-score -> final order + proof; returns the queries whose proof failed
 static int tc_finish(ThreadCtx &t, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq, int k, int R, const int *pos_map,
                      int pos_cols, long long pos_stride, const float *part_d, const int *part_i, const float *part_thr, const float *qnorm, const float *xnorm,
-                     const int64_t *id_map, int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d, std::vector<int> &redo) {
-    const int kr = k > KP ? KR_WIDE : KR;
+                     const int64_t *id_map, int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d, std::vector<int> &redo,
+                     const float *qlonorm = nullptr, const float *xlonorm = nullptr) {   // both given: the candidate pass was hi-only (one term)
+    const int one_term = qlonorm && xlonorm ? 1 : 0;
+    const int kr = (k > KP || one_term) ? KR_WIDE : KR;   // a looser approximation needs more exact re-scores to prove the top k
     int *cand = (int *)arena_alloc(t, sizeof(int) * (size_t)nq * kr);
     float *exact = (float *)arena_alloc(t, sizeof(float) * (size_t)nq * kr);
     float *t_excl = (float *)arena_alloc(t, sizeof(float) * (size_t)nq + 16);
     int *flags = (int *)arena_alloc(t, sizeof(int) * (size_t)nq);
     if (!cand || !exact || !t_excl || !flags) return MO_RC_INTERNAL_ERROR;
-    float *xmax = t_excl + nq;
-    MOB_CUDA_TRY(cudaMemsetAsync(xmax, 0, 4, t.stream));
+    float *xmax = t_excl + nq, *xlomax = xmax + 1;
+    MOB_CUDA_TRY(cudaMemsetAsync(xmax, 0, 8, t.stream));
     tc_max_kernel<<<num_sms() * 2, 256, 0, t.stream>>>(xnorm, n, xmax);
     MOB_LAUNCH_CHECK();
+    if (one_term) { tc_max_kernel<<<num_sms() * 2, 256, 0, t.stream>>>(xlonorm, n, xlomax); MOB_LAUNCH_CHECK(); }
     if (R > kMaxMergeLists) { set_error("tc search: %d candidate lists per query exceed the merge limit %d", R, kMaxMergeLists); return MO_RC_INTERNAL_ERROR; }
     tc_merge_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, t.stream>>>((int)nq, R, part_d, part_i, part_thr, pos_map, pos_cols, pos_stride, kr, cand, t_excl);
     MOB_LAUNCH_CHECK();
     tc_rescore_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(ddata, dq, dim, (int)nq, kr, cand, exact);
     MOB_LAUNCH_CHECK();
-    if (kr == KR) tc_final_kernel<KR><<<(unsigned)((nq + 127) / 128), 128, 0, t.stream>>>((int)nq, k, n, dim, cand, exact, t_excl, qnorm, xmax, id_map, key_base, sqrt_out, out_k, out_d, flags);
-    else tc_final_kernel<KR_WIDE><<<(unsigned)((nq + 127) / 128), 128, 0, t.stream>>>((int)nq, k, n, dim, cand, exact, t_excl, qnorm, xmax, id_map, key_base, sqrt_out, out_k, out_d, flags);
+    if (kr == KR) tc_final_kernel<KR><<<(unsigned)((nq + 127) / 128), 128, 0, t.stream>>>((int)nq, k, n, dim, cand, exact, t_excl, qnorm, xmax, qlonorm, xlomax, one_term, id_map, key_base, sqrt_out, out_k, out_d, flags);
+    else tc_final_kernel<KR_WIDE><<<(unsigned)((nq + 127) / 128), 128, 0, t.stream>>>((int)nq, k, n, dim, cand, exact, t_excl, qnorm, xmax, qlonorm, xlomax, one_term, id_map, key_base, sqrt_out, out_k, out_d, flags);
     MOB_LAUNCH_CHECK();
     std::vector<int> hflags((size_t)nq);
     MOB_CUDA_TRY(cudaMemcpyAsync(hflags.data(), flags, sizeof(int) * (size_t)nq, cudaMemcpyDeviceToHost, t.stream));
@@ -550,6 +681,34 @@ static int tc_finish(ThreadCtx &t, const float *ddata, int64_t n, int dim, const
     redo.clear();
     for (int64_t q = 0; q < nq; q++) if (hflags[(size_t)q]) redo.push_back((int)q);
     return MO_RC_SUCCESS;
+}
+
+// Number of row ranges for a brute-force search: units (range r, query tile m) are dealt round-robin to `workers` persistent
+// CTAs, so the makespan is the heaviest worker's tile count.  Pick the R in [rmin, rcap] with the smallest makespan;
+// every unit also pays a fixed cost (list init + write-out, more insertions while the list is young) counted as one tile.
+// rmin comes from the L2: the query tiles of a range run on different SMs at about the same time, and only a range that
+// stays L2-resident while they sweep it is read from HBM once.
+static int plan_ranges(int64_t ntiles, int mt, int workers, int rmin, int rcap) {
+    int best = 1; double best_cost = 1e300;
+    const int rmax = (int)(ntiles < rcap ? ntiles : rcap);
+    if (rmin > rmax) rmin = rmax;
+    if (rmin < 1) rmin = 1;
+    std::vector<double> load((size_t)workers);
+    for (int R = rmin; R <= rmax; R++) {
+        const int64_t per = (ntiles + R - 1) / R;
+        const int reff = (int)((ntiles + per - 1) / per);
+        if (reff != R) continue;   // same partition as a smaller R
+        std::fill(load.begin(), load.end(), 0.0);
+        size_t u = 0;
+        for (int r = 0; r < R; r++) {
+            const double tiles = (double)((r + 1) * per <= ntiles ? per : ntiles - r * per) + 1.0;
+            for (int m = 0; m < mt; m++, u++) load[u % (size_t)workers] += tiles;
+        }
+        double cost = 0;
+        for (double l : load) cost = l > cost ? l : cost;
+        if (cost < best_cost * 0.999) { best_cost = cost; best = R; }
+    }
+    return best;
 }
 
 bool tc_search_applicable(int64_t n, int dim, int64_t nq, int k, int metric) {
@@ -579,8 +738,15 @@ bool tc_ivf_applicable(int64_t n, int dim, int64_t nq, int k, int nprobe, int me
 }
 
 // Brute-force top-k through the tensor-core candidate pass; results are the exact answer (see file header).
-int bruteforce_topk_tc_device(ThreadCtx &t, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq, int k,
-                              int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d, bool record_stats) {
+// A precision ladder: level 0 runs only the first dim columns of K' (the hi.hi product, a third of the flop) and proves what it
+// can with the looser one-term error bound; level 1 re-runs the unproven queries over the whole K' (three-term product); what is
+// still unproven goes to the exact kernel.  Every level answers its queries exactly or hands them down.
+static int bf_tc_level(ThreadCtx &t, int level, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq, int k,
+                       int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d, bool record_stats, bool timed) {
+    if (level >= 2) {
+        if (record_stats) g_last_tc_fallbacks = (int)nq;
+        return bruteforce_topk_device(t, ddata, n, dim, dq, nq, k, MO_METRIC_L2SQ, key_base, sqrt_out, out_k, out_d);
+    }
     int *dnonfinite = (int *)arena_alloc(t, 4);
     if (!dnonfinite) return MO_RC_INTERNAL_ERROR;
     MOB_CUDA_TRY(cudaMemsetAsync(dnonfinite, 0, 4, t.stream));
@@ -591,17 +757,25 @@ int bruteforce_topk_tc_device(ThreadCtx &t, const float *ddata, int64_t n, int d
     int hnonfinite = 0;
     rc = read_back(t, &hnonfinite, dnonfinite, 4);
     if (rc) return rc;
-    if (hnonfinite) {   // the error bound of the tensor-core pass does not apply to Inf/NaN inputs
-        if (record_stats) g_last_tc_fallbacks = (int)nq;
-        return bruteforce_topk_device(t, ddata, n, dim, dq, nq, k, MO_METRIC_L2SQ, key_base, sqrt_out, out_k, out_d);
-    }
+    if (hnonfinite)   // the error bound of the tensor-core pass does not apply to Inf/NaN inputs
+        return bf_tc_level(t, 2, ddata, n, dim, dq, nq, k, key_base, sqrt_out, out_k, out_d, record_stats, false);
+    const bool one_term = level == 0;
+    const int nkb = one_term ? (dim + BK - 1) / BK : A.kprime / BK;
     // work units: (query tile, row range); ranges sized so that units ~ a whole number of waves over the SMs
-    const int mt = (int)((nq + BM - 1) / BM);
+    // enough queries to fill 256-row tiles: CTA pairs (cta_group::2) stage 1.5x fewer bytes per flop
+    const bool pair = g_tc_pair_mode == 2 || (g_tc_pair_mode == 0 && nq >= 1024);
+    const int tile_m = pair ? TcCfg<true>::kTileM : TcCfg<false>::kTileM;
+    const int mt = (int)((nq + tile_m - 1) / tile_m);
     const int64_t ntiles = (n + BN - 1) / BN;
-    int R = (int)((8ll * num_sms() + mt - 1) / mt);
-    if (R > ntiles) R = (int)ntiles;
-    if (R > 64) R = 64;
-    if (R < 1) R = 1;
+    const int workers = pair ? num_sms() / 2 : num_sms();
+    int rmin = 1;
+    if (g_tc_range_mb > 0) {   // experiment knob: cap the bytes of one row range (L2 residency)
+        const int64_t tile_bytes = (int64_t)BN * nkb * BK * 2;
+        int64_t tiles_fit = ((int64_t)g_tc_range_mb << 20) / tile_bytes;
+        if (tiles_fit < 4) tiles_fit = 4;
+        rmin = (int)((ntiles + tiles_fit - 1) / tiles_fit);
+    }
+    int R = plan_ranges(ntiles, mt, workers, rmin, rmin > 64 ? kMaxMergeLists : 64);
     int64_t range_rows = (ntiles + R - 1) / R * BN;
     if (k > KP) {   // wide mode: R * KP candidates must comfortably exceed k -> short ranges (the MMA tile is masked beyond n_end)
         range_rows = ((n + 63) / 64 + 127) / 128 * 128;
@@ -611,35 +785,50 @@ int bruteforce_topk_tc_device(ThreadCtx &t, const float *ddata, int64_t n, int d
     std::vector<TcUnit> units;
     for (int r = 0; r < R; r++)
         for (int m = 0; m < mt; m++) {
-            TcUnit u; u.a_row0 = m * BM; u.a_valid = (int)(nq - u.a_row0 < BM ? nq - u.a_row0 : BM);
+            TcUnit u; u.a_row0 = m * tile_m; u.a_valid = (int)(nq - u.a_row0 < tile_m ? nq - u.a_row0 : tile_m);
             u.n_begin = (int)(r * range_rows); u.n_end = (int)((r + 1) * range_rows < n ? (r + 1) * range_rows : n);
             u.out_base = (long long)r * nq + u.a_row0;
             if (u.n_begin < u.n_end) units.push_back(u);
         }
     float *part_d, *part_thr; int *part_i;
-    rc = tc_run_units(t, A, nq, B, n, units, (int64_t)R * nq, &part_d, &part_i, &part_thr, record_stats);
+    rc = tc_run_units(t, A, nq, B, n, units, (int64_t)R * nq, &part_d, &part_i, &part_thr, timed, pair, nkb);
     if (rc) return rc;
     std::vector<int> redo;
-    rc = tc_finish(t, ddata, n, dim, dq, nq, k, R, nullptr, 0, 0, part_d, part_i, part_thr, A.norm, B.norm, nullptr, key_base, sqrt_out, out_k, out_d, redo);
+    rc = tc_finish(t, ddata, n, dim, dq, nq, k, R, nullptr, 0, 0, part_d, part_i, part_thr, A.norm, B.norm, nullptr, key_base, sqrt_out, out_k, out_d, redo,
+                   one_term ? A.lonorm : nullptr, one_term ? B.lonorm : nullptr);
     if (rc) return rc;
-    if (record_stats) g_last_tc_fallbacks = (int)redo.size();
-    if (!redo.empty()) {   // queries whose completeness could not be proven: exact kernel, results scattered back
-        const int m = (int)redo.size();
-        int *didx = (int *)arena_alloc(t, sizeof(int) * (size_t)m);
-        float *sub = (float *)arena_alloc(t, sizeof(float) * (size_t)m * dim);
-        int64_t *sk = (int64_t *)arena_alloc(t, sizeof(int64_t) * (size_t)m * k);
-        double *sd = (double *)arena_alloc(t, sizeof(double) * (size_t)m * k);
-        if (!didx || !sub || !sk || !sd) return MO_RC_INTERNAL_ERROR;
-        MOB_CUDA_TRY(cudaMemcpyAsync(didx, redo.data(), sizeof(int) * (size_t)m, cudaMemcpyHostToDevice, t.stream));
-        MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));
-        gather_rows_kernel<<<num_sms() * 4, 256, 0, t.stream>>>(dq, didx, m, dim, sub);
-        MOB_LAUNCH_CHECK();
-        rc = bruteforce_topk_device(t, ddata, n, dim, sub, m, k, MO_METRIC_L2SQ, key_base, sqrt_out, sk, sd);
-        if (rc) return rc;
-        scatter_results_kernel<<<(unsigned)((m * k + 255) / 256), 256, 0, t.stream>>>(sk, sd, didx, m, k, out_k, out_d);
-        MOB_LAUNCH_CHECK();
+    if (record_stats && level == 0) {
+        g_last_tc_refined = (int)redo.size();
+        // a dataset whose norms dwarf its neighbour distances defeats the one-term bound: stop trying for a while
+        if (nq >= 64 && (int64_t)redo.size() * 5 > nq * 2) g_one_term_skip = 16;
     }
+    if (redo.empty()) return MO_RC_SUCCESS;
+    // queries whose completeness could not be proven: next level, results scattered back
+    const int m = (int)redo.size();
+    int *didx = (int *)arena_alloc(t, sizeof(int) * (size_t)m);
+    float *sub = (float *)arena_alloc(t, sizeof(float) * (size_t)m * dim);
+    int64_t *sk = (int64_t *)arena_alloc(t, sizeof(int64_t) * (size_t)m * k);
+    double *sd = (double *)arena_alloc(t, sizeof(double) * (size_t)m * k);
+    if (!didx || !sub || !sk || !sd) return MO_RC_INTERNAL_ERROR;
+    MOB_CUDA_TRY(cudaMemcpyAsync(didx, redo.data(), sizeof(int) * (size_t)m, cudaMemcpyHostToDevice, t.stream));
+    MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));
+    gather_rows_kernel<<<num_sms() * 4, 256, 0, t.stream>>>(dq, didx, m, dim, sub);
+    MOB_LAUNCH_CHECK();
+    rc = bf_tc_level(t, level + 1, ddata, n, dim, sub, m, k, key_base, sqrt_out, sk, sd, record_stats, false);
+    if (rc) return rc;
+    scatter_results_kernel<<<(unsigned)((m * k + 255) / 256), 256, 0, t.stream>>>(sk, sd, didx, m, k, out_k, out_d);
+    MOB_LAUNCH_CHECK();
     return MO_RC_SUCCESS;
+}
+
+int bruteforce_topk_tc_device(ThreadCtx &t, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq, int k,
+                              int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d, bool record_stats) {
+    // the one-term level needs k <= KP (its proof re-scores 64 candidates) and is skipped while it has recently been failing
+    bool ladder = g_tc_ladder_mode == 2 || (g_tc_ladder_mode == 0 && g_one_term_skip == 0);
+    if (g_tc_ladder_mode == 0 && g_one_term_skip > 0 && record_stats) g_one_term_skip--;
+    if (k > KP) ladder = false;
+    if (record_stats) { g_last_tc_fallbacks = 0; g_last_tc_refined = -1; }
+    return bf_tc_level(t, ladder ? 0 : 1, ddata, n, dim, dq, nq, k, key_base, sqrt_out, out_k, out_d, record_stats, record_stats);
 }
 
 // IVF list scan on the tensor cores: the queries probing a list are gathered (as split bf16 rows) next to each other, so
@@ -717,13 +906,14 @@ int32_t MoB200_SearchPrepare(const void *data, uint64_t n, int64_t dim) {
     PreparedOperand e; e.x = (const float *)data; e.n = (int64_t)n; e.dim = (int)dim; e.device = 0;
     e.op.kprime = ((3 * (int)dim + BK - 1) / BK) * BK;
     MOB_CUDA_TRY(cudaMalloc((void **)&e.op.bf, (size_t)n * e.op.kprime * 2 + 1024));
-    if (cudaMalloc((void **)&e.op.norm, (size_t)n * 4) != cudaSuccess) { cudaFree(e.op.bf); set_error("SearchPrepare: out of device memory"); return MO_RC_INTERNAL_ERROR; }
+    if (cudaMalloc((void **)&e.op.norm, (size_t)n * 8) != cudaSuccess) { cudaFree(e.op.bf); set_error("SearchPrepare: out of device memory"); return MO_RC_INTERNAL_ERROR; }
+    e.op.lonorm = e.op.norm + n;
     int *dnonfinite = (int *)arena_alloc(t, 4);
     int hnonfinite = 1;
     int rc = dnonfinite ? MO_RC_SUCCESS : MO_RC_INTERNAL_ERROR;
     if (!rc && cudaMemsetAsync(dnonfinite, 0, 4, t.stream) != cudaSuccess) rc = MO_RC_INTERNAL_ERROR;
     if (!rc) {
-        split_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(e.x, e.n, e.dim, e.op.kprime, 1, e.op.bf, e.op.norm, nullptr, dnonfinite);
+        split_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(e.x, e.n, e.dim, e.op.kprime, 1, e.op.bf, e.op.norm, e.op.lonorm, dnonfinite);
         g_launches++;
         if (cudaGetLastError() != cudaSuccess) rc = MO_RC_INTERNAL_ERROR;
     }

@@ -120,7 +120,9 @@ def test_ivf_empty_lists_and_small_index(gpu):
 
 @pytest.mark.parametrize("n,dim,nq,k", [(20_000, 128, 300, 10), (9_000, 768, 257, 10), (5_000, 100, 130, 5), (70_000, 64, 1000, 16), (300, 32, 40, 3),
                                         (20_000, 96, 200, 32), (1_024, 64, 500, 25)])   # k > 16: the wide mode of centroid probes
-def test_tensor_core_candidate_path_is_exact(gpu, n, dim, nq, k):
+@pytest.mark.parametrize("pair", [1, 2])   # 1: single-CTA units (cta_group::1), 2: CTA pairs (cta_group::2, M = 256)
+@pytest.mark.parametrize("ladder", [1, 2])  # 1: three-term product only, 2: hi-only level first, then three-term for the unproven
+def test_tensor_core_candidate_path_is_exact(gpu, n, dim, nq, k, pair, ladder):
     """tcgen05 candidate generation + exact re-scoring + completeness proof (csrc/tcsearch.cu): the results must be the exact
     answer (bit-exact distances), and the tensor path itself must be doing the work (few proof failures -> few fallbacks)."""
     ds = datagen.vectors_f32(40, 0, n, dim); qs = datagen.vectors_f32(41, 0, nq, dim)
@@ -128,12 +130,16 @@ def test_tensor_core_candidate_path_is_exact(gpu, n, dim, nq, k):
     okeys, odists = O.bruteforce(ds, qs, k)
     try:
         gpu.MoB200_SetTuning(b"search_mode", 2)
+        gpu.MoB200_SetTuning(b"tc_pair", pair)
+        gpu.MoB200_SetTuning(b"tc_ladder", ladder)
         idx = ops.BruteForceIndex(ds, dim)
         keys, dists = idx.search(qs, k)
         fallbacks = gpu.MoB200_SetTuning(b"get_tc_fallbacks", 0)
         idx.destroy()
     finally:
         gpu.MoB200_SetTuning(b"search_mode", 0)
+        gpu.MoB200_SetTuning(b"tc_pair", 0)
+        gpu.MoB200_SetTuning(b"tc_ladder", 0)
     _check_topk(keys, dists, okeys, odists, nq, k)
     assert dists.reshape(nq, k)[:7, 0].tolist() == [0.0] * 7
     assert 0 <= fallbacks <= max(2, nq // 20), fallbacks
