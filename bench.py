@@ -131,6 +131,27 @@ def cpu_reference(workload, sample_rows, steps, warmup, threads, dataset=None, q
             O.bruteforce(ds, qs, 10, 0, threads)
         dt = time.perf_counter() - t0
         return nq * steps / dt, dt / steps
+    if workload == "ivf":
+        # IvfflatSearchIndex.Search (findCentroids + scan of the nprobe probed lists + heap) on a full per-GPU shard: nlist 1024,
+        # nprobe 32, top-10; `queries` per step spread over the host threads.  dataset = (entries, list id per entry, centroids)
+        dim, nlist, nprobe, k = 768, 1024, 32, 10
+        if dataset is None:
+            centers = datagen.vectors_f32(30, 0, nlist, dim) * 4
+            ents = datagen.vectors_f32(31, 0, sample_rows, dim, centers, 1.0)
+            assign = datagen.vector_components(31, 0, sample_rows, nlist)   # the generating component: a valid list assignment
+        else:
+            ents, assign, centers = dataset
+        qs = queries if queries is not None else datagen.vectors_f32(32, 0, 8 * threads, dim, centers, 1.0)
+        nq = qs.shape[0]
+        keys = np.zeros(nq * k, dtype=np.int64); dists = np.zeros(nq * k)
+        run = lambda m: O.go().og_ivf_search_f32(O.p(ents), O.p(assign), ents.shape[0], dim, O.p(centers), nlist, O.p(qs), m, nprobe, k, 0, 0, threads, O.p(keys), O.p(dists))
+        for _ in range(warmup):
+            run(max(1, nq // 4))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            run(nq)
+        dt = time.perf_counter() - t0
+        return nq * steps / dt, dt / steps
     if workload == "q6":
         cols = datagen.lineitem(10, 0, sample_rows)
         P = datagen.q6_params()
@@ -162,10 +183,21 @@ def run_reference_arm(args):
     sample = min(wl["rows"], 1 << 25)
     steps = max(1, args.steps)
     warmup = max(1, min(args.warmup, 2))
-    if args.workload == "bruteforce":
+    if args.workload in ("bruteforce", "ivf"):
         steps, warmup = min(steps, 3), 1
+    if args.workload == "ivf":
+        sample = 1_250_000   # one GPU's shard of the 10 M-row index
     value, sec_per_step = cpu_reference(args.workload, sample, steps, warmup, threads)
-    unit = "queries/s" if args.workload == "bruteforce" else "rows/s"
+    unit = "queries/s" if args.workload in ("bruteforce", "ivf") else "rows/s"
+    if args.workload == "ivf":
+        line = {"impl": "reference", "metric": wl["metric"], "value": value, "unit": unit, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+                "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": wl["name"], "rows": sample, "queries_per_step": 8 * threads},
+                "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": "port",
+                                 "sample": "1.25 M x 768 shard (nlist 1024, nprobe 32, top-10), %d queries per step over %d host threads; oracle/oracle_go.c og_ivf_search_f32 (IvfflatSearchIndex.Search)" % (8 * threads, threads)},
+                "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
     if args.workload == "bruteforce":
         line = {"impl": "reference", "metric": wl["metric"], "value": value, "unit": unit, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
                 "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -476,6 +508,15 @@ def main():
         v, sec = cpu_reference("bruteforce", n, 1, 1, threads, hds, hqs)
         cpu_baseline = {"value": v, "unit": "queries/s", "cores": threads, "kind": "port",
                         "sample": "full dataset, %d queries (one per host thread), 1 pass after a quarter-size warm-up; oracle/oracle_go.c GoBruteForceIndex.Search" % hqs.shape[0]}
+    if not args.no_cpu and world == 1 and args.workload == "ivf":
+        threads = os.cpu_count() or 1
+        ents = ivf.d_data.to_numpy(np.float32).reshape(ivf.n, 768)                  # list-ordered entries
+        assign = np.repeat(np.arange(1024, dtype=np.int32), np.diff(ivf.offsets))     # their list ids
+        cents = ivf.d_cent.to_numpy(np.float32).reshape(1024, 768)
+        hqs = bufs["queries"].to_numpy(np.float32).reshape(-1, 768)[:8 * threads]
+        v, sec = cpu_reference("ivf", ivf.n, 1, 1, threads, (ents, assign, cents), hqs)
+        cpu_baseline = {"value": v, "unit": "queries/s", "cores": threads, "kind": "port",
+                        "sample": "the GPU's own shard (%d x 768, nlist 1024, nprobe 32), %d queries over %d host threads, 1 pass after a quarter-size warm-up; oracle/oracle_go.c og_ivf_search_f32" % (ivf.n, hqs.shape[0], threads)}
     if not args.no_cpu and world == 1 and args.workload in ("q6", "q1", "sum"):
         threads = os.cpu_count() or 1
         sample = min(n, 1 << 25)

@@ -80,6 +80,12 @@ def vectors_f32(seed, row0, n, dim, centers=None, sigma=1.0):
     return out
 
 
+def vector_components(seed, row0, n, ncenters):
+    """mixture component every row of vectors_f32(seed, row0, n, dim, centers) was drawn from"""
+    r = np.arange(row0, row0 + n, dtype=np.uint64)
+    return (hash3(seed, 7, r) % np.uint64(ncenters)).astype(np.int32)
+
+
 def q6_params():
     """(date_lo, date_hi, disc_lo, disc_hi, qty_hi) with the constants folded in float64 like q6.sql:58-61."""
     return DATE_1994_01_01, DATE_1995_01_01, 0.03 - 0.01, 0.03 + 0.01, 24.0

@@ -15,14 +15,27 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active",
         "l1tex__t_bytes_pipe_lsu_mem_global_op_ld.sum", "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "smsp__cycles_active.avg", "sm__cycles_elapsed.max", "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_issued.avg.pct_of_peak_sustained_active",
-        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed_pipe_lsu.sum"]
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed_pipe_lsu.sum",
+        "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes.sum",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.avg.per_second", "launch__cluster_size", "launch__shared_mem_per_block_dynamic"]
 
 
 def raw(rep):
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
-    return [dict(zip(hdr, r)) for r in rows[2:]], dict(zip(hdr, units))
+    # some section metrics carry a "UNIT.Section." prefix (e.g. TPC.TriageCompute.sm__pipe_tensor...): index them by bare name too
+    bare = [h.split(".", 2)[2] if h.count(".") >= 2 and h.split(".")[0].isupper() else h for h in hdr]
+    recs = []
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        for b, v in zip(bare, r):
+            d.setdefault(b, v)
+        recs.append(d)
+    u = dict(zip(hdr, units))
+    for b, v in zip(bare, units):
+        u.setdefault(b, v)
+    return recs, u
 
 
 def stalls(rep, top=12):
@@ -59,11 +72,11 @@ def main():
     os.makedirs(out_dir, exist_ok=True)
     src = os.path.join(ROOT, "gpurun_out")
     prefix = sys.argv[1] if len(sys.argv) > 1 else "r01"
-    algo = {"q6": 28.0 * 600_037_902, "q1": 38.0 * 600_037_902, "agg": None, "bf": None}
+    algo = {"q6": 28.0 * 600_037_902, "q1": 38.0 * 600_037_902}
     lines = ["# ncu evidence, %s" % prefix, "",
              "Captured with `tools/profile_%s.sh` under gpurun (`ncu --set full --clock-control none --import-source on`); the `.ncu-rep`" % prefix,
              "files stay in gpurun_out/ (scratch).  Durations under ncu are cold-cache and serialised: compare shares, not absolutes.", ""]
-    for name in ("q6", "q1", "agg", "bf"):
+    for name in ("q6", "q1", "agg", "bf", "tc_bruteforce", "tc_ivf"):
         rep = os.path.join(src, "%s_%s.ncu-rep" % (prefix, name))
         if not os.path.exists(rep):
             continue
@@ -87,12 +100,14 @@ def main():
                 lines += ["", "Top sampled instructions (warp-stall samples):", "", "| samples | % | SASS |", "|---|---|---|"]
                 lines += ["| %d | %.1f | `%s` |" % (n, pct, s_[:90]) for n, pct, s_ in st]
             lines.append("")
-    for name in ("q6", "q1"):
+    for name in ("q6", "q1", "bruteforce", "ivf"):
         p = os.path.join(src, "%s_launches_%s.csv" % (prefix, name))
         if os.path.exists(p):
             agg = launches(p)
             tot = sum(v[1] for v in agg.values()) or 1
-            lines += ["## launch list: `python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu%s`" % ("" if name == "q6" else " --workload q1"), "",
+            cmd = {"q6": "--steps 2 --warmup 3", "q1": "--steps 2 --warmup 3 --workload q1", "bruteforce": "--steps 1 --warmup 3 --workload bruteforce",
+                   "ivf": "--steps 1 --warmup 3 --workload ivf --rows 1250000"}[name]
+            lines += ["## launch list: `python bench.py %s --no-e2e --no-cpu`" % cmd, "",
                       "| kernel | launches | total ns | share |", "|---|---|---|---|"]
             for k, (c, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
                 lines.append("| `%s` | %d | %.0f | %.1f %% |" % (k, c, v, 100 * v / tot))
