@@ -262,6 +262,9 @@ int32_t MoB200_GatherRowsF32(float *dst, const float *src, const int64_t *idx, u
  * MO_XCALL_BRUTEFORCE_TOPK_F32 / MO_XCALL_IVF_TOPK_F32 once, instead of once per search; the rows must not change until
  * SearchRelease(data).  Optional: searches return identical results with or without it.  Costs 6*dim bytes of HBM per row. */
 int32_t MoB200_SearchPrepare(const void *data, uint64_t n, int64_t dim);
+/* IVF-flat: the list-ordered entries are split as residuals against their list's centroid (centroids [nlist][dim] float32,
+ * offsets [nlist + 1] int64, device pointers; the same buffers MO_XCALL_IVF_TOPK_F32 is later called with). */
+int32_t MoB200_SearchPrepareIvf(const void *data, uint64_t n, int64_t dim, const void *centroids, uint64_t nlist, const void *offsets);
 int32_t MoB200_SearchRelease(const void *data);
 
 #ifdef __cplusplus

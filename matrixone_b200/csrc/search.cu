@@ -490,12 +490,13 @@ __global__ void ivf_count_kernel(const int64_t *probes, int64_t npairs, int *cnt
     }
 }
 __global__ void ivf_fill_kernel(const int64_t *probes, int64_t npairs, int nprobe, const int *start, int *cursor,
-                                int32_t *bucket_q, int64_t *bucket_slot, int32_t *pair_pos) {
+                                int32_t *bucket_q, int32_t *bucket_l, int64_t *bucket_slot, int32_t *pair_pos) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npairs; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t l = probes[i];
         if (l < 0) { pair_pos[i] = -1; continue; }
         const int pos = start[l] + atomicAdd(&cursor[l], 1);
         bucket_q[pos] = (int32_t)(i / nprobe);
+        bucket_l[pos] = (int32_t)l;
         bucket_slot[pos] = i;
         pair_pos[i] = pos;
     }
@@ -518,13 +519,15 @@ __global__ void ivf_scatter_kernel(const int64_t *__restrict__ sk, const double 
 namespace mob {
 
 struct IvfJob {
-    const float *dcent; int64_t nlist; const float *ddata; int64_t n; int dim; const std::vector<int64_t> *offsets; const int64_t *drowids;
+    const float *dcent; int64_t nlist; const float *ddata; int64_t n; int dim; const std::vector<int64_t> *offsets; const int64_t *doffsets;
+    const int64_t *drowids;
     int k, nprobe, metric, sqrt_out;
 };
 
-// level 0: tensor-core candidate pass over whole lists (when the shape qualifies), level 1: the queries it could not prove, again on
-// the tensor cores but with every list cut into sub-ranges, level 2: whatever is still unproven through the exact kernel.
-// Each level answers its queries exactly or hands them down; results are scattered back into the caller's rows.
+// level 0: tensor-core candidate pass over whole lists (one-term product when the ladder allows it, else three-term), level 1: the
+// queries it could not prove, three-term product with every list cut into sub-ranges, level 2: whatever is still unproven
+// through the exact kernel.  Each level answers its queries exactly or hands them down; results are scattered back into the
+// caller's rows.
 static int ivf_search_level(ThreadCtx &t, const IvfJob &J, int level, const float *dq, int64_t nq, int64_t *ok, double *od) {
     IvfPlan plan;
     int rc = ivf_make_plan(t, J.dcent, J.nlist, J.dim, dq, nq, J.nprobe, J.metric, plan);
@@ -535,7 +538,9 @@ static int ivf_search_level(ThreadCtx &t, const IvfJob &J, int level, const floa
     }
     std::vector<int> redo;
     bool nonfinite = false;
-    rc = ivf_tc_scan(t, plan, J.ddata, J.n, J.dim, dq, nq, *J.offsets, J.drowids, J.k, J.sqrt_out, level == 1, ok, od, redo, &nonfinite);
+    const int pass = level == 1 ? 2 : (tc_one_term_wanted(J.k, true) ? 0 : 1);
+    rc = ivf_tc_scan(t, plan, J.ddata, J.n, J.dim, dq, nq, J.dcent, J.doffsets, *J.offsets, J.drowids, J.k, J.sqrt_out, pass, ok, od, redo, &nonfinite);
+    if (!rc && pass == 0 && !nonfinite) tc_one_term_report(nq, (int64_t)redo.size());
     if (rc) return rc;
     if (level == 0) { g_last_tc_refined = (int)redo.size(); g_last_tc_fallbacks = 0; }
     if (redo.empty()) return MO_RC_SUCCESS;
@@ -583,6 +588,7 @@ int xcall_ivf(mo_xcall_args_t *args, uint64_t len) {
     const float *dq = (const float *)st.in(args[3].pdata, (size_t)P.nq * dim * 4);
     const float *dcent = (const float *)st.in(args[5].pdata, (size_t)P.nlist * dim * 4);
     const int64_t *drowids = (const int64_t *)st.in(args[7].pdata, (size_t)P.n * 8);
+    const int64_t *doffsets = (const int64_t *)st.in(args[6].pdata, (size_t)(P.nlist + 1) * 8);
     int64_t *ok = (int64_t *)st.out(args[0].pdata, (size_t)P.nq * P.k * 8);
     double *od = (double *)st.out(args[1].pdata, (size_t)P.nq * P.k * 8);
     if (st.failed) { st.finish(); return MO_RC_INTERNAL_ERROR; }
@@ -590,7 +596,7 @@ int xcall_ivf(mo_xcall_args_t *args, uint64_t len) {
     if (is_device_ptr(args[6].pdata)) { MOB_CUDA_TRY(cudaMemcpyAsync(offsets.data(), args[6].pdata, offsets.size() * 8, cudaMemcpyDeviceToHost, t.stream)); MOB_CUDA_TRY(cudaStreamSynchronize(t.stream)); }
     else memcpy(offsets.data(), args[6].pdata, offsets.size() * 8);
 
-    IvfJob job{dcent, P.nlist, ddata, P.n, dim, &offsets, drowids, (int)P.k, nprobe, (int)P.metric, (int)P.sqrt_out};
+    IvfJob job{dcent, P.nlist, ddata, P.n, dim, &offsets, doffsets, drowids, (int)P.k, nprobe, (int)P.metric, (int)P.sqrt_out};
     g_last_tc_fallbacks = -1; g_last_tc_refined = -1;
     rc = ivf_search_level(t, job, 0, dq, P.nq, ok, od);
     int frc = st.finish();
@@ -609,7 +615,8 @@ int ivf_make_plan(ThreadCtx &t, const float *dcent, int64_t nlist, int dim, cons
     plan.bucket_q = (int32_t *)arena_alloc(t, (size_t)npairs * 4);
     plan.bucket_slot = (int64_t *)arena_alloc(t, (size_t)npairs * 8);
     plan.pair_pos = (int32_t *)arena_alloc(t, (size_t)npairs * 4);
-    if (!plan.probes || !probe_d || !cnt || !plan.bucket_q || !plan.bucket_slot || !plan.pair_pos) return MO_RC_INTERNAL_ERROR;
+    plan.bucket_l = (int32_t *)arena_alloc(t, (size_t)npairs * 4);
+    if (!plan.probes || !probe_d || !cnt || !plan.bucket_q || !plan.bucket_slot || !plan.pair_pos || !plan.bucket_l) return MO_RC_INTERNAL_ERROR;
     // exact either way: the tensor-core pass proves its top-nprobe complete or re-runs the query through the exact kernel
     int rc = tc_probe_applicable(nlist, dim, nq, nprobe, metric)
                  ? bruteforce_topk_tc_device(t, dcent, nlist, dim, dq, nq, nprobe, 0, 0, plan.probes, probe_d, false)
@@ -625,7 +632,7 @@ int ivf_make_plan(ThreadCtx &t, const float *dcent, int64_t nlist, int dim, cons
     int run = 0;
     for (int64_t l = 0; l < nlist; l++) { plan.hstart[(size_t)l] = run; run += plan.hcnt[(size_t)l]; }
     MOB_CUDA_TRY(cudaMemcpyAsync(dstart, plan.hstart.data(), (size_t)nlist * 4, cudaMemcpyHostToDevice, t.stream));
-    ivf_fill_kernel<<<num_sms() * 4, 256, 0, t.stream>>>(plan.probes, npairs, nprobe, dstart, cursor, plan.bucket_q, plan.bucket_slot, plan.pair_pos);
+    ivf_fill_kernel<<<num_sms() * 4, 256, 0, t.stream>>>(plan.probes, npairs, nprobe, dstart, cursor, plan.bucket_q, plan.bucket_l, plan.bucket_slot, plan.pair_pos);
     MOB_LAUNCH_CHECK();
     MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));   // hstart (pageable host memory) must stay valid until the copy above is done
     return MO_RC_SUCCESS;

@@ -38,6 +38,7 @@ namespace {
 
 constexpr int BM = 128, BN = 256, BK = 64;
 constexpr int KP = 16;                      // candidates kept per (query, row range)
+constexpr int KP_LONG = 32;                 // ... by the one-term pass over IVF lists (short ranges: the list threshold must sit well above the k-th result)
 constexpr int kTcThreads = 256;             // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warp 3 idle, warps 4-7 epilogue
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 
@@ -159,7 +160,7 @@ constexpr unsigned kIdescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)
 // one work unit: up to kTileM rows of the A' operand (queries) x dataset rows [n_begin, n_end); lists are written at out_base + row
 struct TcUnit { int a_row0; int a_valid; int n_begin; int n_end; long long out_base; };
 
-template <bool PAIR>
+template <bool PAIR, int KPT>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                      const TcUnit *__restrict__ units, int nunits, int nkb /* 64-element k-blocks of K' to run */,
@@ -260,12 +261,12 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             const TcUnit U = units[u];
             const bool valid_row = row_in_unit < U.a_valid;
             const float qn = valid_row ? qnorm[U.a_row0 + row_in_unit] : 0.f;
-            // the KP best (approximate distance, row) pairs of this query row live in REGISTERS, ascending; an insertion is a
+            // the KPT best (approximate distance, row) pairs of this query row live in REGISTERS, ascending; an insertion is a
             // branch-free compare/select sweep (no shared-memory dependency chain, lanes of a warp insert at different ranks at
             // the same cost).  Rows of the tile past a_valid never insert (thr = -inf).
-            float ld[KP]; int li[KP];
+            float ld[KPT]; int li[KPT];
 #pragma unroll
-            for (int j = 0; j < KP; j++) { ld[j] = INFINITY; li[j] = -1; }
+            for (int j = 0; j < KPT; j++) { ld[j] = INFINITY; li[j] = -1; }
             float thr = valid_row ? INFINITY : -INFINITY;
             for (int n0 = U.n_begin; n0 < U.n_end; n0 += BN, tile++) {
                 const unsigned acc = tile & 1;
@@ -305,14 +306,14 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                             if (d < thr) {   // thr may have dropped since the mask was taken
                                 const int id = n0 + c + j;
 #pragma unroll
-                                for (int p = KP - 1; p > 0; p--) {     // descending: ld[p - 1] is still the old value when read
+                                for (int p = KPT - 1; p > 0; p--) {     // descending: ld[p - 1] is still the old value when read
                                     const bool shift = d < ld[p - 1];  // the old neighbour moves down to p
                                     const bool here = !shift && d < ld[p];
                                     li[p] = shift ? li[p - 1] : (here ? id : li[p]);
                                     ld[p] = shift ? ld[p - 1] : (here ? d : ld[p]);
                                 }
                                 if (d < ld[0]) { ld[0] = d; li[0] = id; }
-                                thr = ld[KP - 1];
+                                thr = ld[KPT - 1];
                             }
                         }
                     }
@@ -325,9 +326,9 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 }
             }
             if (valid_row) {
-                const size_t base = (size_t)(U.out_base + row_in_unit) * KP;
+                const size_t base = (size_t)(U.out_base + row_in_unit) * KPT;
 #pragma unroll
-                for (int j = 0; j < KP; j++) { part_d[base + j] = ld[j]; part_i[base + j] = li[j]; }   // empty slots: (+inf, -1)
+                for (int j = 0; j < KPT; j++) { part_d[base + j] = ld[j]; part_i[base + j] = li[j]; }   // empty slots: (+inf, -1)
                 part_thr[U.out_base + row_in_unit] = thr;        // every row of this unit that is NOT listed has d~ >= thr (+inf: list not full)
             }
         }
@@ -363,6 +364,46 @@ __global__ void split_kernel(const float *__restrict__ x, int64_t n, int dim, in
             const double l = (double)(v - __bfloat162float(hi));   // exact in fp32
             sl += l * l;
             if (!(fabsf(v) <= 3.0e38f)) *nonfinite = 1;   // Inf / NaN: the caller falls back to the exact kernel
+        }
+        for (int j = 3 * dim + lane; j < kprime; j += 32) o[j] = __float2bfloat16_rn(0.f);
+        s = warp_sum_f64(s); sl = warp_sum_f64(sl);
+        if (lane == 0) { norm[r] = (float)s; lonorm[r] = (float)sl; }
+    }
+}
+
+// IVF operands are RESIDUALS: x - centroid(list of x) for the entries, q - centroid(l) for every (query, probed list l) pair.
+// |q - x|^2 = |(q - c) - (x - c)|^2, and residual norms are the within-list spread instead of the distance from the origin, so
+// the error bounds of the candidate pass (proportional to |a||b|) shrink with them.  fl(v - c) differs from v - c by 2^-24
+// relative per element, covered by the 2^-20 (|a|^2 + |b|^2) term of the proof.
+// mode 1 (entries): src row r belongs to the list l with offsets[l] <= r < offsets[l + 1]; mode 0 (pairs): row g = (idx_q[g], idx_l[g]).
+__global__ void split_residual_kernel(const float *__restrict__ x, int64_t n, int dim, int kprime, int mode,
+                                      const float *__restrict__ cent, const int64_t *__restrict__ offsets, int64_t nlist,
+                                      const int32_t *__restrict__ idx_q, const int32_t *__restrict__ idx_l,
+                                      __nv_bfloat16 *__restrict__ out, float *__restrict__ norm, float *__restrict__ lonorm, int *__restrict__ nonfinite) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n; r += nwarps) {
+        int64_t src = r, l;
+        if (mode == 0) { src = idx_q[r]; l = idx_l[r]; }
+        else {   // largest l with offsets[l] <= r (empty lists share an offset: any of them gives the same answer only if non-empty => upper bound - 1)
+            int64_t lo = 0, hi = nlist;          // invariant: offsets[lo] <= r < offsets[hi]
+            while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (offsets[mid] <= r) lo = mid; else hi = mid; }
+            l = lo;
+        }
+        const float *p = x + src * dim, *c = cent + l * dim;
+        __nv_bfloat16 *o = out + r * kprime;
+        double s = 0.0, sl = 0.0;
+        for (int j = lane; j < dim; j += 32) {
+            const float v = __fsub_rn(p[j], c[j]);
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+            o[j] = hi;
+            o[dim + j] = mode == 0 ? hi : lo;
+            o[2 * dim + j] = mode == 0 ? lo : hi;
+            s += (double)v * (double)v;
+            const double d = (double)(v - __bfloat162float(hi));
+            sl += d * d;
+            if (!(fabsf(v) <= 3.0e38f)) *nonfinite = 1;
         }
         for (int j = 3 * dim + lane; j < kprime; j += 32) o[j] = __float2bfloat16_rn(0.f);
         s = warp_sum_f64(s); sl = warp_sum_f64(sl);
@@ -406,26 +447,43 @@ constexpr int KW = 32;
 // index = s * pos_stride + pos_map[q * pos_cols + p]  (pos_map < 0 = no such list)
 constexpr int kMaxMergeLists = 256;
 constexpr int kMergeSlots = kMaxMergeLists / 32;
+
+// bound on |approximate - real| squared distance of one (query operand, row operand) pair, from the operand norms:
+//   three-term product: |2 q.x error| <= 2 (3 * 2^-16 [dropped lo.lo + bf16 residuals] + 144 * 2^-23 [fp32 accumulation over K'/16
+//     MMA steps]) |q||x| < 2^-12.8 |q||x|; 2^-12 is used
+//   one-term (hi-only) product: q.x - qh.xh = qh.xL + qL.xh + qL.xL with qL = q - qh, xL = x - xh known exactly, so
+//     |error| <= |q||xL| + |qL||x| + 3 |qL||xL|  (|qh| <= |q| + |qL|); fp32 accumulation over dim/16 MMA steps < 2^-17 |q||x|
+//   both: norm / final-formula / residual-formation rounding 2^-20 (|q|^2 + |x|^2)
+// qn, ql = |q|^2, |q - hi(q)|^2 of the query operand; xm, xl = the largest |x|^2, |x - hi(x)|^2 over the row operand
+__device__ __forceinline__ float tc_eps(float qn, float ql, float xm, float xl, int one_term) {
+    if (one_term)
+        return 2.002f * (sqrtf(qn * xl) + sqrtf(ql * xm) + 3.0f * sqrtf(ql * xl)) + 1.52587890625e-5f * sqrtf(qn * xm) + 9.5367431640625e-7f * (qn + xm);
+    return 2.44140625e-4f * sqrtf(qn * xm) + 9.5367431640625e-7f * (qn + xm);
+}
+
+// pnorm / plonorm (IVF): the query operand differs per probed list (residual against that list's centroid), so every list's
+// exclusion bound is lowered by ITS error bound before the minimum is taken: t_excl = min_l (t_l - eps_l)
 __global__ void tc_merge_kernel(int nq, int R, const float *__restrict__ part_d, const int *__restrict__ part_i,
                                 const float *__restrict__ part_thr, const int *__restrict__ pos_map, int pos_cols, long long pos_stride,
-                                int kr, int *__restrict__ cand, float *__restrict__ t_excl) {
+                                const float *__restrict__ pnorm, const float *__restrict__ plonorm, const float *__restrict__ xmax2, int one_term,
+                                int kp, int kr, int *__restrict__ cand, float *__restrict__ t_excl) {
     const int lane = threadIdx.x & 31;
     const int q = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
     if (q >= nq) return;   // whole warps leave together
-    long long L[kMergeSlots]; int head[kMergeSlots]; float cur[kMergeSlots];
-    float t = INFINITY;
+    long long L[kMergeSlots]; int head[kMergeSlots]; float cur[kMergeSlots], tl[kMergeSlots], eps[kMergeSlots];
 #pragma unroll
     for (int i = 0; i < kMergeSlots; i++) {
         const int r = lane + 32 * i;
-        long long l = -1;
+        long long l = -1; int p = -1;
         if (r < R) {
             if (!pos_map) l = (long long)r * nq + q;
-            else { const int p = pos_map[(size_t)q * pos_cols + r % pos_cols]; l = p < 0 ? -1ll : (long long)(r / pos_cols) * pos_stride + p; }
+            else { p = pos_map[(size_t)q * pos_cols + r % pos_cols]; l = p < 0 ? -1ll : (long long)(r / pos_cols) * pos_stride + p; }
         }
-        L[i] = l; head[i] = 0; cur[i] = INFINITY;
+        L[i] = l; head[i] = 0; cur[i] = INFINITY; tl[i] = INFINITY; eps[i] = 0.f;
         if (l >= 0) {
-            t = fminf(t, part_thr[l]);
-            if (part_i[(size_t)l * KP] >= 0) cur[i] = part_d[(size_t)l * KP];
+            tl[i] = part_thr[l];
+            if (part_i[(size_t)l * kp] >= 0) cur[i] = part_d[(size_t)l * kp];
+            if (pnorm && p >= 0) eps[i] = tc_eps(pnorm[p], plonorm[p], xmax2[0], xmax2[1], one_term);
         }
     }
     for (int j = 0; j < kr; j++) {
@@ -442,15 +500,16 @@ __global__ void tc_merge_kernel(int nq, int R, const float *__restrict__ part_d,
 #pragma unroll
             for (int i = 0; i < kMergeSlots; i++)
                 if (i == (br >> 5)) {
-                    const size_t idx = (size_t)L[i] * KP + head[i];
+                    const size_t idx = (size_t)L[i] * kp + head[i];
                     cand[(size_t)q * kr + j] = part_i[idx];
                     head[i]++;
-                    cur[i] = (head[i] < KP && part_i[idx + 1] >= 0) ? part_d[idx + 1] : INFINITY;
+                    cur[i] = (head[i] < kp && part_i[idx + 1] >= 0) ? part_d[idx + 1] : INFINITY;
                 }
         }
     }
+    float t = INFINITY;
 #pragma unroll
-    for (int i = 0; i < kMergeSlots; i++) t = fminf(t, cur[i]);   // first unconsumed entry of every list
+    for (int i = 0; i < kMergeSlots; i++) t = fminf(t, fminf(tl[i], cur[i]) - eps[i]);   // list-full threshold / first unconsumed entry (inf - eps = inf)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) t = fminf(t, __shfl_xor_sync(0xffffffffu, t, o));
     if (lane == 0) t_excl[q] = t;
@@ -487,7 +546,7 @@ __global__ void tc_max_kernel(const float *__restrict__ v, int64_t n, float *out
 template <int KRT>
 __global__ void tc_final_kernel(int nq, int k, int64_t n_rows, int dim, const int *__restrict__ cand, const float *__restrict__ exact,
                                 const float *__restrict__ t_excl, const float *__restrict__ qnorm, const float *__restrict__ xnorm_max,
-                                const float *__restrict__ qlonorm, const float *__restrict__ xlonorm_max, int one_term,
+                                const float *__restrict__ qlonorm, const float *__restrict__ xlonorm_max, int one_term, int eps_applied,
                                 const int64_t *__restrict__ id_map, int64_t key_base, int sqrt_out, int64_t *__restrict__ out_k,
                                 double *__restrict__ out_d, int *__restrict__ flags) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -512,41 +571,20 @@ __global__ void tc_final_kernel(int nq, int k, int64_t n_rows, int dim, const in
     if (t == INFINITY) proven = true;                       // nothing was excluded (every row of every range is listed)
     else if (m < k) proven = false;
     else {
-        const float qn = qnorm[q], xm = *xnorm_max;
-        // |2 q.x error| <= 2 * (3 * 2^-16 [dropped lo.lo + bf16 residuals] + 144 * 2^-23 [fp32 accumulation over K'/16 MMA steps]) * |q||x|
-        //               < 2^-12.8 |q||x|; 2^-12 is used.  Norm / final-formula rounding: 2^-21 (|q|^2 + |x|^2).
-        float eps_tc = 2.44140625e-4f * sqrtf(qn * xm) + 4.76837158203125e-7f * (qn + xm);
-        if (one_term) {
-            // hi-only pass: q.x - qh.xh = qh.xL + qL.xh + qL.xL with qL = q - qh, xL = x - xh known exactly, so
-            // |error| <= |q||xL| + |qL||x| + 3 |qL||xL|  (|qh| <= |q| + |qL|); fp32 accumulation over dim/16 MMA steps < 2^-17 |q||x|
-            const float ql = qlonorm[q], xl = *xlonorm_max;
-            eps_tc = 2.002f * (sqrtf(qn * xl) + sqrtf(ql * xm) + 3.0f * sqrtf(ql * xl)) + 1.52587890625e-5f * sqrtf(qn * xm) +
-                     4.76837158203125e-7f * (qn + xm);
-        }
+        // eps_applied: the merge already lowered t by every list's own bound (IVF residual operands)
+        const float eps_tc = eps_applied ? 0.f : tc_eps(qnorm[q], one_term ? qlonorm[q] : 0.f, *xnorm_max, one_term ? *xlonorm_max : 0.f, one_term);
         const float eps_go = (float)dim * 1.1920928955078125e-7f * t;                                  // dim * 2^-23 * distance scale
         proven = d[k - 1] + eps_tc + eps_go < t;
     }
     flags[q] = proven ? 0 : 1;
 }
 
-__global__ void tc_fill_kernel(float *thr, int *ids, int64_t nlists) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nlists * KP; i += (int64_t)gridDim.x * blockDim.x) {
+__global__ void tc_fill_kernel(float *thr, int *ids, int64_t nlists, int kp) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nlists * kp; i += (int64_t)gridDim.x * blockDim.x) {
         ids[i] = -1;
         if (i < nlists) thr[i] = INFINITY;
     }
 }
-// dst row g = src row idx[g] (rows of kprime bf16 = 16-byte multiples); also gathers the fp32 norms
-__global__ void gather_split_rows_kernel(const __nv_bfloat16 *__restrict__ src, const float *__restrict__ snorm, const int32_t *__restrict__ idx,
-                                         int64_t m, int kprime, __nv_bfloat16 *__restrict__ dst, float *__restrict__ dnorm) {
-    const int vec_per_row = kprime / 8;   // int4 = 8 bf16
-    const int4 *s4 = reinterpret_cast<const int4 *>(src); int4 *d4 = reinterpret_cast<int4 *>(dst);
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < m * vec_per_row; e += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t g = e / vec_per_row; const int v = (int)(e % vec_per_row);
-        d4[e] = s4[(int64_t)idx[g] * vec_per_row + v];
-        if (v == 0) dnorm[g] = snorm[idx[g]];
-    }
-}
-
 __global__ void gather_rows_kernel(const float *__restrict__ src, const int *__restrict__ idx, int m, int dim, float *__restrict__ dst) {
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < (int64_t)m * dim; e += (int64_t)gridDim.x * blockDim.x)
         dst[e] = src[(int64_t)idx[e / dim] * dim + e % dim];
@@ -575,7 +613,7 @@ int g_last_tc_fallbacks = -1;   // queries of the last tensor-core search that f
 struct TcOperand { __nv_bfloat16 *bf = nullptr; float *norm = nullptr; float *lonorm = nullptr; int kprime = 0; };   // norm = |x|^2, lonorm = |x - bf16(x)|^2 per row
 
 // datasets split once by MoB200_SearchPrepare (index load); looked up by (pointer, rows, dim)
-struct PreparedOperand { const float *x; int64_t n; int dim; int device; TcOperand op; };
+struct PreparedOperand { const float *x; int64_t n; int dim; int device; TcOperand op; const float *cent = nullptr; int64_t nlist = 0; };   // cent != nullptr: IVF residual operand
 static std::mutex g_prepared_mu;
 static std::vector<PreparedOperand> g_prepared;
 
@@ -588,7 +626,7 @@ static int tc_prepare(ThreadCtx &t, const float *x, int64_t n, int dim, int mode
     Cached &c = cache[mode & 1];
     if (mode == 1) {
         std::lock_guard<std::mutex> lk(g_prepared_mu);
-        for (const PreparedOperand &e : g_prepared) if (e.x == x && e.n == n && e.dim == dim) { op = e.op; return MO_RC_SUCCESS; }
+        for (const PreparedOperand &e : g_prepared) if (e.x == x && e.n == n && e.dim == dim && !e.cent) { op = e.op; return MO_RC_SUCCESS; }
     }
     if (c.t == &t && c.epoch == t.arena_epoch && c.x == x && c.n == n && c.dim == dim && c.mode == mode) { op = c.op; return MO_RC_SUCCESS; }
     op.kprime = ((3 * dim + BK - 1) / BK) * BK;
@@ -601,9 +639,32 @@ static int tc_prepare(ThreadCtx &t, const float *x, int64_t n, int dim, int mode
     return MO_RC_SUCCESS;
 }
 
+// IVF entries as residual operand (see split_residual_kernel); prepared at index load or once per call
+static int tc_prepare_ivf_entries(ThreadCtx &t, const float *x, int64_t n, int dim, const float *dcent, int64_t nlist, const int64_t *doffsets,
+                                  int *dnonfinite, TcOperand &op) {
+    {
+        std::lock_guard<std::mutex> lk(g_prepared_mu);
+        for (const PreparedOperand &e : g_prepared) if (e.x == x && e.n == n && e.dim == dim && e.cent == dcent && e.nlist == nlist) { op = e.op; return MO_RC_SUCCESS; }
+    }
+    struct Cached { const float *x = nullptr, *c = nullptr; int64_t n = 0; int dim = 0; uint64_t epoch = ~0ull; const ThreadCtx *t = nullptr; TcOperand op; };
+    static thread_local Cached c;
+    if (c.t == &t && c.epoch == t.arena_epoch && c.x == x && c.c == dcent && c.n == n && c.dim == dim) { op = c.op; return MO_RC_SUCCESS; }
+    op.kprime = ((3 * dim + BK - 1) / BK) * BK;
+    op.bf = (__nv_bfloat16 *)arena_alloc(t, (size_t)(n > 0 ? n : 1) * op.kprime * 2 + 1024);
+    op.norm = (float *)arena_alloc(t, (size_t)(n > 0 ? n : 1) * 4);
+    op.lonorm = (float *)arena_alloc(t, (size_t)(n > 0 ? n : 1) * 4);
+    if (!op.bf || !op.norm || !op.lonorm) return MO_RC_INTERNAL_ERROR;
+    if (n > 0) {
+        split_residual_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(x, n, dim, op.kprime, 1, dcent, doffsets, nlist, nullptr, nullptr, op.bf, op.norm, op.lonorm, dnonfinite);
+        MOB_LAUNCH_CHECK();
+    }
+    c.x = x; c.c = dcent; c.n = n; c.dim = dim; c.epoch = t.arena_epoch; c.t = &t; c.op = op;
+    return MO_RC_SUCCESS;
+}
+
 // run the candidate kernel over `units`; lists are written at unit.out_base + row (nlists lists in total, pre-initialised empty)
 static int tc_run_units(ThreadCtx &t, const TcOperand &A, int64_t a_rows, const TcOperand &B, int64_t b_rows, const std::vector<TcUnit> &units,
-                        int64_t nlists, float **part_d, int **part_i, float **part_thr, bool timed = true, bool pair = false, int nkb = 0) {
+                        int64_t nlists, float **part_d, int **part_i, float **part_thr, bool timed = true, bool pair = false, int nkb = 0, int kp = KP) {
     if (nkb <= 0 || nkb > A.kprime / BK) nkb = A.kprime / BK;   // 0 = the whole K' (three-term product)
     CUtensorMap map_a, map_b;
     int rc = make_map(&map_a, A.bf, (uint64_t)a_rows, (uint64_t)A.kprime, BM);
@@ -611,11 +672,11 @@ static int tc_run_units(ThreadCtx &t, const TcOperand &A, int64_t a_rows, const 
     rc = make_map(&map_b, B.bf, (uint64_t)b_rows, (uint64_t)B.kprime, pair ? TcCfg<true>::kBRows : TcCfg<false>::kBRows);
     if (rc) return rc;
     TcUnit *dunits = (TcUnit *)arena_alloc(t, sizeof(TcUnit) * (units.size() ? units.size() : 1));
-    *part_d = (float *)arena_alloc(t, sizeof(float) * (size_t)nlists * KP);
-    *part_i = (int *)arena_alloc(t, sizeof(int) * (size_t)nlists * KP);
+    *part_d = (float *)arena_alloc(t, sizeof(float) * (size_t)nlists * kp);
+    *part_i = (int *)arena_alloc(t, sizeof(int) * (size_t)nlists * kp);
     *part_thr = (float *)arena_alloc(t, sizeof(float) * (size_t)nlists);
     if (!dunits || !*part_d || !*part_i || !*part_thr) return MO_RC_INTERNAL_ERROR;
-    tc_fill_kernel<<<num_sms() * 4, 256, 0, t.stream>>>(*part_thr, *part_i, nlists);
+    tc_fill_kernel<<<num_sms() * 4, 256, 0, t.stream>>>(*part_thr, *part_i, nlists, kp);
     MOB_LAUNCH_CHECK();
     if (units.empty()) return MO_RC_SUCCESS;
     MOB_CUDA_TRY(cudaMemcpyAsync(dunits, units.data(), sizeof(TcUnit) * units.size(), cudaMemcpyHostToDevice, t.stream));
@@ -623,8 +684,9 @@ static int tc_run_units(ThreadCtx &t, const TcOperand &A, int64_t a_rows, const 
     static bool attr = false;
     const size_t smem1 = sizeof(TcSmemT<false>) + 1024, smem2 = sizeof(TcSmemT<true>) + 1024;
     if (!attr) {
-        MOB_CUDA_TRY(cudaFuncSetAttribute(tc_candidates_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-        MOB_CUDA_TRY(cudaFuncSetAttribute(tc_candidates_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        MOB_CUDA_TRY(cudaFuncSetAttribute(tc_candidates_kernel<false, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        MOB_CUDA_TRY(cudaFuncSetAttribute(tc_candidates_kernel<false, KP_LONG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        MOB_CUDA_TRY(cudaFuncSetAttribute(tc_candidates_kernel<true, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         attr = true;
     }
     const int nunits = (int)units.size();
@@ -632,8 +694,10 @@ static int tc_run_units(ThreadCtx &t, const TcOperand &A, int64_t a_rows, const 
     if (!pair) {
         int grid = num_sms();
         if (grid > nunits) grid = nunits;
-        tc_candidates_kernel<false><<<grid, kTcThreads, smem1, t.stream>>>(map_a, map_b, dunits, nunits, nkb, A.norm, B.norm, *part_d, *part_i, *part_thr);
+        if (kp == KP_LONG) tc_candidates_kernel<false, KP_LONG><<<grid, kTcThreads, smem1, t.stream>>>(map_a, map_b, dunits, nunits, nkb, A.norm, B.norm, *part_d, *part_i, *part_thr);
+        else tc_candidates_kernel<false, KP><<<grid, kTcThreads, smem1, t.stream>>>(map_a, map_b, dunits, nunits, nkb, A.norm, B.norm, *part_d, *part_i, *part_thr);
     } else {
+        if (kp != KP) { set_error("tc search: CTA pairs keep %d candidates per list", KP); return MO_RC_INTERNAL_ERROR; }
         // clusters of two CTAs (one TPC each): one persistent pair per two SMs
         int pairs = num_sms() / 2;
         if (pairs > nunits) pairs = nunits;
@@ -643,7 +707,7 @@ static int tc_run_units(ThreadCtx &t, const TcOperand &A, int64_t a_rows, const 
         at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         const float *an = A.norm, *bn = B.norm; int kp = nkb;
-        MOB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_candidates_kernel<true>, map_a, map_b, (const TcUnit *)dunits, nunits, kp, an, bn, *part_d, *part_i, *part_thr));
+        MOB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_candidates_kernel<true, KP>, map_a, map_b, (const TcUnit *)dunits, nunits, kp, an, bn, *part_d, *part_i, *part_thr));
     }
     if (timed) cudaEventRecord(t.kev1, t.stream);
     MOB_LAUNCH_CHECK();
@@ -654,8 +718,10 @@ static int tc_run_units(ThreadCtx &t, const TcOperand &A, int64_t a_rows, const 
 static int tc_finish(ThreadCtx &t, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq, int k, int R, const int *pos_map,
                      int pos_cols, long long pos_stride, const float *part_d, const int *part_i, const float *part_thr, const float *qnorm, const float *xnorm,
                      const int64_t *id_map, int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d, std::vector<int> &redo,
-                     const float *qlonorm = nullptr, const float *xlonorm = nullptr) {   // both given: the candidate pass was hi-only (one term)
-    const int one_term = qlonorm && xlonorm ? 1 : 0;
+                     const float *qlonorm = nullptr, const float *xlonorm = nullptr,   // both given: the candidate pass was hi-only (one term)
+                     const float *pair_norm = nullptr, const float *pair_lonorm = nullptr,   // IVF: operand norms per (query, list) pair
+                     int kp = KP) {
+    const int one_term = xlonorm ? 1 : 0;
     const int kr = (k > KP || one_term) ? KR_WIDE : KR;   // a looser approximation needs more exact re-scores to prove the top k
     int *cand = (int *)arena_alloc(t, sizeof(int) * (size_t)nq * kr);
     float *exact = (float *)arena_alloc(t, sizeof(float) * (size_t)nq * kr);
@@ -668,12 +734,12 @@ static int tc_finish(ThreadCtx &t, const float *ddata, int64_t n, int dim, const
     MOB_LAUNCH_CHECK();
     if (one_term) { tc_max_kernel<<<num_sms() * 2, 256, 0, t.stream>>>(xlonorm, n, xlomax); MOB_LAUNCH_CHECK(); }
     if (R > kMaxMergeLists) { set_error("tc search: %d candidate lists per query exceed the merge limit %d", R, kMaxMergeLists); return MO_RC_INTERNAL_ERROR; }
-    tc_merge_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, t.stream>>>((int)nq, R, part_d, part_i, part_thr, pos_map, pos_cols, pos_stride, kr, cand, t_excl);
+    tc_merge_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, t.stream>>>((int)nq, R, part_d, part_i, part_thr, pos_map, pos_cols, pos_stride, pair_norm, pair_lonorm, xmax, one_term, kp, kr, cand, t_excl);
     MOB_LAUNCH_CHECK();
     tc_rescore_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(ddata, dq, dim, (int)nq, kr, cand, exact);
     MOB_LAUNCH_CHECK();
-    if (kr == KR) tc_final_kernel<KR><<<(unsigned)((nq + 127) / 128), 128, 0, t.stream>>>((int)nq, k, n, dim, cand, exact, t_excl, qnorm, xmax, qlonorm, xlomax, one_term, id_map, key_base, sqrt_out, out_k, out_d, flags);
-    else tc_final_kernel<KR_WIDE><<<(unsigned)((nq + 127) / 128), 128, 0, t.stream>>>((int)nq, k, n, dim, cand, exact, t_excl, qnorm, xmax, qlonorm, xlomax, one_term, id_map, key_base, sqrt_out, out_k, out_d, flags);
+    if (kr == KR) tc_final_kernel<KR><<<(unsigned)((nq + 127) / 128), 128, 0, t.stream>>>((int)nq, k, n, dim, cand, exact, t_excl, qnorm, xmax, qlonorm, xlomax, one_term, pair_norm ? 1 : 0, id_map, key_base, sqrt_out, out_k, out_d, flags);
+    else tc_final_kernel<KR_WIDE><<<(unsigned)((nq + 127) / 128), 128, 0, t.stream>>>((int)nq, k, n, dim, cand, exact, t_excl, qnorm, xmax, qlonorm, xlomax, one_term, pair_norm ? 1 : 0, id_map, key_base, sqrt_out, out_k, out_d, flags);
     MOB_LAUNCH_CHECK();
     std::vector<int> hflags((size_t)nq);
     MOB_CUDA_TRY(cudaMemcpyAsync(hflags.data(), flags, sizeof(int) * (size_t)nq, cudaMemcpyDeviceToHost, t.stream));
@@ -741,6 +807,7 @@ bool tc_ivf_applicable(int64_t n, int dim, int64_t nq, int k, int nprobe, int me
 // A precision ladder: level 0 runs only the first dim columns of K' (the hi.hi product, a third of the flop) and proves what it
 // can with the looser one-term error bound; level 1 re-runs the unproven queries over the whole K' (three-term product); what is
 // still unproven goes to the exact kernel.  Every level answers its queries exactly or hands them down.
+void tc_one_term_report(int64_t nq, int64_t failed);
 static int bf_tc_level(ThreadCtx &t, int level, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq, int k,
                        int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d, bool record_stats, bool timed) {
     if (level >= 2) {
@@ -799,8 +866,7 @@ static int bf_tc_level(ThreadCtx &t, int level, const float *ddata, int64_t n, i
     if (rc) return rc;
     if (record_stats && level == 0) {
         g_last_tc_refined = (int)redo.size();
-        // a dataset whose norms dwarf its neighbour distances defeats the one-term bound: stop trying for a while
-        if (nq >= 64 && (int64_t)redo.size() * 5 > nq * 2) g_one_term_skip = 16;
+        tc_one_term_report(nq, (int64_t)redo.size());
     }
     if (redo.empty()) return MO_RC_SUCCESS;
     // queries whose completeness could not be proven: next level, results scattered back
@@ -821,12 +887,19 @@ static int bf_tc_level(ThreadCtx &t, int level, const float *ddata, int64_t n, i
     return MO_RC_SUCCESS;
 }
 
+// the one-term level needs k <= KP (its proof re-scores 64 candidates) and is skipped while it has recently been failing
+bool tc_one_term_wanted(int k, bool record) {
+    if (k > KP || g_tc_ladder_mode == 1) return false;
+    if (g_tc_ladder_mode == 2) return true;
+    if (g_one_term_skip > 0) { if (record) g_one_term_skip--; return false; }
+    return true;
+}
+// a dataset whose norms dwarf its neighbour distances defeats the one-term bound: stop trying for a while
+void tc_one_term_report(int64_t nq, int64_t failed) { if (nq >= 64 && failed * 5 > nq * 2) g_one_term_skip = 16; }
+
 int bruteforce_topk_tc_device(ThreadCtx &t, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq, int k,
                               int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d, bool record_stats) {
-    // the one-term level needs k <= KP (its proof re-scores 64 candidates) and is skipped while it has recently been failing
-    bool ladder = g_tc_ladder_mode == 2 || (g_tc_ladder_mode == 0 && g_one_term_skip == 0);
-    if (g_tc_ladder_mode == 0 && g_one_term_skip > 0 && record_stats) g_one_term_skip--;
-    if (k > KP) ladder = false;
+    const bool ladder = tc_one_term_wanted(k, record_stats);
     if (record_stats) { g_last_tc_fallbacks = 0; g_last_tc_refined = -1; }
     return bf_tc_level(t, ladder ? 0 : 1, ddata, n, dim, dq, nq, k, key_base, sqrt_out, out_k, out_d, record_stats, record_stats);
 }
@@ -834,17 +907,19 @@ int bruteforce_topk_tc_device(ThreadCtx &t, const float *ddata, int64_t n, int d
 // IVF list scan on the tensor cores: the queries probing a list are gathered (as split bf16 rows) next to each other, so
 // a (list, 128-query tile) pair is one work unit of the same candidate kernel; every (query, probe rank) pair owns one list.
 int ivf_tc_scan(ThreadCtx &t, const IvfPlan &plan, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq,
-                const std::vector<int64_t> &offsets, const int64_t *drowids, int k, int sqrt_out, bool refine, int64_t *ok, double *od,
-                std::vector<int> &redo, bool *nonfinite) {
+                const float *dcent, const int64_t *doffsets, const std::vector<int64_t> &offsets, const int64_t *drowids, int k, int sqrt_out,
+                int pass, int64_t *ok, double *od, std::vector<int> &redo, bool *nonfinite) {
+    // pass 0: hi-only product over whole lists (one term), pass 1: three-term product over whole lists, pass 2 (refine): three-term
+    // product with every list cut into sub-ranges of `chunk` rows, each keeping its own KP candidates, so the excluded-row
+    // threshold of a (query, list) pair moves far away from the k-th result
     *nonfinite = false;
+    const bool one_term = pass == 0, refine = pass == 2;
     const int64_t nlist = (int64_t)offsets.size() - 1;
-    // refine pass (queries the first pass could not prove): every list is cut into sub-ranges of `chunk` rows, each keeping its own
-    // KP candidates, so the excluded-row threshold of a (query, list) pair moves far away from the k-th result
     int split = 1; int64_t chunk = (int64_t)1 << 40;
-    if (refine) {
-        int64_t maxlen = 1;
-        for (int64_t l = 0; l < nlist; l++) if (plan.hcnt[(size_t)l] > 0 && offsets[(size_t)l + 1] - offsets[(size_t)l] > maxlen) maxlen = offsets[(size_t)l + 1] - offsets[(size_t)l];
-        split = (int)((maxlen + BN - 1) / BN);
+    int64_t maxlen = 1;
+    for (int64_t l = 0; l < nlist; l++) if (plan.hcnt[(size_t)l] > 0 && offsets[(size_t)l + 1] - offsets[(size_t)l] > maxlen) maxlen = offsets[(size_t)l + 1] - offsets[(size_t)l];
+    if (refine) split = (int)((maxlen + BN - 1) / BN);
+    if (split > 1) {
         const int cap = kMaxMergeLists / plan.nprobe > 0 ? kMaxMergeLists / plan.nprobe : 1;
         if (split > cap) split = cap;
         chunk = ((maxlen + split - 1) / split + BN - 1) / BN * BN;
@@ -852,21 +927,22 @@ int ivf_tc_scan(ThreadCtx &t, const IvfPlan &plan, const float *ddata, int64_t n
     int *dnonfinite = (int *)arena_alloc(t, 4);
     if (!dnonfinite) return MO_RC_INTERNAL_ERROR;
     MOB_CUDA_TRY(cudaMemsetAsync(dnonfinite, 0, 4, t.stream));
-    TcOperand Aq, B, A;
-    int rc = tc_prepare(t, dq, nq, dim, 0, dnonfinite, Aq);
-    if (!rc) rc = tc_prepare(t, ddata, n, dim, 1, dnonfinite, B);
+    // operands are residuals against the list centroid: entries prepared at index load (or once per call), queries per (query, list) pair
+    TcOperand B, A;
+    int rc = tc_prepare_ivf_entries(t, ddata, n, dim, dcent, nlist, doffsets, dnonfinite, B);
     if (rc) return rc;
+    A.kprime = B.kprime;
+    A.bf = (__nv_bfloat16 *)arena_alloc(t, (size_t)plan.npairs * A.kprime * 2 + 1024);
+    A.norm = (float *)arena_alloc(t, (size_t)plan.npairs * 4);
+    A.lonorm = (float *)arena_alloc(t, (size_t)plan.npairs * 4);
+    if (!A.bf || !A.norm || !A.lonorm) return MO_RC_INTERNAL_ERROR;
+    split_residual_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(dq, plan.npairs, dim, A.kprime, 0, dcent, nullptr, nlist, plan.bucket_q, plan.bucket_l,
+                                                               A.bf, A.norm, A.lonorm, dnonfinite);
+    MOB_LAUNCH_CHECK();
     int hnonfinite = 0;
     rc = read_back(t, &hnonfinite, dnonfinite, 4);
     if (rc) return rc;
     if (hnonfinite) { *nonfinite = true; redo.resize((size_t)nq); for (int64_t q = 0; q < nq; q++) redo[(size_t)q] = (int)q; return MO_RC_SUCCESS; }
-    // gathered A operand: one row per (query, probe rank) pair, pairs of a list contiguous
-    A.kprime = Aq.kprime;
-    A.bf = (__nv_bfloat16 *)arena_alloc(t, (size_t)plan.npairs * A.kprime * 2 + 1024);
-    A.norm = (float *)arena_alloc(t, (size_t)plan.npairs * 4);
-    if (!A.bf || !A.norm) return MO_RC_INTERNAL_ERROR;
-    gather_split_rows_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(Aq.bf, Aq.norm, plan.bucket_q, plan.npairs, A.kprime, A.bf, A.norm);
-    MOB_LAUNCH_CHECK();
     std::vector<TcUnit> units;
     for (int64_t l = 0; l < nlist; l++) {
         const int c = plan.hcnt[(size_t)l];
@@ -881,11 +957,16 @@ int ivf_tc_scan(ThreadCtx &t, const IvfPlan &plan, const float *ddata, int64_t n
             }
     }
     float *part_d, *part_thr; int *part_i;
-    rc = tc_run_units(t, A, plan.npairs, B, n, units, plan.npairs * split, &part_d, &part_i, &part_thr, !refine);
+    // one-term pass: the looser bound needs the list threshold further from the k-th result -> 32 candidates per (query, list).
+    // (Measured alternative: two half-lists of 16 each made the kernel 16 % faster but left a few queries to the refine pass, whose
+    // fixed cost outweighs that.)
+    const int kp = one_term ? KP_LONG : KP;
+    rc = tc_run_units(t, A, plan.npairs, B, n, units, plan.npairs * split, &part_d, &part_i, &part_thr, !refine, false, one_term ? (dim + BK - 1) / BK : 0, kp);
     if (rc) return rc;
     // the approximate lists are indexed by bucket position; tc_finish walks them per query through pair_pos; the final keys are
-    // the primary keys row_ids[local row] and Aq.norm holds |q|^2 per query
-    rc = tc_finish(t, ddata, n, dim, dq, nq, k, plan.nprobe * split, plan.pair_pos, plan.nprobe, plan.npairs, part_d, part_i, part_thr, Aq.norm, B.norm, drowids, 0, sqrt_out, ok, od, redo);
+    // the primary keys row_ids[local row]; every probed list's exclusion bound is lowered by the error bound of ITS operand pair
+    rc = tc_finish(t, ddata, n, dim, dq, nq, k, plan.nprobe * split, plan.pair_pos, plan.nprobe, plan.npairs, part_d, part_i, part_thr, nullptr, B.norm, drowids, 0,
+                   sqrt_out, ok, od, redo, nullptr, one_term ? B.lonorm : nullptr, A.norm, A.lonorm, kp);
     return rc;
 }
 
@@ -914,6 +995,38 @@ int32_t MoB200_SearchPrepare(const void *data, uint64_t n, int64_t dim) {
     if (!rc && cudaMemsetAsync(dnonfinite, 0, 4, t.stream) != cudaSuccess) rc = MO_RC_INTERNAL_ERROR;
     if (!rc) {
         split_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(e.x, e.n, e.dim, e.op.kprime, 1, e.op.bf, e.op.norm, e.op.lonorm, dnonfinite);
+        g_launches++;
+        if (cudaGetLastError() != cudaSuccess) rc = MO_RC_INTERNAL_ERROR;
+    }
+    if (!rc) rc = read_back(t, &hnonfinite, dnonfinite, 4);
+    arena_reset(t);
+    if (rc || hnonfinite) { cudaFree(e.op.bf); cudaFree(e.op.norm); return rc; }
+    std::lock_guard<std::mutex> lk(g_prepared_mu);
+    g_prepared.push_back(e);
+    return MO_RC_SUCCESS;
+}
+
+// Index load for an IVF-flat index: the list-ordered entries [n][dim] are split as RESIDUALS against their list's centroid
+// (centroids [nlist][dim], offsets [nlist + 1] int64; all device pointers).  Same contract as MoB200_SearchPrepare.
+int32_t MoB200_SearchPrepareIvf(const void *data, uint64_t n, int64_t dim, const void *centroids, uint64_t nlist, const void *offsets) {
+    using namespace mob;
+    ThreadCtx &t = tctx();
+    if (!t.ready) return MO_RC_INTERNAL_ERROR;
+    if (!data || n == 0 || dim < 16 || n >= (1ull << 31) - BN || nlist == 0) return MO_RC_SUCCESS;
+    if (!is_device_ptr(data) || !is_device_ptr(centroids) || !is_device_ptr(offsets)) { set_error("SearchPrepareIvf: entries, centroids and offsets must be device memory"); return MO_RC_INVALID_ARGUMENT; }
+    MoB200_SearchRelease(data);
+    PreparedOperand e; e.x = (const float *)data; e.n = (int64_t)n; e.dim = (int)dim; e.device = 0; e.cent = (const float *)centroids; e.nlist = (int64_t)nlist;
+    e.op.kprime = ((3 * (int)dim + BK - 1) / BK) * BK;
+    MOB_CUDA_TRY(cudaMalloc((void **)&e.op.bf, (size_t)n * e.op.kprime * 2 + 1024));
+    if (cudaMalloc((void **)&e.op.norm, (size_t)n * 8) != cudaSuccess) { cudaFree(e.op.bf); set_error("SearchPrepareIvf: out of device memory"); return MO_RC_INTERNAL_ERROR; }
+    e.op.lonorm = e.op.norm + n;
+    int *dnonfinite = (int *)arena_alloc(t, 4);
+    int hnonfinite = 1;
+    int rc = dnonfinite ? MO_RC_SUCCESS : MO_RC_INTERNAL_ERROR;
+    if (!rc && cudaMemsetAsync(dnonfinite, 0, 4, t.stream) != cudaSuccess) rc = MO_RC_INTERNAL_ERROR;
+    if (!rc) {
+        split_residual_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(e.x, e.n, e.dim, e.op.kprime, 1, e.cent, (const int64_t *)offsets, e.nlist, nullptr, nullptr,
+                                                                   e.op.bf, e.op.norm, e.op.lonorm, dnonfinite);
         g_launches++;
         if (cudaGetLastError() != cudaSuccess) rc = MO_RC_INTERNAL_ERROR;
     }

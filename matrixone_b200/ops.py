@@ -194,8 +194,8 @@ class IvfflatSearchIndex:
         self.d_cent = DeviceBuffer.from_numpy(centroids, self.lib)
         self.d_off = DeviceBuffer.from_numpy(self.offsets, self.lib)
         self.prepared = self.metric in (capi.METRIC_L2, capi.METRIC_L2SQ) and self.n > 0
-        if self.prepared:   # LoadIndex: the list-ordered entries are split into the tensor-core operand once
-            capi.check(self.lib.MoB200_SearchPrepare(self.d_data.ptr, self.n, self.dim), self.lib)
+        if self.prepared:   # LoadIndex: the list-ordered entries are split (as residuals against their centroid) once
+            capi.check(self.lib.MoB200_SearchPrepareIvf(self.d_data.ptr, self.n, self.dim, self.d_cent.ptr, self.nlist, self.d_off.ptr), self.lib)
 
     @classmethod
     def build(cls, data_dev, n, centroids, metric=capi.METRIC_L2, lib=None, chunk=500_000):

@@ -181,7 +181,8 @@ def test_tensor_core_path_non_finite_inputs_use_exact_kernel(gpu):
 @pytest.mark.parametrize("sqrt_out", [False, True])
 @pytest.mark.parametrize("nlist,dim,n,nq,k,nprobe", [(64, 96, 20_000, 150, 10, 8), (32, 768, 6_000, 300, 10, 32), (16, 100, 3_000, 64, 5, 3),
                                                     (1024, 64, 30_000, 300, 10, 32), (300, 64, 9_000, 200, 4, 9)])   # probe itself on the tensor cores
-def test_ivf_tensor_core_scan_is_exact(gpu, nlist, dim, n, nq, k, nprobe, sqrt_out):
+@pytest.mark.parametrize("ladder,prepared", [(1, True), (2, True), (2, False)])   # three-term only / one-term level first; operand split at load or per call
+def test_ivf_tensor_core_scan_is_exact(gpu, nlist, dim, n, nq, k, nprobe, sqrt_out, ladder, prepared):
     """IVF list scan through the tcgen05 candidate kernel ((list, query-tile) units over gathered split operands): exact results"""
     centers = datagen.vectors_f32(30, 0, nlist, dim) * 4
     data = datagen.vectors_f32(31, 0, n, dim, centers, 1.0)
@@ -192,12 +193,17 @@ def test_ivf_tensor_core_scan_is_exact(gpu, nlist, dim, n, nq, k, nprobe, sqrt_o
     okeys = np.zeros(nq * k, dtype=np.int64); odists = np.zeros(nq * k)
     O.go().og_ivf_search_f32(O.p(data), O.p(assign), n, dim, O.p(centers), nlist, O.p(qs), nq, nprobe, k, 0, int(sqrt_out), 8, O.p(okeys), O.p(odists))
     idx = ops.IvfflatSearchIndex(data, assign, centers)
+    if not prepared:
+        gpu.MoB200_SearchRelease(idx.d_data.ptr)
+        idx.prepared = False
     try:
         gpu.MoB200_SetTuning(b"search_mode", 2)
+        gpu.MoB200_SetTuning(b"tc_ladder", ladder)
         keys, dists = idx.search(qs, k, nprobe, sqrt_out)
         fallbacks = gpu.MoB200_SetTuning(b"get_tc_fallbacks", 0)
     finally:
         gpu.MoB200_SetTuning(b"search_mode", 0)
+        gpu.MoB200_SetTuning(b"tc_ladder", 0)
         idx.destroy()
     _check_topk(keys, dists, okeys, odists, nq, k)
     assert dists.reshape(nq, k)[:5, 0].tolist() == [0.0] * 5
