@@ -8,11 +8,13 @@
 //              cosine_similarity evaluate per row).  BIT-EXACT: the accumulator has the element type and the
 //              8-way (cosine: 4-way) unrolled association of the Go source is reproduced operation by operation.
 //
-// Mapping: one warp per row.  Lane l computes the partial sums of chunks l, l+32, ... (a chunk = 8 consecutive
-// elements = 2 x 128-bit loads per operand, so a warp instruction reads 512 contiguous bytes of the row); the
-// serial "sum += chunk" chain of the Go loop is then replayed in chunk order with warp shuffles (every lane keeps
-// the same running sum).  3 KB rows stream at HBM rate: algorithmic bytes per row = 2 * dim * sizeof(T) (one side
-// const: dim * sizeof(T)) + 24 per varlena cell + 8 for the result.
+// Mapping: LANE per row, warp-transposed.  A warp takes 32 consecutive rows; it copies one 128-byte slice of each of them per
+// step with cp.async (16 bytes per lane per instruction, 8 lanes cover a row slice: fully coalesced, no registers held while
+// the bytes are in flight) into a per-warp shared-memory ring, and every lane then walks ITS row's slice serially in exactly
+// the order of the Go loop -- no shuffles, ~100 warp instructions per row instead of ~520 (one warp per row replayed the
+// serial `sum += chunk` chain with 96 shuffle+add pairs and was instruction/MIO-bound at 0.55 of the HBM rate; cosine with
+// its three chains at 0.19).  The ring (5 stages, or 3 when both operands are per-row) is what keeps ~128 KB per SM in flight.
+// Algorithmic bytes per row = 2 * dim * sizeof(T) (one side const: dim * sizeof(T)) + 24 per varlena cell + 8 for the result.
 #include "common.cuh"
 #include "godist.cuh"
 #include <cstring>
@@ -21,7 +23,7 @@ using namespace mob;
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 128;   // 4 warps; every warp owns a shared-memory ring
 
 enum Kind { K_XC_L2 = 0, K_XC_L2SQ, K_GO_L2, K_GO_L2SQ, K_GO_IP, K_GO_COSDIST, K_GO_COSSIM };
 constexpr unsigned ST_DIM = 1u, ST_AREA = 2u, ST_ZERO = 4u;
@@ -45,92 +47,221 @@ __device__ __forceinline__ Ref varlena_ref(const uint8_t *cells, uint64_t i, con
 
 using namespace mob::godist;
 
-// xcall.c:55-75: float diff, (double)(diff*diff) accumulated in double
-template <typename T>
-__device__ double xc_l2sq(const uint8_t *p, const uint8_t *q, int dim, int lane, bool al, bool sp, bool sq) {
-    constexpr int V = 16 / sizeof(T);
-    double s = 0.0;
-    const int nv = dim / V;
-    for (int v = lane; v < nv; v += 32) {
-        T a[V], b[V];
-        load_elems<T, V>(p + (size_t)v * 16, a, al, sp);
-        load_elems<T, V>(q + (size_t)v * 16, b, al, sq);
+constexpr int kTileRows = 32, kSliceBytes = 128, kPitch = 144;   // 144-byte row pitch: LDS.128 by the row owners is conflict-free
+constexpr int kTileBytes = kTileRows * kPitch;
+template <bool TWO> struct RingCfg {
+    static constexpr int kStages = TWO ? 3 : 5;
+    static constexpr int kStageBytes = TWO ? 2 * kTileBytes : kTileBytes + kPitch;   // [row tile][second row tile | const slice]
+};
+
+__device__ __forceinline__ void cp_async16(unsigned dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ const uint8_t *shfl_ptr(const uint8_t *p, int src) {
+    unsigned long long v = (unsigned long long)(uintptr_t)p;
+    unsigned lo = __shfl_sync(FULL, (unsigned)v, src), hi = __shfl_sync(FULL, (unsigned)(v >> 32), src);
+    return (const uint8_t *)(uintptr_t)(((unsigned long long)hi << 32) | lo);
+}
+// 16 bytes global -> shared for a row whose base is not 16-byte aligned (byte loads: varlena offsets are arbitrary)
+__device__ __forceinline__ void copy16_unaligned(unsigned char *dst, const uint8_t *src) {
 #pragma unroll
-        for (int j = 0; j < V; j++) { T d = sub_rn(a[j], b[j]); s = __dadd_rn(s, (double)mul_rn(d, d)); }
-    }
-    for (int i = nv * V + lane; i < dim; i += 32) {
-        T d = sub_rn(load1<T>(p + (size_t)i * sizeof(T)), load1<T>(q + (size_t)i * sizeof(T)));
-        s = __dadd_rn(s, (double)mul_rn(d, d));
-    }
-    return warp_sum_f64(s);
+    for (int k = 0; k < 16; k++) dst[k] = src[k];
 }
 
-template <typename T, int KIND>
+// per-row accumulators of one kind; add_slice consumes EPS = 128 / sizeof(T) consecutive elements of both operands
+template <typename T, int KIND> struct RowAcc {
+    static constexpr bool kCos = KIND == K_GO_COSDIST || KIND == K_GO_COSSIM;
+    static constexpr bool kXc = KIND == K_XC_L2 || KIND == K_XC_L2SQ;
+    static constexpr int CH = kCos ? 4 : 8;          // chunk of the Go loop (distance_func.go: 8-way, cosine 4-way)
+    T sum = 0, n1 = 0, n2 = 0; double dsum = 0.0;
+    __device__ __forceinline__ void chunk(const T *a, const T *b) {   // CH elements, exact association of the Go source
+        if (kXc) {
+#pragma unroll
+            for (int j = 0; j < CH; j++) { T d = sub_rn(a[j], b[j]); dsum = __dadd_rn(dsum, (double)mul_rn(d, d)); }
+        } else if (kCos) {
+            sum = add_rn(sum, add_rn(add_rn(add_rn(mul_rn(a[0], b[0]), mul_rn(a[1], b[1])), mul_rn(a[2], b[2])), mul_rn(a[3], b[3])));
+            n1 = add_rn(n1, add_rn(add_rn(add_rn(mul_rn(a[0], a[0]), mul_rn(a[1], a[1])), mul_rn(a[2], a[2])), mul_rn(a[3], a[3])));
+            n2 = add_rn(n2, add_rn(add_rn(add_rn(mul_rn(b[0], b[0]), mul_rn(b[1], b[1])), mul_rn(b[2], b[2])), mul_rn(b[3], b[3])));
+        } else if (KIND == K_GO_IP) {
+            T c = add_rn(mul_rn(a[0], b[0]), mul_rn(a[1], b[1]));
+#pragma unroll
+            for (int j = 2; j < 8; j++) c = add_rn(c, mul_rn(a[j], b[j]));
+            sum = add_rn(sum, c);
+        } else {
+            T t[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) { T d = sub_rn(a[j], b[j]); t[j] = mul_rn(d, d); }
+            sum = add_rn(sum, add_rn(add_rn(add_rn(add_rn(t[0], t[1]), add_rn(t[2], t[3])), add_rn(t[4], t[5])), add_rn(t[6], t[7])));
+        }
+    }
+    __device__ __forceinline__ void elem(T a, T b) {   // remainder loops of the Go functions
+        if (kXc) { T d = sub_rn(a, b); dsum = __dadd_rn(dsum, (double)mul_rn(d, d)); }
+        else if (kCos) { sum = add_rn(sum, mul_rn(a, b)); n1 = add_rn(n1, mul_rn(a, a)); n2 = add_rn(n2, mul_rn(b, b)); }
+        else if (KIND == K_GO_IP) sum = add_rn(sum, mul_rn(a, b));
+        else { T d = sub_rn(a, b); sum = add_rn(sum, mul_rn(d, d)); }
+    }
+};
+
+template <typename T, int KIND, bool TWO>
 __global__ void __launch_bounds__(kThreads)
 rowdist_kernel(double *__restrict__ res, const uint64_t *__restrict__ rnulls, uint64_t n,
                const uint8_t *__restrict__ cells1, const uint8_t *__restrict__ area1, uint64_t area1Sz, bool const1,
                const uint8_t *__restrict__ cells2, const uint8_t *__restrict__ area2, uint64_t area2Sz, bool const2,
                unsigned *status) {
-    const int lane = threadIdx.x & 31;
+    using Cfg = RingCfg<TWO>;
+    using Acc = RowAcc<T, KIND>;
+    constexpr int NST = Cfg::kStages, EPS = kSliceBytes / (int)sizeof(T), CH = Acc::CH;
+    extern __shared__ __align__(16) unsigned char dist_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    unsigned char *ring = dist_smem + (size_t)wib * NST * Cfg::kStageBytes;
+    const unsigned ring_u32 = (unsigned)__cvta_generic_to_shared(ring);
     const uint64_t warp = (blockIdx.x * (uint64_t)kThreads + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * kThreads) >> 5;
     int xc_dim = 0;
-    if (KIND == K_XC_L2 || KIND == K_XC_L2SQ) {  // dim = c1.len / sizeof(T) from the FIRST cell of arg 1, xcall.c:40,55
+    if (Acc::kXc) {  // dim = c1.len / sizeof(T) from the FIRST cell of arg 1, xcall.c:40,55
         Ref r0 = varlena_ref(cells1, 0, area1, area1Sz);
         xc_dim = r0.ok ? (int)(r0.len / sizeof(T)) : 0;
     }
+    // the per-row ("x") side is arg 1 unless only arg 1 is const; every kind is symmetric in its operands bit for bit
+    // ((a-b)^2 == (b-a)^2, products commute, the cosine denominator sqrt(n1)*sqrt(n2) commutes)
+    const bool swap = !TWO && const1 && !const2;
+    const int piece = lane & 7, rgrp = lane >> 3;
     unsigned st = 0;
-    for (uint64_t i = warp; i < n; i += nwarps) {
-        if (bm_test(rnulls, i)) continue;
-        Ref a = varlena_ref(cells1, const1 ? 0 : i, area1, area1Sz);
-        Ref b = varlena_ref(cells2, const2 ? 0 : i, area2, area2Sz);
-        if (!a.ok || !b.ok) { st |= ST_AREA; continue; }
-        int dim;
-        if (KIND == K_XC_L2 || KIND == K_XC_L2SQ) {
-            dim = xc_dim;
-            if ((uint64_t)dim * sizeof(T) > a.len || (uint64_t)dim * sizeof(T) > b.len) { st |= ST_DIM; continue; }  // would read out of bounds
-        } else {
-            if (a.len != b.len) { st |= ST_DIM; continue; }  // moerr.NewArrayInvalidOpNoCtx, external.go:182-184
-            dim = (int)(a.len / sizeof(T));
-        }
-        const bool al = ((((uintptr_t)a.ptr) | ((uintptr_t)b.ptr)) & 15) == 0;
-        const bool sa = !const1, sb = !const2;  // const side is re-read by every row: keep it cached
-        double out;
-        if (KIND == K_XC_L2 || KIND == K_XC_L2SQ) {
-            double s = xc_l2sq<T>(a.ptr, b.ptr, dim, lane, al, sa, sb);
-            out = KIND == K_XC_L2 ? sqrt(s) : s;
-        } else if (KIND == K_GO_L2SQ) {
-            out = (double)go_l2sq<T>(a.ptr, b.ptr, dim, lane, al, sa, sb);
-        } else if (KIND == K_GO_L2) {
-            out = (double)(T)sqrt((double)go_l2sq<T>(a.ptr, b.ptr, dim, lane, al, sa, sb));  // distance_func.go:35-42
-        } else if (KIND == K_GO_IP) {
-            out = (double)go_ip<T>(a.ptr, b.ptr, dim, lane, al, sa, sb);
-        } else {
-            T dp, n1, n2;
-            go_cos_parts<T>(a.ptr, b.ptr, dim, lane, al, sa, sb, dp, n1, n2);
-            const double den = sqrt((double)n1) * sqrt((double)n2);
-            if (KIND == K_GO_COSDIST) {
-                if (dim == 0) out = 0.0;
-                else if (den == 0.0) out = (double)(T)1.0;        // distance_func.go:268-271
-                else {
-                    double sim = (double)dp / den;
-                    sim = sim > 1.0 ? 1.0 : (sim < -1.0 ? -1.0 : sim);
-                    out = (double)(T)(1.0 - sim);
-                }
+    for (uint64_t base = warp * 32; base < n; base += nwarps * 32) {
+        const uint64_t i = base + lane;
+        const bool live = i < n && !bm_test(rnulls, i);
+        int dim = 0; bool good = false;
+        const uint8_t *px = nullptr, *pq = nullptr;
+        if (live) {
+            Ref a = varlena_ref(cells1, const1 ? 0 : i, area1, area1Sz);
+            Ref b = varlena_ref(cells2, const2 ? 0 : i, area2, area2Sz);
+            if (!a.ok || !b.ok) st |= ST_AREA;
+            else if (Acc::kXc) {
+                if ((uint64_t)xc_dim * sizeof(T) > a.len || (uint64_t)xc_dim * sizeof(T) > b.len) st |= ST_DIM;   // would read out of bounds
+                else { dim = xc_dim; good = true; }
             } else {
-                if (dim == 0) out = 0.0;
-                else if (den == 0.0) { st |= ST_ZERO; continue; }   // "one of the vector is zero", distance_func.go:342-345
-                else {
-                    double sim = (double)dp / den;
-                    sim = sim > 1.0 ? 1.0 : (sim < -1.0 ? -1.0 : sim);
-                    double c = (double)(T)sim;
-                    const float f = (float)c;                        // moarray.CosineSimilarity snap, external.go:252-257
-                    if (f == 1.0f) c = 1.0; else if (f == -1.0f) c = -1.0;
-                    out = c;
+                if (a.len != b.len) st |= ST_DIM;   // moerr.NewArrayInvalidOpNoCtx, external.go:182-184
+                else { dim = (int)(a.len / sizeof(T)); good = true; }
+            }
+            px = swap ? b.ptr : a.ptr; pq = swap ? a.ptr : b.ptr;
+        }
+        if (!good) dim = 0;
+        const int nfull = (dim / CH) * CH;                                  // elements covered by whole chunks
+        const int nsl = (int)(((size_t)nfull * sizeof(T)) / kSliceBytes);    // whole 128-byte slices of this row
+        const bool alx = (((uintptr_t)px) & 15) == 0, alq = (((uintptr_t)pq) & 15) == 0;
+        const int maxsl = __reduce_max_sync(FULL, nsl);
+        // loader view: this lane copies piece `piece` of rows rgrp, rgrp + 4, ..., rgrp + 28
+        const uint8_t *lx[8], *lq[8]; int lnsl[8]; unsigned lal = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int rr = rgrp + 4 * k;
+            lx[k] = shfl_ptr(px, rr); lnsl[k] = __shfl_sync(FULL, nsl, rr);
+            if (__shfl_sync(FULL, (int)alx, rr)) lal |= 1u << k;
+            if (TWO) { lq[k] = shfl_ptr(pq, rr); if (__shfl_sync(FULL, (int)alq, rr)) lal |= 1u << (8 + k); }
+        }
+        // the const side: taken from the first row that has one (all rows share it)
+        const unsigned goodmask = __ballot_sync(FULL, good);
+        const int qsrc = goodmask ? __ffs((int)goodmask) - 1 : 0;
+        const uint8_t *cq = TWO ? nullptr : shfl_ptr(pq, qsrc);
+        const bool cq_al = TWO ? false : (__shfl_sync(FULL, (int)alq, qsrc) != 0);
+
+        auto issue = [&](int s) {   // slice s of every row -> stage s % NST; always commits one group
+            if (s < maxsl) {
+                const unsigned sb = ring_u32 + (unsigned)((s % NST) * Cfg::kStageBytes);
+                unsigned char *sp = ring + (size_t)(s % NST) * Cfg::kStageBytes;
+                const size_t off = (size_t)s * kSliceBytes + (size_t)piece * 16;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int rr = rgrp + 4 * k;
+                    if (s < lnsl[k]) {
+                        if (lal & (1u << k)) cp_async16(sb + rr * kPitch + piece * 16, lx[k] + off);
+                        else copy16_unaligned(sp + rr * kPitch + piece * 16, lx[k] + off);
+                        if (TWO) {
+                            if (lal & (1u << (8 + k))) cp_async16(sb + kTileBytes + rr * kPitch + piece * 16, lq[k] + off);
+                            else copy16_unaligned(sp + kTileBytes + rr * kPitch + piece * 16, lq[k] + off);
+                        }
+                    }
+                }
+                if (!TWO && lane < 8) {
+                    if (cq_al) cp_async16(sb + kTileBytes + lane * 16, cq + (size_t)s * kSliceBytes + (size_t)lane * 16);
+                    else copy16_unaligned(sp + kTileBytes + lane * 16, cq + (size_t)s * kSliceBytes + (size_t)lane * 16);
                 }
             }
+            cp_async_commit();
+        };
+
+        Acc acc;
+#pragma unroll 1
+        for (int s = 0; s < NST - 1; s++) issue(s);
+#pragma unroll 1
+        for (int s = 0; s < maxsl; s++) {
+            issue(s + NST - 1);            // its stage was consumed in the previous iteration (ordered by the __syncwarp below)
+            cp_async_wait<NST - 1>();      // all but the NST - 1 newest groups are complete => slice s has landed
+            __syncwarp();
+            if (s < nsl) {
+                const unsigned char *sp = ring + (size_t)(s % NST) * Cfg::kStageBytes;
+                const unsigned char *ra = sp + lane * kPitch;
+                const unsigned char *rb = TWO ? sp + kTileBytes + lane * kPitch : sp + kTileBytes;   // const slice: broadcast reads
+#pragma unroll
+                for (int h = 0; h < 2; h++) {     // half a slice at a time keeps the register footprint down
+                    T a[EPS / 2], b[EPS / 2];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int4 va = *reinterpret_cast<const int4 *>(ra + h * 64 + j * 16);
+                        const int4 vb = *reinterpret_cast<const int4 *>(rb + h * 64 + j * 16);
+                        memcpy(reinterpret_cast<char *>(a) + 16 * j, &va, 16);
+                        memcpy(reinterpret_cast<char *>(b) + 16 * j, &vb, 16);
+                    }
+#pragma unroll
+                    for (int c = 0; c < EPS / 2; c += CH) acc.chunk(a + c, b + c);
+                }
+            }
+            __syncwarp();
         }
-        if (lane == 0) res[i] = out;
+        cp_async_wait<0>();
+        // every lane finishes its own row: whole chunks past the last full slice, then the element remainder loop
+        if (good) {
+            const bool al = alx && alq;
+            for (int c = nsl * EPS; c < nfull; c += CH) {
+                T a[CH], b[CH];
+                load_elems<T, CH>(px + (size_t)c * sizeof(T), a, al && CH * sizeof(T) >= 16, false);
+                load_elems<T, CH>(pq + (size_t)c * sizeof(T), b, al && CH * sizeof(T) >= 16, false);
+                acc.chunk(a, b);
+            }
+            for (int e = nfull; e < dim; e++) acc.elem(load1<T>(px + (size_t)e * sizeof(T)), load1<T>(pq + (size_t)e * sizeof(T)));
+            double out; bool write = true;
+            if (KIND == K_XC_L2) out = sqrt(acc.dsum);
+            else if (KIND == K_XC_L2SQ) out = acc.dsum;
+            else if (KIND == K_GO_L2SQ) out = (double)acc.sum;
+            else if (KIND == K_GO_L2) out = (double)(T)sqrt((double)acc.sum);  // distance_func.go:35-42
+            else if (KIND == K_GO_IP) out = (double)(-acc.sum);               // InnerProduct returns -sum, distance_func.go:172-205
+            else {
+                const double den = sqrt((double)acc.n1) * sqrt((double)acc.n2);
+                if (KIND == K_GO_COSDIST) {
+                    if (dim == 0) out = 0.0;
+                    else if (den == 0.0) out = (double)(T)1.0;        // distance_func.go:268-271
+                    else {
+                        double sim = (double)acc.sum / den;
+                        sim = sim > 1.0 ? 1.0 : (sim < -1.0 ? -1.0 : sim);
+                        out = (double)(T)(1.0 - sim);
+                    }
+                } else {
+                    if (dim == 0) out = 0.0;
+                    else if (den == 0.0) { st |= ST_ZERO; write = false; out = 0.0; }   // "one of the vector is zero", distance_func.go:342-345
+                    else {
+                        double sim = (double)acc.sum / den;
+                        sim = sim > 1.0 ? 1.0 : (sim < -1.0 ? -1.0 : sim);
+                        double c = (double)(T)sim;
+                        const float f = (float)c;                        // moarray.CosineSimilarity snap, external.go:252-257
+                        if (f == 1.0f) c = 1.0; else if (f == -1.0f) c = -1.0;
+                        out = c;
+                    }
+                }
+            }
+            if (write) res[i] = out;
+        }
     }
     st = __reduce_or_sync(FULL, st);
     if (lane == 0 && st) atomicOr(status, st);
@@ -154,11 +285,19 @@ int run_rowdist(mo_xcall_args_t *args, uint64_t len) {
     unsigned *dstatus = (unsigned *)st.tmp(4);
     if (st.failed) { st.finish(); return MO_RC_INTERNAL_ERROR; }
     MOB_CUDA_TRY(cudaMemsetAsync(dstatus, 0, 4, t.stream));
-    uint64_t blocks = (len * 32 + kThreads - 1) / kThreads;
-    const uint64_t cap = (uint64_t)num_sms() * 8;
+    const bool two = !c1 && !c2;
+    const uint64_t warps = (len + 31) / 32;
+    uint64_t blocks = (warps + kThreads / 32 - 1) / (kThreads / 32);
+    const uint64_t cap = (uint64_t)num_sms() * 2;   // 2 CTAs per SM by shared memory (95 / 111 KB each)
     if (blocks > cap) blocks = cap;
-    rowdist_kernel<T, KIND><<<(unsigned)blocks, kThreads, 0, t.stream>>>(res, rn, len, cells1, area1, args[1].areaSz, c1,
-                                                                         cells2, area2, args[2].areaSz, c2, dstatus);
+    const size_t smem = (size_t)(kThreads / 32) * (two ? RingCfg<true>::kStages * RingCfg<true>::kStageBytes : RingCfg<false>::kStages * RingCfg<false>::kStageBytes);
+    static bool attr1 = false, attr2 = false;
+    if (two && !attr2) { MOB_CUDA_TRY(cudaFuncSetAttribute(rowdist_kernel<T, KIND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr2 = true; }
+    if (!two && !attr1) { MOB_CUDA_TRY(cudaFuncSetAttribute(rowdist_kernel<T, KIND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr1 = true; }
+    cudaEventRecord(t.kev0, t.stream);
+    if (two) rowdist_kernel<T, KIND, true><<<(unsigned)blocks, kThreads, smem, t.stream>>>(res, rn, len, cells1, area1, args[1].areaSz, c1, cells2, area2, args[2].areaSz, c2, dstatus);
+    else rowdist_kernel<T, KIND, false><<<(unsigned)blocks, kThreads, smem, t.stream>>>(res, rn, len, cells1, area1, args[1].areaSz, c1, cells2, area2, args[2].areaSz, c2, dstatus);
+    cudaEventRecord(t.kev1, t.stream);
     MOB_LAUNCH_CHECK();
     unsigned status = 0;
     int rc = read_back(t, &status, dstatus, 4);

@@ -50,6 +50,12 @@ def test_go_semantics_distances_bit_exact(gpu, dim, dt):
             assert (res == want).all(), (kind, dim, const, np.abs(res - want).max())
             if kind in (0, 4) and not const:
                 assert res[7] == 0.0
+        # const FIRST argument (the kernel swaps the operand roles internally; the result must equal f(a0, b_i) evaluated in that order)
+        want = _go_rows(kind, np.repeat(a[:1], n, axis=0), b)
+        res = np.zeros(n)
+        va = _cols(a[:1]); va.const = True
+        xcall(fid, [Vector(data=res, length=n), va, _cols(b)], n)
+        assert (res == want).all(), (kind, dim, "const-first", np.abs(res - want).max())
 
 
 def test_reference_golden_vectors_through_xcall(gpu):
