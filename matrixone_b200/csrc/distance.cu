@@ -25,7 +25,6 @@ namespace {
 
 constexpr int kThreads = 128;   // 4 warps; every warp owns a shared-memory ring
 
-enum Kind { K_XC_L2 = 0, K_XC_L2SQ, K_GO_L2, K_GO_L2SQ, K_GO_IP, K_GO_COSDIST, K_GO_COSSIM };
 constexpr unsigned ST_DIM = 1u, ST_AREA = 2u, ST_ZERO = 4u;
 
 struct Ref { const uint8_t *ptr; uint32_t len; bool ok; };
@@ -47,63 +46,6 @@ __device__ __forceinline__ Ref varlena_ref(const uint8_t *cells, uint64_t i, con
 
 using namespace mob::godist;
 
-constexpr int kTileRows = 32, kSliceBytes = 128, kPitch = 144;   // 144-byte row pitch: LDS.128 by the row owners is conflict-free
-constexpr int kTileBytes = kTileRows * kPitch;
-template <bool TWO> struct RingCfg {
-    static constexpr int kStages = TWO ? 3 : 5;
-    static constexpr int kStageBytes = TWO ? 2 * kTileBytes : kTileBytes + kPitch;   // [row tile][second row tile | const slice]
-};
-
-__device__ __forceinline__ void cp_async16(unsigned dst, const void *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ const uint8_t *shfl_ptr(const uint8_t *p, int src) {
-    unsigned long long v = (unsigned long long)(uintptr_t)p;
-    unsigned lo = __shfl_sync(FULL, (unsigned)v, src), hi = __shfl_sync(FULL, (unsigned)(v >> 32), src);
-    return (const uint8_t *)(uintptr_t)(((unsigned long long)hi << 32) | lo);
-}
-// 16 bytes global -> shared for a row whose base is not 16-byte aligned (byte loads: varlena offsets are arbitrary)
-__device__ __forceinline__ void copy16_unaligned(unsigned char *dst, const uint8_t *src) {
-#pragma unroll
-    for (int k = 0; k < 16; k++) dst[k] = src[k];
-}
-
-// per-row accumulators of one kind; add_slice consumes EPS = 128 / sizeof(T) consecutive elements of both operands
-template <typename T, int KIND> struct RowAcc {
-    static constexpr bool kCos = KIND == K_GO_COSDIST || KIND == K_GO_COSSIM;
-    static constexpr bool kXc = KIND == K_XC_L2 || KIND == K_XC_L2SQ;
-    static constexpr int CH = kCos ? 4 : 8;          // chunk of the Go loop (distance_func.go: 8-way, cosine 4-way)
-    T sum = 0, n1 = 0, n2 = 0; double dsum = 0.0;
-    __device__ __forceinline__ void chunk(const T *a, const T *b) {   // CH elements, exact association of the Go source
-        if (kXc) {
-#pragma unroll
-            for (int j = 0; j < CH; j++) { T d = sub_rn(a[j], b[j]); dsum = __dadd_rn(dsum, (double)mul_rn(d, d)); }
-        } else if (kCos) {
-            sum = add_rn(sum, add_rn(add_rn(add_rn(mul_rn(a[0], b[0]), mul_rn(a[1], b[1])), mul_rn(a[2], b[2])), mul_rn(a[3], b[3])));
-            n1 = add_rn(n1, add_rn(add_rn(add_rn(mul_rn(a[0], a[0]), mul_rn(a[1], a[1])), mul_rn(a[2], a[2])), mul_rn(a[3], a[3])));
-            n2 = add_rn(n2, add_rn(add_rn(add_rn(mul_rn(b[0], b[0]), mul_rn(b[1], b[1])), mul_rn(b[2], b[2])), mul_rn(b[3], b[3])));
-        } else if (KIND == K_GO_IP) {
-            T c = add_rn(mul_rn(a[0], b[0]), mul_rn(a[1], b[1]));
-#pragma unroll
-            for (int j = 2; j < 8; j++) c = add_rn(c, mul_rn(a[j], b[j]));
-            sum = add_rn(sum, c);
-        } else {
-            T t[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) { T d = sub_rn(a[j], b[j]); t[j] = mul_rn(d, d); }
-            sum = add_rn(sum, add_rn(add_rn(add_rn(add_rn(t[0], t[1]), add_rn(t[2], t[3])), add_rn(t[4], t[5])), add_rn(t[6], t[7])));
-        }
-    }
-    __device__ __forceinline__ void elem(T a, T b) {   // remainder loops of the Go functions
-        if (kXc) { T d = sub_rn(a, b); dsum = __dadd_rn(dsum, (double)mul_rn(d, d)); }
-        else if (kCos) { sum = add_rn(sum, mul_rn(a, b)); n1 = add_rn(n1, mul_rn(a, a)); n2 = add_rn(n2, mul_rn(b, b)); }
-        else if (KIND == K_GO_IP) sum = add_rn(sum, mul_rn(a, b));
-        else { T d = sub_rn(a, b); sum = add_rn(sum, mul_rn(d, d)); }
-    }
-};
-
 template <typename T, int KIND, bool TWO>
 __global__ void __launch_bounds__(kThreads)
 rowdist_kernel(double *__restrict__ res, const uint64_t *__restrict__ rnulls, uint64_t n,
@@ -112,11 +54,10 @@ rowdist_kernel(double *__restrict__ res, const uint64_t *__restrict__ rnulls, ui
                unsigned *status) {
     using Cfg = RingCfg<TWO>;
     using Acc = RowAcc<T, KIND>;
-    constexpr int NST = Cfg::kStages, EPS = kSliceBytes / (int)sizeof(T), CH = Acc::CH;
+    constexpr int NST = Cfg::kStages;
     extern __shared__ __align__(16) unsigned char dist_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     unsigned char *ring = dist_smem + (size_t)wib * NST * Cfg::kStageBytes;
-    const unsigned ring_u32 = (unsigned)__cvta_generic_to_shared(ring);
     const uint64_t warp = (blockIdx.x * (uint64_t)kThreads + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * kThreads) >> 5;
     int xc_dim = 0;
@@ -127,7 +68,6 @@ rowdist_kernel(double *__restrict__ res, const uint64_t *__restrict__ rnulls, ui
     // the per-row ("x") side is arg 1 unless only arg 1 is const; every kind is symmetric in its operands bit for bit
     // ((a-b)^2 == (b-a)^2, products commute, the cosine denominator sqrt(n1)*sqrt(n2) commutes)
     const bool swap = !TWO && const1 && !const2;
-    const int piece = lane & 7, rgrp = lane >> 3;
     unsigned st = 0;
     for (uint64_t base = warp * 32; base < n; base += nwarps * 32) {
         const uint64_t i = base + lane;
@@ -148,89 +88,8 @@ rowdist_kernel(double *__restrict__ res, const uint64_t *__restrict__ rnulls, ui
             px = swap ? b.ptr : a.ptr; pq = swap ? a.ptr : b.ptr;
         }
         if (!good) dim = 0;
-        const int nfull = (dim / CH) * CH;                                  // elements covered by whole chunks
-        const int nsl = (int)(((size_t)nfull * sizeof(T)) / kSliceBytes);    // whole 128-byte slices of this row
-        const bool alx = (((uintptr_t)px) & 15) == 0, alq = (((uintptr_t)pq) & 15) == 0;
-        const int maxsl = __reduce_max_sync(FULL, nsl);
-        // loader view: this lane copies piece `piece` of rows rgrp, rgrp + 4, ..., rgrp + 28
-        const uint8_t *lx[8], *lq[8]; int lnsl[8]; unsigned lal = 0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const int rr = rgrp + 4 * k;
-            lx[k] = shfl_ptr(px, rr); lnsl[k] = __shfl_sync(FULL, nsl, rr);
-            if (__shfl_sync(FULL, (int)alx, rr)) lal |= 1u << k;
-            if (TWO) { lq[k] = shfl_ptr(pq, rr); if (__shfl_sync(FULL, (int)alq, rr)) lal |= 1u << (8 + k); }
-        }
-        // the const side: taken from the first row that has one (all rows share it)
-        const unsigned goodmask = __ballot_sync(FULL, good);
-        const int qsrc = goodmask ? __ffs((int)goodmask) - 1 : 0;
-        const uint8_t *cq = TWO ? nullptr : shfl_ptr(pq, qsrc);
-        const bool cq_al = TWO ? false : (__shfl_sync(FULL, (int)alq, qsrc) != 0);
-
-        auto issue = [&](int s) {   // slice s of every row -> stage s % NST; always commits one group
-            if (s < maxsl) {
-                const unsigned sb = ring_u32 + (unsigned)((s % NST) * Cfg::kStageBytes);
-                unsigned char *sp = ring + (size_t)(s % NST) * Cfg::kStageBytes;
-                const size_t off = (size_t)s * kSliceBytes + (size_t)piece * 16;
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const int rr = rgrp + 4 * k;
-                    if (s < lnsl[k]) {
-                        if (lal & (1u << k)) cp_async16(sb + rr * kPitch + piece * 16, lx[k] + off);
-                        else copy16_unaligned(sp + rr * kPitch + piece * 16, lx[k] + off);
-                        if (TWO) {
-                            if (lal & (1u << (8 + k))) cp_async16(sb + kTileBytes + rr * kPitch + piece * 16, lq[k] + off);
-                            else copy16_unaligned(sp + kTileBytes + rr * kPitch + piece * 16, lq[k] + off);
-                        }
-                    }
-                }
-                if (!TWO && lane < 8) {
-                    if (cq_al) cp_async16(sb + kTileBytes + lane * 16, cq + (size_t)s * kSliceBytes + (size_t)lane * 16);
-                    else copy16_unaligned(sp + kTileBytes + lane * 16, cq + (size_t)s * kSliceBytes + (size_t)lane * 16);
-                }
-            }
-            cp_async_commit();
-        };
-
-        Acc acc;
-#pragma unroll 1
-        for (int s = 0; s < NST - 1; s++) issue(s);
-#pragma unroll 1
-        for (int s = 0; s < maxsl; s++) {
-            issue(s + NST - 1);            // its stage was consumed in the previous iteration (ordered by the __syncwarp below)
-            cp_async_wait<NST - 1>();      // all but the NST - 1 newest groups are complete => slice s has landed
-            __syncwarp();
-            if (s < nsl) {
-                const unsigned char *sp = ring + (size_t)(s % NST) * Cfg::kStageBytes;
-                const unsigned char *ra = sp + lane * kPitch;
-                const unsigned char *rb = TWO ? sp + kTileBytes + lane * kPitch : sp + kTileBytes;   // const slice: broadcast reads
-#pragma unroll
-                for (int h = 0; h < 2; h++) {     // half a slice at a time keeps the register footprint down
-                    T a[EPS / 2], b[EPS / 2];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const int4 va = *reinterpret_cast<const int4 *>(ra + h * 64 + j * 16);
-                        const int4 vb = *reinterpret_cast<const int4 *>(rb + h * 64 + j * 16);
-                        memcpy(reinterpret_cast<char *>(a) + 16 * j, &va, 16);
-                        memcpy(reinterpret_cast<char *>(b) + 16 * j, &vb, 16);
-                    }
-#pragma unroll
-                    for (int c = 0; c < EPS / 2; c += CH) acc.chunk(a + c, b + c);
-                }
-            }
-            __syncwarp();
-        }
-        cp_async_wait<0>();
-        // every lane finishes its own row: whole chunks past the last full slice, then the element remainder loop
+        Acc acc = row_batch<T, KIND, TWO>(ring, lane, px, pq, dim, good);
         if (good) {
-            const bool al = alx && alq;
-            for (int c = nsl * EPS; c < nfull; c += CH) {
-                T a[CH], b[CH];
-                load_elems<T, CH>(px + (size_t)c * sizeof(T), a, al && CH * sizeof(T) >= 16, false);
-                load_elems<T, CH>(pq + (size_t)c * sizeof(T), b, al && CH * sizeof(T) >= 16, false);
-                acc.chunk(a, b);
-            }
-            for (int e = nfull; e < dim; e++) acc.elem(load1<T>(px + (size_t)e * sizeof(T)), load1<T>(pq + (size_t)e * sizeof(T)));
             double out; bool write = true;
             if (KIND == K_XC_L2) out = sqrt(acc.dsum);
             else if (KIND == K_XC_L2SQ) out = acc.dsum;

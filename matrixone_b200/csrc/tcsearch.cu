@@ -515,20 +515,27 @@ __global__ void tc_merge_kernel(int nq, int R, const float *__restrict__ part_d,
     if (lane == 0) t_excl[q] = t;
 }
 
-// one warp per (query, candidate): the bit-exact Go-order L2sq (godist.cuh)
-__global__ void tc_rescore_kernel(const float *__restrict__ data, const float *__restrict__ queries, int dim, int nq, int kr,
-                                  const int *__restrict__ cand, float *__restrict__ exact) {
-    const int lane = threadIdx.x & 31;
-    const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t p = w; p < (int64_t)nq * kr; p += nw) {
-        const int id = cand[p];
-        float d = INFINITY;
-        if (id >= 0) {
-            const uint8_t *a = reinterpret_cast<const uint8_t *>(queries + (p / kr) * dim), *b = reinterpret_cast<const uint8_t *>(data + (int64_t)id * dim);
-            const bool al = ((((uintptr_t)a) | ((uintptr_t)b)) & 15) == 0;
-            d = godist::go_l2sq<float>(a, b, dim, lane, al, false, true);
-        }
-        if (lane == 0) exact[p] = d;
+// exact re-scoring: one warp per (query, 32 candidates) batch, lane = candidate row, the query is the constant operand: the
+// bit-exact Go-order L2sq through the lane-per-row batch machinery of godist.cuh (rows stream through a per-warp cp.async ring)
+constexpr int kRescoreThreads = 128;
+__global__ void __launch_bounds__(kRescoreThreads)
+tc_rescore_kernel(const float *__restrict__ data, const float *__restrict__ queries, int dim, int nq, int kr,
+                  const int *__restrict__ cand, float *__restrict__ exact) {
+    using Cfg = godist::RingCfg<false>;
+    extern __shared__ __align__(16) unsigned char rescore_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    unsigned char *ring = rescore_smem + (size_t)wib * Cfg::kStages * Cfg::kStageBytes;
+    const int nb = kr / 32;
+    const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = w0; w < (int64_t)nq * nb; w += nw) {
+        const int64_t q = w / nb; const int h = (int)(w % nb);
+        const size_t slot = (size_t)q * kr + (size_t)h * 32 + lane;
+        const int id = cand[slot];
+        const bool good = id >= 0;
+        const uint8_t *px = good ? reinterpret_cast<const uint8_t *>(data + (int64_t)id * dim) : nullptr;
+        const uint8_t *pq = reinterpret_cast<const uint8_t *>(queries + q * dim);
+        const godist::RowAcc<float, godist::K_GO_L2SQ> acc = godist::row_batch<float, godist::K_GO_L2SQ, false>(ring, lane, px, pq, dim, good);
+        exact[slot] = good ? acc.sum : INFINITY;
     }
 }
 
@@ -736,8 +743,15 @@ static int tc_finish(ThreadCtx &t, const float *ddata, int64_t n, int dim, const
     if (R > kMaxMergeLists) { set_error("tc search: %d candidate lists per query exceed the merge limit %d", R, kMaxMergeLists); return MO_RC_INTERNAL_ERROR; }
     tc_merge_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, t.stream>>>((int)nq, R, part_d, part_i, part_thr, pos_map, pos_cols, pos_stride, pair_norm, pair_lonorm, xmax, one_term, kp, kr, cand, t_excl);
     MOB_LAUNCH_CHECK();
-    tc_rescore_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(ddata, dq, dim, (int)nq, kr, cand, exact);
-    MOB_LAUNCH_CHECK();
+    {
+        const size_t smem = (size_t)(kRescoreThreads / 32) * godist::RingCfg<false>::kStages * godist::RingCfg<false>::kStageBytes;
+        static bool attr = false;
+        if (!attr) { MOB_CUDA_TRY(cudaFuncSetAttribute(tc_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+        int64_t blocks = (nq * (kr / 32) + kRescoreThreads / 32 - 1) / (kRescoreThreads / 32);
+        if (blocks > 2ll * num_sms()) blocks = 2ll * num_sms();
+        tc_rescore_kernel<<<(unsigned)blocks, kRescoreThreads, smem, t.stream>>>(ddata, dq, dim, (int)nq, kr, cand, exact);
+        MOB_LAUNCH_CHECK();
+    }
     if (kr == KR) tc_final_kernel<KR><<<(unsigned)((nq + 127) / 128), 128, 0, t.stream>>>((int)nq, k, n, dim, cand, exact, t_excl, qnorm, xmax, qlonorm, xlomax, one_term, pair_norm ? 1 : 0, id_map, key_base, sqrt_out, out_k, out_d, flags);
     else tc_final_kernel<KR_WIDE><<<(unsigned)((nq + 127) / 128), 128, 0, t.stream>>>((int)nq, k, n, dim, cand, exact, t_excl, qnorm, xmax, qlonorm, xlomax, one_term, pair_norm ? 1 : 0, id_map, key_base, sqrt_out, out_k, out_d, flags);
     MOB_LAUNCH_CHECK();
