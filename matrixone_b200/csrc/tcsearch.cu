@@ -466,10 +466,15 @@ __device__ __forceinline__ float tc_eps(float qn, float ql, float xm, float xl, 
 __global__ void tc_merge_kernel(int nq, int R, const float *__restrict__ part_d, const int *__restrict__ part_i,
                                 const float *__restrict__ part_thr, const int *__restrict__ pos_map, int pos_cols, long long pos_stride,
                                 const float *__restrict__ pnorm, const float *__restrict__ plonorm, const float *__restrict__ xmax2, int one_term,
+                                const float *__restrict__ qnorm, const float *__restrict__ qlonorm, int k, int dim,
                                 int kp, int kr, int *__restrict__ cand, float *__restrict__ t_excl) {
     const int lane = threadIdx.x & 31;
     const int q = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
     if (q >= nq) return;   // whole warps leave together
+    // error bound of every list of this query when it does not depend on the list (brute force: one query operand)
+    const float eps_q = (!pnorm && qnorm) ? tc_eps(qnorm[q], one_term ? qlonorm[q] : 0.f, xmax2[0], one_term ? xmax2[1] : 0.f, one_term) : 0.f;
+    float sel_d0 = 0.f, sel_d1 = 0.f, sel_e0 = 0.f, sel_e1 = 0.f;   // approximate distance / bound of selections lane and lane + 32
+    int nsel = 0;
     long long L[kMergeSlots]; int head[kMergeSlots]; float cur[kMergeSlots], tl[kMergeSlots], eps[kMergeSlots];
 #pragma unroll
     for (int i = 0; i < kMergeSlots; i++) {
@@ -496,6 +501,7 @@ __global__ void tc_merge_kernel(int nq, int R, const float *__restrict__ part_d,
             if (od < bd || (od == bd && orr < br)) { bd = od; br = orr; }
         }
         if (br == 0x7fffffff) { if (lane == 0) cand[(size_t)q * kr + j] = -1; continue; }   // every list is exhausted (warp-uniform)
+        float we = eps_q;
         if ((br & 31) == lane) {
 #pragma unroll
             for (int i = 0; i < kMergeSlots; i++)
@@ -504,8 +510,33 @@ __global__ void tc_merge_kernel(int nq, int R, const float *__restrict__ part_d,
                     cand[(size_t)q * kr + j] = part_i[idx];
                     head[i]++;
                     cur[i] = (head[i] < kp && part_i[idx + 1] >= 0) ? part_d[idx + 1] : INFINITY;
+                    if (pnorm) we = eps[i];
                 }
         }
+        we = __shfl_sync(0xffffffffu, we, br & 31);
+        if ((j & 31) == lane) { if (j < 32) { sel_d0 = bd; sel_e0 = we; } else { sel_d1 = bd; sel_e1 = we; } }
+        nsel = j + 1;   // selections are made in order: the first nsel slots are the valid ones
+    }
+    // prune before the exact re-score: with U = the k-th smallest UPPER bound (d~ + eps) among the selections, at least k rows have
+    // a real distance <= U, so a selection whose LOWER bound (d~ - eps) exceeds U cannot be in the top k (gamma = the Go-order
+    // fp32 evaluation error relative to the real distance)
+    if ((pnorm || qnorm) && nsel > k && kr <= 64) {
+        const bool v0 = lane < nsel, v1 = lane + 32 < nsel;
+        const float u0 = v0 ? sel_d0 + sel_e0 : INFINITY, u1 = v1 ? sel_d1 + sel_e1 : INFINITY;
+        int rank0 = 0, rank1 = 0;
+        for (int jj = 0; jj < nsel; jj++) {
+            const float v = __shfl_sync(0xffffffffu, jj < 32 ? u0 : u1, jj & 31);
+            rank0 += (v < u0 || (v == u0 && jj < lane)) ? 1 : 0;
+            rank1 += (v < u1 || (v == u1 && jj < lane + 32)) ? 1 : 0;
+        }
+        float U = (v0 && rank0 == k - 1) ? u0 : ((v1 && rank1 == k - 1) ? u1 : INFINITY);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) U = fminf(U, __shfl_xor_sync(0xffffffffu, U, o));
+        const float gamma = (float)dim * 1.1920928955078125e-7f;
+        const float lim = U * (1.0f + 2.0f * gamma) + 1e-30f;
+        __syncwarp();   // the selections above were written by other lanes
+        if (v0 && (sel_d0 - sel_e0) * (1.0f - 2.0f * gamma) > lim) cand[(size_t)q * kr + lane] = -1;
+        if (v1 && (sel_d1 - sel_e1) * (1.0f - 2.0f * gamma) > lim) cand[(size_t)q * kr + lane + 32] = -1;
     }
     float t = INFINITY;
 #pragma unroll
@@ -741,7 +772,7 @@ static int tc_finish(ThreadCtx &t, const float *ddata, int64_t n, int dim, const
     MOB_LAUNCH_CHECK();
     if (one_term) { tc_max_kernel<<<num_sms() * 2, 256, 0, t.stream>>>(xlonorm, n, xlomax); MOB_LAUNCH_CHECK(); }
     if (R > kMaxMergeLists) { set_error("tc search: %d candidate lists per query exceed the merge limit %d", R, kMaxMergeLists); return MO_RC_INTERNAL_ERROR; }
-    tc_merge_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, t.stream>>>((int)nq, R, part_d, part_i, part_thr, pos_map, pos_cols, pos_stride, pair_norm, pair_lonorm, xmax, one_term, kp, kr, cand, t_excl);
+    tc_merge_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, t.stream>>>((int)nq, R, part_d, part_i, part_thr, pos_map, pos_cols, pos_stride, pair_norm, pair_lonorm, xmax, one_term, qnorm, qlonorm, k, dim, kp, kr, cand, t_excl);
     MOB_LAUNCH_CHECK();
     {
         const size_t smem = (size_t)(kRescoreThreads / 32) * godist::RingCfg<false>::kStages * godist::RingCfg<false>::kStageBytes;
