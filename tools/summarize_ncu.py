@@ -74,9 +74,9 @@ def main():
     prefix = sys.argv[1] if len(sys.argv) > 1 else "r01"
     algo = {"q6": 28.0 * 600_037_902, "q1": 38.0 * 600_037_902}
     lines = ["# ncu evidence, %s" % prefix, "",
-             "Captured with `tools/profile_%s.sh` under gpurun (`ncu --set full --clock-control none --import-source on`); the `.ncu-rep`" % prefix,
+             "Captured with `tools/profile_%s.sh` and `tools/profile_search.sh` under gpurun (`ncu --set full --clock-control none --import-source on`); the `.ncu-rep`" % prefix,
              "files stay in gpurun_out/ (scratch).  Durations under ncu are cold-cache and serialised: compare shares, not absolutes.", ""]
-    for name in ("q6", "q1", "agg", "bf", "tc_bruteforce", "tc_ivf"):
+    for name in ("q6", "q1", "agg", "bf", "tc_bruteforce", "tc_ivf", "rowdist_l2", "rowdist_cos"):
         rep = os.path.join(src, "%s_%s.ncu-rep" % (prefix, name))
         if not os.path.exists(rep):
             continue
