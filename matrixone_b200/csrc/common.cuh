@@ -42,6 +42,9 @@ int num_sms();
 // cudaPointerGetAttributes classification
 bool is_device_ptr(const void *p);
 
+// prepared search operands (tcsearch.cu) that read [p, p + bytes) are dropped: called by every library entry point that WRITES device memory
+void search_invalidate(const void *p, uint64_t bytes);
+
 // --- device scratch arena -------------------------------------------------------------------------------
 void *arena_alloc(ThreadCtx &t, size_t bytes);   // 256-byte aligned; nullptr on failure (error set)
 void arena_reset(ThreadCtx &t);                  // called at the end of every API call

@@ -115,6 +115,7 @@ int32_t MoB200_GenVectorsF32(uint64_t seed, uint64_t row0, uint64_t n, int64_t d
     ThreadCtx &t = tctx();
     if (!t.ready) return MO_RC_INTERNAL_ERROR;
     if (n == 0) return MO_RC_SUCCESS;
+    search_invalidate(out, n * (uint64_t)dim * 4);
     gen_vectors_kernel<<<num_sms() * 16, 256, 0, t.stream>>>(seed, row0, n, dim, out, centers, ncenters, sigma);
     MOB_LAUNCH_CHECK();
     MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));
@@ -126,6 +127,7 @@ int32_t MoB200_GatherRowsF32(float *dst, const float *src, const int64_t *idx, u
     ThreadCtx &t = tctx();
     if (!t.ready) return MO_RC_INTERNAL_ERROR;
     if (m == 0) return MO_RC_SUCCESS;
+    search_invalidate(dst, m * (uint64_t)dim * 4);
     gather_rows_f32_kernel<<<num_sms() * 16, 256, 0, t.stream>>>(src, idx, m, dim, dst);
     MOB_LAUNCH_CHECK();
     MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));

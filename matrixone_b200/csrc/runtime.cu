@@ -218,6 +218,7 @@ int32_t MoB200_DeviceAlloc(uint64_t bytes, void **dptr) {
 }
 int32_t MoB200_DeviceFree(void *dptr) {
     REQUIRE_CTX(t);
+    MoB200_SearchRelease(dptr);   // a prepared search operand of (or built against) this buffer must not outlive it
     MOB_CUDA_TRY(cudaFree(dptr));
     return MO_RC_SUCCESS;
 }
@@ -243,6 +244,7 @@ int32_t MoB200_HostUnregister(void *hptr) {
 }
 int32_t MoB200_Upload(void *dst_dev, const void *src_host, uint64_t bytes) {
     REQUIRE_CTX(t);
+    search_invalidate(dst_dev, bytes);
     MOB_CUDA_TRY(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, t.stream));
     MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));
     return MO_RC_SUCCESS;
@@ -255,6 +257,7 @@ int32_t MoB200_Download(void *dst_host, const void *src_dev, uint64_t bytes) {
 }
 int32_t MoB200_Memset(void *dst_dev, int32_t value, uint64_t bytes) {
     REQUIRE_CTX(t);
+    search_invalidate(dst_dev, bytes);
     MOB_CUDA_TRY(cudaMemsetAsync(dst_dev, value, bytes, t.stream));
     MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));
     return MO_RC_SUCCESS;

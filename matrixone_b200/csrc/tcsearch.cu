@@ -932,6 +932,20 @@ static int bf_tc_level(ThreadCtx &t, int level, const float *ddata, int64_t n, i
     return MO_RC_SUCCESS;
 }
 
+void search_invalidate(const void *p, uint64_t bytes) {
+    std::lock_guard<std::mutex> lk(g_prepared_mu);
+    const char *lo = (const char *)p, *hi = lo + bytes;
+    for (size_t i = 0; i < g_prepared.size();) {
+        const PreparedOperand &e = g_prepared[i];
+        const char *xl = (const char *)e.x, *xh = xl + (size_t)e.n * e.dim * 4;
+        const char *cl = (const char *)e.cent, *ch = e.cent ? cl + (size_t)e.nlist * e.dim * 4 : cl;
+        if ((lo < xh && xl < hi) || (e.cent && lo < ch && cl < hi)) {
+            cudaFree(e.op.bf); cudaFree(e.op.norm);
+            g_prepared.erase(g_prepared.begin() + (long)i);
+        } else i++;
+    }
+}
+
 // the one-term level needs k <= KP (its proof re-scores 64 candidates) and is skipped while it has recently been failing
 bool tc_one_term_wanted(int k, bool record) {
     if (k > KP || g_tc_ladder_mode == 1) return false;
@@ -1086,12 +1100,13 @@ int32_t MoB200_SearchPrepareIvf(const void *data, uint64_t n, int64_t dim, const
 int32_t MoB200_SearchRelease(const void *data) {
     using namespace mob;
     std::lock_guard<std::mutex> lk(g_prepared_mu);
-    for (size_t i = 0; i < g_prepared.size(); i++)
-        if (g_prepared[i].x == data) {
+    // also drops IVF operands built against `data` as their centroid table (residuals would be stale)
+    for (size_t i = 0; i < g_prepared.size();) {
+        if (g_prepared[i].x == data || (g_prepared[i].cent && (const void *)g_prepared[i].cent == data)) {
             cudaFree(g_prepared[i].op.bf); cudaFree(g_prepared[i].op.norm);
             g_prepared.erase(g_prepared.begin() + (long)i);
-            return MO_RC_SUCCESS;
-        }
+        } else i++;
+    }
     return MO_RC_SUCCESS;
 }
 

@@ -239,3 +239,25 @@ def test_ivf_refine_pass_resolves_crowded_lists(gpu):
     _check_topk(keys, dists, okeys, odists, nq, k)
     assert refined >= 1, refined
     assert fallbacks <= refined
+
+
+@pytest.mark.gpu
+def test_prepared_operand_is_dropped_when_the_dataset_is_overwritten(gpu):
+    """MoB200_SearchPrepare caches the split operand of a resident dataset; a library write into that buffer (Upload) must
+    invalidate it, so the next search sees the new rows"""
+    n, dim, nq, k = 20_000, 64, 300, 5
+    ds1 = datagen.vectors_f32(50, 0, n, dim); ds2 = datagen.vectors_f32(51, 0, n, dim)
+    qs = datagen.vectors_f32(52, 0, nq, dim)
+    idx = ops.BruteForceIndex(ds1, dim)
+    try:
+        gpu.MoB200_SetTuning(b"search_mode", 2)
+        k1, d1 = idx.search(qs, k)
+        ok1, od1 = O.bruteforce(ds1, qs, k)
+        _check_topk(k1, d1, ok1, od1, nq, k)
+        capi.check(gpu.MoB200_Upload(idx.buf.ptr, ds2.ctypes.data, ds2.nbytes), gpu)
+        k2, d2 = idx.search(qs, k)
+        ok2, od2 = O.bruteforce(ds2, qs, k)
+        _check_topk(k2, d2, ok2, od2, nq, k)
+    finally:
+        gpu.MoB200_SetTuning(b"search_mode", 0)
+        idx.destroy()
