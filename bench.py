@@ -402,7 +402,8 @@ def main():
     clocks = sampler.stop(t_region0, time.time()) if rank == 0 else None
     total_ms = max_over_ranks(max(ms.value, 0.0))
     ms_per_step = total_ms / K
-    value = units * world * K / (total_ms * 1e-3)
+    # weak workloads: every rank processes `units` rows of its own; strong (search): all ranks work on the SAME `units` queries
+    value = units * (1 if args.workload in ("bruteforce", "ivf") else world) * K / (total_ms * 1e-3)
     kern_ms = statistics.mean(kernel_ms)
 
     # ---------------------------------------------------------------------------------------------- e2e: host buffers
