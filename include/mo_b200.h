@@ -261,7 +261,9 @@ int32_t MoB200_GatherRowsF32(float *dst, const float *src, const int64_t *idx, u
  * Destroy frees it).  SearchPrepare splits a RESIDENT float32 dataset [n][dim] into the tensor-core operand of
  * MO_XCALL_BRUTEFORCE_TOPK_F32 / MO_XCALL_IVF_TOPK_F32 once, instead of once per search; the rows must not change until
  * SearchRelease(data).  Optional: searches return identical results with or without it.  Costs 6*dim bytes of HBM per row. */
-int32_t MoB200_SearchPrepare(const void *data, uint64_t n, int64_t dim);
+int32_t MoB200_SearchPrepare(const void *data, uint64_t n, int64_t dim);   /* = SearchPrepareMetric(..., MO_METRIC_L2) */
+/* MO_METRIC_L2 / L2SQ / IP share one operand; MO_METRIC_COS keeps the rows normalised; other metrics have nothing to prepare */
+int32_t MoB200_SearchPrepareMetric(const void *data, uint64_t n, int64_t dim, int32_t metric);
 /* IVF-flat: the list-ordered entries are split as residuals against their list's centroid (centroids [nlist][dim] float32,
  * offsets [nlist + 1] int64, device pointers; the same buffers MO_XCALL_IVF_TOPK_F32 is later called with). */
 int32_t MoB200_SearchPrepareIvf(const void *data, uint64_t n, int64_t dim, const void *centroids, uint64_t nlist, const void *offsets);

@@ -100,6 +100,7 @@ PROTOTYPES = {
     "MoB200_GenVectorsF32": (_i32, [_u64, _u64, _u64, _i64, _vp, _vp, _i64, C.c_float]),
     "MoB200_GatherRowsF32": (_i32, [_vp, _vp, _vp, _u64, _i64]),
     "MoB200_SearchPrepare": (_i32, [_vp, _u64, _i64]),
+    "MoB200_SearchPrepareMetric": (_i32, [_vp, _u64, _i64, _i32]),
     "MoB200_SearchPrepareIvf": (_i32, [_vp, _u64, _i64, _vp, _u64, _vp]),
     "MoB200_SearchRelease": (_i32, [_vp]),
 }

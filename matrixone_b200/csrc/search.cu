@@ -445,7 +445,7 @@ int xcall_bruteforce(mo_xcall_args_t *args, uint64_t len) {
     double *od = (double *)st.out(args[1].pdata, (size_t)P.nq * P.k * 8);
     if (st.failed) { st.finish(); return MO_RC_INTERNAL_ERROR; }
     if (tc_search_applicable(P.n, (int)P.dim, P.nq, P.k, P.metric))
-        rc = bruteforce_topk_tc_device(t, ddata, P.n, (int)P.dim, dq, P.nq, P.k, P.key_base, P.sqrt_out, ok, od);
+        rc = bruteforce_topk_tc_device(t, ddata, P.n, (int)P.dim, dq, P.nq, P.k, P.key_base, P.sqrt_out, ok, od, true, (int)P.metric);
     else
         rc = bruteforce_topk_device(t, ddata, P.n, (int)P.dim, dq, P.nq, P.k, P.metric, P.key_base, P.sqrt_out, ok, od);
     int frc = st.finish();

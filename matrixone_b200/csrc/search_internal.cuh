@@ -27,7 +27,7 @@ bool tc_search_applicable(int64_t n, int dim, int64_t nq, int k, int metric);
 bool tc_probe_applicable(int64_t nlist, int dim, int64_t nq, int nprobe, int metric);
 // record_stats = false: a helper search inside another call (IVF centroid probe) leaves the fallback counter and kernel timer alone
 int bruteforce_topk_tc_device(ThreadCtx &t, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq, int k,
-                              int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d, bool record_stats = true);
+                              int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d, bool record_stats = true, int metric = MO_METRIC_L2SQ);
 bool tc_ivf_applicable(int64_t n, int dim, int64_t nq, int k, int nprobe, int metric, bool refine);
 // returns the queries whose completeness proof failed in `redo` (their rows of ok/od are still filled with best-effort results).
 // pass 0 = one-term product, 1 = three-term, 2 = three-term over list sub-ranges.  *nonfinite: Inf/NaN input, the error bound

@@ -344,17 +344,27 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 
 // ---- operand preparation -------------------------------------------------------------------------------------------------
 // mode 0: A' = [hi | hi | lo] (queries), mode 1: B' = [hi | lo | hi] (dataset).  One warp per row; pads K' with zeros.
-__global__ void split_kernel(const float *__restrict__ x, int64_t n, int dim, int kprime, int mode, __nv_bfloat16 *__restrict__ out,
+__global__ void split_kernel(const float *__restrict__ x, int64_t n, int dim, int kprime, int mode, int normalize, __nv_bfloat16 *__restrict__ out,
                              float *__restrict__ norm, float *__restrict__ lonorm, int *__restrict__ nonfinite) {
-    // norm = |x|^2, lonorm = |x - hi|^2 (the part of x a hi-only product does not see); both accumulated in double
+    // norm = |x|^2, lonorm = |x - hi|^2 (the part of x a hi-only product does not see); both accumulated in double.
+    // normalize (cosine): the row is first divided by its length, so 1 - cos(q, x) = |q^ - x^|^2 / 2 and the L2 machinery applies;
+    // a zero (or non-finite) row raises *nonfinite and the caller answers the whole call with the exact kernel.
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t r = warp; r < n; r += nwarps) {
         const float *p = x + r * dim;
         __nv_bfloat16 *o = out + r * kprime;
+        float len = 1.0f;
+        if (normalize) {
+            double s0 = 0.0;
+            for (int j = lane; j < dim; j += 32) { const double v = (double)p[j]; s0 += v * v; }
+            s0 = warp_sum_f64(s0);
+            len = (float)sqrt(s0);
+            if (!(len > 0.f && len <= 3.0e38f)) { if (lane == 0) *nonfinite = 1; len = 1.0f; }
+        }
         double s = 0.0, sl = 0.0;
         for (int j = lane; j < dim; j += 32) {
-            const float v = p[j];
+            const float v = normalize ? __fdiv_rn(p[j], len) : p[j];
             const __nv_bfloat16 hi = __float2bfloat16_rn(v);
             const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
             o[j] = hi;
@@ -549,10 +559,12 @@ __global__ void tc_merge_kernel(int nq, int R, const float *__restrict__ part_d,
 // exact re-scoring: one warp per (query, 32 candidates) batch, lane = candidate row, the query is the constant operand: the
 // bit-exact Go-order L2sq through the lane-per-row batch machinery of godist.cuh (rows stream through a per-warp cp.async ring)
 constexpr int kRescoreThreads = 128;
+template <int METRIC>   // MO_METRIC_L2SQ, MO_METRIC_IP, MO_METRIC_COS: the value the exact kernel (search.cu) would produce for the pair
 __global__ void __launch_bounds__(kRescoreThreads)
 tc_rescore_kernel(const float *__restrict__ data, const float *__restrict__ queries, int dim, int nq, int kr,
                   const int *__restrict__ cand, float *__restrict__ exact) {
     using Cfg = godist::RingCfg<false>;
+    constexpr int KIND = METRIC == MO_METRIC_IP ? godist::K_GO_IP : (METRIC == MO_METRIC_COS ? godist::K_GO_COSDIST : godist::K_GO_L2SQ);
     extern __shared__ __align__(16) unsigned char rescore_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     unsigned char *ring = rescore_smem + (size_t)wib * Cfg::kStages * Cfg::kStageBytes;
@@ -563,10 +575,18 @@ tc_rescore_kernel(const float *__restrict__ data, const float *__restrict__ quer
         const size_t slot = (size_t)q * kr + (size_t)h * 32 + lane;
         const int id = cand[slot];
         const bool good = id >= 0;
+        // operand order (query, row) as in the exact kernel: the cosine accumulators n1 / n2 belong to the query / the row
         const uint8_t *px = good ? reinterpret_cast<const uint8_t *>(data + (int64_t)id * dim) : nullptr;
         const uint8_t *pq = reinterpret_cast<const uint8_t *>(queries + q * dim);
-        const godist::RowAcc<float, godist::K_GO_L2SQ> acc = godist::row_batch<float, godist::K_GO_L2SQ, false>(ring, lane, px, pq, dim, good);
-        exact[slot] = good ? acc.sum : INFINITY;
+        const godist::RowAcc<float, KIND> acc = godist::row_batch<float, KIND, false>(ring, lane, px, pq, dim, good);
+        float d = acc.sum;
+        if (METRIC == MO_METRIC_IP) d = -acc.sum;
+        if (METRIC == MO_METRIC_COS) {     // distance_func.go:264-284, as bf_topk_kernel evaluates it
+            const double den = sqrt((double)acc.n1) * sqrt((double)acc.n2);
+            if (den == 0.0) d = 1.0f;
+            else { double sim = (double)acc.sum / den; sim = sim > 1.0 ? 1.0 : (sim < -1.0 ? -1.0 : sim); d = (float)(1.0 - sim); }
+        }
+        exact[slot] = good ? d : INFINITY;
     }
 }
 
@@ -584,7 +604,7 @@ __global__ void tc_max_kernel(const float *__restrict__ v, int64_t n, float *out
 template <int KRT>
 __global__ void tc_final_kernel(int nq, int k, int64_t n_rows, int dim, const int *__restrict__ cand, const float *__restrict__ exact,
                                 const float *__restrict__ t_excl, const float *__restrict__ qnorm, const float *__restrict__ xnorm_max,
-                                const float *__restrict__ qlonorm, const float *__restrict__ xlonorm_max, int one_term, int eps_applied,
+                                const float *__restrict__ qlonorm, const float *__restrict__ xlonorm_max, int one_term, int eps_applied, int metric,
                                 const int64_t *__restrict__ id_map, int64_t key_base, int sqrt_out, int64_t *__restrict__ out_k,
                                 double *__restrict__ out_d, int *__restrict__ flags) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -604,14 +624,21 @@ __global__ void tc_final_kernel(int nq, int k, int64_t n_rows, int dim, const in
     int64_t *ok = out_k + (size_t)q * k; double *od = out_d + (size_t)q * k;
     for (int j = 0; j < pad; j++) { ok[j] = -1; od[j] = 0.0; }
     for (int j = 0; j < total; j++) { ok[pad + j] = id[j]; od[pad + j] = sqrt_out ? sqrt((double)d[j]) : (double)d[j]; }
-    const float t = t_excl[q];
+    // the candidate kernel works in units of |q|^2 + |x|^2 - 2 q.x: that IS the L2 distance; for inner product (norms left out)
+    // and cosine (normalised operands) it is twice the metric's distance
+    const float scale = (metric == MO_METRIC_IP || metric == MO_METRIC_COS) ? 0.5f : 1.0f;
+    const float t = t_excl[q] * scale;
     bool proven;
     if (t == INFINITY) proven = true;                       // nothing was excluded (every row of every range is listed)
     else if (m < k) proven = false;
     else {
         // eps_applied: the merge already lowered t by every list's own bound (IVF residual operands)
-        const float eps_tc = eps_applied ? 0.f : tc_eps(qnorm[q], one_term ? qlonorm[q] : 0.f, *xnorm_max, one_term ? *xlonorm_max : 0.f, one_term);
-        const float eps_go = (float)dim * 1.1920928955078125e-7f * t;                                  // dim * 2^-23 * distance scale
+        const float eps_tc = eps_applied ? 0.f : scale * tc_eps(qnorm[q], one_term ? qlonorm[q] : 0.f, *xnorm_max, one_term ? *xlonorm_max : 0.f, one_term);
+        // |Go-order fp32 value - real value|: relative dim * 2^-23 for L2; absolute dim * 2^-23 |q||x| for the inner product;
+        // for cosine 4 dim 2^-24 (dot product and both norms) + 2^-19 (normalisation of the operands of the candidate pass)
+        float eps_go = (float)dim * 1.1920928955078125e-7f * t;
+        if (metric == MO_METRIC_IP) eps_go = (float)dim * 1.1920928955078125e-7f * sqrtf(qnorm[q] * *xnorm_max);
+        if (metric == MO_METRIC_COS) eps_go = (float)dim * 2.384185791015625e-7f + 1.9073486328125e-6f;
         proven = d[k - 1] + eps_tc + eps_go < t;
     }
     flags[q] = proven ? 0 : 1;
@@ -648,32 +675,32 @@ int g_tc_pair_mode = 0;          // 0 = auto, 1 = single-CTA units only, 2 = CTA
 int g_last_tc_refined = -1;
 int g_last_tc_fallbacks = -1;   // queries of the last tensor-core search that failed the completeness proof and were re-run exactly
 
-struct TcOperand { __nv_bfloat16 *bf = nullptr; float *norm = nullptr; float *lonorm = nullptr; int kprime = 0; };   // norm = |x|^2, lonorm = |x - bf16(x)|^2 per row
+struct TcOperand { __nv_bfloat16 *bf = nullptr; float *norm = nullptr; float *lonorm = nullptr; const float *enorm = nullptr; int kprime = 0; };   // enorm: what the epilogue adds (null = norm; zeros for inner product)   // norm = |x|^2, lonorm = |x - bf16(x)|^2 per row
 
 // datasets split once by MoB200_SearchPrepare (index load); looked up by (pointer, rows, dim)
-struct PreparedOperand { const float *x; int64_t n; int dim; int device; TcOperand op; const float *cent = nullptr; int64_t nlist = 0; };   // cent != nullptr: IVF residual operand
+struct PreparedOperand { const float *x; int64_t n; int dim; int device; TcOperand op; const float *cent = nullptr; int64_t nlist = 0; int normalized = 0; };   // cent != nullptr: IVF residual operand; normalized: cosine
 static std::mutex g_prepared_mu;
 static std::vector<PreparedOperand> g_prepared;
 
 // split an fp32 row-major matrix into the K-concatenated bf16 operand; *nonfinite (device flag) is raised on Inf/NaN
-static int tc_prepare(ThreadCtx &t, const float *x, int64_t n, int dim, int mode, int *dnonfinite, TcOperand &op) {
+static int tc_prepare(ThreadCtx &t, const float *x, int64_t n, int dim, int mode, int *dnonfinite, TcOperand &op, int normalize = 0) {
     // one API call may split the same matrix more than once (IVF refine pass): the operand lives in the call's arena, so it
     // is reused while the arena epoch lasts.  A nonfinite input was already reported by the split that filled the cache.
-    struct Cached { const float *x = nullptr; int64_t n = 0; int dim = 0, mode = 0; uint64_t epoch = ~0ull; const ThreadCtx *t = nullptr; TcOperand op; };
+    struct Cached { const float *x = nullptr; int64_t n = 0; int dim = 0, mode = 0, normalize = 0; uint64_t epoch = ~0ull; const ThreadCtx *t = nullptr; TcOperand op; };
     static thread_local Cached cache[2];
     Cached &c = cache[mode & 1];
     if (mode == 1) {
         std::lock_guard<std::mutex> lk(g_prepared_mu);
-        for (const PreparedOperand &e : g_prepared) if (e.x == x && e.n == n && e.dim == dim && !e.cent) { op = e.op; return MO_RC_SUCCESS; }
+        for (const PreparedOperand &e : g_prepared) if (e.x == x && e.n == n && e.dim == dim && !e.cent && e.normalized == normalize) { op = e.op; return MO_RC_SUCCESS; }
     }
-    if (c.t == &t && c.epoch == t.arena_epoch && c.x == x && c.n == n && c.dim == dim && c.mode == mode) { op = c.op; return MO_RC_SUCCESS; }
+    if (c.t == &t && c.epoch == t.arena_epoch && c.x == x && c.n == n && c.dim == dim && c.mode == mode && c.normalize == normalize) { op = c.op; return MO_RC_SUCCESS; }
     op.kprime = ((3 * dim + BK - 1) / BK) * BK;
     op.bf = (__nv_bfloat16 *)arena_alloc(t, (size_t)(n > 0 ? n : 1) * op.kprime * 2 + 1024);
     op.norm = (float *)arena_alloc(t, (size_t)(n > 0 ? n : 1) * 4);
     op.lonorm = (float *)arena_alloc(t, (size_t)(n > 0 ? n : 1) * 4);
     if (!op.bf || !op.norm || !op.lonorm) return MO_RC_INTERNAL_ERROR;
-    if (n > 0) { split_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(x, n, dim, op.kprime, mode, op.bf, op.norm, op.lonorm, dnonfinite); MOB_LAUNCH_CHECK(); }
-    c.x = x; c.n = n; c.dim = dim; c.mode = mode; c.epoch = t.arena_epoch; c.t = &t; c.op = op;
+    if (n > 0) { split_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(x, n, dim, op.kprime, mode, normalize, op.bf, op.norm, op.lonorm, dnonfinite); MOB_LAUNCH_CHECK(); }
+    c.x = x; c.n = n; c.dim = dim; c.mode = mode; c.normalize = normalize; c.epoch = t.arena_epoch; c.t = &t; c.op = op;
     return MO_RC_SUCCESS;
 }
 
@@ -732,8 +759,8 @@ static int tc_run_units(ThreadCtx &t, const TcOperand &A, int64_t a_rows, const 
     if (!pair) {
         int grid = num_sms();
         if (grid > nunits) grid = nunits;
-        if (kp == KP_LONG) tc_candidates_kernel<false, KP_LONG><<<grid, kTcThreads, smem1, t.stream>>>(map_a, map_b, dunits, nunits, nkb, A.norm, B.norm, *part_d, *part_i, *part_thr);
-        else tc_candidates_kernel<false, KP><<<grid, kTcThreads, smem1, t.stream>>>(map_a, map_b, dunits, nunits, nkb, A.norm, B.norm, *part_d, *part_i, *part_thr);
+        if (kp == KP_LONG) tc_candidates_kernel<false, KP_LONG><<<grid, kTcThreads, smem1, t.stream>>>(map_a, map_b, dunits, nunits, nkb, A.enorm ? A.enorm : A.norm, B.enorm ? B.enorm : B.norm, *part_d, *part_i, *part_thr);
+        else tc_candidates_kernel<false, KP><<<grid, kTcThreads, smem1, t.stream>>>(map_a, map_b, dunits, nunits, nkb, A.enorm ? A.enorm : A.norm, B.enorm ? B.enorm : B.norm, *part_d, *part_i, *part_thr);
     } else {
         if (kp != KP) { set_error("tc search: CTA pairs keep %d candidates per list", KP); return MO_RC_INTERNAL_ERROR; }
         // clusters of two CTAs (one TPC each): one persistent pair per two SMs
@@ -744,7 +771,7 @@ static int tc_run_units(ThreadCtx &t, const TcOperand &A, int64_t a_rows, const 
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        const float *an = A.norm, *bn = B.norm; int kp = nkb;
+        const float *an = A.enorm ? A.enorm : A.norm, *bn = B.enorm ? B.enorm : B.norm; int kp = nkb;
         MOB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_candidates_kernel<true, KP>, map_a, map_b, (const TcUnit *)dunits, nunits, kp, an, bn, *part_d, *part_i, *part_thr));
     }
     if (timed) cudaEventRecord(t.kev1, t.stream);
@@ -758,7 +785,8 @@ static int tc_finish(ThreadCtx &t, const float *ddata, int64_t n, int dim, const
                      const int64_t *id_map, int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d, std::vector<int> &redo,
                      const float *qlonorm = nullptr, const float *xlonorm = nullptr,   // both given: the candidate pass was hi-only (one term)
                      const float *pair_norm = nullptr, const float *pair_lonorm = nullptr,   // IVF: operand norms per (query, list) pair
-                     int kp = KP) {
+                     int kp = KP, int metric = MO_METRIC_L2SQ) {
+    const bool l2 = metric != MO_METRIC_IP && metric != MO_METRIC_COS;
     const int one_term = xlonorm ? 1 : 0;
     const int kr = (k > KP || one_term) ? KR_WIDE : KR;   // a looser approximation needs more exact re-scores to prove the top k
     int *cand = (int *)arena_alloc(t, sizeof(int) * (size_t)nq * kr);
@@ -772,19 +800,26 @@ static int tc_finish(ThreadCtx &t, const float *ddata, int64_t n, int dim, const
     MOB_LAUNCH_CHECK();
     if (one_term) { tc_max_kernel<<<num_sms() * 2, 256, 0, t.stream>>>(xlonorm, n, xlomax); MOB_LAUNCH_CHECK(); }
     if (R > kMaxMergeLists) { set_error("tc search: %d candidate lists per query exceed the merge limit %d", R, kMaxMergeLists); return MO_RC_INTERNAL_ERROR; }
-    tc_merge_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, t.stream>>>((int)nq, R, part_d, part_i, part_thr, pos_map, pos_cols, pos_stride, pair_norm, pair_lonorm, xmax, one_term, qnorm, qlonorm, k, dim, kp, kr, cand, t_excl);
+    tc_merge_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, t.stream>>>((int)nq, R, part_d, part_i, part_thr, pos_map, pos_cols, pos_stride, pair_norm, pair_lonorm, xmax, one_term, qnorm, qlonorm, l2 ? k : (1 << 30) /* pruning bound is L2-specific */, dim, kp, kr, cand, t_excl);
     MOB_LAUNCH_CHECK();
     {
         const size_t smem = (size_t)(kRescoreThreads / 32) * godist::RingCfg<false>::kStages * godist::RingCfg<false>::kStageBytes;
         static bool attr = false;
-        if (!attr) { MOB_CUDA_TRY(cudaFuncSetAttribute(tc_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+        if (!attr) {
+            MOB_CUDA_TRY(cudaFuncSetAttribute(tc_rescore_kernel<MO_METRIC_L2SQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            MOB_CUDA_TRY(cudaFuncSetAttribute(tc_rescore_kernel<MO_METRIC_IP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            MOB_CUDA_TRY(cudaFuncSetAttribute(tc_rescore_kernel<MO_METRIC_COS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr = true;
+        }
         int64_t blocks = (nq * (kr / 32) + kRescoreThreads / 32 - 1) / (kRescoreThreads / 32);
         if (blocks > 2ll * num_sms()) blocks = 2ll * num_sms();
-        tc_rescore_kernel<<<(unsigned)blocks, kRescoreThreads, smem, t.stream>>>(ddata, dq, dim, (int)nq, kr, cand, exact);
+        if (metric == MO_METRIC_IP) tc_rescore_kernel<MO_METRIC_IP><<<(unsigned)blocks, kRescoreThreads, smem, t.stream>>>(ddata, dq, dim, (int)nq, kr, cand, exact);
+        else if (metric == MO_METRIC_COS) tc_rescore_kernel<MO_METRIC_COS><<<(unsigned)blocks, kRescoreThreads, smem, t.stream>>>(ddata, dq, dim, (int)nq, kr, cand, exact);
+        else tc_rescore_kernel<MO_METRIC_L2SQ><<<(unsigned)blocks, kRescoreThreads, smem, t.stream>>>(ddata, dq, dim, (int)nq, kr, cand, exact);
         MOB_LAUNCH_CHECK();
     }
-    if (kr == KR) tc_final_kernel<KR><<<(unsigned)((nq + 127) / 128), 128, 0, t.stream>>>((int)nq, k, n, dim, cand, exact, t_excl, qnorm, xmax, qlonorm, xlomax, one_term, pair_norm ? 1 : 0, id_map, key_base, sqrt_out, out_k, out_d, flags);
-    else tc_final_kernel<KR_WIDE><<<(unsigned)((nq + 127) / 128), 128, 0, t.stream>>>((int)nq, k, n, dim, cand, exact, t_excl, qnorm, xmax, qlonorm, xlomax, one_term, pair_norm ? 1 : 0, id_map, key_base, sqrt_out, out_k, out_d, flags);
+    if (kr == KR) tc_final_kernel<KR><<<(unsigned)((nq + 127) / 128), 128, 0, t.stream>>>((int)nq, k, n, dim, cand, exact, t_excl, qnorm, xmax, qlonorm, xlomax, one_term, pair_norm ? 1 : 0, metric, id_map, key_base, sqrt_out, out_k, out_d, flags);
+    else tc_final_kernel<KR_WIDE><<<(unsigned)((nq + 127) / 128), 128, 0, t.stream>>>((int)nq, k, n, dim, cand, exact, t_excl, qnorm, xmax, qlonorm, xlomax, one_term, pair_norm ? 1 : 0, metric, id_map, key_base, sqrt_out, out_k, out_d, flags);
     MOB_LAUNCH_CHECK();
     std::vector<int> hflags((size_t)nq);
     MOB_CUDA_TRY(cudaMemcpyAsync(hflags.data(), flags, sizeof(int) * (size_t)nq, cudaMemcpyDeviceToHost, t.stream));
@@ -825,8 +860,8 @@ static int plan_ranges(int64_t ntiles, int mt, int workers, int rmin, int rcap) 
 bool tc_search_applicable(int64_t n, int dim, int64_t nq, int k, int metric) {
     if (g_search_mode == 1) return false;
     // k <= KP: one candidate list per (query, row range); KP < k <= KW ("wide", centroid probes): ranges of >= 128 rows, at least 8 of them
-    const bool shape_ok = (metric == MO_METRIC_L2 || metric == MO_METRIC_L2SQ) && k >= 1 && dim >= 16 && n < (1ll << 31) - BN &&
-                          (k <= KP ? n >= BN : (k <= KW && n >= 1024));
+    const bool metric_ok = metric == MO_METRIC_L2 || metric == MO_METRIC_L2SQ || metric == MO_METRIC_IP || metric == MO_METRIC_COS;
+    const bool shape_ok = metric_ok && k >= 1 && dim >= 16 && n < (1ll << 31) - BN && (k <= KP ? n >= BN : (k <= KW && n >= 1024));
     if (g_search_mode == 2) return shape_ok;
     return shape_ok && nq >= 256 && n >= 16384 && dim >= 64;   // below this the exact kernel wins (operand split + launch overheads)
 }
@@ -853,24 +888,31 @@ bool tc_ivf_applicable(int64_t n, int dim, int64_t nq, int k, int nprobe, int me
 // can with the looser one-term error bound; level 1 re-runs the unproven queries over the whole K' (three-term product); what is
 // still unproven goes to the exact kernel.  Every level answers its queries exactly or hands them down.
 void tc_one_term_report(int64_t nq, int64_t failed);
-static int bf_tc_level(ThreadCtx &t, int level, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq, int k,
+static int bf_tc_level(ThreadCtx &t, int level, int metric, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq, int k,
                        int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d, bool record_stats, bool timed) {
     if (level >= 2) {
         if (record_stats) g_last_tc_fallbacks = (int)nq;
-        return bruteforce_topk_device(t, ddata, n, dim, dq, nq, k, MO_METRIC_L2SQ, key_base, sqrt_out, out_k, out_d);
+        return bruteforce_topk_device(t, ddata, n, dim, dq, nq, k, metric, key_base, sqrt_out, out_k, out_d);
     }
+    const int normalize = metric == MO_METRIC_COS ? 1 : 0;
     int *dnonfinite = (int *)arena_alloc(t, 4);
     if (!dnonfinite) return MO_RC_INTERNAL_ERROR;
     MOB_CUDA_TRY(cudaMemsetAsync(dnonfinite, 0, 4, t.stream));
     TcOperand A, B;
-    int rc = tc_prepare(t, dq, nq, dim, 0, dnonfinite, A);
-    if (!rc) rc = tc_prepare(t, ddata, n, dim, 1, dnonfinite, B);
+    int rc = tc_prepare(t, dq, nq, dim, 0, dnonfinite, A, normalize);
+    if (!rc) rc = tc_prepare(t, ddata, n, dim, 1, dnonfinite, B, normalize);
     if (rc) return rc;
     int hnonfinite = 0;
     rc = read_back(t, &hnonfinite, dnonfinite, 4);
     if (rc) return rc;
-    if (hnonfinite)   // the error bound of the tensor-core pass does not apply to Inf/NaN inputs
-        return bf_tc_level(t, 2, ddata, n, dim, dq, nq, k, key_base, sqrt_out, out_k, out_d, record_stats, false);
+    if (hnonfinite)   // the error bound of the tensor-core pass does not apply to Inf/NaN inputs (cosine: nor to zero vectors)
+        return bf_tc_level(t, 2, metric, ddata, n, dim, dq, nq, k, key_base, sqrt_out, out_k, out_d, record_stats, false);
+    if (metric == MO_METRIC_IP) {   // -q.x: the epilogue adds no norms (the candidate kernel then works in units of -2 q.x)
+        float *zeros = (float *)arena_alloc(t, (size_t)(n > nq ? n : nq) * 4);
+        if (!zeros) return MO_RC_INTERNAL_ERROR;
+        MOB_CUDA_TRY(cudaMemsetAsync(zeros, 0, (size_t)(n > nq ? n : nq) * 4, t.stream));
+        A.enorm = zeros; B.enorm = zeros;
+    }
     const bool one_term = level == 0;
     const int nkb = one_term ? (dim + BK - 1) / BK : A.kprime / BK;
     // work units: (query tile, row range); ranges sized so that units ~ a whole number of waves over the SMs
@@ -907,7 +949,7 @@ static int bf_tc_level(ThreadCtx &t, int level, const float *ddata, int64_t n, i
     if (rc) return rc;
     std::vector<int> redo;
     rc = tc_finish(t, ddata, n, dim, dq, nq, k, R, nullptr, 0, 0, part_d, part_i, part_thr, A.norm, B.norm, nullptr, key_base, sqrt_out, out_k, out_d, redo,
-                   one_term ? A.lonorm : nullptr, one_term ? B.lonorm : nullptr);
+                   one_term ? A.lonorm : nullptr, one_term ? B.lonorm : nullptr, nullptr, nullptr, KP, metric);
     if (rc) return rc;
     if (record_stats && level == 0) {
         g_last_tc_refined = (int)redo.size();
@@ -925,7 +967,7 @@ static int bf_tc_level(ThreadCtx &t, int level, const float *ddata, int64_t n, i
     MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));
     gather_rows_kernel<<<num_sms() * 4, 256, 0, t.stream>>>(dq, didx, m, dim, sub);
     MOB_LAUNCH_CHECK();
-    rc = bf_tc_level(t, level + 1, ddata, n, dim, sub, m, k, key_base, sqrt_out, sk, sd, record_stats, false);
+    rc = bf_tc_level(t, level + 1, metric, ddata, n, dim, sub, m, k, key_base, sqrt_out, sk, sd, record_stats, false);
     if (rc) return rc;
     scatter_results_kernel<<<(unsigned)((m * k + 255) / 256), 256, 0, t.stream>>>(sk, sd, didx, m, k, out_k, out_d);
     MOB_LAUNCH_CHECK();
@@ -957,10 +999,11 @@ bool tc_one_term_wanted(int k, bool record) {
 void tc_one_term_report(int64_t nq, int64_t failed) { if (nq >= 64 && failed * 5 > nq * 2) g_one_term_skip = 16; }
 
 int bruteforce_topk_tc_device(ThreadCtx &t, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq, int k,
-                              int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d, bool record_stats) {
+                              int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d, bool record_stats, int metric) {
     const bool ladder = tc_one_term_wanted(k, record_stats);
     if (record_stats) { g_last_tc_fallbacks = 0; g_last_tc_refined = -1; }
-    return bf_tc_level(t, ladder ? 0 : 1, ddata, n, dim, dq, nq, k, key_base, sqrt_out, out_k, out_d, record_stats, record_stats);
+    if (metric == MO_METRIC_L2) metric = MO_METRIC_L2SQ;
+    return bf_tc_level(t, ladder ? 0 : 1, metric, ddata, n, dim, dq, nq, k, key_base, sqrt_out, out_k, out_d, record_stats, record_stats);
 }
 
 // IVF list scan on the tensor cores: the queries probing a list are gathered (as split bf16 rows) next to each other, so
@@ -1036,14 +1079,18 @@ extern "C" {
 // Index load: split a RESIDENT dataset into the tensor-core operand once instead of once per search.  The rows must not change
 // until MoB200_SearchRelease(data).  Datasets the tensor-core path cannot serve (dim < 16, Inf/NaN values) are left unprepared:
 // searches on them behave exactly as without this call.
-int32_t MoB200_SearchPrepare(const void *data, uint64_t n, int64_t dim) {
+int32_t MoB200_SearchPrepare(const void *data, uint64_t n, int64_t dim) { return MoB200_SearchPrepareMetric(data, n, dim, MO_METRIC_L2); }
+
+// metric: MO_METRIC_L2 / L2SQ / IP share one operand; MO_METRIC_COS keeps the rows normalised; other metrics: nothing to prepare
+int32_t MoB200_SearchPrepareMetric(const void *data, uint64_t n, int64_t dim, int32_t metric) {
     using namespace mob;
     ThreadCtx &t = tctx();
     if (!t.ready) return MO_RC_INTERNAL_ERROR;
+    if (metric != MO_METRIC_L2 && metric != MO_METRIC_L2SQ && metric != MO_METRIC_IP && metric != MO_METRIC_COS) return MO_RC_SUCCESS;
     if (!data || n == 0 || dim < 16 || n >= (1ull << 31) - BN) return MO_RC_SUCCESS;
     if (!is_device_ptr(data)) { set_error("SearchPrepare: the dataset must be device memory"); return MO_RC_INVALID_ARGUMENT; }
     MoB200_SearchRelease(data);
-    PreparedOperand e; e.x = (const float *)data; e.n = (int64_t)n; e.dim = (int)dim; e.device = 0;
+    PreparedOperand e; e.x = (const float *)data; e.n = (int64_t)n; e.dim = (int)dim; e.device = 0; e.normalized = metric == MO_METRIC_COS ? 1 : 0;
     e.op.kprime = ((3 * (int)dim + BK - 1) / BK) * BK;
     MOB_CUDA_TRY(cudaMalloc((void **)&e.op.bf, (size_t)n * e.op.kprime * 2 + 1024));
     if (cudaMalloc((void **)&e.op.norm, (size_t)n * 8) != cudaSuccess) { cudaFree(e.op.bf); set_error("SearchPrepare: out of device memory"); return MO_RC_INTERNAL_ERROR; }
@@ -1053,7 +1100,7 @@ int32_t MoB200_SearchPrepare(const void *data, uint64_t n, int64_t dim) {
     int rc = dnonfinite ? MO_RC_SUCCESS : MO_RC_INTERNAL_ERROR;
     if (!rc && cudaMemsetAsync(dnonfinite, 0, 4, t.stream) != cudaSuccess) rc = MO_RC_INTERNAL_ERROR;
     if (!rc) {
-        split_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(e.x, e.n, e.dim, e.op.kprime, 1, e.op.bf, e.op.norm, e.op.lonorm, dnonfinite);
+        split_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(e.x, e.n, e.dim, e.op.kprime, 1, e.normalized, e.op.bf, e.op.norm, e.op.lonorm, dnonfinite);
         g_launches++;
         if (cudaGetLastError() != cudaSuccess) rc = MO_RC_INTERNAL_ERROR;
     }

@@ -140,9 +140,9 @@ class BruteForceIndex:
 
     def _prepare(self):
         # Load: split the resident rows into the tensor-core operand once (L2 metrics; a no-op where it does not apply)
-        self.prepared = self.metric in (capi.METRIC_L2, capi.METRIC_L2SQ) and self.n > 0
+        self.prepared = self.metric in (capi.METRIC_L2, capi.METRIC_L2SQ, capi.METRIC_IP, capi.METRIC_COS) and self.n > 0
         if self.prepared:
-            capi.check(self.lib.MoB200_SearchPrepare(self.buf.ptr, self.n, self.dim), self.lib)
+            capi.check(self.lib.MoB200_SearchPrepareMetric(self.buf.ptr, self.n, self.dim, self.metric), self.lib)
 
     def search(self, queries, limit, out_device=False):
         if isinstance(queries, DeviceBuffer):

@@ -261,3 +261,45 @@ def test_prepared_operand_is_dropped_when_the_dataset_is_overwritten(gpu):
     finally:
         gpu.MoB200_SetTuning(b"search_mode", 0)
         idx.destroy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,dim,nq,k", [(20_000, 128, 300, 10), (9_000, 768, 257, 10), (70_000, 64, 1000, 16)])
+@pytest.mark.parametrize("metric", [capi.METRIC_IP, capi.METRIC_COS])
+@pytest.mark.parametrize("ladder", [1, 2])
+def test_tensor_core_path_inner_product_and_cosine_are_exact(gpu, n, dim, nq, k, metric, ladder):
+    """inner product (no norms in the epilogue) and cosine (operands normalised at split time: 1 - cos = |q^ - x^|^2 / 2) go through the
+    same candidate kernel; re-scoring uses the Go-order inner product / cosine distance, so results equal the exact kernel's"""
+    ds = datagen.vectors_f32(60, 0, n, dim); qs = datagen.vectors_f32(61, 0, nq, dim)
+    ds[11] *= 3.0; ds[12] *= 0.25          # different lengths: inner product and cosine disagree about the order
+    qs[:3] = ds[[0, 5, n // 2]]
+    okeys, odists = O.bruteforce(ds, qs, k, metric)
+    try:
+        gpu.MoB200_SetTuning(b"search_mode", 2)
+        gpu.MoB200_SetTuning(b"tc_ladder", ladder)
+        idx = ops.BruteForceIndex(ds, dim, metric)
+        keys, dists = idx.search(qs, k)
+        fallbacks = gpu.MoB200_SetTuning(b"get_tc_fallbacks", 0)
+        idx.destroy()
+    finally:
+        gpu.MoB200_SetTuning(b"search_mode", 0)
+        gpu.MoB200_SetTuning(b"tc_ladder", 0)
+    _check_topk(keys, dists, okeys, odists, nq, k)
+    assert 0 <= fallbacks <= max(8, nq // 5), fallbacks
+
+
+@pytest.mark.gpu
+def test_tensor_core_cosine_with_a_zero_vector_uses_the_exact_kernel(gpu):
+    n, dim, nq, k = 5_000, 64, 64, 4
+    ds = datagen.vectors_f32(62, 0, n, dim); qs = datagen.vectors_f32(63, 0, nq, dim)
+    ds[100] = 0.0                           # cosine distance to a zero vector is 1 by the Go rule; it cannot be normalised
+    okeys, odists = O.bruteforce(ds, qs, k, capi.METRIC_COS)
+    try:
+        gpu.MoB200_SetTuning(b"search_mode", 2)
+        idx = ops.BruteForceIndex(ds, dim, capi.METRIC_COS)
+        keys, dists = idx.search(qs, k)
+        assert gpu.MoB200_SetTuning(b"get_tc_fallbacks", 0) == nq
+        idx.destroy()
+    finally:
+        gpu.MoB200_SetTuning(b"search_mode", 0)
+    _check_topk(keys, dists, okeys, odists, nq, k)
