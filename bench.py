@@ -234,6 +234,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--queries", type=int, default=10_000)
+    ap.add_argument("--metric", default="l2", choices=["l2", "ip", "cos"], help="bruteforce workload only (experiments; BASELINE config 4 is l2)")
     ap.add_argument("--tune", action="append", default=[], metavar="NAME=VALUE",
                     help="kernel-variant knob passed to MoB200_SetTuning (experiments only; the default run uses none)")
     args = ap.parse_args()
@@ -348,7 +349,7 @@ def main():
         capi.check(lib.MoB200_GenVectorsF32(20, rank * n_local, n_local, dim, ds.ptr, None, 0, 1.0), lib)
         dq = DeviceBuffer(4 * nq * dim, lib)
         capi.check(lib.MoB200_GenVectorsF32(21, 0, nq, dim, dq.ptr, None, 0, 1.0), lib)
-        idx = ops.BruteForceIndex(ds, dim, capi.METRIC_L2, key_base=rank * n_local, lib=lib)
+        idx = ops.BruteForceIndex(ds, dim, {"l2": capi.METRIC_L2, "ip": capi.METRIC_IP, "cos": capi.METRIC_COS}[args.metric], key_base=rank * n_local, lib=lib)
         bufs = {"queries": dq}
         def step(cols=bufs):
             return idx.search(cols["queries"], k)

@@ -157,6 +157,19 @@ __device__ __forceinline__ unsigned long long make_desc(unsigned smem_addr) {
 constexpr unsigned kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
 constexpr unsigned kIdescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)((2 * BM) >> 4) << 24);
 
+// bound on |approximate - real| squared distance of one (query operand, row operand) pair, from the operand norms:
+//   three-term product: |2 q.x error| <= 2 (3 * 2^-16 [dropped lo.lo + bf16 residuals] + 144 * 2^-23 [fp32 accumulation over K'/16
+//     MMA steps]) |q||x| < 2^-12.8 |q||x|; 2^-12 is used
+//   one-term (hi-only) product: q.x - qh.xh = qh.xL + qL.xh + qL.xL with qL = q - qh, xL = x - xh known exactly, so
+//     |error| <= |q||xL| + |qL||x| + 3 |qL||xL|  (|qh| <= |q| + |qL|); fp32 accumulation over dim/16 MMA steps < 2^-17 |q||x|
+//   both: norm / final-formula / residual-formation rounding 2^-20 (|q|^2 + |x|^2)
+// qn, ql = |q|^2, |q - hi(q)|^2 of the query operand; xm, xl = the largest |x|^2, |x - hi(x)|^2 over the row operand
+__device__ __forceinline__ float tc_eps(float qn, float ql, float xm, float xl, int one_term) {
+    if (one_term)
+        return 2.002f * (sqrtf(qn * xl) + sqrtf(ql * xm) + 3.0f * sqrtf(ql * xl)) + 1.52587890625e-5f * sqrtf(qn * xm) + 9.5367431640625e-7f * (qn + xm);
+    return 2.44140625e-4f * sqrtf(qn * xm) + 9.5367431640625e-7f * (qn + xm);
+}
+
 // one work unit: up to kTileM rows of the A' operand (queries) x dataset rows [n_begin, n_end); lists are written at out_base + row
 struct TcUnit { int a_row0; int a_valid; int n_begin; int n_end; long long out_base; };
 
@@ -165,7 +178,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                      const TcUnit *__restrict__ units, int nunits, int nkb /* 64-element k-blocks of K' to run */,
                      const float *__restrict__ qnorm, const float *__restrict__ xnorm,
-                     float *__restrict__ part_d, int *__restrict__ part_i, float *__restrict__ part_thr) {
+                     float *__restrict__ part_d, int *__restrict__ part_i, float *__restrict__ part_thr,
+                     // cross-unit threshold sharing (qbound == nullptr: off): the units of one query run on different SMs at
+                     // different times; each publishes an upper bound of the query's k-th real distance and prunes with the best one
+                     float *qbound, const int *__restrict__ row_query, const float *__restrict__ alonorm,
+                     const float *__restrict__ xmax2, int one_term, int topk, float rel_margin, float abs_margin) {
     using Cfg = TcCfg<PAIR>;
     constexpr int STAGES = Cfg::kStages;
     extern __shared__ unsigned char smem_raw[];
@@ -268,6 +285,12 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 #pragma unroll
             for (int j = 0; j < KPT; j++) { ld[j] = INFINITY; li[j] = -1; }
             float thr = valid_row ? INFINITY : -INFINITY;
+            // sharing: `cap` = (best published bound of this query) + this pair's own error bound + the Go-order margin; rows at or
+            // above it cannot displace the k-th result, so they are excluded exactly like rows beyond a full list (thr only falls)
+            const bool share = qbound != nullptr && valid_row;
+            const int qid = share ? (row_query ? row_query[U.a_row0 + row_in_unit] : U.a_row0 + row_in_unit) : 0;
+            const float my_eps = share ? tc_eps(qn, one_term ? alonorm[U.a_row0 + row_in_unit] : 0.f, xmax2[0], one_term ? xmax2[1] : 0.f, one_term) : 0.f;
+            float cap = INFINITY, published = INFINITY;
             for (int n0 = U.n_begin; n0 < U.n_end; n0 += BN, tile++) {
                 const unsigned acc = tile & 1;
                 // |x|^2 of this tile's rows -> shared (2 per thread); named barrier over the 128 epilogue threads
@@ -276,6 +299,10 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 mbar_wait(&S.tmem_full[acc], (tile >> 1) & 1);
                 tc_fence_after();
                 const int ncols = U.n_end - n0 < BN ? U.n_end - n0 : BN;
+                if (share) {
+                    const float b = __ldcg(&qbound[qid]);
+                    if (b < INFINITY) { cap = fminf(cap, b + my_eps + b * rel_margin + abs_margin + 1e-30f); thr = fminf(thr, cap); }
+                }
                 const unsigned trow = tmem_base + ((unsigned)(32 * ew) << 16) + acc * BN;
 #pragma unroll 1
                 for (int c = 0; c < ncols; c += 32) {
@@ -313,10 +340,17 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                                     ld[p] = shift ? ld[p - 1] : (here ? d : ld[p]);
                                 }
                                 if (d < ld[0]) { ld[0] = d; li[0] = id; }
-                                thr = ld[KPT - 1];
+                                thr = fminf(ld[KPT - 1], cap);
                             }
                         }
                     }
+                }
+                if (share && topk <= KPT) {   // the k best rows seen by this unit bound the query's k-th real distance from above
+                    float kth = INFINITY;
+#pragma unroll
+                    for (int j = 0; j < KPT; j++) if (j == topk - 1) kth = ld[j];
+                    const float pb = fmaxf(kth + my_eps, 0.f);
+                    if (pb < published) { published = pb; atomicMin(reinterpret_cast<int *>(&qbound[qid]), __float_as_int(pb)); }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -457,19 +491,6 @@ constexpr int KW = 32;
 // index = s * pos_stride + pos_map[q * pos_cols + p]  (pos_map < 0 = no such list)
 constexpr int kMaxMergeLists = 256;
 constexpr int kMergeSlots = kMaxMergeLists / 32;
-
-// bound on |approximate - real| squared distance of one (query operand, row operand) pair, from the operand norms:
-//   three-term product: |2 q.x error| <= 2 (3 * 2^-16 [dropped lo.lo + bf16 residuals] + 144 * 2^-23 [fp32 accumulation over K'/16
-//     MMA steps]) |q||x| < 2^-12.8 |q||x|; 2^-12 is used
-//   one-term (hi-only) product: q.x - qh.xh = qh.xL + qL.xh + qL.xL with qL = q - qh, xL = x - xh known exactly, so
-//     |error| <= |q||xL| + |qL||x| + 3 |qL||xL|  (|qh| <= |q| + |qL|); fp32 accumulation over dim/16 MMA steps < 2^-17 |q||x|
-//   both: norm / final-formula / residual-formation rounding 2^-20 (|q|^2 + |x|^2)
-// qn, ql = |q|^2, |q - hi(q)|^2 of the query operand; xm, xl = the largest |x|^2, |x - hi(x)|^2 over the row operand
-__device__ __forceinline__ float tc_eps(float qn, float ql, float xm, float xl, int one_term) {
-    if (one_term)
-        return 2.002f * (sqrtf(qn * xl) + sqrtf(ql * xm) + 3.0f * sqrtf(ql * xl)) + 1.52587890625e-5f * sqrtf(qn * xm) + 9.5367431640625e-7f * (qn + xm);
-    return 2.44140625e-4f * sqrtf(qn * xm) + 9.5367431640625e-7f * (qn + xm);
-}
 
 // pnorm / plonorm (IVF): the query operand differs per probed list (residual against that list's centroid), so every list's
 // exclusion bound is lowered by ITS error bound before the minimum is taken: t_excl = min_l (t_l - eps_l)
@@ -667,6 +688,7 @@ __global__ void scatter_results_kernel(const int64_t *__restrict__ sk, const dou
 namespace mob {
 
 int g_search_mode = 0;          // 0 = auto, 1 = exact kernel only, 2 = force the tensor-core path (MoB200_SetTuning("search_mode"))
+int g_tc_share_mode = 0;         // 1 = no cross-unit threshold sharing (MoB200_SetTuning("tc_share"))
 int g_tc_ladder_mode = 0;        // 0 = auto (one-term level first unless it has been failing), 1 = never, 2 = always (MoB200_SetTuning("tc_ladder"))
 int g_one_term_skip = 0;         // searches left before the one-term level is tried again
 int g_last_tc_kused = 0;         // K elements per (query, row) pair the timed candidate pass multiplied (dim = one term, 3*dim = three)
@@ -728,8 +750,15 @@ static int tc_prepare_ivf_entries(ThreadCtx &t, const float *x, int64_t n, int d
 }
 
 // run the candidate kernel over `units`; lists are written at unit.out_base + row (nlists lists in total, pre-initialised empty)
+// cross-unit threshold sharing (see the kernel): nq queries, row_query maps an A row to its query (nullptr: identity)
+struct TcShare { int64_t nq; const int *row_query; int topk; int one_term; float rel_margin, abs_margin; const float *xmax2; };
+__global__ void tc_fill_inf_kernel(float *p, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = INFINITY;
+}
+
 static int tc_run_units(ThreadCtx &t, const TcOperand &A, int64_t a_rows, const TcOperand &B, int64_t b_rows, const std::vector<TcUnit> &units,
-                        int64_t nlists, float **part_d, int **part_i, float **part_thr, bool timed = true, bool pair = false, int nkb = 0, int kp = KP) {
+                        int64_t nlists, float **part_d, int **part_i, float **part_thr, bool timed = true, bool pair = false, int nkb = 0, int kp = KP,
+                        const TcShare *share = nullptr) {
     if (nkb <= 0 || nkb > A.kprime / BK) nkb = A.kprime / BK;   // 0 = the whole K' (three-term product)
     CUtensorMap map_a, map_b;
     int rc = make_map(&map_a, A.bf, (uint64_t)a_rows, (uint64_t)A.kprime, BM);
@@ -755,12 +784,21 @@ static int tc_run_units(ThreadCtx &t, const TcOperand &A, int64_t a_rows, const 
         attr = true;
     }
     const int nunits = (int)units.size();
+    float *qbound = nullptr; const int *row_query = nullptr; const float *alonorm = A.lonorm, *xmax2 = nullptr;
+    int sh_one = 0, sh_k = 0; float sh_rel = 0.f, sh_abs = 0.f;
+    if (share && !A.enorm && !B.enorm && g_tc_share_mode != 1) {   // inner product leaves the norms out of the epilogue: no sharing there
+        qbound = (float *)arena_alloc(t, (size_t)share->nq * 4);
+        if (!qbound) return MO_RC_INTERNAL_ERROR;
+        tc_fill_inf_kernel<<<num_sms() * 2, 256, 0, t.stream>>>(qbound, share->nq);
+        MOB_LAUNCH_CHECK();
+        row_query = share->row_query; xmax2 = share->xmax2; sh_one = share->one_term; sh_k = share->topk; sh_rel = share->rel_margin; sh_abs = share->abs_margin;
+    }
     if (timed) { t.kev_prio = 2; g_last_tc_kused = nkb * BK; cudaEventRecord(t.kev0, t.stream); }   // MoB200_LastKernelMs reports the first (whole-list) pass, not the refine pass
     if (!pair) {
         int grid = num_sms();
         if (grid > nunits) grid = nunits;
-        if (kp == KP_LONG) tc_candidates_kernel<false, KP_LONG><<<grid, kTcThreads, smem1, t.stream>>>(map_a, map_b, dunits, nunits, nkb, A.enorm ? A.enorm : A.norm, B.enorm ? B.enorm : B.norm, *part_d, *part_i, *part_thr);
-        else tc_candidates_kernel<false, KP><<<grid, kTcThreads, smem1, t.stream>>>(map_a, map_b, dunits, nunits, nkb, A.enorm ? A.enorm : A.norm, B.enorm ? B.enorm : B.norm, *part_d, *part_i, *part_thr);
+        if (kp == KP_LONG) tc_candidates_kernel<false, KP_LONG><<<grid, kTcThreads, smem1, t.stream>>>(map_a, map_b, dunits, nunits, nkb, A.enorm ? A.enorm : A.norm, B.enorm ? B.enorm : B.norm, *part_d, *part_i, *part_thr, qbound, row_query, alonorm, xmax2, sh_one, sh_k, sh_rel, sh_abs);
+        else tc_candidates_kernel<false, KP><<<grid, kTcThreads, smem1, t.stream>>>(map_a, map_b, dunits, nunits, nkb, A.enorm ? A.enorm : A.norm, B.enorm ? B.enorm : B.norm, *part_d, *part_i, *part_thr, qbound, row_query, alonorm, xmax2, sh_one, sh_k, sh_rel, sh_abs);
     } else {
         if (kp != KP) { set_error("tc search: CTA pairs keep %d candidates per list", KP); return MO_RC_INTERNAL_ERROR; }
         // clusters of two CTAs (one TPC each): one persistent pair per two SMs
@@ -772,10 +810,21 @@ static int tc_run_units(ThreadCtx &t, const TcOperand &A, int64_t a_rows, const 
         at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         const float *an = A.enorm ? A.enorm : A.norm, *bn = B.enorm ? B.enorm : B.norm; int kp = nkb;
-        MOB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_candidates_kernel<true, KP>, map_a, map_b, (const TcUnit *)dunits, nunits, kp, an, bn, *part_d, *part_i, *part_thr));
+        MOB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_candidates_kernel<true, KP>, map_a, map_b, (const TcUnit *)dunits, nunits, kp, an, bn, *part_d, *part_i, *part_thr, qbound, row_query, alonorm, xmax2, sh_one, sh_k, sh_rel, sh_abs));
     }
     if (timed) cudaEventRecord(t.kev1, t.stream);
     MOB_LAUNCH_CHECK();
+    return MO_RC_SUCCESS;
+}
+
+// largest |x|^2 and |x - hi(x)|^2 over the row operand (the error bounds use them): two floats in the call's arena
+static int tc_operand_max(ThreadCtx &t, const TcOperand &B, int64_t n, bool with_lo, float **xmax2) {
+    *xmax2 = (float *)arena_alloc(t, 16);
+    if (!*xmax2) return MO_RC_INTERNAL_ERROR;
+    MOB_CUDA_TRY(cudaMemsetAsync(*xmax2, 0, 8, t.stream));
+    tc_max_kernel<<<num_sms() * 2, 256, 0, t.stream>>>(B.norm, n, *xmax2);
+    MOB_LAUNCH_CHECK();
+    if (with_lo) { tc_max_kernel<<<num_sms() * 2, 256, 0, t.stream>>>(B.lonorm, n, *xmax2 + 1); MOB_LAUNCH_CHECK(); }
     return MO_RC_SUCCESS;
 }
 
@@ -785,7 +834,7 @@ static int tc_finish(ThreadCtx &t, const float *ddata, int64_t n, int dim, const
                      const int64_t *id_map, int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d, std::vector<int> &redo,
                      const float *qlonorm = nullptr, const float *xlonorm = nullptr,   // both given: the candidate pass was hi-only (one term)
                      const float *pair_norm = nullptr, const float *pair_lonorm = nullptr,   // IVF: operand norms per (query, list) pair
-                     int kp = KP, int metric = MO_METRIC_L2SQ) {
+                     int kp = KP, int metric = MO_METRIC_L2SQ, float *xmax2_in = nullptr) {
     const bool l2 = metric != MO_METRIC_IP && metric != MO_METRIC_COS;
     const int one_term = xlonorm ? 1 : 0;
     const int kr = (k > KP || one_term) ? KR_WIDE : KR;   // a looser approximation needs more exact re-scores to prove the top k
@@ -794,11 +843,13 @@ static int tc_finish(ThreadCtx &t, const float *ddata, int64_t n, int dim, const
     float *t_excl = (float *)arena_alloc(t, sizeof(float) * (size_t)nq + 16);
     int *flags = (int *)arena_alloc(t, sizeof(int) * (size_t)nq);
     if (!cand || !exact || !t_excl || !flags) return MO_RC_INTERNAL_ERROR;
-    float *xmax = t_excl + nq, *xlomax = xmax + 1;
-    MOB_CUDA_TRY(cudaMemsetAsync(xmax, 0, 8, t.stream));
-    tc_max_kernel<<<num_sms() * 2, 256, 0, t.stream>>>(xnorm, n, xmax);
-    MOB_LAUNCH_CHECK();
-    if (one_term) { tc_max_kernel<<<num_sms() * 2, 256, 0, t.stream>>>(xlonorm, n, xlomax); MOB_LAUNCH_CHECK(); }
+    float *xmax = xmax2_in ? xmax2_in : t_excl + nq, *xlomax = xmax + 1;
+    if (!xmax2_in) {
+        MOB_CUDA_TRY(cudaMemsetAsync(xmax, 0, 8, t.stream));
+        tc_max_kernel<<<num_sms() * 2, 256, 0, t.stream>>>(xnorm, n, xmax);
+        MOB_LAUNCH_CHECK();
+        if (one_term) { tc_max_kernel<<<num_sms() * 2, 256, 0, t.stream>>>(xlonorm, n, xlomax); MOB_LAUNCH_CHECK(); }
+    }
     if (R > kMaxMergeLists) { set_error("tc search: %d candidate lists per query exceed the merge limit %d", R, kMaxMergeLists); return MO_RC_INTERNAL_ERROR; }
     tc_merge_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, t.stream>>>((int)nq, R, part_d, part_i, part_thr, pos_map, pos_cols, pos_stride, pair_norm, pair_lonorm, xmax, one_term, qnorm, qlonorm, l2 ? k : (1 << 30) /* pruning bound is L2-specific */, dim, kp, kr, cand, t_excl);
     MOB_LAUNCH_CHECK();
@@ -945,11 +996,17 @@ static int bf_tc_level(ThreadCtx &t, int level, int metric, const float *ddata, 
             if (u.n_begin < u.n_end) units.push_back(u);
         }
     float *part_d, *part_thr; int *part_i;
-    rc = tc_run_units(t, A, nq, B, n, units, (int64_t)R * nq, &part_d, &part_i, &part_thr, timed, pair, nkb);
+    float *xmax2 = nullptr;
+    rc = tc_operand_max(t, B, n, one_term, &xmax2);
+    if (rc) return rc;
+    // margins of the shared bound in kernel units: L2 relative 4 dim 2^-23; cosine absolute (its Go-order error does not scale with the distance)
+    TcShare sh{nq, nullptr, k, one_term ? 1 : 0, metric == MO_METRIC_COS ? 0.f : (float)dim * 4.76837158203125e-7f,
+               metric == MO_METRIC_COS ? 2.0f * ((float)dim * 4.76837158203125e-7f + 3.814697265625e-6f) : 0.f, xmax2};
+    rc = tc_run_units(t, A, nq, B, n, units, (int64_t)R * nq, &part_d, &part_i, &part_thr, timed, pair, nkb, KP, k <= KP ? &sh : nullptr);
     if (rc) return rc;
     std::vector<int> redo;
     rc = tc_finish(t, ddata, n, dim, dq, nq, k, R, nullptr, 0, 0, part_d, part_i, part_thr, A.norm, B.norm, nullptr, key_base, sqrt_out, out_k, out_d, redo,
-                   one_term ? A.lonorm : nullptr, one_term ? B.lonorm : nullptr, nullptr, nullptr, KP, metric);
+                   one_term ? A.lonorm : nullptr, one_term ? B.lonorm : nullptr, nullptr, nullptr, KP, metric, xmax2);
     if (rc) return rc;
     if (record_stats && level == 0) {
         g_last_tc_refined = (int)redo.size();
@@ -1063,12 +1120,16 @@ int ivf_tc_scan(ThreadCtx &t, const IvfPlan &plan, const float *ddata, int64_t n
     // (Measured alternative: two half-lists of 16 each made the kernel 16 % faster but left a few queries to the refine pass, whose
     // fixed cost outweighs that.)
     const int kp = one_term ? KP_LONG : KP;
-    rc = tc_run_units(t, A, plan.npairs, B, n, units, plan.npairs * split, &part_d, &part_i, &part_thr, !refine, false, one_term ? (dim + BK - 1) / BK : 0, kp);
+    float *xmax2 = nullptr;
+    rc = tc_operand_max(t, B, n, one_term, &xmax2);
+    if (rc) return rc;
+    TcShare sh{nq, plan.bucket_q, k, one_term ? 1 : 0, (float)dim * 4.76837158203125e-7f, 0.f, xmax2};
+    rc = tc_run_units(t, A, plan.npairs, B, n, units, plan.npairs * split, &part_d, &part_i, &part_thr, !refine, false, one_term ? (dim + BK - 1) / BK : 0, kp, &sh);
     if (rc) return rc;
     // the approximate lists are indexed by bucket position; tc_finish walks them per query through pair_pos; the final keys are
     // the primary keys row_ids[local row]; every probed list's exclusion bound is lowered by the error bound of ITS operand pair
     rc = tc_finish(t, ddata, n, dim, dq, nq, k, plan.nprobe * split, plan.pair_pos, plan.nprobe, plan.npairs, part_d, part_i, part_thr, nullptr, B.norm, drowids, 0,
-                   sqrt_out, ok, od, redo, nullptr, one_term ? B.lonorm : nullptr, A.norm, A.lonorm, kp);
+                   sqrt_out, ok, od, redo, nullptr, one_term ? B.lonorm : nullptr, A.norm, A.lonorm, kp, MO_METRIC_L2SQ, xmax2);
     return rc;
 }
 

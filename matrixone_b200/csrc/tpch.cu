@@ -557,7 +557,7 @@ namespace mob {
 unsigned long long *q1_debug_buffer() { return g_q1_dbg; }
 
 extern int g_search_mode;
-extern int g_last_tc_fallbacks, g_last_tc_refined, g_tc_pair_mode, g_tc_range_mb, g_tc_ladder_mode, g_last_tc_kused, g_one_term_skip;
+extern int g_last_tc_fallbacks, g_last_tc_refined, g_tc_pair_mode, g_tc_range_mb, g_tc_ladder_mode, g_last_tc_kused, g_one_term_skip, g_tc_share_mode;
 
 int tuning_set(const char *name, int value) {
     if (!strcmp(name, "search_mode")) { g_search_mode = value; return 0; }
@@ -567,6 +567,7 @@ int tuning_set(const char *name, int value) {
     if (!strcmp(name, "tc_range_mb")) { g_tc_range_mb = (int)value; return 0; }
     if (!strcmp(name, "tc_ladder")) { g_tc_ladder_mode = (int)value; g_one_term_skip = 0; return 0; }
     if (!strcmp(name, "get_tc_kused")) return g_last_tc_kused;
+    if (!strcmp(name, "tc_share")) { g_tc_share_mode = (int)value; return 0; }
     if (!strcmp(name, "q6_variant")) { g_q6_variant = value; return 0; }
     if (!strcmp(name, "q1_variant")) { g_q1_variant = value; return 0; }
     if (!strcmp(name, "q1_debug")) {
