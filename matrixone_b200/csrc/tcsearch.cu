@@ -611,6 +611,32 @@ tc_rescore_kernel(const float *__restrict__ data, const float *__restrict__ quer
     }
 }
 
+// IVF: seed the shared bound of every query with the exact k-th distance among the first 32 rows of its nearest list -- loose
+// (k-th of 32 instead of k-th of ~nprobe lists), but enough to keep the rows of far lists out of the candidate lists from the
+// first tile on.  One warp per query, lane = row, through the same batch machinery as the re-score.
+__global__ void __launch_bounds__(kRescoreThreads)
+ivf_seed_bound_kernel(const float *__restrict__ data, const float *__restrict__ queries, int dim, int nq, int nprobe, int k,
+                      const int64_t *__restrict__ probes, const int64_t *__restrict__ offsets, float *__restrict__ qbound) {
+    using Cfg = godist::RingCfg<false>;
+    extern __shared__ __align__(16) unsigned char rescore_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    unsigned char *ring = rescore_smem + (size_t)wib * Cfg::kStages * Cfg::kStageBytes;
+    const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t q = w0; q < nq; q += nw) {
+        const int64_t l = probes[q * nprobe];
+        const int64_t b = l >= 0 ? offsets[l] : 0, e = l >= 0 ? offsets[l + 1] : 0;
+        const bool good = b + lane < e;
+        const uint8_t *px = good ? reinterpret_cast<const uint8_t *>(data + (b + lane) * dim) : nullptr;
+        const uint8_t *pq = reinterpret_cast<const uint8_t *>(queries + q * dim);
+        const godist::RowAcc<float, godist::K_GO_L2SQ> acc = godist::row_batch<float, godist::K_GO_L2SQ, false>(ring, lane, px, pq, dim, good);
+        const float d = good ? acc.sum : INFINITY;
+        int rank = 0;
+        for (int j = 0; j < 32; j++) { const float o = __shfl_sync(0xffffffffu, d, j); rank += (o < d || (o == d && j < lane)) ? 1 : 0; }
+        // the lane holding the k-th smallest: its Go-order value, inflated by the Go-order error, bounds the real k-th distance
+        if (rank == k - 1 && d < INFINITY) qbound[q] = d * (1.0f + (float)dim * 2.384185791015625e-7f);
+    }
+}
+
 __global__ void tc_max_kernel(const float *__restrict__ v, int64_t n, float *out) {   // max of non-negative floats
     float m = 0.f;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, v[i]);
@@ -751,7 +777,7 @@ static int tc_prepare_ivf_entries(ThreadCtx &t, const float *x, int64_t n, int d
 
 // run the candidate kernel over `units`; lists are written at unit.out_base + row (nlists lists in total, pre-initialised empty)
 // cross-unit threshold sharing (see the kernel): nq queries, row_query maps an A row to its query (nullptr: identity)
-struct TcShare { int64_t nq; const int *row_query; int topk; int one_term; float rel_margin, abs_margin; const float *xmax2; };
+struct TcShare { int64_t nq; const int *row_query; int topk; int one_term; float rel_margin, abs_margin; const float *xmax2; float *qbound = nullptr; };   // qbound: pre-seeded bounds (else +inf)
 __global__ void tc_fill_inf_kernel(float *p, int64_t n) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = INFINITY;
 }
@@ -787,10 +813,13 @@ static int tc_run_units(ThreadCtx &t, const TcOperand &A, int64_t a_rows, const 
     float *qbound = nullptr; const int *row_query = nullptr; const float *alonorm = A.lonorm, *xmax2 = nullptr;
     int sh_one = 0, sh_k = 0; float sh_rel = 0.f, sh_abs = 0.f;
     if (share && !A.enorm && !B.enorm && g_tc_share_mode != 1) {   // inner product leaves the norms out of the epilogue: no sharing there
-        qbound = (float *)arena_alloc(t, (size_t)share->nq * 4);
-        if (!qbound) return MO_RC_INTERNAL_ERROR;
-        tc_fill_inf_kernel<<<num_sms() * 2, 256, 0, t.stream>>>(qbound, share->nq);
-        MOB_LAUNCH_CHECK();
+        qbound = share->qbound;
+        if (!qbound) {
+            qbound = (float *)arena_alloc(t, (size_t)share->nq * 4);
+            if (!qbound) return MO_RC_INTERNAL_ERROR;
+            tc_fill_inf_kernel<<<num_sms() * 2, 256, 0, t.stream>>>(qbound, share->nq);
+            MOB_LAUNCH_CHECK();
+        }
         row_query = share->row_query; xmax2 = share->xmax2; sh_one = share->one_term; sh_k = share->topk; sh_rel = share->rel_margin; sh_abs = share->abs_margin;
     }
     if (timed) { t.kev_prio = 2; g_last_tc_kused = nkb * BK; cudaEventRecord(t.kev0, t.stream); }   // MoB200_LastKernelMs reports the first (whole-list) pass, not the refine pass
@@ -1124,6 +1153,19 @@ int ivf_tc_scan(ThreadCtx &t, const IvfPlan &plan, const float *ddata, int64_t n
     rc = tc_operand_max(t, B, n, one_term, &xmax2);
     if (rc) return rc;
     TcShare sh{nq, plan.bucket_q, k, one_term ? 1 : 0, (float)dim * 4.76837158203125e-7f, 0.f, xmax2};
+    if (k <= 32 && g_tc_share_mode == 0) {
+        sh.qbound = (float *)arena_alloc(t, (size_t)nq * 4);
+        if (!sh.qbound) return MO_RC_INTERNAL_ERROR;
+        tc_fill_inf_kernel<<<num_sms() * 2, 256, 0, t.stream>>>(sh.qbound, nq);
+        MOB_LAUNCH_CHECK();
+        const size_t smem = (size_t)(kRescoreThreads / 32) * godist::RingCfg<false>::kStages * godist::RingCfg<false>::kStageBytes;
+        static bool attr = false;
+        if (!attr) { MOB_CUDA_TRY(cudaFuncSetAttribute(ivf_seed_bound_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+        int64_t blocks = (nq + kRescoreThreads / 32 - 1) / (kRescoreThreads / 32);
+        if (blocks > 2ll * num_sms()) blocks = 2ll * num_sms();
+        ivf_seed_bound_kernel<<<(unsigned)blocks, kRescoreThreads, smem, t.stream>>>(ddata, dq, dim, (int)nq, plan.nprobe, k, plan.probes, doffsets, sh.qbound);
+        MOB_LAUNCH_CHECK();
+    }
     rc = tc_run_units(t, A, plan.npairs, B, n, units, plan.npairs * split, &part_d, &part_i, &part_thr, !refine, false, one_term ? (dim + BK - 1) / BK : 0, kp, &sh);
     if (rc) return rc;
     // the approximate lists are indexed by bucket position; tc_finish walks them per query through pair_pos; the final keys are
