@@ -362,16 +362,39 @@ def main():
         n = n_local
 
     gather_buf = None
+    search_dev = None
     if dist is not None:
         import torch
         send = torch.zeros(rec_bytes, dtype=torch.uint8, device="cuda")
         gather_buf = torch.zeros(rec_bytes * world, dtype=torch.uint8, device="cuda")
+        if args.workload in ("bruteforce", "ivf"):
+            # MergeTop seam kept on the device: every rank's (keys, distances) go from the search kernels' output buffers through
+            # NCCL into the merge kernel; the host sees only the final top-k
+            search_dev = {"k": torch.empty(nq * k, dtype=torch.int64, device="cuda"), "d": torch.empty(nq * k, dtype=torch.float64, device="cuda"),
+                          "gk": torch.empty(world * nq * k, dtype=torch.int64, device="cuda"), "gd": torch.empty(world * nq * k, dtype=torch.float64, device="cuda"),
+                          "ok": torch.empty(nq * k, dtype=torch.int64, device="cuda"), "od": torch.empty(nq * k, dtype=torch.float64, device="cuda")}
+            host_step = step
+            def step(cols=bufs):
+                if cols is not bufs:          # e2e arm: host queries in, host results out
+                    return host_step(cols)
+                out = (search_dev["k"].data_ptr(), search_dev["d"].data_ptr())
+                if args.workload == "ivf":
+                    ivf.search(cols["queries"], k, nprobe, out=out)
+                else:
+                    idx.search(cols["queries"], k, out=out)
+                return None
 
     def exchange(res):
         """the reduce seam (MergeGroup / MergeTop): all ranks receive every rank's partial record"""
         if dist is None:
             return
         import torch
+        if search_dev is not None and res is None:
+            dist.all_gather_into_tensor(search_dev["gk"], search_dev["k"])
+            dist.all_gather_into_tensor(search_dev["gd"], search_dev["d"])
+            torch.cuda.current_stream().synchronize()     # NCCL ran on torch's stream, the merge kernel runs on the library's
+            ops.topk_merge_device(search_dev["gk"].data_ptr(), search_dev["gd"].data_ptr(), world, nq, k, search_dev["ok"].data_ptr(), search_dev["od"].data_ptr())
+            return search_dev["ok"].cpu().numpy(), search_dev["od"].cpu().numpy()
         send.copy_(torch.frombuffer(bytearray(pack(res)), dtype=torch.uint8))
         dist.all_gather_into_tensor(gather_buf, send)
         return merge(gather_buf.cpu().numpy().tobytes())
@@ -380,8 +403,17 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()          # started before the warm-up: nvidia-smi needs ~100 ms to deliver its first sample
-    for _ in range(W):
-        exchange(step())
+    for wi in range(W):
+        merged = exchange(step())
+        if wi == 0 and search_dev is not None:
+            # the device-side MergeTop seam must give what the host-side one (shard.py, covered by the gloo CPU test) gives
+            import torch
+            hres = host_step(bufs)
+            send.copy_(torch.frombuffer(bytearray(pack(hres)), dtype=torch.uint8))
+            dist.all_gather_into_tensor(gather_buf, send)
+            hk, hd = merge(gather_buf.cpu().numpy().tobytes())
+            if not (np.array_equal(hk, merged[0]) and np.array_equal(hd, merged[1])):
+                raise SystemExit("device-side top-k exchange disagrees with the host-side merge")
     if rank == 0:
         time.sleep(0.25)
     barrier_sync()

@@ -144,7 +144,9 @@ class BruteForceIndex:
         if self.prepared:
             capi.check(self.lib.MoB200_SearchPrepareMetric(self.buf.ptr, self.n, self.dim, self.metric), self.lib)
 
-    def search(self, queries, limit, out_device=False):
+    def search(self, queries, limit, out_device=False, out=None):
+        """out = (keys_device_ptr, distances_device_ptr): results stay in caller-owned device memory (int64 / float64, nq*limit
+        each) and nothing is returned -- the form a multi-GPU caller hands straight to NCCL"""
         if isinstance(queries, DeviceBuffer):
             nq = queries.nbytes // (4 * self.dim)
             qv = Vector(data_ptr=queries.ptr, data_nbytes=queries.nbytes, length=nq)
@@ -154,10 +156,15 @@ class BruteForceIndex:
             qv = Vector(data=q.reshape(-1), length=nq)
         if limit == 0 or nq == 0:
             return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.float64)
-        keys = np.zeros(nq * limit, dtype=np.int64)
-        dists = np.zeros(nq * limit, dtype=np.float64)
         p = _search_params(self.n, self.dim, nq, limit, self.metric, key_base=self.key_base)
         dv = Vector(data_ptr=self.buf.ptr, data_nbytes=self.n * self.dim * 4, length=self.n)
+        if out is not None:
+            kv = Vector(data_ptr=out[0], data_nbytes=nq * limit * 8, length=nq)
+            dvv = Vector(data_ptr=out[1], data_nbytes=nq * limit * 8, length=nq)
+            xcall(capi.XCALL_BRUTEFORCE_TOPK_F32, [kv, dvv, dv, qv, _params_vec(p)], nq)
+            return None
+        keys = np.zeros(nq * limit, dtype=np.int64)
+        dists = np.zeros(nq * limit, dtype=np.float64)
         xcall(capi.XCALL_BRUTEFORCE_TOPK_F32, [Vector(data=keys, length=nq), Vector(data=dists, length=nq), dv, qv, _params_vec(p)], nq)
         return keys, dists
 
@@ -216,7 +223,7 @@ class IvfflatSearchIndex:
         cidx.destroy()
         return cls(data_dev, assign, centroids, metric, lib)
 
-    def search(self, queries, limit, nprobe, sqrt_out=False):
+    def search(self, queries, limit, nprobe, sqrt_out=False, out=None):
         if isinstance(queries, DeviceBuffer):
             nq = queries.nbytes // (4 * self.dim)
             qvec = Vector(data_ptr=queries.ptr, data_nbytes=queries.nbytes, length=nq)
@@ -224,11 +231,17 @@ class IvfflatSearchIndex:
             q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dim)
             nq = q.shape[0]
             qvec = Vector(data=q.reshape(-1), length=nq)
-        keys = np.zeros(nq * limit, dtype=np.int64)
-        dists = np.zeros(nq * limit, dtype=np.float64)
+        if out is not None:     # results stay in caller-owned device memory (see BruteForceIndex.search)
+            keys = dists = None
+            kv = Vector(data_ptr=out[0], data_nbytes=nq * limit * 8, length=nq)
+            dvv = Vector(data_ptr=out[1], data_nbytes=nq * limit * 8, length=nq)
+        else:
+            keys = np.zeros(nq * limit, dtype=np.int64)
+            dists = np.zeros(nq * limit, dtype=np.float64)
+            kv, dvv = Vector(data=keys, length=nq), Vector(data=dists, length=nq)
         p = _search_params(self.n, self.dim, nq, limit, self.metric, nprobe=nprobe, sqrt_out=int(sqrt_out), nlist=self.nlist)
         xcall(capi.XCALL_IVF_TOPK_F32, [
-            Vector(data=keys, length=nq), Vector(data=dists, length=nq),
+            kv, dvv,
             Vector(data_ptr=self.d_data.ptr, data_nbytes=self.d_data.nbytes, length=self.n),
             qvec, _params_vec(p),
             Vector(data_ptr=self.d_cent.ptr, data_nbytes=self.d_cent.nbytes, length=self.nlist),
@@ -241,6 +254,14 @@ class IvfflatSearchIndex:
             self.lib.MoB200_SearchRelease(self.d_data.ptr)
         for b in (self.d_data, self.d_cent, self.d_off, self.d_ids):
             b.free()
+
+
+def topk_merge_device(keys_ptr, dists_ptr, nshards, nq, k, out_keys_ptr, out_dists_ptr):
+    """topk_merge on device-resident [nshards, nq, k] results (e.g. straight out of an NCCL all_gather); outputs stay on the device"""
+    p = _search_params(nshards, 0, nq, k, 0)
+    xcall(capi.XCALL_TOPK_MERGE, [Vector(data_ptr=out_keys_ptr, data_nbytes=nq * k * 8, length=nq), Vector(data_ptr=out_dists_ptr, data_nbytes=nq * k * 8, length=nq),
+                                  Vector(data_ptr=keys_ptr, data_nbytes=nshards * nq * k * 8, length=nq),
+                                  Vector(data_ptr=dists_ptr, data_nbytes=nshards * nq * k * 8, length=nq), _params_vec(p)], nq)
 
 
 def topk_merge(keys_shards, dists_shards, nq, k):
