@@ -168,6 +168,27 @@ typedef struct mo_xcall_args_t {
  * args: [0] result f64 (+ 1-word nulls bitmap, bit0 = no row qualified) ; [1] d int32/DATE col ; [2] b f64 col
  * (discount) ; [3] c f64 col (quantity) ; [4] a f64 col (extendedprice) ; [5] params: pdata -> mo_q6_params_t.
  * Optional second result word: if args[0].dataSz >= 16 the qualifying row count (int64) is written at pdata+8. */
+/* ---- The Go elementwise engine's conventions (pkg/sql/plan/function/baseTemplate.go:457-728, arithmetic.go:222-762,
+ * func_compare.go:285-1185, operator_between.go:138-199, logicalOperator.go:36-168) -- the LIVE per-batch path of the reference;
+ * the mo.h symbols above keep the C kernels' conventions.  Differences: rows whose RESULT null bit is set on entry are skipped
+ * (the caller pre-fills args[0].pnulls with NOT selectList, baseTemplate.go:473-486); on return it holds rnulls | n1 | n2 (plus
+ * the rows a zero divisor nulled); a const operand is a 1-element vector (dataSz == sizeof(T)), a const NULL operand nulls every
+ * row; the FIRST offending row in row order fails the call (MO_RC_OUT_OF_RANGE with "data out of range: data type int64, value
+ * '(a + b)'" / MO_RC_DIVISION_BY_ZERO) and its index is stored in the parameter block; rows before it hold their results.
+ *   ARITH(op, T)   op: 0 + 1 - 2 * 3 / (floats) 4 %     args: [0] result T[len] + pnulls (in/out)  [1] a  [2] b  [3] mo_go_params_t
+ *   COMPARE(op, T) op: 0 == 1 != 2 > 3 >= 4 < 5 <=      args: [0] result bool[len] + pnulls (in/out)  [1] a  [2] b
+ *   BETWEEN(T)                                           args: [0] result bool[len] + pnulls (in/out)  [1] column (+ pnulls)  [2] lo  [3] hi
+ *                                                        null input -> result false AND null bit set
+ *   MULTI_AND / MULTI_OR                                 args: [0] result bool[len] + pnulls (out)  [1] int32 operand count n (<= 16)
+ *                                                              [2 .. 2 + n) bool operands (+ pnulls); const = 1 byte
+ * T = types.T id (MO_T_*); DATE compares as int32, TIME / DATETIME / TIMESTAMP as int64. */
+typedef struct { int32_t div0_null; int32_t reserved; int64_t err_row; } mo_go_params_t;   /* err_row: out, -1 = no error */
+#define MO_XCALL_GO_ARITH(op, T) (0x4000 + ((op) << 8) + (T))
+#define MO_XCALL_GO_COMPARE(op, T) (0x4800 + ((op) << 8) + (T))
+#define MO_XCALL_GO_BETWEEN(T) (0x5000 + (T))
+#define MO_XCALL_GO_MULTI_AND 0x5100
+#define MO_XCALL_GO_MULTI_OR 0x5101
+
 #define MO_XCALL_Q6_FILTER_SUM 0x2000
 typedef struct mo_q6_params_t {
     int32_t date_lo, date_hi;  /* date_lo <= d < date_hi */

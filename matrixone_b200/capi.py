@@ -46,6 +46,21 @@ XCALL_BRUTEFORCE_TOPK_F32 = 0x3000
 XCALL_IVF_TOPK_F32 = 0x3001
 XCALL_TOPK_MERGE = 0x3002
 METRIC_L2, METRIC_IP, METRIC_COS, METRIC_L1, METRIC_L2SQ = 0, 1, 2, 3, 4
+
+
+def XCALL_GO_ARITH(op, T):
+    return 0x4000 + (op << 8) + T
+
+
+def XCALL_GO_COMPARE(op, T):
+    return 0x4800 + (op << 8) + T
+
+
+def XCALL_GO_BETWEEN(T):
+    return 0x5000 + T
+
+
+XCALL_GO_MULTI_AND, XCALL_GO_MULTI_OR = 0x5100, 0x5101
 Q1_MAX_GROUPS = 8
 
 
