@@ -100,20 +100,55 @@ go_arith_kernel(T *__restrict__ r, const T *__restrict__ a, const T *__restrict_
     }
 }
 
+template <typename T> __device__ __forceinline__ bool go_cmp(T x, T y, int op) {
+    switch (op) {
+    case CMP_EQ: return x == y; case CMP_NE: return x != y;
+    case CMP_GT: return x > y;  case CMP_GE: return x >= y;
+    case CMP_LT: return x < y;  default: return x <= y;
+    }
+}
+// 8 consecutive rows of a column as 128-bit loads (the group never straddles a bitmap word: 8 | 64)
+template <typename T> __device__ __forceinline__ void load8(const T *p, uint64_t i0, bool cst, T *out) {
+    if (cst) {
+        const T v = p[0];
+#pragma unroll
+        for (int j = 0; j < 8; j++) out[j] = v;
+    } else if (sizeof(T) >= 2) {
+        constexpr int NV = (int)(sizeof(T) * 8 / 16);
+        const int4 *q = reinterpret_cast<const int4 *>(p + i0);
+#pragma unroll
+        for (int v = 0; v < NV; v++) { const int4 w = ld_stream16(q + v); memcpy(reinterpret_cast<char *>(out) + 16 * v, &w, 16); }
+    } else {
+        const uint64_t w = *reinterpret_cast<const uint64_t *>(p + i0);
+        memcpy(out, &w, 8);
+    }
+}
+
+// compare: a thread owns 8 consecutive rows -> one 8-byte store of the bool results when none of them is null
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 go_compare_kernel(uint8_t *__restrict__ r, const T *__restrict__ a, const T *__restrict__ b, uint64_t n, int c1, int c2,
-                  const uint64_t *__restrict__ rnulls, int op) {
-    for (uint64_t i = blockIdx.x * (uint64_t)kThreads + threadIdx.x; i < n; i += (uint64_t)gridDim.x * kThreads) {
-        if (bm_test(rnulls, i)) continue;
-        const T x = a[c1 ? 0 : i], y = b[c2 ? 0 : i];
-        bool v;
-        switch (op) {
-        case CMP_EQ: v = x == y; break; case CMP_NE: v = x != y; break;
-        case CMP_GT: v = x > y; break;  case CMP_GE: v = x >= y; break;
-        case CMP_LT: v = x < y; break;  default: v = x <= y; break;
+                  const uint64_t *__restrict__ rnulls, int op, int vec_ok) {
+    const uint64_t ngroups = vec_ok ? n / 8 : 0;
+    for (uint64_t g = blockIdx.x * (uint64_t)kThreads + threadIdx.x; g < ngroups; g += (uint64_t)gridDim.x * kThreads) {
+        const uint64_t i0 = g * 8;
+        const unsigned nb = (unsigned)((rnulls[i0 >> 6] >> (i0 & 63)) & 0xffu);
+        if (nb == 0xffu) continue;
+        T x[8], y[8];
+        load8<T>(a, i0, c1 != 0, x); load8<T>(b, i0, c2 != 0, y);
+        uint64_t packed = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) packed |= (uint64_t)(go_cmp<T>(x[j], y[j], op) ? 1 : 0) << (8 * j);
+        if (nb == 0) *reinterpret_cast<uint64_t *>(r + i0) = packed;
+        else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) if (!((nb >> j) & 1u)) r[i0 + j] = (uint8_t)(packed >> (8 * j));
         }
-        r[i] = v ? 1 : 0;
+    }
+    // rows not covered by whole groups (all rows when the buffers are not 16-byte aligned)
+    for (uint64_t i = ngroups * 8 + blockIdx.x * (uint64_t)kThreads + threadIdx.x; i < n; i += (uint64_t)gridDim.x * kThreads) {
+        if (bm_test(rnulls, i)) continue;
+        r[i] = go_cmp<T>(a[c1 ? 0 : i], b[c2 ? 0 : i], op) ? 1 : 0;
     }
 }
 
@@ -305,7 +340,8 @@ int run_go_compare(ThreadCtx &t, int op, mo_xcall_args_t *args, uint64_t len) {
     MOB_LAUNCH_CHECK();
     if (!all_null) {
         cudaEventRecord(t.kev0, t.stream);
-        go_compare_kernel<T><<<grid_rows(len), kThreads, 0, t.stream>>>(r, a, b, len, c1 ? 1 : 0, c2 ? 1 : 0, rn, op);
+        const int vec_ok = ((((uintptr_t)r) | ((uintptr_t)a) | ((uintptr_t)b)) & 15) == 0 ? 1 : 0;
+        go_compare_kernel<T><<<grid_rows(vec_ok ? (len + 7) / 8 : len), kThreads, 0, t.stream>>>(r, a, b, len, c1 ? 1 : 0, c2 ? 1 : 0, rn, op, vec_ok);
         cudaEventRecord(t.kev1, t.stream);
         MOB_LAUNCH_CHECK();
     }

@@ -98,6 +98,19 @@ def main():
                 fn()
             ms = (time.perf_counter() - t0) / 5 * 1e3
             report(name, ms, ms, nb, rows=rows, timer="wall clock incl. sync")
+        # the Go-convention ops (goelem.cu): result nulls in/out, first-offender status
+        rn = DeviceBuffer(8 * ((rows + 63) // 64), lib)
+        capi.check(lib.MoB200_Memset(rn.ptr, 0, rn.nbytes), lib)
+        params = np.zeros(2, dtype=np.int64)
+        for name, fid, nb, rsz in (("go_add_i64", capi.XCALL_GO_ARITH(0, capi.T_INT64), 24.125 * rows, 8), ("go_lt_i64", capi.XCALL_GO_COMPARE(4, capi.T_INT64), 17.125 * rows, 1)):
+            args = [Vector(data_ptr=r.ptr, data_nbytes=rsz * rows, nulls_ptr=rn.ptr, length=rows), Vector(data_ptr=a.ptr, data_nbytes=8 * rows, length=rows),
+                    Vector(data_ptr=bb.ptr, data_nbytes=8 * rows, length=rows), Vector(data=params.view(np.uint8), length=rows)]
+            xcall(fid, args, rows); xcall(fid, args, rows)
+            ks = []
+            for _ in range(5):
+                xcall(fid, args, rows); ks.append(kms())
+            report(name, float(np.median(ks)), min(ks), nb, rows=rows)
+        rn.free()
         for x in (a, bb, r):
             x.free()
     if "dist" in which:
