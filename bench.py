@@ -112,6 +112,21 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(section, default_size):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full` capture
+    of this very command (profiles/r01_ncu_summary.md, written by tools/summarize_ncu.py).  Only meaningful at the size the
+    capture was taken at, so None for any other --rows."""
+    if not default_size:
+        return None
+    try:
+        txt = open(os.path.join(ROOT, "profiles", "r01_ncu_summary.md")).read()
+        sec = txt.split("## %s -- " % section, 1)[1].split("\n## ", 1)[0]
+        gb = float(sec.split("DRAM traffic per launch = ", 1)[1].split(" GB", 1)[0])
+        return gb * 1e9
+    except Exception:
+        return None
+
+
 # =====================================================================================================================
 # CPU reference arm / cpu_baseline: the oracle port on the host cores
 # =====================================================================================================================
@@ -508,14 +523,17 @@ def main():
         except Exception:
             tpeak, tsrc = 1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s)"
         ach = flop / (kern_ms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": None,
+        roofline = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak,
+                    "traffic": ncu_traffic("tc_ivf", n == 1_250_000 and args.queries == 10_000),
                     "kernel": "tc_candidates_kernel (tcgen05 bf16, K = %d per pair) over (list, query-tile) units" % kused, "kernel_ms": kern_ms, "algorithmic_flop_per_launch": flop,
-                    "peak_source": tsrc, "tc_refined_queries": int(lib.MoB200_SetTuning(b"get_tc_refined", 0)),
+                    "peak_source": tsrc, "traffic_source": "profiles/r01_ncu_summary.md (ncu --set full capture of this command; null at other sizes)",
+                    "tc_refined_queries": int(lib.MoB200_SetTuning(b"get_tc_refined", 0)),
                     "tc_fallback_queries": int(lib.MoB200_SetTuning(b"get_tc_fallbacks", 0)),
                     "note": "useful flop only: tiles are padded to 128 queries x 256 rows, so the tensor pipe does more work than counted"}
     elif alg_bytes is not None:
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": ncu_traffic({"q6": "q6", "q1": "q1", "sum": None}[args.workload], args.rows == 0) if args.workload != "sum" else None,
                     "kernel": {"q6": "q6_kernel", "q1": "q1_kernel", "sum": "agg_kernel"}[args.workload], "kernel_ms": kern_ms,
                     "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src}
     else:
@@ -530,7 +548,8 @@ def main():
         except Exception:
             tpeak, tsrc = 1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s)"
         ach = flop / (kern_ms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": None,
+        roofline = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak,
+                    "traffic": ncu_traffic("tc_bruteforce", args.rows == 0 and args.queries == 10_000 and args.metric == "l2" and world == 1),
                     "kernel": "tc_candidates_kernel (tcgen05 bf16, K = %d per pair)" % kused, "kernel_ms": kern_ms, "algorithmic_flop_per_launch": flop, "peak_source": tsrc,
                     "tc_refined_queries": int(lib.MoB200_SetTuning(b"get_tc_refined", 0)),
                     "tc_fallback_queries": int(lib.MoB200_SetTuning(b"get_tc_fallbacks", 0))}
