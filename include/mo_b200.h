@@ -163,6 +163,16 @@ typedef struct mo_xcall_args_t {
 #define MO_AGG_MAX 3
 #define MO_AGG_AVG 4     /* result float64 = sum/cnt, NULL when cnt == 0 */
 #define MO_XCALL_AGG(op, T) (0x1000 + ((op) << 8) + (T))
+/* Wider results: dataSz >= 16 adds the non-null row count at pdata+8; dataSz >= 24 makes the result a PARTIAL STATE
+ * mo_agg_state_t {value bits (SUM/AVG: the sum in the SUM return type; AVG is NOT divided yet), non-null rows, rc} -- what a partial
+ * Group hands to MergeGroup (pkg/sql/colexec/group/mergeGroup.go:132-247).
+ * Asynchronous form: when the column AND the result (pdata, pnulls) are DEVICE pointers the call only enqueues work on the calling
+ * thread's stream and returns MO_RC_SUCCESS at once; errors detected on the device (SUM overflow) are reported in state.rc. */
+typedef struct mo_agg_state_t { uint64_t bits; int64_t count; int64_t rc; } mo_agg_state_t;
+/* MergeGroup for these aggregates: args [0] result (8 / 16 / 24 bytes as above, + nulls word) ; [1] len partial states (24 bytes each),
+ * folded in order with the reference's BatchMerge rules (sumavg2.go:205-248 incl. int64OfCheck / uint64OfCheck, minmax2.go:90-110).
+ * Device pointers on both sides: asynchronous as above. */
+#define MO_XCALL_AGG_MERGE(op, T) (0x1800 + ((op) << 8) + (T))
 
 /* --- new: fused TPC-H Q6 shape  SUM(a*b) WHERE d in [d_lo,d_hi) AND b BETWEEN b_lo AND b_hi AND c < c_hi
  * args: [0] result f64 (+ 1-word nulls bitmap, bit0 = no row qualified) ; [1] d int32/DATE col ; [2] b f64 col
@@ -185,6 +195,9 @@ typedef struct mo_xcall_args_t {
 typedef struct { int32_t div0_null; int32_t reserved; int64_t err_row; } mo_go_params_t;   /* err_row: out, -1 = no error */
 #define MO_XCALL_GO_ARITH(op, T) (0x4000 + ((op) << 8) + (T))
 #define MO_XCALL_GO_COMPARE(op, T) (0x4800 + ((op) << 8) + (T))
+/* float32 columns declared with scale > 0 compare after rounding both sides to `scale` decimals (func_compare.go:207-216,725-734,
+ * 852-861,979-988,1106-1115,1233-1242): same args as COMPARE(op, MO_T_FLOAT32), scale 1..22 */
+#define MO_XCALL_GO_COMPARE_F32_SCALE(op, scale) (0x5200 + ((op) << 8) + (scale))
 #define MO_XCALL_GO_BETWEEN(T) (0x5000 + (T))
 #define MO_XCALL_GO_MULTI_AND 0x5100
 #define MO_XCALL_GO_MULTI_OR 0x5101
@@ -196,11 +209,24 @@ typedef struct mo_q6_params_t {
     double qty_hi;             /* c < qty_hi */
 } mo_q6_params_t;
 
+/* Asynchronous form: device columns AND a device result (pdata 16 bytes = {f64 sum, i64 qualifying rows}, pnulls device or NULL): the
+ * call enqueues the kernel on the calling thread's stream and returns at once.
+ * MO_XCALL_Q6_MERGE (MergeGroup): args [0] result as above ; [1] len partial results of 16 bytes each, added in order; an empty partial
+ * (count 0) is NULL and skipped (sumavg2.go:222-236). */
+#define MO_XCALL_Q6_MERGE 0x2002
+
 /* --- new: fused TPC-H Q1 shape: filter d <= cutoff, group by two 1-byte keys, 8 aggregates (q1.sql:5-12).
  * args: [0] result: pdata -> mo_q1_result_t ; [1] shipdate int32 ; [2] quantity f64 ; [3] extendedprice f64 ;
  * [4] discount f64 ; [5] tax f64 ; [6] returnflag ; [7] linestatus ; [8] params: pdata -> int32 cutoff.
  * Key columns: dataSz == len -> packed uint8 column; dataSz == 24*len -> MatrixOne varlena cells (inline char(1)). */
 #define MO_XCALL_Q1_GROUP_AGG 0x2001
+/* args[8] may also hold mo_q1_params_t (dataSz >= 16): row_base is added to every first_row (the block-range offset of this shard), so
+ * partial results of different shards order their groups globally.  Asynchronous form as for Q6 (device columns + device result);
+ * there "more than MO_Q1_MAX_GROUPS keys" is reported as ngroups = -1 instead of MO_RC_INVALID_ARGUMENT.
+ * MO_XCALL_Q1_MERGE (MergeGroup): args [0] mo_q1_result_t ; [1] len partial mo_q1_result_t, merged in order, groups re-sorted by
+ * first_row, averages recomputed from the merged sums and counts. */
+#define MO_XCALL_Q1_MERGE 0x2003
+typedef struct mo_q1_params_t { int32_t cutoff; int32_t reserved; int64_t row_base; } mo_q1_params_t;
 #define MO_Q1_MAX_GROUPS 8
 typedef struct mo_q1_group_t {
     uint8_t returnflag, linestatus; uint8_t pad[6];
@@ -257,6 +283,8 @@ int32_t MoB200_HostRegister(void *hptr, uint64_t bytes);
 int32_t MoB200_HostUnregister(void *hptr);
 int32_t MoB200_Upload(void *dst_dev, const void *src_host, uint64_t bytes);   /* on the calling thread's stream, synchronous */
 int32_t MoB200_Download(void *dst_host, const void *src_dev, uint64_t bytes);
+int32_t MoB200_DownloadAsync(void *dst_host, const void *src_dev, uint64_t bytes);  /* stream-ordered, NO synchronise (pinned host memory) */
+int32_t MoB200_UploadAsync(void *dst_dev, const void *src_host, uint64_t bytes);
 int32_t MoB200_Memset(void *dst_dev, int32_t value, uint64_t bytes);
 int32_t MoB200_Sync(void);                    /* synchronize the calling thread's stream */
 int32_t MoB200_SetStream(void *cuda_stream);  /* adopt an external cudaStream_t for the calling thread (NULL = own) */

@@ -40,8 +40,15 @@ def XCALL_AGG(op, T):
     return 0x1000 + (op << 8) + T
 
 
+def XCALL_AGG_MERGE(op, T):
+    return 0x1800 + (op << 8) + T
+
+
 XCALL_Q6_FILTER_SUM = 0x2000
 XCALL_Q1_GROUP_AGG = 0x2001
+XCALL_Q6_MERGE = 0x2002
+XCALL_Q1_MERGE = 0x2003
+AGG_STATE_BYTES = 24
 XCALL_BRUTEFORCE_TOPK_F32 = 0x3000
 XCALL_IVF_TOPK_F32 = 0x3001
 XCALL_TOPK_MERGE = 0x3002
@@ -54,6 +61,10 @@ def XCALL_GO_ARITH(op, T):
 
 def XCALL_GO_COMPARE(op, T):
     return 0x4800 + (op << 8) + T
+
+
+def XCALL_GO_COMPARE_F32_SCALE(op, scale):
+    return 0x5200 + (op << 8) + scale
 
 
 def XCALL_GO_BETWEEN(T):
@@ -86,6 +97,10 @@ class Q1Result(C.Structure):
     _fields_ = [("ngroups", C.c_int64), ("groups", Q1Group * Q1_MAX_GROUPS)]
 
 
+class Q1Params(C.Structure):
+    _fields_ = [("cutoff", C.c_int32), ("reserved", C.c_int32), ("row_base", C.c_int64)]
+
+
 class SearchParams(C.Structure):
     _fields_ = [("n", C.c_int64), ("dim", C.c_int64), ("nq", C.c_int64), ("k", C.c_int32), ("metric", C.c_int32),
                 ("nprobe", C.c_int32), ("sqrt_out", C.c_int32), ("nlist", C.c_int64), ("key_base", C.c_int64)]
@@ -107,6 +122,7 @@ PROTOTYPES = {
     "MoB200_HostAlloc": (_i32, [_u64, C.POINTER(_vp)]), "MoB200_HostFree": (_i32, [_vp]),
     "MoB200_HostRegister": (_i32, [_vp, _u64]), "MoB200_HostUnregister": (_i32, [_vp]),
     "MoB200_Upload": (_i32, [_vp, _vp, _u64]), "MoB200_Download": (_i32, [_vp, _vp, _u64]), "MoB200_Memset": (_i32, [_vp, _i32, _u64]),
+    "MoB200_DownloadAsync": (_i32, [_vp, _vp, _u64]), "MoB200_UploadAsync": (_i32, [_vp, _vp, _u64]),
     "MoB200_Sync": (_i32, []), "MoB200_SetStream": (_i32, [_vp]), "MoB200_TimerStart": (_i32, []),
     "MoB200_TimerStop": (_i32, [C.POINTER(C.c_float)]), "MoB200_KernelLaunchCount": (_u64, []), "MoB200_LastKernelMs": (_i32, [C.POINTER(C.c_float)]),
     "MoB200_LastError": (_i32, [C.c_char_p, _u64]), "MoB200_FlushL2": (_i32, []), "MoB200_SetTuning": (_i32, [C.c_char_p, _i32]), "MoB200_DebugBuffer": (_vp, []),

@@ -205,9 +205,16 @@ agg_kernel(const T *__restrict__ col, const uint64_t *__restrict__ nulls, uint64
 // contiguous segment as (total, max prefix, min prefix) in 128-bit; segments are then folded in row order.
 struct Seg { __int128 total, maxp, minp; };
 
+// `gate` (async path): the aggregate record of the same call; when its magnitude sum fits int64 no prefix can overflow and the
+// whole grid returns at once
+__device__ __forceinline__ bool prefix_check_needed(const Rec *gate) { return !gate || gate->w3 != 0 || gate->w2 > (uint64_t)INT64_MAX; }
+
 template <typename T>
-__global__ void prefix_seg_kernel(const T *__restrict__ col, const uint64_t *__restrict__ nulls, uint64_t n, uint64_t seg_rows, Seg *segs) {
+__global__ void prefix_seg_kernel(const T *__restrict__ col, const uint64_t *__restrict__ nulls, uint64_t n, uint64_t seg_rows, uint64_t nseg,
+                                  Seg *segs, const Rec *gate) {
+    if (!prefix_check_needed(gate)) return;
     uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (s >= nseg) return;   // the grid is rounded up to whole CTAs: surplus threads own no segment
     uint64_t r0 = s * seg_rows, r1 = r0 + seg_rows;
     if (r1 > n) r1 = n;
     __int128 tot = 0, mx = 0, mn = 0;
@@ -219,7 +226,8 @@ __global__ void prefix_seg_kernel(const T *__restrict__ col, const uint64_t *__r
     }
     segs[s].total = tot; segs[s].maxp = mx; segs[s].minp = mn;
 }
-__global__ void prefix_fold_kernel(const Seg *segs, uint64_t nseg, int32_t *overflow) {
+__global__ void prefix_fold_kernel(const Seg *segs, uint64_t nseg, int32_t *overflow, const Rec *gate) {
+    if (!prefix_check_needed(gate)) { *overflow = 0; return; }
     __int128 run = 0; int32_t ov = 0;
     const __int128 hi = (__int128)INT64_MAX, lo = (__int128)INT64_MIN;
     for (uint64_t s = 0; s < nseg; s++) {
@@ -230,7 +238,7 @@ __global__ void prefix_fold_kernel(const Seg *segs, uint64_t nseg, int32_t *over
 }
 
 template <typename T, int KIND>
-int launch_agg(ThreadCtx &t, const void *dcol, const uint64_t *dnulls, uint64_t n, Rec *hrec) {
+int launch_agg(ThreadCtx &t, const void *dcol, const uint64_t *dnulls, uint64_t n, Rec *hrec, Rec **drec = nullptr) {
     int grid = num_sms() * kCtasPerSm;
     uint64_t work = (n + (16 / sizeof(T)) * kThreads - 1) / ((16 / sizeof(T)) * kThreads);
     if ((uint64_t)grid > work) grid = work ? (int)work : 1;
@@ -242,11 +250,13 @@ int launch_agg(ThreadCtx &t, const void *dcol, const uint64_t *dnulls, uint64_t 
     agg_kernel<T, KIND><<<grid, kThreads, 0, t.stream>>>((const T *)dcol, dnulls, n, vec, partials, out, t.ctrl);
     cudaEventRecord(t.kev1, t.stream);
     MOB_LAUNCH_CHECK();
+    if (drec) { *drec = out; return MO_RC_SUCCESS; }   // async: the record stays on the device
     return read_back(t, hrec, out, sizeof(Rec));
 }
 
 template <typename T>
-int signed_prefix_overflow(ThreadCtx &t, const void *dcol, const uint64_t *dnulls, uint64_t n, int32_t *ov) {
+int signed_prefix_overflow(ThreadCtx &t, const void *dcol, const uint64_t *dnulls, uint64_t n, int32_t *ov, const Rec *gate = nullptr,
+                           int32_t **dov_out = nullptr) {
     const uint64_t nseg_target = (uint64_t)num_sms() * 256;
     uint64_t seg_rows = (n + nseg_target - 1) / nseg_target;
     if (seg_rows < 64) seg_rows = 64;
@@ -254,10 +264,11 @@ int signed_prefix_overflow(ThreadCtx &t, const void *dcol, const uint64_t *dnull
     Seg *segs = (Seg *)arena_alloc(t, sizeof(Seg) * nseg + 16);
     if (!segs) return MO_RC_INTERNAL_ERROR;
     int32_t *dov = (int32_t *)(segs + nseg);
-    prefix_seg_kernel<T><<<(unsigned)((nseg + 255) / 256), 256, 0, t.stream>>>((const T *)dcol, dnulls, n, seg_rows, segs);
+    prefix_seg_kernel<T><<<(unsigned)((nseg + 255) / 256), 256, 0, t.stream>>>((const T *)dcol, dnulls, n, seg_rows, nseg, segs, gate);
     MOB_LAUNCH_CHECK();
-    prefix_fold_kernel<<<1, 1, 0, t.stream>>>(segs, nseg, dov);
+    prefix_fold_kernel<<<1, 1, 0, t.stream>>>(segs, nseg, dov, gate);
     MOB_LAUNCH_CHECK();
+    if (dov_out) { *dov_out = dov; return MO_RC_SUCCESS; }   // async: the flag stays on the device
     return read_back(t, ov, dov, 4);
 }
 
@@ -327,9 +338,178 @@ __global__ void popcount_kernel(const uint64_t *p, uint64_t nbits, unsigned long
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
+// ---- device-resident results (the asynchronous form) ----------------------------------------------------------------------------
+// When the column AND the result vector live in device memory the call only enqueues work on the calling thread's stream: no host
+// read-back, no synchronisation.  A 1-thread kernel turns the aggregate record into the caller's result words.  This is what lets a
+// multi-GPU caller hand the partial state straight to NCCL (MergeGroup seam, mergeGroup.go:132-247) and merge on the device.
+enum Cls { C_SIGNED = 0, C_UNSIGNED = 1, C_FLOAT = 2, C_MINMAX = 3, C_COUNT = 4 };
+
+__global__ void agg_state_kernel(const Rec *rec, int op, int cls, uint64_t len, const unsigned long long *nullcount, const int32_t *ovflag,
+                                 uint64_t *res, uint64_t res_words, uint64_t *rnulls) {
+    uint64_t bits = 0, cnt = 0; int64_t rc = MO_RC_SUCCESS; bool isnull = false;
+    if (cls == C_COUNT) { cnt = len - (nullcount ? *nullcount : 0ull); bits = cnt; }
+    else {
+        cnt = rec->cnt; isnull = cnt == 0;
+        double dsum = 0.0;
+        if (cls == C_SIGNED) {
+            bits = rec->w0; dsum = (double)(int64_t)rec->w0;
+            if ((rec->w3 != 0 || rec->w2 > (uint64_t)INT64_MAX) && ovflag && *ovflag) rc = MO_RC_OUT_OF_RANGE;
+        } else if (cls == C_UNSIGNED) { bits = rec->w0; dsum = (double)rec->w0; if (rec->w1) rc = MO_RC_OUT_OF_RANGE; }
+        else if (cls == C_FLOAT) { dsum = rec->d; memcpy(&bits, &dsum, 8); }
+        else bits = rec->w0;
+        // a 1-word result of AVG is the final value; a 3-word result is the partial STATE (sum in the SUM return type, count, rc) and AVG divides at the merge
+        if (op == MO_AGG_AVG && res_words < 3 && !isnull) { double avg = dsum / (double)cnt; memcpy(&bits, &avg, 8); }
+    }
+    res[0] = bits;
+    if (res_words >= 2) res[1] = cnt;
+    if (res_words >= 3) res[2] = (uint64_t)rc;
+    if (rnulls) rnulls[0] = isnull ? 1ull : 0ull;
+}
+
+template <typename T>
+static int agg_async_typed(ThreadCtx &t, int op, int cls, const void *dcol, const uint64_t *dnulls, uint64_t n, Rec **drec, int32_t **dov) {
+    *dov = nullptr;
+    if (op == MO_AGG_MIN) return launch_agg<T, K_MIN>(t, dcol, dnulls, n, nullptr, drec);
+    if (op == MO_AGG_MAX) return launch_agg<T, K_MAX>(t, dcol, dnulls, n, nullptr, drec);
+    if (cls == C_FLOAT) return launch_agg<T, K_SUM_FLOAT>(t, dcol, dnulls, n, nullptr, drec);
+    if (cls == C_UNSIGNED) return launch_agg<T, K_SUM_UNSIGNED>(t, dcol, dnulls, n, nullptr, drec);
+    int rc = launch_agg<T, K_SUM_SIGNED>(t, dcol, dnulls, n, nullptr, drec);
+    if (rc) return rc;
+    // the exact serial-order prefix check runs only when the device-side gate says the magnitudes do not fit int64
+    return signed_prefix_overflow<T>(t, dcol, dnulls, n, nullptr, *drec, dov);
+}
+
+static int xcall_agg_async(ThreadCtx &t, int op, int T, mo_xcall_args_t *args, uint64_t len) {
+    const void *dcol = args[1].pdata;
+    const uint64_t *dnulls = args[1].pnulls;
+    const bool is_signed = T >= MO_T_INT8 && T <= MO_T_INT64, is_unsigned = T >= MO_T_UINT8 && T <= MO_T_UINT64;
+    const bool is_float = T == MO_T_FLOAT32 || T == MO_T_FLOAT64;
+    Rec *drec = nullptr; int32_t *dov = nullptr; unsigned long long *dcount = nullptr;
+    int cls, rc = MO_RC_SUCCESS;
+    Rec *zero = (Rec *)arena_alloc(t, sizeof(Rec));
+    if (!zero) return MO_RC_INTERNAL_ERROR;
+    if (op == MO_AGG_COUNT) {
+        cls = C_COUNT;
+        if (dnulls && len) {
+            dcount = (unsigned long long *)arena_alloc(t, 8);
+            if (!dcount) return MO_RC_INTERNAL_ERROR;
+            MOB_CUDA_TRY(cudaMemsetAsync(dcount, 0, 8, t.stream));
+            uint64_t nw = (len + 63) >> 6;
+            int grid = (int)((nw + 255) / 256);
+            if (grid > num_sms() * 8) grid = num_sms() * 8;
+            popcount_kernel<<<grid, 256, 0, t.stream>>>(dnulls, len, dcount);
+            MOB_LAUNCH_CHECK();
+        }
+    } else if (op == MO_AGG_MIN || op == MO_AGG_MAX || op == MO_AGG_SUM || op == MO_AGG_AVG) {
+        const bool mm = op == MO_AGG_MIN || op == MO_AGG_MAX;
+        cls = mm ? C_MINMAX : is_signed ? C_SIGNED : is_unsigned ? C_UNSIGNED : C_FLOAT;
+        if (!mm && !is_signed && !is_unsigned && !is_float) { set_error("sum: unsupported type %d", T); return MO_RC_INVALID_ARGUMENT; }
+        if (len == 0) { MOB_CUDA_TRY(cudaMemsetAsync(zero, 0, sizeof(Rec), t.stream)); drec = zero; }
+        else switch (T) {
+        case MO_T_BOOL: case MO_T_UINT8: rc = agg_async_typed<uint8_t>(t, op, cls, dcol, dnulls, len, &drec, &dov); break;
+        case MO_T_INT8: rc = agg_async_typed<int8_t>(t, op, cls, dcol, dnulls, len, &drec, &dov); break;
+        case MO_T_INT16: rc = agg_async_typed<int16_t>(t, op, cls, dcol, dnulls, len, &drec, &dov); break;
+        case MO_T_UINT16: rc = agg_async_typed<uint16_t>(t, op, cls, dcol, dnulls, len, &drec, &dov); break;
+        case MO_T_INT32: case MO_T_DATE: rc = agg_async_typed<int32_t>(t, op, cls, dcol, dnulls, len, &drec, &dov); break;
+        case MO_T_UINT32: rc = agg_async_typed<uint32_t>(t, op, cls, dcol, dnulls, len, &drec, &dov); break;
+        case MO_T_INT64: case MO_T_TIME: case MO_T_DATETIME: case MO_T_TIMESTAMP: rc = agg_async_typed<int64_t>(t, op, cls, dcol, dnulls, len, &drec, &dov); break;
+        case MO_T_UINT64: rc = agg_async_typed<uint64_t>(t, op, cls, dcol, dnulls, len, &drec, &dov); break;
+        case MO_T_FLOAT32: rc = agg_async_typed<float>(t, op, cls, dcol, dnulls, len, &drec, &dov); break;
+        case MO_T_FLOAT64: rc = agg_async_typed<double>(t, op, cls, dcol, dnulls, len, &drec, &dov); break;
+        default: set_error("agg: unsupported type %d", T); return MO_RC_INVALID_ARGUMENT;
+        }
+        if (rc) return rc;
+    } else { set_error("agg: unknown op %d", op); return MO_RC_INVALID_ARGUMENT; }
+    agg_state_kernel<<<1, 1, 0, t.stream>>>(drec, op, cls, len, dcount, dov, (uint64_t *)args[0].pdata, args[0].dataSz / 8, args[0].pnulls);
+    MOB_LAUNCH_CHECK();
+    arena_reset(t);   // stream order protects the scratch: the next call's kernels queue behind these
+    return MO_RC_SUCCESS;
+}
+
+// ---- MergeGroup for H0 aggregates: fold `n` partial states (value bits, non-null count, rc) in order (BatchMerge, sumavg2.go:205-248,
+// count2.go, minmax2.go:90-110).  1 thread: n is the number of pipelines / GPUs.
+template <typename T>
+__device__ bool mm_less(uint64_t a, uint64_t b) { return from_bits<T>(a) < from_bits<T>(b); }
+
+__global__ void agg_merge_kernel(const uint64_t *parts, uint64_t n, int op, int T, int cls, uint64_t *res, uint64_t res_words, uint64_t *rnulls) {
+    uint64_t bits = 0, cnt = 0; int64_t rc = MO_RC_SUCCESS; bool has = false;
+    double dsum = 0.0;
+    for (uint64_t i = 0; i < n; i++) {
+        const uint64_t b = parts[3 * i], c = parts[3 * i + 1]; const int64_t prc = (int64_t)parts[3 * i + 2];
+        if (prc && !rc) rc = prc;
+        if (op == MO_AGG_COUNT) { bits += b; cnt += c; continue; }
+        if (c == 0) continue;   // a NULL partial is skipped
+        if (!has) { has = true; bits = b; cnt = c; memcpy(&dsum, &b, 8); continue; }
+        cnt += c;
+        if (cls == C_FLOAT) { double x; memcpy(&x, &b, 8); dsum = dsum + x; memcpy(&bits, &dsum, 8); }
+        else if (cls == C_SIGNED) {
+            const int64_t v1 = (int64_t)bits, v2 = (int64_t)b, sum = (int64_t)(bits + b);
+            if (((v1 > 0 && v2 > 0 && sum <= 0) || (v1 < 0 && v2 < 0 && sum >= 0)) && !rc) rc = MO_RC_OUT_OF_RANGE;   // int64OfCheck
+            bits = (uint64_t)sum;
+        } else if (cls == C_UNSIGNED) {
+            const uint64_t sum = bits + b;
+            if ((sum < bits || sum < b) && !rc) rc = MO_RC_OUT_OF_RANGE;                                                   // uint64OfCheck
+            bits = sum;
+        } else {   // MIN / MAX: strict compare, the earlier partial wins ties (minmax2.go:97-104)
+            bool repl = false;
+#define MMCASE(TT) repl = op == MO_AGG_MIN ? mm_less<TT>(b, bits) : mm_less<TT>(bits, b)
+            switch (T) {
+            case MO_T_BOOL: case MO_T_UINT8: MMCASE(uint8_t); break;
+            case MO_T_INT8: MMCASE(int8_t); break;
+            case MO_T_INT16: MMCASE(int16_t); break;
+            case MO_T_UINT16: MMCASE(uint16_t); break;
+            case MO_T_INT32: case MO_T_DATE: MMCASE(int32_t); break;
+            case MO_T_UINT32: MMCASE(uint32_t); break;
+            case MO_T_UINT64: MMCASE(uint64_t); break;
+            case MO_T_FLOAT32: MMCASE(float); break;
+            case MO_T_FLOAT64: MMCASE(double); break;
+            default: MMCASE(int64_t); break;
+            }
+#undef MMCASE
+            if (repl) bits = b;
+        }
+    }
+    const bool isnull = op != MO_AGG_COUNT && !has;
+    if (op == MO_AGG_AVG && has && res_words < 3) {   // float64(sum) / float64(cnt), sumavg2.go:331
+        if (cls == C_SIGNED) dsum = (double)(int64_t)bits; else if (cls == C_UNSIGNED) dsum = (double)bits; else memcpy(&dsum, &bits, 8);
+        double avg = dsum / (double)cnt; memcpy(&bits, &avg, 8);
+    }
+    res[0] = bits;
+    if (res_words >= 2) res[1] = cnt;
+    if (res_words >= 3) res[2] = (uint64_t)rc;
+    if (rnulls) rnulls[0] = isnull ? 1ull : 0ull;
+}
+
 }  // namespace
 
 namespace mob {
+
+// MO_XCALL_AGG_MERGE(op, T): args[0] = result (as MO_XCALL_AGG), args[1] = len partial states of 24 bytes each
+int xcall_agg_merge(int op, int T, mo_xcall_args_t *args, uint64_t len) {
+    ThreadCtx &t = tctx();
+    if (!t.ready) return MO_RC_INTERNAL_ERROR;
+    if (!type_size(T) || op < 0 || op > MO_AGG_AVG) { set_error("agg merge: bad op/type"); return MO_RC_INVALID_ARGUMENT; }
+    if (!args[0].pdata || args[0].dataSz < 8 || args[1].dataSz < 24 * len) { set_error("agg merge: result needs 8 bytes, partial states 24 bytes each"); return MO_RC_INVALID_ARGUMENT; }
+    const bool is_signed = T >= MO_T_INT8 && T <= MO_T_INT64, is_unsigned = T >= MO_T_UINT8 && T <= MO_T_UINT64;
+    const int cls = op == MO_AGG_COUNT ? C_COUNT : (op == MO_AGG_MIN || op == MO_AGG_MAX) ? C_MINMAX : is_signed ? C_SIGNED : is_unsigned ? C_UNSIGNED : C_FLOAT;
+    const bool async = is_device_ptr(args[0].pdata) && (len == 0 || is_device_ptr(args[1].pdata));
+    Stager st(t);
+    const uint64_t *dparts = (const uint64_t *)st.in(args[1].pdata, 24 * len);
+    uint64_t *dres = (uint64_t *)st.out(args[0].pdata, args[0].dataSz >= 24 ? 24 : args[0].dataSz >= 16 ? 16 : 8);
+    uint64_t *dn = (uint64_t *)st.out(args[0].pnulls, args[0].pnulls ? 8 : 0);
+    if (st.failed) { st.finish(); return MO_RC_INTERNAL_ERROR; }
+    agg_merge_kernel<<<1, 1, 0, t.stream>>>(dparts, len, op, T, cls, dres, args[0].dataSz / 8, dn);
+    MOB_LAUNCH_CHECK();
+    if (async) { arena_reset(t); return MO_RC_SUCCESS; }
+    int rc = MO_RC_SUCCESS;
+    if (args[0].dataSz >= 24) {   // a host-visible state carries its rc; report it as the call's rc too
+        uint64_t w[3];
+        int r2 = read_back(t, w, dres, 24);
+        if (r2) rc = r2; else if ((int64_t)w[2]) rc = (int)(int64_t)w[2];
+    }
+    int frc = st.finish();
+    return rc ? rc : frc;
+}
 
 int bitmap_count_device(ThreadCtx &t, const uint64_t *dp, uint64_t nbits, uint64_t *count) {
     if (nbits == 0 || !dp) { *count = 0; return MO_RC_SUCCESS; }
@@ -352,6 +532,9 @@ int xcall_agg(int op, int T, mo_xcall_args_t *args, uint64_t len) {
     if (!sz || T == MO_T_BOOL && op != MO_AGG_COUNT && op != MO_AGG_MIN && op != MO_AGG_MAX) { set_error("agg: unsupported type %d", T); return MO_RC_INVALID_ARGUMENT; }
     if (!args[0].pdata || args[0].dataSz < 8) { set_error("agg: result vector must hold 8 bytes"); return MO_RC_INVALID_ARGUMENT; }
     if (args[1].dataSz < (uint64_t)sz * len) { set_error("agg: column shorter than len"); return MO_RC_INVALID_ARGUMENT; }
+    if (is_device_ptr(args[0].pdata) && (len == 0 || is_device_ptr(args[1].pdata)) && (!args[0].pnulls || is_device_ptr(args[0].pnulls)) &&
+        (!args[1].pnulls || is_device_ptr(args[1].pnulls)))
+        return xcall_agg_async(t, op, T, args, len);
     Stager st(t);
     const void *dcol = st.in(args[1].pdata, (size_t)sz * len);
     const uint64_t *dnulls = (const uint64_t *)st.in(args[1].pnulls, args[1].pnulls ? ((len + 63) / 64) * 8 : 0);
@@ -389,7 +572,8 @@ int xcall_agg(int op, int T, mo_xcall_args_t *args, uint64_t len) {
             memcpy(&bits, &dsum, 8);
         } else { set_error("sum: unsupported type %d", T); rc = MO_RC_INVALID_ARGUMENT; }
         isnull = cnt == 0;
-        if (op == MO_AGG_AVG && !isnull) { double avg = dsum / (double)cnt; memcpy(&bits, &avg, 8); }  // sumavg2.go:331
+        if (op == MO_AGG_AVG && args[0].dataSz >= 24) { /* partial STATE: the raw sum, the merge divides */ }
+        else if (op == MO_AGG_AVG && !isnull) { double avg = dsum / (double)cnt; memcpy(&bits, &avg, 8); }  // sumavg2.go:331
     } else if (op == MO_AGG_MIN || op == MO_AGG_MAX) {
 #define MM(TT) (op == MO_AGG_MIN ? run_minmax<TT, K_MIN>(t, dcol, dnulls, len, &bits, &cnt) : run_minmax<TT, K_MAX>(t, dcol, dnulls, len, &bits, &cnt))
         switch (T) {
@@ -412,8 +596,11 @@ int xcall_agg(int op, int T, mo_xcall_args_t *args, uint64_t len) {
     // write the result (host memory directly; device memory through the stream)
     if (rc == MO_RC_SUCCESS || rc == MO_RC_OUT_OF_RANGE) {
         uint64_t nullword = isnull ? 1ull : 0ull;
-        if (is_device_ptr(args[0].pdata)) cudaMemcpyAsync(args[0].pdata, &bits, 8, cudaMemcpyHostToDevice, t.stream);
-        else memcpy(args[0].pdata, &bits, 8);
+        if (op == MO_AGG_COUNT) cnt = bits;
+        uint64_t words[3] = {bits, cnt, (uint64_t)(int64_t)rc};
+        const size_t wb = args[0].dataSz >= 24 ? 24 : args[0].dataSz >= 16 ? 16 : 8;   // 8: value; 16: + non-null rows; 24: + rc (partial state)
+        if (is_device_ptr(args[0].pdata)) cudaMemcpyAsync(args[0].pdata, words, wb, cudaMemcpyHostToDevice, t.stream);
+        else memcpy(args[0].pdata, words, wb);
         if (args[0].pnulls) {
             if (is_device_ptr(args[0].pnulls)) cudaMemcpyAsync(args[0].pnulls, &nullword, 8, cudaMemcpyHostToDevice, t.stream);
             else memcpy(args[0].pnulls, &nullword, 8);

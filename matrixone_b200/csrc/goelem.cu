@@ -124,11 +124,18 @@ template <typename T> __device__ __forceinline__ void load8(const T *p, uint64_t
     }
 }
 
+// float32(math.Round(float64(a) * pow) / pow): math.Round = half away from zero = round(); IEEE double multiply / divide
+template <typename T> __device__ __forceinline__ T round_scale(T v, double) { return v; }
+template <> __device__ __forceinline__ float round_scale<float>(float v, double pw) {
+    return pw > 0.0 ? (float)__ddiv_rn(round(__dmul_rn((double)v, pw)), pw) : v;
+}
+
 // compare: a thread owns 8 consecutive rows -> one 8-byte store of the bool results when none of them is null
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 go_compare_kernel(uint8_t *__restrict__ r, const T *__restrict__ a, const T *__restrict__ b, uint64_t n, int c1, int c2,
-                  const uint64_t *__restrict__ rnulls, int op, int vec_ok) {
+                  const uint64_t *__restrict__ rnulls, int op, int vec_ok, double pw) {
+    // pw > 0 (float32 columns declared with scale > 0, func_compare.go:725-734): both sides are rounded to `scale` decimals first
     const uint64_t ngroups = vec_ok ? n / 8 : 0;
     for (uint64_t g = blockIdx.x * (uint64_t)kThreads + threadIdx.x; g < ngroups; g += (uint64_t)gridDim.x * kThreads) {
         const uint64_t i0 = g * 8;
@@ -138,7 +145,7 @@ go_compare_kernel(uint8_t *__restrict__ r, const T *__restrict__ a, const T *__r
         load8<T>(a, i0, c1 != 0, x); load8<T>(b, i0, c2 != 0, y);
         uint64_t packed = 0;
 #pragma unroll
-        for (int j = 0; j < 8; j++) packed |= (uint64_t)(go_cmp<T>(x[j], y[j], op) ? 1 : 0) << (8 * j);
+        for (int j = 0; j < 8; j++) packed |= (uint64_t)(go_cmp<T>(round_scale<T>(x[j], pw), round_scale<T>(y[j], pw), op) ? 1 : 0) << (8 * j);
         if (nb == 0) *reinterpret_cast<uint64_t *>(r + i0) = packed;
         else {
 #pragma unroll
@@ -148,7 +155,7 @@ go_compare_kernel(uint8_t *__restrict__ r, const T *__restrict__ a, const T *__r
     // rows not covered by whole groups (all rows when the buffers are not 16-byte aligned)
     for (uint64_t i = ngroups * 8 + blockIdx.x * (uint64_t)kThreads + threadIdx.x; i < n; i += (uint64_t)gridDim.x * kThreads) {
         if (bm_test(rnulls, i)) continue;
-        r[i] = go_cmp<T>(a[c1 ? 0 : i], b[c2 ? 0 : i], op) ? 1 : 0;
+        r[i] = go_cmp<T>(round_scale<T>(a[c1 ? 0 : i], pw), round_scale<T>(b[c2 ? 0 : i], pw), op) ? 1 : 0;
     }
 }
 
@@ -318,7 +325,7 @@ int go_arith_op(ThreadCtx &t, int op, int Tid, mo_xcall_args_t *args, uint64_t l
 }
 
 template <typename T>
-int run_go_compare(ThreadCtx &t, int op, mo_xcall_args_t *args, uint64_t len) {
+int run_go_compare(ThreadCtx &t, int op, mo_xcall_args_t *args, uint64_t len, double pw = 0.0) {
     const uint64_t nwords = (len + 63) / 64;
     const bool c1 = args[1].dataSz == sizeof(T) && len > 1, c2 = args[2].dataSz == sizeof(T) && len > 1;
     if ((!c1 && args[1].dataSz < sizeof(T) * len) || (!c2 && args[2].dataSz < sizeof(T) * len) || args[0].dataSz < len || !args[0].pnulls) {
@@ -341,7 +348,7 @@ int run_go_compare(ThreadCtx &t, int op, mo_xcall_args_t *args, uint64_t len) {
     if (!all_null) {
         cudaEventRecord(t.kev0, t.stream);
         const int vec_ok = ((((uintptr_t)r) | ((uintptr_t)a) | ((uintptr_t)b)) & 15) == 0 ? 1 : 0;
-        go_compare_kernel<T><<<grid_rows(vec_ok ? (len + 7) / 8 : len), kThreads, 0, t.stream>>>(r, a, b, len, c1 ? 1 : 0, c2 ? 1 : 0, rn, op, vec_ok);
+        go_compare_kernel<T><<<grid_rows(vec_ok ? (len + 7) / 8 : len), kThreads, 0, t.stream>>>(r, a, b, len, c1 ? 1 : 0, c2 ? 1 : 0, rn, op, vec_ok, pw);
         cudaEventRecord(t.kev1, t.stream);
         MOB_LAUNCH_CHECK();
     }
@@ -446,6 +453,13 @@ int xcall_go_elementwise(int64_t funcId, mo_xcall_args_t *args, uint64_t len) {
         }
         set_error("go compare: unsupported type %d", T);
         return MO_RC_INVALID_ARGUMENT;
+    }
+    if (funcId >= 0x5200 && funcId < 0x5800) {   // MO_XCALL_GO_COMPARE_F32_SCALE(op, scale)
+        const int op = (int)((funcId - 0x5200) >> 8), scale = (int)(funcId & 0xff);
+        if (op > CMP_LE || scale < 1 || scale > 22) { set_error("go compare f32 scale: operator 0..5, scale 1..22"); return MO_RC_INVALID_ARGUMENT; }
+        double pw = 1.0;
+        for (int k = 0; k < scale; k++) pw *= 10.0;   // math.Pow10(scale), exact
+        return run_go_compare<float>(t, op, args, len, pw);
     }
     if (funcId >= 0x5000 && funcId < 0x5100) {
         const int T = (int)(funcId & 0xff);

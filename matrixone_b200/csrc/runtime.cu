@@ -255,6 +255,19 @@ int32_t MoB200_Download(void *dst_host, const void *src_dev, uint64_t bytes) {
     MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));
     return MO_RC_SUCCESS;
 }
+// stream-ordered copies without a synchronise: the host buffer should be pinned (MoB200_HostAlloc / HostRegister) and must not be
+// read (download) or reused (upload) before MoB200_Sync
+int32_t MoB200_DownloadAsync(void *dst_host, const void *src_dev, uint64_t bytes) {
+    REQUIRE_CTX(t);
+    MOB_CUDA_TRY(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, t.stream));
+    return MO_RC_SUCCESS;
+}
+int32_t MoB200_UploadAsync(void *dst_dev, const void *src_host, uint64_t bytes) {
+    REQUIRE_CTX(t);
+    search_invalidate(dst_dev, bytes);
+    MOB_CUDA_TRY(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, t.stream));
+    return MO_RC_SUCCESS;
+}
 int32_t MoB200_Memset(void *dst_dev, int32_t value, uint64_t bytes) {
     REQUIRE_CTX(t);
     search_invalidate(dst_dev, bytes);

@@ -29,12 +29,15 @@ constexpr int kThreads = 256;
 // Q6
 // =========================================================================================================
 struct Q6Rec { double sum; unsigned long long cnt; };
+// caller-owned device result (asynchronous form): sum at res[0], qualifying rows at res[1] when res_words >= 2, nulls word bit 0 =
+// "no row qualified" -- the layout MO_XCALL_Q6_MERGE consumes
+struct Q6DevOut { double *res; uint64_t res_words; uint64_t *rnulls; };
 
 template <int UNROLL, int CTAS>
 __global__ void __launch_bounds__(kThreads, CTAS)
 q6_kernel(const int32_t *__restrict__ sd, const double *__restrict__ disc, const double *__restrict__ qty,
           const double *__restrict__ price, uint64_t n, mo_q6_params_t P, Q6Rec *__restrict__ partials,
-          Q6Rec *__restrict__ out, unsigned *ticket) {
+          Q6Rec *__restrict__ out, unsigned *ticket, Q6DevOut dres) {
     const uint64_t npairs = n >> 1;
     const uint64_t tid = blockIdx.x * (uint64_t)kThreads + threadIdx.x;
     const uint64_t nthreads = (uint64_t)gridDim.x * kThreads;
@@ -111,6 +114,11 @@ q6_kernel(const int32_t *__restrict__ sd, const double *__restrict__ disc, const
 #pragma unroll
             for (int w = 0; w < kThreads / 32; w++) { f = __dadd_rn(f, ss[w]); fc += sc[w]; }
             out->sum = f; out->cnt = fc;
+            if (dres.res) {
+                dres.res[0] = f;
+                if (dres.res_words >= 2) reinterpret_cast<long long *>(dres.res)[1] = (long long)fc;
+                if (dres.rnulls) dres.rnulls[0] = fc ? 0ull : 1ull;
+            }
         }
     }
 }
@@ -351,7 +359,9 @@ __global__ void __launch_bounds__(kThreads, CTAS)
 q1_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty, const double *__restrict__ price,
           const double *__restrict__ disc, const double *__restrict__ tax, const uint8_t *__restrict__ rf,
           const uint8_t *__restrict__ ls, uint64_t n, int32_t cutoff, Q1Rec *__restrict__ partials,
-          Q1Rec *__restrict__ out, unsigned *ticket, unsigned long long *dbg) {
+          Q1Rec *__restrict__ out, unsigned *ticket, unsigned long long *dbg, const Q1Rec *gate) {
+    // asynchronous form: the 8-slot retry is enqueued behind the 4-slot pass and runs only if that pass overflowed its dictionary
+    if (gate && !gate->overflow) return;
     if (dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[blockIdx.x * 16] = t; }
     __shared__ Q1Shared S;
     S.dict[threadIdx.x & (MO_Q1_MAX_GROUPS - 1)] = kEmptyKey;   // all threads write (same values): no lane-dependent branch
@@ -528,7 +538,7 @@ q1_staged_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty,
     q1_epilogue<G, kStagedThreads>(T, S, partials, out, ticket, dbg);
 }
 
-void q1_finalize(const Q1Rec &F, mo_q1_result_t *res) {
+__host__ __device__ void q1_finalize(const Q1Rec &F, mo_q1_result_t *res, int64_t row_base = 0) {
     memset(res, 0, sizeof *res);
     int order[MO_Q1_MAX_GROUPS], ng = 0;
     for (int g = 0; g < MO_Q1_MAX_GROUPS; g++) if (F.slot[g].used && F.slot[g].cnt) order[ng++] = g;
@@ -539,12 +549,69 @@ void q1_finalize(const Q1Rec &F, mo_q1_result_t *res) {
         const Q1Slot &s = F.slot[order[i]];
         mo_q1_group_t &o = res->groups[i];
         o.returnflag = (uint8_t)(s.key & 0xff); o.linestatus = (uint8_t)((s.key >> 8) & 0xff);
-        o.first_row = (int64_t)s.first_row;
+        o.first_row = (int64_t)s.first_row + row_base;
         o.sum_qty = s.v[0]; o.sum_base_price = s.v[1]; o.sum_disc_price = s.v[2]; o.sum_charge = s.v[3]; o.sum_disc = s.v[4];
         o.count_order = (int64_t)s.cnt;
         const double c = (double)s.cnt;   // avg = float64(sum)/float64(cnt), sumavg2.go:331
         o.avg_qty = s.v[0] / c; o.avg_price = s.v[1] / c; o.avg_disc = s.v[4] / c;
     }
+}
+
+// asynchronous form: pick the pass that did not overflow, order the groups, write the caller's device result.  ngroups = -1 reports
+// "more than MO_Q1_MAX_GROUPS distinct keys" (the synchronous form returns MO_RC_INVALID_ARGUMENT for that).
+__global__ void q1_finalize_kernel(const Q1Rec *narrow, const Q1Rec *wide, mo_q1_result_t *res, int64_t row_base) {
+    const Q1Rec *F = (narrow && !narrow->overflow) ? narrow : wide;
+    if (!F || F->overflow) { memset(res, 0, sizeof *res); res->ngroups = -1; return; }
+    q1_finalize(*F, res, row_base);
+}
+
+// MergeGroup on the device (mergeGroup.go:132-247): re-hash the partial group keys of `nparts` results and BatchMerge them IN ORDER
+// (rank order => deterministic); groups come back in global first-seen row order.  One thread: <= 8 groups x nparts.
+__global__ void q1_merge_kernel(const mo_q1_result_t *parts, uint64_t nparts, mo_q1_result_t *res) {
+    mo_q1_result_t R; memset(&R, 0, sizeof R);
+    bool bad = false;
+    for (uint64_t p = 0; p < nparts && !bad; p++) {
+        const mo_q1_result_t &P = parts[p];
+        if (P.ngroups < 0 || P.ngroups > MO_Q1_MAX_GROUPS) { bad = true; break; }
+        for (int64_t g = 0; g < P.ngroups; g++) {
+            const mo_q1_group_t &s = P.groups[g];
+            int dst = -1;
+            for (int64_t x = 0; x < R.ngroups; x++) if (R.groups[x].returnflag == s.returnflag && R.groups[x].linestatus == s.linestatus) { dst = (int)x; break; }
+            if (dst < 0) {
+                if (R.ngroups == MO_Q1_MAX_GROUPS) { bad = true; break; }
+                R.groups[R.ngroups++] = s;
+                continue;
+            }
+            mo_q1_group_t &D = R.groups[dst];
+            D.sum_qty = __dadd_rn(D.sum_qty, s.sum_qty); D.sum_base_price = __dadd_rn(D.sum_base_price, s.sum_base_price);
+            D.sum_disc_price = __dadd_rn(D.sum_disc_price, s.sum_disc_price); D.sum_charge = __dadd_rn(D.sum_charge, s.sum_charge);
+            D.sum_disc = __dadd_rn(D.sum_disc, s.sum_disc);
+            D.count_order += s.count_order;
+            if (s.first_row < D.first_row) D.first_row = s.first_row;
+        }
+    }
+    if (bad) { memset(res, 0, sizeof *res); res->ngroups = -1; return; }
+    for (int64_t i = 1; i < R.ngroups; i++)
+        for (int64_t j = i; j > 0 && R.groups[j].first_row < R.groups[j - 1].first_row; j--) { mo_q1_group_t tmp = R.groups[j]; R.groups[j] = R.groups[j - 1]; R.groups[j - 1] = tmp; }
+    for (int64_t i = 0; i < R.ngroups; i++) {
+        mo_q1_group_t &o = R.groups[i];
+        const double c = (double)o.count_order;
+        o.avg_qty = o.sum_qty / c; o.avg_price = o.sum_base_price / c; o.avg_disc = o.sum_disc / c;
+    }
+    *res = R;
+}
+
+// MergeGroup for the Q6 shape: (sum, count) partials added in order; an empty partial is NULL and skipped (sumavg2.go:222-236)
+__global__ void q6_merge_kernel(const double *parts, uint64_t nparts, Q6DevOut o) {
+    double total = 0.0; long long cnt = 0; bool any = false;
+    for (uint64_t p = 0; p < nparts; p++) {
+        const double s = parts[2 * p]; const long long c = reinterpret_cast<const long long *>(parts)[2 * p + 1];
+        if (c == 0) continue;
+        total = any ? __dadd_rn(total, s) : s; any = true; cnt += c;
+    }
+    o.res[0] = total;
+    if (o.res_words >= 2) reinterpret_cast<long long *>(o.res)[1] = cnt;
+    if (o.rnulls) o.rnulls[0] = any ? 0ull : 1ull;
 }
 
 int g_q6_variant = 0, g_q1_variant = 0;  // tuning knobs (MoB200_SetTuning)
@@ -584,7 +651,7 @@ static const uint64_t kHostChunkRows = 32ull << 20;
 static bool aligned_to(const void *p, uintptr_t a) { return (((uintptr_t)p) & (a - 1)) == 0; }
 
 static int launch_q6(ThreadCtx &t, const int32_t *sd, const double *disc, const double *qty, const double *price,
-                     uint64_t n, const mo_q6_params_t &P, Q6Rec *hrec) {
+                     uint64_t n, const mo_q6_params_t &P, Q6Rec *hrec, Q6DevOut dres = Q6DevOut{nullptr, 0, nullptr}) {
     if (!aligned_to(sd, 8) || !aligned_to(disc, 16) || !aligned_to(qty, 16) || !aligned_to(price, 16)) {
         set_error("q6: columns must be 16-byte aligned (int32 column 8-byte)"); return MO_RC_INVALID_ARGUMENT;
     }
@@ -598,13 +665,14 @@ static int launch_q6(ThreadCtx &t, const int32_t *sd, const double *disc, const 
     Q6Rec *out = partials + grid;
     cudaEventRecord(t.kev0, t.stream);
     switch (variant) {
-    case 1: q6_kernel<4, 2><<<grid, kThreads, 0, t.stream>>>(sd, disc, qty, price, n, P, partials, out, t.ctrl); break;
-    case 2: q6_kernel<2, 4><<<grid, kThreads, 0, t.stream>>>(sd, disc, qty, price, n, P, partials, out, t.ctrl); break;
-    case 3: q6_kernel<8, 2><<<grid, kThreads, 0, t.stream>>>(sd, disc, qty, price, n, P, partials, out, t.ctrl); break;
-    default: q6_kernel<4, 4><<<grid, kThreads, 0, t.stream>>>(sd, disc, qty, price, n, P, partials, out, t.ctrl); break;
+    case 1: q6_kernel<4, 2><<<grid, kThreads, 0, t.stream>>>(sd, disc, qty, price, n, P, partials, out, t.ctrl, dres); break;
+    case 2: q6_kernel<2, 4><<<grid, kThreads, 0, t.stream>>>(sd, disc, qty, price, n, P, partials, out, t.ctrl, dres); break;
+    case 3: q6_kernel<8, 2><<<grid, kThreads, 0, t.stream>>>(sd, disc, qty, price, n, P, partials, out, t.ctrl, dres); break;
+    default: q6_kernel<4, 4><<<grid, kThreads, 0, t.stream>>>(sd, disc, qty, price, n, P, partials, out, t.ctrl, dres); break;
     }
     cudaEventRecord(t.kev1, t.stream);
     MOB_LAUNCH_CHECK();
+    if (dres.res) return MO_RC_SUCCESS;   // asynchronous form: the last CTA wrote the caller's device result
     return read_back(t, hrec, out, sizeof(Q6Rec));
 }
 
@@ -626,6 +694,14 @@ int xcall_q6(mo_xcall_args_t *args, uint64_t len) {
 
     double sum = 0.0; unsigned long long cnt = 0; bool any = false;
     int rc = MO_RC_SUCCESS;
+    if (dev && len && is_device_ptr(args[0].pdata) && (!args[0].pnulls || is_device_ptr(args[0].pnulls))) {
+        // resident columns AND a device result: enqueue only (no read-back, no synchronisation); the result is ordered on the calling
+        // thread's stream, ready for NCCL + MO_XCALL_Q6_MERGE or a later MoB200_Download
+        rc = launch_q6(t, (const int32_t *)args[1].pdata, (const double *)args[2].pdata, (const double *)args[3].pdata,
+                       (const double *)args[4].pdata, len, P, nullptr, Q6DevOut{(double *)args[0].pdata, args[0].dataSz / 8, args[0].pnulls});
+        arena_reset(t);
+        return rc;
+    }
     if (dev || len == 0) {
         if (len) {
             Q6Rec r;
@@ -672,7 +748,7 @@ int xcall_q6(mo_xcall_args_t *args, uint64_t len) {
 
 template <int KEYMODE>
 static int launch_q1(ThreadCtx &t, const int32_t *sd, const double *qty, const double *price, const double *disc, const double *tax,
-                     const uint8_t *rf, const uint8_t *ls, uint64_t n, int32_t cutoff, Q1Rec *hrec) {
+                     const uint8_t *rf, const uint8_t *ls, uint64_t n, int32_t cutoff, Q1Rec *hrec, mo_q1_result_t *dres = nullptr, int64_t row_base = 0) {
     if (!aligned_to(sd, 8) || !aligned_to(qty, 16) || !aligned_to(price, 16) || !aligned_to(disc, 16) || !aligned_to(tax, 16) ||
         !aligned_to(rf, KEYMODE ? 8 : 2) || !aligned_to(ls, KEYMODE ? 8 : 2)) {
         set_error("q1: columns must be 16-byte aligned (int32 column 8-byte, key columns 2/8-byte)"); return MO_RC_INVALID_ARGUMENT;
@@ -680,6 +756,7 @@ static int launch_q1(ThreadCtx &t, const int32_t *sd, const double *qty, const d
     // variant: 0 = auto (cp.async-staged kernel, 3 stages, for packed keys; register kernel otherwise), 1 = register kernel,
     // 2 = register kernel with 8 group slots, 3 = staged with 4 stages, 4 = staged with 5 stages
     const bool can_stage = KEYMODE == 0 && aligned_to(sd, 16) && aligned_to(rf, 16) && aligned_to(ls, 16) && n >= kTileRows;
+    Q1Rec *first_out = nullptr;   // asynchronous form: result record of the 4-slot pass
     for (int attempt = 0; attempt < 2; attempt++) {
         const bool wide = attempt == 1 || g_q1_variant == 2;
         const bool staged = can_stage && !wide && g_q1_variant != 1;
@@ -692,7 +769,7 @@ static int launch_q1(ThreadCtx &t, const int32_t *sd, const double *qty, const d
         Q1Rec *partials = (Q1Rec *)arena_alloc(t, sizeof(Q1Rec) * (size_t)(grid + 1));
         if (!partials) return MO_RC_INTERNAL_ERROR;
         Q1Rec *out = partials + grid;
-        cudaEventRecord(t.kev0, t.stream);
+        if (attempt == 0 || !dres) cudaEventRecord(t.kev0, t.stream);
         if (staged) {
             const int stages = g_q1_variant == 3 ? 4 : (g_q1_variant == 4 ? 5 : 3);   // 3 stages measured best (tools/tune.py q1)
             const size_t smem = (size_t)(kStagedThreads / 32) * stages * kTileBytes;
@@ -708,12 +785,19 @@ static int launch_q1(ThreadCtx &t, const int32_t *sd, const double *qty, const d
             else if (stages == 4) q1_staged_kernel<4, 4><<<grid, kStagedThreads, smem, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg);
             else q1_staged_kernel<4, 5><<<grid, kStagedThreads, smem, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg);
         } else if (!wide) {
-            q1_kernel<4, 2, 2, KEYMODE><<<grid, kThreads, 0, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg);
+            q1_kernel<4, 2, 2, KEYMODE><<<grid, kThreads, 0, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg, nullptr);
         } else {
-            q1_kernel<8, 2, 2, KEYMODE><<<grid, kThreads, 0, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg);
+            q1_kernel<8, 2, 2, KEYMODE><<<grid, kThreads, 0, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg, first_out);
         }
-        cudaEventRecord(t.kev1, t.stream);
+        if (attempt == 0 || !dres) cudaEventRecord(t.kev1, t.stream);
         MOB_LAUNCH_CHECK();
+        if (dres) {
+            // no read-back: enqueue the gated 8-slot retry behind a 4-slot pass, then the finalize kernel
+            if (!wide) { first_out = out; continue; }
+            q1_finalize_kernel<<<1, 1, 0, t.stream>>>(first_out, out, dres, row_base);
+            MOB_LAUNCH_CHECK();
+            return MO_RC_SUCCESS;
+        }
         int rc = read_back(t, hrec, out, sizeof(Q1Rec));
         if (rc) return rc;
         if (!hrec->overflow) return MO_RC_SUCCESS;
@@ -759,6 +843,17 @@ int xcall_q1(mo_xcall_args_t *args, uint64_t len) {
     const bool dev = is_device_ptr(args[1].pdata);
     for (int i = 2; i <= 7; i++) if (is_device_ptr(args[i].pdata) != dev) { set_error("q1: columns must all be host or all device"); return MO_RC_INVALID_ARGUMENT; }
     const uint64_t ksz = keymode ? 24 : 1;
+    int64_t row_base = 0;   // optional: params = {int32 cutoff; int32 pad; int64 row_base} -> first_row values are global row numbers
+    if (args[8].dataSz >= 16 && !is_device_ptr(args[8].pdata)) memcpy(&row_base, args[8].pdata + 8, 8);
+
+    if (dev && len && is_device_ptr(args[0].pdata)) {
+        // resident columns AND a device result: enqueue only (see xcall_q6)
+        mo_q1_result_t *dres = (mo_q1_result_t *)args[0].pdata;
+        int rc = keymode ? launch_q1<1>(t, (const int32_t *)args[1].pdata, (const double *)args[2].pdata, (const double *)args[3].pdata, (const double *)args[4].pdata, (const double *)args[5].pdata, args[6].pdata, args[7].pdata, len, cutoff, nullptr, dres, row_base)
+                         : launch_q1<0>(t, (const int32_t *)args[1].pdata, (const double *)args[2].pdata, (const double *)args[3].pdata, (const double *)args[4].pdata, (const double *)args[5].pdata, args[6].pdata, args[7].pdata, len, cutoff, nullptr, dres, row_base);
+        arena_reset(t);
+        return rc;
+    }
 
     Q1Rec F; memset(&F, 0, sizeof F); bool first = true; int rc = MO_RC_SUCCESS;
     for (int g = 0; g < MO_Q1_MAX_GROUPS; g++) F.slot[g].key = kEmptyKey;
@@ -796,12 +891,47 @@ int xcall_q1(mo_xcall_args_t *args, uint64_t len) {
     if (rc) return rc;
     if (F.overflow) { set_error("q1: too many groups"); return MO_RC_INVALID_ARGUMENT; }
     mo_q1_result_t res;
-    q1_finalize(F, &res);
+    q1_finalize(F, &res, row_base);
     if (is_device_ptr(args[0].pdata)) {
         MOB_CUDA_TRY(cudaMemcpyAsync(args[0].pdata, &res, sizeof res, cudaMemcpyHostToDevice, t.stream));
         MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));
     } else memcpy(args[0].pdata, &res, sizeof res);
     return MO_RC_SUCCESS;
+}
+
+// MO_XCALL_Q6_MERGE: args[0] = result as MO_XCALL_Q6_FILTER_SUM ; args[1] = len partial results of 16 bytes (sum f64, count i64)
+int xcall_q6_merge(mo_xcall_args_t *args, uint64_t len) {
+    ThreadCtx &t = tctx();
+    if (!t.ready) return MO_RC_INTERNAL_ERROR;
+    if (!args[0].pdata || args[0].dataSz < 8 || args[1].dataSz < 16 * len) { set_error("q6 merge: result needs 8 bytes, partials 16 bytes each"); return MO_RC_INVALID_ARGUMENT; }
+    const bool async = is_device_ptr(args[0].pdata) && (len == 0 || is_device_ptr(args[1].pdata));
+    Stager st(t);
+    const double *dparts = (const double *)st.in(args[1].pdata, 16 * len);
+    double *dres = (double *)st.out(args[0].pdata, args[0].dataSz >= 16 ? 16 : 8);
+    uint64_t *dn = (uint64_t *)st.out(args[0].pnulls, args[0].pnulls ? 8 : 0);
+    if (st.failed) { st.finish(); return MO_RC_INTERNAL_ERROR; }
+    q6_merge_kernel<<<1, 1, 0, t.stream>>>(dparts, len, Q6DevOut{dres, args[0].dataSz / 8, dn});
+    MOB_LAUNCH_CHECK();
+    if (async) { arena_reset(t); return MO_RC_SUCCESS; }
+    return st.finish();
+}
+
+// MO_XCALL_Q1_MERGE: args[0] = mo_q1_result_t ; args[1] = len partial mo_q1_result_t (first_row already global: row_base param)
+int xcall_q1_merge(mo_xcall_args_t *args, uint64_t len) {
+    ThreadCtx &t = tctx();
+    if (!t.ready) return MO_RC_INTERNAL_ERROR;
+    if (!args[0].pdata || args[0].dataSz < sizeof(mo_q1_result_t) || args[1].dataSz < sizeof(mo_q1_result_t) * len) { set_error("q1 merge: buffers too small"); return MO_RC_INVALID_ARGUMENT; }
+    const bool async = is_device_ptr(args[0].pdata) && (len == 0 || is_device_ptr(args[1].pdata));
+    Stager st(t);
+    const mo_q1_result_t *dparts = (const mo_q1_result_t *)st.in(args[1].pdata, sizeof(mo_q1_result_t) * len);
+    mo_q1_result_t *dres = (mo_q1_result_t *)st.out(args[0].pdata, sizeof(mo_q1_result_t));
+    if (st.failed) { st.finish(); return MO_RC_INTERNAL_ERROR; }
+    q1_merge_kernel<<<1, 1, 0, t.stream>>>(dparts, len, dres);
+    MOB_LAUNCH_CHECK();
+    if (async) { arena_reset(t); return MO_RC_SUCCESS; }
+    int rc = st.finish();
+    if (!rc && !is_device_ptr(args[0].pdata) && ((mo_q1_result_t *)args[0].pdata)->ngroups < 0) { set_error("q1 merge: more than %d distinct group keys", MO_Q1_MAX_GROUPS); return MO_RC_INVALID_ARGUMENT; }
+    return rc;
 }
 
 }  // namespace mob

@@ -11,6 +11,9 @@ int xcall_agg(int op, int T, mo_xcall_args_t *args, uint64_t len);
 int xcall_q6(mo_xcall_args_t *args, uint64_t len);
 int xcall_go_elementwise(int64_t funcId, mo_xcall_args_t *args, uint64_t len);
 int xcall_q1(mo_xcall_args_t *args, uint64_t len);
+int xcall_q6_merge(mo_xcall_args_t *args, uint64_t len);
+int xcall_q1_merge(mo_xcall_args_t *args, uint64_t len);
+int xcall_agg_merge(int op, int T, mo_xcall_args_t *args, uint64_t len);
 int xcall_bruteforce(mo_xcall_args_t *args, uint64_t len);
 int xcall_ivf(mo_xcall_args_t *args, uint64_t len);
 int xcall_topk_merge(mo_xcall_args_t *args, uint64_t len);
@@ -40,7 +43,10 @@ extern "C" int32_t XCall(int64_t runtimeId, int64_t funcId, uint8_t *errStr, uin
     int rc;
     if ((funcId >= 0 && funcId <= 3) || (funcId >= 100 && funcId <= 109)) rc = xcall_rowdist(funcId, a, len);
     else if (funcId >= 0x1000 && funcId < 0x1000 + (5 << 8)) rc = xcall_agg((int)((funcId - 0x1000) >> 8), (int)((funcId - 0x1000) & 0xff), a, len);
-    else if (funcId >= 0x4000 && funcId < 0x5200) rc = xcall_go_elementwise(funcId, a, len);
+    else if (funcId >= 0x1800 && funcId < 0x1800 + (5 << 8)) rc = xcall_agg_merge((int)((funcId - 0x1800) >> 8), (int)((funcId - 0x1800) & 0xff), a, len);
+    else if (funcId == MO_XCALL_Q6_MERGE) rc = xcall_q6_merge(a, len);
+    else if (funcId == MO_XCALL_Q1_MERGE) rc = xcall_q1_merge(a, len);
+    else if (funcId >= 0x4000 && funcId < 0x5800) rc = xcall_go_elementwise(funcId, a, len);
     else if (funcId == MO_XCALL_Q6_FILTER_SUM) rc = xcall_q6(a, len);
     else if (funcId == MO_XCALL_Q1_GROUP_AGG) rc = xcall_q1(a, len);
     else if (funcId == MO_XCALL_BRUTEFORCE_TOPK_F32) rc = xcall_bruteforce(a, len);

@@ -99,12 +99,125 @@ def q6_filter_sum(shipdate, discount, quantity, extendedprice, n, date_lo, date_
     return float(res[0]), int(res.view(np.int64)[1]), bool(rv.nulls[0] & np.uint64(1))
 
 
-def q1_group_agg(shipdate, quantity, extendedprice, discount, tax, returnflag, linestatus, n, cutoff):
+Q6_RESULT_BYTES = 16
+Q1_RESULT_BYTES = C.sizeof(capi.Q1Result)
+
+
+def q6_filter_sum_device(shipdate, discount, quantity, extendedprice, n, date_lo, date_hi, disc_lo, disc_hi, qty_hi, out_ptr, out_nulls_ptr=None):
+    """asynchronous form: resident columns, result {f64 sum, i64 rows} written to caller-owned DEVICE memory at out_ptr, nothing is
+    read back and the calling thread's stream is not synchronised (the partial Group of a multi-GPU scan)"""
+    rv = Vector(data_ptr=out_ptr, data_nbytes=Q6_RESULT_BYTES, nulls_ptr=out_nulls_ptr, length=1)
+    p = capi.Q6Params(date_lo, date_hi, disc_lo, disc_hi, qty_hi)
+    xcall(capi.XCALL_Q6_FILTER_SUM, [rv, _vec(shipdate, n), _vec(discount, n), _vec(quantity, n), _vec(extendedprice, n), _params_vec(p)], n)
+
+
+def q6_merge_device(parts_ptr, nparts, out_ptr, out_nulls_ptr=None):
+    """MergeGroup on the device: nparts x {f64 sum, i64 rows} -> one, in order"""
+    xcall(capi.XCALL_Q6_MERGE, [Vector(data_ptr=out_ptr, data_nbytes=Q6_RESULT_BYTES, nulls_ptr=out_nulls_ptr, length=1),
+                                Vector(data_ptr=parts_ptr, data_nbytes=Q6_RESULT_BYTES * nparts, length=nparts)], nparts)
+
+
+def q6_merge(parts):
+    """host form of the same merge: parts = [(sum, rows), ...] -> (sum, rows, is_null)"""
+    buf = np.zeros(2 * len(parts), dtype=np.float64)
+    for i, (s_, c_) in enumerate(parts):
+        buf[2 * i] = s_
+        buf.view(np.int64)[2 * i + 1] = c_
+    res = np.zeros(2, dtype=np.float64)
+    rn = np.zeros(1, dtype=np.uint64)
+    xcall(capi.XCALL_Q6_MERGE, [Vector(data=res, nulls=rn, length=1), Vector(data=buf, length=len(parts))], len(parts))
+    return float(res[0]), int(res.view(np.int64)[1]), bool(rn[0] & np.uint64(1))
+
+
+def _q1_groups(r):
+    out = []
+    for g in range(r.ngroups):
+        s = r.groups[g]
+        out.append({k: getattr(s, k) for k in ("returnflag", "linestatus", "first_row", "sum_qty", "sum_base_price", "sum_disc_price",
+                                               "sum_charge", "avg_qty", "avg_price", "avg_disc", "sum_disc", "count_order")})
+    return out
+
+
+def q1_result_from_bytes(raw):
+    """mo_q1_result_t bytes -> list of group dicts (ngroups = -1: too many distinct keys)"""
+    r = capi.Q1Result.from_buffer_copy(bytes(raw))
+    if r.ngroups < 0:
+        raise capi.MoError(capi.RC_INVALID_ARGUMENT, "q1: more than %d distinct group keys" % capi.Q1_MAX_GROUPS)
+    return _q1_groups(r)
+
+
+def q1_group_agg_device(shipdate, quantity, extendedprice, discount, tax, returnflag, linestatus, n, cutoff, out_ptr, row_base=0):
+    """asynchronous form of q1_group_agg: mo_q1_result_t written to DEVICE memory at out_ptr; first_row values are offset by row_base"""
+    rv = Vector(data_ptr=out_ptr, data_nbytes=Q1_RESULT_BYTES, length=1)
+    xcall(capi.XCALL_Q1_GROUP_AGG, [rv, _vec(shipdate, n), _vec(quantity, n), _vec(extendedprice, n), _vec(discount, n), _vec(tax, n),
+                                     _vec(returnflag, n), _vec(linestatus, n), _params_vec(capi.Q1Params(cutoff, 0, row_base))], n)
+
+
+def q1_merge_device(parts_ptr, nparts, out_ptr):
+    xcall(capi.XCALL_Q1_MERGE, [Vector(data_ptr=out_ptr, data_nbytes=Q1_RESULT_BYTES, length=1),
+                                Vector(data_ptr=parts_ptr, data_nbytes=Q1_RESULT_BYTES * nparts, length=nparts)], nparts)
+
+
+def q1_merge(parts_bytes, nparts):
+    """host form: nparts concatenated mo_q1_result_t -> merged list of group dicts"""
+    buf = np.frombuffer(bytes(parts_bytes), dtype=np.uint8).copy()
+    res = np.zeros(Q1_RESULT_BYTES, dtype=np.uint8)
+    xcall(capi.XCALL_Q1_MERGE, [Vector(data=res, length=1), Vector(data=buf, length=nparts)], nparts)
+    return q1_result_from_bytes(res.tobytes())
+
+
+def agg_state_device(op, T, col, nulls, n, out_ptr, out_nulls_ptr=None):
+    """asynchronous MO_XCALL_AGG: mo_agg_state_t (24 bytes) written to DEVICE memory"""
+    cv = _vec(col, n)
+    if nulls is not None:
+        cv.nulls_ptr = nulls.ptr
+    cv.length = n
+    xcall(capi.XCALL_AGG(op, T), [Vector(data_ptr=out_ptr, data_nbytes=capi.AGG_STATE_BYTES, nulls_ptr=out_nulls_ptr, length=1), cv], n)
+
+
+def agg_merge_device(op, T, parts_ptr, nparts, out_ptr, out_bytes=capi.AGG_STATE_BYTES, out_nulls_ptr=None):
+    xcall(capi.XCALL_AGG_MERGE(op, T), [Vector(data_ptr=out_ptr, data_nbytes=out_bytes, nulls_ptr=out_nulls_ptr, length=1),
+                                        Vector(data_ptr=parts_ptr, data_nbytes=capi.AGG_STATE_BYTES * nparts, length=nparts)], nparts)
+
+
+def agg_state(op, T, col, nulls=None, length=None):
+    """synchronous partial state (bits, count, rc) of one column"""
+    n = length if length is not None else (col.nbytes // np.dtype(capi.NP_OF_T[T]).itemsize if isinstance(col, DeviceBuffer) else len(col))
+    res = np.zeros(3, dtype=np.uint64)
+    rn = np.zeros(1, dtype=np.uint64)
+    cv = _vec(col, n)
+    if nulls is not None:
+        if isinstance(nulls, DeviceBuffer):
+            cv.nulls_ptr = nulls.ptr
+        else:
+            cv.nulls = np.ascontiguousarray(nulls, dtype=np.uint64)
+    cv.length = n
+    rc, msg = xcall(capi.XCALL_AGG(op, T), [Vector(data=res, nulls=rn, length=1), cv], n, raise_on_error=False)
+    if rc not in (0, capi.RC_OUT_OF_RANGE):
+        raise capi.MoError(rc, msg)
+    return res
+
+
+def agg_merge(op, T, states, final=True):
+    """MergeGroup of partial states (array [n, 3] uint64).  final=True: (rc, value bits as uint64, count, is_null); else the merged state"""
+    st = np.ascontiguousarray(states, dtype=np.uint64).reshape(-1, 3)
+    res = np.zeros(3 if not final else 2, dtype=np.uint64)
+    rn = np.zeros(1, dtype=np.uint64)
+    rc, msg = xcall(capi.XCALL_AGG_MERGE(op, T), [Vector(data=res, nulls=rn, length=1), Vector(data=st.reshape(-1), length=st.shape[0])], st.shape[0],
+                    raise_on_error=False)
+    if rc not in (0, capi.RC_OUT_OF_RANGE):
+        raise capi.MoError(rc, msg)
+    if not final:
+        return res
+    return rc, res[0], int(res[1]), bool(rn[0] & np.uint64(1))
+
+
+def q1_group_agg(shipdate, quantity, extendedprice, discount, tax, returnflag, linestatus, n, cutoff, row_base=0):
     """TPC-H Q1 grouped aggregates (q1.sql).  returnflag/linestatus: packed uint8 columns or varlena cell buffers.
     Returns a list of dicts in first-seen group order."""
     res = np.zeros(C.sizeof(capi.Q1Result), dtype=np.uint8)
     rv = Vector(data=res, length=1)
-    cut = Vector(data=np.asarray([cutoff], dtype=np.int32), length=1, const=True)
+    cut = _params_vec(capi.Q1Params(cutoff, 0, row_base))
     xcall(capi.XCALL_Q1_GROUP_AGG, [rv, _vec(shipdate, n), _vec(quantity, n), _vec(extendedprice, n), _vec(discount, n), _vec(tax, n),
                                      _vec(returnflag, n), _vec(linestatus, n), cut], n)
     r = capi.Q1Result.from_buffer_copy(res.tobytes())

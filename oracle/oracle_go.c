@@ -40,6 +40,78 @@ enum { CMP_EQ = 0, CMP_NE, CMP_GT, CMP_GE, CMP_LT, CMP_LE };
 /* ---------------------------------------------------------------------------------------------
  * bitmap: pkg/common/bitmap/bitmap.go:196-229 (Add/Contains), LSB-first uint64 words, set = NULL
  * ------------------------------------------------------------------------------------------- */
+
+/* ---------------------------------------------------------------------------------------------
+ * Persistent worker pool for the multi-threaded pipelines below (the reference keeps one pipeline goroutine per core
+ * alive for the query, pkg/sql/compile/scope.go:442-499; creating and joining 128 pthreads per call made the timed CPU
+ * arm noisy).  Job j always runs on worker j % nworkers and worker w is pinned to the w-th CPU this process may use, so
+ * the rows a worker generated (first touch) are the rows it later scans: NUMA-local without libnuma.
+ * ------------------------------------------------------------------------------------------- */
+#include <sched.h>
+typedef void *(*og_fn)(void *);
+static struct {
+    pthread_mutex_t mu; pthread_cond_t start, done;
+    pthread_t *th; int nth;
+    og_fn fn; char *jobs; size_t jobsz; int njobs;
+    uint64_t gen; int remaining;
+    cpu_set_t allowed; int nallowed; int have_allowed;
+} POOL = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER};
+static pthread_mutex_t POOL_RUN = PTHREAD_MUTEX_INITIALIZER;
+
+static void *pool_main(void *arg) {
+    /* arg = (id, generation current when the worker was created): the first generation published after that is its first job */
+    const int id = (int)((uint64_t *)arg)[0];
+    uint64_t seen_gen = ((uint64_t *)arg)[1];
+    free(arg);
+    if (POOL.have_allowed && POOL.nallowed > 0) {
+        int want = id % POOL.nallowed, seen = 0;
+        for (int c = 0; c < CPU_SETSIZE; c++) {
+            if (!CPU_ISSET(c, &POOL.allowed)) continue;
+            if (seen++ == want) { cpu_set_t one; CPU_ZERO(&one); CPU_SET(c, &one); pthread_setaffinity_np(pthread_self(), sizeof one, &one); break; }
+        }
+    }
+    for (;;) {
+        pthread_mutex_lock(&POOL.mu);
+        while (POOL.gen == seen_gen) pthread_cond_wait(&POOL.start, &POOL.mu);
+        seen_gen = POOL.gen;
+        og_fn fn = POOL.fn; char *jobs = POOL.jobs; size_t jobsz = POOL.jobsz; int njobs = POOL.njobs, nth = POOL.nth;
+        pthread_mutex_unlock(&POOL.mu);
+        for (int j = id; j < njobs; j += nth) fn(jobs + (size_t)j * jobsz);
+        pthread_mutex_lock(&POOL.mu);
+        if (--POOL.remaining == 0) pthread_cond_signal(&POOL.done);
+        pthread_mutex_unlock(&POOL.mu);
+    }
+    return NULL;
+}
+
+/* run fn over njobs job records (jobsz bytes apart) on the pool; returns when all are done */
+static void og_run(og_fn fn, void *jobs, size_t jobsz, int njobs) {
+    if (njobs <= 0) return;
+    if (njobs == 1) { fn(jobs); return; }
+    pthread_mutex_lock(&POOL_RUN);
+    pthread_mutex_lock(&POOL.mu);
+    if (!POOL.have_allowed) {
+        CPU_ZERO(&POOL.allowed);
+        if (sched_getaffinity(0, sizeof POOL.allowed, &POOL.allowed) == 0) POOL.nallowed = CPU_COUNT(&POOL.allowed);
+        POOL.have_allowed = 1;
+    }
+    if (POOL.nth < njobs) {   /* grow: worker ids are stable, so the job -> CPU map stays fixed */
+        POOL.th = realloc(POOL.th, sizeof(pthread_t) * (size_t)njobs);
+        for (int t = POOL.nth; t < njobs; t++) {
+            uint64_t *a = malloc(16); a[0] = (uint64_t)t; a[1] = POOL.gen;
+            pthread_create(&POOL.th[t], NULL, pool_main, a);
+        }
+        POOL.nth = njobs;
+    }
+    POOL.fn = fn; POOL.jobs = jobs; POOL.jobsz = jobsz; POOL.njobs = njobs;
+    POOL.remaining = POOL.nth;
+    POOL.gen++;
+    pthread_cond_broadcast(&POOL.start);
+    while (POOL.remaining) pthread_cond_wait(&POOL.done, &POOL.mu);
+    pthread_mutex_unlock(&POOL.mu);
+    pthread_mutex_unlock(&POOL_RUN);
+}
+
 static inline bool bm_has(const uint64_t *p, uint64_t i) { return p && ((p[i >> 6] >> (i & 63)) & 1); }
 static inline void bm_add(uint64_t *p, uint64_t i) { p[i >> 6] |= (uint64_t)1 << (i & 63); }
 static inline void bm_del(uint64_t *p, uint64_t i) { p[i >> 6] &= ~((uint64_t)1 << (i & 63)); }
@@ -233,6 +305,38 @@ int32_t og_compare(int32_t op, int32_t type, bool *r, const void *a, const void 
     case T_float32: CMP_LOOP(float); case T_float64: CMP_LOOP(double);
     }
     return OG_RC_INVALID;
+}
+
+/* og_compare_f32_scale: the float32 branch of the six compare functions when the column type carries scale > 0
+ * (func_compare.go:207-216 eq, :725-734 gt, :852-861 ge, :979-988 ne, :1106-1115 lt, :1233-1242 le): both sides are rounded to
+ * `scale` decimals first -- a = float32(math.Round(float64(a)*pow) / pow), pow = math.Pow10(scale); math.Round rounds half away
+ * from zero = C round(). */
+int32_t og_compare_f32_scale(int32_t op, int32_t scale, bool *r, const float *a, const float *b, uint64_t n,
+                             int32_t c1, int32_t c2, const uint64_t *n1, const uint64_t *n2, uint64_t *rnulls) {
+    if ((c1 && bm_has(n1, 0)) || (c2 && bm_has(n2, 0))) {
+        for (uint64_t i = 0; i < n; i++) bm_add(rnulls, i);
+        return OG_RC_OK;
+    }
+    for (uint64_t w = 0; w < bm_words(n); w++) {
+        if (!c1 && n1) rnulls[w] |= n1[w];
+        if (!c2 && n2) rnulls[w] |= n2[w];
+    }
+    if (n & 63) rnulls[bm_words(n) - 1] &= (((uint64_t)1 << (n & 63)) - 1);
+    double pw = 1.0;
+    for (int k = 0; k < scale; k++) pw *= 10.0;   /* math.Pow10: exact for scale <= 22 */
+    for (uint64_t i = 0; i < n; i++) {
+        if (bm_has(rnulls, i)) continue;
+        float x = a[c1 ? 0 : i], y = b[c2 ? 0 : i]; bool v;
+        x = (float)(round((double)x * pw) / pw);
+        y = (float)(round((double)y * pw) / pw);
+        switch (op) {
+        case CMP_EQ: v = x == y; break; case CMP_NE: v = x != y; break;
+        case CMP_GT: v = x > y; break;  case CMP_GE: v = x >= y; break;
+        case CMP_LT: v = x < y; break;  default: v = x <= y; break;
+        }
+        r[i] = v;
+    }
+    return OG_RC_OK;
 }
 
 /*
@@ -723,16 +827,14 @@ int32_t og_bruteforce_search(int32_t is_f64, int32_t metric, const void *dataset
     if (limit == 0) return OG_RC_OK;
     if (nthreads < 1) nthreads = 1;
     if (nthreads > nq) nthreads = (int32_t)(nq > 0 ? nq : 1);
-    pthread_t *th = malloc(sizeof(pthread_t) * (size_t)nthreads);
     bf_job *jobs = malloc(sizeof(bf_job) * (size_t)nthreads);
     int64_t per = (nq + nthreads - 1) / nthreads;
     for (int t = 0; t < nthreads; t++) {
         int64_t q0 = t * per, q1 = q0 + per; if (q1 > nq) q1 = nq; if (q0 > nq) q0 = nq;
         jobs[t] = (bf_job){is_f64, metric, limit, dataset, queries, n, dim, q0, q1, keys, dists, NULL, 0};
-        pthread_create(&th[t], NULL, bf_worker, &jobs[t]);
     }
-    for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
-    free(th); free(jobs);
+    og_run(bf_worker, jobs, sizeof(bf_job), nthreads);
+    free(jobs);
     return OG_RC_OK;
 }
 
@@ -784,16 +886,14 @@ int32_t og_ivf_search_f32(const float *data, const int32_t *assign, int64_t n, i
     if (nthreads < 1) nthreads = 1;
     if (nthreads > nq) nthreads = (int32_t)(nq > 0 ? nq : 1);
     if (nprobe > nlist) nprobe = (int32_t)nlist;
-    pthread_t *th = malloc(sizeof(pthread_t) * (size_t)nthreads);
     ivf_job *jobs = malloc(sizeof(ivf_job) * (size_t)nthreads);
     int64_t per = (nq + nthreads - 1) / nthreads;
     for (int t = 0; t < nthreads; t++) {
         int64_t q0 = t * per, q1 = q0 + per; if (q1 > nq) q1 = nq; if (q0 > nq) q0 = nq;
         jobs[t] = (ivf_job){data, assign, n, dim, centroids, nlist, queries, q0, q1, nprobe, limit, metric, sqrt_out, keys, dists};
-        pthread_create(&th[t], NULL, ivf_worker, &jobs[t]);
     }
-    for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
-    free(th); free(jobs);
+    og_run(ivf_worker, jobs, sizeof(ivf_job), nthreads);
+    free(jobs);
     return OG_RC_OK;
 }
 
@@ -874,22 +974,20 @@ int32_t og_q6(const int32_t *shipdate, const double *discount, const double *qua
     if (nthreads < 1) nthreads = 1;
     int64_t nblocks = (n + BLOCK_ROWS - 1) / BLOCK_ROWS;
     if (nthreads > nblocks) nthreads = (int32_t)(nblocks > 0 ? nblocks : 1);
-    pthread_t *th = malloc(sizeof(pthread_t) * (size_t)nthreads);
     q6_job *jobs = malloc(sizeof(q6_job) * (size_t)nthreads);
     int64_t per = (nblocks + nthreads - 1) / nthreads;
     for (int t = 0; t < nthreads; t++) {
         int64_t r0 = t * per * BLOCK_ROWS, r1 = r0 + per * BLOCK_ROWS; if (r0 > n) r0 = n; if (r1 > n) r1 = n;
         jobs[t] = (q6_job){shipdate, discount, quantity, extprice, r0, r1, date_lo, date_hi, disc_lo, disc_hi, qty_hi, 0, 0, 1};
-        pthread_create(&th[t], NULL, q6_worker, &jobs[t]);
     }
+    og_run(q6_worker, jobs, sizeof(q6_job), nthreads);
     double s = 0; uint8_t nul = 1; int64_t ns = 0;
     for (int t = 0; t < nthreads; t++) {
-        pthread_join(th[t], NULL);
         if (!jobs[t].isnull) { if (nul) { nul = 0; s = jobs[t].sum; } else s = s + jobs[t].sum; } /* BatchMerge sumavg2.go:222-236 */
         ns += jobs[t].nsel;
     }
     *sum = s; *isnull = nul; *nsel = ns;
-    free(th); free(jobs);
+    free(jobs);
     return OG_RC_OK;
 }
 
@@ -961,18 +1059,16 @@ int64_t og_q1(const int32_t *shipdate, const double *qty, const double *price, c
     if (nthreads < 1) nthreads = 1;
     int64_t nblocks = (n + BLOCK_ROWS - 1) / BLOCK_ROWS;
     if (nthreads > nblocks) nthreads = (int32_t)(nblocks > 0 ? nblocks : 1);
-    pthread_t *th = malloc(sizeof(pthread_t) * (size_t)nthreads);
     q1_job *jobs = calloc((size_t)nthreads, sizeof(q1_job));
     int64_t per = (nblocks + nthreads - 1) / nthreads;
     for (int t = 0; t < nthreads; t++) {
         int64_t r0 = t * per * BLOCK_ROWS, r1 = r0 + per * BLOCK_ROWS; if (r0 > n) r0 = n; if (r1 > n) r1 = n;
         jobs[t].shipdate = shipdate; jobs[t].qty = qty; jobs[t].price = price; jobs[t].disc = disc; jobs[t].tax = tax;
         jobs[t].rf = rf; jobs[t].ls = ls; jobs[t].row0 = r0; jobs[t].row1 = r1; jobs[t].cutoff = cutoff;
-        pthread_create(&th[t], NULL, q1_worker, &jobs[t]);
     }
+    og_run(q1_worker, jobs, sizeof(q1_job), nthreads);
     int64_t ng = 0; int bad = 0;
     for (int t = 0; t < nthreads; t++) {
-        pthread_join(th[t], NULL);
         if (jobs[t].overflow) bad = 1;
         for (int64_t g = 0; g < jobs[t].ng && !bad; g++) { /* MergeGroup: re-hash partial keys, BatchMerge */
             int64_t d = -1;
@@ -987,7 +1083,7 @@ int64_t og_q1(const int32_t *shipdate, const double *qty, const double *price, c
             for (int a = 0; a < 4; a++) out_cnts[d * 4 + a] += jobs[t].cnts[g * 4 + a];
         }
     }
-    free(th); free(jobs);
+    free(jobs);
     return bad ? -1 : ng;
 }
 
@@ -1006,17 +1102,15 @@ int32_t og_sum_int64_mt(const int64_t *col, const uint64_t *nulls, int64_t n, in
     if (nthreads < 1) nthreads = 1;
     int64_t nblocks = (n + BLOCK_ROWS - 1) / BLOCK_ROWS;
     if (nthreads > nblocks) nthreads = (int32_t)(nblocks > 0 ? nblocks : 1);
-    pthread_t *th = malloc(sizeof(pthread_t) * (size_t)nthreads);
     s64_job *jobs = calloc((size_t)nthreads, sizeof(s64_job));
     int64_t per = (nblocks + nthreads - 1) / nthreads;
     for (int t = 0; t < nthreads; t++) {
         int64_t r0 = t * per * BLOCK_ROWS, r1 = r0 + per * BLOCK_ROWS; if (r0 > n) r0 = n; if (r1 > n) r1 = n;
         jobs[t].col = col; jobs[t].nulls = nulls; jobs[t].row0 = r0; jobs[t].row1 = r1;
-        pthread_create(&th[t], NULL, s64_worker, &jobs[t]);
     }
+    og_run(s64_worker, jobs, sizeof(s64_job), nthreads);
     int64_t s = 0; uint8_t nul = 1; int32_t rc = 0;
     for (int t = 0; t < nthreads; t++) {
-        pthread_join(th[t], NULL);
         if (jobs[t].rc) rc = jobs[t].rc;
         if (!jobs[t].isnull && !rc) {
             if (nul) { nul = 0; s = jobs[t].sum; }
@@ -1028,8 +1122,109 @@ int32_t og_sum_int64_mt(const int64_t *col, const uint64_t *nulls, int64_t n, in
         }
     }
     *sum = s; *isnull = nul;
-    free(th); free(jobs);
+    free(jobs);
     return rc;
+}
+
+
+/* ---------------------------------------------------------------------------------------------
+ * Synthetic column generators: the C twin of matrixone_b200/csrc/datagen.cu (and datagen.py), bit for bit, run on the
+ * worker pool with the SAME block-range split the pipelines above use, so every worker first-touches the rows it will scan.
+ * Data synthesis only -- used by bench.py's CPU legs so that they neither depend on the GPU library nor spend minutes in numpy.
+ * ------------------------------------------------------------------------------------------- */
+static inline uint64_t gen_mix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+static inline uint64_t gen_hash3(uint64_t seed, uint64_t stream, uint64_t row) { return gen_mix64(gen_mix64(seed ^ (stream * 0xD6E8FEB86659FD93ull)) + row); }
+
+typedef struct { uint64_t seed, row0; int64_t i0, i1; int32_t *sd; double *qty, *price, *disc, *tax; uint8_t *rf, *ls; } genl_job;
+static void *genl_worker(void *arg) {
+    genl_job *j = (genl_job *)arg;
+    for (int64_t i = j->i0; i < j->i1; i++) {
+        const uint64_t r = j->row0 + (uint64_t)i;
+        const int32_t sd = 8036 + (int32_t)(gen_hash3(j->seed, 1, r) % 2526ull);
+        const uint64_t q = 1 + gen_hash3(j->seed, 2, r) % 50ull;
+        const uint64_t cents = q * (90000ull + gen_hash3(j->seed, 3, r) % 120001ull);
+        if (j->sd) j->sd[i] = sd;
+        if (j->qty) j->qty[i] = (double)q;
+        if (j->price) j->price[i] = (double)cents / 100.0;
+        if (j->disc) j->disc[i] = (double)(gen_hash3(j->seed, 4, r) % 11ull) / 100.0;
+        if (j->tax) j->tax[i] = (double)(gen_hash3(j->seed, 5, r) % 9ull) / 100.0;
+        const uint64_t h6 = gen_hash3(j->seed, 6, r);
+        const int32_t receipt = sd + 1 + (int32_t)(h6 % 30ull);
+        if (j->rf) j->rf[i] = receipt <= 9298 ? (((h6 >> 32) & 1ull) ? 'R' : 'A') : 'N';
+        if (j->ls) j->ls[i] = sd <= 9298 ? 'F' : 'O';
+    }
+    return NULL;
+}
+void og_gen_lineitem(uint64_t seed, uint64_t row0, int64_t n, int32_t nthreads, int32_t *sd, double *qty, double *price, double *disc,
+                     double *tax, uint8_t *rf, uint8_t *ls) {
+    if (nthreads < 1) nthreads = 1;
+    int64_t nblocks = (n + BLOCK_ROWS - 1) / BLOCK_ROWS;
+    if (nthreads > nblocks) nthreads = (int32_t)(nblocks > 0 ? nblocks : 1);
+    genl_job *jobs = malloc(sizeof(genl_job) * (size_t)nthreads);
+    int64_t per = (nblocks + nthreads - 1) / nthreads;
+    for (int t = 0; t < nthreads; t++) {
+        int64_t r0 = t * per * BLOCK_ROWS, r1 = r0 + per * BLOCK_ROWS; if (r0 > n) r0 = n; if (r1 > n) r1 = n;
+        jobs[t] = (genl_job){seed, row0, r0, r1, sd, qty, price, disc, tax, rf, ls};
+    }
+    og_run(genl_worker, jobs, sizeof(genl_job), nthreads);
+    free(jobs);
+}
+
+typedef struct { uint64_t seed, row0; int64_t i0, i1; int64_t *out; } geni_job;
+static void *geni_worker(void *arg) {
+    geni_job *j = (geni_job *)arg;
+    for (int64_t i = j->i0; i < j->i1; i++) j->out[i] = (int64_t)(int32_t)(uint32_t)(gen_hash3(j->seed, 1, j->row0 + (uint64_t)i) & 0xffffffffull);
+    return NULL;
+}
+void og_gen_int64(uint64_t seed, uint64_t row0, int64_t n, int32_t nthreads, int64_t *out) {
+    if (nthreads < 1) nthreads = 1;
+    int64_t nblocks = (n + BLOCK_ROWS - 1) / BLOCK_ROWS;
+    if (nthreads > nblocks) nthreads = (int32_t)(nblocks > 0 ? nblocks : 1);
+    geni_job *jobs = malloc(sizeof(geni_job) * (size_t)nthreads);
+    int64_t per = (nblocks + nthreads - 1) / nthreads;
+    for (int t = 0; t < nthreads; t++) {
+        int64_t r0 = t * per * BLOCK_ROWS, r1 = r0 + per * BLOCK_ROWS; if (r0 > n) r0 = n; if (r1 > n) r1 = n;
+        jobs[t] = (geni_job){seed, row0, r0, r1, out};
+    }
+    og_run(geni_worker, jobs, sizeof(geni_job), nthreads);
+    free(jobs);
+}
+
+typedef struct { uint64_t seed, row0; int64_t i0, i1, dim; float *out; const float *centers; int64_t ncenters; float sigma; int32_t *comp; } genv_job;
+static void *genv_worker(void *arg) {
+    genv_job *j = (genv_job *)arg;
+    for (int64_t i = j->i0; i < j->i1; i++) {
+        const uint64_t r = j->row0 + (uint64_t)i;
+        const uint64_t c = j->centers ? gen_hash3(j->seed, 7, r) % (uint64_t)j->ncenters : 0;
+        if (j->comp) j->comp[i] = (int32_t)c;
+        for (int64_t d = 0; d < j->dim; d++) {
+            const uint64_t h = gen_hash3(j->seed, 16 + (uint64_t)d, r);
+            const int32_t s = (int32_t)(h & 0xffff) + (int32_t)((h >> 16) & 0xffff) + (int32_t)((h >> 32) & 0xffff) + (int32_t)((h >> 48) & 0xffff) - 131070;
+            float z = (float)s * 2.6428965e-05f;
+            if (j->centers) { float sz = j->sigma * z; z = j->centers[c * (uint64_t)j->dim + (uint64_t)d] + sz; }
+            j->out[i * j->dim + d] = z;
+        }
+    }
+    return NULL;
+}
+/* comp (optional): the mixture component of every row (a valid IVF list assignment when centers are the centroids) */
+void og_gen_vectors_f32(uint64_t seed, uint64_t row0, int64_t n, int64_t dim, int32_t nthreads, float *out, const float *centers,
+                        int64_t ncenters, float sigma, int32_t *comp) {
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > n) nthreads = (int32_t)(n > 0 ? n : 1);
+    genv_job *jobs = malloc(sizeof(genv_job) * (size_t)nthreads);
+    int64_t per = (n + nthreads - 1) / nthreads;
+    for (int t = 0; t < nthreads; t++) {
+        int64_t r0 = t * per, r1 = r0 + per; if (r0 > n) r0 = n; if (r1 > n) r1 = n;
+        jobs[t] = (genv_job){seed, row0, r0, r1, dim, out, centers, ncenters, sigma, comp};
+    }
+    og_run(genv_worker, jobs, sizeof(genv_job), nthreads);
+    free(jobs);
 }
 
 /* Kahan-compensated fp64 sum, used by tests to separate ordering noise from real bugs. */

@@ -119,3 +119,163 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# round 2: the reference-held TPC-H fixture and the FunctionTestCase tables of the elementwise engine
+# ---------------------------------------------------------------------------------------------------------------------
+def tpch_lineitem():
+    """test/distributed/cases/benchmark/tpch/02_LOAD/03_insert_lineitem.sql -> the seven columns Q1 / Q6 read, exact (integers:
+    days since 1970-01-01, quantity, price in cents, discount and tax in 1/100) -- DECIMAL(15,2) columns of 01_create_table.sql:83-86"""
+    import datetime
+    path = os.path.join(REF, "test/distributed/cases/benchmark/tpch/02_LOAD/03_insert_lineitem.sql")
+    rows = re.findall(r'^\((\d+),(\d+),(\d+),(\d+),(\d+),(\d+(?:\.\d+)?),(\d+\.\d+),(\d+\.\d+),(\d+\.\d+),"(.)","(.)","(\d{4})-(\d\d)-(\d\d)"', open(path).read(), re.M)
+    epoch = datetime.date(1970, 1, 1).toordinal()
+    def cents(s):
+        a, _, b = s.partition(".")
+        return int(a) * 100 + int((b + "00")[:2])
+    out = {"_source": "test/distributed/cases/benchmark/tpch/02_LOAD/03_insert_lineitem.sql (%d rows); expected results in tpch_kat.json" % len(rows),
+           "shipdate_days": [datetime.date(int(r[11]), int(r[12]), int(r[13])).toordinal() - epoch for r in rows],
+           "quantity": [int(float(r[5])) for r in rows], "extendedprice_cents": [cents(r[6]) for r in rows],
+           "discount_pct": [cents(r[7]) for r in rows], "tax_pct": [cents(r[8]) for r in rows],
+           "returnflag": "".join(r[9] for r in rows), "linestatus": "".join(r[10] for r in rows)}
+    assert len(rows) > 6000
+    return out
+
+
+_GO_CONSTS = {"math.MaxInt8": 127, "math.MinInt8": -128, "math.MaxInt16": 32767, "math.MinInt16": -32768, "math.MaxInt32": 2 ** 31 - 1,
+              "math.MinInt32": -2 ** 31, "math.MaxInt64": 2 ** 63 - 1, "math.MinInt64": -2 ** 63, "math.MaxUint8": 255, "math.MaxUint16": 65535,
+              "math.MaxUint32": 2 ** 32 - 1, "math.MaxUint64": 2 ** 64 - 1, "math.MaxFloat32": 3.40282346638528859811704183484516925440e+38,
+              "math.MaxFloat64": 1.79769313486231570814527423731704356798070e+308, "math.SmallestNonzeroFloat64": 5e-324,
+              "math.SmallestNonzeroFloat32": 1.401298464324817070923729583289916131280e-45}
+_FIXED = {"int8", "int16", "int32", "int64", "uint8", "uint16", "uint32", "uint64", "float32", "float64", "bool"}
+
+
+def _split_top(s):
+    """split at top-level commas (respects () {} [])"""
+    out, depth, cur = [], 0, []
+    for ch in s:
+        if ch in "({[":
+            depth += 1
+        elif ch in ")}]":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append("".join(cur).strip()); cur = []
+        else:
+            cur.append(ch)
+    if "".join(cur).strip():
+        out.append("".join(cur).strip())
+    return out
+
+
+def _go_value(tok):
+    tok = tok.strip()
+    if tok in ("true", "false"):
+        return tok == "true"
+    t = tok
+    for k, v in sorted(_GO_CONSTS.items(), key=lambda kv: -len(kv[0])):
+        t = t.replace(k, repr(v))
+    t = re.sub(r"\b(?:int8|int16|int32|int64|uint8|uint16|uint32|uint64|float32|float64)\(", "(", t)
+    t = t.replace("math.Inf(1)", "float('inf')").replace("math.Inf(-1)", "float('-inf')").replace("math.NaN()", "float('nan')")
+    if not re.fullmatch(r"[-+*/ ().0-9eE'infat]+", t):
+        raise ValueError(tok)
+    return eval(t, {"__builtins__": {}}, {"float": float})
+
+
+def _go_slice(expr):
+    """[]T{...} -> (T, [values]) ; nil -> (None, None)"""
+    expr = expr.strip()
+    if expr == "nil":
+        return None, None
+    m = re.fullmatch(r"\[\](\w+)\{(.*)\}", expr, re.S)
+    if not m:
+        raise ValueError(expr[:40])
+    body = re.sub(r"//[^\n]*", "", m.group(2))
+    return m.group(1), [_go_value(x) for x in _split_top(body) if x.strip()]
+
+
+def _call_args(src, start):
+    """src[start] == '(' -> (args string, index after the closing paren)"""
+    depth, i = 0, start
+    while True:
+        if src[i] in "({[":
+            depth += 1
+        elif src[i] in ")}]":
+            depth -= 1
+            if depth == 0:
+                return src[start + 1:i], i + 1
+        i += 1
+
+
+def function_kats():
+    """FunctionTestCase tables of pkg/sql/plan/function/{arithmetic_plus,arithmetic_minus,arithmetic_multi,arithmetic_div_mod,
+    arithmetic_div_zero,func_compare,func_compare_logic,operatorSet}_test.go restricted to the fixed-width numeric / bool types and the operators on the
+    hot path: inputs (values + null flags, const flag), expected values + null flags, expected error."""
+    base = os.path.join(REF, "pkg/sql/plan/function")
+    files = ["arithmetic_plus_test.go", "arithmetic_minus_test.go", "arithmetic_multi_test.go", "arithmetic_div_mod_test.go",
+             "arithmetic_div_zero_test.go", "func_compare_test.go", "func_compare_logic_test.go", "operatorSet_test.go"]
+    fns = {"plusFn": "add", "minusFn": "sub", "multiFn": "mul", "divFn": "div", "modFn": "mod", "equalFn": "eq", "notEqualFn": "ne", "greatThanFn": "gt",
+           "greatEqualFn": "ge", "lessThanFn": "lt", "lessEqualFn": "le", "opMultiAnd": "and", "opMultiOr": "or", "notFn": "not", "xorFn": "xor"}
+    cases, skipped = [], 0
+    for fname in files:
+        src = open(os.path.join(base, fname)).read()
+        for m in re.finditer(r"NewFunctionTestCase\(proc,\s*tc\.inputs,\s*tc\.expect,\s*(\w+)\)", src):
+            fn = m.group(1)
+            if fn not in fns:
+                continue
+            blk_start = src.rfind("tcTemp{", 0, m.start())
+            blk = src[blk_start:m.start()]
+            line = src.count("\n", 0, blk_start) + 1
+            try:
+                inputs = []
+                for im in re.finditer(r"NewFunctionTest(Const)?Input\(", blk):
+                    args, _ = _call_args(blk, im.end() - 1)
+                    a = _split_top(args)
+                    ty = re.search(r"types\.T_(\w+)", a[0]).group(1)
+                    scale = 0
+                    sm = re.search(r"types\.New\(types\.T_\w+,\s*(\d+),\s*(\d+)\)", a[0])
+                    if sm:
+                        scale = int(sm.group(2))
+                    gt, vals = _go_slice(a[1])
+                    _, nulls = _go_slice(a[2]) if len(a) > 2 else (None, None)
+                    if ty not in _FIXED or gt != ty and not (ty == "bool" and gt == "bool"):
+                        raise ValueError("type " + ty)
+                    inputs.append({"type": ty, "scale": scale, "const": bool(im.group(1)), "values": vals, "nulls": nulls})
+                em = re.search(r"NewFunctionTestResult\(", blk)
+                args, _ = _call_args(blk, em.end() - 1)
+                a = _split_top(args)
+                ety = re.search(r"types\.T_(\w+)", a[0]).group(1)
+                want_err = a[1].strip() == "true"
+                _, evals = _go_slice(a[2])
+                _, enulls = _go_slice(a[3]) if len(a) > 3 else (None, None)
+                if ety not in _FIXED:
+                    raise ValueError("type " + ety)
+                info = re.search(r'info:\s*"([^"]*)"', blk)
+                cases.append({"file": fname, "line": line, "fn": fn, "op": fns[fn], "info": info.group(1) if info else "", "inputs": inputs,
+                              "expect": {"type": ety, "want_err": want_err, "values": evals, "nulls": enulls}})
+            except (ValueError, AttributeError, IndexError, SyntaxError):
+                skipped += 1
+    assert len(cases) >= 60, len(cases)
+    # JSON has no inf / nan: encode specials as strings
+    def enc(v):
+        if isinstance(v, float) and (v != v or v in (float("inf"), float("-inf"))):
+            return "nan" if v != v else ("inf" if v > 0 else "-inf")
+        return v
+    for c in cases:
+        for x in c["inputs"] + [c["expect"]]:
+            if x["values"] is not None:
+                x["values"] = [enc(v) for v in x["values"]]
+    return {"_source": "pkg/sql/plan/function/{%s}: FunctionTestCase tables (fixed-width numeric / bool types, hot-path operators); %d other-type cases not transcribed" % (",".join(files), skipped),
+            "cases": cases}
+
+
+def main2():
+    for name, fn in (("tpch_lineitem", tpch_lineitem), ("function_kat", function_kats)):
+        data = fn()
+        with open(os.path.join(OUT, name + ".json"), "w") as f:
+            json.dump(data, f, separators=(",", ":") if name == "tpch_lineitem" else None, indent=None if name == "tpch_lineitem" else 0)
+        print(name, {k: (len(v) if isinstance(v, (list, str)) else "") for k, v in data.items() if not k.startswith("_")})
+
+
+if __name__ == "__main__" and "--round2" in __import__("sys").argv:
+    main2()

@@ -28,6 +28,8 @@ def go():
         lib.og_arith.argtypes = [_i32, _i32, _vp, _vp, _vp, _u64, _i32, _i32, _vp, _vp, _vp, _i32, _vp]
         lib.og_compare.restype = _i32
         lib.og_compare.argtypes = [_i32, _i32, _vp, _vp, _vp, _u64, _i32, _i32, _vp, _vp, _vp]
+        lib.og_compare_f32_scale.restype = _i32
+        lib.og_compare_f32_scale.argtypes = [_i32, _i32, _vp, _vp, _vp, _u64, _i32, _i32, _vp, _vp, _vp]
         lib.og_between.restype = _i32
         lib.og_between.argtypes = [_i32, _vp, _vp, _vp, _vp, _u64, _vp, _vp]
         lib.og_multi_logic.restype = _i32
@@ -77,6 +79,12 @@ def go():
         lib.og_q1.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp]
         lib.og_sum_int64_mt.restype = _i32
         lib.og_sum_int64_mt.argtypes = [_vp, _vp, _i64, _i32, _vp, _vp]
+        lib.og_gen_lineitem.restype = None
+        lib.og_gen_lineitem.argtypes = [_u64, _u64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+        lib.og_gen_int64.restype = None
+        lib.og_gen_int64.argtypes = [_u64, _u64, _i64, _i32, _vp]
+        lib.og_gen_vectors_f32.restype = None
+        lib.og_gen_vectors_f32.argtypes = [_u64, _u64, _i64, _i64, _i32, _vp, _vp, _i64, C.c_float, _vp]
         lib.og_kahan_sum.restype = _f64
         lib.og_kahan_sum.argtypes = [_vp, _i64]
         _go = lib
@@ -169,3 +177,26 @@ def q1(cols, n, cutoff, nthreads=1):
                     "avg_qty": s[4] / c[0], "avg_price": s[5] / c[1], "avg_disc": s[6] / c[2], "sum_disc": s[6], "count_order": int(c[3])})
     out.sort(key=lambda g: g["first_row"])
     return out
+
+
+def gen_lineitem(seed, row0, n, nthreads=8, names=("shipdate", "quantity", "extendedprice", "discount", "tax", "returnflag", "linestatus")):
+    """lineitem columns for rows [row0, row0 + n): the C twin of MoB200_GenLineitem / datagen.lineitem, first-touched by the pool"""
+    dts = {"shipdate": np.int32, "returnflag": np.uint8, "linestatus": np.uint8}
+    cols = {k: np.empty(n, dtype=dts.get(k, np.float64)) for k in names}
+    g = lambda k: p(cols[k]) if k in cols else None
+    go().og_gen_lineitem(seed, row0, n, nthreads, g("shipdate"), g("quantity"), g("extendedprice"), g("discount"), g("tax"), g("returnflag"), g("linestatus"))
+    return cols
+
+
+def gen_int64(seed, row0, n, nthreads=8):
+    out = np.empty(n, dtype=np.int64)
+    go().og_gen_int64(seed, row0, n, nthreads, p(out))
+    return out
+
+
+def gen_vectors_f32(seed, row0, n, dim, nthreads=8, centers=None, sigma=1.0, want_components=False):
+    out = np.empty((n, dim), dtype=np.float32)
+    comp = np.empty(n, dtype=np.int32) if want_components else None
+    c = None if centers is None else np.ascontiguousarray(centers, dtype=np.float32)
+    go().og_gen_vectors_f32(seed, row0, n, dim, nthreads, p(out), p(c), 0 if c is None else c.shape[0], float(sigma), p(comp))
+    return (out, comp) if want_components else out
