@@ -202,6 +202,34 @@ typedef struct { int32_t div0_null; int32_t reserved; int64_t err_row; } mo_go_p
 #define MO_XCALL_GO_MULTI_AND 0x5100
 #define MO_XCALL_GO_MULTI_OR 0x5101
 
+/* ---- the standalone column operators of the colexec pipeline (csrc/colops.cu).  Host or device pointers; with device pointers on
+ * every vector FILTER_SELS and SHUFFLE only enqueue work (asynchronous form, as MO_XCALL_AGG).
+ *
+ * FILTER_SELS  Filter.Call inner loop (filter.go:116-152): rows with (!null && true), ascending.
+ *              args: [0] sels int64[] (a host buffer only has to hold the selected rows) ; [1] count int64[1] ; [2] bool vector (+pnulls).  len = rows
+ * SHUFFLE(sz)  Vector.Shrink / Union / shuffle.FixedLengthShuffle (vector.go:1014,2583 ; shuffle.go:21-26) with nulls.Filter
+ *              (nulls.go:237-281) fused: dst[i] = src[sels[i]], dst null bit i = src null bit sels[i].  sz = element bytes: 1, 2, 4, 8, 16, 24 (varlena cell).
+ *              args: [0] dst (+pnulls out) ; [1] src (+pnulls, nullCnt = its length in bits) ; [2] sels int64[len].  len = selected rows
+ * PACK_KEYS    intHashMapIterator.encodeHashKeys / fillKeys (inthashmap.go:92-183): up to 8 key bytes per row from fixed-width columns, in
+ *              has_null mode a marker byte (0 / 1) precedes every column's value bytes and a NULL contributes the marker only.
+ *              args: [0] keys uint64[len] (+pnulls out, has_null = 0: rows with a NULL key join no group) ; [1] host params {int32 ncols, int32 has_null}
+ *              ; [2 .. 2+ncols) key columns (+pnulls; a const vector holds one element)
+ * GROUP_IDS    IntHashMap insert as driven by Group.buildOneBatch (exec2.go:325-362): 1-based group ids in FIRST-SEEN order; the table persists across
+ *              calls through (ngroups, table_keys).  The hash function is not observable (random seeds, hashtable/hash.go:41-47), the ids are.
+ *              args: [0] groups uint64[len] ; [1] int64 ngroups (in/out) ; [2] table_keys uint64[capacity] (in: keys of groups 1..ngroups ; out: + new groups)
+ *              ; [3] keys uint64[len] (+pnulls: such rows get id 0 = GroupNotMatched)
+ * GROUP_AGG(op, T)  sumAvgExec / countColumnExec / minMaxExecFixed .BatchFill (sumavg2.go:133-199, count2.go:120-146, minmax2.go:49-80) into a
+ *              caller-owned state that persists across batches: SUM into int64 / uint64 / float64 (overflow -> MO_RC_OUT_OF_RANGE exactly when
+ *              the serial loop would fail), AVG = SUM + counts, COUNT into int64, MIN / MAX in 8-byte slots (value in the low bytes) with the
+ *              first-value-initialises / strict-compare rule incl. NaN.  A group is NULL until its first value (state pnulls, in/out).
+ *              args: [0] state 8 bytes per group (+pnulls) ; [1] counts int64 per group (AVG: required) ; [2] groups uint64[len] ; [3] column (+pnulls)
+ * float64 group sums are accumulated with atomics: the association order is not fixed, results agree with the serial loop to ~1e-13 relative. */
+#define MO_XCALL_FILTER_SELS 0x6000
+#define MO_XCALL_PACK_KEYS 0x6001
+#define MO_XCALL_GROUP_IDS 0x6002
+#define MO_XCALL_SHUFFLE(szof) (0x6100 + (szof))
+#define MO_XCALL_GROUP_AGG(op, T) (0x6400 + ((op) << 8) + (T))
+
 #define MO_XCALL_Q6_FILTER_SUM 0x2000
 typedef struct mo_q6_params_t {
     int32_t date_lo, date_hi;  /* date_lo <= d < date_hi */

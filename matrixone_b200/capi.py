@@ -44,6 +44,17 @@ def XCALL_AGG_MERGE(op, T):
     return 0x1800 + (op << 8) + T
 
 
+XCALL_FILTER_SELS, XCALL_PACK_KEYS, XCALL_GROUP_IDS = 0x6000, 0x6001, 0x6002
+
+
+def XCALL_SHUFFLE(szof):
+    return 0x6100 + szof
+
+
+def XCALL_GROUP_AGG(op, T):
+    return 0x6400 + (op << 8) + T
+
+
 XCALL_Q6_FILTER_SUM = 0x2000
 XCALL_Q1_GROUP_AGG = 0x2001
 XCALL_Q6_MERGE = 0x2002

@@ -344,9 +344,20 @@ __global__ void popcount_kernel(const uint64_t *p, uint64_t nbits, unsigned long
 // multi-GPU caller hand the partial state straight to NCCL (MergeGroup seam, mergeGroup.go:132-247) and merge on the device.
 enum Cls { C_SIGNED = 0, C_UNSIGNED = 1, C_FLOAT = 2, C_MINMAX = 3, C_COUNT = 4 };
 
-__global__ void agg_state_kernel(const Rec *rec, int op, int cls, uint64_t len, const unsigned long long *nullcount, const int32_t *ovflag,
+__global__ void agg_state_kernel(const Rec *rec, int op, int cls, uint64_t len, const unsigned long long *nullcount, const Seg *segs, uint64_t nseg,
                                  uint64_t *res, uint64_t res_words, uint64_t *rnulls) {
     uint64_t bits = 0, cnt = 0; int64_t rc = MO_RC_SUCCESS; bool isnull = false;
+    // signed SUM whose magnitudes do not fit int64: fold the serial-order segment summaries (prefix_seg_kernel ran behind the same gate)
+    int32_t ov = 0;
+    if (cls == C_SIGNED && segs && prefix_check_needed(rec)) {
+        __int128 run = 0;
+        const __int128 hi = (__int128)INT64_MAX, lo = (__int128)INT64_MIN;
+        for (uint64_t s = 0; s < nseg; s++) {
+            if (run + segs[s].maxp > hi || run + segs[s].minp < lo) { ov = 1; break; }
+            run += segs[s].total;
+        }
+    }
+    const int32_t *ovflag = &ov;
     if (cls == C_COUNT) { cnt = len - (nullcount ? *nullcount : 0ull); bits = cnt; }
     else {
         cnt = rec->cnt; isnull = cnt == 0;
@@ -367,16 +378,26 @@ __global__ void agg_state_kernel(const Rec *rec, int op, int cls, uint64_t len, 
 }
 
 template <typename T>
-static int agg_async_typed(ThreadCtx &t, int op, int cls, const void *dcol, const uint64_t *dnulls, uint64_t n, Rec **drec, int32_t **dov) {
-    *dov = nullptr;
+static int agg_async_typed(ThreadCtx &t, int op, int cls, const void *dcol, const uint64_t *dnulls, uint64_t n, Rec **drec, Seg **dsegs, uint64_t *nseg_out) {
+    *dsegs = nullptr; *nseg_out = 0;
     if (op == MO_AGG_MIN) return launch_agg<T, K_MIN>(t, dcol, dnulls, n, nullptr, drec);
     if (op == MO_AGG_MAX) return launch_agg<T, K_MAX>(t, dcol, dnulls, n, nullptr, drec);
     if (cls == C_FLOAT) return launch_agg<T, K_SUM_FLOAT>(t, dcol, dnulls, n, nullptr, drec);
     if (cls == C_UNSIGNED) return launch_agg<T, K_SUM_UNSIGNED>(t, dcol, dnulls, n, nullptr, drec);
     int rc = launch_agg<T, K_SUM_SIGNED>(t, dcol, dnulls, n, nullptr, drec);
     if (rc) return rc;
-    // the exact serial-order prefix check runs only when the device-side gate says the magnitudes do not fit int64
-    return signed_prefix_overflow<T>(t, dcol, dnulls, n, nullptr, *drec, dov);
+    // the exact serial-order prefix check runs only when the device-side gate says the magnitudes do not fit int64: the gated segment
+    // kernel is enqueued, the 1-thread state kernel folds the segments (one launch less than the synchronous form)
+    const uint64_t nseg_target = (uint64_t)num_sms() * 256;
+    uint64_t seg_rows = (n + nseg_target - 1) / nseg_target;
+    if (seg_rows < 64) seg_rows = 64;
+    const uint64_t nseg = (n + seg_rows - 1) / seg_rows;
+    Seg *segs = (Seg *)arena_alloc(t, sizeof(Seg) * nseg + 16);
+    if (!segs) return MO_RC_INTERNAL_ERROR;
+    prefix_seg_kernel<T><<<(unsigned)((nseg + 255) / 256), 256, 0, t.stream>>>((const T *)dcol, dnulls, n, seg_rows, nseg, segs, *drec);
+    MOB_LAUNCH_CHECK();
+    *dsegs = segs; *nseg_out = nseg;
+    return MO_RC_SUCCESS;
 }
 
 static int xcall_agg_async(ThreadCtx &t, int op, int T, mo_xcall_args_t *args, uint64_t len) {
@@ -384,7 +405,7 @@ static int xcall_agg_async(ThreadCtx &t, int op, int T, mo_xcall_args_t *args, u
     const uint64_t *dnulls = args[1].pnulls;
     const bool is_signed = T >= MO_T_INT8 && T <= MO_T_INT64, is_unsigned = T >= MO_T_UINT8 && T <= MO_T_UINT64;
     const bool is_float = T == MO_T_FLOAT32 || T == MO_T_FLOAT64;
-    Rec *drec = nullptr; int32_t *dov = nullptr; unsigned long long *dcount = nullptr;
+    Rec *drec = nullptr; Seg *dsegs = nullptr; uint64_t nseg = 0; unsigned long long *dcount = nullptr;
     int cls, rc = MO_RC_SUCCESS;
     Rec *zero = (Rec *)arena_alloc(t, sizeof(Rec));
     if (!zero) return MO_RC_INTERNAL_ERROR;
@@ -406,21 +427,21 @@ static int xcall_agg_async(ThreadCtx &t, int op, int T, mo_xcall_args_t *args, u
         if (!mm && !is_signed && !is_unsigned && !is_float) { set_error("sum: unsupported type %d", T); return MO_RC_INVALID_ARGUMENT; }
         if (len == 0) { MOB_CUDA_TRY(cudaMemsetAsync(zero, 0, sizeof(Rec), t.stream)); drec = zero; }
         else switch (T) {
-        case MO_T_BOOL: case MO_T_UINT8: rc = agg_async_typed<uint8_t>(t, op, cls, dcol, dnulls, len, &drec, &dov); break;
-        case MO_T_INT8: rc = agg_async_typed<int8_t>(t, op, cls, dcol, dnulls, len, &drec, &dov); break;
-        case MO_T_INT16: rc = agg_async_typed<int16_t>(t, op, cls, dcol, dnulls, len, &drec, &dov); break;
-        case MO_T_UINT16: rc = agg_async_typed<uint16_t>(t, op, cls, dcol, dnulls, len, &drec, &dov); break;
-        case MO_T_INT32: case MO_T_DATE: rc = agg_async_typed<int32_t>(t, op, cls, dcol, dnulls, len, &drec, &dov); break;
-        case MO_T_UINT32: rc = agg_async_typed<uint32_t>(t, op, cls, dcol, dnulls, len, &drec, &dov); break;
-        case MO_T_INT64: case MO_T_TIME: case MO_T_DATETIME: case MO_T_TIMESTAMP: rc = agg_async_typed<int64_t>(t, op, cls, dcol, dnulls, len, &drec, &dov); break;
-        case MO_T_UINT64: rc = agg_async_typed<uint64_t>(t, op, cls, dcol, dnulls, len, &drec, &dov); break;
-        case MO_T_FLOAT32: rc = agg_async_typed<float>(t, op, cls, dcol, dnulls, len, &drec, &dov); break;
-        case MO_T_FLOAT64: rc = agg_async_typed<double>(t, op, cls, dcol, dnulls, len, &drec, &dov); break;
+        case MO_T_BOOL: case MO_T_UINT8: rc = agg_async_typed<uint8_t>(t, op, cls, dcol, dnulls, len, &drec, &dsegs, &nseg); break;
+        case MO_T_INT8: rc = agg_async_typed<int8_t>(t, op, cls, dcol, dnulls, len, &drec, &dsegs, &nseg); break;
+        case MO_T_INT16: rc = agg_async_typed<int16_t>(t, op, cls, dcol, dnulls, len, &drec, &dsegs, &nseg); break;
+        case MO_T_UINT16: rc = agg_async_typed<uint16_t>(t, op, cls, dcol, dnulls, len, &drec, &dsegs, &nseg); break;
+        case MO_T_INT32: case MO_T_DATE: rc = agg_async_typed<int32_t>(t, op, cls, dcol, dnulls, len, &drec, &dsegs, &nseg); break;
+        case MO_T_UINT32: rc = agg_async_typed<uint32_t>(t, op, cls, dcol, dnulls, len, &drec, &dsegs, &nseg); break;
+        case MO_T_INT64: case MO_T_TIME: case MO_T_DATETIME: case MO_T_TIMESTAMP: rc = agg_async_typed<int64_t>(t, op, cls, dcol, dnulls, len, &drec, &dsegs, &nseg); break;
+        case MO_T_UINT64: rc = agg_async_typed<uint64_t>(t, op, cls, dcol, dnulls, len, &drec, &dsegs, &nseg); break;
+        case MO_T_FLOAT32: rc = agg_async_typed<float>(t, op, cls, dcol, dnulls, len, &drec, &dsegs, &nseg); break;
+        case MO_T_FLOAT64: rc = agg_async_typed<double>(t, op, cls, dcol, dnulls, len, &drec, &dsegs, &nseg); break;
         default: set_error("agg: unsupported type %d", T); return MO_RC_INVALID_ARGUMENT;
         }
         if (rc) return rc;
     } else { set_error("agg: unknown op %d", op); return MO_RC_INVALID_ARGUMENT; }
-    agg_state_kernel<<<1, 1, 0, t.stream>>>(drec, op, cls, len, dcount, dov, (uint64_t *)args[0].pdata, args[0].dataSz / 8, args[0].pnulls);
+    agg_state_kernel<<<1, 1, 0, t.stream>>>(drec, op, cls, len, dcount, dsegs, nseg, (uint64_t *)args[0].pdata, args[0].dataSz / 8, args[0].pnulls);
     MOB_LAUNCH_CHECK();
     arena_reset(t);   // stream order protects the scratch: the next call's kernels queue behind these
     return MO_RC_SUCCESS;
@@ -431,7 +452,7 @@ static int xcall_agg_async(ThreadCtx &t, int op, int T, mo_xcall_args_t *args, u
 template <typename T>
 __device__ bool mm_less(uint64_t a, uint64_t b) { return from_bits<T>(a) < from_bits<T>(b); }
 
-__global__ void agg_merge_kernel(const uint64_t *parts, uint64_t n, int op, int T, int cls, uint64_t *res, uint64_t res_words, uint64_t *rnulls) {
+__global__ void agg_merge_kernel(const uint64_t *parts, uint64_t n, int op, int T, int cls, uint64_t *res, uint64_t res_words, uint64_t *rnulls, int64_t *rc_out) {
     uint64_t bits = 0, cnt = 0; int64_t rc = MO_RC_SUCCESS; bool has = false;
     double dsum = 0.0;
     for (uint64_t i = 0; i < n; i++) {
@@ -478,6 +499,7 @@ __global__ void agg_merge_kernel(const uint64_t *parts, uint64_t n, int op, int 
     if (res_words >= 2) res[1] = cnt;
     if (res_words >= 3) res[2] = (uint64_t)rc;
     if (rnulls) rnulls[0] = isnull ? 1ull : 0ull;
+    if (rc_out) *rc_out = rc;
 }
 
 }  // namespace
@@ -498,15 +520,15 @@ int xcall_agg_merge(int op, int T, mo_xcall_args_t *args, uint64_t len) {
     uint64_t *dres = (uint64_t *)st.out(args[0].pdata, args[0].dataSz >= 24 ? 24 : args[0].dataSz >= 16 ? 16 : 8);
     uint64_t *dn = (uint64_t *)st.out(args[0].pnulls, args[0].pnulls ? 8 : 0);
     if (st.failed) { st.finish(); return MO_RC_INTERNAL_ERROR; }
-    agg_merge_kernel<<<1, 1, 0, t.stream>>>(dparts, len, op, T, cls, dres, args[0].dataSz / 8, dn);
+    int64_t *drc = async ? nullptr : (int64_t *)st.tmp(8);
+    if (st.failed) { st.finish(); return MO_RC_INTERNAL_ERROR; }
+    agg_merge_kernel<<<1, 1, 0, t.stream>>>(dparts, len, op, T, cls, dres, args[0].dataSz / 8, dn, drc);
     MOB_LAUNCH_CHECK();
-    if (async) { arena_reset(t); return MO_RC_SUCCESS; }
+    if (async) { arena_reset(t); return MO_RC_SUCCESS; }   // the merged state's rc word carries errors
     int rc = MO_RC_SUCCESS;
-    if (args[0].dataSz >= 24) {   // a host-visible state carries its rc; report it as the call's rc too
-        uint64_t w[3];
-        int r2 = read_back(t, w, dres, 24);
-        if (r2) rc = r2; else if ((int64_t)w[2]) rc = (int)(int64_t)w[2];
-    }
+    int64_t hrc = 0;
+    int r2 = read_back(t, &hrc, drc, 8);
+    if (r2) rc = r2; else if (hrc) { rc = (int)hrc; set_error("data out of range: merged SUM overflows its 64-bit state"); }
     int frc = st.finish();
     return rc ? rc : frc;
 }

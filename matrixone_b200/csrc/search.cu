@@ -483,6 +483,14 @@ namespace {
 
 // (query, probe rank) -> bucket of its list.  Order inside a bucket is arbitrary (atomics) but results do not depend on it:
 // every (query, list) pair is scanned independently and exactly, and lands in the fixed slot query*nprobe + rank.
+// list sharding (whole lists per GPU): a probed list that is empty on this shard contributes nothing -- drop the pair before it is
+// bucketed, so neither its residual operand nor its work unit is ever built
+__global__ void ivf_mask_empty_kernel(int64_t *probes, int64_t npairs, const int64_t *__restrict__ offsets) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npairs; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t l = probes[i];
+        if (l >= 0 && offsets[l + 1] <= offsets[l]) probes[i] = -1;
+    }
+}
 __global__ void ivf_count_kernel(const int64_t *probes, int64_t npairs, int *cnt) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npairs; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t l = probes[i];
@@ -530,7 +538,7 @@ struct IvfJob {
 // caller's rows.
 static int ivf_search_level(ThreadCtx &t, const IvfJob &J, int level, const float *dq, int64_t nq, int64_t *ok, double *od) {
     IvfPlan plan;
-    int rc = ivf_make_plan(t, J.dcent, J.nlist, J.dim, dq, nq, J.nprobe, J.metric, plan);
+    int rc = ivf_make_plan(t, J.dcent, J.nlist, J.dim, dq, nq, J.nprobe, J.metric, plan, J.doffsets);
     if (rc) return rc;
     if (level >= 2 || !tc_ivf_applicable(J.n, J.dim, nq, J.k, J.nprobe, J.metric, level == 1)) {
         if (level > 0) g_last_tc_fallbacks = (int)nq;
@@ -605,7 +613,8 @@ int xcall_ivf(mo_xcall_args_t *args, uint64_t len) {
 
 // 1. probes[q][rank] = list id by ascending centroid distance (findCentroids, ivfflat/search.go:292-311): the exact top-nprobe kernel
 // 2. invert: list -> bucket of (query, slot) pairs
-int ivf_make_plan(ThreadCtx &t, const float *dcent, int64_t nlist, int dim, const float *dq, int64_t nq, int nprobe, int metric, IvfPlan &plan) {
+int ivf_make_plan(ThreadCtx &t, const float *dcent, int64_t nlist, int dim, const float *dq, int64_t nq, int nprobe, int metric, IvfPlan &plan,
+                  const int64_t *doffsets) {
     plan.nprobe = nprobe;
     plan.npairs = nq * nprobe;
     const int64_t npairs = plan.npairs;
@@ -623,6 +632,7 @@ int ivf_make_plan(ThreadCtx &t, const float *dcent, int64_t nlist, int dim, cons
                  : bruteforce_topk_device(t, dcent, nlist, dim, dq, nq, nprobe, metric, 0, 0, plan.probes, probe_d);
     if (rc) return rc;
     int *dstart = cnt + nlist, *cursor = cnt + 2 * nlist;
+    if (doffsets) { ivf_mask_empty_kernel<<<num_sms() * 4, 256, 0, t.stream>>>(plan.probes, npairs, doffsets); MOB_LAUNCH_CHECK(); }
     MOB_CUDA_TRY(cudaMemsetAsync(cnt, 0, (size_t)nlist * 4 * 3, t.stream));
     ivf_count_kernel<<<num_sms() * 4, 256, 0, t.stream>>>(plan.probes, npairs, cnt);
     MOB_LAUNCH_CHECK();
@@ -631,6 +641,7 @@ int ivf_make_plan(ThreadCtx &t, const float *dcent, int64_t nlist, int dim, cons
     MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));
     int run = 0;
     for (int64_t l = 0; l < nlist; l++) { plan.hstart[(size_t)l] = run; run += plan.hcnt[(size_t)l]; }
+    plan.nvalid = run;   // bucket entries [0, nvalid) are defined; pairs of missing / empty lists have none
     MOB_CUDA_TRY(cudaMemcpyAsync(dstart, plan.hstart.data(), (size_t)nlist * 4, cudaMemcpyHostToDevice, t.stream));
     ivf_fill_kernel<<<num_sms() * 4, 256, 0, t.stream>>>(plan.probes, npairs, nprobe, dstart, cursor, plan.bucket_q, plan.bucket_l, plan.bucket_slot, plan.pair_pos);
     MOB_LAUNCH_CHECK();

@@ -9,6 +9,7 @@ namespace mob {
 struct IvfPlan {
     int nprobe = 0;
     int64_t npairs = 0;            // nq * nprobe
+    int64_t nvalid = 0;            // pairs that landed in a bucket (npairs minus missing / empty lists)
     int64_t *probes = nullptr;     // [nq][nprobe] list ids by ascending centroid distance (-1 = none)       (device)
     int32_t *bucket_q = nullptr;   // [npairs] query of every bucket entry, entries of one list are contiguous  (device)
     int32_t *bucket_l = nullptr;   // [npairs] list of every bucket entry                                        (device)
@@ -19,7 +20,8 @@ struct IvfPlan {
 
 int bruteforce_topk_device(ThreadCtx &t, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq, int k, int metric,
                            int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d);
-int ivf_make_plan(ThreadCtx &t, const float *dcent, int64_t nlist, int dim, const float *dq, int64_t nq, int nprobe, int metric, IvfPlan &plan);
+int ivf_make_plan(ThreadCtx &t, const float *dcent, int64_t nlist, int dim, const float *dq, int64_t nq, int nprobe, int metric, IvfPlan &plan,
+                  const int64_t *doffsets = nullptr);   // doffsets: drop the pairs of lists that are empty here (list-sharded index)
 int ivf_exact_scan(ThreadCtx &t, const IvfPlan &plan, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq,
                    const std::vector<int64_t> &offsets, const int64_t *drowids, int k, int metric, int sqrt_out, int64_t *ok, double *od);
 

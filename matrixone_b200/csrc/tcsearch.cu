@@ -423,7 +423,8 @@ __global__ void split_kernel(const float *__restrict__ x, int64_t n, int dim, in
 __global__ void split_residual_kernel(const float *__restrict__ x, int64_t n, int dim, int kprime, int mode,
                                       const float *__restrict__ cent, const int64_t *__restrict__ offsets, int64_t nlist,
                                       const int32_t *__restrict__ idx_q, const int32_t *__restrict__ idx_l,
-                                      __nv_bfloat16 *__restrict__ out, float *__restrict__ norm, float *__restrict__ lonorm, int *__restrict__ nonfinite) {
+                                      __nv_bfloat16 *__restrict__ out, float *__restrict__ norm, float *__restrict__ lonorm, int *__restrict__ nonfinite,
+                                      int hi_only) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t r = warp; r < n; r += nwarps) {
@@ -437,6 +438,29 @@ __global__ void split_residual_kernel(const float *__restrict__ x, int64_t n, in
         const float *p = x + src * dim, *c = cent + l * dim;
         __nv_bfloat16 *o = out + r * kprime;
         double s = 0.0, sl = 0.0;
+        if (hi_only && (dim & 7) == 0 && (kprime & 7) == 0) {
+            // one-term level: the candidate pass multiplies only the first `dim` columns (hi . hi), so only they are written -- a third
+            // of the bytes; 8 elements per lane: two 128-bit loads per operand, one 128-bit store
+            for (int j = lane * 8; j < dim; j += 256) {
+                const float4 p0 = *reinterpret_cast<const float4 *>(p + j), p1 = *reinterpret_cast<const float4 *>(p + j + 4);
+                const float4 c0 = *reinterpret_cast<const float4 *>(c + j), c1 = *reinterpret_cast<const float4 *>(c + j + 4);
+                const float v[8] = {__fsub_rn(p0.x, c0.x), __fsub_rn(p0.y, c0.y), __fsub_rn(p0.z, c0.z), __fsub_rn(p0.w, c0.w),
+                                    __fsub_rn(p1.x, c1.x), __fsub_rn(p1.y, c1.y), __fsub_rn(p1.z, c1.z), __fsub_rn(p1.w, c1.w)};
+                __align__(16) __nv_bfloat16 h[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    h[e] = __float2bfloat16_rn(v[e]);
+                    s += (double)v[e] * (double)v[e];
+                    const double d = (double)(v[e] - __bfloat162float(h[e]));
+                    sl += d * d;
+                    if (!(fabsf(v[e]) <= 3.0e38f)) *nonfinite = 1;
+                }
+                *reinterpret_cast<int4 *>(o + j) = *reinterpret_cast<const int4 *>(h);
+            }
+            s = warp_sum_f64(s); sl = warp_sum_f64(sl);
+            if (lane == 0) { norm[r] = (float)s; lonorm[r] = (float)sl; }
+            continue;
+        }
         for (int j = lane; j < dim; j += 32) {
             const float v = __fsub_rn(p[j], c[j]);
             const __nv_bfloat16 hi = __float2bfloat16_rn(v);
@@ -623,7 +647,8 @@ ivf_seed_bound_kernel(const float *__restrict__ data, const float *__restrict__ 
     unsigned char *ring = rescore_smem + (size_t)wib * Cfg::kStages * Cfg::kStageBytes;
     const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t q = w0; q < nq; q += nw) {
-        const int64_t l = probes[q * nprobe];
+        int64_t l = -1;   // the nearest probed list that has rows here (a list-sharded index holds only some of them)
+        for (int r = 0; r < nprobe && l < 0; r++) { const int64_t c = probes[q * nprobe + r]; if (c >= 0 && offsets[c + 1] > offsets[c]) l = c; }
         const int64_t b = l >= 0 ? offsets[l] : 0, e = l >= 0 ? offsets[l + 1] : 0;
         const bool good = b + lane < e;
         const uint8_t *px = good ? reinterpret_cast<const uint8_t *>(data + (b + lane) * dim) : nullptr;
@@ -768,7 +793,7 @@ static int tc_prepare_ivf_entries(ThreadCtx &t, const float *x, int64_t n, int d
     op.lonorm = (float *)arena_alloc(t, (size_t)(n > 0 ? n : 1) * 4);
     if (!op.bf || !op.norm || !op.lonorm) return MO_RC_INTERNAL_ERROR;
     if (n > 0) {
-        split_residual_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(x, n, dim, op.kprime, 1, dcent, doffsets, nlist, nullptr, nullptr, op.bf, op.norm, op.lonorm, dnonfinite);
+        split_residual_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(x, n, dim, op.kprime, 1, dcent, doffsets, nlist, nullptr, nullptr, op.bf, op.norm, op.lonorm, dnonfinite, 0);
         MOB_LAUNCH_CHECK();
     }
     c.x = x; c.c = dcent; c.n = n; c.dim = dim; c.epoch = t.arena_epoch; c.t = &t; c.op = op;
@@ -1124,8 +1149,8 @@ int ivf_tc_scan(ThreadCtx &t, const IvfPlan &plan, const float *ddata, int64_t n
     A.norm = (float *)arena_alloc(t, (size_t)plan.npairs * 4);
     A.lonorm = (float *)arena_alloc(t, (size_t)plan.npairs * 4);
     if (!A.bf || !A.norm || !A.lonorm) return MO_RC_INTERNAL_ERROR;
-    split_residual_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(dq, plan.npairs, dim, A.kprime, 0, dcent, nullptr, nlist, plan.bucket_q, plan.bucket_l,
-                                                               A.bf, A.norm, A.lonorm, dnonfinite);
+    split_residual_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(dq, plan.nvalid, dim, A.kprime, 0, dcent, nullptr, nlist, plan.bucket_q, plan.bucket_l,
+                                                               A.bf, A.norm, A.lonorm, dnonfinite, one_term ? 1 : 0);
     MOB_LAUNCH_CHECK();
     int hnonfinite = 0;
     rc = read_back(t, &hnonfinite, dnonfinite, 4);
@@ -1235,7 +1260,7 @@ int32_t MoB200_SearchPrepareIvf(const void *data, uint64_t n, int64_t dim, const
     if (!rc && cudaMemsetAsync(dnonfinite, 0, 4, t.stream) != cudaSuccess) rc = MO_RC_INTERNAL_ERROR;
     if (!rc) {
         split_residual_kernel<<<num_sms() * 8, 256, 0, t.stream>>>(e.x, e.n, e.dim, e.op.kprime, 1, e.cent, (const int64_t *)offsets, e.nlist, nullptr, nullptr,
-                                                                   e.op.bf, e.op.norm, e.op.lonorm, dnonfinite);
+                                                                   e.op.bf, e.op.norm, e.op.lonorm, dnonfinite, 0);
         g_launches++;
         if (cudaGetLastError() != cudaSuccess) rc = MO_RC_INTERNAL_ERROR;
     }

@@ -14,6 +14,11 @@ int xcall_q1(mo_xcall_args_t *args, uint64_t len);
 int xcall_q6_merge(mo_xcall_args_t *args, uint64_t len);
 int xcall_q1_merge(mo_xcall_args_t *args, uint64_t len);
 int xcall_agg_merge(int op, int T, mo_xcall_args_t *args, uint64_t len);
+int xcall_filter_sels(mo_xcall_args_t *args, uint64_t len);
+int xcall_shuffle(int szof, mo_xcall_args_t *args, uint64_t len);
+int xcall_pack_keys(mo_xcall_args_t *args, uint64_t len);
+int xcall_group_ids(mo_xcall_args_t *args, uint64_t len);
+int xcall_group_agg(int op, int T, mo_xcall_args_t *args, uint64_t len);
 int xcall_bruteforce(mo_xcall_args_t *args, uint64_t len);
 int xcall_ivf(mo_xcall_args_t *args, uint64_t len);
 int xcall_topk_merge(mo_xcall_args_t *args, uint64_t len);
@@ -44,6 +49,11 @@ extern "C" int32_t XCall(int64_t runtimeId, int64_t funcId, uint8_t *errStr, uin
     if ((funcId >= 0 && funcId <= 3) || (funcId >= 100 && funcId <= 109)) rc = xcall_rowdist(funcId, a, len);
     else if (funcId >= 0x1000 && funcId < 0x1000 + (5 << 8)) rc = xcall_agg((int)((funcId - 0x1000) >> 8), (int)((funcId - 0x1000) & 0xff), a, len);
     else if (funcId >= 0x1800 && funcId < 0x1800 + (5 << 8)) rc = xcall_agg_merge((int)((funcId - 0x1800) >> 8), (int)((funcId - 0x1800) & 0xff), a, len);
+    else if (funcId == MO_XCALL_FILTER_SELS) rc = xcall_filter_sels(a, len);
+    else if (funcId == MO_XCALL_PACK_KEYS) rc = xcall_pack_keys(a, len);
+    else if (funcId == MO_XCALL_GROUP_IDS) rc = xcall_group_ids(a, len);
+    else if (funcId > 0x6100 && funcId <= 0x6100 + 24) rc = xcall_shuffle((int)(funcId - 0x6100), a, len);
+    else if (funcId >= 0x6400 && funcId < 0x6400 + (5 << 8)) rc = xcall_group_agg((int)((funcId - 0x6400) >> 8), (int)((funcId - 0x6400) & 0xff), a, len);
     else if (funcId == MO_XCALL_Q6_MERGE) rc = xcall_q6_merge(a, len);
     else if (funcId == MO_XCALL_Q1_MERGE) rc = xcall_q1_merge(a, len);
     else if (funcId >= 0x4000 && funcId < 0x5800) rc = xcall_go_elementwise(funcId, a, len);

@@ -336,6 +336,40 @@ class IvfflatSearchIndex:
         cidx.destroy()
         return cls(data_dev, assign, centroids, metric, lib)
 
+    @classmethod
+    def build_list_shard(cls, gen_rows, n_total, centroids, rank, world, metric=capi.METRIC_L2, lib=None, chunk=500_000):
+        """index build for ONE shard of a list-sharded index (BASELINE config 5: "lists sharded 8 x B200"): every row of the table is assigned to
+        its nearest centroid (Productl2, product_l2.go:317-407) and this shard keeps the WHOLE lists l with l % world == rank; the centroid table is
+        replicated, the other lists are empty here.  gen_rows(row0, m, device_ptr) materialises table rows [row0, row0 + m) in device memory.
+        Row ids are the table's row numbers (primary keys)."""
+        lib = lib or capi.load_library()
+        centroids = np.ascontiguousarray(centroids, dtype=np.float32)
+        dim = centroids.shape[1]
+        cidx = BruteForceIndex(centroids, dim, metric, lib=lib)
+        cap = n_total if world == 1 else int(n_total / world * 1.1) + chunk
+        tmp = DeviceBuffer(4 * cap * dim, lib)
+        scratch = DeviceBuffer(4 * min(chunk, n_total) * dim, lib)
+        ids, lists, filled = [], [], 0
+        for r0 in range(0, n_total, chunk):
+            m = min(chunk, n_total - r0)
+            gen_rows(r0, m, scratch.ptr)
+            keys, _ = cidx.search(scratch.view(4 * m * dim), 1)
+            mine = np.flatnonzero(keys % world == rank).astype(np.int64)
+            if filled + mine.shape[0] > cap:
+                raise capi.MoError(capi.RC_INTERNAL_ERROR, "list shard larger than expected")
+            if mine.shape[0]:
+                didx = DeviceBuffer.from_numpy(mine, lib)
+                capi.check(lib.MoB200_GatherRowsF32(tmp.ptr + 4 * filled * dim, scratch.ptr, didx.ptr, mine.shape[0], dim), lib)
+                didx.free()
+            ids.append(mine + r0); lists.append(keys[mine].astype(np.int32)); filled += mine.shape[0]
+        cidx.destroy(); scratch.free()
+        gids = np.concatenate(ids) if ids else np.zeros(0, dtype=np.int64)
+        ix = cls(tmp.view(4 * filled * dim), np.concatenate(lists) if lists else np.zeros(0, dtype=np.int32), centroids, metric, lib)
+        tmp.free()
+        ix.row_ids = gids[ix.row_ids]                  # list-ordered position -> table row number
+        ix.d_ids.free(); ix.d_ids = DeviceBuffer.from_numpy(ix.row_ids, lib)
+        return ix
+
     def search(self, queries, limit, nprobe, sqrt_out=False, out=None):
         if isinstance(queries, DeviceBuffer):
             nq = queries.nbytes // (4 * self.dim)
@@ -388,3 +422,94 @@ def topk_merge(keys_shards, dists_shards, nq, k):
     xcall(capi.XCALL_TOPK_MERGE, [Vector(data=keys, length=nq), Vector(data=dists, length=nq), Vector(data=ks, length=nq),
                                   Vector(data=ds, length=nq), _params_vec(p)], nq)
     return keys, dists
+
+
+# ------------------------------------------------------------------------------------------------ column operators (csrc/colops.cu)
+def _with_nulls(x, nulls, length):
+    v = _vec(x, length)
+    if nulls is not None:
+        if isinstance(nulls, DeviceBuffer):
+            v.nulls_ptr = nulls.ptr
+        else:
+            v.nulls = np.ascontiguousarray(nulls, dtype=np.uint64)
+    v.length = length
+    return v
+
+
+def filter_sels(bools, nulls=None, length=None):
+    """Filter.Call inner loop (filter.go:116-152): ascending row numbers with (!null && true).  Host arrays in, numpy sels out."""
+    b = np.ascontiguousarray(bools, dtype=np.uint8)
+    n = length if length is not None else b.shape[0]
+    sels = np.zeros(max(n, 1), dtype=np.int64)
+    cnt = np.zeros(1, dtype=np.int64)
+    xcall(capi.XCALL_FILTER_SELS, [Vector(data=sels, length=n), Vector(data=cnt, length=1), _with_nulls(b, nulls, n)], n)
+    return sels[:int(cnt[0])]
+
+
+def filter_sels_device(bools_dev, nulls_dev, n, sels_ptr, count_ptr):
+    """asynchronous form on resident vectors: sels (int64[n] capacity) and the count stay on the device"""
+    bv = Vector(data_ptr=bools_dev.ptr, data_nbytes=n, nulls_ptr=nulls_dev.ptr if nulls_dev is not None else None, length=n)
+    xcall(capi.XCALL_FILTER_SELS, [Vector(data_ptr=sels_ptr, data_nbytes=8 * n, length=n), Vector(data_ptr=count_ptr, data_nbytes=8, length=1), bv], n)
+
+
+def shuffle(src, sels, src_nulls=None, want_nulls=False):
+    """Vector.Shrink / Union (shuffle.FixedLengthShuffle + nulls.Filter): returns dst (and dst nulls words when want_nulls)"""
+    a = np.ascontiguousarray(src)
+    s = np.ascontiguousarray(sels, dtype=np.int64)
+    m = s.shape[0]
+    dst = np.zeros(m, dtype=a.dtype)
+    dn = np.zeros((m + 63) // 64, dtype=np.uint64) if want_nulls else None
+    sv = Vector(data=a.view(np.uint8).reshape(-1), nulls=src_nulls, length=a.shape[0])
+    xcall(capi.XCALL_SHUFFLE(a.dtype.itemsize), [Vector(data=dst.view(np.uint8).reshape(-1), nulls=dn, length=m), sv, Vector(data=s, length=m)], m)
+    return (dst, dn) if want_nulls else dst
+
+
+def pack_keys(cols, nulls=None, has_null=True, length=None):
+    """fillKeys (inthashmap.go:92-183): <= 8 key bytes per row.  cols: list of fixed-width numpy columns (a 1-element array = const vector).
+    Returns (keys uint64[n], skip bitmap words or None)"""
+    n = length if length is not None else max(len(c) for c in cols)
+    keys = np.zeros(n, dtype=np.uint64)
+    skip = None if has_null else np.zeros((n + 63) // 64, dtype=np.uint64)
+    prm = np.asarray([len(cols), 1 if has_null else 0], dtype=np.int32)
+    vecs = [Vector(data=keys, nulls=skip, length=n), Vector(data=prm.view(np.uint8), length=1, const=True)]
+    for i, c in enumerate(cols):
+        c = np.ascontiguousarray(c)
+        vecs.append(Vector(data=c.view(np.uint8).reshape(-1), nulls=None if nulls is None else nulls[i], length=n))
+    xcall(capi.XCALL_PACK_KEYS, vecs, n)
+    return keys, skip
+
+
+class GroupTable:
+    """IntHashMap as the group operator sees it: insert(keys) -> 1-based group ids in first-seen order; the table persists across batches"""
+
+    def __init__(self, capacity):
+        self.keys = np.zeros(capacity, dtype=np.uint64)
+        self.ngroups = np.zeros(1, dtype=np.int64)
+
+    def insert(self, keys, skip=None):
+        k = np.ascontiguousarray(keys, dtype=np.uint64)
+        n = k.shape[0]
+        groups = np.zeros(n, dtype=np.uint64)
+        xcall(capi.XCALL_GROUP_IDS, [Vector(data=groups, length=n), Vector(data=self.ngroups, length=1), Vector(data=self.keys, length=self.keys.shape[0]),
+                                     Vector(data=k, nulls=skip, length=n)], n)
+        return groups
+
+    def insert_device(self, keys_dev, n, groups_dev, d_ngroups, d_table_keys, capacity):
+        """all vectors resident (DeviceBuffer); the group count is read back by the call (it sizes the next operator's state)"""
+        xcall(capi.XCALL_GROUP_IDS, [Vector(data_ptr=groups_dev.ptr, data_nbytes=8 * n, length=n), Vector(data_ptr=d_ngroups.ptr, data_nbytes=8, length=1),
+                                     Vector(data_ptr=d_table_keys.ptr, data_nbytes=8 * capacity, length=capacity),
+                                     Vector(data_ptr=keys_dev.ptr, data_nbytes=8 * n, length=n)], n)
+
+
+def group_agg(op, T, state, state_nulls, counts, groups, col, col_nulls=None, length=None):
+    """BatchFill of one aggregate into caller-owned state arrays (numpy, modified in place): state uint64/int64/float64[ngroups] (8-byte slots),
+    state_nulls bitmap words (group is NULL), counts int64[ngroups] or None.  Returns rc (0 or RC_OUT_OF_RANGE)."""
+    g = np.ascontiguousarray(groups, dtype=np.uint64)
+    n = length if length is not None else g.shape[0]
+    sv = Vector(data=state.view(np.uint8).reshape(-1), nulls=state_nulls, length=state.shape[0])
+    cv = Vector(data=counts, length=state.shape[0]) if counts is not None else Vector(length=0)
+    colv = _with_nulls(np.ascontiguousarray(col).view(np.uint8).reshape(-1), col_nulls, n) if col is not None else _with_nulls(np.zeros(0, dtype=np.uint8), col_nulls, n)
+    rc, msg = xcall(capi.XCALL_GROUP_AGG(op, T), [sv, cv, Vector(data=g, length=n), colv], n, raise_on_error=False)
+    if rc not in (0, capi.RC_OUT_OF_RANGE):
+        raise capi.MoError(rc, msg)
+    return rc

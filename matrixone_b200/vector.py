@@ -113,10 +113,16 @@ class DeviceBuffer:
             capi.check(self.lib.MoB200_Download(out.ctypes.data, self.ptr, out.nbytes), self.lib)
         return out
 
+    def view(self, nbytes, offset=0):
+        """non-owning window [offset, offset + nbytes) of this buffer (a prefix / block range of a resident column)"""
+        v = DeviceBuffer.__new__(DeviceBuffer)
+        v.lib, v.nbytes, v.ptr, v.owner = self.lib, int(nbytes), self.ptr + int(offset), self
+        return v
+
     def free(self):
-        if self.ptr:
+        if self.ptr and getattr(self, "owner", None) is None:
             self.lib.MoB200_DeviceFree(self.ptr)
-            self.ptr = None
+        self.ptr = None
 
     def __del__(self):
         try:
