@@ -230,6 +230,66 @@ typedef struct { int32_t div0_null; int32_t reserved; int64_t err_row; } mo_go_p
 #define MO_XCALL_SHUFFLE(szof) (0x6100 + (szof))
 #define MO_XCALL_GROUP_AGG(op, T) (0x6400 + ((op) << 8) + (T))
 
+/* ---- Decimal64 / Decimal128 (csrc/decimal.cu): the reference's native TPC-H column type is DECIMAL(15,2).  Decimal64 = int64 unscaled value,
+ * Decimal128 = 16 bytes two's complement {B0_63, B64_127}; scales travel in the parameter block.  Conventions of the Go engine (as GO_ARITH).
+ *   DEC_ARITH(op, width)  op 0 + 1 - 2 * ; width 64 / 128 = operand type.  d64Add/d64Sub/d64Mul/d128Add/d128Sub/d128Mul,
+ *                         pkg/sql/plan/function/arith_decimal_fast.go:111-733,3618-4095.  + - : the lower-scale operand is scaled up, result
+ *                         scale = max(scale1, scale2), result type = operand type; * : result Decimal128 with scale
+ *                         min(scale1 + scale2, max(12, scale1, scale2)), scaled down with round-half-up when that is smaller than scale1 + scale2.
+ *                         The first row that overflows fails the call with MO_RC_INVALID_ARGUMENT (moerr ErrInvalidInput) and err_row is set.
+ *                         args: [0] result (+pnulls in/out) ; [1] a ; [2] b (const = one element) ; [3] host mo_dec_params_t
+ *   DEC_SUM(width)        SUM / AVG accumulation of a decimal column into Decimal128 sums + int64 counts per group (count 0 = NULL; AVG divides at
+ *                         Flush), sumDecimal64FastExec / sumDecimal128FastExec.batchFill, pkg/sql/colexec/aggexec/sum_decimal_fast.go -- exact and
+ *                         order independent.  args: [0] sums Decimal128 per group (in/out) ; [1] counts int64 per group (in/out) ;
+ *                         [2] groups uint64[len] (1-based, 0 = skip) or pdata NULL for one group ; [3] the column (+pnulls) */
+typedef struct mo_dec_params_t { int32_t scale1, scale2; int64_t err_row; } mo_dec_params_t;
+#define MO_XCALL_DEC_ARITH(op, width) (0x7000 + ((op) << 8) + (width))
+#define MO_XCALL_DEC_SUM(width) (0x7400 + (width))
+
+/* ---- the generic fused operator: scan -> filter -> project -> (hash) group -> aggregate in ONE pass over the columns (csrc/plan.cu).
+ * What the colexec pipeline runs per block as table_scan -> filter -> projection -> group (filter.go:87-153, evalExpression.go:575-640,
+ * group/exec2.go:296-367, aggexec/*), described by a host-side mo_plan_t:
+ *   columns      args[2 .. 2+ncols): fixed-width columns of col_type[c] (MO_T_*), each with an optional nulls bitmap
+ *   predicates   conjunction of  col OP lo  (OP: 0 == 1 != 2 > 3 >= 4 < 5 <=)  or  col BETWEEN lo AND hi (op 6); a NULL operand rejects the row
+ *   instructions SSA program: value slot ncols + i = COL(a) | CONST(imm) | slot a (+ - * /) slot b; slots 0..ncols-1 are the columns.  float64
+ *                arithmetic, one rounding per instruction (the reference evaluates one node at a time); integer columns are converted (exact
+ *                below 2^53); NULL in -> NULL out; x / 0 -> NULL
+ *   keys         nkeys columns packed into <= 8 bytes exactly like fillKeys (inthashmap.go:92-183; has_null_keys: marker byte per column)
+ *   aggregates   kind MO_AGG_SUM / COUNT / MIN / MAX / AVG over value slot `value`; value = -1 with MO_AGG_COUNT is COUNT(*)
+ * Result: mo_plan_result_header_t followed by ngroups records {mo_plan_group_t, naggs x mo_plan_agg_value_t}, groups in first-seen row order
+ * (the reference's group-id order) when header.sorted (up to 8192 groups; beyond that in table order, first_row is there to sort by).  An
+ * aggregate with count 0 is NULL.  No group-by (nkeys = 0): one group, present only if a row qualified.  header.overflow = more groups than the
+ * result buffer holds (synchronous form: MO_RC_INVALID_ARGUMENT).  Device columns AND a device result: asynchronous form (as MO_XCALL_AGG).
+ * float64 sums are accumulated with atomics: the association order is not fixed (agreement with the serial loop ~1e-13 relative); MIN / MAX
+ * ignore NaN.  The TPC-H Q6 / Q1 shapes below are hand-specialised instances of this operator that reach the HBM roofline. */
+#define MO_XCALL_PLAN 0x2100
+#define MO_PLAN_MAX_COLS 12
+#define MO_PLAN_MAX_PREDS 8
+#define MO_PLAN_MAX_INSTR 16
+#define MO_PLAN_MAX_KEYS 4
+#define MO_PLAN_MAX_AGGS 12
+#define MO_PLAN_OP_COL 0
+#define MO_PLAN_OP_CONST 1
+#define MO_PLAN_OP_ADD 2
+#define MO_PLAN_OP_SUB 3
+#define MO_PLAN_OP_MUL 4
+#define MO_PLAN_OP_DIV 5
+typedef struct mo_plan_pred_t { int32_t col; int32_t op; double lo; double hi; } mo_plan_pred_t;
+typedef struct mo_plan_instr_t { int32_t op; int32_t a; int32_t b; int32_t reserved; double imm; } mo_plan_instr_t;
+typedef struct mo_plan_agg_t { int32_t kind; int32_t value; } mo_plan_agg_t;
+typedef struct mo_plan_t {
+    int32_t ncols, npreds, ninstr, nkeys, naggs, has_null_keys;
+    int64_t row_base;                       /* added to first_row (block-range offset of a shard) */
+    int32_t col_type[MO_PLAN_MAX_COLS];
+    mo_plan_pred_t pred[MO_PLAN_MAX_PREDS];
+    mo_plan_instr_t instr[MO_PLAN_MAX_INSTR];
+    int32_t key_col[MO_PLAN_MAX_KEYS];
+    mo_plan_agg_t agg[MO_PLAN_MAX_AGGS];
+} mo_plan_t;
+typedef struct mo_plan_result_header_t { int64_t ngroups; int32_t sorted; int32_t overflow; int64_t reserved; } mo_plan_result_header_t;
+typedef struct mo_plan_group_t { uint64_t key; int64_t first_row; int64_t rows; } mo_plan_group_t;
+typedef struct mo_plan_agg_value_t { double value; int64_t count; } mo_plan_agg_value_t;
+
 #define MO_XCALL_Q6_FILTER_SUM 0x2000
 typedef struct mo_q6_params_t {
     int32_t date_lo, date_hi;  /* date_lo <= d < date_hi */

@@ -194,3 +194,44 @@ def check(rc, lib=None):
     if rc != 0:
         raise MoError(rc, last_error(lib))
     return rc
+
+
+# ---- the generic fused operator (include/mo_b200.h MO_XCALL_PLAN)
+XCALL_PLAN = 0x2100
+PLAN_MAX_COLS, PLAN_MAX_PREDS, PLAN_MAX_INSTR, PLAN_MAX_KEYS, PLAN_MAX_AGGS = 12, 8, 16, 4, 12
+PLAN_OP_COL, PLAN_OP_CONST, PLAN_OP_ADD, PLAN_OP_SUB, PLAN_OP_MUL, PLAN_OP_DIV = 0, 1, 2, 3, 4, 5
+PLAN_CMP = {"==": 0, "!=": 1, ">": 2, ">=": 3, "<": 4, "<=": 5, "between": 6}
+
+
+class PlanPred(C.Structure):
+    _fields_ = [("col", C.c_int32), ("op", C.c_int32), ("lo", C.c_double), ("hi", C.c_double)]
+
+
+class PlanInstr(C.Structure):
+    _fields_ = [("op", C.c_int32), ("a", C.c_int32), ("b", C.c_int32), ("reserved", C.c_int32), ("imm", C.c_double)]
+
+
+class PlanAgg(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("value", C.c_int32)]
+
+
+class Plan(C.Structure):
+    _fields_ = [("ncols", C.c_int32), ("npreds", C.c_int32), ("ninstr", C.c_int32), ("nkeys", C.c_int32), ("naggs", C.c_int32), ("has_null_keys", C.c_int32),
+                ("row_base", C.c_int64), ("col_type", C.c_int32 * PLAN_MAX_COLS), ("pred", PlanPred * PLAN_MAX_PREDS), ("instr", PlanInstr * PLAN_MAX_INSTR),
+                ("key_col", C.c_int32 * PLAN_MAX_KEYS), ("agg", PlanAgg * PLAN_MAX_AGGS)]
+
+
+class PlanHeader(C.Structure):
+    _fields_ = [("ngroups", C.c_int64), ("sorted", C.c_int32), ("overflow", C.c_int32), ("reserved", C.c_int64)]
+
+
+def XCALL_DEC_ARITH(op, width):
+    return 0x7000 + (op << 8) + width
+
+
+def XCALL_DEC_SUM(width):
+    return 0x7400 + width
+
+
+class DecParams(C.Structure):
+    _fields_ = [("scale1", C.c_int32), ("scale2", C.c_int32), ("err_row", C.c_int64)]

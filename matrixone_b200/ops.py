@@ -513,3 +513,154 @@ def group_agg(op, T, state, state_nulls, counts, groups, col, col_nulls=None, le
     if rc not in (0, capi.RC_OUT_OF_RANGE):
         raise capi.MoError(rc, msg)
     return rc
+
+
+# ------------------------------------------------------------------------------------------------ the generic fused operator (csrc/plan.cu)
+class FusedPlan:
+    """Builder for mo_plan_t: table_scan -> filter -> projection -> group in one kernel.
+
+        p = FusedPlan([capi.T_DATE, capi.T_FLOAT64, capi.T_FLOAT64, capi.T_FLOAT64])          # column types
+        p.where(0, ">=", lo).where(0, "<", hi).where(1, "between", a, b).where(2, "<", 24.0)
+        revenue = p.mul(p.col(3), p.col(1))                                                 # value slots
+        p.agg(capi.AGG_SUM, revenue)
+        groups = p.run([shipdate, discount, quantity, price], n)
+    """
+
+    def __init__(self, col_types, has_null_keys=False, row_base=0):
+        self.P = capi.Plan()
+        self.P.ncols = len(col_types)
+        for i, t in enumerate(col_types):
+            self.P.col_type[i] = t
+        self.P.has_null_keys = 1 if has_null_keys else 0
+        self.P.row_base = row_base
+
+    def where(self, col, op, lo, hi=0.0):
+        q = self.P.pred[self.P.npreds]
+        q.col, q.op, q.lo, q.hi = col, capi.PLAN_CMP[op], float(lo), float(hi)
+        self.P.npreds += 1
+        return self
+
+    def _emit(self, op, a=0, b=0, imm=0.0):
+        i = self.P.ninstr
+        ins = self.P.instr[i]
+        ins.op, ins.a, ins.b, ins.imm = op, a, b, float(imm)
+        self.P.ninstr += 1
+        return self.P.ncols + i
+
+    def col(self, c):
+        return c                      # a column IS value slot c
+
+    def const(self, x):
+        return self._emit(capi.PLAN_OP_CONST, imm=x)
+
+    def add(self, a, b):
+        return self._emit(capi.PLAN_OP_ADD, a, b)
+
+    def sub(self, a, b):
+        return self._emit(capi.PLAN_OP_SUB, a, b)
+
+    def mul(self, a, b):
+        return self._emit(capi.PLAN_OP_MUL, a, b)
+
+    def div(self, a, b):
+        return self._emit(capi.PLAN_OP_DIV, a, b)
+
+    def group_by(self, *cols):
+        for c in cols:
+            self.P.key_col[self.P.nkeys] = c
+            self.P.nkeys += 1
+        return self
+
+    def agg(self, kind, value=-1):
+        a = self.P.agg[self.P.naggs]
+        a.kind, a.value = kind, value
+        self.P.naggs += 1
+        return self
+
+    def result_bytes(self, max_groups):
+        return C.sizeof(capi.PlanHeader) + max_groups * (24 + 16 * self.P.naggs)
+
+    def run(self, cols, n, nulls=None, max_groups=64, out_ptr=None):
+        """cols: numpy arrays or DeviceBuffers (one per declared column); nulls: optional list of bitmap words (numpy / DeviceBuffer / None).
+        out_ptr: device result buffer of result_bytes(max_groups) -> asynchronous form, returns None.  Else a list of group dicts
+        {key, first_row, rows, aggs: [(value, count), ...]} in first-seen order."""
+        vecs = []
+        for i, c in enumerate(cols):
+            nb = None if nulls is None else nulls[i]
+            vecs.append(_with_nulls(c if isinstance(c, DeviceBuffer) else np.ascontiguousarray(c).view(np.uint8).reshape(-1), nb, n))
+        nbytes = self.result_bytes(max_groups)
+        if out_ptr is not None:
+            xcall(capi.XCALL_PLAN, [Vector(data_ptr=out_ptr, data_nbytes=nbytes, length=1), _params_vec(self.P)] + vecs, n)
+            return None
+        res = np.zeros(nbytes, dtype=np.uint8)
+        xcall(capi.XCALL_PLAN, [Vector(data=res, length=1), _params_vec(self.P)] + vecs, n)
+        return self.parse(res.tobytes())
+
+    def parse(self, raw):
+        h = capi.PlanHeader.from_buffer_copy(raw[:C.sizeof(capi.PlanHeader)])
+        if h.overflow:
+            raise capi.MoError(capi.RC_INVALID_ARGUMENT, "plan: more groups than the result buffer holds")
+        rec = 24 + 16 * self.P.naggs
+        out = []
+        for g in range(h.ngroups):
+            b = raw[C.sizeof(capi.PlanHeader) + g * rec: C.sizeof(capi.PlanHeader) + (g + 1) * rec]
+            key, first_row, rows = np.frombuffer(b[:8], dtype=np.uint64)[0], np.frombuffer(b[8:16], dtype=np.int64)[0], np.frombuffer(b[16:24], dtype=np.int64)[0]
+            aggs = []
+            for a in range(self.P.naggs):
+                v = np.frombuffer(b[24 + 16 * a: 32 + 16 * a], dtype=np.float64)[0]
+                c = np.frombuffer(b[32 + 16 * a: 40 + 16 * a], dtype=np.int64)[0]
+                aggs.append((float(v), int(c)))
+            out.append({"key": int(key), "first_row": int(first_row), "rows": int(rows), "aggs": aggs})
+        if not h.sorted:
+            out.sort(key=lambda g: g["first_row"])
+        return out
+
+
+def q6_plan():
+    """TPC-H Q6 (q6.sql) as a FusedPlan over columns [shipdate DATE, discount f64, quantity f64, extendedprice f64]"""
+    from . import datagen
+    lo, hi, dlo, dhi, qhi = datagen.q6_params()
+    p = FusedPlan([capi.T_DATE, capi.T_FLOAT64, capi.T_FLOAT64, capi.T_FLOAT64])
+    p.where(0, ">=", lo).where(0, "<", hi).where(1, "between", dlo, dhi).where(2, "<", qhi)
+    p.agg(capi.AGG_SUM, p.mul(p.col(3), p.col(1)))
+    return p
+
+
+def q1_plan(cutoff, row_base=0):
+    """TPC-H Q1 (q1.sql) as a FusedPlan over columns [shipdate, quantity, extendedprice, discount, tax, returnflag u8, linestatus u8]"""
+    p = FusedPlan([capi.T_DATE, capi.T_FLOAT64, capi.T_FLOAT64, capi.T_FLOAT64, capi.T_FLOAT64, capi.T_UINT8, capi.T_UINT8], row_base=row_base)
+    p.where(0, "<=", cutoff)
+    one = p.const(1.0)
+    disc_price = p.mul(p.col(2), p.sub(one, p.col(3)))
+    charge = p.mul(disc_price, p.add(one, p.col(4)))
+    p.group_by(5, 6)
+    for kind, v in ((capi.AGG_SUM, 1), (capi.AGG_SUM, 2), (capi.AGG_SUM, disc_price), (capi.AGG_SUM, charge), (capi.AGG_AVG, 1), (capi.AGG_AVG, 2), (capi.AGG_AVG, 3)):
+        p.agg(kind, v)
+    p.agg(capi.AGG_COUNT, -1)
+    return p
+
+
+# ------------------------------------------------------------------------------------------------ decimals (csrc/decimal.cu)
+def dec_arith(op, width, a, b, scale1, scale2, n, n1=None, n2=None, rnulls=None):
+    """d64/d128 Add (op 0) / Sub (1) / Mul (2).  a, b: int64 arrays (width 64) or uint64[n, 2] {lo, hi} arrays (width 128); a 1-row operand is a
+    const vector.  Returns (rc, result, result nulls words, err_row); result is int64[n] (64-bit + -) or uint64[n, 2]."""
+    out128 = op == 2 or width == 128
+    r = np.zeros((n, 2), dtype=np.uint64) if out128 else np.zeros(n, dtype=np.int64)
+    rn = np.zeros((n + 63) // 64, dtype=np.uint64) if rnulls is None else np.ascontiguousarray(rnulls, dtype=np.uint64).copy()
+    prm = np.frombuffer(bytes(capi.DecParams(scale1, scale2, -1)), dtype=np.uint8).copy()
+    av = Vector(data=np.ascontiguousarray(a).view(np.uint8).reshape(-1), nulls=n1, length=n)
+    bv = Vector(data=np.ascontiguousarray(b).view(np.uint8).reshape(-1), nulls=n2, length=n)
+    rc, msg = xcall(capi.XCALL_DEC_ARITH(op, width), [Vector(data=r.view(np.uint8).reshape(-1), nulls=rn, length=n), av, bv, Vector(data=prm, length=1, const=True)], n,
+                    raise_on_error=False)
+    if rc not in (0, capi.RC_INVALID_ARGUMENT):
+        raise capi.MoError(rc, msg)
+    return rc, r, rn, int(prm.view(np.int64)[1])
+
+
+def dec_sum(width, col, sums, counts, groups=None, nulls=None, n=None):
+    """SUM/AVG accumulation into sums uint64[ngroups, 2] (Decimal128) and counts int64[ngroups], in place"""
+    c = np.ascontiguousarray(col)
+    n = n if n is not None else (c.shape[0])
+    gv = Vector(data=np.ascontiguousarray(groups, dtype=np.uint64), length=n) if groups is not None else Vector(length=0)
+    xcall(capi.XCALL_DEC_SUM(width), [Vector(data=sums.view(np.uint8).reshape(-1), length=sums.shape[0]), Vector(data=counts, length=counts.shape[0]), gv,
+                                      _with_nulls(c.view(np.uint8).reshape(-1), nulls, n)], n)

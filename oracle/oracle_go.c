@@ -1127,6 +1127,163 @@ int32_t og_sum_int64_mt(const int64_t *col, const uint64_t *nulls, int64_t n, in
 }
 
 
+
+/* ---------------------------------------------------------------------------------------------
+ * Decimal64 / Decimal128 batch arithmetic and decimal SUM (the reference's native TPC-H types are
+ * DECIMAL(15,2)).  Decimal64 = int64 unscaled value, Decimal128 = two's-complement 128-bit {B0_63, B64_127}; the scale lives in the type.
+ *   og_d64_addsub   d64Add / d64Sub, pkg/sql/plan/function/arith_decimal_fast.go:3618-3900: the lower-scale operand is scaled up by
+ *                   10^diff (d64ScaleIntoRs / d64MulPow10 :4807-4890, error "scale overflow" when |x|*10^diff >= 2^63), then a plain int64
+ *                   add/sub whose sign-rule overflow fails the call at the FIRST offending row; result scale = max(scale1, scale2)
+ *   og_d64_mul      d64Mul :3901-4095: exact 128-bit product, result scale = min(s1+s2, max(12, s1, s2)); when that is smaller than s1+s2
+ *                   the magnitude is divided by 10^k with round-half-up (d128DivPow10Once :4913-4923)
+ *   og_d128_addsub  d128Add / d128Sub :111-430 (same rules on 128 bits)
+ *   og_d128_mul     d128Mul / d128MulInline :545-733: 256-bit product of the magnitudes, same scale rule, "Decimal128 Mul overflow" when the
+ *                   result does not fit 127 bits
+ *   og_sum_d64 / og_sum_d128   sumDecimal64FastExec / sumDecimal128FastExec.batchFill, pkg/sql/colexec/aggexec/sum_decimal_fast.go: 128-bit
+ *                   wrapping accumulation per group + a row count (count == 0 -> NULL); AVG divides at Flush
+ * rc: 0, or OG_RC_INVALID_INPUT with *err_row = first offending row.
+ * ------------------------------------------------------------------------------------------- */
+#define OG_RC_INVALID_INPUT 20203
+typedef struct { uint64_t lo, hi; } og_d128;
+static const uint64_t OG_POW10[20] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull, 100000000ull, 1000000000ull,
+    10000000000ull, 100000000000ull, 1000000000000ull, 10000000000000ull, 100000000000000ull, 1000000000000000ull, 10000000000000000ull,
+    100000000000000000ull, 1000000000000000000ull, 10000000000000000000ull};
+static inline __int128 d128_get(og_d128 v) { return (__int128)(((unsigned __int128)v.hi << 64) | v.lo); }
+static inline og_d128 d128_put(__int128 x) { og_d128 r = {(uint64_t)(unsigned __int128)x, (uint64_t)((unsigned __int128)x >> 64)}; return r; }
+
+static int d64_scale_up(int64_t x, int diff, int64_t *out) {   /* d64MulPow10: ok iff |x| * 10^diff < 2^63 */
+    uint64_t sign = (uint64_t)x >> 63, mask = 0 - sign, ab = ((uint64_t)x ^ mask) + sign;
+    unsigned __int128 p = (unsigned __int128)ab * OG_POW10[diff];
+    if ((uint64_t)(p >> 64) | ((uint64_t)p >> 63)) return 0;
+    *out = (int64_t)((((uint64_t)p) ^ mask) + sign);
+    return 1;
+}
+int32_t og_d64_addsub(int32_t is_sub, int64_t *r, const int64_t *a, const int64_t *b, uint64_t n, int32_t c1, int32_t c2, int32_t scale1, int32_t scale2,
+                      const uint64_t *n1, const uint64_t *n2, uint64_t *rnulls, int64_t *err_row) {
+    if ((c1 && bm_has(n1, 0)) || (c2 && bm_has(n2, 0))) { for (uint64_t i = 0; i < n; i++) bm_add(rnulls, i); return OG_RC_OK; }
+    for (uint64_t w = 0; w < bm_words(n); w++) { if (!c1 && n1) rnulls[w] |= n1[w]; if (!c2 && n2) rnulls[w] |= n2[w]; }
+    if (n & 63) rnulls[bm_words(n) - 1] &= (((uint64_t)1 << (n & 63)) - 1);
+    const int d1 = scale2 > scale1 ? scale2 - scale1 : 0, d2 = scale1 > scale2 ? scale1 - scale2 : 0;
+    if (d1 > 18 || d2 > 18) return OG_RC_INVALID;
+    for (uint64_t i = 0; i < n; i++) {
+        if (bm_has(rnulls, i)) continue;
+        int64_t x = a[c1 ? 0 : i], y = b[c2 ? 0 : i];
+        if ((d1 && !d64_scale_up(x, d1, &x)) || (d2 && !d64_scale_up(y, d2, &y))) { if (err_row) *err_row = (int64_t)i; return OG_RC_INVALID_INPUT; }
+        int64_t z = (int64_t)(is_sub ? (uint64_t)x - (uint64_t)y : (uint64_t)x + (uint64_t)y);
+        uint64_t sx = (uint64_t)x >> 63, sy = (uint64_t)y >> 63, sz = (uint64_t)z >> 63;
+        int ov = is_sub ? (sx != sy && sx != sz) : (sx == sy && sx != sz);
+        r[i] = z;
+        if (ov) { if (err_row) *err_row = (int64_t)i; return OG_RC_INVALID_INPUT; }
+    }
+    return OG_RC_OK;
+}
+
+static int mul_scale_adj(int s1, int s2) { int d = 12; if (s1 > d) d = s1; if (s2 > d) d = s2; if (s1 + s2 < d) d = s1 + s2; return d - s1 - s2; }
+int32_t og_mul_result_scale(int32_t s1, int32_t s2) { return s1 + s2 + mul_scale_adj(s1, s2); }
+
+/* magnitude / 10^k with the reference's round-half-up, one or two steps (d128DivPow10 :518-526) on a 256-bit magnitude held as 4 limbs */
+static void mag_div_pow10_once(uint64_t m[4], uint64_t d) {
+    unsigned __int128 rem = 0;
+    for (int k = 3; k >= 0; k--) { unsigned __int128 cur = (rem << 64) | m[k]; m[k] = (uint64_t)(cur / d); rem = cur % d; }
+    if ((uint64_t)rem >= (d + 1) >> 1) { for (int k = 0; k < 4; k++) { if (++m[k] != 0) break; } }
+}
+static void mag_div_pow10(uint64_t m[4], int k) {
+    if (k <= 0) return;
+    if (k <= 19) { mag_div_pow10_once(m, OG_POW10[k]); return; }
+    mag_div_pow10_once(m, OG_POW10[19]); mag_div_pow10_once(m, OG_POW10[k - 19]);
+}
+int32_t og_d64_mul(og_d128 *r, const int64_t *a, const int64_t *b, uint64_t n, int32_t c1, int32_t c2, int32_t scale1, int32_t scale2,
+                   const uint64_t *n1, const uint64_t *n2, uint64_t *rnulls) {
+    if ((c1 && bm_has(n1, 0)) || (c2 && bm_has(n2, 0))) { for (uint64_t i = 0; i < n; i++) bm_add(rnulls, i); return OG_RC_OK; }
+    for (uint64_t w = 0; w < bm_words(n); w++) { if (!c1 && n1) rnulls[w] |= n1[w]; if (!c2 && n2) rnulls[w] |= n2[w]; }
+    if (n & 63) rnulls[bm_words(n) - 1] &= (((uint64_t)1 << (n & 63)) - 1);
+    const int adj = mul_scale_adj(scale1, scale2);
+    for (uint64_t i = 0; i < n; i++) {
+        if (bm_has(rnulls, i)) continue;
+        int64_t x = a[c1 ? 0 : i], y = b[c2 ? 0 : i];
+        uint64_t ax = x < 0 ? 0 - (uint64_t)x : (uint64_t)x, ay = y < 0 ? 0 - (uint64_t)y : (uint64_t)y;
+        unsigned __int128 p = (unsigned __int128)ax * ay;
+        uint64_t m[4] = {(uint64_t)p, (uint64_t)(p >> 64), 0, 0};
+        mag_div_pow10(m, -adj);
+        __int128 v = (__int128)(((unsigned __int128)m[1] << 64) | m[0]);
+        if ((x < 0) != (y < 0)) v = -v;
+        r[i] = d128_put(v);
+    }
+    return OG_RC_OK;
+}
+int32_t og_d128_addsub(int32_t is_sub, og_d128 *r, const og_d128 *a, const og_d128 *b, uint64_t n, int32_t c1, int32_t c2, int32_t scale1, int32_t scale2,
+                       const uint64_t *n1, const uint64_t *n2, uint64_t *rnulls, int64_t *err_row) {
+    if ((c1 && bm_has(n1, 0)) || (c2 && bm_has(n2, 0))) { for (uint64_t i = 0; i < n; i++) bm_add(rnulls, i); return OG_RC_OK; }
+    for (uint64_t w = 0; w < bm_words(n); w++) { if (!c1 && n1) rnulls[w] |= n1[w]; if (!c2 && n2) rnulls[w] |= n2[w]; }
+    if (n & 63) rnulls[bm_words(n) - 1] &= (((uint64_t)1 << (n & 63)) - 1);
+    const int d1 = scale2 > scale1 ? scale2 - scale1 : 0, d2 = scale1 > scale2 ? scale1 - scale2 : 0;
+    if (d1 > 19 || d2 > 19) return OG_RC_INVALID;
+    const __int128 MAXV = (__int128)(((unsigned __int128)1 << 127) - 1);
+    for (uint64_t i = 0; i < n; i++) {
+        if (bm_has(rnulls, i)) continue;
+        __int128 x = d128_get(a[c1 ? 0 : i]), y = d128_get(b[c2 ? 0 : i]);
+        for (int side = 0; side < 2; side++) {   /* d128ScaleUp: |v| * 10^d must stay below 2^127 (d128Mul1Limb :4890-4906) */
+            const int d = side ? d2 : d1; __int128 *v = side ? &y : &x;
+            if (!d) continue;
+            unsigned __int128 ab = *v < 0 ? (unsigned __int128)0 - (unsigned __int128)*v : (unsigned __int128)*v;
+            unsigned __int128 lim = (((unsigned __int128)1 << 127) - 1) / OG_POW10[d];
+            if (ab > lim) { if (err_row) *err_row = (int64_t)i; return OG_RC_INVALID_INPUT; }
+            ab *= OG_POW10[d];
+            *v = *v < 0 ? -(__int128)ab : (__int128)ab;
+        }
+        unsigned __int128 uz = is_sub ? (unsigned __int128)x - (unsigned __int128)y : (unsigned __int128)x + (unsigned __int128)y;
+        __int128 z = (__int128)uz;
+        int sx = x < 0, sy = y < 0, sz = z < 0;
+        int ov = is_sub ? (sx != sy && sx != sz) : (sx == sy && sx != sz);
+        r[i] = d128_put(z);
+        if (ov) { if (err_row) *err_row = (int64_t)i; return OG_RC_INVALID_INPUT; }
+        (void)MAXV;
+    }
+    return OG_RC_OK;
+}
+int32_t og_d128_mul(og_d128 *r, const og_d128 *a, const og_d128 *b, uint64_t n, int32_t c1, int32_t c2, int32_t scale1, int32_t scale2,
+                    const uint64_t *n1, const uint64_t *n2, uint64_t *rnulls, int64_t *err_row) {
+    if ((c1 && bm_has(n1, 0)) || (c2 && bm_has(n2, 0))) { for (uint64_t i = 0; i < n; i++) bm_add(rnulls, i); return OG_RC_OK; }
+    for (uint64_t w = 0; w < bm_words(n); w++) { if (!c1 && n1) rnulls[w] |= n1[w]; if (!c2 && n2) rnulls[w] |= n2[w]; }
+    if (n & 63) rnulls[bm_words(n) - 1] &= (((uint64_t)1 << (n & 63)) - 1);
+    const int adj = mul_scale_adj(scale1, scale2);
+    for (uint64_t i = 0; i < n; i++) {
+        if (bm_has(rnulls, i)) continue;
+        __int128 x = d128_get(a[c1 ? 0 : i]), y = d128_get(b[c2 ? 0 : i]);
+        unsigned __int128 ax = x < 0 ? (unsigned __int128)0 - (unsigned __int128)x : (unsigned __int128)x;
+        unsigned __int128 ay = y < 0 ? (unsigned __int128)0 - (unsigned __int128)y : (unsigned __int128)y;
+        uint64_t xl = (uint64_t)ax, xh = (uint64_t)(ax >> 64), yl = (uint64_t)ay, yh = (uint64_t)(ay >> 64);
+        uint64_t m[4] = {0, 0, 0, 0};
+        unsigned __int128 t = (unsigned __int128)xl * yl; m[0] = (uint64_t)t; unsigned __int128 carry = t >> 64;
+        t = (unsigned __int128)xl * yh + carry; unsigned __int128 t2 = (unsigned __int128)xh * yl + (uint64_t)t; m[1] = (uint64_t)t2;
+        carry = (t >> 64) + (t2 >> 64);
+        t = (unsigned __int128)xh * yh + carry; m[2] = (uint64_t)t; m[3] = (uint64_t)(t >> 64);
+        mag_div_pow10(m, -adj);
+        if (m[2] | m[3] | (m[1] >> 63)) { if (err_row) *err_row = (int64_t)i; return OG_RC_INVALID_INPUT; }
+        __int128 v = (__int128)(((unsigned __int128)m[1] << 64) | m[0]);
+        if ((x < 0) != (y < 0)) v = -v;
+        r[i] = d128_put(v);
+    }
+    return OG_RC_OK;
+}
+/* grouped SUM / AVG accumulation of a decimal column into 128-bit sums + counts (groups == NULL: one group) */
+void og_sum_d64(const int64_t *col, const uint64_t *nulls, uint64_t offset, const uint64_t *groups, uint64_t n, og_d128 *sums, int64_t *cnts) {
+    for (uint64_t i = 0; i < n; i++) {
+        uint64_t grp = groups ? groups[i] : 1; if (grp == 0) continue;
+        if (bm_has(nulls, i + offset)) continue;
+        sums[grp - 1] = d128_put((__int128)((unsigned __int128)d128_get(sums[grp - 1]) + (unsigned __int128)(__int128)col[i + offset]));
+        cnts[grp - 1] += 1;
+    }
+}
+void og_sum_d128(const og_d128 *col, const uint64_t *nulls, uint64_t offset, const uint64_t *groups, uint64_t n, og_d128 *sums, int64_t *cnts) {
+    for (uint64_t i = 0; i < n; i++) {
+        uint64_t grp = groups ? groups[i] : 1; if (grp == 0) continue;
+        if (bm_has(nulls, i + offset)) continue;
+        sums[grp - 1] = d128_put((__int128)((unsigned __int128)d128_get(sums[grp - 1]) + (unsigned __int128)d128_get(col[i + offset])));
+        cnts[grp - 1] += 1;
+    }
+}
+
 /* ---------------------------------------------------------------------------------------------
  * Synthetic column generators: the C twin of matrixone_b200/csrc/datagen.cu (and datagen.py), bit for bit, run on the
  * worker pool with the SAME block-range split the pipelines above use, so every worker first-touches the rows it will scan.

@@ -269,8 +269,60 @@ def function_kats():
             "cases": cases}
 
 
+def _dec_slice(expr):
+    """[]types.Decimal64{1, 2} -> ("decimal64", [ints]) ; []types.Decimal128{{B0_63: a, B64_127: b}, ...} -> ("decimal128", [signed 128-bit ints])"""
+    expr = re.sub(r"//[^\n]*", "", expr.strip())
+    m = re.fullmatch(r"\[\]types\.Decimal64\{(.*)\}", expr, re.S)
+    if m:
+        return "decimal64", [int(_go_value(x)) for x in _split_top(m.group(1)) if x.strip()]
+    m = re.fullmatch(r"\[\]types\.Decimal128\{(.*)\}", expr, re.S)
+    if m:
+        vals = []
+        for lo, hi in re.findall(r"\{\s*B0_63:\s*([^,]+),\s*B64_127:\s*([^}]+?)\s*,?\s*\}", m.group(1)):
+            u = ((int(_go_value(hi)) & 0xFFFFFFFFFFFFFFFF) << 64) | (int(_go_value(lo)) & 0xFFFFFFFFFFFFFFFF)
+            vals.append(u - (1 << 128) if u >> 127 else u)
+        return "decimal128", vals
+    raise ValueError(expr[:40])
+
+
+def decimal_kats():
+    """the Decimal64 / Decimal128 FunctionTestCase tables of arithmetic_{plus,minus,multi}_test.go (scale 0 columns: T_decimalNN.ToType())"""
+    base = os.path.join(REF, "pkg/sql/plan/function")
+    fns = {"plusFn": "add", "minusFn": "sub", "multiFn": "mul"}
+    cases = []
+    for fname in ("arithmetic_plus_test.go", "arithmetic_minus_test.go", "arithmetic_multi_test.go"):
+        src = open(os.path.join(base, fname)).read()
+        for m in re.finditer(r"NewFunctionTestCase\(proc,\s*tc\.inputs,\s*tc\.expect,\s*(\w+)\)", src):
+            if m.group(1) not in fns:
+                continue
+            blk_start = src.rfind("tcTemp{", 0, m.start())
+            blk = src[blk_start:m.start()]
+            if "Decimal" not in blk:
+                continue
+            try:
+                inputs = []
+                for im in re.finditer(r"NewFunctionTestInput\(", blk):
+                    args, _ = _call_args(blk, im.end() - 1)
+                    a = _split_top(args)
+                    ty, vals = _dec_slice(a[1])
+                    _, nulls = _go_slice(a[2])
+                    inputs.append({"type": ty, "scale": 0, "values": [str(v) for v in vals], "nulls": nulls})
+                em = re.search(r"NewFunctionTestResult\(", blk)
+                args, _ = _call_args(blk, em.end() - 1)
+                a = _split_top(args)
+                ety, evals = _dec_slice(a[2])
+                _, enulls = _go_slice(a[3])
+                cases.append({"file": fname, "line": src.count("\n", 0, blk_start) + 1, "op": fns[m.group(1)], "inputs": inputs,
+                              "expect": {"type": ety, "want_err": a[1].strip() == "true", "values": [str(v) for v in evals], "nulls": enulls}})
+            except (ValueError, AttributeError, IndexError):
+                pass
+    assert len(cases) >= 8, len(cases)
+    return {"_source": "pkg/sql/plan/function/arithmetic_{plus,minus,multi}_test.go: Decimal64 / Decimal128 FunctionTestCase tables (values as decimal strings of the unscaled integers)",
+            "cases": cases}
+
+
 def main2():
-    for name, fn in (("tpch_lineitem", tpch_lineitem), ("function_kat", function_kats)):
+    for name, fn in (("tpch_lineitem", tpch_lineitem), ("function_kat", function_kats), ("decimal_kat", decimal_kats)):
         data = fn()
         with open(os.path.join(OUT, name + ".json"), "w") as f:
             json.dump(data, f, separators=(",", ":") if name == "tpch_lineitem" else None, indent=None if name == "tpch_lineitem" else 0)

@@ -85,6 +85,20 @@ def go():
         lib.og_gen_int64.argtypes = [_u64, _u64, _i64, _i32, _vp]
         lib.og_gen_vectors_f32.restype = None
         lib.og_gen_vectors_f32.argtypes = [_u64, _u64, _i64, _i64, _i32, _vp, _vp, _i64, C.c_float, _vp]
+        lib.og_d64_addsub.restype = _i32
+        lib.og_d64_addsub.argtypes = [_i32, _vp, _vp, _vp, _u64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]
+        lib.og_d64_mul.restype = _i32
+        lib.og_d64_mul.argtypes = [_vp, _vp, _vp, _u64, _i32, _i32, _i32, _i32, _vp, _vp, _vp]
+        lib.og_d128_addsub.restype = _i32
+        lib.og_d128_addsub.argtypes = [_i32, _vp, _vp, _vp, _u64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]
+        lib.og_d128_mul.restype = _i32
+        lib.og_d128_mul.argtypes = [_vp, _vp, _vp, _u64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]
+        lib.og_mul_result_scale.restype = _i32
+        lib.og_mul_result_scale.argtypes = [_i32, _i32]
+        lib.og_sum_d64.restype = None
+        lib.og_sum_d64.argtypes = [_vp, _vp, _u64, _vp, _u64, _vp, _vp]
+        lib.og_sum_d128.restype = None
+        lib.og_sum_d128.argtypes = [_vp, _vp, _u64, _vp, _u64, _vp, _vp]
         lib.og_kahan_sum.restype = _f64
         lib.og_kahan_sum.argtypes = [_vp, _i64]
         _go = lib
@@ -200,3 +214,29 @@ def gen_vectors_f32(seed, row0, n, dim, nthreads=8, centers=None, sigma=1.0, wan
     c = None if centers is None else np.ascontiguousarray(centers, dtype=np.float32)
     go().og_gen_vectors_f32(seed, row0, n, dim, nthreads, p(out), p(c), 0 if c is None else c.shape[0], float(sigma), p(comp))
     return (out, comp) if want_components else out
+
+
+def d128_to_int(arr):
+    """uint64[n, 2] {lo, hi} two's-complement -> python ints"""
+    a = np.asarray(arr, dtype=np.uint64).reshape(-1, 2)
+    out = []
+    for lo, hi in a:
+        v = (int(hi) << 64) | int(lo)
+        out.append(v - (1 << 128) if v >> 127 else v)
+    return out
+
+
+def int_to_d128(vals):
+    out = np.zeros((len(vals), 2), dtype=np.uint64)
+    for i, v in enumerate(vals):
+        u = v & ((1 << 128) - 1)
+        out[i, 0] = u & 0xFFFFFFFFFFFFFFFF
+        out[i, 1] = u >> 64
+    return out
+
+
+def decimal_str(v, scale):
+    """Decimal.Format: unscaled integer -> fixed-point text"""
+    sign = "-" if v < 0 else ""
+    s = str(abs(v)).rjust(scale + 1, "0")
+    return sign + (s[:-scale] + "." + s[-scale:] if scale else s)
