@@ -878,8 +878,11 @@ def run_dropin(env):
         return [Vector(data_ptr=dr.ptr, data_nbytes=8 * n, nulls_ptr=dn.ptr, length=n), Vector(data_ptr=da.ptr, data_nbytes=8 * n, length=n),
                 Vector(data_ptr=db.ptr, data_nbytes=8 * n, length=n), pv], (da, db, dr, dn)
     out = {}
-    for label, host in (("host_pointers", True), ("resident", False)):
+    for label, host in (("host_pointers", True), ("host_pointers_inputs_pinned_in_column_cache", True), ("resident", False)):
         vecs, keep = mk(host)
+        if "pinned" in label:      # MoB200_ColumnPin: the block's input columns are uploaded once, later calls find them on the device
+            env.check(lib.MoB200_ColumnCacheConfigure(64 << 20))
+            env.check(lib.MoB200_ColumnPin(a.ctypes.data, a.nbytes, 1)); env.check(lib.MoB200_ColumnPin(b.ctypes.data, b.nbytes, 1))
         arr = (capi.XCallArgs * len(vecs))()
         for i, v in enumerate(vecs):
             arr[i] = v.fill_raw_ptr_len()
@@ -895,8 +898,23 @@ def run_dropin(env):
         env.sync()
         sec = (time.perf_counter() - t0) / reps
         out[label] = {"us_per_block": sec * 1e6, "rows_per_s": n / sec, "rc": int(rc)}
+        if "pinned" in label:
+            env.check(lib.MoB200_ColumnCacheConfigure(0))
         if host:
-            ok = bool(np.array_equal(keep, a + b))
+            ok = bool(np.array_equal(keep, a + b)) and (label == "host_pointers" or ok)
+    # one call over 1024 blocks at once from host pointers (the multi-block form of the same entry point: the per-call costs are paid once)
+    nb = 1024 * n
+    A = env.datagen.int64_column(1, 0, nb)[0]; B = env.datagen.int64_column(2, 0, nb)[0]
+    R = np.zeros(nb, dtype=np.int64); RN = np.zeros(nb // 64, dtype=np.uint64)
+    pvv = Vector(data=np.frombuffer(bytes(GoParams(0, 0, -1)), dtype=np.uint8).copy(), length=1, const=True)
+    bv = [Vector(data=R, nulls=RN, length=nb), Vector(data=A, length=nb), Vector(data=B, length=nb), pvv]
+    xcall(fid, bv, nb)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        xcall(fid, bv, nb)
+    secb = (time.perf_counter() - t0) / 5
+    out["host_pointers_1024_blocks_per_call"] = {"us_per_block": secb * 1e6 / 1024, "rows_per_s": nb / secb, "rc": 0}
+    ok = ok and bool(np.array_equal(R, A + B))
     res = {"value": out["host_pointers"]["rows_per_s"], "units_per_step": n, "timing": {"total_ms": out["host_pointers"]["us_per_block"] * 2.0, "ms_per_step": out["host_pointers"]["us_per_block"] * 1e-3, "launches": 2000, "steps": 2000, "warmup": 50, "clocks": None, "wall_ms": None},
            "kernel_ms": None, "kernel": "go_arith_kernel<int64, +>", "blocks": out, "e2e": {"value": out["host_pointers"]["rows_per_s"], "unit": "rows/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 8 * n + n // 8, "host_memory": "pageable (numpy)"},
            "parity": {"bit_exact": ok, "ok": ok}, "parallelism": "1 OS thread, 1 block in flight"}

@@ -374,6 +374,15 @@ int32_t MoB200_Download(void *dst_host, const void *src_dev, uint64_t bytes);
 int32_t MoB200_DownloadAsync(void *dst_host, const void *src_dev, uint64_t bytes);  /* stream-ordered, NO synchronise (pinned host memory) */
 int32_t MoB200_UploadAsync(void *dst_dev, const void *src_host, uint64_t bytes);
 int32_t MoB200_Memset(void *dst_dev, int32_t value, uint64_t bytes);
+/* Device column cache (off by default).  The ABI hands the library HOST vectors; re-uploading a column on every call makes every call
+ * PCIe-bound (the reference's CUDA shim re-allocates and re-copies per call, cgo/cuda/cuda.cpp:123-201).  A caller that knows a host range is
+ * immutable -- the column of a decoded block, an index's dataset -- pins it once: ColumnPin uploads [host, host + bytes) and from then on EVERY
+ * entry point that is handed a host pointer inside that range reads the device copy instead of staging it.  `generation` distinguishes reuses of
+ * the same buffer (block id / version): pinning the same address with another generation replaces the copy.  LRU eviction beyond the capacity. */
+int32_t MoB200_ColumnCacheConfigure(uint64_t capacity_bytes);   /* 0 = off (drops everything) */
+int32_t MoB200_ColumnPin(const void *host, uint64_t bytes, uint64_t generation);
+int32_t MoB200_ColumnUnpin(const void *host);
+int32_t MoB200_ColumnCacheStats(uint64_t *hits, uint64_t *misses, uint64_t *bytes);
 int32_t MoB200_Sync(void);                    /* synchronize the calling thread's stream */
 int32_t MoB200_SetStream(void *cuda_stream);  /* adopt an external cudaStream_t for the calling thread (NULL = own) */
 int32_t MoB200_TimerStart(void);              /* CUDA event on the calling thread's stream */

@@ -133,6 +133,8 @@ PROTOTYPES = {
     "MoB200_HostAlloc": (_i32, [_u64, C.POINTER(_vp)]), "MoB200_HostFree": (_i32, [_vp]),
     "MoB200_HostRegister": (_i32, [_vp, _u64]), "MoB200_HostUnregister": (_i32, [_vp]),
     "MoB200_Upload": (_i32, [_vp, _vp, _u64]), "MoB200_Download": (_i32, [_vp, _vp, _u64]), "MoB200_Memset": (_i32, [_vp, _i32, _u64]),
+    "MoB200_ColumnCacheConfigure": (_i32, [_u64]), "MoB200_ColumnPin": (_i32, [_vp, _u64, _u64]), "MoB200_ColumnUnpin": (_i32, [_vp]),
+    "MoB200_ColumnCacheStats": (_i32, [C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)]),
     "MoB200_DownloadAsync": (_i32, [_vp, _vp, _u64]), "MoB200_UploadAsync": (_i32, [_vp, _vp, _u64]),
     "MoB200_Sync": (_i32, []), "MoB200_SetStream": (_i32, [_vp]), "MoB200_TimerStart": (_i32, []),
     "MoB200_TimerStop": (_i32, [C.POINTER(C.c_float)]), "MoB200_KernelLaunchCount": (_u64, []), "MoB200_LastKernelMs": (_i32, [C.POINTER(C.c_float)]),

@@ -524,7 +524,7 @@ int xcall_agg_merge(int op, int T, mo_xcall_args_t *args, uint64_t len) {
     if (st.failed) { st.finish(); return MO_RC_INTERNAL_ERROR; }
     agg_merge_kernel<<<1, 1, 0, t.stream>>>(dparts, len, op, T, cls, dres, args[0].dataSz / 8, dn, drc);
     MOB_LAUNCH_CHECK();
-    if (async) { arena_reset(t); return MO_RC_SUCCESS; }   // the merged state's rc word carries errors
+    if (async) { st.release_async(); return MO_RC_SUCCESS; }   // the merged state's rc word carries errors
     int rc = MO_RC_SUCCESS;
     int64_t hrc = 0;
     int r2 = read_back(t, &hrc, drc, 8);

@@ -520,7 +520,7 @@ int xcall_filter_sels(mo_xcall_args_t *args, uint64_t len) {
     int rc = launch_select<int64_t>(t, v, nulls, len, sels, dcount);
     cudaEventRecord(t.kev1, t.stream);
     if (rc) { st.finish(); return rc; }
-    if (dev) { arena_reset(t); return MO_RC_SUCCESS; }   // asynchronous form: everything stays on the device
+    if (dev) { st.release_async(); return MO_RC_SUCCESS; }   // asynchronous form: everything stays on the device
     unsigned long long cnt = 0;
     rc = read_back(t, &cnt, dcount, 8);
     if (rc) { st.finish(); return rc; }
@@ -562,7 +562,7 @@ int xcall_shuffle(int szof, mo_xcall_args_t *args, uint64_t len) {
     }
     cudaEventRecord(t.kev1, t.stream);
     MOB_LAUNCH_CHECK();
-    if (dev) { arena_reset(t); return MO_RC_SUCCESS; }
+    if (dev) { st.release_async(); return MO_RC_SUCCESS; }
     return st.finish();
 }
 

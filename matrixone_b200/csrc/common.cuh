@@ -9,6 +9,7 @@
 #include <stddef.h>
 #include <vector>
 #include <atomic>
+#include <memory>
 #include "../../include/mo_b200.h"
 
 namespace mob {
@@ -54,7 +55,9 @@ struct Stager {
     ThreadCtx &t;
     struct Back { void *host; const void *dev; size_t bytes; };
     std::vector<Back> backs;
+    std::vector<std::shared_ptr<void>> pins;   // column-cache blocks this call reads (kept alive until finish())
     bool failed = false;
+    bool finished = false;   // set by finish(); the destructor cleans up otherwise
     explicit Stager(ThreadCtx &tc) : t(tc) {}
     // input: device pointers pass through, host pointers are copied into the arena (async on t.stream)
     const void *in(const void *p, size_t bytes);
@@ -65,6 +68,8 @@ struct Stager {
     void *tmp(size_t bytes) { void *q = arena_alloc(t, bytes); if (!q) failed = true; return q; }
     // copy-backs + stream sync + arena reset. Returns MO_RC_SUCCESS or MO_RC_INTERNAL_ERROR.
     int finish();
+    // asynchronous form (every pointer was a device pointer): nothing to copy back, no synchronise; the scratch is handed back in stream order
+    void release_async() { backs.clear(); arena_reset(t); finished = true; }   // (no cached host blocks on this path: every pointer was a device pointer)
     ~Stager();
 };
 

@@ -394,7 +394,7 @@ int xcall_plan(mo_xcall_args_t *args, uint64_t len) {
     MOB_LAUNCH_CHECK();
     plan_emit_kernel<<<num_sms() * 2, 256, 0, t.stream>>>(G, dP, used, nused, dres, res_groups, 8192);
     MOB_LAUNCH_CHECK();
-    if (dev_res && dev_cols) { arena_reset(t); return MO_RC_SUCCESS; }   // asynchronous form: header.overflow reports a full table
+    if (dev_res && dev_cols) { st.release_async(); return MO_RC_SUCCESS; }   // asynchronous form: header.overflow reports a full table
     mo_plan_result_header_t H;
     int rc = read_back(t, &H, dres, sizeof H);
     int frc = st.finish();

@@ -9,6 +9,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <map>
+#include <list>
+#include <memory>
 
 namespace mob {
 
@@ -130,9 +133,45 @@ void arena_reset(ThreadCtx &t) {
     t.cur_block = 0; t.cur_off = 0; t.arena_epoch++; t.kev_prio = 0;
 }
 
+// ---- device column cache ----------------------------------------------------------------------------------------------------------
+// the ABI hands the library HOST vectors, and re-uploading a column on every call makes everything PCIe-bound
+// (the reference's CUDA shim has exactly this flaw, cgo/cuda/cuda.cpp:123-201).  A caller that knows a host range is immutable -- a decoded
+// block's column, an index's dataset -- declares it once with MoB200_ColumnPin(host, bytes, generation); from then on every entry point
+// that is handed a pointer inside that range uses the device copy instead of staging it.  Explicit opt-in, because the library cannot know
+// when the Go side recycles a buffer: a new generation or MoB200_ColumnUnpin drops the copy.  LRU eviction beyond the configured capacity.
+struct DevBlock {
+    void *d = nullptr; size_t bytes = 0; uint64_t gen = 0;
+    ~DevBlock() { if (d) cudaFree(d); }
+};
+static std::mutex g_cache_mu;
+static std::map<uintptr_t, std::shared_ptr<DevBlock>> g_cache;   // keyed by host base address
+static std::list<uintptr_t> g_cache_lru;                            // front = most recently used
+static size_t g_cache_bytes = 0, g_cache_cap = 0;
+static std::atomic<uint64_t> g_cache_hits{0}, g_cache_misses{0};
+
+// device pointer for [p, p + bytes) if a pinned block covers it; `keep` holds the block alive for the caller's lifetime
+static const void *cache_lookup(const void *p, size_t bytes, std::shared_ptr<DevBlock> &keep) {
+    if (g_cache_cap == 0) return nullptr;
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    const uintptr_t a = (uintptr_t)p;
+    auto it = g_cache.upper_bound(a);
+    if (it == g_cache.begin()) { g_cache_misses++; return nullptr; }
+    --it;
+    if (a + bytes > it->first + it->second->bytes) { g_cache_misses++; return nullptr; }
+    keep = it->second;
+    g_cache_lru.remove(it->first); g_cache_lru.push_front(it->first);
+    g_cache_hits++;
+    return (const char *)it->second->d + (a - it->first);
+}
+
 const void *Stager::in(const void *p, size_t bytes) {
     if (!p || bytes == 0) return p;
     if (is_device_ptr(p)) return p;
+    {
+        std::shared_ptr<DevBlock> keep;
+        const void *c = cache_lookup(p, bytes, keep);
+        if (c) { pins.push_back(std::static_pointer_cast<void>(keep)); return c; }
+    }
     void *d = arena_alloc(t, bytes);
     if (!d) { failed = true; return nullptr; }
     cudaError_t e = cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, t.stream);
@@ -164,12 +203,16 @@ int Stager::finish() {
     cudaError_t e = cudaStreamSynchronize(t.stream);
     if (e != cudaSuccess) { set_error("stream synchronize failed: %s", cudaGetErrorString(e)); rc = MO_RC_INTERNAL_ERROR; }
     backs.clear();
+    pins.clear();   // the stream is idle: cached blocks may be evicted now
     arena_reset(t);
+    finished = true;
     return rc;
 }
 
 Stager::~Stager() {
-    if (!backs.empty()) { cudaStreamSynchronize(t.stream); arena_reset(t); }
+    // an early return between construction and finish() (MOB_CUDA_TRY / MOB_LAUNCH_CHECK): wait for whatever was enqueued on the scratch and
+    // give it back, so the arena does not grow and per-call caches keyed on the arena epoch are invalidated
+    if (!finished) { cudaStreamSynchronize(t.stream); backs.clear(); pins.clear(); arena_reset(t); }
 }
 
 int read_back(ThreadCtx &t, void *host_dst, const void *dev_src, size_t bytes) {
@@ -266,6 +309,63 @@ int32_t MoB200_UploadAsync(void *dst_dev, const void *src_host, uint64_t bytes) 
     REQUIRE_CTX(t);
     search_invalidate(dst_dev, bytes);
     MOB_CUDA_TRY(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, t.stream));
+    return MO_RC_SUCCESS;
+}
+int32_t MoB200_ColumnCacheConfigure(uint64_t capacity_bytes) {
+    REQUIRE_CTX(t);
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    g_cache_cap = (size_t)capacity_bytes;
+    while (g_cache_bytes > g_cache_cap && !g_cache_lru.empty()) {
+        const uintptr_t k = g_cache_lru.back(); g_cache_lru.pop_back();
+        auto it = g_cache.find(k);
+        if (it != g_cache.end()) { g_cache_bytes -= it->second->bytes; g_cache.erase(it); }
+    }
+    return MO_RC_SUCCESS;
+}
+int32_t MoB200_ColumnPin(const void *host, uint64_t bytes, uint64_t generation) {
+    REQUIRE_CTX(t);
+    if (!host || bytes == 0) return MO_RC_SUCCESS;
+    if (is_device_ptr(host)) { set_error("ColumnPin: host pointer expected"); return MO_RC_INVALID_ARGUMENT; }
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        if (g_cache_cap == 0 || bytes > g_cache_cap) return MO_RC_SUCCESS;     // cache off / column larger than the cache: calls keep staging it
+        auto it = g_cache.find((uintptr_t)host);
+        if (it != g_cache.end()) {
+            if (it->second->gen == generation && it->second->bytes >= bytes) { g_cache_lru.remove(it->first); g_cache_lru.push_front(it->first); return MO_RC_SUCCESS; }
+            g_cache_bytes -= it->second->bytes; g_cache_lru.remove(it->first); g_cache.erase(it);   // a new generation of the same buffer
+        }
+    }
+    auto blk = std::make_shared<DevBlock>();
+    MOB_CUDA_TRY(cudaMalloc(&blk->d, bytes));
+    blk->bytes = bytes; blk->gen = generation;
+    MOB_CUDA_TRY(cudaMemcpyAsync(blk->d, host, bytes, cudaMemcpyHostToDevice, t.stream));
+    MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    // overlapping older entries would shadow / be shadowed by this one: drop them
+    for (auto it = g_cache.begin(); it != g_cache.end();) {
+        if (it->first < (uintptr_t)host + bytes && (uintptr_t)host < it->first + it->second->bytes) { g_cache_bytes -= it->second->bytes; g_cache_lru.remove(it->first); it = g_cache.erase(it); }
+        else ++it;
+    }
+    g_cache[(uintptr_t)host] = blk; g_cache_lru.push_front((uintptr_t)host); g_cache_bytes += bytes;
+    while (g_cache_bytes > g_cache_cap && g_cache_lru.size() > 1) {
+        const uintptr_t k = g_cache_lru.back(); g_cache_lru.pop_back();
+        auto it = g_cache.find(k);
+        if (it != g_cache.end()) { g_cache_bytes -= it->second->bytes; g_cache.erase(it); }   // in-flight calls hold their own reference
+    }
+    return MO_RC_SUCCESS;
+}
+int32_t MoB200_ColumnUnpin(const void *host) {
+    REQUIRE_CTX(t);
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    auto it = g_cache.find((uintptr_t)host);
+    if (it != g_cache.end()) { g_cache_bytes -= it->second->bytes; g_cache_lru.remove(it->first); g_cache.erase(it); }
+    return MO_RC_SUCCESS;
+}
+int32_t MoB200_ColumnCacheStats(uint64_t *hits, uint64_t *misses, uint64_t *bytes) {
+    if (hits) *hits = g_cache_hits.load();
+    if (misses) *misses = g_cache_misses.load();
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    if (bytes) *bytes = g_cache_bytes;
     return MO_RC_SUCCESS;
 }
 int32_t MoB200_Memset(void *dst_dev, int32_t value, uint64_t bytes) {

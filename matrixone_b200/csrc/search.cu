@@ -317,7 +317,8 @@ __global__ void topk_merge_kernel(int64_t nq, int k, int nlists, int64_t list_st
     }
     const int total = avail < k ? avail : k;
     const int pad = k - total;
-    for (int j = 0; j < pad; j++) { ok[j] = -1; od[j] = 0.0; }
+    // limit == 1 over an empty dataset leaves the running minimum untouched: key -1, distance MaxFloat32 (brute_force.go:289-303)
+    for (int j = 0; j < pad; j++) { ok[j] = -1; od[j] = (k == 1 && !slot_major) ? (double)3.40282346638528859811704183484516925440e+38f : 0.0; }
     while (produced < total) {
         int best = -1; double bd = 0; int64_t bk = 0;
         for (int l = 0; l < nlists; l++) {
@@ -429,6 +430,7 @@ int bruteforce_topk_device(ThreadCtx &t, const float *ddata, int64_t n, int dim,
 int xcall_bruteforce(mo_xcall_args_t *args, uint64_t len) {
     ThreadCtx &t = tctx();
     if (!t.ready) return MO_RC_INTERNAL_ERROR;
+    SearchReadGuard guard;   // prepared operands stay alive until this call returns
     mo_search_params_t P;
     int rc = read_params(t, args[4], &P);
     if (rc) return rc;
@@ -576,6 +578,7 @@ static int ivf_search_level(ThreadCtx &t, const IvfJob &J, int level, const floa
 int xcall_ivf(mo_xcall_args_t *args, uint64_t len) {
     ThreadCtx &t = tctx();
     if (!t.ready) return MO_RC_INTERNAL_ERROR;
+    SearchReadGuard guard;
     mo_search_params_t P;
     int rc = read_params(t, args[4], &P);
     if (rc) return rc;

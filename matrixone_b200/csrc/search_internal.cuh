@@ -25,6 +25,9 @@ int ivf_make_plan(ThreadCtx &t, const float *dcent, int64_t nlist, int dim, cons
 int ivf_exact_scan(ThreadCtx &t, const IvfPlan &plan, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq,
                    const std::vector<int64_t> &offsets, const int64_t *drowids, int k, int metric, int sqrt_out, int64_t *ok, double *od);
 
+// held (shared) by every search entry point for the duration of the call; see g_search_rw in tcsearch.cu
+struct SearchReadGuard { SearchReadGuard(); ~SearchReadGuard(); SearchReadGuard(const SearchReadGuard &) = delete; SearchReadGuard &operator=(const SearchReadGuard &) = delete; };
+
 bool tc_search_applicable(int64_t n, int dim, int64_t nq, int k, int metric);
 bool tc_probe_applicable(int64_t nlist, int dim, int64_t nq, int nprobe, int metric);
 // record_stats = false: a helper search inside another call (IVF centroid probe) leaves the fallback counter and kernel timer alone
@@ -40,7 +43,7 @@ int ivf_tc_scan(ThreadCtx &t, const IvfPlan &plan, const float *ddata, int64_t n
 bool tc_one_term_wanted(int k, bool record);   // ladder policy shared by brute force and IVF
 void tc_one_term_report(int64_t nq, int64_t failed);
 
-extern int g_last_tc_fallbacks;   // queries of the last tensor-core search that ended in the exact kernel
-extern int g_last_tc_refined;     // IVF: queries of the last search that needed the sub-range refine pass
+extern thread_local int g_last_tc_fallbacks;   // queries of the last tensor-core search that ended in the exact kernel
+extern thread_local int g_last_tc_refined;     // IVF: queries of the last search that needed the sub-range refine pass
 
 }  // namespace mob

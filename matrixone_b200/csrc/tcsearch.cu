@@ -25,6 +25,8 @@
 #include "godist.cuh"
 #include "search_internal.cuh"
 #include <mutex>
+#include <shared_mutex>
+#include <atomic>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cstring>
@@ -741,12 +743,12 @@ namespace mob {
 int g_search_mode = 0;          // 0 = auto, 1 = exact kernel only, 2 = force the tensor-core path (MoB200_SetTuning("search_mode"))
 int g_tc_share_mode = 0;         // 1 = no cross-unit threshold sharing (MoB200_SetTuning("tc_share"))
 int g_tc_ladder_mode = 0;        // 0 = auto (one-term level first unless it has been failing), 1 = never, 2 = always (MoB200_SetTuning("tc_ladder"))
-int g_one_term_skip = 0;         // searches left before the one-term level is tried again
-int g_last_tc_kused = 0;         // K elements per (query, row) pair the timed candidate pass multiplied (dim = one term, 3*dim = three)
+std::atomic<int> g_one_term_skip{0};   // searches left before the one-term level is tried again (shared by all callers: a property of the data)
+thread_local int g_last_tc_kused = 0;   // (per calling thread, like the kernel timer) K elements per (query, row) pair the timed candidate pass multiplied (dim = one term, 3*dim = three)
 int g_tc_range_mb = 0;         // L2 budget of one row range of the brute-force candidate pass, MB (0 = ignore the L2)
 int g_tc_pair_mode = 0;          // 0 = auto, 1 = single-CTA units only, 2 = CTA pairs wherever the brute-force path runs (MoB200_SetTuning("tc_pair"))
-int g_last_tc_refined = -1;
-int g_last_tc_fallbacks = -1;   // queries of the last tensor-core search that failed the completeness proof and were re-run exactly
+thread_local int g_last_tc_refined = -1;
+thread_local int g_last_tc_fallbacks = -1;   // queries of the last tensor-core search that failed the completeness proof and were re-run exactly
 
 struct TcOperand { __nv_bfloat16 *bf = nullptr; float *norm = nullptr; float *lonorm = nullptr; const float *enorm = nullptr; int kprime = 0; };   // enorm: what the epilogue adds (null = norm; zeros for inner product)   // norm = |x|^2, lonorm = |x - bf16(x)|^2 per row
 
@@ -754,6 +756,12 @@ struct TcOperand { __nv_bfloat16 *bf = nullptr; float *norm = nullptr; float *lo
 struct PreparedOperand { const float *x; int64_t n; int dim; int device; TcOperand op; const float *cent = nullptr; int64_t nlist = 0; int normalized = 0; };   // cent != nullptr: IVF residual operand; normalized: cosine
 static std::mutex g_prepared_mu;
 static std::vector<PreparedOperand> g_prepared;
+// A search holds this shared for its whole call (the kernels it launched have finished when it returns); whoever frees or rebuilds a
+// prepared operand -- SearchRelease, DeviceFree, Upload / Memset over the dataset, SearchPrepare* -- takes it exclusively, so a concurrent
+// search on another OS thread never runs TMA loads on freed memory.
+static std::shared_mutex g_search_rw;
+SearchReadGuard::SearchReadGuard() { g_search_rw.lock_shared(); }
+SearchReadGuard::~SearchReadGuard() { g_search_rw.unlock_shared(); }
 
 // split an fp32 row-major matrix into the K-concatenated bf16 operand; *nonfinite (device flag) is raised on Inf/NaN
 static int tc_prepare(ThreadCtx &t, const float *x, int64_t n, int dim, int mode, int *dnonfinite, TcOperand &op, int normalize = 0) {
@@ -1086,6 +1094,18 @@ static int bf_tc_level(ThreadCtx &t, int level, int metric, const float *ddata, 
 }
 
 void search_invalidate(const void *p, uint64_t bytes) {
+    {   // cheap pre-check under the list mutex only: most writes (scratch uploads, generators) touch no prepared dataset
+        std::lock_guard<std::mutex> lk0(g_prepared_mu);
+        bool hit = false;
+        const char *lo0 = (const char *)p, *hi0 = lo0 + bytes;
+        for (const PreparedOperand &e : g_prepared) {
+            const char *xl = (const char *)e.x, *xh = xl + (size_t)e.n * e.dim * 4;
+            const char *cl = (const char *)e.cent, *ch = e.cent ? cl + (size_t)e.nlist * e.dim * 4 : cl;
+            if ((lo0 < xh && xl < hi0) || (e.cent && lo0 < ch && cl < hi0)) hit = true;
+        }
+        if (!hit) return;
+    }
+    std::unique_lock<std::shared_mutex> wr(g_search_rw);   // wait for running searches to finish before freeing their operand
     std::lock_guard<std::mutex> lk(g_prepared_mu);
     const char *lo = (const char *)p, *hi = lo + bytes;
     for (size_t i = 0; i < g_prepared.size();) {
@@ -1103,11 +1123,11 @@ void search_invalidate(const void *p, uint64_t bytes) {
 bool tc_one_term_wanted(int k, bool record) {
     if (k > KP || g_tc_ladder_mode == 1) return false;
     if (g_tc_ladder_mode == 2) return true;
-    if (g_one_term_skip > 0) { if (record) g_one_term_skip--; return false; }
+    if (g_one_term_skip.load() > 0) { if (record) g_one_term_skip.fetch_sub(1); return false; }
     return true;
 }
 // a dataset whose norms dwarf its neighbour distances defeats the one-term bound: stop trying for a while
-void tc_one_term_report(int64_t nq, int64_t failed) { if (nq >= 64 && failed * 5 > nq * 2) g_one_term_skip = 16; }
+void tc_one_term_report(int64_t nq, int64_t failed) { if (nq >= 64 && failed * 5 > nq * 2) g_one_term_skip.store(16); }
 
 int bruteforce_topk_tc_device(ThreadCtx &t, const float *ddata, int64_t n, int dim, const float *dq, int64_t nq, int k,
                               int64_t key_base, int sqrt_out, int64_t *out_k, double *out_d, bool record_stats, int metric) {
@@ -1274,6 +1294,13 @@ int32_t MoB200_SearchPrepareIvf(const void *data, uint64_t n, int64_t dim, const
 
 int32_t MoB200_SearchRelease(const void *data) {
     using namespace mob;
+    {
+        std::lock_guard<std::mutex> lk0(g_prepared_mu);
+        bool hit = false;
+        for (const PreparedOperand &e : g_prepared) if (e.x == data || (e.cent && (const void *)e.cent == data)) hit = true;
+        if (!hit) return MO_RC_SUCCESS;
+    }
+    std::unique_lock<std::shared_mutex> wr(g_search_rw);   // running searches first
     std::lock_guard<std::mutex> lk(g_prepared_mu);
     // also drops IVF operands built against `data` as their centroid table (residuals would be stale)
     for (size_t i = 0; i < g_prepared.size();) {

@@ -18,6 +18,7 @@
 // the records in CTA-index order => bitwise run-to-run deterministic for a fixed grid.
 #include "common.cuh"
 #include <cstring>
+#include <atomic>
 
 using namespace mob;
 
@@ -538,6 +539,106 @@ q1_staged_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty,
     q1_epilogue<G, kStagedThreads>(T, S, partials, out, ticket, dbg);
 }
 
+// ---- variant C: bulk-copy (TMA 1-D) staged tiles ---------------------------------------------------------------------------------
+// Same per-warp ring as variant B, but every column slice of a tile is ONE cp.async.bulk (256 B shipdate, 4 x 512 B float64 columns,
+// 2 x 64 B key bytes) issued by lane 0 and completed on a per-(warp, stage) mbarrier: 7 copy instructions per 64-row tile instead of
+// 6 x 32 per-lane LDGSTS, nothing passes through L1, and the L2 -> SM crossbar moves every byte once (ncu on variant B:
+// l1tex__m_xbar2l1tex_read_bytes = 1.84 x the DRAM bytes, sector hit rate 49 %).
+__device__ __forceinline__ void q1_mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void q1_mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void q1_mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nQ1_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra Q1_DONE;\nbra Q1_WAIT;\nQ1_DONE:\n}"
+        ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void q1_bulk_copy(void *smem, const void *gmem, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+template <int G, int kStages>
+__global__ void __launch_bounds__(kStagedThreads, 1)
+q1_bulk_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty, const double *__restrict__ price,
+               const double *__restrict__ disc, const double *__restrict__ tax, const uint8_t *__restrict__ rf,
+               const uint8_t *__restrict__ ls, uint64_t n, int32_t cutoff, Q1Rec *__restrict__ partials,
+               Q1Rec *__restrict__ out, unsigned *ticket, unsigned long long *dbg) {
+    extern __shared__ __align__(128) unsigned char ring[];   // [warp][stage][kTileBytes], then the mbarriers
+    if (dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[blockIdx.x * 16] = t; }
+    __shared__ Q1Shared S;
+    S.dict[threadIdx.x & (MO_Q1_MAX_GROUPS - 1)] = kEmptyKey;
+    S.overflow = 0; S.slow = 0;
+    constexpr int kWarps = kStagedThreads / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *wring = ring + (size_t)warp * kStages * kTileBytes;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(ring + (size_t)kWarps * kStages * kTileBytes) + warp * kStages;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; s++) q1_mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    Q1Thread<G> T;
+    T.init(&S, cutoff, dbg != nullptr);
+    const uint64_t ntiles = n / kTileRows;
+    const uint64_t gw = blockIdx.x * (uint64_t)kWarps + warp, nw = (uint64_t)gridDim.x * kWarps;
+
+    auto issue = [&](uint64_t tile, int stage) {   // lane 0 only
+        unsigned char *s = wring + stage * kTileBytes;
+        const uint64_t r0 = tile * kTileRows;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the slot was last READ through the generic proxy
+        q1_mbar_expect_tx(&bars[stage], kTileBytes);
+        q1_bulk_copy(s, sd + r0, 256, &bars[stage]);
+        q1_bulk_copy(s + 256, qty + r0, 512, &bars[stage]);
+        q1_bulk_copy(s + 768, price + r0, 512, &bars[stage]);
+        q1_bulk_copy(s + 1280, disc + r0, 512, &bars[stage]);
+        q1_bulk_copy(s + 1792, tax + r0, 512, &bars[stage]);
+        q1_bulk_copy(s + 2304, rf + r0, 64, &bars[stage]);
+        q1_bulk_copy(s + 2368, ls + r0, 64, &bars[stage]);
+    };
+
+    uint64_t next = gw;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages - 1; s++) { if (next < ntiles) issue(next, s); next += nw; }
+    } else next += (uint64_t)(kStages - 1) * nw;
+    int stage = 0; unsigned phase = 0;
+    for (uint64_t tile = gw; tile < ntiles; tile += nw) {
+        const int fill = (stage + kStages - 1) % kStages;
+        if (lane == 0 && next < ntiles) issue(next, fill);   // the slot consumed in the previous iteration (all lanes passed its __syncwarp)
+        next += nw;
+        q1_mbar_wait(&bars[stage], phase);
+        const unsigned char *s = wring + stage * kTileBytes;
+        const uint64_t r0 = tile * kTileRows;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int rl = lane + 32 * h;
+            const int32_t d = *reinterpret_cast<const int32_t *>(s + rl * 4);
+            const double q = *reinterpret_cast<const double *>(s + 256 + rl * 8);
+            const double pr = *reinterpret_cast<const double *>(s + 768 + rl * 8);
+            const double di = *reinterpret_cast<const double *>(s + 1280 + rl * 8);
+            const double tx = *reinterpret_cast<const double *>(s + 1792 + rl * 8);
+            const unsigned key = (unsigned)s[2304 + rl] | ((unsigned)s[2368 + rl] << 8);
+            T.row(r0 + rl, true, d, q, pr, di, tx, key);
+        }
+        __syncwarp();
+        stage = (stage + 1) % kStages;
+        if (stage == 0) phase ^= 1u;
+    }
+    if (blockIdx.x == 0 && warp == 0) {
+        for (uint64_t r = ntiles * kTileRows + lane; r - lane < n; r += 32) {
+            const bool has = r < n;
+            unsigned key = 0; int32_t dd = 0; double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+            if (has) { key = q1_key_scalar<0>(rf, ls, r); dd = sd[r]; v0 = qty[r]; v1 = price[r]; v2 = disc[r]; v3 = tax[r]; }
+            T.row(r, has, dd, v0, v1, v2, v3, key);
+        }
+    }
+    q1_epilogue<G, kStagedThreads>(T, S, partials, out, ticket, dbg);
+}
+
 __host__ __device__ void q1_finalize(const Q1Rec &F, mo_q1_result_t *res, int64_t row_base = 0) {
     memset(res, 0, sizeof *res);
     int order[MO_Q1_MAX_GROUPS], ng = 0;
@@ -622,9 +723,12 @@ unsigned long long *g_q1_dbg = nullptr;   // optional per-CTA phase timestamps (
 namespace mob {
 
 unsigned long long *q1_debug_buffer() { return g_q1_dbg; }
+int xcall_plan(mo_xcall_args_t *args, uint64_t len);
 
 extern int g_search_mode;
-extern int g_last_tc_fallbacks, g_last_tc_refined, g_tc_pair_mode, g_tc_range_mb, g_tc_ladder_mode, g_last_tc_kused, g_one_term_skip, g_tc_share_mode;
+extern thread_local int g_last_tc_fallbacks, g_last_tc_refined, g_last_tc_kused;
+extern int g_tc_pair_mode, g_tc_range_mb, g_tc_ladder_mode, g_tc_share_mode;
+extern std::atomic<int> g_one_term_skip;
 
 int tuning_set(const char *name, int value) {
     if (!strcmp(name, "search_mode")) { g_search_mode = value; return 0; }
@@ -632,7 +736,7 @@ int tuning_set(const char *name, int value) {
     if (!strcmp(name, "get_tc_refined")) return g_last_tc_refined;
     if (!strcmp(name, "tc_pair")) { g_tc_pair_mode = (int)value; return 0; }
     if (!strcmp(name, "tc_range_mb")) { g_tc_range_mb = (int)value; return 0; }
-    if (!strcmp(name, "tc_ladder")) { g_tc_ladder_mode = (int)value; g_one_term_skip = 0; return 0; }
+    if (!strcmp(name, "tc_ladder")) { g_tc_ladder_mode = (int)value; g_one_term_skip.store(0); return 0; }
     if (!strcmp(name, "get_tc_kused")) return g_last_tc_kused;
     if (!strcmp(name, "tc_share")) { g_tc_share_mode = (int)value; return 0; }
     if (!strcmp(name, "q6_variant")) { g_q6_variant = value; return 0; }
@@ -684,10 +788,44 @@ int xcall_q6(mo_xcall_args_t *args, uint64_t len) {
     if (args[1].dataSz < 4 * len || args[2].dataSz < 8 * len || args[3].dataSz < 8 * len || args[4].dataSz < 8 * len) {
         set_error("q6: column shorter than len"); return MO_RC_INVALID_ARGUMENT;
     }
-    for (int i = 1; i <= 4; i++) if (args[i].pnulls) { set_error("q6: nullable columns are not supported by the fused kernel"); return MO_RC_INVALID_ARGUMENT; }
     mo_q6_params_t P;
     if (is_device_ptr(args[5].pdata)) { int rc = read_back(t, &P, args[5].pdata, sizeof P); if (rc) return rc; }
     else memcpy(&P, args[5].pdata, sizeof P);
+    bool nullable = false;
+    for (int i = 1; i <= 4; i++) nullable = nullable || args[i].pnulls != nullptr;
+    if (nullable) {
+        // nullable inputs: the same query through the generic fused operator (plan.cu), which carries a nulls bitmap on every column --
+        // a NULL predicate operand rejects the row, a NULL product is skipped by SUM.  The specialised kernel above is the no-nulls fast path.
+        mo_plan_t Q; memset(&Q, 0, sizeof Q);
+        Q.ncols = 4; Q.col_type[0] = MO_T_DATE; Q.col_type[1] = Q.col_type[2] = Q.col_type[3] = MO_T_FLOAT64;
+        Q.npreds = 4;
+        Q.pred[0] = mo_plan_pred_t{0, 3, (double)P.date_lo, 0.0}; Q.pred[1] = mo_plan_pred_t{0, 4, (double)P.date_hi, 0.0};
+        Q.pred[2] = mo_plan_pred_t{1, 6, P.disc_lo, P.disc_hi};    Q.pred[3] = mo_plan_pred_t{2, 4, P.qty_hi, 0.0};
+        Q.ninstr = 1; Q.instr[0] = mo_plan_instr_t{MO_PLAN_OP_MUL, 3, 1, 0, 0.0};      // l_extendedprice * l_discount
+        Q.naggs = 1; Q.agg[0] = mo_plan_agg_t{MO_AGG_SUM, 4};
+        struct { mo_plan_result_header_t h; mo_plan_group_t g; mo_plan_agg_value_t a; } R;
+        memset(&R, 0, sizeof R);
+        mo_xcall_args_t pa[6]; memset(pa, 0, sizeof pa);
+        pa[0].pdata = (uint8_t *)&R; pa[0].dataSz = sizeof R;
+        pa[1].pdata = (uint8_t *)&Q; pa[1].dataSz = sizeof Q;
+        pa[2] = args[1]; pa[3] = args[2]; pa[4] = args[3]; pa[5] = args[4];
+        int rc = xcall_plan(pa, len);
+        if (rc) return rc;
+        const bool any_ = R.h.ngroups > 0 && R.a.count > 0;
+        const double sum_ = any_ ? R.a.value : 0.0;
+        const int64_t rows_ = R.h.ngroups > 0 ? R.g.rows : 0;
+        const uint64_t nullword_ = any_ ? 0ull : 1ull;
+        if (is_device_ptr(args[0].pdata)) {
+            MOB_CUDA_TRY(cudaMemcpyAsync(args[0].pdata, &sum_, 8, cudaMemcpyHostToDevice, t.stream));
+            if (args[0].dataSz >= 16) MOB_CUDA_TRY(cudaMemcpyAsync(args[0].pdata + 8, &rows_, 8, cudaMemcpyHostToDevice, t.stream));
+            MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));
+        } else { memcpy(args[0].pdata, &sum_, 8); if (args[0].dataSz >= 16) memcpy(args[0].pdata + 8, &rows_, 8); }
+        if (args[0].pnulls) {
+            if (is_device_ptr(args[0].pnulls)) { MOB_CUDA_TRY(cudaMemcpyAsync(args[0].pnulls, &nullword_, 8, cudaMemcpyHostToDevice, t.stream)); MOB_CUDA_TRY(cudaStreamSynchronize(t.stream)); }
+            else memcpy(args[0].pnulls, &nullword_, 8);
+        }
+        return MO_RC_SUCCESS;
+    }
 
     const bool dev = is_device_ptr(args[1].pdata);
     for (int i = 2; i <= 4; i++) if (is_device_ptr(args[i].pdata) != dev) { set_error("q6: columns must all be host or all device"); return MO_RC_INVALID_ARGUMENT; }
@@ -770,7 +908,22 @@ static int launch_q1(ThreadCtx &t, const int32_t *sd, const double *qty, const d
         if (!partials) return MO_RC_INTERNAL_ERROR;
         Q1Rec *out = partials + grid;
         if (attempt == 0 || !dres) cudaEventRecord(t.kev0, t.stream);
-        if (staged) {
+        if (staged && g_q1_variant >= 5 && g_q1_variant <= 7) {
+            const int stages = g_q1_variant == 5 ? 3 : (g_q1_variant == 6 ? 4 : 6);
+            const size_t smem = (size_t)(kStagedThreads / 32) * stages * kTileBytes + (size_t)(kStagedThreads / 32) * stages * 8;
+            static bool battr[3] = {false, false, false};
+            const int bi = g_q1_variant - 5;
+            if (!battr[bi]) {
+                cudaError_t e = stages == 3 ? cudaFuncSetAttribute(q1_bulk_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                              : stages == 4 ? cudaFuncSetAttribute(q1_bulk_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                            : cudaFuncSetAttribute(q1_bulk_kernel<4, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) { set_error("q1: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return MO_RC_INTERNAL_ERROR; }
+                battr[bi] = true;
+            }
+            if (stages == 3) q1_bulk_kernel<4, 3><<<grid, kStagedThreads, smem, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg);
+            else if (stages == 4) q1_bulk_kernel<4, 4><<<grid, kStagedThreads, smem, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg);
+            else q1_bulk_kernel<4, 6><<<grid, kStagedThreads, smem, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg);
+        } else if (staged) {
             const int stages = g_q1_variant == 3 ? 4 : (g_q1_variant == 4 ? 5 : 3);   // 3 stages measured best (tools/tune.py q1)
             const size_t smem = (size_t)(kStagedThreads / 32) * stages * kTileBytes;
             static bool attr_done[3] = {false, false, false};
@@ -832,7 +985,8 @@ int xcall_q1(mo_xcall_args_t *args, uint64_t len) {
     if (!args[8].pdata || args[8].dataSz < 4) { set_error("q1: cutoff param missing"); return MO_RC_INVALID_ARGUMENT; }
     if (args[1].dataSz < 4 * len) { set_error("q1: shipdate shorter than len"); return MO_RC_INVALID_ARGUMENT; }
     for (int i = 2; i <= 5; i++) if (args[i].dataSz < 8 * len) { set_error("q1: column %d shorter than len", i); return MO_RC_INVALID_ARGUMENT; }
-    for (int i = 1; i <= 7; i++) if (args[i].pnulls) { set_error("q1: nullable columns are not supported by the fused kernel"); return MO_RC_INVALID_ARGUMENT; }
+    bool q1_nullable = false;
+    for (int i = 1; i <= 7; i++) q1_nullable = q1_nullable || args[i].pnulls != nullptr;
     int keymode;
     if (args[6].dataSz == len && args[7].dataSz == len) keymode = 0;
     else if (args[6].dataSz == 24 * len && args[7].dataSz == 24 * len) keymode = 1;
@@ -845,6 +999,54 @@ int xcall_q1(mo_xcall_args_t *args, uint64_t len) {
     const uint64_t ksz = keymode ? 24 : 1;
     int64_t row_base = 0;   // optional: params = {int32 cutoff; int32 pad; int64 row_base} -> first_row values are global row numbers
     if (args[8].dataSz >= 16 && !is_device_ptr(args[8].pdata)) memcpy(&row_base, args[8].pdata + 8, 8);
+    if (q1_nullable) {
+        // nullable inputs: the generic fused operator (plan.cu).  NULL shipdate rejects the row; NULL values are skipped by their aggregates;
+        // a NULL key is its own group (has_null_keys; its key byte reads 0 here).  Packed uint8 keys only.
+        if (keymode != 0) { set_error("q1: nullable columns need packed uint8 key columns"); return MO_RC_INVALID_ARGUMENT; }
+        mo_plan_t Q; memset(&Q, 0, sizeof Q);
+        Q.ncols = 7; Q.col_type[0] = MO_T_DATE; for (int c = 1; c <= 4; c++) Q.col_type[c] = MO_T_FLOAT64; Q.col_type[5] = Q.col_type[6] = MO_T_UINT8;
+        Q.row_base = row_base; Q.has_null_keys = (args[6].pnulls || args[7].pnulls) ? 1 : 0;
+        Q.npreds = 1; Q.pred[0] = mo_plan_pred_t{0, 5, (double)cutoff, 0.0};
+        Q.ninstr = 5;
+        Q.instr[0] = mo_plan_instr_t{MO_PLAN_OP_CONST, 0, 0, 0, 1.0};        // slot 7: 1
+        Q.instr[1] = mo_plan_instr_t{MO_PLAN_OP_SUB, 7, 3, 0, 0.0};          // slot 8: 1 - l_discount
+        Q.instr[2] = mo_plan_instr_t{MO_PLAN_OP_MUL, 2, 8, 0, 0.0};          // slot 9: l_extendedprice * (1 - l_discount)
+        Q.instr[3] = mo_plan_instr_t{MO_PLAN_OP_ADD, 7, 4, 0, 0.0};          // slot 10: 1 + l_tax
+        Q.instr[4] = mo_plan_instr_t{MO_PLAN_OP_MUL, 9, 10, 0, 0.0};         // slot 11: ... * (1 + l_tax)
+        Q.nkeys = 2; Q.key_col[0] = 5; Q.key_col[1] = 6;
+        Q.naggs = 6;
+        Q.agg[0] = mo_plan_agg_t{MO_AGG_SUM, 1}; Q.agg[1] = mo_plan_agg_t{MO_AGG_SUM, 2}; Q.agg[2] = mo_plan_agg_t{MO_AGG_SUM, 9}; Q.agg[3] = mo_plan_agg_t{MO_AGG_SUM, 11};
+        Q.agg[4] = mo_plan_agg_t{MO_AGG_SUM, 3}; Q.agg[5] = mo_plan_agg_t{MO_AGG_COUNT, -1};
+        struct Rec { mo_plan_group_t g; mo_plan_agg_value_t a[6]; };
+        struct { mo_plan_result_header_t h; Rec r[MO_Q1_MAX_GROUPS]; } R;
+        memset(&R, 0, sizeof R);
+        mo_xcall_args_t pa[9]; memset(pa, 0, sizeof pa);
+        pa[0].pdata = (uint8_t *)&R; pa[0].dataSz = sizeof R;
+        pa[1].pdata = (uint8_t *)&Q; pa[1].dataSz = sizeof Q;
+        for (int c = 0; c < 7; c++) pa[2 + c] = args[1 + c];
+        int rc = xcall_plan(pa, len);
+        if (rc) { if (rc == MO_RC_INVALID_ARGUMENT) set_error("q1: more than %d distinct group keys", MO_Q1_MAX_GROUPS); return rc; }
+        mo_q1_result_t res; memset(&res, 0, sizeof res);
+        res.ngroups = R.h.ngroups;
+        for (int64_t g = 0; g < R.h.ngroups; g++) {
+            const Rec &r = R.r[g]; mo_q1_group_t &o = res.groups[g];
+            const int shift = Q.has_null_keys ? 8 : 0;   // has_null mode: marker byte, then the value byte
+            const bool n0 = Q.has_null_keys && (r.g.key & 0xff) != 0;
+            o.returnflag = n0 ? 0 : (uint8_t)((r.g.key >> shift) & 0xff);
+            const int off1 = Q.has_null_keys ? (n0 ? 1 : 2) : 1;
+            const bool n1 = Q.has_null_keys && ((r.g.key >> (8 * off1)) & 0xff) != 0;
+            o.linestatus = n1 ? 0 : (uint8_t)((r.g.key >> (8 * (off1 + (Q.has_null_keys ? 1 : 0)))) & 0xff);
+            o.first_row = r.g.first_row;
+            o.sum_qty = r.a[0].value; o.sum_base_price = r.a[1].value; o.sum_disc_price = r.a[2].value; o.sum_charge = r.a[3].value; o.sum_disc = r.a[4].value;
+            o.avg_qty = r.a[0].count ? r.a[0].value / (double)r.a[0].count : 0.0;
+            o.avg_price = r.a[1].count ? r.a[1].value / (double)r.a[1].count : 0.0;
+            o.avg_disc = r.a[4].count ? r.a[4].value / (double)r.a[4].count : 0.0;
+            o.count_order = r.a[5].count;
+        }
+        if (is_device_ptr(args[0].pdata)) { MOB_CUDA_TRY(cudaMemcpyAsync(args[0].pdata, &res, sizeof res, cudaMemcpyHostToDevice, t.stream)); MOB_CUDA_TRY(cudaStreamSynchronize(t.stream)); }
+        else memcpy(args[0].pdata, &res, sizeof res);
+        return MO_RC_SUCCESS;
+    }
 
     if (dev && len && is_device_ptr(args[0].pdata)) {
         // resident columns AND a device result: enqueue only (see xcall_q6)
@@ -912,7 +1114,7 @@ int xcall_q6_merge(mo_xcall_args_t *args, uint64_t len) {
     if (st.failed) { st.finish(); return MO_RC_INTERNAL_ERROR; }
     q6_merge_kernel<<<1, 1, 0, t.stream>>>(dparts, len, Q6DevOut{dres, args[0].dataSz / 8, dn});
     MOB_LAUNCH_CHECK();
-    if (async) { arena_reset(t); return MO_RC_SUCCESS; }
+    if (async) { st.release_async(); return MO_RC_SUCCESS; }
     return st.finish();
 }
 
@@ -928,7 +1130,7 @@ int xcall_q1_merge(mo_xcall_args_t *args, uint64_t len) {
     if (st.failed) { st.finish(); return MO_RC_INTERNAL_ERROR; }
     q1_merge_kernel<<<1, 1, 0, t.stream>>>(dparts, len, dres);
     MOB_LAUNCH_CHECK();
-    if (async) { arena_reset(t); return MO_RC_SUCCESS; }
+    if (async) { st.release_async(); return MO_RC_SUCCESS; }
     int rc = st.finish();
     if (!rc && !is_device_ptr(args[0].pdata) && ((mo_q1_result_t *)args[0].pdata)->ngroups < 0) { set_error("q1 merge: more than %d distinct group keys", MO_Q1_MAX_GROUPS); return MO_RC_INVALID_ARGUMENT; }
     return rc;

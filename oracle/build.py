@@ -88,9 +88,23 @@ def build_usearch_ref(force=False):
     return out
 
 
+def build_mocl_ref(force=False):
+    """the reference's own CUDA kernels (cgo/cuda/mocl.cu:4-92: l2distance_f32/_f64[_const], one thread per row), compiled UNCHANGED for sm_100a into a
+    cubin.  The reference ships them as mocl_kernel64.fatbin loaded with cuModuleLoad (cgo/cuda/cuda.cpp:82-95); tools/ref_cuda_compare.py loads
+    this cubin the same way and times the kernels next to ours (SURVEY.md section 2.3 bar (ii))."""
+    out = os.path.join(REF_DIR, "mocl_sm100a.cubin")
+    src = os.path.join(REF, "cgo", "cuda", "mocl.cu")
+    if not os.path.exists(src):
+        return out if os.path.exists(out) else None
+    if force or _newer(out, [src]):
+        os.makedirs(REF_DIR, exist_ok=True)
+        _run([os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc"), "-cubin", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, src])
+    return out
+
+
 def build_all(force=False, verbose=False):
     res = {"oracle_go": build_oracle_go(force)}
-    for name, fn in (("mo_ref", build_mo_ref), ("usearch_ref", build_usearch_ref)):
+    for name, fn in (("mo_ref", build_mo_ref), ("usearch_ref", build_usearch_ref), ("mocl_ref", build_mocl_ref)):
         try:
             res[name] = fn(force)
         except Exception as e:  # the reference libs are optional strengthening, the restatement is not

@@ -61,20 +61,64 @@ def test_q6_predicate_edges(gpu):
     assert got[1] == ns == 3 and got[0] == want
 
 
-def test_q6_rejects_nullable_and_short_columns(gpu):
-    from matrixone_b200.vector import Vector, xcall
-    n = 100
+def test_q6_nullable_columns_and_short_columns(gpu):
+    """nullable inputs take the generic fused operator (plan.cu): a NULL predicate operand rejects the row, a NULL product is skipped by SUM;
+    an all-zero bitmap gives the no-nulls answer; short columns are rejected"""
+    from matrixone_b200.vector import Vector, bitmap_from_bools, xcall
+    n = 100_000
     cols = datagen.lineitem(1, 0, n)
-    res = np.zeros(2)
-    p = capi.Q6Params(*datagen.q6_params())
+    P = datagen.q6_params()
+    res = np.zeros(2); rn = np.zeros(1, dtype=np.uint64)
+    p = capi.Q6Params(*P)
     pv = Vector(data=np.frombuffer(bytes(p), dtype=np.uint8).copy(), length=1)
-    bad = Vector(data=cols["shipdate"], nulls=np.zeros(2, dtype=np.uint64), length=n)
-    rc, msg = xcall(capi.XCALL_Q6_FILTER_SUM, [Vector(data=res, length=1), bad, Vector(data=cols["discount"]), Vector(data=cols["quantity"]),
-                                               Vector(data=cols["extendedprice"]), pv], n, raise_on_error=False)
-    assert rc == capi.RC_INVALID_ARGUMENT and "nullable" in msg
+    want = ops.q6_filter_sum(cols["shipdate"], cols["discount"], cols["quantity"], cols["extendedprice"], n, *P)
+    zero = np.zeros((n + 63) // 64, dtype=np.uint64)
+    xcall(capi.XCALL_Q6_FILTER_SUM, [Vector(data=res, nulls=rn, length=1), Vector(data=cols["shipdate"], nulls=zero, length=n), Vector(data=cols["discount"], length=n),
+                                     Vector(data=cols["quantity"], length=n), Vector(data=cols["extendedprice"], length=n), pv], n)
+    assert int(res.view(np.int64)[1]) == want[1] and abs(res[0] - want[0]) <= 1e-12 * abs(want[0])
+    rng = np.random.default_rng(0)
+    sdn = rng.random(n) < 0.2; prn = rng.random(n) < 0.2
+    xcall(capi.XCALL_Q6_FILTER_SUM, [Vector(data=res, nulls=rn, length=1), Vector(data=cols["shipdate"], nulls=bitmap_from_bools(sdn), length=n), Vector(data=cols["discount"], length=n),
+                                     Vector(data=cols["quantity"], length=n), Vector(data=cols["extendedprice"], nulls=bitmap_from_bools(prn), length=n), pv], n)
+    m = (cols["shipdate"] >= P[0]) & (cols["shipdate"] < P[1]) & (cols["discount"] >= P[2]) & (cols["discount"] <= P[3]) & (cols["quantity"] < P[4]) & ~sdn
+    assert int(res.view(np.int64)[1]) == int(m.sum())                                   # rows that pass the filter
+    ref = float((cols["extendedprice"][m & ~prn] * cols["discount"][m & ~prn]).sum())     # SUM skips the NULL prices
+    assert abs(res[0] - ref) <= 1e-11 * abs(ref)
     rc, msg = xcall(capi.XCALL_Q6_FILTER_SUM, [Vector(data=res, length=1), Vector(data=cols["shipdate"]), Vector(data=cols["discount"][:50]),
                                                Vector(data=cols["quantity"]), Vector(data=cols["extendedprice"]), pv], n, raise_on_error=False)
     assert rc == capi.RC_INVALID_ARGUMENT
+
+
+def test_q1_nullable_columns(gpu):
+    """Q1 with nulls bitmaps: NULL shipdate rejects the row, NULL measures are skipped by their own aggregate only (count(*) still counts), a NULL
+    key forms its own group"""
+    from matrixone_b200.vector import Vector, bitmap_from_bools, xcall
+    import ctypes as C
+    n = 200_000
+    cols = datagen.lineitem(3, 0, n)
+    rng = np.random.default_rng(1)
+    nm = {k: rng.random(n) < 0.1 for k in ("shipdate", "quantity", "discount", "returnflag")}
+    names = ("shipdate", "quantity", "extendedprice", "discount", "tax", "returnflag", "linestatus")
+    vecs = [Vector(data=cols[k], nulls=bitmap_from_bools(nm[k]) if k in nm else None, length=n) for k in names]
+    res = np.zeros(C.sizeof(capi.Q1Result), dtype=np.uint8)
+    xcall(capi.XCALL_Q1_GROUP_AGG, [Vector(data=res, length=1)] + vecs + [Vector(data=np.asarray([datagen.Q1_CUTOFF], dtype=np.int32), length=1)], n)
+    got = ops.q1_result_from_bytes(res.tobytes())
+    sel = (cols["shipdate"] <= datagen.Q1_CUTOFF) & ~nm["shipdate"]
+    rf = np.where(nm["returnflag"], 0, cols["returnflag"])
+    seen = {}
+    for g in got:
+        k = (g["returnflag"], g["linestatus"])
+        m = sel & (rf == k[0]) & (cols["linestatus"] == k[1]) & (nm["returnflag"] == (k[0] == 0))
+        assert g["count_order"] == int(m.sum()) and g["first_row"] == int(np.flatnonzero(m)[0]), k
+        q = cols["quantity"][m & ~nm["quantity"]]
+        assert abs(g["sum_qty"] - q.sum()) <= 1e-11 * q.sum() and abs(g["avg_qty"] - q.mean()) <= 1e-11 * q.mean()
+        dm = m & ~nm["discount"]
+        dp = (cols["extendedprice"][dm] * (1 - cols["discount"][dm])).sum()
+        assert abs(g["sum_disc_price"] - dp) <= 1e-11 * dp
+        assert abs(g["sum_base_price"] - cols["extendedprice"][m].sum()) <= 1e-11 * cols["extendedprice"][m].sum()
+        seen[k] = True
+    assert sum(g["count_order"] for g in got) == int(sel.sum()) and any(k[0] == 0 for k in seen)
+    assert [g["first_row"] for g in got] == sorted(g["first_row"] for g in got)
 
 
 def _check_q1(got, want):
@@ -185,3 +229,24 @@ def test_q1_non_finite_values_stay_inside_their_group(gpu):
                 assert (np.isnan(g[k]) and np.isnan(w[k])) or g[k] == w[k], (chr(g["returnflag"]), k, g[k], w[k])
     a = [g for g in got if g["returnflag"] == ord("A")][0]
     assert np.isinf(a["sum_qty"]) and np.isnan(a["sum_charge"])
+
+
+@pytest.mark.parametrize("variant", [3, 5, 6, 7])
+def test_q1_kernel_variants_agree(gpu, variant):
+    """the cp.async-staged (3, 4 stages) and the bulk-copy / TMA staged (5, 6, 7 = 3, 4, 6 stages) Q1 kernels give the default kernel's result:
+    same groups, counts and first rows; sums to the last few bits (per-thread row sets are identical, so in fact bitwise)"""
+    n = 5_000_011
+    bufs = dev_lineitem(gpu, 10, n)
+    args = [bufs[k] for k in ("shipdate", "quantity", "extendedprice", "discount", "tax", "returnflag", "linestatus")]
+    want = ops.q1_group_agg(*args, n, datagen.Q1_CUTOFF)
+    try:
+        assert gpu.MoB200_SetTuning(b"q1_variant", variant) == 0
+        got = ops.q1_group_agg(*args, n, datagen.Q1_CUTOFF)
+    finally:
+        gpu.MoB200_SetTuning(b"q1_variant", 0)
+    assert [(g["returnflag"], g["linestatus"], g["count_order"], g["first_row"]) for g in got] == [(g["returnflag"], g["linestatus"], g["count_order"], g["first_row"]) for g in want]
+    for a, b in zip(got, want):
+        for f in ("sum_qty", "sum_base_price", "sum_disc_price", "sum_charge", "avg_disc"):
+            assert abs(a[f] - b[f]) <= 1e-12 * abs(b[f])
+    for b in bufs.values():
+        b.free()
