@@ -129,11 +129,31 @@ __device__ Rec block_reduce(Rec r) {
     return r;  // valid in warp 0
 }
 
+struct Seg { __int128 total, maxp, minp; };
+enum Cls { C_SIGNED = 0, C_UNSIGNED = 1, C_FLOAT = 2, C_MINMAX = 3, C_COUNT = 4 };
+// asynchronous form: the last CTA writes the caller's device-resident result / partial state itself (no second launch)
+struct AggStateOut { uint64_t *res; uint64_t res_words; uint64_t *rnulls; int op; int cls; };
+
+__device__ __forceinline__ void write_agg_state(const Rec &rec, const AggStateOut &so, int32_t ov) {
+    uint64_t bits = 0, cnt = rec.cnt; int64_t rc = MO_RC_SUCCESS; const bool isnull = cnt == 0;
+    double dsum = 0.0;
+    if (so.cls == C_SIGNED) { bits = rec.w0; dsum = (double)(int64_t)rec.w0; if (ov) rc = MO_RC_OUT_OF_RANGE; }
+    else if (so.cls == C_UNSIGNED) { bits = rec.w0; dsum = (double)rec.w0; if (rec.w1) rc = MO_RC_OUT_OF_RANGE; }
+    else if (so.cls == C_FLOAT) { dsum = rec.d; memcpy(&bits, &dsum, 8); }
+    else bits = rec.w0;
+    // a 1-word result of AVG is the final value; a 3-word result is the partial STATE (sum in the SUM return type, count, rc) and AVG divides at the merge
+    if (so.op == MO_AGG_AVG && so.res_words < 3 && !isnull) { double avg = dsum / (double)cnt; memcpy(&bits, &avg, 8); }
+    so.res[0] = bits;
+    if (so.res_words >= 2) so.res[1] = cnt;
+    if (so.res_words >= 3) so.res[2] = (uint64_t)rc;
+    if (so.rnulls) so.rnulls[0] = isnull ? 1ull : 0ull;
+}
+
 // col must be 16-byte aligned for the vector path (vec = true); rows are [0, n).
 template <typename T, int KIND>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 agg_kernel(const T *__restrict__ col, const uint64_t *__restrict__ nulls, uint64_t n, bool vec,
-           Rec *__restrict__ partials, Rec *__restrict__ out, unsigned *ticket) {
+           Rec *__restrict__ partials, Rec *__restrict__ out, unsigned *ticket, AggStateOut so) {
     constexpr int V = 16 / sizeof(T);  // rows per 128-bit load
     Acc<T, KIND> acc;
     const uint64_t tid = blockIdx.x * (uint64_t)kThreads + threadIdx.x;
@@ -197,13 +217,44 @@ agg_kernel(const T *__restrict__ col, const uint64_t *__restrict__ nulls, uint64
             }
             *out = fr;
         }
+        if (so.res) {
+            // signed SUM whose magnitudes do not fit int64 (pathological): the exact serial-order prefix check, done by this CTA alone --
+            // thread k summarises rows [k * seg, (k + 1) * seg) as (total, max prefix, min prefix), thread 0 folds the 256 summaries in order
+            __shared__ Seg sseg[KIND == K_SUM_SIGNED ? kThreads : 1];
+            __shared__ Rec sfr;
+            __shared__ int32_t sov;
+            if (threadIdx.x == 0) { sfr = fr; sov = 0; }
+            __syncthreads();
+            if (KIND == K_SUM_SIGNED && (sfr.w3 != 0 || sfr.w2 > (uint64_t)INT64_MAX)) {
+                const uint64_t seg = (n + kThreads - 1) / kThreads;
+                const uint64_t r0 = (uint64_t)threadIdx.x * seg, r1 = r0 + seg < n ? r0 + seg : n;
+                __int128 tot = 0, mx = 0, mn = 0;
+                for (uint64_t i = r0; i < r1; i++) {
+                    if (bm_test(nulls, i)) continue;
+                    tot += (__int128)(int64_t)col[i];
+                    if (tot > mx) mx = tot;
+                    if (tot < mn) mn = tot;
+                }
+                sseg[threadIdx.x].total = tot; sseg[threadIdx.x].maxp = mx; sseg[threadIdx.x].minp = mn;
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    __int128 run = 0;
+                    const __int128 hi = (__int128)INT64_MAX, lo = (__int128)INT64_MIN;
+                    for (int k = 0; k < kThreads; k++) {
+                        if (run + sseg[k].maxp > hi || run + sseg[k].minp < lo) { sov = 1; break; }
+                        run += sseg[k].total;
+                    }
+                }
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) write_agg_state(sfr, so, sov);
+        }
     }
 }
 
 // ---- exact serial-order overflow check for SUM over signed ints (slow path, rare) ---------------------------------
 // Go errors at the first row whose running sum leaves int64 (int64OfCheck, sumavg2.go:89-94).  Each thread summarises a
 // contiguous segment as (total, max prefix, min prefix) in 128-bit; segments are then folded in row order.
-struct Seg { __int128 total, maxp, minp; };
 
 // `gate` (async path): the aggregate record of the same call; when its magnitude sum fits int64 no prefix can overflow and the
 // whole grid returns at once
@@ -238,7 +289,7 @@ __global__ void prefix_fold_kernel(const Seg *segs, uint64_t nseg, int32_t *over
 }
 
 template <typename T, int KIND>
-int launch_agg(ThreadCtx &t, const void *dcol, const uint64_t *dnulls, uint64_t n, Rec *hrec, Rec **drec = nullptr) {
+int launch_agg(ThreadCtx &t, const void *dcol, const uint64_t *dnulls, uint64_t n, Rec *hrec, Rec **drec = nullptr, AggStateOut so = AggStateOut{nullptr, 0, nullptr, 0, 0}) {
     int grid = num_sms() * kCtasPerSm;
     uint64_t work = (n + (16 / sizeof(T)) * kThreads - 1) / ((16 / sizeof(T)) * kThreads);
     if ((uint64_t)grid > work) grid = work ? (int)work : 1;
@@ -247,7 +298,7 @@ int launch_agg(ThreadCtx &t, const void *dcol, const uint64_t *dnulls, uint64_t 
     Rec *out = partials + grid;
     bool vec = (((uintptr_t)dcol) & 15) == 0;
     cudaEventRecord(t.kev0, t.stream);
-    agg_kernel<T, KIND><<<grid, kThreads, 0, t.stream>>>((const T *)dcol, dnulls, n, vec, partials, out, t.ctrl);
+    agg_kernel<T, KIND><<<grid, kThreads, 0, t.stream>>>((const T *)dcol, dnulls, n, vec, partials, out, t.ctrl, so);
     cudaEventRecord(t.kev1, t.stream);
     MOB_LAUNCH_CHECK();
     if (drec) { *drec = out; return MO_RC_SUCCESS; }   // async: the record stays on the device
@@ -342,8 +393,6 @@ __global__ void popcount_kernel(const uint64_t *p, uint64_t nbits, unsigned long
 // When the column AND the result vector live in device memory the call only enqueues work on the calling thread's stream: no host
 // read-back, no synchronisation.  A 1-thread kernel turns the aggregate record into the caller's result words.  This is what lets a
 // multi-GPU caller hand the partial state straight to NCCL (MergeGroup seam, mergeGroup.go:132-247) and merge on the device.
-enum Cls { C_SIGNED = 0, C_UNSIGNED = 1, C_FLOAT = 2, C_MINMAX = 3, C_COUNT = 4 };
-
 __global__ void agg_state_kernel(const Rec *rec, int op, int cls, uint64_t len, const unsigned long long *nullcount, const Seg *segs, uint64_t nseg,
                                  uint64_t *res, uint64_t res_words, uint64_t *rnulls) {
     uint64_t bits = 0, cnt = 0; int64_t rc = MO_RC_SUCCESS; bool isnull = false;
@@ -378,26 +427,14 @@ __global__ void agg_state_kernel(const Rec *rec, int op, int cls, uint64_t len, 
 }
 
 template <typename T>
-static int agg_async_typed(ThreadCtx &t, int op, int cls, const void *dcol, const uint64_t *dnulls, uint64_t n, Rec **drec, Seg **dsegs, uint64_t *nseg_out) {
-    *dsegs = nullptr; *nseg_out = 0;
-    if (op == MO_AGG_MIN) return launch_agg<T, K_MIN>(t, dcol, dnulls, n, nullptr, drec);
-    if (op == MO_AGG_MAX) return launch_agg<T, K_MAX>(t, dcol, dnulls, n, nullptr, drec);
-    if (cls == C_FLOAT) return launch_agg<T, K_SUM_FLOAT>(t, dcol, dnulls, n, nullptr, drec);
-    if (cls == C_UNSIGNED) return launch_agg<T, K_SUM_UNSIGNED>(t, dcol, dnulls, n, nullptr, drec);
-    int rc = launch_agg<T, K_SUM_SIGNED>(t, dcol, dnulls, n, nullptr, drec);
-    if (rc) return rc;
-    // the exact serial-order prefix check runs only when the device-side gate says the magnitudes do not fit int64: the gated segment
-    // kernel is enqueued, the 1-thread state kernel folds the segments (one launch less than the synchronous form)
-    const uint64_t nseg_target = (uint64_t)num_sms() * 256;
-    uint64_t seg_rows = (n + nseg_target - 1) / nseg_target;
-    if (seg_rows < 64) seg_rows = 64;
-    const uint64_t nseg = (n + seg_rows - 1) / seg_rows;
-    Seg *segs = (Seg *)arena_alloc(t, sizeof(Seg) * nseg + 16);
-    if (!segs) return MO_RC_INTERNAL_ERROR;
-    prefix_seg_kernel<T><<<(unsigned)((nseg + 255) / 256), 256, 0, t.stream>>>((const T *)dcol, dnulls, n, seg_rows, nseg, segs, *drec);
-    MOB_LAUNCH_CHECK();
-    *dsegs = segs; *nseg_out = nseg;
-    return MO_RC_SUCCESS;
+static int agg_async_typed(ThreadCtx &t, int op, int cls, const void *dcol, const uint64_t *dnulls, uint64_t n, Rec **drec, AggStateOut so) {
+    // ONE launch: the last CTA of the aggregate kernel writes the caller's result / state (and, for a signed SUM whose magnitudes do not fit
+    // int64, runs the exact serial-order check itself)
+    if (op == MO_AGG_MIN) return launch_agg<T, K_MIN>(t, dcol, dnulls, n, nullptr, drec, so);
+    if (op == MO_AGG_MAX) return launch_agg<T, K_MAX>(t, dcol, dnulls, n, nullptr, drec, so);
+    if (cls == C_FLOAT) return launch_agg<T, K_SUM_FLOAT>(t, dcol, dnulls, n, nullptr, drec, so);
+    if (cls == C_UNSIGNED) return launch_agg<T, K_SUM_UNSIGNED>(t, dcol, dnulls, n, nullptr, drec, so);
+    return launch_agg<T, K_SUM_SIGNED>(t, dcol, dnulls, n, nullptr, drec, so);
 }
 
 static int xcall_agg_async(ThreadCtx &t, int op, int T, mo_xcall_args_t *args, uint64_t len) {
@@ -405,7 +442,8 @@ static int xcall_agg_async(ThreadCtx &t, int op, int T, mo_xcall_args_t *args, u
     const uint64_t *dnulls = args[1].pnulls;
     const bool is_signed = T >= MO_T_INT8 && T <= MO_T_INT64, is_unsigned = T >= MO_T_UINT8 && T <= MO_T_UINT64;
     const bool is_float = T == MO_T_FLOAT32 || T == MO_T_FLOAT64;
-    Rec *drec = nullptr; Seg *dsegs = nullptr; uint64_t nseg = 0; unsigned long long *dcount = nullptr;
+    Rec *drec = nullptr; unsigned long long *dcount = nullptr;
+    bool state_written = false;
     int cls, rc = MO_RC_SUCCESS;
     Rec *zero = (Rec *)arena_alloc(t, sizeof(Rec));
     if (!zero) return MO_RC_INTERNAL_ERROR;
@@ -425,24 +463,28 @@ static int xcall_agg_async(ThreadCtx &t, int op, int T, mo_xcall_args_t *args, u
         const bool mm = op == MO_AGG_MIN || op == MO_AGG_MAX;
         cls = mm ? C_MINMAX : is_signed ? C_SIGNED : is_unsigned ? C_UNSIGNED : C_FLOAT;
         if (!mm && !is_signed && !is_unsigned && !is_float) { set_error("sum: unsupported type %d", T); return MO_RC_INVALID_ARGUMENT; }
+        const AggStateOut so{(uint64_t *)args[0].pdata, args[0].dataSz / 8, args[0].pnulls, op, cls};
+        state_written = len != 0;
         if (len == 0) { MOB_CUDA_TRY(cudaMemsetAsync(zero, 0, sizeof(Rec), t.stream)); drec = zero; }
         else switch (T) {
-        case MO_T_BOOL: case MO_T_UINT8: rc = agg_async_typed<uint8_t>(t, op, cls, dcol, dnulls, len, &drec, &dsegs, &nseg); break;
-        case MO_T_INT8: rc = agg_async_typed<int8_t>(t, op, cls, dcol, dnulls, len, &drec, &dsegs, &nseg); break;
-        case MO_T_INT16: rc = agg_async_typed<int16_t>(t, op, cls, dcol, dnulls, len, &drec, &dsegs, &nseg); break;
-        case MO_T_UINT16: rc = agg_async_typed<uint16_t>(t, op, cls, dcol, dnulls, len, &drec, &dsegs, &nseg); break;
-        case MO_T_INT32: case MO_T_DATE: rc = agg_async_typed<int32_t>(t, op, cls, dcol, dnulls, len, &drec, &dsegs, &nseg); break;
-        case MO_T_UINT32: rc = agg_async_typed<uint32_t>(t, op, cls, dcol, dnulls, len, &drec, &dsegs, &nseg); break;
-        case MO_T_INT64: case MO_T_TIME: case MO_T_DATETIME: case MO_T_TIMESTAMP: rc = agg_async_typed<int64_t>(t, op, cls, dcol, dnulls, len, &drec, &dsegs, &nseg); break;
-        case MO_T_UINT64: rc = agg_async_typed<uint64_t>(t, op, cls, dcol, dnulls, len, &drec, &dsegs, &nseg); break;
-        case MO_T_FLOAT32: rc = agg_async_typed<float>(t, op, cls, dcol, dnulls, len, &drec, &dsegs, &nseg); break;
-        case MO_T_FLOAT64: rc = agg_async_typed<double>(t, op, cls, dcol, dnulls, len, &drec, &dsegs, &nseg); break;
+        case MO_T_BOOL: case MO_T_UINT8: rc = agg_async_typed<uint8_t>(t, op, cls, dcol, dnulls, len, &drec, so); break;
+        case MO_T_INT8: rc = agg_async_typed<int8_t>(t, op, cls, dcol, dnulls, len, &drec, so); break;
+        case MO_T_INT16: rc = agg_async_typed<int16_t>(t, op, cls, dcol, dnulls, len, &drec, so); break;
+        case MO_T_UINT16: rc = agg_async_typed<uint16_t>(t, op, cls, dcol, dnulls, len, &drec, so); break;
+        case MO_T_INT32: case MO_T_DATE: rc = agg_async_typed<int32_t>(t, op, cls, dcol, dnulls, len, &drec, so); break;
+        case MO_T_UINT32: rc = agg_async_typed<uint32_t>(t, op, cls, dcol, dnulls, len, &drec, so); break;
+        case MO_T_INT64: case MO_T_TIME: case MO_T_DATETIME: case MO_T_TIMESTAMP: rc = agg_async_typed<int64_t>(t, op, cls, dcol, dnulls, len, &drec, so); break;
+        case MO_T_UINT64: rc = agg_async_typed<uint64_t>(t, op, cls, dcol, dnulls, len, &drec, so); break;
+        case MO_T_FLOAT32: rc = agg_async_typed<float>(t, op, cls, dcol, dnulls, len, &drec, so); break;
+        case MO_T_FLOAT64: rc = agg_async_typed<double>(t, op, cls, dcol, dnulls, len, &drec, so); break;
         default: set_error("agg: unsupported type %d", T); return MO_RC_INVALID_ARGUMENT;
         }
         if (rc) return rc;
     } else { set_error("agg: unknown op %d", op); return MO_RC_INVALID_ARGUMENT; }
-    agg_state_kernel<<<1, 1, 0, t.stream>>>(drec, op, cls, len, dcount, dsegs, nseg, (uint64_t *)args[0].pdata, args[0].dataSz / 8, args[0].pnulls);
-    MOB_LAUNCH_CHECK();
+    if (!state_written) {   // COUNT, or an empty column
+        agg_state_kernel<<<1, 1, 0, t.stream>>>(drec, op, cls, len, dcount, nullptr, 0, (uint64_t *)args[0].pdata, args[0].dataSz / 8, args[0].pnulls);
+        MOB_LAUNCH_CHECK();
+    }
     arena_reset(t);   // stream order protects the scratch: the next call's kernels queue behind these
     return MO_RC_SUCCESS;
 }

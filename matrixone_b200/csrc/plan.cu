@@ -19,13 +19,15 @@
 // Group sums are accumulated with atomics: the association order is not fixed (results agree with the serial loop to ~1e-13).
 #include "common.cuh"
 #include <cstring>
+#include <vector>
 
 using namespace mob;
 
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kCtaSlots = 256;          // per-CTA group table
+constexpr int kCtaSlots = 128;          // per-CTA group table (shared atomics)
+constexpr int kPriv = 4;               // groups whose state every thread keeps PRIVATELY in shared memory (no atomics, no shuffles)
 constexpr uint64_t kEmptyKey = 0xffffffffffffffffull;
 
 struct PlanCols { const uint8_t *data[MO_PLAN_MAX_COLS]; const uint64_t *nulls[MO_PLAN_MAX_COLS]; };
@@ -132,16 +134,46 @@ plan_kernel(const mo_plan_t *__restrict__ Pg, PlanCols C, uint64_t n, PlanGlobal
         tkey[s] = kEmptyKey; tfirst[s] = ~0ull; trows[s] = 0;
         for (int a = 0; a < naggs; a++) { tacc[s * naggs + a] = agg_identity(P.agg[a].kind); tcnt[s * naggs + a] = 0; }
     }
+    // The first kPriv distinct keys a CTA meets (a first-come dictionary, as in the Q1 kernel) get PRIVATE per-thread state in shared memory,
+    // slot-major so every access is conflict-free: a row then costs naggs x (LDS, op, STS) on its own copy -- no atomics, no shuffles.  Plans
+    // with few groups (or none) live entirely here; further keys go to the shared CTA table, then to the global one.
+    __shared__ unsigned long long pdict[kPriv];
+    double *pacc = reinterpret_cast<double *>(tcnt + (size_t)kCtaSlots * naggs) + threadIdx.x;   // [(slot * naggs + a) * kThreads + tid]
+    unsigned *pcnt = reinterpret_cast<unsigned *>(pacc - threadIdx.x + (size_t)kPriv * naggs * kThreads) + threadIdx.x;   // same indexing
+    unsigned *prows = pcnt - threadIdx.x + (size_t)kPriv * naggs * kThreads + threadIdx.x;       // [slot * kThreads + tid]
+    unsigned long long *pfirst = reinterpret_cast<unsigned long long *>(prows - threadIdx.x + (size_t)kPriv * kThreads) + threadIdx.x;
+    if (threadIdx.x < kPriv) pdict[threadIdx.x] = kEmptyKey;
+    for (int g = 0; g < kPriv; g++) {
+        for (int a = 0; a < naggs; a++) { pacc[(g * naggs + a) * kThreads] = agg_identity(P.agg[a].kind); pcnt[(g * naggs + a) * kThreads] = 0u; }
+        prows[g * kThreads] = 0u; pfirst[g * kThreads] = ~0ull;
+    }
+    unsigned long long dk[kPriv];
+#pragma unroll
+    for (int g = 0; g < kPriv; g++) dk[g] = kEmptyKey;
+    bool dict_full = false;
     __syncthreads();
     double *my = vreg + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * kThreads;
-    for (uint64_t r = blockIdx.x * (uint64_t)kThreads + threadIdx.x; r < n; r += stride) {
-        // ---- table scan: every referenced column value -> register-file slot c, null-ness -> bit c
-        unsigned nullbits = 0;
-        for (int c = 0; c < P.ncols; c++) {
-            my[c * kThreads] = load_as_f64(C.data[c], P.col_type[c], r);
-            if (C.nulls[c] && ((C.nulls[c][r >> 6] >> (r & 63)) & 1ull)) nullbits |= 1u << c;
+    // software prefetch: the column values of the NEXT row of this thread are loaded while the current row is evaluated (twice the bytes in flight)
+    double nxt[MO_PLAN_MAX_COLS]; unsigned nxtnull = 0;
+    auto fetch = [&](uint64_t r) {
+        nxtnull = 0;
+#pragma unroll
+        for (int c = 0; c < MO_PLAN_MAX_COLS; c++) {
+            if (c < P.ncols) {
+                nxt[c] = load_as_f64(C.data[c], P.col_type[c], r);
+                if (C.nulls[c] && ((C.nulls[c][r >> 6] >> (r & 63)) & 1ull)) nxtnull |= 1u << c;
+            }
         }
+    };
+    uint64_t r = blockIdx.x * (uint64_t)kThreads + threadIdx.x;
+    if (r < n) fetch(r);
+    for (; r < n; r += stride) {
+        // ---- table scan: every referenced column value -> register-file slot c, null-ness -> bit c
+        unsigned nullbits = nxtnull;
+#pragma unroll
+        for (int c = 0; c < MO_PLAN_MAX_COLS; c++) if (c < P.ncols) my[c * kThreads] = nxt[c];
+        if (r + stride < n) fetch(r + stride);
         // ---- filter: conjunction; a NULL operand makes the conjunct not-true (filter.go:125-141 keeps rows with !null && true)
         bool ok = true;
         for (int j = 0; j < P.npreds; j++) {
@@ -192,6 +224,42 @@ plan_kernel(const mo_plan_t *__restrict__ Pg, PlanCols C, uint64_t n, PlanGlobal
                 off += sz;
             }
         }
+        const uint64_t grow = (uint64_t)P.row_base + r;
+        // ---- private dictionary (first kPriv keys of this CTA)
+        int ps = -1;
+#pragma unroll
+        for (int g = 0; g < kPriv; g++) if (dk[g] == key) ps = g;
+        if (ps < 0 && !dict_full && key != kEmptyKey) {
+            // claim or find the key in the shared dictionary, then refresh the register copy
+            bool okc = false;
+#pragma unroll
+            for (int g = 0; g < kPriv; g++) {
+                const unsigned long long prev = okc ? key : atomicCAS(&pdict[g], (unsigned long long)kEmptyKey, (unsigned long long)key);
+                okc = okc || prev == kEmptyKey || prev == key;
+            }
+            bool full = true;
+#pragma unroll
+            for (int g = 0; g < kPriv; g++) { dk[g] = ((volatile unsigned long long *)pdict)[g]; full = full && dk[g] != kEmptyKey; if (dk[g] == key) ps = g; }
+            dict_full = full;
+        }
+        if (ps >= 0) {
+            prows[ps * kThreads] += 1u;
+            if (pfirst[ps * kThreads] == ~0ull) pfirst[ps * kThreads] = grow;     // a thread meets its rows in increasing order
+            for (int a = 0; a < naggs; a++) {
+                const int vs = P.agg[a].value, kind = P.agg[a].kind;
+                if (vs >= 0 && ((nullbits >> vs) & 1u)) continue;
+                const int ix = (ps * naggs + a) * kThreads;
+                pcnt[ix] += 1u;
+                if (vs < 0) continue;
+                const double v = my[vs * kThreads];
+                if (kind == MO_AGG_SUM || kind == MO_AGG_AVG) pacc[ix] = __dadd_rn(pacc[ix], v);
+                else if (v == v) {
+                    const unsigned long long kv = flt_key(v), cur = (unsigned long long)__double_as_longlong(pacc[ix]);
+                    if (kind == MO_AGG_MIN ? kv < cur : kv > cur) pacc[ix] = __longlong_as_double((long long)kv);
+                }
+            }
+            continue;
+        }
         // ---- group slot: CTA table first, global table when it is full
         int slot = -1;
         if (key != kEmptyKey) {
@@ -206,7 +274,6 @@ plan_kernel(const mo_plan_t *__restrict__ Pg, PlanCols C, uint64_t n, PlanGlobal
                 s = (s + 1) & (kCtaSlots - 1);
             }
         }
-        const uint64_t grow = (uint64_t)P.row_base + r;
         if (slot >= 0) {
             // warp pre-aggregation: the lanes of this warp that hit the same slot elect a leader, which adds the peers' values in lane
             // order and issues ONE atomic per aggregate -- with few groups (or none) the shared-memory atomics would otherwise serialise
@@ -249,8 +316,23 @@ plan_kernel(const mo_plan_t *__restrict__ Pg, PlanCols C, uint64_t n, PlanGlobal
             }
         }
     }
-    // ---- retire: fold the CTA table into the global one
+    // ---- retire: every thread folds its private states into the global table (at most kPriv x naggs atomics per thread, once)
     __syncthreads();
+    for (int g = 0; g < kPriv; g++) {
+        const unsigned long long pk = pdict[g];
+        if (pk == kEmptyKey || prows[g * kThreads] == 0u) continue;
+        const uint64_t gs = global_find(G, pk);
+        if (gs == ~0ull) continue;
+        atomicMin(&G.first_row[gs], pfirst[g * kThreads]);
+        atomicAdd(&G.rows[gs], (unsigned long long)prows[g * kThreads]);
+        for (int a = 0; a < naggs; a++) {
+            const int ix = (g * naggs + a) * kThreads;
+            if (pcnt[ix] == 0u) continue;
+            agg_fold(P.agg[a].kind, &G.acc[gs * naggs + a], pacc[ix]);
+            atomicAdd(&G.cnt[gs * naggs + a], (unsigned long long)pcnt[ix]);
+        }
+    }
+    // ---- and the shared CTA table
     for (int s = threadIdx.x; s < kCtaSlots; s += kThreads) {
         if (tkey[s] == kEmptyKey || trows[s] == 0) continue;
         const uint64_t gs = global_find(G, tkey[s]);
@@ -303,9 +385,142 @@ __global__ void plan_emit_kernel(PlanGlobal G, const mo_plan_t *P, const uint32_
     }
 }
 
+// ---- recognised shapes: the two hand-specialised instances of this operator (tpch.cu) ---------------------------------------------------
+// A descriptor that IS the Q6 shape  SUM(c3 * c1) WHERE c0 >= lo AND c0 < hi AND c1 BETWEEN a AND b AND c2 < q  over (DATE, f64, f64, f64)
+// or the Q1 shape (q1.sql: filter c0 <= cutoff, keys (c5, c6) uint8, the eight aggregates in select-list order) over non-nullable resident or
+// host columns runs the specialised kernel, which streams at the HBM roofline; the result is rewritten in this operator's record format.
+struct Q6Out { double sum; long long rows; };
+__global__ void plan_from_q6_kernel(const Q6Out *q, uint8_t *res) {
+    mo_plan_result_header_t *H = reinterpret_cast<mo_plan_result_header_t *>(res);
+    H->ngroups = q->rows ? 1 : 0; H->sorted = 1; H->overflow = 0; H->reserved = 0;
+    if (q->rows) {
+        mo_plan_group_t *g = reinterpret_cast<mo_plan_group_t *>(res + sizeof(mo_plan_result_header_t));
+        g->key = 0; g->first_row = -1; g->rows = q->rows;     // the specialised kernel does not track the first qualifying row
+        mo_plan_agg_value_t *a = reinterpret_cast<mo_plan_agg_value_t *>(g + 1);
+        a->value = q->sum; a->count = q->rows;
+    }
+}
+__global__ void plan_from_q1_kernel(const mo_q1_result_t *q, uint8_t *res, uint64_t res_groups, int *fallback) {
+    mo_plan_result_header_t *H = reinterpret_cast<mo_plan_result_header_t *>(res);
+    if (q->ngroups < 0 || (uint64_t)q->ngroups > res_groups) { *fallback = 1; return; }   // more than 8 groups: the generic path answers
+    *fallback = 0;
+    H->ngroups = q->ngroups; H->sorted = 1; H->overflow = 0; H->reserved = 0;
+    const size_t rec = sizeof(mo_plan_group_t) + 8 * sizeof(mo_plan_agg_value_t);
+    for (int64_t i = 0; i < q->ngroups; i++) {
+        const mo_q1_group_t &s = q->groups[i];
+        mo_plan_group_t *g = reinterpret_cast<mo_plan_group_t *>(res + sizeof(mo_plan_result_header_t) + rec * i);
+        g->key = (uint64_t)s.returnflag | ((uint64_t)s.linestatus << 8); g->first_row = s.first_row; g->rows = s.count_order;
+        mo_plan_agg_value_t *a = reinterpret_cast<mo_plan_agg_value_t *>(g + 1);
+        const double v[8] = {s.sum_qty, s.sum_base_price, s.sum_disc_price, s.sum_charge, s.avg_qty, s.avg_price, s.avg_disc, (double)s.count_order};
+        for (int k = 0; k < 8; k++) { a[k].value = v[k]; a[k].count = s.count_order; }
+    }
+}
+
+static bool is_q6_shape(const mo_plan_t &P) {
+    if (P.ncols != 4 || P.npreds != 4 || P.ninstr != 1 || P.nkeys != 0 || P.naggs != 1) return false;
+    if ((P.col_type[0] != MO_T_DATE && P.col_type[0] != MO_T_INT32) || P.col_type[1] != MO_T_FLOAT64 || P.col_type[2] != MO_T_FLOAT64 || P.col_type[3] != MO_T_FLOAT64) return false;
+    const mo_plan_pred_t *q = P.pred;
+    if (q[0].col != 0 || q[0].op != 3 || q[1].col != 0 || q[1].op != 4 || q[2].col != 1 || q[2].op != 6 || q[3].col != 2 || q[3].op != 4) return false;
+    if (q[0].lo != (double)(int32_t)q[0].lo || q[1].lo != (double)(int32_t)q[1].lo) return false;
+    const mo_plan_instr_t &m = P.instr[0];
+    if (m.op != MO_PLAN_OP_MUL || !((m.a == 3 && m.b == 1) || (m.a == 1 && m.b == 3))) return false;
+    return P.agg[0].kind == MO_AGG_SUM && P.agg[0].value == 4;
+}
+static bool is_q1_shape(const mo_plan_t &P) {
+    if (P.ncols != 7 || P.npreds != 1 || P.ninstr != 5 || P.nkeys != 2 || P.naggs != 8 || P.has_null_keys) return false;
+    if (P.col_type[0] != MO_T_DATE && P.col_type[0] != MO_T_INT32) return false;
+    for (int c = 1; c <= 4; c++) if (P.col_type[c] != MO_T_FLOAT64) return false;
+    if (P.col_type[5] != MO_T_UINT8 || P.col_type[6] != MO_T_UINT8 || P.key_col[0] != 5 || P.key_col[1] != 6) return false;
+    if (P.pred[0].col != 0 || P.pred[0].op != 5 || P.pred[0].lo != (double)(int32_t)P.pred[0].lo) return false;
+    const mo_plan_instr_t *in = P.instr;
+    if (in[0].op != MO_PLAN_OP_CONST || in[0].imm != 1.0) return false;
+    if (in[1].op != MO_PLAN_OP_SUB || in[1].a != 7 || in[1].b != 3) return false;
+    if (in[2].op != MO_PLAN_OP_MUL || in[2].a != 2 || in[2].b != 8) return false;
+    if (in[3].op != MO_PLAN_OP_ADD || in[3].a != 7 || in[3].b != 4) return false;
+    if (in[4].op != MO_PLAN_OP_MUL || in[4].a != 9 || in[4].b != 10) return false;
+    const int kind[8] = {MO_AGG_SUM, MO_AGG_SUM, MO_AGG_SUM, MO_AGG_SUM, MO_AGG_AVG, MO_AGG_AVG, MO_AGG_AVG, MO_AGG_COUNT};
+    const int val[8] = {1, 2, 9, 11, 1, 2, 3, -1};
+    for (int a = 0; a < 8; a++) if (P.agg[a].kind != kind[a] || P.agg[a].value != val[a]) return false;
+    return true;
+}
+
 }  // namespace
 
 namespace mob {
+
+int xcall_q6(mo_xcall_args_t *args, uint64_t len);
+int xcall_q1(mo_xcall_args_t *args, uint64_t len);
+extern int g_plan_specialise;   // MoB200_SetTuning("plan_specialise", 0) forces the interpreter (tests, profiling)
+
+// returns 1 when a specialised kernel answered (rc in *rc), 0 when the interpreter must run
+static int plan_try_specialised(ThreadCtx &t, const mo_plan_t &P, mo_xcall_args_t *args, uint64_t len, uint64_t res_groups, int *rc) {
+    if (!g_plan_specialise || len == 0) return 0;
+    for (int c = 0; c < P.ncols; c++) if (args[2 + c].pnulls) return 0;
+    const bool q6 = is_q6_shape(P), q1 = !q6 && is_q1_shape(P);
+    if (!q6 && !q1) return 0;
+    const bool dev_res = is_device_ptr(args[0].pdata);
+    bool dev_cols = true;
+    for (int c = 0; c < P.ncols; c++) dev_cols = dev_cols && is_device_ptr(args[2 + c].pdata);
+    const bool async = dev_res && dev_cols;
+    mo_xcall_args_t a[9]; memset(a, 0, sizeof a);
+    if (q6) {
+        mo_q6_params_t Q{(int32_t)P.pred[0].lo, (int32_t)P.pred[1].lo, P.pred[2].lo, P.pred[2].hi, P.pred[3].lo};
+        Q6Out hq{0.0, 0};
+        Q6Out *dq = async ? (Q6Out *)arena_alloc(t, sizeof(Q6Out)) : nullptr;
+        if (async && !dq) { *rc = MO_RC_INTERNAL_ERROR; return 1; }
+        a[0].pdata = async ? (uint8_t *)dq : (uint8_t *)&hq; a[0].dataSz = 16;
+        a[1] = args[2]; a[2] = args[3]; a[3] = args[4]; a[4] = args[5];
+        a[5].pdata = (uint8_t *)&Q; a[5].dataSz = sizeof Q;
+        *rc = xcall_q6(a, len);
+        if (*rc) return 1;
+        if (async) { plan_from_q6_kernel<<<1, 1, 0, t.stream>>>(dq, args[0].pdata); g_launches.fetch_add(1); return 1; }   // dq: arena memory, stream ordered
+        mo_plan_result_header_t H{hq.rows ? 1 : 0, 1, 0, 0};
+        struct { mo_plan_result_header_t h; mo_plan_group_t g; mo_plan_agg_value_t v; } R{H, {0, -1, hq.rows}, {hq.sum, hq.rows}};
+        const size_t bytes = hq.rows ? sizeof R : sizeof H;
+        if (dev_res) { *rc = cudaMemcpyAsync(args[0].pdata, &R, bytes, cudaMemcpyHostToDevice, t.stream) == cudaSuccess && cudaStreamSynchronize(t.stream) == cudaSuccess ? 0 : MO_RC_INTERNAL_ERROR; }
+        else memcpy(args[0].pdata, &R, bytes);
+        return 1;
+    }
+    if (res_groups < 1) return 0;
+    mo_q1_params_t Q{(int32_t)P.pred[0].lo, 0, P.row_base};
+    mo_q1_result_t hq; memset(&hq, 0, sizeof hq);
+    mo_q1_result_t *dq = async ? (mo_q1_result_t *)arena_alloc(t, sizeof(mo_q1_result_t) + 16) : nullptr;
+    if (async && !dq) { *rc = MO_RC_INTERNAL_ERROR; return 1; }
+    a[0].pdata = async ? (uint8_t *)dq : (uint8_t *)&hq; a[0].dataSz = sizeof(mo_q1_result_t);
+    for (int c = 0; c < 7; c++) a[1 + c] = args[2 + c];
+    a[6].dataSz = len; a[7].dataSz = len;     // packed uint8 keys: exactly len bytes (the Q1 entry point tells key layouts apart by size)
+    a[8].pdata = (uint8_t *)&Q; a[8].dataSz = sizeof Q;
+    *rc = xcall_q1(a, len);
+    if (async) {
+        if (*rc) return 1;
+        // more than 8 groups cannot be known without a read-back: the asynchronous form keeps the specialised kernel only when the caller's
+        // buffer could not hold more groups than it anyway; otherwise the interpreter runs
+        int *dflag = (int *)(dq + 1);
+        plan_from_q1_kernel<<<1, 1, 0, t.stream>>>(dq, args[0].pdata, res_groups, dflag);
+        g_launches.fetch_add(1);
+        int hflag = 0;
+        *rc = read_back(t, &hflag, dflag, 4);
+        return (*rc || !hflag) ? 1 : 0;
+    }
+    if (*rc == MO_RC_INVALID_ARGUMENT) { *rc = 0; return 0; }          // > 8 groups: the generic path answers
+    if (*rc) return 1;
+    if ((uint64_t)hq.ngroups > res_groups) { *rc = 0; return 0; }
+    const size_t rec = sizeof(mo_plan_group_t) + 8 * sizeof(mo_plan_agg_value_t);
+    std::vector<uint8_t> buf(sizeof(mo_plan_result_header_t) + rec * (size_t)hq.ngroups);
+    mo_plan_result_header_t H{hq.ngroups, 1, 0, 0};
+    memcpy(buf.data(), &H, sizeof H);
+    for (int64_t i = 0; i < hq.ngroups; i++) {
+        const mo_q1_group_t &s = hq.groups[i];
+        mo_plan_group_t g{(uint64_t)s.returnflag | ((uint64_t)s.linestatus << 8), s.first_row, s.count_order};
+        const double v[8] = {s.sum_qty, s.sum_base_price, s.sum_disc_price, s.sum_charge, s.avg_qty, s.avg_price, s.avg_disc, (double)s.count_order};
+        uint8_t *p = buf.data() + sizeof H + rec * (size_t)i;
+        memcpy(p, &g, sizeof g);
+        for (int k = 0; k < 8; k++) { mo_plan_agg_value_t av{v[k], s.count_order}; memcpy(p + sizeof g + k * sizeof av, &av, sizeof av); }
+    }
+    if (dev_res) { *rc = cudaMemcpyAsync(args[0].pdata, buf.data(), buf.size(), cudaMemcpyHostToDevice, t.stream) == cudaSuccess && cudaStreamSynchronize(t.stream) == cudaSuccess ? 0 : MO_RC_INTERNAL_ERROR; }
+    else memcpy(args[0].pdata, buf.data(), buf.size());
+    return 1;
+}
 
 // MO_XCALL_PLAN: args [0] result buffer ; [1] mo_plan_t (host) ; [2 .. 2 + ncols) the columns (+pnulls).  len = rows.  See include/mo_b200.h.
 int xcall_plan(mo_xcall_args_t *args, uint64_t len) {
@@ -343,6 +558,7 @@ int xcall_plan(mo_xcall_args_t *args, uint64_t len) {
     const size_t rec = sizeof(mo_plan_group_t) + sizeof(mo_plan_agg_value_t) * (size_t)P.naggs;
     if (!args[0].pdata || args[0].dataSz < sizeof(mo_plan_result_header_t) + rec) { set_error("plan: result buffer too small for one group"); return MO_RC_INVALID_ARGUMENT; }
     const uint64_t res_groups = (args[0].dataSz - sizeof(mo_plan_result_header_t)) / rec;
+    { int src = 0; if (plan_try_specialised(t, P, args, len, res_groups, &src)) return src; }
     const bool dev_res = is_device_ptr(args[0].pdata);
     bool dev_cols = true;
     for (int c = 0; c < P.ncols; c++) dev_cols = dev_cols && (len == 0 || is_device_ptr(args[2 + c].pdata)) && (!args[2 + c].pnulls || is_device_ptr(args[2 + c].pnulls));
@@ -376,7 +592,8 @@ int xcall_plan(mo_xcall_args_t *args, uint64_t len) {
     const unsigned igrid = (unsigned)((cap + 1 + 255) / 256 > (uint64_t)num_sms() * 8 ? (uint64_t)num_sms() * 8 : (cap + 1 + 255) / 256);
     plan_init_kernel<<<igrid, 256, 0, t.stream>>>(G, P.naggs, dP);
     MOB_LAUNCH_CHECK();
-    const size_t smem = (size_t)(P.ncols + P.ninstr) * kThreads * 8 + (size_t)kCtaSlots * (24 + 16 * (size_t)P.naggs);
+    const size_t smem = (size_t)(P.ncols + P.ninstr) * kThreads * 8 + (size_t)kCtaSlots * (24 + 16 * (size_t)P.naggs) +
+                        (size_t)kPriv * kThreads * ((size_t)P.naggs * 12 + 12);
     static size_t attr_smem = 0;
     if (smem > attr_smem) { MOB_CUDA_TRY(cudaFuncSetAttribute(plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; }
     if (len) {

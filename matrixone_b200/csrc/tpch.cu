@@ -140,6 +140,41 @@ struct Q1Shared {
     unsigned slow;   // debug: dictionary slow-path entries
 };
 
+// Shared-memory accumulators (staged kernels, G = 4): the per-thread state acc[slot][5], cnt[slot], first[slot] lives in shared memory,
+// slot-major ([(slot * 5 + j) * threads + tid]: conflict-free whatever slot each lane uses), so a row costs 5 x (LDS, DADD, STS) on ITS
+// slot instead of 20 indicator-FMAs over all four: ncu put the register version at 2.87 G warp instructions per SF100 pass with the
+// issue slots 70 % busy -- instruction-bound, not HBM-bound.  Branch-free like the register version: rows that do not qualify add 0.0 to
+// slot 0.  acc + v is the same single rounding as before, so results are bit-identical.
+template <int kT>
+struct Q1SmemAcc {
+    double *acc; unsigned *cnt; unsigned *first;   // bases already offset by tid
+    static constexpr size_t kBytes = (size_t)kT * 4 * (kQ1Vals * 8 + 4 + 4);
+    __device__ __forceinline__ void bind(unsigned char *base, int tid) {
+        acc = reinterpret_cast<double *>(base) + tid;
+        cnt = reinterpret_cast<unsigned *>(base + (size_t)kT * 4 * kQ1Vals * 8) + tid;
+        first = cnt + (size_t)kT * 4;
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+#pragma unroll
+            for (int j = 0; j < kQ1Vals; j++) acc[(g * kQ1Vals + j) * kT] = 0.0;
+            cnt[g * kT] = 0u; first[g * kT] = 0xffffffffu;
+        }
+    }
+    __device__ __forceinline__ void add(int slot, bool m, uint64_t r, double q, double pr, double t2, double t4, double di) {
+        const int s = m ? slot : 0;
+        double *a = acc + (size_t)s * kQ1Vals * kT;
+        a[0] = __dadd_rn(a[0], m ? q : 0.0);
+        a[kT] = __dadd_rn(a[kT], m ? pr : 0.0);
+        a[2 * kT] = __dadd_rn(a[2 * kT], m ? t2 : 0.0);
+        a[3 * kT] = __dadd_rn(a[3 * kT], m ? t4 : 0.0);
+        a[4 * kT] = __dadd_rn(a[4 * kT], m ? di : 0.0);
+        const unsigned c = cnt[s * kT];
+        cnt[s * kT] = c + (m ? 1u : 0u);
+        const unsigned f = first[s * kT];
+        first[s * kT] = (m && c == 0u) ? (unsigned)r : f;     // rows of one launch are numbered below 2^32 (checked by the launcher)
+    }
+};
+
 // Per-thread aggregation state (registers).  Control flow of every method is WARP-UNIFORM: all 32 lanes call row() together
 // and the dictionary slow path is taken by the whole warp (ballot + one elected lane doing the CAS).  A first version let
 // lanes diverge inside the insert loop; some warps then never reconverged and ran ~8x slower to the end of the kernel.
@@ -193,6 +228,29 @@ struct Q1Thread {
             miss = __ballot_sync(0xffffffffu, !settled);
         }
         return slot;
+    }
+
+    // shared-memory accumulator form of row(): same dictionary, same products, 15 accumulate instructions instead of ~44
+    template <int kT>
+    __device__ __forceinline__ void row_smem(Q1SmemAcc<kT> &A, uint64_t r, bool inb, int32_t d, double q, double pr, double di, double tx, unsigned key) {
+        const bool valid = inb && d <= cutoff;
+        const int slot = find_slot(key, valid);
+        const double t1 = __dsub_rn(1.0, di);
+        const double t2 = __dmul_rn(pr, t1);
+        const double t3 = __dadd_rn(1.0, tx);
+        const double t4 = __dmul_rn(t2, t3);
+        A.add(slot, valid && slot >= 0, r, q, pr, t2, t4, di);
+    }
+    template <int kT>
+    __device__ __forceinline__ void load_from(const Q1SmemAcc<kT> &A) {   // registers <- shared state, for the common epilogue (G >= 4)
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+#pragma unroll
+            for (int j = 0; j < kQ1Vals; j++) acc[g][j] = A.acc[(g * kQ1Vals + j) * kT];
+            cnt[g] = A.cnt[g * kT];
+            const unsigned f = A.first[g * kT];
+            first[g] = f == 0xffffffffu ? ~0ull : (unsigned long long)f;
+        }
     }
 
     // `inb` = the row exists; the shipdate filter is folded into `valid`.
@@ -461,7 +519,7 @@ __device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int G, int kStages>
+template <int G, int kStages, bool SMEMACC>
 __global__ void __launch_bounds__(kStagedThreads, 1)
 q1_staged_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty, const double *__restrict__ price,
                  const double *__restrict__ disc, const double *__restrict__ tax, const uint8_t *__restrict__ rf,
@@ -478,6 +536,8 @@ q1_staged_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty,
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int kWarps = kStagedThreads / 32;
     unsigned char *wring = ring + (size_t)warp * kStages * kTileBytes;
+    Q1SmemAcc<kStagedThreads> A;
+    if (SMEMACC) A.bind(ring + (size_t)kWarps * kStages * kTileBytes, threadIdx.x);
     const uint64_t ntiles = n / kTileRows;
     const uint64_t gw = blockIdx.x * (uint64_t)kWarps + warp, nw = (uint64_t)gridDim.x * kWarps;
 
@@ -521,7 +581,8 @@ q1_staged_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty,
             const double di = *reinterpret_cast<const double *>(s + 1280 + rl * 8);
             const double tx = *reinterpret_cast<const double *>(s + 1792 + rl * 8);
             const unsigned key = (unsigned)s[2304 + rl] | ((unsigned)s[2368 + rl] << 8);
-            T.row(r0 + rl, true, d, q, pr, di, tx, key);
+            if (SMEMACC) T.row_smem(A, r0 + rl, true, d, q, pr, di, tx, key);
+            else T.row(r0 + rl, true, d, q, pr, di, tx, key);
         }
         __syncwarp();   // every lane is done with this slot before any lane's next cp.async overwrites it
         stage = (stage + 1) % kStages;
@@ -533,9 +594,11 @@ q1_staged_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty,
             const bool has = r < n;
             unsigned key = 0; int32_t dd = 0; double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
             if (has) { key = q1_key_scalar<0>(rf, ls, r); dd = sd[r]; v0 = qty[r]; v1 = price[r]; v2 = disc[r]; v3 = tax[r]; }
-            T.row(r, has, dd, v0, v1, v2, v3, key);
+            if (SMEMACC) T.row_smem(A, r, has, dd, v0, v1, v2, v3, key);
+            else T.row(r, has, dd, v0, v1, v2, v3, key);
         }
     }
+    if (SMEMACC) T.load_from(A);
     q1_epilogue<G, kStagedThreads>(T, S, partials, out, ticket, dbg);
 }
 
@@ -566,7 +629,7 @@ q1_bulk_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty, c
                const double *__restrict__ disc, const double *__restrict__ tax, const uint8_t *__restrict__ rf,
                const uint8_t *__restrict__ ls, uint64_t n, int32_t cutoff, Q1Rec *__restrict__ partials,
                Q1Rec *__restrict__ out, unsigned *ticket, unsigned long long *dbg) {
-    extern __shared__ __align__(128) unsigned char ring[];   // [warp][stage][kTileBytes], then the mbarriers
+    extern __shared__ __align__(16) unsigned char ring[];   // [warp][stage][kTileBytes], then the mbarriers
     if (dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[blockIdx.x * 16] = t; }
     __shared__ Q1Shared S;
     S.dict[threadIdx.x & (MO_Q1_MAX_GROUPS - 1)] = kEmptyKey;
@@ -637,6 +700,99 @@ q1_bulk_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty, c
         }
     }
     q1_epilogue<G, kStagedThreads>(T, S, partials, out, ticket, dbg);
+}
+
+// ---- variant D: CTA-wide TMA pipeline ------------------------------------------------------------------------------------------------
+// ncu on variant B shows every 32-byte sector requested twice from L2 (lts__t_sector_hit_rate 49 %, l1tex__m_xbar2l1tex_read_bytes = 1.84 x the
+// DRAM bytes): the per-lane 16-byte LDGSTS requests of a warp are not merged into sector requests the way LDG.128 is.  Variant C (per-warp bulk
+// copies of 64-512 bytes) fixed that but drowned the TMA unit in tiny copies (7 per 64 rows; 0.75 of the HBM rate).  Here ONE producer warp
+// streams 1024-row tiles -- 7 bulk copies of 1-8 KB per tile, 4 tiles (156 KB) in flight per SM -- and the 16 consumer warps share each tile:
+// full[stage] (transaction count) / empty[stage] (one arrival per consumer warp) mbarriers, no CTA barrier in the steady state.
+constexpr int kCtaTileRows = 1024, kCtaStages = 4, kCtaConsumers = 16;
+constexpr int kCtaTileBytes = kCtaTileRows * 38;   // 4096 shipdate + 4 x 8192 + 2 x 1024
+constexpr int kCtaThreads = (kCtaConsumers + 1) * 32;
+
+__device__ __forceinline__ void q1_mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+template <int G>
+__global__ void __launch_bounds__(kCtaThreads, 1)
+q1_tma_kernel(const int32_t *__restrict__ sd, const double *__restrict__ qty, const double *__restrict__ price,
+              const double *__restrict__ disc, const double *__restrict__ tax, const uint8_t *__restrict__ rf,
+              const uint8_t *__restrict__ ls, uint64_t n, int32_t cutoff, Q1Rec *__restrict__ partials,
+              Q1Rec *__restrict__ out, unsigned *ticket, unsigned long long *dbg) {
+    extern __shared__ __align__(16) unsigned char ring[];   // [stage][kCtaTileBytes], then full[] and empty[] mbarriers
+    if (dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[blockIdx.x * 16] = t; }
+    __shared__ Q1Shared S;
+    S.dict[threadIdx.x & (MO_Q1_MAX_GROUPS - 1)] = kEmptyKey;
+    S.overflow = 0; S.slow = 0;
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(ring + (size_t)kCtaStages * kCtaTileBytes);
+    unsigned long long *empty = full + kCtaStages;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kCtaStages; s++) { q1_mbar_init(&full[s], 1); q1_mbar_init(&empty[s], kCtaConsumers); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    Q1Thread<G> T;
+    T.init(&S, cutoff, dbg != nullptr);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t ntiles = n / kCtaTileRows;
+    // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+    const uint64_t mine = ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (warp == kCtaConsumers) {
+        // ---------------- producer warp: lane 0 issues, the others idle (they rejoin at the epilogue barrier)
+        if (lane == 0) {
+            for (uint64_t k = 0; k < mine; k++) {
+                const int stage = (int)(k % kCtaStages);
+                if (k >= kCtaStages) q1_mbar_wait(&empty[stage], (unsigned)(((k / kCtaStages) - 1) & 1));   // every consumer warp released the slot
+                unsigned char *s = ring + (size_t)stage * kCtaTileBytes;
+                const uint64_t r0 = (blockIdx.x + k * gridDim.x) * (uint64_t)kCtaTileRows;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                q1_mbar_expect_tx(&full[stage], kCtaTileBytes);
+                q1_bulk_copy(s, sd + r0, 4096, &full[stage]);
+                q1_bulk_copy(s + 4096, qty + r0, 8192, &full[stage]);
+                q1_bulk_copy(s + 12288, price + r0, 8192, &full[stage]);
+                q1_bulk_copy(s + 20480, disc + r0, 8192, &full[stage]);
+                q1_bulk_copy(s + 28672, tax + r0, 8192, &full[stage]);
+                q1_bulk_copy(s + 36864, rf + r0, 1024, &full[stage]);
+                q1_bulk_copy(s + 37888, ls + r0, 1024, &full[stage]);
+            }
+        }
+    } else {
+        // ---------------- consumer warps: thread t owns rows t and t + 512 of every tile
+        for (uint64_t k = 0; k < mine; k++) {
+            const int stage = (int)(k % kCtaStages);
+            q1_mbar_wait(&full[stage], (unsigned)((k / kCtaStages) & 1));
+            const unsigned char *s = ring + (size_t)stage * kCtaTileBytes;
+            const uint64_t r0 = (blockIdx.x + k * gridDim.x) * (uint64_t)kCtaTileRows;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int rl = threadIdx.x + 512 * h;
+                const int32_t d = *reinterpret_cast<const int32_t *>(s + rl * 4);
+                const double q = *reinterpret_cast<const double *>(s + 4096 + rl * 8);
+                const double pr = *reinterpret_cast<const double *>(s + 12288 + rl * 8);
+                const double di = *reinterpret_cast<const double *>(s + 20480 + rl * 8);
+                const double tx = *reinterpret_cast<const double *>(s + 28672 + rl * 8);
+                const unsigned key = (unsigned)s[36864 + rl] | ((unsigned)s[37888 + rl] << 8);
+                T.row(r0 + rl, true, d, q, pr, di, tx, key);
+            }
+            __syncwarp();
+            if (lane == 0) q1_mbar_arrive(&empty[stage]);
+        }
+        // rows past the last full tile (< 1024): warp 0 of CTA 0, direct loads
+        if (blockIdx.x == 0 && warp == 0) {
+            for (uint64_t r = ntiles * kCtaTileRows + lane; r - lane < n; r += 32) {
+                const bool has = r < n;
+                unsigned key = 0; int32_t dd = 0; double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+                if (has) { key = q1_key_scalar<0>(rf, ls, r); dd = sd[r]; v0 = qty[r]; v1 = price[r]; v2 = disc[r]; v3 = tax[r]; }
+                T.row(r, has, dd, v0, v1, v2, v3, key);
+            }
+        }
+    }
+    q1_epilogue<G, kCtaThreads>(T, S, partials, out, ticket, dbg);
 }
 
 __host__ __device__ void q1_finalize(const Q1Rec &F, mo_q1_result_t *res, int64_t row_base = 0) {
@@ -723,6 +879,7 @@ unsigned long long *g_q1_dbg = nullptr;   // optional per-CTA phase timestamps (
 namespace mob {
 
 unsigned long long *q1_debug_buffer() { return g_q1_dbg; }
+int g_plan_specialise = 1;
 int xcall_plan(mo_xcall_args_t *args, uint64_t len);
 
 extern int g_search_mode;
@@ -740,6 +897,7 @@ int tuning_set(const char *name, int value) {
     if (!strcmp(name, "get_tc_kused")) return g_last_tc_kused;
     if (!strcmp(name, "tc_share")) { g_tc_share_mode = (int)value; return 0; }
     if (!strcmp(name, "q6_variant")) { g_q6_variant = value; return 0; }
+    if (!strcmp(name, "plan_specialise")) { g_plan_specialise = value; return 0; }
     if (!strcmp(name, "q1_variant")) { g_q1_variant = value; return 0; }
     if (!strcmp(name, "q1_debug")) {
         if (value && !g_q1_dbg) { if (cudaMalloc((void **)&g_q1_dbg, 8 * 16 * 1024) != cudaSuccess) return -1; cudaMemset(g_q1_dbg, 0, 8 * 16 * 1024); }
@@ -909,34 +1067,59 @@ static int launch_q1(ThreadCtx &t, const int32_t *sd, const double *qty, const d
         Q1Rec *out = partials + grid;
         if (attempt == 0 || !dres) cudaEventRecord(t.kev0, t.stream);
         if (staged && g_q1_variant >= 5 && g_q1_variant <= 7) {
-            const int stages = g_q1_variant == 5 ? 3 : (g_q1_variant == 6 ? 4 : 6);
+            const int stages = g_q1_variant == 5 ? 3 : (g_q1_variant == 6 ? 4 : 5);
             const size_t smem = (size_t)(kStagedThreads / 32) * stages * kTileBytes + (size_t)(kStagedThreads / 32) * stages * 8;
             static bool battr[3] = {false, false, false};
             const int bi = g_q1_variant - 5;
             if (!battr[bi]) {
                 cudaError_t e = stages == 3 ? cudaFuncSetAttribute(q1_bulk_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                               : stages == 4 ? cudaFuncSetAttribute(q1_bulk_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                                            : cudaFuncSetAttribute(q1_bulk_kernel<4, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                                            : cudaFuncSetAttribute(q1_bulk_kernel<4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e != cudaSuccess) { set_error("q1: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return MO_RC_INTERNAL_ERROR; }
                 battr[bi] = true;
             }
             if (stages == 3) q1_bulk_kernel<4, 3><<<grid, kStagedThreads, smem, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg);
             else if (stages == 4) q1_bulk_kernel<4, 4><<<grid, kStagedThreads, smem, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg);
-            else q1_bulk_kernel<4, 6><<<grid, kStagedThreads, smem, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg);
+            else q1_bulk_kernel<4, 5><<<grid, kStagedThreads, smem, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg);
+        } else if (staged && (g_q1_variant == 10 || g_q1_variant == 0) && n >= (uint64_t)kCtaTileRows * 64) {   // default for packed keys (measured 1.07 vs 0.83 of the HBM rate for variant B)
+            grid = num_sms();
+            const uint64_t nt = n / kCtaTileRows;
+            if ((uint64_t)grid > nt) grid = (int)nt;
+            const size_t smem = (size_t)kCtaStages * kCtaTileBytes + 2 * kCtaStages * 8;
+            static bool tattr = false;
+            if (!tattr) {
+                cudaError_t e = cudaFuncSetAttribute(q1_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) { set_error("q1: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return MO_RC_INTERNAL_ERROR; }
+                tattr = true;
+            }
+            q1_tma_kernel<4><<<grid, kCtaThreads, smem, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg);
+        } else if (staged && (g_q1_variant == 8 || g_q1_variant == 9) && n < (1ull << 32)) {
+            // shared-memory accumulators: 8 = 3 stages, 9 = 2 stages
+            const int stages = g_q1_variant == 8 ? 3 : 2;
+            const size_t smem = (size_t)(kStagedThreads / 32) * stages * kTileBytes + Q1SmemAcc<kStagedThreads>::kBytes;
+            static bool sattr[2] = {false, false};
+            if (!sattr[stages - 2]) {
+                cudaError_t e = stages == 3 ? cudaFuncSetAttribute(q1_staged_kernel<4, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                            : cudaFuncSetAttribute(q1_staged_kernel<4, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) { set_error("q1: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return MO_RC_INTERNAL_ERROR; }
+                sattr[stages - 2] = true;
+            }
+            if (stages == 3) q1_staged_kernel<4, 3, true><<<grid, kStagedThreads, smem, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg);
+            else q1_staged_kernel<4, 2, true><<<grid, kStagedThreads, smem, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg);
         } else if (staged) {
             const int stages = g_q1_variant == 3 ? 4 : (g_q1_variant == 4 ? 5 : 3);   // 3 stages measured best (tools/tune.py q1)
             const size_t smem = (size_t)(kStagedThreads / 32) * stages * kTileBytes;
             static bool attr_done[3] = {false, false, false};
             if (!attr_done[stages - 3]) {
-                cudaError_t e = stages == 3 ? cudaFuncSetAttribute(q1_staged_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                              : stages == 4 ? cudaFuncSetAttribute(q1_staged_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                                            : cudaFuncSetAttribute(q1_staged_kernel<4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                cudaError_t e = stages == 3 ? cudaFuncSetAttribute(q1_staged_kernel<4, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                              : stages == 4 ? cudaFuncSetAttribute(q1_staged_kernel<4, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                            : cudaFuncSetAttribute(q1_staged_kernel<4, 5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e != cudaSuccess) { set_error("q1: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return MO_RC_INTERNAL_ERROR; }
                 attr_done[stages - 3] = true;
             }
-            if (stages == 3) q1_staged_kernel<4, 3><<<grid, kStagedThreads, smem, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg);
-            else if (stages == 4) q1_staged_kernel<4, 4><<<grid, kStagedThreads, smem, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg);
-            else q1_staged_kernel<4, 5><<<grid, kStagedThreads, smem, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg);
+            if (stages == 3) q1_staged_kernel<4, 3, false><<<grid, kStagedThreads, smem, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg);
+            else if (stages == 4) q1_staged_kernel<4, 4, false><<<grid, kStagedThreads, smem, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg);
+            else q1_staged_kernel<4, 5, false><<<grid, kStagedThreads, smem, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg);
         } else if (!wide) {
             q1_kernel<4, 2, 2, KEYMODE><<<grid, kThreads, 0, t.stream>>>(sd, qty, price, disc, tax, rf, ls, n, cutoff, partials, out, t.ctrl, g_q1_dbg, nullptr);
         } else {

@@ -14,6 +14,14 @@ pytestmark = pytest.mark.gpu
 Q1COLS = ("shipdate", "quantity", "extendedprice", "discount", "tax", "returnflag", "linestatus")
 
 
+@pytest.fixture(params=[1, 0], ids=["specialised", "interpreter"])
+def mode(request, gpu):
+    """recognised Q6 / Q1 shapes dispatch to the hand-specialised kernels; plan_specialise = 0 forces the generic interpreter"""
+    assert gpu.MoB200_SetTuning(b"plan_specialise", request.param) == 0
+    yield request.param
+    gpu.MoB200_SetTuning(b"plan_specialise", 1)
+
+
 def q1_groups(res):
     out = []
     for g in res:
@@ -24,7 +32,7 @@ def q1_groups(res):
 
 
 @pytest.mark.parametrize("n", [1, 255, 256, 257, 100_003, 2_000_001])
-def test_q6_plan_matches_oracle_and_specialised_kernel(gpu, n):
+def test_q6_plan_matches_oracle_and_specialised_kernel(gpu, mode, n):
     cols = datagen.lineitem(10, 0, n)
     P = datagen.q6_params()
     want, ns, nul = O.q6(cols, n, P, nthreads=1)
@@ -40,7 +48,7 @@ def test_q6_plan_matches_oracle_and_specialised_kernel(gpu, n):
 
 
 @pytest.mark.parametrize("n", [64, 100_003, 3_000_001])
-def test_q1_plan_matches_oracle(gpu, n):
+def test_q1_plan_matches_oracle(gpu, mode, n):
     cols = datagen.lineitem(10, 0, n)
     want = O.q1(cols, n, datagen.Q1_CUTOFF)
     res = q1_groups(ops.q1_plan(datagen.Q1_CUTOFF, row_base=5).run([cols[k] for k in Q1COLS], n))
@@ -50,7 +58,7 @@ def test_q1_plan_matches_oracle(gpu, n):
             assert abs(a[f] - b[f]) <= 1e-11 * abs(b[f]), f
 
 
-def test_plans_reproduce_reference_results_on_reference_lineitem(gpu):
+def test_plans_reproduce_reference_results_on_reference_lineitem(gpu, mode):
     cols, ints, expected = G.tpch_fixture()
     n = len(cols["shipdate"])
     r6 = ops.q6_plan().run([cols["shipdate"], cols["discount"], cols["quantity"], cols["extendedprice"]], n)

@@ -231,9 +231,9 @@ def test_q1_non_finite_values_stay_inside_their_group(gpu):
     assert np.isinf(a["sum_qty"]) and np.isnan(a["sum_charge"])
 
 
-@pytest.mark.parametrize("variant", [3, 5, 6, 7])
+@pytest.mark.parametrize("variant", [3, 5, 6, 7, 8, 9, 10])
 def test_q1_kernel_variants_agree(gpu, variant):
-    """the cp.async-staged (3, 4 stages) and the bulk-copy / TMA staged (5, 6, 7 = 3, 4, 6 stages) Q1 kernels give the default kernel's result:
+    """the cp.async-staged (3, 4 stages) and the bulk-copy / TMA staged (5, 6, 7 = 3, 4, 5 stages), and the shared-memory-accumulator kernel (8, 9 = 3, 2 stages) Q1 kernels give the default kernel's result:
     same groups, counts and first rows; sums to the last few bits (per-thread row sets are identical, so in fact bitwise)"""
     n = 5_000_011
     bufs = dev_lineitem(gpu, 10, n)

@@ -1,0 +1,100 @@
+"""Resident-column timings of the operator kernels that have no bench.py workload of their own (generic fused plan, filter->sels, Shrink,
+first-seen group ids, grouped aggregates, decimal SUM): CUDA-event kernel time through MoB200_LastKernelMs, GB/s of ALGORITHMIC bytes.
+Also the command ncu captures are taken on (tools/profile_r02.sh).   python tools/profile_ops.py [rows] > gpurun_out/r02_ops.json"""
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from matrixone_b200 import capi, datagen, ops  # noqa: E402
+from matrixone_b200.vector import DeviceBuffer, Vector, xcall  # noqa: E402
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 200_000_000
+    lib = capi.load_library()
+    capi.check(lib.MoB200_Init(0), lib)
+    kms = C.c_float()
+    out = {"rows": n}
+
+    def timed(fn, reps=5):
+        ts = []
+        for _ in range(reps + 1):
+            fn()
+            capi.check(lib.MoB200_LastKernelMs(C.byref(kms)), lib)
+            ts.append(kms.value)
+        return float(np.median(ts[1:]))
+
+    names = ("shipdate", "quantity", "extendedprice", "discount", "tax", "returnflag", "linestatus")
+    size = {"shipdate": 4, "returnflag": 1, "linestatus": 1}
+    bufs = {k: DeviceBuffer(size.get(k, 8) * n, lib) for k in names}
+    capi.check(lib.MoB200_GenLineitem(10, 0, n, *[bufs[k].ptr for k in names]), lib)
+    # ---- generic fused plan: Q6 and Q1 shapes, device-resident result
+    lib.MoB200_SetTuning(b"plan_specialise", 0)      # time the generic interpreter (the recognised shapes would dispatch to the specialised kernels)
+    p6 = ops.q6_plan(); r6 = DeviceBuffer(p6.result_bytes(4), lib)
+    ms = timed(lambda: p6.run([bufs["shipdate"], bufs["discount"], bufs["quantity"], bufs["extendedprice"]], n, max_groups=4, out_ptr=r6.ptr))
+    out["plan_q6"] = {"ms": ms, "gbs": 28.0 * n / ms / 1e6, "rows_per_s": n / ms * 1e3}
+    p1 = ops.q1_plan(datagen.Q1_CUTOFF); r1 = DeviceBuffer(p1.result_bytes(16), lib)
+    ms = timed(lambda: p1.run([bufs[k] for k in names], n, max_groups=16, out_ptr=r1.ptr))
+    out["plan_q1"] = {"ms": ms, "gbs": 38.0 * n / ms / 1e6, "rows_per_s": n / ms * 1e3}
+    lib.MoB200_SetTuning(b"plan_specialise", 1)
+    ms = timed(lambda: p6.run([bufs["shipdate"], bufs["discount"], bufs["quantity"], bufs["extendedprice"]], n, max_groups=4, out_ptr=r6.ptr))
+    out["plan_q6_recognised_shape"] = {"ms": ms, "gbs": 28.0 * n / ms / 1e6}
+    ms = timed(lambda: p1.run([bufs[k] for k in names], n, max_groups=16, out_ptr=r1.ptr))
+    out["plan_q1_recognised_shape"] = {"ms": ms, "gbs": 38.0 * n / ms / 1e6}
+    spec6 = DeviceBuffer(16, lib)
+    ms = timed(lambda: ops.q6_filter_sum_device(bufs["shipdate"], bufs["discount"], bufs["quantity"], bufs["extendedprice"], n, *datagen.q6_params(), out_ptr=spec6.ptr))
+    out["q6_specialised"] = {"ms": ms, "gbs": 28.0 * n / ms / 1e6}
+    # ---- compare -> sels -> Shrink on one column
+    dr = DeviceBuffer(n, lib); drn = DeviceBuffer(((n + 63) // 64) * 8, lib)
+    capi.check(lib.MoB200_Memset(drn.ptr, 0, drn.nbytes), lib)
+    cut = np.asarray([datagen.DATE_1995_01_01], dtype=np.int32)
+    cmpv = [Vector(data_ptr=dr.ptr, data_nbytes=n, nulls_ptr=drn.ptr, length=n), Vector(data_ptr=bufs["shipdate"].ptr, data_nbytes=4 * n, length=n), Vector(data=cut, length=n)]
+    ms = timed(lambda: xcall(capi.XCALL_GO_COMPARE(4, capi.T_DATE), cmpv, n))
+    out["go_compare_date_lt"] = {"ms": ms, "gbs": (5.0 + 0.125) * n / ms / 1e6}
+    dsels = DeviceBuffer(8 * n, lib); dcnt = DeviceBuffer(8, lib)
+    ms = timed(lambda: ops.filter_sels_device(dr, drn, n, dsels.ptr, dcnt.ptr))
+    k = int(dcnt.to_numpy(np.int64)[0])
+    out["filter_sels"] = {"ms": ms, "selected": k, "gbs": (1.125 * n + 8.0 * k) / ms / 1e6}
+    dst = DeviceBuffer(8 * k, lib)
+    shv = [Vector(data_ptr=dst.ptr, data_nbytes=8 * k, length=k), Vector(data_ptr=bufs["quantity"].ptr, data_nbytes=8 * n, length=n), Vector(data_ptr=dsels.ptr, data_nbytes=8 * k, length=k)]
+    ms = timed(lambda: xcall(capi.XCALL_SHUFFLE(8), shv, k))
+    out["shuffle_f64"] = {"ms": ms, "gbs": 24.0 * k / ms / 1e6}
+    dsels.free(); dst.free(); dr.free(); drn.free()
+    # ---- first-seen group ids + grouped SUM, low and high cardinality
+    m = min(n, 100_000_000)
+    for card in (4, 1_000_000):
+        keys = DeviceBuffer(8 * m, lib); groups = DeviceBuffer(8 * m, lib)
+        capi.check(lib.MoB200_GenInt64(7, 0, m, keys.ptr, None, 0), lib)
+        # fold the 2^32 generator range down to `card` distinct keys with the Go modulo kernel (non-negative after + 2^31)
+        kb = np.asarray([1 << 31], dtype=np.int64); kc = np.asarray([card], dtype=np.int64)
+        rn = DeviceBuffer(((m + 63) // 64) * 8, lib); capi.check(lib.MoB200_Memset(rn.ptr, 0, rn.nbytes), lib)
+        prm = np.zeros(2, dtype=np.int64); prm[1] = -1
+        kv = lambda: Vector(data_ptr=keys.ptr, data_nbytes=8 * m, nulls_ptr=rn.ptr, length=m)
+        xcall(capi.XCALL_GO_ARITH(0, capi.T_INT64), [kv(), Vector(data_ptr=keys.ptr, data_nbytes=8 * m, length=m), Vector(data=kb, length=m), Vector(data=prm.view(np.uint8), length=m)], m)
+        xcall(capi.XCALL_GO_ARITH(4, capi.T_INT64), [kv(), Vector(data_ptr=keys.ptr, data_nbytes=8 * m, length=m), Vector(data=kc, length=m), Vector(data=prm.view(np.uint8), length=m)], m)
+        cap = card + 64
+        tkeys = DeviceBuffer(8 * cap, lib); ng = DeviceBuffer(8, lib)
+        def gid():
+            capi.check(lib.MoB200_Memset(ng.ptr, 0, 8), lib)
+            ops.GroupTable(1).insert_device(keys, m, groups, ng, tkeys, cap)
+        ms = timed(gid, reps=3)
+        found = int(ng.to_numpy(np.int64)[0])
+        out["group_ids_card_%d" % card] = {"ms_insert_kernel": ms, "rows": m, "groups": found, "rows_per_s_insert": m / ms * 1e3}
+        state = DeviceBuffer(8 * found, lib); sn = DeviceBuffer(((found + 63) // 64) * 8, lib); cnt = DeviceBuffer(8 * found, lib)
+        capi.check(lib.MoB200_Memset(state.ptr, 0, state.nbytes), lib); capi.check(lib.MoB200_Memset(sn.ptr, 0xff, sn.nbytes), lib); capi.check(lib.MoB200_Memset(cnt.ptr, 0, cnt.nbytes), lib)
+        gv = [Vector(data_ptr=state.ptr, data_nbytes=8 * found, nulls_ptr=sn.ptr, length=found), Vector(data_ptr=cnt.ptr, data_nbytes=8 * found, length=found),
+              Vector(data_ptr=groups.ptr, data_nbytes=8 * m, length=m), Vector(data_ptr=bufs["quantity"].ptr, data_nbytes=8 * m, length=m)]
+        ms = timed(lambda: xcall(capi.XCALL_GROUP_AGG(capi.AGG_SUM, capi.T_FLOAT64), gv, m), reps=3)
+        out["group_sum_f64_card_%d" % card] = {"ms": ms, "gbs": 16.0 * m / ms / 1e6, "rows_per_s": m / ms * 1e3}
+        for b in (keys, groups, rn, tkeys, ng, state, sn, cnt):
+            b.free()
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -68,18 +68,23 @@ def launches(path):
 
 
 def main():
+    import glob
+    import json
     out_dir = os.path.join(ROOT, "profiles")
     os.makedirs(out_dir, exist_ok=True)
     src = os.path.join(ROOT, "gpurun_out")
-    prefix = sys.argv[1] if len(sys.argv) > 1 else "r01"
-    algo = {"q6": 28.0 * 600_037_902, "q1": 38.0 * 600_037_902}
+    prefix = sys.argv[1] if len(sys.argv) > 1 else "r02"
+    SF = 600_037_902
+    algo = {"q6": 28.0 * SF, "q1": 38.0 * SF, "sum": 8.0 * 10_000_000}
+    # bench.py roofline.traffic keys: "<workload>:<rows_per_gpu>[:<queries>]"
+    traffic_key = {"q6": "q6:%d" % SF, "q1": "q1:%d" % SF, "sum": "sum:10000000", "tc_ivf": "ivf:10000000:10000", "tc_bruteforce": "bruteforce:1000000:10000"}
+    traffic = {}
     lines = ["# ncu evidence, %s" % prefix, "",
-             "Captured with `tools/profile_%s.sh` and `tools/profile_search.sh` under gpurun (`ncu --set full --clock-control none --import-source on`); the `.ncu-rep`" % prefix,
+             "Captured with `tools/profile_%s.sh` under gpurun (`ncu --set full --clock-control none --import-source on`); the `.ncu-rep`" % prefix,
              "files stay in gpurun_out/ (scratch).  Durations under ncu are cold-cache and serialised: compare shares, not absolutes.", ""]
-    for name in ("q6", "q1", "agg", "bf", "tc_bruteforce", "tc_ivf", "rowdist_l2", "rowdist_cos"):
+    names = sorted(os.path.basename(f)[len(prefix) + 1:-len(".ncu-rep")] for f in glob.glob(os.path.join(src, "%s_*.ncu-rep" % prefix)))
+    for name in names:
         rep = os.path.join(src, "%s_%s.ncu-rep" % (prefix, name))
-        if not os.path.exists(rep):
-            continue
         recs, units = raw(rep)
         for rec in recs[:1]:
             lines += ["## %s -- `%s`" % (name, rec.get("Kernel Name", "?")[:110]), "", "| metric | value | unit |", "|---|---|---|"]
@@ -93,6 +98,9 @@ def main():
                 lines += ["", "DRAM traffic per launch = %.4f GB (read %.4f + write %.4f); duration under ncu %.3f ms => %.0f GB/s of DRAM traffic." % ((rd + wr) / 1e9, rd / 1e9, wr / 1e9, dur * 1e3, (rd + wr) / dur / 1e9)]
                 if algo.get(name):
                     lines.append("Algorithmic bytes per launch = %.4f GB => traffic / algorithmic = %.3f." % (algo[name] / 1e9, (rd + wr) / algo[name]))
+                if name in traffic_key:
+                    traffic[traffic_key[name]] = {"bytes_per_launch": rd + wr, "kernel": rec.get("Kernel Name", "?")[:80],
+                                                  "source": "profiles/%s_ncu_summary.md section '%s' (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this bench command)" % (prefix, name)}
             except Exception as ex:
                 lines.append("(traffic summary unavailable: %s)" % ex)
             st = stalls(rep)
@@ -100,20 +108,20 @@ def main():
                 lines += ["", "Top sampled instructions (warp-stall samples):", "", "| samples | % | SASS |", "|---|---|---|"]
                 lines += ["| %d | %.1f | `%s` |" % (n, pct, s_[:90]) for n, pct, s_ in st]
             lines.append("")
-    for name in ("q6", "q1", "bruteforce", "ivf"):
+    for name in ("q6", "q1", "sum", "bruteforce", "ivf"):
         p = os.path.join(src, "%s_launches_%s.csv" % (prefix, name))
         if os.path.exists(p):
             agg = launches(p)
             tot = sum(v[1] for v in agg.values()) or 1
-            cmd = {"q6": "--steps 2 --warmup 3", "q1": "--steps 2 --warmup 3 --workload q1", "bruteforce": "--steps 1 --warmup 3 --workload bruteforce",
-                   "ivf": "--steps 1 --warmup 3 --workload ivf --rows 1250000"}[name]
-            lines += ["## launch list: `python bench.py %s --no-e2e --no-cpu`" % cmd, "",
+            lines += ["## launch list: `python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --workload %s` (set-up kernels included)" % name, "",
                       "| kernel | launches | total ns | share |", "|---|---|---|---|"]
             for k, (c, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
                 lines.append("| `%s` | %d | %.0f | %.1f %% |" % (k, c, v, 100 * v / tot))
             lines.append("")
     open(os.path.join(out_dir, "%s_ncu_summary.md" % prefix), "w").write("\n".join(lines) + "\n")
-    print("\n".join(lines[:80]))
+    if traffic:
+        open(os.path.join(out_dir, "ncu_traffic.json"), "w").write(json.dumps(traffic, indent=1) + "\n")
+    print("\n".join(lines[:60]))
 
 
 if __name__ == "__main__":
