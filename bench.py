@@ -385,13 +385,15 @@ class Env:
         launches = self.lib.MoB200_KernelLaunchCount() - launches0
         total_ms = self.max_over_ranks(max(ms.value, 0.0))
         clocks = None
+        if total_ms < 250.0:
+            # a short region holds too few 20 ms nvidia-smi samples: keep stepping (untimed) under the sampler.  The number of extra steps is
+            # derived from the rank-maximum time, i.e. identical on every rank: the steps contain collectives
+            extra = min(20000, int(400.0 / max(total_ms / K, 1e-3)) + 1)
+            for _ in range(extra):
+                step()
+            self.barrier_sync()
+            t_region1 = time.time()
         if self.rank == 0:
-            if t_region1 - t_region0 < 0.25:     # a short region holds too few 20 ms samples: keep stepping (untimed) under the sampler
-                t_end = time.time() + 0.4
-                while time.time() < t_end:
-                    step()
-                self.sync()
-                t_region1 = time.time()
             clocks = self.sampler.window(t_region0, t_region1)
         if self.dist is not None:
             self.barrier_sync()

@@ -151,6 +151,8 @@ typedef struct mo_xcall_args_t {
 #define MO_XCALL_GO_COSDIST_F64 107
 #define MO_XCALL_GO_COSSIM_F32 108
 #define MO_XCALL_GO_COSSIM_F64 109
+#define MO_XCALL_GO_L1_F32 110   /* metric.L1Distance, distance_func.go:112-154 (l1_norm of the difference) */
+#define MO_XCALL_GO_L1_F64 111
 
 /* --- new: single-column aggregates (aggexec sumavg2.go / count2.go / minmax2.go semantics, no group-by = H0).
  * funcId = MO_XCALL_AGG(op, T).  args: [0] result: pdata -> one 8-byte value (int64 / uint64 / float64, or the

@@ -33,6 +33,7 @@ XCALL_L2DISTANCE_F32, XCALL_L2DISTANCE_F64, XCALL_L2DISTANCE_SQ_F32, XCALL_L2DIS
 XCALL_GO_L2_F32, XCALL_GO_L2_F64, XCALL_GO_L2SQ_F32, XCALL_GO_L2SQ_F64 = 100, 101, 102, 103
 XCALL_GO_IP_F32, XCALL_GO_IP_F64, XCALL_GO_COSDIST_F32, XCALL_GO_COSDIST_F64 = 104, 105, 106, 107
 XCALL_GO_COSSIM_F32, XCALL_GO_COSSIM_F64 = 108, 109
+XCALL_GO_L1_F32, XCALL_GO_L1_F64 = 110, 111
 AGG_SUM, AGG_COUNT, AGG_MIN, AGG_MAX, AGG_AVG = 0, 1, 2, 3, 4
 
 

@@ -93,7 +93,7 @@ rowdist_kernel(double *__restrict__ res, const uint64_t *__restrict__ rnulls, ui
             double out; bool write = true;
             if (KIND == K_XC_L2) out = sqrt(acc.dsum);
             else if (KIND == K_XC_L2SQ) out = acc.dsum;
-            else if (KIND == K_GO_L2SQ) out = (double)acc.sum;
+            else if (KIND == K_GO_L2SQ || KIND == K_GO_L1) out = (double)acc.sum;
             else if (KIND == K_GO_L2) out = (double)(T)sqrt((double)acc.sum);  // distance_func.go:35-42
             else if (KIND == K_GO_IP) out = (double)(-acc.sum);               // InnerProduct returns -sum, distance_func.go:172-205
             else {
@@ -189,6 +189,8 @@ int xcall_rowdist(int64_t funcId, mo_xcall_args_t *args, uint64_t len) {
     case MO_XCALL_GO_COSDIST_F64: return run_rowdist<double, K_GO_COSDIST>(args, len);
     case MO_XCALL_GO_COSSIM_F32: return run_rowdist<float, K_GO_COSSIM>(args, len);
     case MO_XCALL_GO_COSSIM_F64: return run_rowdist<double, K_GO_COSSIM>(args, len);
+    case MO_XCALL_GO_L1_F32: return run_rowdist<float, K_GO_L1>(args, len);
+    case MO_XCALL_GO_L1_F64: return run_rowdist<double, K_GO_L1>(args, len);
     }
     return -1;
 }

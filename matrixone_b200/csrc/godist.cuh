@@ -127,7 +127,7 @@ __device__ void go_cos_parts(const uint8_t *p, const uint8_t *q, int dim, int la
     }
 }
 
-enum Kind { K_XC_L2 = 0, K_XC_L2SQ, K_GO_L2, K_GO_L2SQ, K_GO_IP, K_GO_COSDIST, K_GO_COSSIM };
+enum Kind { K_XC_L2 = 0, K_XC_L2SQ, K_GO_L2, K_GO_L2SQ, K_GO_IP, K_GO_COSDIST, K_GO_COSSIM, K_GO_L1 };
 
 // ---- lane-per-row batches over a per-warp cp.async ring (see distance.cu for the mapping) ---------------------------------------
 constexpr int kTileRows = 32, kSliceBytes = 128, kPitch = 144;   // 144-byte row pitch: LDS.128 by the row owners is conflict-free
@@ -167,6 +167,9 @@ template <typename T, int KIND> struct RowAcc {
             sum = add_rn(sum, add_rn(add_rn(add_rn(mul_rn(a[0], b[0]), mul_rn(a[1], b[1])), mul_rn(a[2], b[2])), mul_rn(a[3], b[3])));
             n1 = add_rn(n1, add_rn(add_rn(add_rn(mul_rn(a[0], a[0]), mul_rn(a[1], a[1])), mul_rn(a[2], a[2])), mul_rn(a[3], a[3])));
             n2 = add_rn(n2, add_rn(add_rn(add_rn(mul_rn(b[0], b[0]), mul_rn(b[1], b[1])), mul_rn(b[2], b[2])), mul_rn(b[3], b[3])));
+        } else if (KIND == K_GO_L1) {   // L1Distance, distance_func.go:112-154: eight serial  sum += abs(p[j] - q[j])
+#pragma unroll
+            for (int j = 0; j < 8; j++) { T d = sub_rn(a[j], b[j]); sum = add_rn(sum, d < 0 ? -d : d); }
         } else if (KIND == K_GO_IP) {
             T c = add_rn(mul_rn(a[0], b[0]), mul_rn(a[1], b[1]));
 #pragma unroll
@@ -183,6 +186,7 @@ template <typename T, int KIND> struct RowAcc {
         if (kXc) { T d = sub_rn(a, b); dsum = __dadd_rn(dsum, (double)mul_rn(d, d)); }
         else if (kCos) { sum = add_rn(sum, mul_rn(a, b)); n1 = add_rn(n1, mul_rn(a, a)); n2 = add_rn(n2, mul_rn(b, b)); }
         else if (KIND == K_GO_IP) sum = add_rn(sum, mul_rn(a, b));
+        else if (KIND == K_GO_L1) { T d = sub_rn(a, b); sum = add_rn(sum, d < 0 ? -d : d); }
         else { T d = sub_rn(a, b); sum = add_rn(sum, mul_rn(d, d)); }
     }
 };

@@ -1223,6 +1223,7 @@ int ivf_tc_scan(ThreadCtx &t, const IvfPlan &plan, const float *ddata, int64_t n
 }  // namespace mob
 
 extern "C" {
+static void release_same_kind(const void *data, bool ivf, int normalized);
 
 // Index load: split a RESIDENT dataset into the tensor-core operand once instead of once per search.  The rows must not change
 // until MoB200_SearchRelease(data).  Datasets the tensor-core path cannot serve (dim < 16, Inf/NaN values) are left unprepared:
@@ -1237,7 +1238,7 @@ int32_t MoB200_SearchPrepareMetric(const void *data, uint64_t n, int64_t dim, in
     if (metric != MO_METRIC_L2 && metric != MO_METRIC_L2SQ && metric != MO_METRIC_IP && metric != MO_METRIC_COS) return MO_RC_SUCCESS;
     if (!data || n == 0 || dim < 16 || n >= (1ull << 31) - BN) return MO_RC_SUCCESS;
     if (!is_device_ptr(data)) { set_error("SearchPrepare: the dataset must be device memory"); return MO_RC_INVALID_ARGUMENT; }
-    MoB200_SearchRelease(data);
+    release_same_kind(data, false, metric == MO_METRIC_COS ? 1 : 0);
     PreparedOperand e; e.x = (const float *)data; e.n = (int64_t)n; e.dim = (int)dim; e.device = 0; e.normalized = metric == MO_METRIC_COS ? 1 : 0;
     e.op.kprime = ((3 * (int)dim + BK - 1) / BK) * BK;
     MOB_CUDA_TRY(cudaMalloc((void **)&e.op.bf, (size_t)n * e.op.kprime * 2 + 1024));
@@ -1268,7 +1269,7 @@ int32_t MoB200_SearchPrepareIvf(const void *data, uint64_t n, int64_t dim, const
     if (!t.ready) return MO_RC_INTERNAL_ERROR;
     if (!data || n == 0 || dim < 16 || n >= (1ull << 31) - BN || nlist == 0) return MO_RC_SUCCESS;
     if (!is_device_ptr(data) || !is_device_ptr(centroids) || !is_device_ptr(offsets)) { set_error("SearchPrepareIvf: entries, centroids and offsets must be device memory"); return MO_RC_INVALID_ARGUMENT; }
-    MoB200_SearchRelease(data);
+    release_same_kind(data, true, 0);
     PreparedOperand e; e.x = (const float *)data; e.n = (int64_t)n; e.dim = (int)dim; e.device = 0; e.cent = (const float *)centroids; e.nlist = (int64_t)nlist;
     e.op.kprime = ((3 * (int)dim + BK - 1) / BK) * BK;
     MOB_CUDA_TRY(cudaMalloc((void **)&e.op.bf, (size_t)n * e.op.kprime * 2 + 1024));
@@ -1290,6 +1291,25 @@ int32_t MoB200_SearchPrepareIvf(const void *data, uint64_t n, int64_t dim, const
     std::lock_guard<std::mutex> lk(g_prepared_mu);
     g_prepared.push_back(e);
     return MO_RC_SUCCESS;
+}
+
+// drop only the operand of the same kind (brute force with the same normalisation, or IVF): preparing COS after L2, or IVF after brute force,
+// on one dataset keeps the earlier operand
+static void release_same_kind(const void *data, bool ivf, int normalized) {
+    using namespace mob;
+    {
+        std::lock_guard<std::mutex> lk0(g_prepared_mu);
+        bool hit = false;
+        for (const PreparedOperand &e : g_prepared) if (e.x == data && (e.cent != nullptr) == ivf && (ivf || e.normalized == normalized)) hit = true;
+        if (!hit) return;
+    }
+    std::unique_lock<std::shared_mutex> wr(g_search_rw);
+    std::lock_guard<std::mutex> lk(g_prepared_mu);
+    for (size_t i = 0; i < g_prepared.size();) {
+        const PreparedOperand &e = g_prepared[i];
+        if (e.x == data && (e.cent != nullptr) == ivf && (ivf || e.normalized == normalized)) { cudaFree(e.op.bf); cudaFree(e.op.norm); g_prepared.erase(g_prepared.begin() + (long)i); }
+        else i++;
+    }
 }
 
 int32_t MoB200_SearchRelease(const void *data) {

@@ -683,7 +683,7 @@ static inline double distfn_f64(int metric, const double *p, const double *q, in
 /* og_distance_rows: the SQL builtins L2DistanceArray / L2DistanceSqArray / InnerProductArray /
  * CosineDistanceArray (pkg/sql/plan/function/func_binary.go:7763-7786,10540-10554 via
  * moarray/external.go:171-210): per row float64(metric(a_i, b_i)); b may be const (stride 0).
- * kind: 0 l2, 1 ip, 2 cosine distance, 4 l2sq.  Rows null in rnulls are skipped. */
+ * kind: 0 l2, 1 ip, 2 cosine distance, 3 l1, 4 l2sq (the METRIC_* ids).  Rows null in rnulls are skipped. */
 int32_t og_distance_rows_f32(int32_t kind, double *r, const float *a, int64_t astride, const float *b, int64_t bstride,
                              int64_t dim, uint64_t n, const uint64_t *rnulls) {
     for (uint64_t i = 0; i < n; i++) {

@@ -29,8 +29,8 @@ def _go_rows(kind, a, b, rnulls=None):
     return out
 
 
-GO_IDS = {np.float32: {0: capi.XCALL_GO_L2_F32, 4: capi.XCALL_GO_L2SQ_F32, 1: capi.XCALL_GO_IP_F32, 2: capi.XCALL_GO_COSDIST_F32},
-          np.float64: {0: capi.XCALL_GO_L2_F64, 4: capi.XCALL_GO_L2SQ_F64, 1: capi.XCALL_GO_IP_F64, 2: capi.XCALL_GO_COSDIST_F64}}
+GO_IDS = {np.float32: {0: capi.XCALL_GO_L2_F32, 4: capi.XCALL_GO_L2SQ_F32, 1: capi.XCALL_GO_IP_F32, 2: capi.XCALL_GO_COSDIST_F32, 3: capi.XCALL_GO_L1_F32},
+          np.float64: {0: capi.XCALL_GO_L2_F64, 4: capi.XCALL_GO_L2SQ_F64, 1: capi.XCALL_GO_IP_F64, 2: capi.XCALL_GO_COSDIST_F64, 3: capi.XCALL_GO_L1_F64}}
 
 
 @pytest.mark.parametrize("dim", [1, 3, 4, 5, 8, 9, 31, 128, 257, 768, 1027])
@@ -61,7 +61,7 @@ def test_go_semantics_distances_bit_exact(gpu, dim, dt):
 def test_reference_golden_vectors_through_xcall(gpu):
     k = json.load(open(os.path.join(G, "metric_kat.json")))
     for key, fid in (("l2", capi.XCALL_GO_L2_F64), ("l2sq", capi.XCALL_GO_L2SQ_F64), ("inner_product", capi.XCALL_GO_IP_F64),
-                     ("cosine_distance", capi.XCALL_GO_COSDIST_F64)):
+                     ("cosine_distance", capi.XCALL_GO_COSDIST_F64), ("l1", capi.XCALL_GO_L1_F64)):
         for c in k[key]:
             a = np.asarray([c["v1"]], dtype=np.float64); b = np.asarray([c["v2"]], dtype=np.float64)
             res = np.zeros(1)
