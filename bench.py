@@ -318,7 +318,9 @@ class Env:
             import torch.distributed as dist
             self.torch, self.dist = torch, dist
             torch.cuda.set_device(self.local)
-            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            import datetime
+            # a collective mismatch should fail in minutes, not after the default 10-minute watchdog
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local), timeout=datetime.timedelta(seconds=env_int("MO_B200_NCCL_TIMEOUT_S", 180)))
             # ONE stream for the library's kernels and torch's NCCL calls: the whole step (kernel -> all_gather -> merge kernel -> D2H)
             # is stream-ordered on the device, the host never waits inside a step
             self.stream = torch.cuda.Stream()
@@ -368,9 +370,10 @@ class Env:
         W = self.W if W is None else W
         for _ in range(W):
             step()
-        self.barrier_sync()
+        self.sync()
         if self.rank == 0:
             time.sleep(0.12)      # nvidia-smi needs ~100 ms between samples; keep the idle gap out of the window below
+        self.barrier_sync()       # AFTER the sleep: the other ranks wait here, not inside their timed region
         t_region0 = time.time()
         launches0 = self.lib.MoB200_KernelLaunchCount()
         self.check(self.lib.MoB200_TimerStart())
