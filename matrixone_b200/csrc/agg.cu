@@ -24,12 +24,14 @@ constexpr int kUnroll = 8;   // 8 x 128-bit loads in flight per thread: 128 KB p
 enum Kind { K_SUM_SIGNED = 0, K_SUM_UNSIGNED = 1, K_SUM_FLOAT = 2, K_MIN = 3, K_MAX = 4 };
 
 // Per-CTA / final record.  Meaning of the words depends on Kind:
-//  SUM_SIGNED  : w0 = two's-complement (wrapping) sum ; w2,w3 = sum of |v| (lo,hi): if that fits int64 no prefix can overflow
+//  SUM_SIGNED  : w0 = two's-complement (wrapping) sum ; w2 = max |v| : if max|v| * (non-null rows) fits int64 no prefix can overflow (w3 unused)
 //  SUM_UNSIGNED: w0,w1 = sum (lo,hi)
 //  SUM_FLOAT   : d = sum (double)
 //  MIN / MAX   : w0 = value bits (zero-extended), w1 = smallest row index of a non-null row (floats: NaN rule)
 //  all         : cnt = non-null rows
 struct Rec { uint64_t w0, w1, w2, w3; double d; uint64_t cnt; uint64_t pad0, pad1; };
+// signed SUM: can a prefix of the serial sum leave int64?  Not if every |v| <= INT64_MAX / rows (then even the sum of all magnitudes fits).
+__host__ __device__ __forceinline__ bool sum_check_needed(const Rec &r) { return r.cnt != 0 && r.w2 > (uint64_t)INT64_MAX / r.cnt; }
 
 __device__ __forceinline__ void add128(uint64_t &lo, uint64_t &hi, uint64_t x) { lo += x; hi += (lo < x); }
 __device__ __forceinline__ void add128p(uint64_t &lo, uint64_t &hi, uint64_t lo2, uint64_t hi2) {
@@ -53,7 +55,8 @@ struct Acc {
         if (KIND == K_SUM_SIGNED) {
             const int64_t x = (int64_t)v;
             w0 += (uint64_t)x;
-            add128(w2, w3, x < 0 ? (0ull - (uint64_t)x) : (uint64_t)x);
+            const uint64_t m = x < 0 ? (0ull - (uint64_t)x) : (uint64_t)x;   // one compare + select instead of a 128-bit running sum of magnitudes
+            w2 = m > w2 ? m : w2;
         } else if (KIND == K_SUM_UNSIGNED) {
             add128(w0, w1, (uint64_t)v);
         } else if (KIND == K_SUM_FLOAT) {
@@ -66,7 +69,7 @@ struct Acc {
     }
     __device__ __forceinline__ void merge(const Rec &r) {
         if (r.cnt == 0) return;
-        if (KIND == K_SUM_SIGNED) { w0 += r.w0; add128p(w2, w3, r.w2, r.w3); }
+        if (KIND == K_SUM_SIGNED) { w0 += r.w0; w2 = r.w2 > w2 ? r.w2 : w2; }
         else if (KIND == K_SUM_UNSIGNED) { add128p(w0, w1, r.w0, r.w1); }
         else if (KIND == K_SUM_FLOAT) { d = d + r.d; }
         else {
@@ -225,7 +228,7 @@ agg_kernel(const T *__restrict__ col, const uint64_t *__restrict__ nulls, uint64
             __shared__ int32_t sov;
             if (threadIdx.x == 0) { sfr = fr; sov = 0; }
             __syncthreads();
-            if (KIND == K_SUM_SIGNED && (sfr.w3 != 0 || sfr.w2 > (uint64_t)INT64_MAX)) {
+            if (KIND == K_SUM_SIGNED && sum_check_needed(sfr)) {
                 const uint64_t seg = (n + kThreads - 1) / kThreads;
                 const uint64_t r0 = (uint64_t)threadIdx.x * seg, r1 = r0 + seg < n ? r0 + seg : n;
                 __int128 tot = 0, mx = 0, mn = 0;
@@ -258,7 +261,7 @@ agg_kernel(const T *__restrict__ col, const uint64_t *__restrict__ nulls, uint64
 
 // `gate` (async path): the aggregate record of the same call; when its magnitude sum fits int64 no prefix can overflow and the
 // whole grid returns at once
-__device__ __forceinline__ bool prefix_check_needed(const Rec *gate) { return !gate || gate->w3 != 0 || gate->w2 > (uint64_t)INT64_MAX; }
+__device__ __forceinline__ bool prefix_check_needed(const Rec *gate) { return !gate || sum_check_needed(*gate); }
 
 template <typename T>
 __global__ void prefix_seg_kernel(const T *__restrict__ col, const uint64_t *__restrict__ nulls, uint64_t n, uint64_t seg_rows, uint64_t nseg,
@@ -331,7 +334,7 @@ int run_sum_signed(ThreadCtx &t, const void *dcol, const uint64_t *dnulls, uint6
     *cnt = r.cnt;
     // |every prefix| <= sum of |v|: if that fits int64 nothing can overflow and the wrapping sum is the exact sum
     *sum = (int64_t)r.w0;
-    if (r.w3 == 0 && r.w2 <= (uint64_t)INT64_MAX) return MO_RC_SUCCESS;
+    if (!sum_check_needed(r)) return MO_RC_SUCCESS;
     // otherwise decide with the exact serial-order prefix check; when it passes, the total fits and the wrapping sum is exact
     int32_t ov = 0;
     rc = signed_prefix_overflow<T>(t, dcol, dnulls, n, &ov);
@@ -413,7 +416,7 @@ __global__ void agg_state_kernel(const Rec *rec, int op, int cls, uint64_t len, 
         double dsum = 0.0;
         if (cls == C_SIGNED) {
             bits = rec->w0; dsum = (double)(int64_t)rec->w0;
-            if ((rec->w3 != 0 || rec->w2 > (uint64_t)INT64_MAX) && ovflag && *ovflag) rc = MO_RC_OUT_OF_RANGE;
+            if (sum_check_needed(*rec) && ovflag && *ovflag) rc = MO_RC_OUT_OF_RANGE;
         } else if (cls == C_UNSIGNED) { bits = rec->w0; dsum = (double)rec->w0; if (rec->w1) rc = MO_RC_OUT_OF_RANGE; }
         else if (cls == C_FLOAT) { dsum = rec->d; memcpy(&bits, &dsum, 8); }
         else bits = rec->w0;

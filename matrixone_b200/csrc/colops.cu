@@ -41,7 +41,7 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
 // a CTA takes the next tile (atomic ticket, so every predecessor tile is already running), counts its flagged rows, publishes
 // (aggregate | inclusive prefix) in one 64-bit status word, and walks back over its predecessors' words for its exclusive prefix.
 // =========================================================================================================
-constexpr int kSelThreads = 128, kSelRows = 16, kSelTile = kSelThreads * kSelRows;
+constexpr int kSelThreads = 256, kSelRows = 32, kSelTile = kSelThreads * kSelRows;   // 8192 rows per tile = one MatrixOne block
 constexpr unsigned long long kFlagA = 1ull << 62, kFlagP = 2ull << 62, kValMask = (1ull << 62) - 1;
 
 template <typename OutT>
@@ -58,14 +58,14 @@ select_kernel(const uint8_t *__restrict__ v, const uint64_t *__restrict__ nulls,
     const uint64_t row0 = (uint64_t)tile * kSelTile + (uint64_t)threadIdx.x * kSelRows;
     unsigned mask = 0;
     if (row0 + kSelRows <= n && aligned) {
-        const int4 x = ld_stream16(v + row0);
-        const unsigned w[4] = {(unsigned)x.x, (unsigned)x.y, (unsigned)x.z, (unsigned)x.w};
+        const int4 x0 = ld_stream16(v + row0), x1 = ld_stream16(v + row0 + 16);
+        const unsigned w[8] = {(unsigned)x0.x, (unsigned)x0.y, (unsigned)x0.z, (unsigned)x0.w, (unsigned)x1.x, (unsigned)x1.y, (unsigned)x1.z, (unsigned)x1.w};
 #pragma unroll
-        for (int j = 0; j < 16; j++) mask |= (((w[j >> 2] >> (8 * (j & 3))) & 0xffu) ? 1u : 0u) << j;
+        for (int j = 0; j < 32; j++) mask |= (((w[j >> 2] >> (8 * (j & 3))) & 0xffu) ? 1u : 0u) << j;
     } else {
         for (int j = 0; j < kSelRows; j++) if (row0 + j < n && v[row0 + j]) mask |= 1u << j;
     }
-    if (nulls && row0 < n) mask &= ~(unsigned)((nulls[row0 >> 6] >> (row0 & 63)) & 0xffffu);   // 16 rows never straddle a word
+    if (nulls && row0 < n) mask &= ~(unsigned)((nulls[row0 >> 6] >> (row0 & 63)) & 0xffffffffu);   // 32 rows never straddle a word
     const unsigned cnt = __popc(mask);
     // CTA exclusive scan of cnt
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
