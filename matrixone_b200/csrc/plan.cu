@@ -18,6 +18,7 @@
 // converted to float64 (exact below 2^53); each instruction rounds once like the reference's separate nodes (no FMA contraction).
 // Group sums are accumulated with atomics: the association order is not fixed (results agree with the serial loop to ~1e-13).
 #include "common.cuh"
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -25,8 +26,8 @@ using namespace mob;
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kCtaSlots = 128;          // per-CTA group table (shared atomics)
+constexpr int kThreads = 128;
+constexpr int kCtaSlots = 64;           // per-CTA group table (shared atomics)
 constexpr int kPriv = 4;               // groups whose state every thread keeps PRIVATELY in shared memory (no atomics, no shuffles)
 constexpr uint64_t kEmptyKey = 0xffffffffffffffffull;
 
@@ -71,20 +72,6 @@ __device__ __forceinline__ void agg_fold(int kind, double *a, double p) {
     else if (kind == MO_AGG_SUM || kind == MO_AGG_AVG) atomicAdd(a, p);
 }
 
-__device__ __forceinline__ double load_as_f64(const uint8_t *p, int T, uint64_t r) {
-    switch (T) {
-    case MO_T_BOOL: case MO_T_UINT8: return (double)p[r];
-    case MO_T_INT8: return (double)reinterpret_cast<const int8_t *>(p)[r];
-    case MO_T_INT16: return (double)reinterpret_cast<const int16_t *>(p)[r];
-    case MO_T_UINT16: return (double)reinterpret_cast<const uint16_t *>(p)[r];
-    case MO_T_INT32: case MO_T_DATE: return (double)reinterpret_cast<const int32_t *>(p)[r];
-    case MO_T_UINT32: return (double)reinterpret_cast<const uint32_t *>(p)[r];
-    case MO_T_INT64: case MO_T_TIME: case MO_T_DATETIME: case MO_T_TIMESTAMP: return (double)reinterpret_cast<const int64_t *>(p)[r];
-    case MO_T_UINT64: return (double)reinterpret_cast<const uint64_t *>(p)[r];
-    case MO_T_FLOAT32: return (double)reinterpret_cast<const float *>(p)[r];
-    default: return reinterpret_cast<const double *>(p)[r];
-    }
-}
 __device__ __forceinline__ int type_bytes(int T) {
     switch (T) {
     case MO_T_BOOL: case MO_T_INT8: case MO_T_UINT8: return 1;
@@ -117,30 +104,65 @@ __global__ void plan_init_kernel(PlanGlobal G, int naggs, const mo_plan_t *P) {
     }
 }
 
+// ---- the interpreter: VECTORISED, like the reference's own execution model (one operator over a batch at a time) --------------------------
+// A CTA works on tiles of kThreads x R rows; thread t owns rows t, t + kThreads, ... of the tile.  Every operator of the plan -- column load,
+// predicate, expression node -- is decoded ONCE per tile (the `switch` on type / opcode is warp-uniform) and then applied to the thread's R
+// rows from a shared-memory register file vreg[slot][r][thread] (conflict-free: thread-minor).  That amortises the decode over R rows and puts
+// R x ncols independent loads in flight per thread.  Integer columns stay in the integer domain (raw int64 in the register file): predicates
+// on them compare as int64 when their constants are integral, so a DATE / int column that only feeds the filter never touches the slow
+// int -> float64 conversion pipe; they are converted when an expression node reads them.
+constexpr int R = 4;
+
+struct PlanAux {                       // host-prepared decode of the descriptor
+    int is_int[MO_PLAN_MAX_COLS];      // column is an integer type (raw int64 in the register file)
+    int pred_int[MO_PLAN_MAX_PREDS];   // predicate compares in the integer domain
+    long long ilo[MO_PLAN_MAX_PREDS], ihi[MO_PLAN_MAX_PREDS];
+    int need_cnt;                      // some aggregate input can be NULL (nullable column or a division): per-aggregate counts are kept
+};
+
+__device__ __forceinline__ unsigned long long load_raw(const uint8_t *p, int T, uint64_t r) {
+    switch (T) {
+    case MO_T_BOOL: case MO_T_UINT8: return (unsigned long long)p[r];
+    case MO_T_INT8: return (unsigned long long)(long long)reinterpret_cast<const int8_t *>(p)[r];
+    case MO_T_INT16: return (unsigned long long)(long long)reinterpret_cast<const int16_t *>(p)[r];
+    case MO_T_UINT16: return (unsigned long long)reinterpret_cast<const uint16_t *>(p)[r];
+    case MO_T_INT32: case MO_T_DATE: return (unsigned long long)(long long)reinterpret_cast<const int32_t *>(p)[r];
+    case MO_T_UINT32: return (unsigned long long)reinterpret_cast<const uint32_t *>(p)[r];
+    case MO_T_FLOAT32: return (unsigned long long)__double_as_longlong((double)reinterpret_cast<const float *>(p)[r]);
+    default: return reinterpret_cast<const unsigned long long *>(p)[r];     // int64 / uint64 / float64 / time types: the 8 bytes as they are
+    }
+}
+__device__ __forceinline__ double slot_f64(unsigned long long raw, bool is_int, bool is_u64) {
+    if (!is_int) return __longlong_as_double((long long)raw);
+    return is_u64 ? (double)raw : (double)(long long)raw;
+}
+
 __global__ void __launch_bounds__(kThreads)
-plan_kernel(const mo_plan_t *__restrict__ Pg, PlanCols C, uint64_t n, PlanGlobal G) {
+plan_kernel(const mo_plan_t *__restrict__ Pg, const PlanAux *__restrict__ Ag, PlanCols C, uint64_t n, PlanGlobal G) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ mo_plan_t P;
+    __shared__ PlanAux X;
     for (int i = threadIdx.x; i < (int)(sizeof(mo_plan_t) / 4); i += kThreads) reinterpret_cast<uint32_t *>(&P)[i] = reinterpret_cast<const uint32_t *>(Pg)[i];
+    for (int i = threadIdx.x; i < (int)(sizeof(PlanAux) / 4); i += kThreads) reinterpret_cast<uint32_t *>(&X)[i] = reinterpret_cast<const uint32_t *>(Ag)[i];
     __syncthreads();
     const int nslots = P.ncols + P.ninstr, naggs = P.naggs;
-    double *vreg = reinterpret_cast<double *>(smem_raw);                                   // [nslots][kThreads]
-    uint64_t *tkey = reinterpret_cast<uint64_t *>(vreg + (size_t)nslots * kThreads);       // [kCtaSlots]
+    unsigned long long *vreg = reinterpret_cast<unsigned long long *>(smem_raw);                      // [(slot * R + j) * kThreads + tid]
+    uint64_t *tkey = reinterpret_cast<uint64_t *>(vreg + (size_t)nslots * R * kThreads);              // [kCtaSlots]
     unsigned long long *tfirst = reinterpret_cast<unsigned long long *>(tkey + kCtaSlots);
     unsigned long long *trows = tfirst + kCtaSlots;
-    double *tacc = reinterpret_cast<double *>(trows + kCtaSlots);                          // [kCtaSlots][naggs]
+    double *tacc = reinterpret_cast<double *>(trows + kCtaSlots);                                     // [kCtaSlots][naggs]
     unsigned long long *tcnt = reinterpret_cast<unsigned long long *>(tacc + (size_t)kCtaSlots * naggs);
     for (int s = threadIdx.x; s < kCtaSlots; s += kThreads) {
         tkey[s] = kEmptyKey; tfirst[s] = ~0ull; trows[s] = 0;
         for (int a = 0; a < naggs; a++) { tacc[s * naggs + a] = agg_identity(P.agg[a].kind); tcnt[s * naggs + a] = 0; }
     }
     // The first kPriv distinct keys a CTA meets (a first-come dictionary, as in the Q1 kernel) get PRIVATE per-thread state in shared memory,
-    // slot-major so every access is conflict-free: a row then costs naggs x (LDS, op, STS) on its own copy -- no atomics, no shuffles.  Plans
+    // thread-minor so every access is conflict-free: a row then costs naggs x (LDS, op, STS) on its own copy -- no atomics, no shuffles.  Plans
     // with few groups (or none) live entirely here; further keys go to the shared CTA table, then to the global one.
     __shared__ unsigned long long pdict[kPriv];
-    double *pacc = reinterpret_cast<double *>(tcnt + (size_t)kCtaSlots * naggs) + threadIdx.x;   // [(slot * naggs + a) * kThreads + tid]
-    unsigned *pcnt = reinterpret_cast<unsigned *>(pacc - threadIdx.x + (size_t)kPriv * naggs * kThreads) + threadIdx.x;   // same indexing
-    unsigned *prows = pcnt - threadIdx.x + (size_t)kPriv * naggs * kThreads + threadIdx.x;       // [slot * kThreads + tid]
+    double *pacc = reinterpret_cast<double *>(tcnt + (size_t)kCtaSlots * naggs) + threadIdx.x;        // [(g * naggs + a) * kThreads + tid]
+    unsigned *pcnt = reinterpret_cast<unsigned *>(pacc - threadIdx.x + (size_t)kPriv * naggs * kThreads) + threadIdx.x;
+    unsigned *prows = pcnt - threadIdx.x + (size_t)kPriv * naggs * kThreads + threadIdx.x;            // [g * kThreads + tid]
     unsigned long long *pfirst = reinterpret_cast<unsigned long long *>(prows - threadIdx.x + (size_t)kPriv * kThreads) + threadIdx.x;
     if (threadIdx.x < kPriv) pdict[threadIdx.x] = kEmptyKey;
     for (int g = 0; g < kPriv; g++) {
@@ -152,167 +174,167 @@ plan_kernel(const mo_plan_t *__restrict__ Pg, PlanCols C, uint64_t n, PlanGlobal
     for (int g = 0; g < kPriv; g++) dk[g] = kEmptyKey;
     bool dict_full = false;
     __syncthreads();
-    double *my = vreg + threadIdx.x;
-    const uint64_t stride = (uint64_t)gridDim.x * kThreads;
-    // software prefetch: the column values of the NEXT row of this thread are loaded while the current row is evaluated (twice the bytes in flight)
-    double nxt[MO_PLAN_MAX_COLS]; unsigned nxtnull = 0;
-    auto fetch = [&](uint64_t r) {
-        nxtnull = 0;
+    unsigned long long *my = vreg + threadIdx.x;
+    const uint64_t tile_rows = (uint64_t)kThreads * R;
+    for (uint64_t base = blockIdx.x * tile_rows; base < n; base += (uint64_t)gridDim.x * tile_rows) {
+        // ---- table scan: column c -> slots [c][0..R), null-ness -> bit c of nb[j].  One type decode per column per tile.
+        unsigned nb[R];
+        bool ok[R];
 #pragma unroll
-        for (int c = 0; c < MO_PLAN_MAX_COLS; c++) {
-            if (c < P.ncols) {
-                nxt[c] = load_as_f64(C.data[c], P.col_type[c], r);
-                if (C.nulls[c] && ((C.nulls[c][r >> 6] >> (r & 63)) & 1ull)) nxtnull |= 1u << c;
+        for (int j = 0; j < R; j++) { nb[j] = 0; ok[j] = base + (uint64_t)j * kThreads + threadIdx.x < n; }
+        for (int c = 0; c < P.ncols; c++) {
+            const uint8_t *d = C.data[c]; const uint64_t *nu = C.nulls[c]; const int T = P.col_type[c];
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                const uint64_t r = base + (uint64_t)j * kThreads + threadIdx.x;
+                unsigned long long v = 0;
+                if (ok[j]) {
+                    v = load_raw(d, T, r);
+                    if (nu && ((nu[r >> 6] >> (r & 63)) & 1ull)) nb[j] |= 1u << c;
+                }
+                my[(c * R + j) * kThreads] = v;
             }
         }
-    };
-    uint64_t r = blockIdx.x * (uint64_t)kThreads + threadIdx.x;
-    if (r < n) fetch(r);
-    for (; r < n; r += stride) {
-        // ---- table scan: every referenced column value -> register-file slot c, null-ness -> bit c
-        unsigned nullbits = nxtnull;
-#pragma unroll
-        for (int c = 0; c < MO_PLAN_MAX_COLS; c++) if (c < P.ncols) my[c * kThreads] = nxt[c];
-        if (r + stride < n) fetch(r + stride);
         // ---- filter: conjunction; a NULL operand makes the conjunct not-true (filter.go:125-141 keeps rows with !null && true)
-        bool ok = true;
-        for (int j = 0; j < P.npreds; j++) {
-            const mo_plan_pred_t &q = P.pred[j];
-            const double x = my[q.col * kThreads];
-            bool t;
-            switch (q.op) {
-            case 0: t = x == q.lo; break; case 1: t = x != q.lo; break; case 2: t = x > q.lo; break;
-            case 3: t = x >= q.lo; break; case 4: t = x < q.lo; break; case 5: t = x <= q.lo; break;
-            default: t = x >= q.lo && x <= q.hi; break;   // BETWEEN, inclusive (operator_between.go:138-199)
+        for (int q = 0; q < P.npreds; q++) {
+            const mo_plan_pred_t &pr = P.pred[q];
+            const int c = pr.col, op = pr.op;
+            if (X.pred_int[q]) {
+                const long long lo = X.ilo[q], hi = X.ihi[q];
+#pragma unroll
+                for (int j = 0; j < R; j++) {
+                    const long long x = (long long)my[(c * R + j) * kThreads];
+                    const bool t = op == 0 ? x == lo : op == 1 ? x != lo : op == 2 ? x > lo : op == 3 ? x >= lo : op == 4 ? x < lo : op == 5 ? x <= lo : (x >= lo && x <= hi);
+                    ok[j] = ok[j] && t && !((nb[j] >> c) & 1u);
+                }
+            } else {
+                const double lo = pr.lo, hi = pr.hi;
+                const bool ci = X.is_int[c] != 0, cu = P.col_type[c] == MO_T_UINT64;
+#pragma unroll
+                for (int j = 0; j < R; j++) {
+                    const double x = slot_f64(my[(c * R + j) * kThreads], ci, cu);
+                    const bool t = op == 0 ? x == lo : op == 1 ? x != lo : op == 2 ? x > lo : op == 3 ? x >= lo : op == 4 ? x < lo : op == 5 ? x <= lo : (x >= lo && x <= hi);
+                    ok[j] = ok[j] && t && !((nb[j] >> c) & 1u);
+                }
             }
-            ok = ok && t && !((nullbits >> q.col) & 1u);
         }
-        if (!ok) continue;
-        // ---- projection: SSA program, one rounding per node
+        if (!(ok[0] | ok[1] | ok[2] | ok[3])) continue;
+        // ---- projection: SSA program, one rounding per node (the reference evaluates one expression node at a time too)
         for (int i = 0; i < P.ninstr; i++) {
             const mo_plan_instr_t &in = P.instr[i];
-            const int dst = P.ncols + i;
-            double v; bool isnull = false;
-            if (in.op == MO_PLAN_OP_COL) { v = my[in.a * kThreads]; isnull = (nullbits >> in.a) & 1u; }
-            else if (in.op == MO_PLAN_OP_CONST) v = in.imm;
-            else {
-                const double a = my[in.a * kThreads], b = my[in.b * kThreads];
-                isnull = ((nullbits >> in.a) | (nullbits >> in.b)) & 1u;
-                switch (in.op) {
-                case MO_PLAN_OP_ADD: v = __dadd_rn(a, b); break;
-                case MO_PLAN_OP_SUB: v = __dsub_rn(a, b); break;
-                case MO_PLAN_OP_MUL: v = __dmul_rn(a, b); break;
-                default: if (b == 0.0) { isnull = true; v = 0.0; } else v = __ddiv_rn(a, b); break;   // x / 0 -> NULL (SELECT behaviour)
-                }
-            }
-            my[dst * kThreads] = v;
-            if (isnull) nullbits |= 1u << dst;
-        }
-        // ---- group key (fillKeys, has_null mode: marker byte per column; a NULL contributes the marker only)
-        uint64_t key = 0;
-        {
-            int off = 0;
-            for (int k = 0; k < P.nkeys; k++) {
-                const int c = P.key_col[k];
-                const int sz = type_bytes(P.col_type[c]);
-                const bool isnull = (nullbits >> c) & 1u;
-                if (P.has_null_keys) { if (isnull) { key |= 1ull << (8 * off); off += 1; continue; } off += 1; }
-                uint64_t raw = 0;
-                const uint8_t *p = C.data[c] + r * (uint64_t)sz;
-                for (int b = 0; b < sz; b++) raw |= (uint64_t)p[b] << (8 * b);
-                if (off < 8) key |= raw << (8 * off);
-                off += sz;
-            }
-        }
-        const uint64_t grow = (uint64_t)P.row_base + r;
-        // ---- private dictionary (first kPriv keys of this CTA)
-        int ps = -1;
+            const int dst = P.ncols + i, op = in.op, sa = in.a, sb = in.b;
+            const bool ai = op != MO_PLAN_OP_CONST && sa < P.ncols && X.is_int[sa], au = ai && P.col_type[sa] == MO_T_UINT64;
+            const bool bi = op >= MO_PLAN_OP_ADD && sb < P.ncols && X.is_int[sb], bu = bi && P.col_type[sb] == MO_T_UINT64;
 #pragma unroll
-        for (int g = 0; g < kPriv; g++) if (dk[g] == key) ps = g;
-        if (ps < 0 && !dict_full && key != kEmptyKey) {
-            // claim or find the key in the shared dictionary, then refresh the register copy
-            bool okc = false;
+            for (int j = 0; j < R; j++) {
+                double v; bool isnull = false;
+                if (op == MO_PLAN_OP_CONST) v = in.imm;
+                else {
+                    const double a = slot_f64(my[(sa * R + j) * kThreads], ai, au);
+                    isnull = (nb[j] >> sa) & 1u;
+                    if (op == MO_PLAN_OP_COL) v = a;
+                    else {
+                        const double b = slot_f64(my[(sb * R + j) * kThreads], bi, bu);
+                        isnull = isnull || ((nb[j] >> sb) & 1u);
+                        if (op == MO_PLAN_OP_ADD) v = __dadd_rn(a, b);
+                        else if (op == MO_PLAN_OP_SUB) v = __dsub_rn(a, b);
+                        else if (op == MO_PLAN_OP_MUL) v = __dmul_rn(a, b);
+                        else if (b == 0.0) { isnull = true; v = 0.0; }     // x / 0 -> NULL (SELECT behaviour)
+                        else v = __ddiv_rn(a, b);
+                    }
+                }
+                my[(dst * R + j) * kThreads] = (unsigned long long)__double_as_longlong(v);
+                if (isnull) nb[j] |= 1u << dst;
+            }
+        }
+        // ---- group + aggregate, row by row (dictionary state is sequential)
 #pragma unroll
-            for (int g = 0; g < kPriv; g++) {
-                const unsigned long long prev = okc ? key : atomicCAS(&pdict[g], (unsigned long long)kEmptyKey, (unsigned long long)key);
-                okc = okc || prev == kEmptyKey || prev == key;
+        for (int j = 0; j < R; j++) {
+            if (!ok[j]) continue;
+            const uint64_t r = base + (uint64_t)j * kThreads + threadIdx.x;
+            const unsigned nullbits = nb[j];
+            // group key (fillKeys; has_null mode: marker byte per column, a NULL contributes the marker only) from the raw integer slots
+            uint64_t key = 0;
+            {
+                int off = 0;
+                for (int k = 0; k < P.nkeys; k++) {
+                    const int c = P.key_col[k];
+                    const int sz = type_bytes(P.col_type[c]);
+                    const bool isnull = (nullbits >> c) & 1u;
+                    if (P.has_null_keys) { if (isnull) { key |= 1ull << (8 * off); off += 1; continue; } off += 1; }
+                    uint64_t raw = my[(c * R + j) * kThreads];
+                    if (!X.is_int[c]) {   // float keys group by their stored bit pattern
+                        if (sz == 4) raw = (uint64_t)__float_as_uint((float)__longlong_as_double((long long)raw));
+                    }
+                    if (sz < 8) raw &= (1ull << (8 * sz)) - 1ull;
+                    if (off < 8) key |= raw << (8 * off);
+                    off += sz;
+                }
             }
-            bool full = true;
+            const uint64_t grow = (uint64_t)P.row_base + r;
+            // private dictionary (first kPriv keys of this CTA)
+            int ps = -1;
 #pragma unroll
-            for (int g = 0; g < kPriv; g++) { dk[g] = ((volatile unsigned long long *)pdict)[g]; full = full && dk[g] != kEmptyKey; if (dk[g] == key) ps = g; }
-            dict_full = full;
-        }
-        if (ps >= 0) {
-            prows[ps * kThreads] += 1u;
-            if (pfirst[ps * kThreads] == ~0ull) pfirst[ps * kThreads] = grow;     // a thread meets its rows in increasing order
-            for (int a = 0; a < naggs; a++) {
-                const int vs = P.agg[a].value, kind = P.agg[a].kind;
-                if (vs >= 0 && ((nullbits >> vs) & 1u)) continue;
-                const int ix = (ps * naggs + a) * kThreads;
-                pcnt[ix] += 1u;
-                if (vs < 0) continue;
-                const double v = my[vs * kThreads];
-                if (kind == MO_AGG_SUM || kind == MO_AGG_AVG) pacc[ix] = __dadd_rn(pacc[ix], v);
-                else if (v == v) {
-                    const unsigned long long kv = flt_key(v), cur = (unsigned long long)__double_as_longlong(pacc[ix]);
-                    if (kind == MO_AGG_MIN ? kv < cur : kv > cur) pacc[ix] = __longlong_as_double((long long)kv);
+            for (int g = 0; g < kPriv; g++) if (dk[g] == key) ps = g;
+            if (ps < 0 && !dict_full && key != kEmptyKey) {
+                bool okc = false;
+#pragma unroll
+                for (int g = 0; g < kPriv; g++) {
+                    const unsigned long long prev = okc ? key : atomicCAS(&pdict[g], (unsigned long long)kEmptyKey, (unsigned long long)key);
+                    okc = okc || prev == kEmptyKey || prev == key;
+                }
+                bool full = true;
+#pragma unroll
+                for (int g = 0; g < kPriv; g++) { dk[g] = ((volatile unsigned long long *)pdict)[g]; full = full && dk[g] != kEmptyKey; if (dk[g] == key) ps = g; }
+                dict_full = full;
+            }
+            if (ps >= 0) {
+                prows[ps * kThreads] += 1u;
+                if (pfirst[ps * kThreads] == ~0ull) pfirst[ps * kThreads] = grow;     // a thread meets its rows in increasing order
+                for (int a = 0; a < naggs; a++) {
+                    const int vs = P.agg[a].value, kind = P.agg[a].kind;
+                    if (vs >= 0 && ((nullbits >> vs) & 1u)) continue;
+                    const int ix = (ps * naggs + a) * kThreads;
+                    if (X.need_cnt) pcnt[ix] += 1u;
+                    if (vs < 0) continue;
+                    const double v = slot_f64(my[(vs * R + j) * kThreads], vs < P.ncols && X.is_int[vs], vs < P.ncols && P.col_type[vs] == MO_T_UINT64);
+                    if (kind == MO_AGG_SUM || kind == MO_AGG_AVG) pacc[ix] = __dadd_rn(pacc[ix], v);
+                    else if (kind != MO_AGG_COUNT && v == v) {
+                        const unsigned long long kv = flt_key(v), cur = (unsigned long long)__double_as_longlong(pacc[ix]);
+                        if (kind == MO_AGG_MIN ? kv < cur : kv > cur) pacc[ix] = __longlong_as_double((long long)kv);
+                    }
+                }
+                continue;
+            }
+            // shared CTA table, then the global table
+            int slot = -1;
+            if (key != kEmptyKey) {
+                unsigned s = (unsigned)mix64(key) & (kCtaSlots - 1);
+                for (int probes = 0; probes < kCtaSlots; probes++) {
+                    uint64_t cur = tkey[s];
+                    if (cur == key) { slot = (int)s; break; }
+                    if (cur == kEmptyKey) {
+                        cur = atomicCAS((unsigned long long *)&tkey[s], (unsigned long long)kEmptyKey, (unsigned long long)key);
+                        if (cur == kEmptyKey || cur == key) { slot = (int)s; break; }
+                    }
+                    s = (s + 1) & (kCtaSlots - 1);
                 }
             }
-            continue;
-        }
-        // ---- group slot: CTA table first, global table when it is full
-        int slot = -1;
-        if (key != kEmptyKey) {
-            unsigned s = (unsigned)mix64(key) & (kCtaSlots - 1);
-            for (int probes = 0; probes < kCtaSlots; probes++) {
-                uint64_t cur = tkey[s];
-                if (cur == key) { slot = (int)s; break; }
-                if (cur == kEmptyKey) {
-                    cur = atomicCAS((unsigned long long *)&tkey[s], (unsigned long long)kEmptyKey, (unsigned long long)key);
-                    if (cur == kEmptyKey || cur == key) { slot = (int)s; break; }
-                }
-                s = (s + 1) & (kCtaSlots - 1);
+            unsigned long long *first_p = slot >= 0 ? &tfirst[slot] : nullptr, *rows_p = slot >= 0 ? &trows[slot] : nullptr;
+            double *acc_p = slot >= 0 ? &tacc[slot * naggs] : nullptr; unsigned long long *cnt_p = slot >= 0 ? &tcnt[slot * naggs] : nullptr;
+            if (slot < 0) {
+                const uint64_t gs = global_find(G, key);
+                if (gs == ~0ull) continue;
+                first_p = &G.first_row[gs]; rows_p = &G.rows[gs]; acc_p = &G.acc[gs * naggs]; cnt_p = &G.cnt[gs * naggs];
             }
-        }
-        if (slot >= 0) {
-            // warp pre-aggregation: the lanes of this warp that hit the same slot elect a leader, which adds the peers' values in lane
-            // order and issues ONE atomic per aggregate -- with few groups (or none) the shared-memory atomics would otherwise serialise
-            const unsigned peers = __match_any_sync(__activemask(), slot);
-            const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
-            const unsigned npeers = __popc(peers);
-            if (tfirst[slot] > grow) atomicMin(&tfirst[slot], (unsigned long long)grow);
-            if (lane == leader) atomicAdd(&trows[slot], (unsigned long long)npeers);
-            for (int a = 0; a < naggs; a++) {
-                const int vs = P.agg[a].value, kind = P.agg[a].kind;
-                const bool has = vs < 0 || !((nullbits >> vs) & 1u);       // COUNT(*) counts every row; the others skip NULLs
-                const double v = (vs >= 0 && has) ? my[vs * kThreads] : 0.0;
-                if (kind == MO_AGG_MIN || kind == MO_AGG_MAX) {
-                    if (has) { agg_apply(kind, &tacc[slot * naggs + a], v); atomicAdd(&tcnt[slot * naggs + a], 1ull); }
-                    continue;
-                }
-                double sum = 0.0; unsigned cnt = 0;
-                for (unsigned m = peers; m; m &= m - 1) {
-                    const int src = __ffs(m) - 1;
-                    const double pv = __shfl_sync(peers, v, src);
-                    const unsigned pc = __shfl_sync(peers, has ? 1u : 0u, src);
-                    if (pc) { sum = cnt ? __dadd_rn(sum, pv) : pv; cnt += 1; }
-                }
-                if (lane == leader && cnt) {
-                    if (kind == MO_AGG_SUM || kind == MO_AGG_AVG) atomicAdd(&tacc[slot * naggs + a], sum);
-                    atomicAdd(&tcnt[slot * naggs + a], (unsigned long long)cnt);
-                }
-            }
-        } else {
-            const uint64_t gs = global_find(G, key);
-            if (gs == ~0ull) continue;
-            atomicMin(&G.first_row[gs], (unsigned long long)grow);
-            atomicAdd(&G.rows[gs], 1ull);
+            if (*((volatile unsigned long long *)first_p) > grow) atomicMin(first_p, (unsigned long long)grow);
+            atomicAdd(rows_p, 1ull);
             for (int a = 0; a < naggs; a++) {
                 const int vs = P.agg[a].value;
-                if (vs < 0) { atomicAdd(&G.cnt[gs * naggs + a], 1ull); continue; }
-                if ((nullbits >> vs) & 1u) continue;
-                agg_apply(P.agg[a].kind, &G.acc[gs * naggs + a], my[vs * kThreads]);
-                atomicAdd(&G.cnt[gs * naggs + a], 1ull);
+                if (vs < 0) { atomicAdd(&cnt_p[a], 1ull); continue; }            // COUNT(*)
+                if ((nullbits >> vs) & 1u) continue;                             // aggregates skip NULLs
+                agg_apply(P.agg[a].kind, &acc_p[a], slot_f64(my[(vs * R + j) * kThreads], vs < P.ncols && X.is_int[vs], vs < P.ncols && P.col_type[vs] == MO_T_UINT64));
+                atomicAdd(&cnt_p[a], 1ull);
             }
         }
     }
@@ -327,9 +349,11 @@ plan_kernel(const mo_plan_t *__restrict__ Pg, PlanCols C, uint64_t n, PlanGlobal
         atomicAdd(&G.rows[gs], (unsigned long long)prows[g * kThreads]);
         for (int a = 0; a < naggs; a++) {
             const int ix = (g * naggs + a) * kThreads;
-            if (pcnt[ix] == 0u) continue;
+            // without per-aggregate counts (no nullable input): every row of the group fed every aggregate
+            const unsigned c = X.need_cnt ? pcnt[ix] : prows[g * kThreads];
+            if (c == 0u) continue;
             agg_fold(P.agg[a].kind, &G.acc[gs * naggs + a], pacc[ix]);
-            atomicAdd(&G.cnt[gs * naggs + a], (unsigned long long)pcnt[ix]);
+            atomicAdd(&G.cnt[gs * naggs + a], (unsigned long long)c);
         }
     }
     // ---- and the shared CTA table
@@ -581,29 +605,53 @@ int xcall_plan(mo_xcall_args_t *args, uint64_t len) {
     uint32_t *used = (uint32_t *)st.tmp((cap + 1) * 4);
     unsigned long long *nused = (unsigned long long *)st.tmp(16);
     mo_plan_t *dP = (mo_plan_t *)st.tmp(sizeof(mo_plan_t));
+    PlanAux *dX = (PlanAux *)st.tmp(sizeof(PlanAux));
     if (st.failed) { st.finish(); return MO_RC_INTERNAL_ERROR; }
     G.overflow = (unsigned *)(nused + 1);
     MOB_CUDA_TRY(cudaMemsetAsync(nused, 0, 16, t.stream));
     // the descriptor travels through the thread's pinned staging buffer (the caller's copy may be pageable and short-lived)
-    if (sizeof(mo_plan_t) > t.pinned_sz) { st.finish(); set_error("plan: descriptor larger than the staging buffer"); return MO_RC_INTERNAL_ERROR; }
+    if (sizeof(mo_plan_t) + sizeof(PlanAux) > t.pinned_sz) { st.finish(); set_error("plan: descriptor larger than the staging buffer"); return MO_RC_INTERNAL_ERROR; }
+    // decode once on the host: which columns stay in the integer domain, which predicates compare there, whether per-aggregate counts are needed
+    PlanAux X;
+    memset(&X, 0, sizeof X);
+    for (int c = 0; c < P.ncols; c++) X.is_int[c] = !(P.col_type[c] == MO_T_FLOAT32 || P.col_type[c] == MO_T_FLOAT64);
+    for (int j = 0; j < P.npreds; j++) {
+        const mo_plan_pred_t &q = P.pred[j];
+        auto integral = [](double v) { return v == std::floor(v) && std::fabs(v) < 9007199254740992.0; };
+        const bool ok = X.is_int[q.col] && P.col_type[q.col] != MO_T_UINT64 && integral(q.lo) && (q.op != 6 || integral(q.hi));
+        X.pred_int[j] = ok;
+        if (ok) { X.ilo[j] = (long long)q.lo; X.ihi[j] = q.op == 6 ? (long long)q.hi : 0; }
+    }
+    {
+        // an aggregate input can be NULL iff a nullable column or a division feeds it (null-ness only flows forward through the SSA program)
+        bool maybe[MO_PLAN_MAX_COLS + MO_PLAN_MAX_INSTR];
+        for (int c = 0; c < P.ncols; c++) maybe[c] = args[2 + c].pnulls != nullptr;
+        for (int i = 0; i < P.ninstr; i++) {
+            const mo_plan_instr_t &in = P.instr[i];
+            maybe[P.ncols + i] = in.op == MO_PLAN_OP_CONST ? false : in.op == MO_PLAN_OP_COL ? maybe[in.a] : (in.op == MO_PLAN_OP_DIV || maybe[in.a] || maybe[in.b]);
+        }
+        for (int a = 0; a < P.naggs; a++) if (P.agg[a].value >= 0 && maybe[P.agg[a].value]) X.need_cnt = 1;
+    }
     MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));
     memcpy(t.pinned, &P, sizeof P);
+    memcpy((char *)t.pinned + sizeof P, &X, sizeof X);
     MOB_CUDA_TRY(cudaMemcpyAsync(dP, t.pinned, sizeof P, cudaMemcpyHostToDevice, t.stream));
+    MOB_CUDA_TRY(cudaMemcpyAsync(dX, (char *)t.pinned + sizeof P, sizeof X, cudaMemcpyHostToDevice, t.stream));
     const unsigned igrid = (unsigned)((cap + 1 + 255) / 256 > (uint64_t)num_sms() * 8 ? (uint64_t)num_sms() * 8 : (cap + 1 + 255) / 256);
     plan_init_kernel<<<igrid, 256, 0, t.stream>>>(G, P.naggs, dP);
     MOB_LAUNCH_CHECK();
-    const size_t smem = (size_t)(P.ncols + P.ninstr) * kThreads * 8 + (size_t)kCtaSlots * (24 + 16 * (size_t)P.naggs) +
+    const size_t smem = (size_t)(P.ncols + P.ninstr) * R * kThreads * 8 + (size_t)kCtaSlots * (24 + 16 * (size_t)P.naggs) +
                         (size_t)kPriv * kThreads * ((size_t)P.naggs * 12 + 12);
     static size_t attr_smem = 0;
     if (smem > attr_smem) { MOB_CUDA_TRY(cudaFuncSetAttribute(plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; }
     if (len) {
         int ctas = (int)((220 * 1024) / (smem + 2048));
-        if (ctas > 6) ctas = 6; if (ctas < 1) ctas = 1;
+        if (ctas > 8) ctas = 8; if (ctas < 1) ctas = 1;
         int grid = num_sms() * ctas;
-        const uint64_t work = (len + kThreads - 1) / kThreads;
+        const uint64_t work = (len + (uint64_t)kThreads * R - 1) / ((uint64_t)kThreads * R);
         if ((uint64_t)grid > work) grid = (int)work;
         cudaEventRecord(t.kev0, t.stream);
-        plan_kernel<<<grid, kThreads, smem, t.stream>>>(dP, C, len, G);
+        plan_kernel<<<grid, kThreads, smem, t.stream>>>(dP, dX, C, len, G);
         cudaEventRecord(t.kev1, t.stream);
         MOB_LAUNCH_CHECK();
     }
