@@ -153,6 +153,14 @@ typedef struct mo_xcall_args_t {
 #define MO_XCALL_GO_COSSIM_F64 109
 #define MO_XCALL_GO_L1_F32 110   /* metric.L1Distance, distance_func.go:112-154 (l1_norm of the difference) */
 #define MO_XCALL_GO_L1_F64 111
+/* normalize_l2(v): moarray.NormalizeL2 (pkg/vectorize/moarray/external.go:262-285): a VECTOR-valued result.
+ * args: [0] the result varlena vector (pdata -> 24 * len cells, parea / areaSz -> its area, at least as large as the
+ * argument's: the result area MIRRORS the argument's layout -- cell i gets the same (offset, length), inline cells
+ * stay inline; pnulls = the result nulls, rows set there are skipped and get an empty cell) ; [1] the argument vector
+ * (dataSz == 24: const).  sumSquares in float64 in index order, normalized[i] = T(float64(v[i]) / norm), norm == 0
+ * copies the row; an empty non-null vector -> MO_RC_INTERNAL_ERROR "cannot normalize empty vector". */
+#define MO_XCALL_GO_NORMALIZE_L2_F32 112
+#define MO_XCALL_GO_NORMALIZE_L2_F64 113
 
 /* --- new: single-column aggregates (aggexec sumavg2.go / count2.go / minmax2.go semantics, no group-by = H0).
  * funcId = MO_XCALL_AGG(op, T).  args: [0] result: pdata -> one 8-byte value (int64 / uint64 / float64, or the

@@ -34,6 +34,7 @@ XCALL_GO_L2_F32, XCALL_GO_L2_F64, XCALL_GO_L2SQ_F32, XCALL_GO_L2SQ_F64 = 100, 10
 XCALL_GO_IP_F32, XCALL_GO_IP_F64, XCALL_GO_COSDIST_F32, XCALL_GO_COSDIST_F64 = 104, 105, 106, 107
 XCALL_GO_COSSIM_F32, XCALL_GO_COSSIM_F64 = 108, 109
 XCALL_GO_L1_F32, XCALL_GO_L1_F64 = 110, 111
+XCALL_GO_NORMALIZE_L2_F32, XCALL_GO_NORMALIZE_L2_F64 = 112, 113
 AGG_SUM, AGG_COUNT, AGG_MIN, AGG_MAX, AGG_AVG = 0, 1, 2, 3, 4
 
 

@@ -25,7 +25,7 @@ namespace {
 
 constexpr int kThreads = 128;   // 4 warps; every warp owns a shared-memory ring
 
-constexpr unsigned ST_DIM = 1u, ST_AREA = 2u, ST_ZERO = 4u;
+constexpr unsigned ST_DIM = 1u, ST_AREA = 2u, ST_ZERO = 4u, ST_EMPTY = 8u;
 
 struct Ref { const uint8_t *ptr; uint32_t len; bool ok; };
 
@@ -76,8 +76,9 @@ rowdist_kernel(double *__restrict__ res, const uint64_t *__restrict__ rnulls, ui
         const uint8_t *px = nullptr, *pq = nullptr;
         if (live) {
             Ref a = varlena_ref(cells1, const1 ? 0 : i, area1, area1Sz);
-            Ref b = varlena_ref(cells2, const2 ? 0 : i, area2, area2Sz);
+            Ref b = Acc::kOne ? a : varlena_ref(cells2, const2 ? 0 : i, area2, area2Sz);
             if (!a.ok || !b.ok) st |= ST_AREA;
+            else if (Acc::kOne && a.len < sizeof(T)) st |= ST_EMPTY;   // "cannot normalize empty vector", distance_func.go:413-415
             else if (Acc::kXc) {
                 if ((uint64_t)xc_dim * sizeof(T) > a.len || (uint64_t)xc_dim * sizeof(T) > b.len) st |= ST_DIM;   // would read out of bounds
                 else { dim = xc_dim; good = true; }
@@ -93,6 +94,7 @@ rowdist_kernel(double *__restrict__ res, const uint64_t *__restrict__ rnulls, ui
             double out; bool write = true;
             if (KIND == K_XC_L2) out = sqrt(acc.dsum);
             else if (KIND == K_XC_L2SQ) out = acc.dsum;
+            else if (KIND == K_GO_NORM) out = sqrt(acc.dsum);                    // norm := math.Sqrt(sumSquares), distance_func.go:422
             else if (KIND == K_GO_L2SQ || KIND == K_GO_L1) out = (double)acc.sum;
             else if (KIND == K_GO_L2) out = (double)(T)sqrt((double)acc.sum);  // distance_func.go:35-42
             else if (KIND == K_GO_IP) out = (double)(-acc.sum);               // InnerProduct returns -sum, distance_func.go:172-205
@@ -169,6 +171,115 @@ int run_rowdist(mo_xcall_args_t *args, uint64_t len) {
     return MO_RC_SUCCESS;
 }
 
+// ---- NormalizeL2Array (moarray/external.go:262-285 == metric.NormalizeL2, distance_func.go:411-434): a VECTOR-valued result -------------
+// Pass 1 = rowdist_kernel<T, K_GO_NORM> (the row's norm, float64, summed strictly in index order by the row's lane).  Pass 2 below: one warp
+// per row writes normalized[i] = T(float64(val) / norm) (norm == 0: the row is copied), and the result's varlena cell.  Layout of the
+// result: the cell of row i has the SAME (offset, length) as the input's cell -- the result area mirrors the input area, inline cells stay
+// inline -- so no prefix sum over lengths is needed and a const input yields a const-shaped result (every cell points at the one vector).
+// Algorithmic bytes per row: 2 reads + 1 write of dim * sizeof(T) (the second read is served from L2 when the rows are short), 48 of cells.
+template <typename T>
+__global__ void __launch_bounds__(256)
+normalize_write_kernel(uint8_t *__restrict__ ocells, uint8_t *__restrict__ oarea, const uint64_t *__restrict__ rnulls, uint64_t n,
+                       const uint8_t *__restrict__ cells, const uint8_t *__restrict__ area, uint64_t areaSz, bool cst, const double *__restrict__ norms) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t i = warp; i < n; i += nwarps) {
+        uint8_t *oc = ocells + 24 * i;
+        if (bm_test(rnulls, i)) { if (lane < 24) oc[lane] = 0; continue; }          // NULL row: an empty inline cell
+        const uint8_t *c = cells + 24 * (cst ? 0 : i);
+        const Ref a = varlena_ref(cells, cst ? 0 : i, area, areaSz);
+        if (!a.ok || a.len < sizeof(T)) continue;                                   // reported by pass 1
+        const int dim = (int)(a.len / sizeof(T));
+        const double norm = norms[i];
+        const bool inl = c[0] <= MO_VARLENA_INLINE_SZ;
+        if (inl) {   // <= 23 bytes: the vector lives in the cell
+            if (lane == 0) oc[0] = c[0];
+            if (lane >= 1 && lane < 24 && lane > (int)a.len) oc[lane] = 0;
+            if (lane < dim) {
+                const T v = load1<T>(a.ptr + (size_t)lane * sizeof(T));
+                const T o = norm == 0.0 ? v : (T)__ddiv_rn((double)v, norm);
+                uint8_t b[sizeof(T)]; memcpy(b, &o, sizeof(T));
+#pragma unroll
+                for (int k = 0; k < (int)sizeof(T); k++) oc[1 + lane * sizeof(T) + k] = b[k];
+            }
+            // bytes between dim * sizeof(T) and a.len (a length that is not a multiple of the element size) are copied
+            if (lane < (int)a.len - dim * (int)sizeof(T)) oc[1 + dim * sizeof(T) + lane] = a.ptr[dim * sizeof(T) + lane];
+            continue;
+        }
+        if (lane < 24) oc[lane] = c[lane];
+        if (cst && i != 0) continue;                                                 // a const input: one vector, written once
+        uint8_t *dst = oarea + (a.ptr - area);
+        if (((((uintptr_t)a.ptr) | ((uintptr_t)dst)) & 15) == 0) {
+            constexpr int EPV = 16 / (int)sizeof(T);
+            const int nv = dim / EPV;
+            for (int v = lane; v < nv; v += 32) {
+                const int4 raw = ld_stream16(a.ptr + 16 * (size_t)v);
+                T x[EPV]; memcpy(x, &raw, 16);
+#pragma unroll
+                for (int k = 0; k < EPV; k++) x[k] = norm == 0.0 ? x[k] : (T)__ddiv_rn((double)x[k], norm);
+                int4 o; memcpy(&o, x, 16);
+                *reinterpret_cast<int4 *>(dst + 16 * (size_t)v) = o;
+            }
+            for (int e = nv * EPV + lane; e < dim; e += 32) {
+                const T v = load1<T>(a.ptr + (size_t)e * sizeof(T));
+                const T o = norm == 0.0 ? v : (T)__ddiv_rn((double)v, norm);
+                memcpy(dst + (size_t)e * sizeof(T), &o, sizeof(T));
+            }
+        } else {
+            for (int e = lane; e < dim; e += 32) {
+                const T v = load1<T>(a.ptr + (size_t)e * sizeof(T));
+                const T o = norm == 0.0 ? v : (T)__ddiv_rn((double)v, norm);
+                uint8_t b[sizeof(T)]; memcpy(b, &o, sizeof(T));
+#pragma unroll
+                for (int k = 0; k < (int)sizeof(T); k++) dst[(size_t)e * sizeof(T) + k] = b[k];
+            }
+        }
+    }
+}
+
+template <typename T>
+int run_normalize(mo_xcall_args_t *args, uint64_t len) {
+    ThreadCtx &t = tctx();
+    if (!t.ready) return MO_RC_INTERNAL_ERROR;
+    if (len == 0) return MO_RC_SUCCESS;
+    const bool c1 = args[1].dataSz == MO_VARLENA_SZ && len > 1;
+    if (!args[0].pdata || args[0].dataSz < 24 * len) { set_error("normalize_l2: result vector shorter than len"); return MO_RC_INVALID_ARGUMENT; }
+    if (!c1 && args[1].dataSz < 24 * len) { set_error("normalize_l2: argument vector shorter than len"); return MO_RC_INVALID_ARGUMENT; }
+    if (args[1].areaSz && (!args[0].parea || args[0].areaSz < args[1].areaSz)) { set_error("normalize_l2: the result area must be at least as large as the argument's (it mirrors its layout)"); return MO_RC_INVALID_ARGUMENT; }
+    Stager st(t);
+    const uint8_t *cells = (const uint8_t *)st.in(args[1].pdata, c1 ? 24 : 24 * len);
+    const uint8_t *area = (const uint8_t *)st.in(args[1].parea, args[1].areaSz);
+    const uint64_t *rn = (const uint64_t *)st.in(args[0].pnulls, args[0].pnulls ? ((len + 63) / 64) * 8 : 0);
+    uint8_t *ocells = (uint8_t *)st.out(args[0].pdata, 24 * len);
+    uint8_t *oarea = args[1].areaSz ? (uint8_t *)st.out(args[0].parea, args[1].areaSz, true) : nullptr;
+    double *norms = (double *)st.tmp(8 * len);
+    unsigned *dstatus = (unsigned *)st.tmp(4);
+    if (st.failed) { st.finish(); return MO_RC_INTERNAL_ERROR; }
+    MOB_CUDA_TRY(cudaMemsetAsync(dstatus, 0, 4, t.stream));
+    const uint64_t warps = (len + 31) / 32;
+    uint64_t blocks = (warps + kThreads / 32 - 1) / (kThreads / 32);
+    if (blocks > (uint64_t)num_sms() * 2) blocks = (uint64_t)num_sms() * 2;
+    const size_t smem = (size_t)(kThreads / 32) * RingCfg<false>::kStages * RingCfg<false>::kStageBytes;
+    static bool attr = false;
+    if (!attr) { MOB_CUDA_TRY(cudaFuncSetAttribute(rowdist_kernel<T, K_GO_NORM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    cudaEventRecord(t.kev0, t.stream);
+    rowdist_kernel<T, K_GO_NORM, false><<<(unsigned)blocks, kThreads, smem, t.stream>>>(norms, rn, len, cells, area, args[1].areaSz, c1, cells, area, args[1].areaSz, c1, dstatus);
+    MOB_LAUNCH_CHECK();
+    uint64_t wblocks = (len + 7) / 8;
+    if (wblocks > (uint64_t)num_sms() * 8) wblocks = (uint64_t)num_sms() * 8;
+    normalize_write_kernel<T><<<(unsigned)wblocks, 256, 0, t.stream>>>(ocells, oarea, rn, len, cells, area, args[1].areaSz, c1, norms);
+    cudaEventRecord(t.kev1, t.stream);
+    MOB_LAUNCH_CHECK();
+    unsigned status = 0;
+    int rc = read_back(t, &status, dstatus, 4);
+    int frc = st.finish();
+    if (rc) return rc;
+    if (frc) return frc;
+    if (status & ST_AREA) { set_error("normalize_l2: varlena cell points outside its area"); return MO_RC_INVALID_ARGUMENT; }
+    if (status & ST_EMPTY) { set_error("cannot normalize empty vector"); return MO_RC_INTERNAL_ERROR; }
+    return MO_RC_SUCCESS;
+}
+
 }  // namespace
 
 namespace mob {
@@ -191,6 +302,8 @@ int xcall_rowdist(int64_t funcId, mo_xcall_args_t *args, uint64_t len) {
     case MO_XCALL_GO_COSSIM_F64: return run_rowdist<double, K_GO_COSSIM>(args, len);
     case MO_XCALL_GO_L1_F32: return run_rowdist<float, K_GO_L1>(args, len);
     case MO_XCALL_GO_L1_F64: return run_rowdist<double, K_GO_L1>(args, len);
+    case MO_XCALL_GO_NORMALIZE_L2_F32: return run_normalize<float>(args, len);
+    case MO_XCALL_GO_NORMALIZE_L2_F64: return run_normalize<double>(args, len);
     }
     return -1;
 }

@@ -127,7 +127,7 @@ __device__ void go_cos_parts(const uint8_t *p, const uint8_t *q, int dim, int la
     }
 }
 
-enum Kind { K_XC_L2 = 0, K_XC_L2SQ, K_GO_L2, K_GO_L2SQ, K_GO_IP, K_GO_COSDIST, K_GO_COSSIM, K_GO_L1 };
+enum Kind { K_XC_L2 = 0, K_XC_L2SQ, K_GO_L2, K_GO_L2SQ, K_GO_IP, K_GO_COSDIST, K_GO_COSSIM, K_GO_L1, K_GO_NORM };
 
 // ---- lane-per-row batches over a per-warp cp.async ring (see distance.cu for the mapping) ---------------------------------------
 constexpr int kTileRows = 32, kSliceBytes = 128, kPitch = 144;   // 144-byte row pitch: LDS.128 by the row owners is conflict-free
@@ -157,12 +157,16 @@ __device__ __forceinline__ void copy16_unaligned(unsigned char *dst, const uint8
 template <typename T, int KIND> struct RowAcc {
     static constexpr bool kCos = KIND == K_GO_COSDIST || KIND == K_GO_COSSIM;
     static constexpr bool kXc = KIND == K_XC_L2 || KIND == K_XC_L2SQ;
+    static constexpr bool kOne = KIND == K_GO_NORM;   // one-operand kind: the q side is never staged nor read
     static constexpr int CH = kCos ? 4 : 8;          // chunk of the Go loop (distance_func.go: 8-way, cosine 4-way)
     T sum = 0, n1 = 0, n2 = 0; double dsum = 0.0;
     __device__ __forceinline__ void chunk(const T *a, const T *b) {   // CH elements, exact association of the Go source
         if (kXc) {
 #pragma unroll
             for (int j = 0; j < CH; j++) { T d = sub_rn(a[j], b[j]); dsum = __dadd_rn(dsum, (double)mul_rn(d, d)); }
+        } else if (kOne) {   // NormalizeL2, distance_func.go:417-421: sumSquares += float64(val) * float64(val), strictly in index order
+#pragma unroll
+            for (int j = 0; j < CH; j++) dsum = __dadd_rn(dsum, __dmul_rn((double)a[j], (double)a[j]));
         } else if (kCos) {
             sum = add_rn(sum, add_rn(add_rn(add_rn(mul_rn(a[0], b[0]), mul_rn(a[1], b[1])), mul_rn(a[2], b[2])), mul_rn(a[3], b[3])));
             n1 = add_rn(n1, add_rn(add_rn(add_rn(mul_rn(a[0], a[0]), mul_rn(a[1], a[1])), mul_rn(a[2], a[2])), mul_rn(a[3], a[3])));
@@ -184,6 +188,7 @@ template <typename T, int KIND> struct RowAcc {
     }
     __device__ __forceinline__ void elem(T a, T b) {   // remainder loops of the Go functions
         if (kXc) { T d = sub_rn(a, b); dsum = __dadd_rn(dsum, (double)mul_rn(d, d)); }
+        else if (kOne) dsum = __dadd_rn(dsum, __dmul_rn((double)a, (double)a));
         else if (kCos) { sum = add_rn(sum, mul_rn(a, b)); n1 = add_rn(n1, mul_rn(a, a)); n2 = add_rn(n2, mul_rn(b, b)); }
         else if (KIND == K_GO_IP) sum = add_rn(sum, mul_rn(a, b));
         else if (KIND == K_GO_L1) { T d = sub_rn(a, b); sum = add_rn(sum, d < 0 ? -d : d); }
@@ -238,7 +243,7 @@ __device__ __forceinline__ RowAcc<T, KIND> row_batch(unsigned char *ring, int la
                     }
                 }
             }
-            if (!TWO && lane < 8) {
+            if (!TWO && !Acc::kOne && lane < 8) {
                 if (cq_al) cp_async16(sb + kTileBytes + lane * 16, cq + (size_t)s * kSliceBytes + (size_t)lane * 16);
                 else copy16_unaligned(sp + kTileBytes + lane * 16, cq + (size_t)s * kSliceBytes + (size_t)lane * 16);
             }

@@ -112,26 +112,16 @@ __global__ void plan_init_kernel(PlanGlobal G, int naggs, const mo_plan_t *P) {
 // on them compare as int64 when their constants are integral, so a DATE / int column that only feeds the filter never touches the slow
 // int -> float64 conversion pipe; they are converted when an expression node reads them.
 constexpr int R = 4;
+constexpr int kGroup = 4;      // columns whose loads are issued together
 
 struct PlanAux {                       // host-prepared decode of the descriptor
     int is_int[MO_PLAN_MAX_COLS];      // column is an integer type (raw int64 in the register file)
+    int sz[MO_PLAN_MAX_COLS];          // element width in bytes
     int pred_int[MO_PLAN_MAX_PREDS];   // predicate compares in the integer domain
     long long ilo[MO_PLAN_MAX_PREDS], ihi[MO_PLAN_MAX_PREDS];
     int need_cnt;                      // some aggregate input can be NULL (nullable column or a division): per-aggregate counts are kept
 };
 
-__device__ __forceinline__ unsigned long long load_raw(const uint8_t *p, int T, uint64_t r) {
-    switch (T) {
-    case MO_T_BOOL: case MO_T_UINT8: return (unsigned long long)p[r];
-    case MO_T_INT8: return (unsigned long long)(long long)reinterpret_cast<const int8_t *>(p)[r];
-    case MO_T_INT16: return (unsigned long long)(long long)reinterpret_cast<const int16_t *>(p)[r];
-    case MO_T_UINT16: return (unsigned long long)reinterpret_cast<const uint16_t *>(p)[r];
-    case MO_T_INT32: case MO_T_DATE: return (unsigned long long)(long long)reinterpret_cast<const int32_t *>(p)[r];
-    case MO_T_UINT32: return (unsigned long long)reinterpret_cast<const uint32_t *>(p)[r];
-    case MO_T_FLOAT32: return (unsigned long long)__double_as_longlong((double)reinterpret_cast<const float *>(p)[r]);
-    default: return reinterpret_cast<const unsigned long long *>(p)[r];     // int64 / uint64 / float64 / time types: the 8 bytes as they are
-    }
-}
 __device__ __forceinline__ double slot_f64(unsigned long long raw, bool is_int, bool is_u64) {
     if (!is_int) return __longlong_as_double((long long)raw);
     return is_u64 ? (double)raw : (double)(long long)raw;
@@ -177,22 +167,55 @@ plan_kernel(const mo_plan_t *__restrict__ Pg, const PlanAux *__restrict__ Ag, Pl
     unsigned long long *my = vreg + threadIdx.x;
     const uint64_t tile_rows = (uint64_t)kThreads * R;
     for (uint64_t base = blockIdx.x * tile_rows; base < n; base += (uint64_t)gridDim.x * tile_rows) {
-        // ---- table scan: column c -> slots [c][0..R), null-ness -> bit c of nb[j].  One type decode per column per tile.
+        // ---- table scan: column c -> slots [c][0..R), null-ness -> bit c of nb[j].  Columns are taken kGroup at a time: first ALL their loads are
+        // issued (raw bits by element width, nothing consumes them yet, so kGroup x R loads per thread are in flight), then they are widened by
+        // type and stored.  (Loading and storing column by column serialises on every load: a generic pointer may alias shared memory.)
         unsigned nb[R];
         bool ok[R];
 #pragma unroll
         for (int j = 0; j < R; j++) { nb[j] = 0; ok[j] = base + (uint64_t)j * kThreads + threadIdx.x < n; }
-        for (int c = 0; c < P.ncols; c++) {
-            const uint8_t *d = C.data[c]; const uint64_t *nu = C.nulls[c]; const int T = P.col_type[c];
+        for (int c0 = 0; c0 < P.ncols; c0 += kGroup) {
+            unsigned long long raw[kGroup][R], nw[kGroup][R];
 #pragma unroll
-            for (int j = 0; j < R; j++) {
-                const uint64_t r = base + (uint64_t)j * kThreads + threadIdx.x;
-                unsigned long long v = 0;
-                if (ok[j]) {
-                    v = load_raw(d, T, r);
-                    if (nu && ((nu[r >> 6] >> (r & 63)) & 1ull)) nb[j] |= 1u << c;
+            for (int g = 0; g < kGroup; g++) {
+                const int c = c0 + g;
+                if (c < P.ncols) {
+                    const uint8_t *d = C.data[c]; const uint64_t *nu = C.nulls[c];
+                    const int sz = X.sz[c];
+                    const uint64_t r0 = base + threadIdx.x;
+                    if (sz == 8) {
+#pragma unroll
+                        for (int j = 0; j < R; j++) raw[g][j] = ok[j] ? __ldg(reinterpret_cast<const unsigned long long *>(d) + r0 + (uint64_t)j * kThreads) : 0ull;
+                    } else if (sz == 4) {
+#pragma unroll
+                        for (int j = 0; j < R; j++) raw[g][j] = ok[j] ? (unsigned long long)__ldg(reinterpret_cast<const unsigned *>(d) + r0 + (uint64_t)j * kThreads) : 0ull;
+                    } else if (sz == 2) {
+#pragma unroll
+                        for (int j = 0; j < R; j++) raw[g][j] = ok[j] ? (unsigned long long)__ldg(reinterpret_cast<const unsigned short *>(d) + r0 + (uint64_t)j * kThreads) : 0ull;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < R; j++) raw[g][j] = ok[j] ? (unsigned long long)__ldg(d + r0 + (uint64_t)j * kThreads) : 0ull;
+                    }
+#pragma unroll
+                    for (int j = 0; j < R; j++) nw[g][j] = (nu && ok[j]) ? __ldg(reinterpret_cast<const unsigned long long *>(nu) + ((r0 + (uint64_t)j * kThreads) >> 6)) : 0ull;
                 }
-                my[(c * R + j) * kThreads] = v;
+            }
+#pragma unroll
+            for (int g = 0; g < kGroup; g++) {
+                const int c = c0 + g;
+                if (c < P.ncols) {
+                    const int T = P.col_type[c];
+#pragma unroll
+                    for (int j = 0; j < R; j++) {
+                        unsigned long long v = raw[g][j];
+                        if (T == MO_T_INT8) v = (unsigned long long)(long long)(int8_t)v;
+                        else if (T == MO_T_INT16) v = (unsigned long long)(long long)(int16_t)v;
+                        else if (T == MO_T_INT32 || T == MO_T_DATE) v = (unsigned long long)(long long)(int32_t)v;
+                        else if (T == MO_T_FLOAT32) v = (unsigned long long)__double_as_longlong((double)__uint_as_float((unsigned)v));
+                        my[(c * R + j) * kThreads] = v;
+                        nb[j] |= (unsigned)((nw[g][j] >> ((base + (uint64_t)j * kThreads + threadIdx.x) & 63)) & 1ull) << c;
+                    }
+                }
             }
         }
         // ---- filter: conjunction; a NULL operand makes the conjunct not-true (filter.go:125-141 keeps rows with !null && true)
@@ -614,7 +637,7 @@ int xcall_plan(mo_xcall_args_t *args, uint64_t len) {
     // decode once on the host: which columns stay in the integer domain, which predicates compare there, whether per-aggregate counts are needed
     PlanAux X;
     memset(&X, 0, sizeof X);
-    for (int c = 0; c < P.ncols; c++) X.is_int[c] = !(P.col_type[c] == MO_T_FLOAT32 || P.col_type[c] == MO_T_FLOAT64);
+    for (int c = 0; c < P.ncols; c++) { X.is_int[c] = !(P.col_type[c] == MO_T_FLOAT32 || P.col_type[c] == MO_T_FLOAT64); X.sz[c] = tbytes(P.col_type[c]); }
     for (int j = 0; j < P.npreds; j++) {
         const mo_plan_pred_t &q = P.pred[j];
         auto integral = [](double v) { return v == std::floor(v) && std::fabs(v) < 9007199254740992.0; };

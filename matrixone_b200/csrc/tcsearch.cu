@@ -63,6 +63,8 @@ struct TcSmemT {
     float xn[2][BN];                          // |x|^2 of the current tile's rows (double buffered with the accumulators)
     float scratch[32][BM];                    // epilogue slow path: a thread's 32 distances of the current chunk, [column][thread]
     unsigned long long full[TcCfg<PAIR>::kStages], empty[TcCfg<PAIR>::kStages], tmem_full[2], tmem_empty[2];
+    unsigned long long sched_full[2], sched_empty[2];   // dynamic unit feed (single-CTA units): the producer publishes the next unit index
+    int sched_unit[2];
     unsigned tmem_base;
 };
 
@@ -184,8 +186,15 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                      // cross-unit threshold sharing (qbound == nullptr: off): the units of one query run on different SMs at
                      // different times; each publishes an upper bound of the query's k-th real distance and prunes with the best one
                      float *qbound, const int *__restrict__ row_query, const float *__restrict__ alonorm,
-                     const float *__restrict__ xmax2, int one_term, int topk, float rel_margin, float abs_margin) {
+                     const float *__restrict__ xmax2, int one_term, int topk, float rel_margin, float abs_margin,
+                     // dynamic unit feed (nullptr: unit u = worker, worker + nworkers, ...): the producer thread takes the next unit from this
+                     // counter when it has issued the last load of the current one, and hands the index to the MMA and epilogue warps through a
+                     // two-slot shared-memory queue.  Units are ordered list-major, so the query tiles of one IVF list start within a few
+                     // microseconds of each other on different SMs and stream the list's B' tiles through L2 together (with the static deal they
+                     // drifted apart and every tile of a list re-read it from HBM: 2.5 x the algorithmic bytes), and the tail is balanced.
+                     int *sched) {
     using Cfg = TcCfg<PAIR>;
+    const bool dyn = !PAIR && sched != nullptr;
     constexpr int STAGES = Cfg::kStages;
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B atoms need 1024-byte alignment in the shared window: align by hand (the launch adds 1024 spare bytes)
@@ -198,6 +207,7 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
         for (int a = 0; a < 2; a++) { mbar_init(&S.tmem_full[a], 1); mbar_init(&S.tmem_empty[a], PAIR ? 8 : 4); }
+        for (int a = 0; a < 2; a++) { mbar_init(&S.sched_full[a], 1); mbar_init(&S.sched_empty[a], 1 + 128); }   // readers: the MMA thread + 128 epilogue threads
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -220,7 +230,20 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         // ===== TMA producer (one thread; in a pair both CTAs run it, each for its own rows) =====
         if (lane == 0) {
             int stage = 0; unsigned phase = 0;
-            for (int u = worker; u < nunits; u += nworkers) {
+            for (int it = 0;; it++) {
+                int u;
+                if (dyn) {
+                    const int slot = it & 1;
+                    mbar_wait(&S.sched_empty[slot], ((it >> 1) & 1) ^ 1);
+                    u = atomicAdd(sched, 1);
+                    if (u >= nunits) u = -1;
+                    *(volatile int *)&S.sched_unit[slot] = u;
+                    mbar_arrive(&S.sched_full[slot]);        // release: the index is visible to whoever observes the phase
+                } else {
+                    u = worker + it * nworkers;
+                    if (u >= nunits) u = -1;
+                }
+                if (u < 0) break;
                 const TcUnit U = units[u];
                 for (int n0 = U.n_begin; n0 < U.n_end; n0 += BN) {
                     for (int kb = 0; kb < nkb; kb++) {
@@ -245,7 +268,18 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         // ===== MMA issuer (one thread of the leader CTA) =====
         if (lane == 0 && rank == 0) {
             int stage = 0; unsigned phase = 0; unsigned tile = 0;
-            for (int u = worker; u < nunits; u += nworkers) {
+            for (int it = 0;; it++) {
+                int u;
+                if (dyn) {
+                    const int slot = it & 1;
+                    mbar_wait(&S.sched_full[slot], (it >> 1) & 1);
+                    u = *(volatile int *)&S.sched_unit[slot];
+                    mbar_arrive(&S.sched_empty[slot]);
+                } else {
+                    u = worker + it * nworkers;
+                    if (u >= nunits) u = -1;
+                }
+                if (u < 0) break;
                 const TcUnit U = units[u];
                 for (int n0 = U.n_begin; n0 < U.n_end; n0 += BN, tile++) {
                     const unsigned acc = tile & 1;
@@ -276,7 +310,18 @@ tc_candidates_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         const unsigned tmem_empty_leader0 = PAIR ? mapa_rank(smem_u32(&S.tmem_empty[0]), 0) : 0u;
         const unsigned tmem_empty_leader1 = PAIR ? mapa_rank(smem_u32(&S.tmem_empty[1]), 0) : 0u;
         unsigned tile = 0;
-        for (int u = worker; u < nunits; u += nworkers) {
+        for (int it = 0;; it++) {
+            int u;
+            if (dyn) {
+                const int slot = it & 1;
+                mbar_wait(&S.sched_full[slot], (it >> 1) & 1);
+                u = *(volatile int *)&S.sched_unit[slot];
+                mbar_arrive(&S.sched_empty[slot]);
+            } else {
+                u = worker + it * nworkers;
+                if (u >= nunits) u = -1;
+            }
+            if (u < 0) break;
             const TcUnit U = units[u];
             const bool valid_row = row_in_unit < U.a_valid;
             const float qn = valid_row ? qnorm[U.a_row0 + row_in_unit] : 0.f;
@@ -741,6 +786,7 @@ __global__ void scatter_results_kernel(const int64_t *__restrict__ sk, const dou
 namespace mob {
 
 int g_search_mode = 0;          // 0 = auto, 1 = exact kernel only, 2 = force the tensor-core path (MoB200_SetTuning("search_mode"))
+int g_tc_sched_mode = 0;         // 1 = static round-robin deal of the units of single-CTA launches (MoB200_SetTuning("tc_sched"))
 int g_tc_share_mode = 0;         // 1 = no cross-unit threshold sharing (MoB200_SetTuning("tc_share"))
 int g_tc_ladder_mode = 0;        // 0 = auto (one-term level first unless it has been failing), 1 = never, 2 = always (MoB200_SetTuning("tc_ladder"))
 std::atomic<int> g_one_term_skip{0};   // searches left before the one-term level is tried again (shared by all callers: a property of the data)
@@ -855,12 +901,18 @@ static int tc_run_units(ThreadCtx &t, const TcOperand &A, int64_t a_rows, const 
         }
         row_query = share->row_query; xmax2 = share->xmax2; sh_one = share->one_term; sh_k = share->topk; sh_rel = share->rel_margin; sh_abs = share->abs_margin;
     }
+    int *sched = nullptr;
+    if (!pair && g_tc_sched_mode == 0) {
+        sched = (int *)arena_alloc(t, 4);
+        if (!sched) return MO_RC_INTERNAL_ERROR;
+        MOB_CUDA_TRY(cudaMemsetAsync(sched, 0, 4, t.stream));
+    }
     if (timed) { t.kev_prio = 2; g_last_tc_kused = nkb * BK; cudaEventRecord(t.kev0, t.stream); }   // MoB200_LastKernelMs reports the first (whole-list) pass, not the refine pass
     if (!pair) {
         int grid = num_sms();
         if (grid > nunits) grid = nunits;
-        if (kp == KP_LONG) tc_candidates_kernel<false, KP_LONG><<<grid, kTcThreads, smem1, t.stream>>>(map_a, map_b, dunits, nunits, nkb, A.enorm ? A.enorm : A.norm, B.enorm ? B.enorm : B.norm, *part_d, *part_i, *part_thr, qbound, row_query, alonorm, xmax2, sh_one, sh_k, sh_rel, sh_abs);
-        else tc_candidates_kernel<false, KP><<<grid, kTcThreads, smem1, t.stream>>>(map_a, map_b, dunits, nunits, nkb, A.enorm ? A.enorm : A.norm, B.enorm ? B.enorm : B.norm, *part_d, *part_i, *part_thr, qbound, row_query, alonorm, xmax2, sh_one, sh_k, sh_rel, sh_abs);
+        if (kp == KP_LONG) tc_candidates_kernel<false, KP_LONG><<<grid, kTcThreads, smem1, t.stream>>>(map_a, map_b, dunits, nunits, nkb, A.enorm ? A.enorm : A.norm, B.enorm ? B.enorm : B.norm, *part_d, *part_i, *part_thr, qbound, row_query, alonorm, xmax2, sh_one, sh_k, sh_rel, sh_abs, sched);
+        else tc_candidates_kernel<false, KP><<<grid, kTcThreads, smem1, t.stream>>>(map_a, map_b, dunits, nunits, nkb, A.enorm ? A.enorm : A.norm, B.enorm ? B.enorm : B.norm, *part_d, *part_i, *part_thr, qbound, row_query, alonorm, xmax2, sh_one, sh_k, sh_rel, sh_abs, sched);
     } else {
         if (kp != KP) { set_error("tc search: CTA pairs keep %d candidates per list", KP); return MO_RC_INTERNAL_ERROR; }
         // clusters of two CTAs (one TPC each): one persistent pair per two SMs
@@ -872,7 +924,7 @@ static int tc_run_units(ThreadCtx &t, const TcOperand &A, int64_t a_rows, const 
         at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         const float *an = A.enorm ? A.enorm : A.norm, *bn = B.enorm ? B.enorm : B.norm; int kp = nkb;
-        MOB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_candidates_kernel<true, KP>, map_a, map_b, (const TcUnit *)dunits, nunits, kp, an, bn, *part_d, *part_i, *part_thr, qbound, row_query, alonorm, xmax2, sh_one, sh_k, sh_rel, sh_abs));
+        MOB_CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_candidates_kernel<true, KP>, map_a, map_b, (const TcUnit *)dunits, nunits, kp, an, bn, *part_d, *part_i, *part_thr, qbound, row_query, alonorm, xmax2, sh_one, sh_k, sh_rel, sh_abs, (int *)nullptr));
     }
     if (timed) cudaEventRecord(t.kev1, t.stream);
     MOB_LAUNCH_CHECK();
@@ -976,7 +1028,9 @@ bool tc_search_applicable(int64_t n, int dim, int64_t nq, int k, int metric) {
     const bool metric_ok = metric == MO_METRIC_L2 || metric == MO_METRIC_L2SQ || metric == MO_METRIC_IP || metric == MO_METRIC_COS;
     const bool shape_ok = metric_ok && k >= 1 && dim >= 16 && n < (1ll << 31) - BN && (k <= KP ? n >= BN : (k <= KW && n >= 1024));
     if (g_search_mode == 2) return shape_ok;
-    return shape_ok && nq >= 256 && n >= 16384 && dim >= 64;   // below this the exact kernel wins (operand split + launch overheads)
+    // below this the exact kernel wins (operand split + launch overheads).  The second clause is centroid assignment at index build
+    // (Productl2.probeRun, product_l2.go:317-407): a small table (nlist rows) against a very large batch of queries.
+    return shape_ok && nq >= 256 && dim >= 64 && (n >= 16384 || (n >= 1024 && nq >= 65536));
 }
 
 // centroid probe of an IVF search (findCentroids): many queries against a small table, k = nprobe

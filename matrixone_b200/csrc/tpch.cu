@@ -884,7 +884,7 @@ int xcall_plan(mo_xcall_args_t *args, uint64_t len);
 
 extern int g_search_mode;
 extern thread_local int g_last_tc_fallbacks, g_last_tc_refined, g_last_tc_kused;
-extern int g_tc_pair_mode, g_tc_range_mb, g_tc_ladder_mode, g_tc_share_mode;
+extern int g_tc_pair_mode, g_tc_range_mb, g_tc_ladder_mode, g_tc_share_mode, g_tc_sched_mode;
 extern std::atomic<int> g_one_term_skip;
 
 int tuning_set(const char *name, int value) {
@@ -896,6 +896,7 @@ int tuning_set(const char *name, int value) {
     if (!strcmp(name, "tc_ladder")) { g_tc_ladder_mode = (int)value; g_one_term_skip.store(0); return 0; }
     if (!strcmp(name, "get_tc_kused")) return g_last_tc_kused;
     if (!strcmp(name, "tc_share")) { g_tc_share_mode = (int)value; return 0; }
+    if (!strcmp(name, "tc_sched")) { g_tc_sched_mode = (int)value; return 0; }
     if (!strcmp(name, "q6_variant")) { g_q6_variant = value; return 0; }
     if (!strcmp(name, "plan_specialise")) { g_plan_specialise = value; return 0; }
     if (!strcmp(name, "q1_variant")) { g_q1_variant = value; return 0; }

@@ -49,7 +49,7 @@ extern "C" int32_t XCall(int64_t runtimeId, int64_t funcId, uint8_t *errStr, uin
     t.err[0] = 0;
     mo_xcall_args_t *a = reinterpret_cast<mo_xcall_args_t *>(args);
     int rc;
-    if ((funcId >= 0 && funcId <= 3) || (funcId >= 100 && funcId <= 111)) rc = xcall_rowdist(funcId, a, len);
+    if ((funcId >= 0 && funcId <= 3) || (funcId >= 100 && funcId <= 113)) rc = xcall_rowdist(funcId, a, len);
     else if (funcId >= 0x1000 && funcId < 0x1000 + (5 << 8)) rc = xcall_agg((int)((funcId - 0x1000) >> 8), (int)((funcId - 0x1000) & 0xff), a, len);
     else if (funcId >= 0x1800 && funcId < 0x1800 + (5 << 8)) rc = xcall_agg_merge((int)((funcId - 0x1800) >> 8), (int)((funcId - 0x1800) & 0xff), a, len);
     else if (funcId == MO_XCALL_PLAN) rc = xcall_plan(a, len);

@@ -664,3 +664,17 @@ def dec_sum(width, col, sums, counts, groups=None, nulls=None, n=None):
     gv = Vector(data=np.ascontiguousarray(groups, dtype=np.uint64), length=n) if groups is not None else Vector(length=0)
     xcall(capi.XCALL_DEC_SUM(width), [Vector(data=sums.view(np.uint8).reshape(-1), length=sums.shape[0]), Vector(data=counts, length=counts.shape[0]), gv,
                                       _with_nulls(c.view(np.uint8).reshape(-1), nulls, n)], n)
+
+
+# ---------------------------------------------------------------------------------------------- normalize_l2 (vector-valued)
+def normalize_l2(cells, area, length, dtype=np.float32, nulls=None):
+    """normalize_l2(v) over a varlena vector column (moarray.NormalizeL2, pkg/vectorize/moarray/external.go:262-285).  Returns
+    (result cells uint8[24 * length], result area uint8[len(area)]): the result mirrors the argument's layout."""
+    cells = np.ascontiguousarray(cells, dtype=np.uint8)
+    area = np.ascontiguousarray(area, dtype=np.uint8)
+    ocells = np.zeros(24 * length, dtype=np.uint8)
+    oarea = np.zeros(max(area.nbytes, 1), dtype=np.uint8)
+    res = Vector(data=ocells, area=oarea, nulls=None if nulls is None else np.array(nulls, dtype=np.uint64, copy=True), length=length)
+    fid = capi.XCALL_GO_NORMALIZE_L2_F32 if np.dtype(dtype) == np.float32 else capi.XCALL_GO_NORMALIZE_L2_F64
+    xcall(fid, [res, Vector(data=cells, area=area, length=length)], length)
+    return ocells, oarea[:area.nbytes]

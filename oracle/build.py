@@ -9,6 +9,9 @@
                               /root/reference/thirdparties/usearch-2.23.0.tar.gz, flags per
                               thirdparties/Makefile:60-90 (OpenMP on, SimSIMD off, fp16lib on).
 
+  oracle/_ref/libbloom_ref.so the reference's bloom filter (cgo/bloom.c unchanged) + the xxHash 0.8.3 tarball it pins.
+  oracle/libxxh3_host.so      matrixone_b200/csrc/xxh3_128.cuh compiled for the host (test-only wrapper xxh3_host.cpp).
+
 No reference source is copied into the repo: tarballs are unpacked into a temp dir that is removed.
 """
 import os
@@ -102,9 +105,41 @@ def build_mocl_ref(force=False):
     return out
 
 
+def build_bloom_ref(force=False):
+    """the reference's bloom filter (cgo/bloom.c, UNCHANGED) with the xxHash 0.8.3 it pins (thirdparties/Makefile:26,45-49: xxhash.h copied
+    next to it, XXH_INLINE_ALL).  Validates matrixone_b200/csrc/xxh3_128.cuh and bloom.cu."""
+    out = os.path.join(REF_DIR, "libbloom_ref.so")
+    src = os.path.join(REF, "cgo", "bloom.c")
+    tarball = os.path.join(REF, "thirdparties", "xxHash-0.8.3.tar.gz")
+    if not (os.path.exists(src) and os.path.exists(tarball)):
+        return out if os.path.exists(out) else None
+    if not (force or _newer(out, [src, tarball, os.path.join(HERE, "xxh3_ref_shim.c")])):
+        return out
+    os.makedirs(REF_DIR, exist_ok=True)
+    tmp = tempfile.mkdtemp(prefix="mo_b200_xxhash_")
+    try:
+        with tarfile.open(tarball) as tf:
+            tf.extractall(tmp)
+        xx = os.path.join(tmp, [n for n in os.listdir(tmp) if n.lower().startswith("xxhash")][0])
+        _run(["gcc", "-std=gnu11", "-O3", "-Wall", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-I", xx, "-I", os.path.join(REF, "cgo"), "-o", out, src, os.path.join(HERE, "xxh3_ref_shim.c"), "-lm"])
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return out
+
+
+def build_xxh3_host(force=False):
+    """the device hash header compiled for the HOST (g++), so that the restatement can be pinned to the real xxHash without a GPU"""
+    out = os.path.join(HERE, "libxxh3_host.so")
+    hdr = os.path.join(os.path.dirname(HERE), "matrixone_b200", "csrc", "xxh3_128.cuh")
+    src = os.path.join(HERE, "xxh3_host.cpp")
+    if force or _newer(out, [hdr, src]):
+        _run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-x", "c++", "-I", os.path.dirname(hdr), "-o", out, src])
+    return out
+
+
 def build_all(force=False, verbose=False):
-    res = {"oracle_go": build_oracle_go(force)}
-    for name, fn in (("mo_ref", build_mo_ref), ("usearch_ref", build_usearch_ref), ("mocl_ref", build_mocl_ref)):
+    res = {"oracle_go": build_oracle_go(force), "xxh3_host": build_xxh3_host(force)}
+    for name, fn in (("mo_ref", build_mo_ref), ("usearch_ref", build_usearch_ref), ("mocl_ref", build_mocl_ref), ("bloom_ref", build_bloom_ref)):
         try:
             res[name] = fn(force)
         except Exception as e:  # the reference libs are optional strengthening, the restatement is not

@@ -80,3 +80,37 @@ def test_no_gpu_fails_loudly(lib):
 def test_missing_library_raises_importerror(tmp_path):
     with pytest.raises(ImportError):
         capi.load_library(str(tmp_path / "libmo_b200.so"))
+
+
+def test_bloom_header_symbols_exported_and_match_the_reference_header(lib):
+    """include/mo_b200_bloom.h == the prototypes of the reference's cgo/bloom.h, every one exported; the host-only entry points (init, marshal,
+    unmarshal, free: no GPU work) behave like cgo/bloom.c:98-135,321-339"""
+    def protos(path):
+        src = re.sub(r"/\*.*?\*/", "", open(path).read(), flags=re.S)
+        return sorted(set(re.findall(r"^\s*(?:const\s+)?(?:void|bool|int|uint8_t|bloomfilter_t)\s*\*?\s*(bloomfilter_[a-z0-9_]+)\s*\(", src, flags=re.M)))
+    names = protos(os.path.join(ROOT, "include", "mo_b200_bloom.h"))
+    assert len(names) == 18, names
+    for n in names:
+        assert hasattr(lib, n), n
+    ref_h = "/root/reference/cgo/bloom.h"
+    if os.path.exists(ref_h):
+        assert [n for n in protos(ref_h) if not n.startswith("bloomfilter_get_")] == names
+    lib.bloomfilter_init_with_seed.restype = C.c_void_p; lib.bloomfilter_init_with_seed.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64]
+    lib.bloomfilter_marshal.restype = C.c_void_p; lib.bloomfilter_marshal.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
+    lib.bloomfilter_unmarshal.restype = C.c_void_p; lib.bloomfilter_unmarshal.argtypes = [C.c_void_p, C.c_size_t]
+    lib.bloomfilter_free.restype = None; lib.bloomfilter_free.argtypes = [C.c_void_p]
+    bf = lib.bloomfilter_init_with_seed(1000, 3, 42)        # nbits rounds up to a power of two (bloom.c:119)
+    n = C.c_size_t()
+    p = lib.bloomfilter_marshal(bf, C.byref(n))
+    raw = C.string_at(p, n.value)
+    assert n.value == 32 + 1024 // 8 and raw[:4] == b"XXBF"
+    hdr = np.frombuffer(raw[:24], dtype=np.uint8)
+    assert hdr[4:8].view(np.uint32)[0] == 3 and hdr[8:16].view(np.uint64)[0] == 1024 and hdr[16:24].view(np.uint64)[0] == 42
+    assert not any(raw[24:24 + 128])
+    assert lib.bloomfilter_init_with_seed(64, 65, 0) is None          # k > MAX_K_SEED
+    buf = np.frombuffer(raw, np.uint8).copy()
+    assert lib.bloomfilter_unmarshal(buf.ctypes.data, buf.nbytes) == buf.ctypes.data
+    assert lib.bloomfilter_unmarshal(buf.ctypes.data, 8) is None
+    buf[0] = 0
+    assert lib.bloomfilter_unmarshal(buf.ctypes.data, buf.nbytes) is None
+    lib.bloomfilter_free(bf)

@@ -6,6 +6,7 @@ import pytest
 
 import oracle_lib as O
 from matrixone_b200 import capi, datagen, ops
+from matrixone_b200.vector import DeviceBuffer
 
 pytestmark = pytest.mark.gpu
 
@@ -303,3 +304,24 @@ def test_tensor_core_cosine_with_a_zero_vector_uses_the_exact_kernel(gpu):
     finally:
         gpu.MoB200_SetTuning(b"search_mode", 0)
     _check_topk(keys, dists, okeys, odists, nq, k)
+
+
+@pytest.mark.parametrize("nlist,dim,n", [(64, 96, 20_000), (1024, 64, 70_000)])
+def test_index_build_centroid_assignment_matches_productl2_oracle(gpu, nlist, dim, n):
+    """IvfflatSearchIndex.build == Productl2.probeRun (pkg/sql/colexec/productl2/product_l2.go:317-407): every entry goes to its nearest
+    centroid, brute-force Search(limit = 1).  The second shape (nlist >= 1024, >= 65536 entries per call) takes the tensor-core candidate
+    pass + exact re-score; the first the exact kernel.  Equal only up to ties in the float64 distance."""
+    centers = datagen.vectors_f32(40, 0, nlist, dim) * 4
+    data = datagen.vectors_f32(41, 0, n, dim, centers, 1.0)
+    want = np.zeros(n, dtype=np.int32)
+    O.go().og_assign_centroids_f32(O.p(data), n, dim, O.p(centers), nlist, capi.METRIC_L2, O.p(want))
+    dev = DeviceBuffer.from_numpy(data)
+    idx = ops.IvfflatSearchIndex.build(dev, n, centers, capi.METRIC_L2, chunk=n)
+    got = np.empty(n, dtype=np.int32)
+    got[idx.row_ids] = np.repeat(np.arange(nlist, dtype=np.int32), np.diff(idx.offsets))
+    bad = np.nonzero(got != want)[0]
+    for i in bad:   # a differing assignment must be an exact tie
+        d = ((data[i].astype(np.float64) - centers[[got[i], want[i]]].astype(np.float64)) ** 2).sum(axis=1)
+        assert abs(d[0] - d[1]) <= 1e-6 * max(d[0], 1.0), (i, got[i], want[i], d)
+    assert bad.size <= n // 1000
+    idx.destroy(); dev.free()
