@@ -238,6 +238,29 @@ typedef struct { int32_t div0_null; int32_t reserved; int64_t err_row; } mo_go_p
 #define MO_XCALL_PACK_KEYS 0x6001
 #define MO_XCALL_GROUP_IDS 0x6002
 #define MO_XCALL_SHUFFLE(szof) (0x6100 + (szof))
+/* ---- hash join, equality conditions over <= 8-byte packed keys (csrc/join.cu).  The build side inserts its keys with GROUP_IDS (IntHashMap insert):
+ *   JOIN_SELS   GroupSels.Insert + Finalize (pkg/vm/message/joinMapMsg.go:72-125) as driven by HashmapBuilder.BuildHashmap (hashbuild/hashmap.go:395-412):
+ *               the build rows of every group, ascending.  args: [0] offsets int32[ngroups + 2] (out: [k] = start of 0-based group k, [ngroups] =
+ *               [ngroups + 1] = count) ; [1] vals int32[len] (out) ; [2] int64 count (out: rows that have a group) ; [3] groups uint64[len] (the ids
+ *               GROUP_IDS returned for the build rows; 0 = the row has a NULL key and joins nothing).  len = build rows (< 2^31).
+ *               (The reference keeps no sels when every row got its own group -- HashOnUnique, joinMapMsg.go:83-89,203-205: pass pdata NULL below.)
+ *   JOIN_FIND   intHashMapIterator.Find (pkg/common/hashmap/inthashmap.go): vals[i] = 1-based group id of probe key i, 0 = absent or NULL key.
+ *               args: [0] vals uint64[len] ; [1] table_keys uint64[ngroups] (GROUP_IDS's key table: key of group g at [g - 1]) ; [2] keys uint64[len] (+pnulls)
+ *   JOIN_PROBE  the emission loop of hashjoin container.probe (pkg/sql/colexec/hashjoin/join.go:383-628) without a non-equality condition: result rows
+ *               as (probe row, build row) pairs in the reference's order -- probe rows ascending, per probe row its group's sels ascending.
+ *               join_type INNER: matches only; LEFT: + (row, -1) for a probe row without a match; SEMI: (row, -1) once per matching probe row;
+ *               ANTI: (row, -1) per probe row WITHOUT a match.  args: [0] probe_rows int64[cap] ; [1] build_rows int64[cap] ; [2] int64 count (out; when
+ *               it exceeds cap the call fails with MO_RC_OUT_OF_RANGE and the count is still written) ; [3] host mo_join_params_t ; [4] table_keys ;
+ *               [5] sels offsets int32[ngroups + 2] (pdata NULL: unique map, build row = id - 1) ; [6] sels vals int32[] ; [7] probe keys uint64[len] (+pnulls)
+ * The device hash table is rebuilt from table_keys per call unless MoB200_JoinMapPrepare(table_keys, ngroups) cached it (keyed by that pointer). */
+#define MO_JOIN_INNER 0
+#define MO_JOIN_LEFT 1
+#define MO_JOIN_SEMI 2
+#define MO_JOIN_ANTI 3
+typedef struct mo_join_params_t { int32_t join_type; int32_t reserved; } mo_join_params_t;
+#define MO_XCALL_JOIN_SELS 0x6010
+#define MO_XCALL_JOIN_FIND 0x6011
+#define MO_XCALL_JOIN_PROBE 0x6012
 #define MO_XCALL_GROUP_AGG(op, T) (0x6400 + ((op) << 8) + (T))
 
 /* ---- Decimal64 / Decimal128 (csrc/decimal.cu): the reference's native TPC-H column type is DECIMAL(15,2).  Decimal64 = int64 unscaled value,
@@ -393,6 +416,11 @@ int32_t MoB200_ColumnCacheConfigure(uint64_t capacity_bytes);   /* 0 = off (drop
 int32_t MoB200_ColumnPin(const void *host, uint64_t bytes, uint64_t generation);
 int32_t MoB200_ColumnUnpin(const void *host);
 int32_t MoB200_ColumnCacheStats(uint64_t *hits, uint64_t *misses, uint64_t *bytes);
+
+/* prepared join maps: build the probe-side device hash table of a JoinMap once (the JoinMap message lives for the whole probe phase,
+ * pkg/vm/message/joinMapMsg.go:127-160); JOIN_FIND / JOIN_PROBE calls whose table_keys pointer equals `table_keys` reuse it. */
+int32_t MoB200_JoinMapPrepare(const void *table_keys, uint64_t ngroups);
+int32_t MoB200_JoinMapRelease(const void *table_keys);
 int32_t MoB200_Sync(void);                    /* synchronize the calling thread's stream */
 int32_t MoB200_SetStream(void *cuda_stream);  /* adopt an external cudaStream_t for the calling thread (NULL = own) */
 int32_t MoB200_TimerStart(void);              /* CUDA event on the calling thread's stream */

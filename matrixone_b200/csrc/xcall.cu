@@ -21,6 +21,9 @@ int xcall_filter_sels(mo_xcall_args_t *args, uint64_t len);
 int xcall_shuffle(int szof, mo_xcall_args_t *args, uint64_t len);
 int xcall_pack_keys(mo_xcall_args_t *args, uint64_t len);
 int xcall_group_ids(mo_xcall_args_t *args, uint64_t len);
+int xcall_join_sels(mo_xcall_args_t *args, uint64_t len);
+int xcall_join_find(mo_xcall_args_t *args, uint64_t len);
+int xcall_join_probe(mo_xcall_args_t *args, uint64_t len);
 int xcall_group_agg(int op, int T, mo_xcall_args_t *args, uint64_t len);
 int xcall_bruteforce(mo_xcall_args_t *args, uint64_t len);
 int xcall_ivf(mo_xcall_args_t *args, uint64_t len);
@@ -58,6 +61,9 @@ extern "C" int32_t XCall(int64_t runtimeId, int64_t funcId, uint8_t *errStr, uin
     else if (funcId == MO_XCALL_FILTER_SELS) rc = xcall_filter_sels(a, len);
     else if (funcId == MO_XCALL_PACK_KEYS) rc = xcall_pack_keys(a, len);
     else if (funcId == MO_XCALL_GROUP_IDS) rc = xcall_group_ids(a, len);
+    else if (funcId == MO_XCALL_JOIN_SELS) rc = xcall_join_sels(a, len);
+    else if (funcId == MO_XCALL_JOIN_FIND) rc = xcall_join_find(a, len);
+    else if (funcId == MO_XCALL_JOIN_PROBE) rc = xcall_join_probe(a, len);
     else if (funcId > 0x6100 && funcId <= 0x6100 + 24) rc = xcall_shuffle((int)(funcId - 0x6100), a, len);
     else if (funcId >= 0x6400 && funcId < 0x6400 + (5 << 8)) rc = xcall_group_agg((int)((funcId - 0x6400) >> 8), (int)((funcId - 0x6400) & 0xff), a, len);
     else if (funcId == MO_XCALL_Q6_MERGE) rc = xcall_q6_merge(a, len);

@@ -678,3 +678,70 @@ def normalize_l2(cells, area, length, dtype=np.float32, nulls=None):
     fid = capi.XCALL_GO_NORMALIZE_L2_F32 if np.dtype(dtype) == np.float32 else capi.XCALL_GO_NORMALIZE_L2_F64
     xcall(fid, [res, Vector(data=cells, area=area, length=length)], length)
     return ocells, oarea[:area.nbytes]
+
+
+# ---------------------------------------------------------------------------------------------- hash join (csrc/join.cu)
+class JoinMap:
+    """message.JoinMap for equality joins over <= 8-byte packed keys (pkg/vm/message/joinMapMsg.go:127-210): the build side's IntHashMap
+    (GroupTable: first-seen group ids + key table) and its GroupSels.  HashOnUnique (every build row its own group) keeps no sels."""
+
+    def __init__(self, build_keys, skip=None, prepare=True):
+        k = np.ascontiguousarray(build_keys, dtype=np.uint64)
+        self.nbuild = k.shape[0]
+        tab = GroupTable(max(self.nbuild, 1))
+        groups = tab.insert(k, skip)                                   # HashmapBuilder.BuildHashmap: itr.Insert (hashmap.go:340-360)
+        self.ngroups = int(tab.ngroups[0])
+        self.table_keys = np.ascontiguousarray(tab.keys[:max(self.ngroups, 1)])[:self.ngroups].copy() if self.ngroups else np.zeros(0, np.uint64)
+        self.offsets = self.sels = None
+        if self.ngroups != self.nbuild:                                 # GroupSels.Finalize keeps sels only when some group has != 1 row (joinMapMsg.go:83-89)
+            self.offsets = np.zeros(self.ngroups + 2, dtype=np.int32)
+            self.sels = np.zeros(max(self.nbuild, 1), dtype=np.int32)
+            cnt = np.zeros(1, dtype=np.int64)
+            xcall(capi.XCALL_JOIN_SELS, [Vector(data=self.offsets, length=self.ngroups + 2), Vector(data=self.sels, length=self.nbuild), Vector(data=cnt, length=1),
+                                         Vector(data=groups, length=self.nbuild)], self.nbuild)
+            self.sels = self.sels[:int(cnt[0])]
+            if int(cnt[0]) == 0:                                       # nothing inserted (every key NULL): Finalize keeps no sels (joinMapMsg.go:83-89)
+                self.offsets = self.sels = None
+        self.prepared = False
+        if prepare and self.ngroups:
+            lib = capi.load_library()
+            capi.check(lib.MoB200_JoinMapPrepare(self.table_keys.ctypes.data, self.ngroups), lib)
+            self.prepared = True
+
+    def hash_on_unique(self):
+        return self.offsets is None
+
+    def find(self, keys, nulls=None):
+        """intHashMapIterator.Find: 1-based group id per probe key, 0 = no match"""
+        k = np.ascontiguousarray(keys, dtype=np.uint64)
+        n = k.shape[0]
+        vals = np.zeros(n, dtype=np.uint64)
+        xcall(capi.XCALL_JOIN_FIND, [Vector(data=vals, length=n), Vector(data=self.table_keys, length=self.ngroups), Vector(data=k, nulls=nulls, length=n)], n)
+        return vals
+
+    def probe(self, keys, join_type=capi.JOIN_INNER, nulls=None, capacity=None):
+        """(probe rows, build rows) of the join result in the reference's emission order; build row -1 = no build side (left outer / semi / anti)"""
+        k = np.ascontiguousarray(keys, dtype=np.uint64)
+        n = k.shape[0]
+        cap = capacity if capacity is not None else max(2 * n, 1024)
+        prm = np.array([join_type, 0], dtype=np.int32)
+        while True:
+            op, ob, cnt = np.zeros(cap, np.int64), np.zeros(cap, np.int64), np.zeros(1, np.int64)
+            vecs = [Vector(data=op, length=cap), Vector(data=ob, length=cap), Vector(data=cnt, length=1), Vector(data=prm.view(np.uint8), length=1),
+                    Vector(data=self.table_keys, length=self.ngroups),
+                    Vector(data=self.offsets, length=self.ngroups + 2) if self.offsets is not None else Vector(length=0),
+                    Vector(data=self.sels, length=len(self.sels)) if self.sels is not None else Vector(length=0),
+                    Vector(data=k, nulls=nulls, length=n)]
+            rc, msg = xcall(capi.XCALL_JOIN_PROBE, vecs, n, raise_on_error=False)
+            if rc == capi.RC_OUT_OF_RANGE and capacity is None:       # the count was reported: size the buffers and ask again
+                cap = int(cnt[0])
+                continue
+            if rc:
+                raise capi.MoError(rc, msg)
+            return op[:int(cnt[0])], ob[:int(cnt[0])]
+
+    def release(self):
+        if self.prepared:
+            lib = capi.load_library()
+            lib.MoB200_JoinMapRelease(self.table_keys.ctypes.data)
+            self.prepared = False

@@ -1390,3 +1390,75 @@ double og_kahan_sum(const double *v, int64_t n) {
     for (int64_t i = 0; i < n; i++) { double y = v[i] - c; volatile double t = s + y; c = (t - s) - y; s = t; }
     return s;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Hash join, equality conditions only (test infrastructure like everything in this file).
+ * ------------------------------------------------------------------------------------------- */
+
+/* og_join_sels: GroupSels.Insert + Finalize (pkg/vm/message/joinMapMsg.go:72-125) fed the way HashmapBuilder.BuildHashmap feeds it
+ * (pkg/sql/colexec/hashbuild/hashmap.go:395-412: rows whose key is NULL or got no group are skipped; Insert(v - 1, row)).
+ * offsets has group_count + 2 entries.  Returns the number of inserted rows. */
+int64_t og_join_sels(const uint64_t *groups, int64_t n, int64_t group_count, int32_t *offsets, int32_t *vals) {
+    int32_t *tmp = malloc(sizeof(int32_t) * 2 * (size_t)(n > 0 ? n : 1));
+    int64_t m = 0;
+    for (int64_t i = 0; i < n; i++) {
+        if (groups[i] == 0) continue;
+        tmp[2 * m] = (int32_t)(groups[i] - 1); tmp[2 * m + 1] = (int32_t)i; m++;
+    }
+    for (int64_t i = 0; i < group_count + 2; i++) offsets[i] = 0;
+    for (int64_t i = 0; i < m; i++) offsets[tmp[2 * i] + 1]++;                    /* count occurrences per group */
+    for (int64_t i = 1; i < group_count + 2; i++) offsets[i] += offsets[i - 1];    /* prefix sum */
+    for (int64_t i = 0; i < m; i++) { int32_t k = tmp[2 * i]; vals[offsets[k]] = tmp[2 * i + 1]; offsets[k]++; }   /* scatter, offsets as cursors */
+    for (int64_t i = group_count + 1; i >= 1; i--) offsets[i] = offsets[i - 1];    /* recover: shift right by one */
+    offsets[0] = 0;
+    free(tmp);
+    return m;
+}
+
+/* og_join_find: intHashMapIterator.Find (pkg/common/hashmap/iterator.go, inthashmap.go): 1-based group id of every key, 0 = absent; a NULL key
+ * (zvals == 0) never matches.  Any exact map reproduces the ids (the reference's hash is seeded randomly). */
+void og_join_find(const uint64_t *table_keys, int64_t ngroups, const uint64_t *keys, const uint64_t *nulls, int64_t n, uint64_t *vals) {
+    uint64_t cap = 16;
+    while (cap < 2 * (uint64_t)ngroups) cap <<= 1;
+    int64_t *slot = malloc(sizeof(int64_t) * cap);
+    for (uint64_t s = 0; s < cap; s++) slot[s] = -1;
+    for (int64_t g = 0; g < ngroups; g++) {
+        uint64_t h = table_keys[g] * 0x9E3779B97F4A7C15ull; h ^= h >> 29;
+        uint64_t s = h & (cap - 1);
+        while (slot[s] >= 0) s = (s + 1) & (cap - 1);
+        slot[s] = g;
+    }
+    for (int64_t i = 0; i < n; i++) {
+        vals[i] = 0;
+        if (bm_has(nulls, (uint64_t)i)) continue;
+        uint64_t h = keys[i] * 0x9E3779B97F4A7C15ull; h ^= h >> 29;
+        uint64_t s = h & (cap - 1);
+        while (slot[s] >= 0) { if (table_keys[slot[s]] == keys[i]) { vals[i] = (uint64_t)slot[s] + 1; break; } s = (s + 1) & (cap - 1); }
+    }
+    free(slot);
+}
+
+/* og_join_probe: the emission loop of container.probe (pkg/sql/colexec/hashjoin/join.go:383-628) with NonEqCond == nil, for
+ * join_type 0 inner, 1 left outer (EmitUnmatchedProbe), 2 left semi, 3 left anti.  vals = Find's result; offsets == NULL: HashOnUnique
+ * (build row = v - 1, join.go:431-446), else sels = GetSels(v - 1) appended in order (psSelsForOneRow, join.go:520-560).
+ * Result rows are (probe row, build row | -1); returns how many there are (only the first cap are written). */
+int64_t og_join_probe(const uint64_t *vals, int64_t n, const int32_t *offsets, const int32_t *sels, int32_t join_type,
+                      int64_t *out_probe, int64_t *out_build, int64_t cap) {
+    int64_t r = 0;
+#define EMIT(p, b) do { if (r < cap) { out_probe[r] = (p); out_build[r] = (b); } r++; } while (0)
+    for (int64_t row = 0; row < n; row++) {
+        uint64_t v = vals[row];
+        int64_t nmatch = 0;
+        if (v) nmatch = offsets ? (int64_t)(offsets[v] - offsets[v - 1]) : 1;
+        if (v == 0 || nmatch == 0) {                           /* z == 0 || v == 0 */
+            if (join_type == 1 || join_type == 3) EMIT(row, -1);   /* appendOneNotMatch */
+            continue;
+        }
+        if (join_type == 2) { EMIT(row, -1); continue; }           /* left semi: the probe row once */
+        if (join_type == 3) continue;                              /* left anti: matched rows vanish */
+        if (!offsets) { EMIT(row, (int64_t)v - 1); continue; }
+        for (int32_t j = offsets[v - 1]; j < offsets[v]; j++) EMIT(row, (int64_t)sels[j]);
+    }
+#undef EMIT
+    return r;
+}

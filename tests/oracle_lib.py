@@ -36,6 +36,12 @@ def go():
         lib.og_multi_logic.argtypes = [_i32, _vp, _vp, _i32, _vp, _vp, _vp, _u64]
         lib.og_filter_sels.restype = _i64
         lib.og_filter_sels.argtypes = [_vp, _vp, _u64, _vp]
+        lib.og_join_sels.restype = _i64
+        lib.og_join_sels.argtypes = [_vp, _i64, _i64, _vp, _vp]
+        lib.og_join_find.restype = None
+        lib.og_join_find.argtypes = [_vp, _i64, _vp, _vp, _i64, _vp]
+        lib.og_join_probe.restype = _i64
+        lib.og_join_probe.argtypes = [_vp, _i64, _vp, _vp, _i32, _vp, _vp, _i64]
         lib.og_group_ids.restype = _i64
         lib.og_group_ids.argtypes = [_vp, _u64, _vp, _vp, _i64, _i64]
         lib.og_sum_int64.restype = _i32

@@ -93,6 +93,53 @@ def main():
         out["group_sum_f64_card_%d" % card] = {"ms": ms, "gbs": 16.0 * m / ms / 1e6, "rows_per_s": m / ms * 1e3}
         for b in (keys, groups, rn, tkeys, ng, state, sn, cnt):
             b.free()
+    # ---- bloom filter probe (cgo/bloom.h entry points): build on 10 M keys, probe m int64 keys; the reference's own C next to it on one host core
+    try:
+        _vp, _sz, _u64, _u32 = C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32
+        def proto(l):
+            l.bloomfilter_init_with_seed.restype = _vp; l.bloomfilter_init_with_seed.argtypes = [_u64, _u32, _u64]
+            l.bloomfilter_add_fixed.restype = None; l.bloomfilter_add_fixed.argtypes = [_vp, _vp, _sz, _sz, _sz, _vp, _sz]
+            l.bloomfilter_test_fixed.restype = None; l.bloomfilter_test_fixed.argtypes = [_vp, _vp, _sz, _sz, _sz, _vp, _sz, _vp]
+            l.bloomfilter_free.restype = None; l.bloomfilter_free.argtypes = [_vp]
+            return l
+        proto(lib)
+        nb, nk, kk = 10_000_000, min(n, 100_000_000), 3
+        nbits = 1 << 27                                            # 16 MB filter, ~13 bits per key
+        keys = DeviceBuffer(8 * nk, lib); res = DeviceBuffer(nk, lib)
+        capi.check(lib.MoB200_GenInt64(11, 0, nk, keys.ptr, None, 0), lib)
+        bf = lib.bloomfilter_init_with_seed(nbits, kk, 1)
+        lib.bloomfilter_add_fixed(bf, keys.ptr, 8 * nb, 8, nb, None, 0)
+        ms = timed(lambda: lib.bloomfilter_test_fixed(bf, keys.ptr, 8 * nk, 8, nk, None, 0, res.ptr), reps=3)
+        out["bloom_test_fixed_i64"] = {"ms": ms, "keys": nk, "filter_mb": nbits / 8e6, "k": kk, "keys_per_s": nk / ms * 1e3, "gbs_stream": 9.0 * nk / ms / 1e6}
+        ms = timed(lambda: lib.bloomfilter_add_fixed(bf, keys.ptr, 8 * nb, 8, nb, None, 0), reps=3)
+        out["bloom_add_fixed_i64"] = {"ms": ms, "keys": nb, "keys_per_s": nb / ms * 1e3}
+        hit = int(res.to_numpy(np.uint8).sum())
+        out["bloom_test_fixed_i64"]["positives"] = hit
+        # one 8192-row block from HOST pointers (the drop-in case), and the reference's C on the same block
+        import time
+        hk = keys.to_numpy(np.int64, 8192).copy(); hr = np.zeros(8192, np.uint8)
+        def block(l, f):
+            t0 = time.perf_counter()
+            for _ in range(200):
+                l.bloomfilter_test_fixed(f, hk.ctypes.data, hk.nbytes, 8, 8192, None, 0, hr.ctypes.data)
+            return (time.perf_counter() - t0) / 200 * 1e6
+        block(lib, bf)
+        out["bloom_block_8192_host_us"] = block(lib, bf)
+        refp = os.path.join(ROOT, "oracle", "_ref", "libbloom_ref.so")
+        if os.path.exists(refp):
+            ref = proto(C.CDLL(refp))
+            hb = keys.to_numpy(np.int64, nb)
+            rbf = ref.bloomfilter_init_with_seed(nbits, kk, 1)
+            ref.bloomfilter_add_fixed(rbf, hb.ctypes.data, hb.nbytes, 8, nb, None, 0)
+            out["bloom_block_8192_reference_c_us"] = block(ref, rbf)
+            hres = np.zeros(nb, np.uint8)
+            t0 = time.perf_counter()
+            ref.bloomfilter_test_fixed(rbf, hb.ctypes.data, hb.nbytes, 8, nb, None, 0, hres.ctypes.data)
+            out["bloom_reference_c_keys_per_s_one_core"] = nb / (time.perf_counter() - t0)
+            ref.bloomfilter_free(rbf)
+        lib.bloomfilter_free(bf); keys.free(); res.free()
+    except Exception as e:   # keep the other numbers
+        out["bloom_error"] = repr(e)
     print(json.dumps(out))
 
 
