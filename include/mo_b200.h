@@ -238,6 +238,16 @@ typedef struct { int32_t div0_null; int32_t reserved; int64_t err_row; } mo_go_p
 #define MO_XCALL_PACK_KEYS 0x6001
 #define MO_XCALL_GROUP_IDS 0x6002
 #define MO_XCALL_SHUFFLE(szof) (0x6100 + (szof))
+/* ---- Elkan k-means, dense variant (csrc/kmeans.cu): ElkanClusterer.Cluster from given initial centroids
+ * (pkg/vectorindex/ivfflat/kmeans/elkans/clusterer.go:330-392; distance = metric.L2Distance for every metric, distance_func.go:452-476).
+ * Centroids bit for bit, assignments and iteration count as the reference computes them (serial row-order sums, Go-order distances).
+ * InitCentroids (initializer.go: draws from Go's PCG) stays with the caller.  args: [0] centroids T[k * dim] (in: initial, out: final) ;
+ * [1] assignments int64[n] (out) ; [2] int64 iterations (out) ; [3] host mo_kmeans_params_t ; [4] vectors T[n * dim] ;
+ * [5] rnd float32[] (optional): the rnd.Float32() stream an EMPTY cluster re-seeds its centroid from (clusterer.go:700-707), consumed in
+ * cluster order, dim values per empty cluster; running out of it fails the call with MO_RC_INVALID_ARGUMENT. */
+typedef struct mo_kmeans_params_t { int64_t n, dim, k, max_iter; } mo_kmeans_params_t;
+#define MO_XCALL_KMEANS_ELKAN_F32 0x6020
+#define MO_XCALL_KMEANS_ELKAN_F64 0x6021
 /* ---- hash join, equality conditions over <= 8-byte packed keys (csrc/join.cu).  The build side inserts its keys with GROUP_IDS (IntHashMap insert):
  *   JOIN_SELS   GroupSels.Insert + Finalize (pkg/vm/message/joinMapMsg.go:72-125) as driven by HashmapBuilder.BuildHashmap (hashbuild/hashmap.go:395-412):
  *               the build rows of every group, ascending.  args: [0] offsets int32[ngroups + 2] (out: [k] = start of 0-based group k, [ngroups] =

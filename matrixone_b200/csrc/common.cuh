@@ -49,6 +49,10 @@ void search_invalidate(const void *p, uint64_t bytes);
 // --- device scratch arena -------------------------------------------------------------------------------
 void *arena_alloc(ThreadCtx &t, size_t bytes);   // 256-byte aligned; nullptr on failure (error set)
 void arena_reset(ThreadCtx &t);                  // called at the end of every API call
+// scoped scratch inside one call (loops that need temporaries per iteration): everything allocated after the mark is handed back by the rewind
+struct ArenaMark { size_t block, off; };
+inline ArenaMark arena_mark(ThreadCtx &t) { return ArenaMark{t.cur_block, t.cur_off}; }
+inline void arena_rewind(ThreadCtx &t, ArenaMark m) { t.cur_block = m.block; t.cur_off = m.off; }
 
 // --- Stager: makes every pointer argument a device pointer for the duration of one call -------------------
 struct Stager {

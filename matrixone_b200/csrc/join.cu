@@ -109,10 +109,10 @@ __global__ void __launch_bounds__(kThreads) sels_flag_kernel(const uint64_t *__r
         if (g) atomicAdd((unsigned long long *)&cnt[g - 1], 1ull);
     }
 }
-__global__ void __launch_bounds__(kThreads) sels_compact_kernel(const uint64_t *__restrict__ groups, const uint64_t *__restrict__ pos, uint64_t n, uint32_t *__restrict__ key, uint32_t *__restrict__ row) {
+__global__ void __launch_bounds__(kThreads) sels_compact_kernel(const uint64_t *__restrict__ groups, const uint64_t *__restrict__ pos, uint64_t n, uint64_t ngroups, uint32_t *__restrict__ key, uint32_t *__restrict__ row) {
     for (uint64_t i = blockIdx.x * (uint64_t)kThreads + threadIdx.x; i < n; i += (uint64_t)gridDim.x * kThreads) {
         const uint64_t g = groups[i];
-        if (g) { key[pos[i]] = (uint32_t)(g - 1); row[pos[i]] = (uint32_t)i; }
+        if (g && g <= ngroups) { key[pos[i]] = (uint32_t)(g - 1); row[pos[i]] = (uint32_t)i; }
     }
 }
 // one radix pass, 8 bits at `shift`: tiles of 1024 items, ONE WARP per tile
@@ -306,6 +306,44 @@ __global__ void __launch_bounds__(kThreads) probe_emit_kernel(uint64_t n, const 
 
 }  // namespace
 
+// Stable grouping of rows by their 1-based group id (0 = the row takes no part): *starts = uint64[ngroups + 1] (start of every 0-based group in
+// *rows), *rows = uint32[n] row ids, ascending inside every group, *scal[0] = how many rows have a group, scal[2] (as unsigned) != 0 = an id exceeded
+// ngroups.  Everything lives in the call's arena.  Used by JOIN_SELS and by the k-means centroid update (kmeans.cu).
+int group_rows_stable(ThreadCtx &t, const uint64_t *groups, uint64_t len, uint64_t ngroups, uint64_t **starts, uint32_t **rows, uint64_t **scal_out) {
+    uint64_t *flag = (uint64_t *)arena_alloc(t, (len + 1) * 8), *cnt = (uint64_t *)arena_alloc(t, (ngroups + 1) * 8);
+    uint32_t *k0 = (uint32_t *)arena_alloc(t, len * 4 + 4), *r0 = (uint32_t *)arena_alloc(t, len * 4 + 4), *k1 = (uint32_t *)arena_alloc(t, len * 4 + 4), *r1 = (uint32_t *)arena_alloc(t, len * 4 + 4);
+    const uint64_t nblocks_cap = (len + kRadixTile - 1) / kRadixTile + 1;
+    uint64_t *hist = (uint64_t *)arena_alloc(t, 256 * nblocks_cap * 8);
+    uint64_t *scal = (uint64_t *)arena_alloc(t, 32);     // [0] rows with a group, [1] scratch total, [2] bad flag
+    if (!flag || !cnt || !k0 || !r0 || !k1 || !r1 || !hist || !scal) return MO_RC_INTERNAL_ERROR;
+    MOB_CUDA_TRY(cudaMemsetAsync(cnt, 0, (ngroups + 1) * 8, t.stream));
+    MOB_CUDA_TRY(cudaMemsetAsync(scal, 0, 32, t.stream));
+    sels_flag_kernel<<<grid_for(len ? len : 1), kThreads, 0, t.stream>>>(groups, len, ngroups, flag, cnt, (unsigned *)(scal + 2));
+    MOB_LAUNCH_CHECK();
+    int rc = exclusive_scan(t, flag, len, flag, scal);                 // flag -> position among the rows that have a group ; scal[0] = m
+    if (rc) return rc;
+    sels_compact_kernel<<<grid_for(len ? len : 1), kThreads, 0, t.stream>>>(groups, flag, len, ngroups, k0, r0);
+    MOB_LAUNCH_CHECK();
+    int bits = 0;
+    while (bits < 32 && (1ull << bits) < ngroups) bits++;
+    uint32_t *ka = k0, *ra = r0, *kb = k1, *rb = r1;
+    for (int shift = 0; shift < bits; shift += 8) {
+        const unsigned g = grid_for(nblocks_cap, 1);
+        radix_hist_kernel<<<g, 32, 0, t.stream>>>(ka, scal, shift, hist, nblocks_cap);
+        MOB_LAUNCH_CHECK();
+        rc = exclusive_scan(t, hist, 256 * nblocks_cap, hist, scal + 1);
+        if (rc) return rc;
+        radix_scatter_kernel<<<g, 32, 0, t.stream>>>(ka, ra, scal, shift, hist, nblocks_cap, kb, rb);
+        MOB_LAUNCH_CHECK();
+        uint32_t *x = ka; ka = kb; kb = x; x = ra; ra = rb; rb = x;
+    }
+    rc = exclusive_scan(t, cnt, ngroups, cnt, scal + 1);               // cnt[k] -> start of group k
+    if (rc) return rc;
+    MOB_CUDA_TRY(cudaMemcpyAsync(cnt + ngroups, scal, 8, cudaMemcpyDeviceToDevice, t.stream));   // starts[ngroups] = m
+    *starts = cnt; *rows = ra; *scal_out = scal;
+    return MO_RC_SUCCESS;
+}
+
 // MO_XCALL_JOIN_SELS: args [0] offsets int32[ngroups + 2] ; [1] vals int32[len] ; [2] int64 count (out: rows that have a group) ; [3] groups uint64[len]
 int xcall_join_sels(mo_xcall_args_t *args, uint64_t len) {
     ThreadCtx &t = tctx();
@@ -318,39 +356,14 @@ int xcall_join_sels(mo_xcall_args_t *args, uint64_t len) {
     int32_t *vals = (int32_t *)st.out(args[1].pdata, 4 * len);
     int64_t *count = (int64_t *)st.out(args[2].pdata, 8);
     const uint64_t *groups = (const uint64_t *)st.in(args[3].pdata, 8 * len);
-    uint64_t *flag = (uint64_t *)st.tmp((len + 1) * 8), *cnt = (uint64_t *)st.tmp((ngroups + 1) * 8);
-    uint32_t *k0 = (uint32_t *)st.tmp(len * 4 + 4), *r0 = (uint32_t *)st.tmp(len * 4 + 4), *k1 = (uint32_t *)st.tmp(len * 4 + 4), *r1 = (uint32_t *)st.tmp(len * 4 + 4);
-    const uint64_t nblocks_cap = (len + kRadixTile - 1) / kRadixTile + 1;
-    uint64_t *hist = (uint64_t *)st.tmp(256 * nblocks_cap * 8);
-    uint64_t *scal = (uint64_t *)st.tmp(32);     // [0] rows with a group, [1] scratch total, [2] bad flag
     if (st.failed) { st.finish(); return MO_RC_INTERNAL_ERROR; }
-    MOB_CUDA_TRY(cudaMemsetAsync(cnt, 0, (ngroups + 1) * 8, t.stream));
-    MOB_CUDA_TRY(cudaMemsetAsync(scal, 0, 32, t.stream));
     cudaEventRecord(t.kev0, t.stream);
-    sels_flag_kernel<<<grid_for(len), kThreads, 0, t.stream>>>(groups, len, ngroups, flag, cnt, (unsigned *)(scal + 2));
-    MOB_LAUNCH_CHECK();
-    int rc = exclusive_scan(t, flag, len, flag, scal);                 // flag -> position among the rows that have a group ; scal[0] = m
+    uint64_t *starts, *scal; uint32_t *rows;
+    int rc = group_rows_stable(t, groups, len, ngroups, &starts, &rows, &scal);
     if (rc) { st.finish(); return rc; }
-    sels_compact_kernel<<<grid_for(len), kThreads, 0, t.stream>>>(groups, flag, len, k0, r0);
+    sels_offsets_kernel<<<grid_for(ngroups + 2), kThreads, 0, t.stream>>>(starts, ngroups, scal, offsets);
     MOB_LAUNCH_CHECK();
-    int bits = 0;
-    while (bits < 32 && (1ull << bits) < ngroups) bits++;
-    uint32_t *ka = k0, *ra = r0, *kb = k1, *rb = r1;
-    for (int shift = 0; shift < bits; shift += 8) {
-        const unsigned g = grid_for(nblocks_cap, 1);
-        radix_hist_kernel<<<g, 32, 0, t.stream>>>(ka, scal, shift, hist, nblocks_cap);
-        MOB_LAUNCH_CHECK();
-        rc = exclusive_scan(t, hist, 256 * nblocks_cap, hist, scal + 1);
-        if (rc) { st.finish(); return rc; }
-        radix_scatter_kernel<<<g, 32, 0, t.stream>>>(ka, ra, scal, shift, hist, nblocks_cap, kb, rb);
-        MOB_LAUNCH_CHECK();
-        uint32_t *x = ka; ka = kb; kb = x; x = ra; ra = rb; rb = x;
-    }
-    rc = exclusive_scan(t, cnt, ngroups, cnt, scal + 1);
-    if (rc) { st.finish(); return rc; }
-    sels_offsets_kernel<<<grid_for(ngroups + 2), kThreads, 0, t.stream>>>(cnt, ngroups, scal, offsets);
-    MOB_LAUNCH_CHECK();
-    copy_rows_kernel<<<grid_for(len ? len : 1), kThreads, 0, t.stream>>>(ra, scal, vals, count);
+    copy_rows_kernel<<<grid_for(len ? len : 1), kThreads, 0, t.stream>>>(rows, scal, vals, count);
     cudaEventRecord(t.kev1, t.stream);
     MOB_LAUNCH_CHECK();
     unsigned bad = 0;

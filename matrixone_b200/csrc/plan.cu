@@ -72,14 +72,6 @@ __device__ __forceinline__ void agg_fold(int kind, double *a, double p) {
     else if (kind == MO_AGG_SUM || kind == MO_AGG_AVG) atomicAdd(a, p);
 }
 
-__device__ __forceinline__ int type_bytes(int T) {
-    switch (T) {
-    case MO_T_BOOL: case MO_T_INT8: case MO_T_UINT8: return 1;
-    case MO_T_INT16: case MO_T_UINT16: return 2;
-    case MO_T_INT32: case MO_T_UINT32: case MO_T_FLOAT32: case MO_T_DATE: return 4;
-    default: return 8;
-    }
-}
 
 __device__ __forceinline__ uint64_t global_find(PlanGlobal &G, uint64_t key) {
     if (key == kEmptyKey) { G.key[G.mask + 1] = key; return G.mask + 1; }
@@ -270,11 +262,13 @@ plan_kernel(const mo_plan_t *__restrict__ Pg, const PlanAux *__restrict__ Ag, Pl
                 if (isnull) nb[j] |= 1u << dst;
             }
         }
-        // ---- group + aggregate, row by row (dictionary state is sequential)
+        // ---- group: key + private-dictionary lookup per row (the dictionary state is sequential) ...
+        int ps[R];
+        uint64_t keys[R];
 #pragma unroll
         for (int j = 0; j < R; j++) {
+            ps[j] = -1; keys[j] = 0;
             if (!ok[j]) continue;
-            const uint64_t r = base + (uint64_t)j * kThreads + threadIdx.x;
             const unsigned nullbits = nb[j];
             // group key (fillKeys; has_null mode: marker byte per column, a NULL contributes the marker only) from the raw integer slots
             uint64_t key = 0;
@@ -282,7 +276,7 @@ plan_kernel(const mo_plan_t *__restrict__ Pg, const PlanAux *__restrict__ Ag, Pl
                 int off = 0;
                 for (int k = 0; k < P.nkeys; k++) {
                     const int c = P.key_col[k];
-                    const int sz = type_bytes(P.col_type[c]);
+                    const int sz = X.sz[c];
                     const bool isnull = (nullbits >> c) & 1u;
                     if (P.has_null_keys) { if (isnull) { key |= 1ull << (8 * off); off += 1; continue; } off += 1; }
                     uint64_t raw = my[(c * R + j) * kThreads];
@@ -294,12 +288,11 @@ plan_kernel(const mo_plan_t *__restrict__ Pg, const PlanAux *__restrict__ Ag, Pl
                     off += sz;
                 }
             }
-            const uint64_t grow = (uint64_t)P.row_base + r;
-            // private dictionary (first kPriv keys of this CTA)
-            int ps = -1;
+            keys[j] = key;
+            int p = -1;
 #pragma unroll
-            for (int g = 0; g < kPriv; g++) if (dk[g] == key) ps = g;
-            if (ps < 0 && !dict_full && key != kEmptyKey) {
+            for (int g = 0; g < kPriv; g++) if (dk[g] == key) p = g;
+            if (p < 0 && !dict_full && key != kEmptyKey) {
                 bool okc = false;
 #pragma unroll
                 for (int g = 0; g < kPriv; g++) {
@@ -308,27 +301,42 @@ plan_kernel(const mo_plan_t *__restrict__ Pg, const PlanAux *__restrict__ Ag, Pl
                 }
                 bool full = true;
 #pragma unroll
-                for (int g = 0; g < kPriv; g++) { dk[g] = ((volatile unsigned long long *)pdict)[g]; full = full && dk[g] != kEmptyKey; if (dk[g] == key) ps = g; }
+                for (int g = 0; g < kPriv; g++) { dk[g] = ((volatile unsigned long long *)pdict)[g]; full = full && dk[g] != kEmptyKey; if (dk[g] == key) p = g; }
                 dict_full = full;
             }
-            if (ps >= 0) {
-                prows[ps * kThreads] += 1u;
-                if (pfirst[ps * kThreads] == ~0ull) pfirst[ps * kThreads] = grow;     // a thread meets its rows in increasing order
-                for (int a = 0; a < naggs; a++) {
-                    const int vs = P.agg[a].value, kind = P.agg[a].kind;
-                    if (vs >= 0 && ((nullbits >> vs) & 1u)) continue;
-                    const int ix = (ps * naggs + a) * kThreads;
-                    if (X.need_cnt) pcnt[ix] += 1u;
-                    if (vs < 0) continue;
-                    const double v = slot_f64(my[(vs * R + j) * kThreads], vs < P.ncols && X.is_int[vs], vs < P.ncols && P.col_type[vs] == MO_T_UINT64);
-                    if (kind == MO_AGG_SUM || kind == MO_AGG_AVG) pacc[ix] = __dadd_rn(pacc[ix], v);
-                    else if (kind != MO_AGG_COUNT && v == v) {
-                        const unsigned long long kv = flt_key(v), cur = (unsigned long long)__double_as_longlong(pacc[ix]);
-                        if (kind == MO_AGG_MIN ? kv < cur : kv > cur) pacc[ix] = __longlong_as_double((long long)kv);
-                    }
-                }
-                continue;
+            ps[j] = p;
+            if (p >= 0) {
+                prows[p * kThreads] += 1u;
+                if (pfirst[p * kThreads] == ~0ull) pfirst[p * kThreads] = (uint64_t)P.row_base + base + (uint64_t)j * kThreads + threadIdx.x;   // a thread meets its rows in increasing order
             }
+        }
+        // ---- ... then the aggregates COLUMN AT A TIME over the thread's rows that live in private state: one decode per aggregate per tile
+        for (int a = 0; a < naggs; a++) {
+            const int vs = P.agg[a].value, kind = P.agg[a].kind;
+            const bool vi = vs >= 0 && vs < P.ncols && X.is_int[vs], vu = vi && P.col_type[vs] == MO_T_UINT64;
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                if (ps[j] < 0) continue;
+                if (vs >= 0 && ((nb[j] >> vs) & 1u)) continue;
+                const int ix = (ps[j] * naggs + a) * kThreads;
+                if (X.need_cnt) pcnt[ix] += 1u;
+                if (vs < 0) continue;
+                const double v = slot_f64(my[(vs * R + j) * kThreads], vi, vu);
+                if (kind == MO_AGG_SUM || kind == MO_AGG_AVG) pacc[ix] = __dadd_rn(pacc[ix], v);
+                else if (kind != MO_AGG_COUNT && v == v) {
+                    const unsigned long long kv = flt_key(v), cur = (unsigned long long)__double_as_longlong(pacc[ix]);
+                    if (kind == MO_AGG_MIN ? kv < cur : kv > cur) pacc[ix] = __longlong_as_double((long long)kv);
+                }
+            }
+        }
+        // ---- rows whose key is not in the private dictionary: shared CTA table, then the global table
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            if (!ok[j] || ps[j] >= 0) continue;
+            const uint64_t r = base + (uint64_t)j * kThreads + threadIdx.x;
+            const unsigned nullbits = nb[j];
+            const uint64_t key = keys[j];
+            const uint64_t grow = (uint64_t)P.row_base + r;
             // shared CTA table, then the global table
             int slot = -1;
             if (key != kEmptyKey) {

@@ -745,3 +745,21 @@ class JoinMap:
             lib = capi.load_library()
             lib.MoB200_JoinMapRelease(self.table_keys.ctypes.data)
             self.prepared = False
+
+
+# ---------------------------------------------------------------------------------------------- Elkan k-means (csrc/kmeans.cu)
+def kmeans_elkan(vectors, init_centroids, max_iter=500, rnd=None):
+    """ElkanClusterer.Cluster from given initial centroids (pkg/vectorindex/ivfflat/kmeans/elkans/clusterer.go:330-392), dense variant.
+    Returns (centroids [k, dim], assignments int64[n], iterations)."""
+    v = np.ascontiguousarray(vectors)
+    assert v.dtype in (np.float32, np.float64)
+    n, dim = v.shape
+    cent = np.ascontiguousarray(init_centroids, dtype=v.dtype).copy()
+    k = cent.shape[0]
+    assign = np.zeros(n, dtype=np.int64); iters = np.zeros(1, dtype=np.int64)
+    prm = np.array([n, dim, k, max_iter], dtype=np.int64)
+    vecs = [Vector(data=cent.reshape(-1), length=k * dim), Vector(data=assign, length=n), Vector(data=iters, length=1), Vector(data=prm.view(np.uint8), length=1),
+            Vector(data=v.reshape(-1), length=n * dim),
+            Vector(data=np.ascontiguousarray(rnd, dtype=np.float32), length=len(rnd)) if rnd is not None and len(rnd) else Vector(length=0)]
+    xcall(capi.XCALL_KMEANS_ELKAN_F32 if v.dtype == np.float32 else capi.XCALL_KMEANS_ELKAN_F64, vecs, n)
+    return cent, assign, int(iters[0])

@@ -1462,3 +1462,116 @@ int64_t og_join_probe(const uint64_t *vals, int64_t n, const int32_t *offsets, c
 #undef EMIT
     return r;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Elkan k-means, dense (non-spherical) variant: pkg/vectorindex/ivfflat/kmeans/elkans/clusterer.go.  distFn = metric.L2Distance
+ * for every metric (ResolveKmeansDistanceFnForDense, distance_func.go:452-476).  Every step is deterministic given the initial centroids:
+ * the per-vector loops are independent, recalculateCentroids sums the members serially in row order in T.  The reference's
+ * thread pools only partition independent rows, so one thread reproduces them.  Layouts: vectors [n][dim], centroids [k][dim],
+ * lower [n][k], upper [n], recompute uint8 [n], assign int64 [n], half [k][k], minhalf [k].
+ * ------------------------------------------------------------------------------------------- */
+#define KMEANS_IMPL(T, SFX, MAXT)                                                                                         \
+    /* initBounds, clusterer.go:458-512 */                                                                               \
+    void og_km_init_bounds_##SFX(const T *vec, int64_t n, int64_t dim, const T *cent, int64_t k, T *lower, T *upper, int64_t *assign) { \
+        for (int64_t x = 0; x < n; x++) {                                                                                \
+            T minDist = MAXT; int64_t closest = 0;                                                                        \
+            for (int64_t c = 0; c < k; c++) {                                                                            \
+                T dist = og_l2_##SFX(vec + x * dim, cent + c * dim, dim);                                                 \
+                lower[x * k + c] = dist;                                                                                  \
+                if (dist < minDist) { minDist = dist; closest = c; }                                                      \
+            }                                                                                                             \
+            upper[x] = minDist; assign[x] = closest;                                                                      \
+        }                                                                                                                 \
+    }                                                                                                                     \
+    /* computeCentroidDistances, clusterer.go:516-575: 0.5 d(c, c') (diagonal untouched) and s(c) = min over c' != c */    \
+    void og_km_centroid_dists_##SFX(const T *cent, int64_t k, int64_t dim, T *half, T *minhalf) {                        \
+        for (int64_t i = 0; i < k; i++)                                                                                   \
+            for (int64_t j = i + 1; j < k; j++) {                                                                        \
+                T dist = og_l2_##SFX(cent + i * dim, cent + j * dim, dim);                                                \
+                dist *= (T)0.5;                                                                                           \
+                half[i * k + j] = dist; half[j * k + i] = dist;                                                           \
+            }                                                                                                             \
+        for (int64_t i = 0; i < k; i++) {                                                                                 \
+            T cur = (T)3.40282346638528859811704183484516925440e+38; /* T(math.MaxFloat32) */                             \
+            for (int64_t j = 0; j < k; j++) { if (i == j) continue; cur = (T)fmin((double)cur, (double)half[i * k + j]); } \
+            minhalf[i] = cur;                                                                                             \
+        }                                                                                                                 \
+    }                                                                                                                     \
+    /* assignData, clusterer.go:579-676; returns the number of changes */                                               \
+    int64_t og_km_assign_##SFX(const T *vec, int64_t n, int64_t dim, const T *cent, int64_t k, const T *half, const T *minhalf, \
+                               T *lower, T *upper, uint8_t *recompute, int64_t *assign) {                                 \
+        int64_t changes = 0;                                                                                              \
+        for (int64_t x = 0; x < n; x++) {                                                                                \
+            if (upper[x] <= minhalf[assign[x]]) continue;                                                                 \
+            for (int64_t c = 0; c < k; c++) {                                                                            \
+                if (c != assign[x] && upper[x] > lower[x * k + c] && upper[x] > half[assign[x] * k + c]) {                \
+                    T dxcx;                                                                                               \
+                    if (recompute[x]) {                                                                                   \
+                        recompute[x] = 0;                                                                                 \
+                        dxcx = og_l2_##SFX(vec + x * dim, cent + assign[x] * dim, dim);                                   \
+                        upper[x] = dxcx; lower[x * k + assign[x]] = dxcx;                                                 \
+                        if (upper[x] <= lower[x * k + c]) continue;                                                       \
+                        if (upper[x] <= half[assign[x] * k + c]) continue;                                                \
+                    } else dxcx = upper[x];                                                                               \
+                    if (dxcx > lower[x * k + c] || dxcx > half[assign[x] * k + c]) {                                      \
+                        T dxc = og_l2_##SFX(vec + x * dim, cent + c * dim, dim);                                          \
+                        lower[x * k + c] = dxc;                                                                           \
+                        if (dxc < dxcx) { upper[x] = dxc; assign[x] = c; changes++; }                                     \
+                    }                                                                                                     \
+                }                                                                                                         \
+            }                                                                                                             \
+        }                                                                                                                 \
+        return changes;                                                                                                   \
+    }                                                                                                                     \
+    /* recalculateCentroids, clusterer.go:679-727 (normalize == false).  An empty cluster takes dim values of the caller's rnd.Float32()   \
+       stream (rnd[*rnd_used ...]); returns -1 when that stream runs dry. */                                              \
+    int32_t og_km_recalc_##SFX(const T *vec, int64_t n, int64_t dim, const int64_t *assign, int64_t k, T *newc, int64_t *members, \
+                               const float *rnd, int64_t rnd_len, int64_t *rnd_used) {                                    \
+        for (int64_t c = 0; c < k; c++) members[c] = 0;                                                                   \
+        for (int64_t i = 0; i < k * dim; i++) newc[i] = 0;                                                                \
+        for (int64_t x = 0; x < n; x++) {                                                                                \
+            int64_t cx = assign[x]; members[cx]++;                                                                        \
+            for (int64_t i = 0; i < dim; i++) newc[cx * dim + i] += vec[x * dim + i];                                     \
+        }                                                                                                                 \
+        for (int64_t c = 0; c < k; c++) {                                                                                 \
+            if (members[c] == 0) {                                                                                        \
+                for (int64_t l = 0; l < dim; l++) { if (*rnd_used >= rnd_len) return -1; newc[c * dim + l] = (T)rnd[(*rnd_used)++]; } \
+            } else {                                                                                                      \
+                T scale = (T)1.0 / (T)members[c];              /* metric.ScaleInPlace(v, 1.0/T(count)): v[i] *= scale */   \
+                for (int64_t i = 0; i < dim; i++) newc[c * dim + i] *= scale;                                             \
+            }                                                                                                             \
+        }                                                                                                                 \
+        return 0;                                                                                                         \
+    }                                                                                                                     \
+    /* updateBounds, clusterer.go:730-762 */                                                                             \
+    void og_km_update_bounds_##SFX(const T *cent, const T *newc, int64_t k, int64_t dim, int64_t n, const int64_t *assign, \
+                                   T *lower, T *upper, uint8_t *recompute, T *shift) {                                    \
+        for (int64_t c = 0; c < k; c++) shift[c] = og_l2_##SFX(cent + c * dim, newc + c * dim, dim);                     \
+        for (int64_t x = 0; x < n; x++) {                                                                                \
+            for (int64_t c = 0; c < k; c++) { T s = lower[x * k + c] - shift[c]; lower[x * k + c] = s > 0 ? s : (s != s ? s : (T)0); /* T(math.Max(float64(s), 0)): -0 -> +0 */ } \
+            upper[x] += shift[assign[x]]; recompute[x] = 1;                                                               \
+        }                                                                                                                 \
+    }                                                                                                                     \
+    /* Cluster + elkansCluster, clusterer.go:330-392, from given initial centroids (InitCentroids is the caller's: it draws from Go's    \
+       PCG).  cent [k][dim] in/out; assign out.  Returns the number of iterations run, or -1 (rnd stream dry). */          \
+    int64_t og_km_cluster_##SFX(const T *vec, int64_t n, int64_t dim, T *cent, int64_t k, int64_t max_iter, const float *rnd, int64_t rnd_len, \
+                                int64_t *assign) {                                                                        \
+        T *lower = malloc(sizeof(T) * (size_t)(n * k)), *upper = malloc(sizeof(T) * (size_t)n), *half = calloc((size_t)(k * k), sizeof(T)); \
+        T *minhalf = malloc(sizeof(T) * (size_t)k), *next = malloc(sizeof(T) * (size_t)(k * dim)), *shift = malloc(sizeof(T) * (size_t)k); \
+        uint8_t *recompute = malloc((size_t)n); int64_t *members = malloc(sizeof(int64_t) * (size_t)k);                   \
+        int64_t used = 0, iter = 0; int bad = 0;                                                                          \
+        for (int64_t x = 0; x < n; x++) recompute[x] = 1;       /* NewKMeans: recompute = true, clusterer.go */           \
+        og_km_init_bounds_##SFX(vec, n, dim, cent, k, lower, upper, assign);                                              \
+        for (;; iter++) {                                                                                                 \
+            og_km_centroid_dists_##SFX(cent, k, dim, half, minhalf);                                                      \
+            int64_t changes = og_km_assign_##SFX(vec, n, dim, cent, k, half, minhalf, lower, upper, recompute, assign);   \
+            if (og_km_recalc_##SFX(vec, n, dim, assign, k, next, members, rnd, rnd_len, &used)) { bad = 1; break; }       \
+            og_km_update_bounds_##SFX(cent, next, k, dim, n, assign, lower, upper, recompute, shift);                     \
+            memcpy(cent, next, sizeof(T) * (size_t)(k * dim));  /* km.centroids, km.nextCentroids = newCentroids, km.centroids */ \
+            if (iter != 0 && (iter == max_iter || changes == 0)) break;                                                   \
+        }                                                                                                                 \
+        free(lower); free(upper); free(half); free(minhalf); free(next); free(shift); free(recompute); free(members);     \
+        return bad ? -1 : iter + 1;                                                                                       \
+    }
+KMEANS_IMPL(float, f32, 3.40282346638528859811704183484516925440e+38f)
+KMEANS_IMPL(double, f64, 1.79769313486231570814527423731704356798070e+308)

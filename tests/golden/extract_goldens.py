@@ -331,3 +331,54 @@ def main2():
 
 if __name__ == "__main__" and "--round2" in __import__("sys").argv:
     main2()
+
+
+# ---------------------------------------------------------------------------------------------- round 2, step 3: Elkan k-means step tables
+def _matrix(block, field):
+    m = re.search(r"%s:\s*\[\]\[\]float64\{(.*?)\n\s*\}," % field, block, re.S)
+    if not m:
+        return None
+    body = re.sub(r"//[^\n]*", "", m.group(1))
+    return [_floats(r) for r in re.findall(r"\{([^{}]*)\}", body)]
+
+
+def _metas(block):
+    out = []
+    for m in re.finditer(r"lower:\s*\[\]float64\{([^}]*)\},\s*upper:\s*(%s),\s*recompute:\s*(true|false)," % NUM, block):
+        out.append({"lower": _floats(m.group(1)), "upper": float(m.group(2)), "recompute": m.group(3) == "true"})
+    return out
+
+
+def kmeans_kats():
+    """the per-step tables of pkg/vectorindex/ivfflat/kmeans/elkans/clusterer_test.go (initBounds :501-616, computeCentroidDistances :618-702,
+    recalculateCentroids :704-787, updateBounds :789-939), compared there with assertx.InEpsilonF64 / reflect.DeepEqual"""
+    src = open(os.path.join(REF, "pkg/vectorindex/ivfflat/kmeans/elkans/clusterer_test.go")).read()
+    out = {"_source": "pkg/vectorindex/ivfflat/kmeans/elkans/clusterer_test.go", "_compare": "assertx.InEpsilonF64 (assignments: reflect.DeepEqual)"}
+    b = _func_body(src, "TestElkanClusterer_initBounds")
+    b = b[:b.index("ctx := context.Background()")]
+    out["init_bounds"] = {"vectors": _matrix(b, "vectorList"), "centroids": _matrix(b, "centroids"), "metas": _metas(b),
+                          "assignment": [int(x) for x in re.search(r"assignment:\s*\[\]int\{([^}]*)\}", b).group(1).split(",")]}
+    b = _func_body(src, "TestElkanClusterer_computeCentroidDistances")
+    b = b[:b.index("ctx := context.Background()")]
+    out["centroid_dists"] = {"centroids": _matrix(b, "centroids"), "half": _matrix(b, "halfInterCentroidDistMatrix"),
+                             "minhalf": _floats(re.search(r"minHalfInterCentroidDist:\s*\[\]float64\{([^}]*)\}", b).group(1))}
+    b = _func_body(src, "TestElkanClusterer_recalculateCentroids")
+    b = b[:b.index("ctx := context.Background()")]
+    out["recalc"] = {"vectors": _matrix(b, "vectorList"), "assignments": [int(x) for x in re.search(r"assignments:\s*\[\]int\{([^}]*)\}", b).group(1).split(",")],
+                     "centroids": _matrix(b[b.index("want:"):], "centroids")}
+    b = _func_body(src, "TestElkanClusterer_updateBounds")
+    b = b[:b.index("ctx := context.Background()")]
+    st, wt = b[b.index("state: internalState"):b.index("want: wantState")], b[b.index("want: wantState"):]
+    out["update_bounds"] = {"metas": _metas(st), "centroids": _matrix(st, "centroids"), "new_centroids": _matrix(st, "newCentroids"), "want": _metas(wt)}
+    return out
+
+
+def main3():
+    data = kmeans_kats()
+    with open(os.path.join(OUT, "kmeans_kat.json"), "w") as f:
+        json.dump(data, f, indent=0)
+    print("kmeans_kat", {k: len(v) for k, v in data.items() if not k.startswith("_")})
+
+
+if __name__ == "__main__" and "--kmeans" in __import__("sys").argv:
+    main3()

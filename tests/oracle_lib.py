@@ -36,6 +36,19 @@ def go():
         lib.og_multi_logic.argtypes = [_i32, _vp, _vp, _i32, _vp, _vp, _vp, _u64]
         lib.og_filter_sels.restype = _i64
         lib.og_filter_sels.argtypes = [_vp, _vp, _u64, _vp]
+        for sfx in ("f32", "f64"):
+            getattr(lib, "og_km_init_bounds_" + sfx).restype = None
+            getattr(lib, "og_km_init_bounds_" + sfx).argtypes = [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp]
+            getattr(lib, "og_km_centroid_dists_" + sfx).restype = None
+            getattr(lib, "og_km_centroid_dists_" + sfx).argtypes = [_vp, _i64, _i64, _vp, _vp]
+            getattr(lib, "og_km_assign_" + sfx).restype = _i64
+            getattr(lib, "og_km_assign_" + sfx).argtypes = [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]
+            getattr(lib, "og_km_recalc_" + sfx).restype = _i32
+            getattr(lib, "og_km_recalc_" + sfx).argtypes = [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp]
+            getattr(lib, "og_km_update_bounds_" + sfx).restype = None
+            getattr(lib, "og_km_update_bounds_" + sfx).argtypes = [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]
+            getattr(lib, "og_km_cluster_" + sfx).restype = _i64
+            getattr(lib, "og_km_cluster_" + sfx).argtypes = [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp]
         lib.og_join_sels.restype = _i64
         lib.og_join_sels.argtypes = [_vp, _i64, _i64, _vp, _vp]
         lib.og_join_find.restype = None

@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, step 3: grouped-load plan interpreter, normalize_l2, centroid assignment on the tensor cores, dynamic unit feed of the candidate kernel
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_join.py tests/test_gpu_bloom.py tests/test_gpu_plan.py tests/test_gpu_normalize.py tests/test_gpu_search.py -q -m gpu 2>&1 | tail -25
+timeout 900 python -m pytest tests/test_gpu_kmeans.py tests/test_gpu_join.py tests/test_gpu_bloom.py tests/test_gpu_plan.py tests/test_gpu_normalize.py tests/test_gpu_search.py -q -m gpu 2>&1 | tail -25
 timeout 300 python tools/profile_ops.py > gpurun_out/r02_ops_microbench_v3.json 2> gpurun_out/r02_ops_microbench_v3.err
 python - <<'PY'
 import json
