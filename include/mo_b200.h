@@ -245,6 +245,11 @@ typedef struct { int32_t div0_null; int32_t reserved; int64_t err_row; } mo_go_p
  * [1] assignments int64[n] (out) ; [2] int64 iterations (out) ; [3] host mo_kmeans_params_t ; [4] vectors T[n * dim] ;
  * [5] rnd float32[] (optional): the rnd.Float32() stream an EMPTY cluster re-seeds its centroid from (clusterer.go:700-707), consumed in
  * cluster order, dim values per empty cluster; running out of it fails the call with MO_RC_INVALID_ARGUMENT. */
+/* ---- LZ4 block decompression of column blocks (csrc/lz4.cu): compress.Decompress = lz4.UncompressBlock (pkg/compress/compress.go:37-47), one
+ * warp per block.  args: [0] dst bytes ; [1] src bytes ; [2] int64[4 * len] descriptors {src_off, src_len, dst_off, dst_len} per block (dst_len = the
+ * decoded size the object metadata records; a block that decodes to anything else, or is malformed, fails the call with MO_RC_INVALID_ARGUMENT and
+ * the block number in the error text).  len = number of blocks. */
+#define MO_XCALL_LZ4_DECODE 0x6030
 typedef struct mo_kmeans_params_t { int64_t n, dim, k, max_iter; } mo_kmeans_params_t;
 #define MO_XCALL_KMEANS_ELKAN_F32 0x6020
 #define MO_XCALL_KMEANS_ELKAN_F64 0x6021

@@ -1,0 +1,95 @@
+// lz4.cu -- LZ4 block decompression of column blocks on the device ("block decode -> device").
+//
+// Reference: pkg/compress/compress.go:37-47 (Decompress = lz4.UncompressBlock of github.com/pierrec/lz4/v4 v4.1.21, go.mod:73) as called by the
+// object reader for every column block (pkg/objectio).  The Go module is a third-party dependency that is not part of /root/reference; the LZ4
+// BLOCK format itself is published (lz4_Block_format.md): a block is a series of sequences
+//     token (hi nibble: literal length, lo nibble: match length - 4; 15 = continued in 255-terminated extension bytes)
+//     literals, 2-byte little-endian match offset (1 .. 65535, back from the write position), match copy (may overlap itself)
+// and the last sequence ends after its literals.  The restatement is pinned against liblz4 (pyarrow's lz4_raw codec) in the tests.
+//
+// Mapping: a block is inherently sequential, a table scan has thousands of them: ONE WARP PER BLOCK.  All lanes parse the token stream
+// redundantly (uniform control flow, broadcast loads); literal and match copies are cooperative, lane l takes bytes l, l + 32, ...; an
+// overlapping match (offset < length) is a periodic pattern, byte i of the match is byte (i mod offset) of the last `offset` output bytes, so it is
+// copied in parallel too.  A __syncwarp() between sequences orders the output bytes a later match reads.  Malformed input (offset 0 or before the
+// block, lengths past either buffer, decoded size != the descriptor's) fails the call and names the block.
+// Algorithmic bytes per block: compressed bytes in + decoded bytes out.
+#include "common.cuh"
+#include <cstring>
+
+namespace mob {
+namespace {
+
+constexpr int kWarpsPerCta = 4;
+
+__global__ void __launch_bounds__(32 * kWarpsPerCta)
+lz4_decode_kernel(uint8_t *__restrict__ dst_base, uint64_t dst_cap, const uint8_t *__restrict__ src_base, uint64_t src_cap, const int64_t *__restrict__ desc, uint64_t nblocks,
+                  unsigned long long *first_bad) {
+    const unsigned lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t b = warp; b < nblocks; b += nwarps) {
+        const int64_t so = desc[4 * b], sl = desc[4 * b + 1], dof = desc[4 * b + 2], dl = desc[4 * b + 3];
+        bool bad = so < 0 || sl < 0 || dof < 0 || dl < 0 || (uint64_t)so + (uint64_t)sl > src_cap || (uint64_t)dof + (uint64_t)dl > dst_cap;
+        if (!bad) {
+            const uint8_t *src = src_base + so;
+            volatile uint8_t *dst = dst_base + dof;
+            int64_t ip = 0, op = 0;
+            if (sl == 0) bad = dl != 0;
+            while (!bad && ip < sl) {
+                const unsigned token = src[ip++];
+                int64_t lit = token >> 4;
+                if (lit == 15) { unsigned e; do { if (ip >= sl) { bad = true; break; } e = src[ip++]; lit += e; } while (e == 255); }
+                if (bad || ip + lit > sl || op + lit > dl) { bad = true; break; }
+                for (int64_t i = lane; i < lit; i += 32) dst[op + i] = src[ip + i];
+                ip += lit; op += lit;
+                if (ip >= sl) break;                                   // the last sequence: literals only
+                if (ip + 2 > sl) { bad = true; break; }
+                const int64_t offset = (int64_t)src[ip] | ((int64_t)src[ip + 1] << 8);
+                ip += 2;
+                int64_t mlen = token & 15;
+                if (mlen == 15) { unsigned e; do { if (ip >= sl) { bad = true; break; } e = src[ip++]; mlen += e; } while (e == 255); }
+                mlen += 4;
+                if (bad || offset == 0 || offset > op || op + mlen > dl) { bad = true; break; }
+                __syncwarp();                                          // the bytes this match reads were written by other lanes
+                const int64_t from = op - offset;
+                if (offset >= mlen) { for (int64_t i = lane; i < mlen; i += 32) dst[op + i] = dst[from + i]; }
+                else { for (int64_t i = lane; i < mlen; i += 32) dst[op + i] = dst[from + (i % offset)]; }   // overlapping: periodic with period `offset`
+                op += mlen;
+                __syncwarp();
+            }
+            if (!bad && op != dl) bad = true;
+        }
+        if (bad && lane == 0) atomicMin(first_bad, (unsigned long long)b);
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+// MO_XCALL_LZ4_DECODE: args [0] dst bytes ; [1] src bytes ; [2] descriptors int64[4 * len]: {src_off, src_len, dst_off, dst_len} per block.  len = blocks.
+int xcall_lz4_decode(mo_xcall_args_t *args, uint64_t len) {
+    ThreadCtx &t = tctx();
+    if (!t.ready) return MO_RC_INTERNAL_ERROR;
+    if (len == 0) return MO_RC_SUCCESS;
+    if (!args[2].pdata || args[2].dataSz < 32 * len) { set_error("lz4 decode: descriptor vector shorter than 4 int64 per block"); return MO_RC_INVALID_ARGUMENT; }
+    Stager st(t);
+    uint8_t *dst = (uint8_t *)st.out(args[0].pdata, args[0].dataSz);
+    const uint8_t *src = (const uint8_t *)st.in(args[1].pdata, args[1].dataSz);
+    const int64_t *desc = (const int64_t *)st.in(args[2].pdata, 32 * len);
+    unsigned long long *dbad = (unsigned long long *)st.tmp(8);
+    if (st.failed) { st.finish(); return MO_RC_INTERNAL_ERROR; }
+    MOB_CUDA_TRY(cudaMemsetAsync(dbad, 0xff, 8, t.stream));
+    uint64_t ctas = (len + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (ctas > (uint64_t)num_sms() * 16) ctas = (uint64_t)num_sms() * 16;
+    cudaEventRecord(t.kev0, t.stream);
+    lz4_decode_kernel<<<(unsigned)ctas, 32 * kWarpsPerCta, 0, t.stream>>>(dst, args[0].dataSz, src, args[1].dataSz, desc, len, dbad);
+    cudaEventRecord(t.kev1, t.stream);
+    MOB_LAUNCH_CHECK();
+    unsigned long long bad = ~0ull;
+    int rc = read_back(t, &bad, dbad, 8);
+    int frc = st.finish();
+    if (rc) return rc;
+    if (bad != ~0ull) { set_error("lz4 decode: block %llu is malformed or does not decode to its descriptor's size", bad); return MO_RC_INVALID_ARGUMENT; }
+    return frc;
+}
+
+}  // namespace mob

@@ -98,25 +98,37 @@ __global__ void plan_init_kernel(PlanGlobal G, int naggs, const mo_plan_t *P) {
 
 // ---- the interpreter: VECTORISED, like the reference's own execution model (one operator over a batch at a time) --------------------------
 // A CTA works on tiles of kThreads x R rows; thread t owns rows t, t + kThreads, ... of the tile.  Every operator of the plan -- column load,
-// predicate, expression node -- is decoded ONCE per tile (the `switch` on type / opcode is warp-uniform) and then applied to the thread's R
-// rows from a shared-memory register file vreg[slot][r][thread] (conflict-free: thread-minor).  That amortises the decode over R rows and puts
-// R x ncols independent loads in flight per thread.  Integer columns stay in the integer domain (raw int64 in the register file): predicates
-// on them compare as int64 when their constants are integral, so a DATE / int column that only feeds the filter never touches the slow
-// int -> float64 conversion pipe; they are converted when an expression node reads them.
+// predicate, expression node, key column, aggregate -- is decoded ONCE per tile: the switch on type / opcode sits OUTSIDE the loop over the
+// thread's R rows (explicitly: the compiler does not unswitch it), so the inner loops are straight-line code over a shared-memory register
+// file vreg[slot][r][thread] (thread-minor: conflict-free).  Every slot has a DOMAIN fixed by the host when the plan is decoded: integer
+// columns that only feed integer predicates or group keys stay raw int64 (compared as integers, never converted); columns that feed an
+// expression or an aggregate are converted to float64 once, when they are loaded.  Column loads are issued kGroup columns at a time before
+// anything consumes them (kGroup x R loads in flight per thread).
 constexpr int R = 4;
 constexpr int kGroup = 4;      // columns whose loads are issued together
 
 struct PlanAux {                       // host-prepared decode of the descriptor
-    int is_int[MO_PLAN_MAX_COLS];      // column is an integer type (raw int64 in the register file)
     int sz[MO_PLAN_MAX_COLS];          // element width in bytes
-    int pred_int[MO_PLAN_MAX_PREDS];   // predicate compares in the integer domain
+    int ext[MO_PLAN_MAX_COLS];         // after the load: 0 nothing (zero-extended), 1 / 2 / 3 sign-extend from 8 / 16 / 32 bits
+    int tof[MO_PLAN_MAX_COLS];         // then: 0 keep, 1 int64 -> float64, 2 uint64 -> float64, 3 float32 bits -> float64
+    int pred_int[MO_PLAN_MAX_PREDS];   // predicate compares in the integer domain (the slot holds a raw int64)
     long long ilo[MO_PLAN_MAX_PREDS], ihi[MO_PLAN_MAX_PREDS];
+    int key_mode[MO_PLAN_MAX_KEYS];    // 0 raw integer slot, 1 float64 slot holding an integer (exact: < 8-byte types), 2 reload the 8 bytes from the column,
+                                       // 3 float64 slot holding a float32 (key = its float32 bits), 4 float64 bits
+    int key_shift[MO_PLAN_MAX_KEYS];   // bit offset of the column inside the packed key when has_null_keys == 0
     int need_cnt;                      // some aggregate input can be NULL (nullable column or a division): per-aggregate counts are kept
 };
 
-__device__ __forceinline__ double slot_f64(unsigned long long raw, bool is_int, bool is_u64) {
-    if (!is_int) return __longlong_as_double((long long)raw);
-    return is_u64 ? (double)raw : (double)(long long)raw;
+#define PLAN_FORJ _Pragma("unroll") for (int j = 0; j < R; j++)
+#define PLAN_SLOT(s, j) my[((s) * R + (j)) * kThreads]
+
+__device__ __forceinline__ uint64_t plan_key_bits(int mode, unsigned long long slotv, const uint8_t *col, uint64_t r) {
+    switch (mode) {
+    case 1: return (uint64_t)(long long)__longlong_as_double((long long)slotv);
+    case 2: return reinterpret_cast<const unsigned long long *>(col)[r];
+    case 3: return (uint64_t)__float_as_uint((float)__longlong_as_double((long long)slotv));
+    default: return slotv;
+    }
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -142,10 +154,11 @@ plan_kernel(const mo_plan_t *__restrict__ Pg, const PlanAux *__restrict__ Ag, Pl
     // thread-minor so every access is conflict-free: a row then costs naggs x (LDS, op, STS) on its own copy -- no atomics, no shuffles.  Plans
     // with few groups (or none) live entirely here; further keys go to the shared CTA table, then to the global one.
     __shared__ unsigned long long pdict[kPriv];
-    double *pacc = reinterpret_cast<double *>(tcnt + (size_t)kCtaSlots * naggs) + threadIdx.x;        // [(g * naggs + a) * kThreads + tid]
-    unsigned *pcnt = reinterpret_cast<unsigned *>(pacc - threadIdx.x + (size_t)kPriv * naggs * kThreads) + threadIdx.x;
-    unsigned *prows = pcnt - threadIdx.x + (size_t)kPriv * naggs * kThreads + threadIdx.x;            // [g * kThreads + tid]
-    unsigned long long *pfirst = reinterpret_cast<unsigned long long *>(prows - threadIdx.x + (size_t)kPriv * kThreads) + threadIdx.x;
+    double *pacc0 = reinterpret_cast<double *>(tcnt + (size_t)kCtaSlots * naggs);                     // [(g * naggs + a) * kThreads + tid]
+    unsigned *pcnt0 = reinterpret_cast<unsigned *>(pacc0 + (size_t)kPriv * naggs * kThreads);
+    unsigned *prows0 = pcnt0 + (size_t)kPriv * naggs * kThreads;                                      // [g * kThreads + tid]
+    unsigned long long *pfirst0 = reinterpret_cast<unsigned long long *>(prows0 + (size_t)kPriv * kThreads);
+    double *pacc = pacc0 + threadIdx.x; unsigned *pcnt = pcnt0 + threadIdx.x, *prows = prows0 + threadIdx.x; unsigned long long *pfirst = pfirst0 + threadIdx.x;
     if (threadIdx.x < kPriv) pdict[threadIdx.x] = kEmptyKey;
     for (int g = 0; g < kPriv; g++) {
         for (int a = 0; a < naggs; a++) { pacc[(g * naggs + a) * kThreads] = agg_identity(P.agg[a].kind); pcnt[(g * naggs + a) * kThreads] = 0u; }
@@ -159,13 +172,11 @@ plan_kernel(const mo_plan_t *__restrict__ Pg, const PlanAux *__restrict__ Ag, Pl
     unsigned long long *my = vreg + threadIdx.x;
     const uint64_t tile_rows = (uint64_t)kThreads * R;
     for (uint64_t base = blockIdx.x * tile_rows; base < n; base += (uint64_t)gridDim.x * tile_rows) {
-        // ---- table scan: column c -> slots [c][0..R), null-ness -> bit c of nb[j].  Columns are taken kGroup at a time: first ALL their loads are
-        // issued (raw bits by element width, nothing consumes them yet, so kGroup x R loads per thread are in flight), then they are widened by
-        // type and stored.  (Loading and storing column by column serialises on every load: a generic pointer may alias shared memory.)
+        const uint64_t r0 = base + threadIdx.x;
         unsigned nb[R];
         bool ok[R];
-#pragma unroll
-        for (int j = 0; j < R; j++) { nb[j] = 0; ok[j] = base + (uint64_t)j * kThreads + threadIdx.x < n; }
+        PLAN_FORJ { nb[j] = 0; ok[j] = r0 + (uint64_t)j * kThreads < n; }
+        // ---- table scan
         for (int c0 = 0; c0 < P.ncols; c0 += kGroup) {
             unsigned long long raw[kGroup][R], nw[kGroup][R];
 #pragma unroll
@@ -174,218 +185,221 @@ plan_kernel(const mo_plan_t *__restrict__ Pg, const PlanAux *__restrict__ Ag, Pl
                 if (c < P.ncols) {
                     const uint8_t *d = C.data[c]; const uint64_t *nu = C.nulls[c];
                     const int sz = X.sz[c];
-                    const uint64_t r0 = base + threadIdx.x;
-                    if (sz == 8) {
-#pragma unroll
-                        for (int j = 0; j < R; j++) raw[g][j] = ok[j] ? __ldg(reinterpret_cast<const unsigned long long *>(d) + r0 + (uint64_t)j * kThreads) : 0ull;
-                    } else if (sz == 4) {
-#pragma unroll
-                        for (int j = 0; j < R; j++) raw[g][j] = ok[j] ? (unsigned long long)__ldg(reinterpret_cast<const unsigned *>(d) + r0 + (uint64_t)j * kThreads) : 0ull;
-                    } else if (sz == 2) {
-#pragma unroll
-                        for (int j = 0; j < R; j++) raw[g][j] = ok[j] ? (unsigned long long)__ldg(reinterpret_cast<const unsigned short *>(d) + r0 + (uint64_t)j * kThreads) : 0ull;
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < R; j++) raw[g][j] = ok[j] ? (unsigned long long)__ldg(d + r0 + (uint64_t)j * kThreads) : 0ull;
-                    }
-#pragma unroll
-                    for (int j = 0; j < R; j++) nw[g][j] = (nu && ok[j]) ? __ldg(reinterpret_cast<const unsigned long long *>(nu) + ((r0 + (uint64_t)j * kThreads) >> 6)) : 0ull;
+                    if (sz == 8) { PLAN_FORJ raw[g][j] = ok[j] ? __ldg(reinterpret_cast<const unsigned long long *>(d) + r0 + (uint64_t)j * kThreads) : 0ull; }
+                    else if (sz == 4) { PLAN_FORJ raw[g][j] = ok[j] ? (unsigned long long)__ldg(reinterpret_cast<const unsigned *>(d) + r0 + (uint64_t)j * kThreads) : 0ull; }
+                    else if (sz == 2) { PLAN_FORJ raw[g][j] = ok[j] ? (unsigned long long)__ldg(reinterpret_cast<const unsigned short *>(d) + r0 + (uint64_t)j * kThreads) : 0ull; }
+                    else { PLAN_FORJ raw[g][j] = ok[j] ? (unsigned long long)__ldg(d + r0 + (uint64_t)j * kThreads) : 0ull; }
+                    if (nu) { PLAN_FORJ nw[g][j] = ok[j] ? __ldg(reinterpret_cast<const unsigned long long *>(nu) + ((r0 + (uint64_t)j * kThreads) >> 6)) : 0ull; }
+                    else { PLAN_FORJ nw[g][j] = 0ull; }
                 }
             }
 #pragma unroll
             for (int g = 0; g < kGroup; g++) {
                 const int c = c0 + g;
                 if (c < P.ncols) {
-                    const int T = P.col_type[c];
-#pragma unroll
-                    for (int j = 0; j < R; j++) {
-                        unsigned long long v = raw[g][j];
-                        if (T == MO_T_INT8) v = (unsigned long long)(long long)(int8_t)v;
-                        else if (T == MO_T_INT16) v = (unsigned long long)(long long)(int16_t)v;
-                        else if (T == MO_T_INT32 || T == MO_T_DATE) v = (unsigned long long)(long long)(int32_t)v;
-                        else if (T == MO_T_FLOAT32) v = (unsigned long long)__double_as_longlong((double)__uint_as_float((unsigned)v));
-                        my[(c * R + j) * kThreads] = v;
-                        nb[j] |= (unsigned)((nw[g][j] >> ((base + (uint64_t)j * kThreads + threadIdx.x) & 63)) & 1ull) << c;
-                    }
+                    const int ext = X.ext[c], tof = X.tof[c];
+                    if (ext == 3) { PLAN_FORJ raw[g][j] = (unsigned long long)(long long)(int32_t)raw[g][j]; }
+                    else if (ext == 2) { PLAN_FORJ raw[g][j] = (unsigned long long)(long long)(int16_t)raw[g][j]; }
+                    else if (ext == 1) { PLAN_FORJ raw[g][j] = (unsigned long long)(long long)(int8_t)raw[g][j]; }
+                    if (tof == 1) { PLAN_FORJ raw[g][j] = (unsigned long long)__double_as_longlong((double)(long long)raw[g][j]); }
+                    else if (tof == 2) { PLAN_FORJ raw[g][j] = (unsigned long long)__double_as_longlong((double)raw[g][j]); }
+                    else if (tof == 3) { PLAN_FORJ raw[g][j] = (unsigned long long)__double_as_longlong((double)__uint_as_float((unsigned)raw[g][j])); }
+                    PLAN_FORJ { PLAN_SLOT(c, j) = raw[g][j]; nb[j] |= (unsigned)((nw[g][j] >> ((r0 + (uint64_t)j * kThreads) & 63)) & 1ull) << c; }
                 }
             }
         }
         // ---- filter: conjunction; a NULL operand makes the conjunct not-true (filter.go:125-141 keeps rows with !null && true)
         for (int q = 0; q < P.npreds; q++) {
-            const mo_plan_pred_t &pr = P.pred[q];
-            const int c = pr.col, op = pr.op;
+            const int c = P.pred[q].col, op = P.pred[q].op;
+#define PLAN_PRED(XT, LOADX, EXPR) PLAN_FORJ { const XT x = LOADX; ok[j] = ok[j] && (EXPR) && !((nb[j] >> c) & 1u); }
+#define PLAN_PRED_SWITCH(XT, LOADX)                                       \
+            switch (op) {                                                 \
+            case 0: PLAN_PRED(XT, LOADX, x == lo) break;                  \
+            case 1: PLAN_PRED(XT, LOADX, x != lo) break;                  \
+            case 2: PLAN_PRED(XT, LOADX, x > lo) break;                   \
+            case 3: PLAN_PRED(XT, LOADX, x >= lo) break;                  \
+            case 4: PLAN_PRED(XT, LOADX, x < lo) break;                   \
+            case 5: PLAN_PRED(XT, LOADX, x <= lo) break;                  \
+            default: PLAN_PRED(XT, LOADX, x >= lo && x <= hi) break;      /* BETWEEN, inclusive (operator_between.go:138-199) */ \
+            }
             if (X.pred_int[q]) {
                 const long long lo = X.ilo[q], hi = X.ihi[q];
-#pragma unroll
-                for (int j = 0; j < R; j++) {
-                    const long long x = (long long)my[(c * R + j) * kThreads];
-                    const bool t = op == 0 ? x == lo : op == 1 ? x != lo : op == 2 ? x > lo : op == 3 ? x >= lo : op == 4 ? x < lo : op == 5 ? x <= lo : (x >= lo && x <= hi);
-                    ok[j] = ok[j] && t && !((nb[j] >> c) & 1u);
-                }
+                PLAN_PRED_SWITCH(long long, (long long)PLAN_SLOT(c, j))
             } else {
-                const double lo = pr.lo, hi = pr.hi;
-                const bool ci = X.is_int[c] != 0, cu = P.col_type[c] == MO_T_UINT64;
-#pragma unroll
-                for (int j = 0; j < R; j++) {
-                    const double x = slot_f64(my[(c * R + j) * kThreads], ci, cu);
-                    const bool t = op == 0 ? x == lo : op == 1 ? x != lo : op == 2 ? x > lo : op == 3 ? x >= lo : op == 4 ? x < lo : op == 5 ? x <= lo : (x >= lo && x <= hi);
-                    ok[j] = ok[j] && t && !((nb[j] >> c) & 1u);
-                }
+                const double lo = P.pred[q].lo, hi = P.pred[q].hi;
+                PLAN_PRED_SWITCH(double, __longlong_as_double((long long)PLAN_SLOT(c, j)))
             }
         }
         if (!(ok[0] | ok[1] | ok[2] | ok[3])) continue;
-        // ---- projection: SSA program, one rounding per node (the reference evaluates one expression node at a time too)
+        // ---- projection: SSA program over float64 slots, one rounding per node (the reference evaluates one expression node at a time too)
         for (int i = 0; i < P.ninstr; i++) {
-            const mo_plan_instr_t &in = P.instr[i];
-            const int dst = P.ncols + i, op = in.op, sa = in.a, sb = in.b;
-            const bool ai = op != MO_PLAN_OP_CONST && sa < P.ncols && X.is_int[sa], au = ai && P.col_type[sa] == MO_T_UINT64;
-            const bool bi = op >= MO_PLAN_OP_ADD && sb < P.ncols && X.is_int[sb], bu = bi && P.col_type[sb] == MO_T_UINT64;
-#pragma unroll
-            for (int j = 0; j < R; j++) {
-                double v; bool isnull = false;
-                if (op == MO_PLAN_OP_CONST) v = in.imm;
-                else {
-                    const double a = slot_f64(my[(sa * R + j) * kThreads], ai, au);
-                    isnull = (nb[j] >> sa) & 1u;
-                    if (op == MO_PLAN_OP_COL) v = a;
-                    else {
-                        const double b = slot_f64(my[(sb * R + j) * kThreads], bi, bu);
-                        isnull = isnull || ((nb[j] >> sb) & 1u);
-                        if (op == MO_PLAN_OP_ADD) v = __dadd_rn(a, b);
-                        else if (op == MO_PLAN_OP_SUB) v = __dsub_rn(a, b);
-                        else if (op == MO_PLAN_OP_MUL) v = __dmul_rn(a, b);
-                        else if (b == 0.0) { isnull = true; v = 0.0; }     // x / 0 -> NULL (SELECT behaviour)
-                        else v = __ddiv_rn(a, b);
-                    }
-                }
-                my[(dst * R + j) * kThreads] = (unsigned long long)__double_as_longlong(v);
-                if (isnull) nb[j] |= 1u << dst;
+            const int dst = P.ncols + i, op = P.instr[i].op, sa = P.instr[i].a, sb = P.instr[i].b;
+#define PLAN_A __longlong_as_double((long long)PLAN_SLOT(sa, j))
+#define PLAN_B __longlong_as_double((long long)PLAN_SLOT(sb, j))
+#define PLAN_BIN(EXPR) PLAN_FORJ { const double a = PLAN_A, b = PLAN_B; PLAN_SLOT(dst, j) = (unsigned long long)__double_as_longlong(EXPR); \
+                                   nb[j] |= (((nb[j] >> sa) | (nb[j] >> sb)) & 1u) << dst; }
+            switch (op) {
+            case MO_PLAN_OP_CONST: { const unsigned long long imm = (unsigned long long)__double_as_longlong(P.instr[i].imm); PLAN_FORJ PLAN_SLOT(dst, j) = imm; } break;
+            case MO_PLAN_OP_COL: PLAN_FORJ { PLAN_SLOT(dst, j) = PLAN_SLOT(sa, j); nb[j] |= ((nb[j] >> sa) & 1u) << dst; } break;
+            case MO_PLAN_OP_ADD: PLAN_BIN(__dadd_rn(a, b)) break;
+            case MO_PLAN_OP_SUB: PLAN_BIN(__dsub_rn(a, b)) break;
+            case MO_PLAN_OP_MUL: PLAN_BIN(__dmul_rn(a, b)) break;
+            default:             // x / 0 -> NULL (SELECT behaviour)
+                PLAN_FORJ { const double a = PLAN_A, b = PLAN_B; const bool z = b == 0.0;
+                            PLAN_SLOT(dst, j) = (unsigned long long)__double_as_longlong(z ? 0.0 : __ddiv_rn(a, b));
+                            nb[j] |= ((((nb[j] >> sa) | (nb[j] >> sb)) & 1u) | (z ? 1u : 0u)) << dst; }
+                break;
             }
         }
-        // ---- group: key + private-dictionary lookup per row (the dictionary state is sequential) ...
-        int ps[R];
+        // ---- group keys (fillKeys): one column at a time
         uint64_t keys[R];
-#pragma unroll
-        for (int j = 0; j < R; j++) {
-            ps[j] = -1; keys[j] = 0;
-            if (!ok[j]) continue;
-            const unsigned nullbits = nb[j];
-            // group key (fillKeys; has_null mode: marker byte per column, a NULL contributes the marker only) from the raw integer slots
-            uint64_t key = 0;
-            {
-                int off = 0;
-                for (int k = 0; k < P.nkeys; k++) {
-                    const int c = P.key_col[k];
-                    const int sz = X.sz[c];
-                    const bool isnull = (nullbits >> c) & 1u;
-                    if (P.has_null_keys) { if (isnull) { key |= 1ull << (8 * off); off += 1; continue; } off += 1; }
-                    uint64_t raw = my[(c * R + j) * kThreads];
-                    if (!X.is_int[c]) {   // float keys group by their stored bit pattern
-                        if (sz == 4) raw = (uint64_t)__float_as_uint((float)__longlong_as_double((long long)raw));
+        PLAN_FORJ keys[j] = 0;
+        if (!P.has_null_keys) {
+            for (int k = 0; k < P.nkeys; k++) {
+                const int c = P.key_col[k], mode = X.key_mode[k], sh = X.key_shift[k];
+                const uint64_t mask = X.sz[c] < 8 ? (1ull << (8 * X.sz[c])) - 1ull : ~0ull;
+                PLAN_FORJ if (ok[j]) keys[j] |= (plan_key_bits(mode, PLAN_SLOT(c, j), C.data[c], r0 + (uint64_t)j * kThreads) & mask) << sh;
+            }
+        } else {   // has_null mode: a marker byte per column, a NULL contributes the marker only -> the byte offset depends on the row
+            PLAN_FORJ {
+                if (ok[j]) {
+                    int off = 0; uint64_t key = 0;
+                    for (int k = 0; k < P.nkeys; k++) {
+                        const int c = P.key_col[k], sz = X.sz[c];
+                        if ((nb[j] >> c) & 1u) { key |= 1ull << (8 * off); off += 1; continue; }
+                        off += 1;
+                        uint64_t raw = plan_key_bits(X.key_mode[k], PLAN_SLOT(c, j), C.data[c], r0 + (uint64_t)j * kThreads);
+                        if (sz < 8) raw &= (1ull << (8 * sz)) - 1ull;
+                        if (off < 8) key |= raw << (8 * off);
+                        off += sz;
                     }
-                    if (sz < 8) raw &= (1ull << (8 * sz)) - 1ull;
-                    if (off < 8) key |= raw << (8 * off);
-                    off += sz;
+                    keys[j] = key;
                 }
-            }
-            keys[j] = key;
-            int p = -1;
-#pragma unroll
-            for (int g = 0; g < kPriv; g++) if (dk[g] == key) p = g;
-            if (p < 0 && !dict_full && key != kEmptyKey) {
-                bool okc = false;
-#pragma unroll
-                for (int g = 0; g < kPriv; g++) {
-                    const unsigned long long prev = okc ? key : atomicCAS(&pdict[g], (unsigned long long)kEmptyKey, (unsigned long long)key);
-                    okc = okc || prev == kEmptyKey || prev == key;
-                }
-                bool full = true;
-#pragma unroll
-                for (int g = 0; g < kPriv; g++) { dk[g] = ((volatile unsigned long long *)pdict)[g]; full = full && dk[g] != kEmptyKey; if (dk[g] == key) p = g; }
-                dict_full = full;
-            }
-            ps[j] = p;
-            if (p >= 0) {
-                prows[p * kThreads] += 1u;
-                if (pfirst[p * kThreads] == ~0ull) pfirst[p * kThreads] = (uint64_t)P.row_base + base + (uint64_t)j * kThreads + threadIdx.x;   // a thread meets its rows in increasing order
             }
         }
-        // ---- ... then the aggregates COLUMN AT A TIME over the thread's rows that live in private state: one decode per aggregate per tile
+        // ---- private-dictionary lookup per row (the dictionary state is sequential)
+        int ps[R];
+        PLAN_FORJ {
+            ps[j] = -1;
+            if (ok[j]) {
+                const uint64_t key = keys[j];
+                int p = -1;
+#pragma unroll
+                for (int g = 0; g < kPriv; g++) if (dk[g] == key) p = g;
+                if (p < 0 && !dict_full && key != kEmptyKey) {
+                    bool okc = false;
+#pragma unroll
+                    for (int g = 0; g < kPriv; g++) {
+                        const unsigned long long prev = okc ? key : atomicCAS(&pdict[g], (unsigned long long)kEmptyKey, (unsigned long long)key);
+                        okc = okc || prev == kEmptyKey || prev == key;
+                    }
+                    bool full = true;
+#pragma unroll
+                    for (int g = 0; g < kPriv; g++) { dk[g] = ((volatile unsigned long long *)pdict)[g]; full = full && dk[g] != kEmptyKey; if (dk[g] == key) p = g; }
+                    dict_full = full;
+                }
+                ps[j] = p;
+                if (p >= 0) {
+                    prows[p * kThreads] += 1u;
+                    if (pfirst[p * kThreads] == ~0ull) pfirst[p * kThreads] = (uint64_t)P.row_base + r0 + (uint64_t)j * kThreads;   // a thread meets its rows in increasing order
+                }
+            }
+        }
+        // ---- the aggregates, COLUMN AT A TIME over the thread's rows that live in private state
         for (int a = 0; a < naggs; a++) {
             const int vs = P.agg[a].value, kind = P.agg[a].kind;
-            const bool vi = vs >= 0 && vs < P.ncols && X.is_int[vs], vu = vi && P.col_type[vs] == MO_T_UINT64;
-#pragma unroll
-            for (int j = 0; j < R; j++) {
-                if (ps[j] < 0) continue;
-                if (vs >= 0 && ((nb[j] >> vs) & 1u)) continue;
-                const int ix = (ps[j] * naggs + a) * kThreads;
-                if (X.need_cnt) pcnt[ix] += 1u;
-                if (vs < 0) continue;
-                const double v = slot_f64(my[(vs * R + j) * kThreads], vi, vu);
-                if (kind == MO_AGG_SUM || kind == MO_AGG_AVG) pacc[ix] = __dadd_rn(pacc[ix], v);
-                else if (kind != MO_AGG_COUNT && v == v) {
-                    const unsigned long long kv = flt_key(v), cur = (unsigned long long)__double_as_longlong(pacc[ix]);
-                    if (kind == MO_AGG_MIN ? kv < cur : kv > cur) pacc[ix] = __longlong_as_double((long long)kv);
+            const int ab = a * kThreads, gstride = naggs * kThreads;
+            if (vs < 0) { if (X.need_cnt) { PLAN_FORJ if (ps[j] >= 0) pcnt[ps[j] * gstride + ab] += 1u; } continue; }          // COUNT(*)
+            if (X.need_cnt) { PLAN_FORJ if (ps[j] >= 0 && !((nb[j] >> vs) & 1u)) pcnt[ps[j] * gstride + ab] += 1u; }
+            if (kind == MO_AGG_SUM || kind == MO_AGG_AVG) {
+                PLAN_FORJ if (ps[j] >= 0 && !((nb[j] >> vs) & 1u)) { const int ix = ps[j] * gstride + ab; pacc[ix] = __dadd_rn(pacc[ix], __longlong_as_double((long long)PLAN_SLOT(vs, j))); }
+            } else if (kind == MO_AGG_MIN) {
+                PLAN_FORJ if (ps[j] >= 0 && !((nb[j] >> vs) & 1u)) {
+                    const double v = __longlong_as_double((long long)PLAN_SLOT(vs, j)); const int ix = ps[j] * gstride + ab;
+                    if (v == v) { const unsigned long long kv = flt_key(v); if (kv < (unsigned long long)__double_as_longlong(pacc[ix])) pacc[ix] = __longlong_as_double((long long)kv); }
+                }
+            } else if (kind == MO_AGG_MAX) {
+                PLAN_FORJ if (ps[j] >= 0 && !((nb[j] >> vs) & 1u)) {
+                    const double v = __longlong_as_double((long long)PLAN_SLOT(vs, j)); const int ix = ps[j] * gstride + ab;
+                    if (v == v) { const unsigned long long kv = flt_key(v); if (kv > (unsigned long long)__double_as_longlong(pacc[ix])) pacc[ix] = __longlong_as_double((long long)kv); }
                 }
             }
         }
         // ---- rows whose key is not in the private dictionary: shared CTA table, then the global table
-#pragma unroll
-        for (int j = 0; j < R; j++) {
-            if (!ok[j] || ps[j] >= 0) continue;
-            const uint64_t r = base + (uint64_t)j * kThreads + threadIdx.x;
-            const unsigned nullbits = nb[j];
-            const uint64_t key = keys[j];
-            const uint64_t grow = (uint64_t)P.row_base + r;
-            // shared CTA table, then the global table
-            int slot = -1;
-            if (key != kEmptyKey) {
-                unsigned s = (unsigned)mix64(key) & (kCtaSlots - 1);
-                for (int probes = 0; probes < kCtaSlots; probes++) {
-                    uint64_t cur = tkey[s];
-                    if (cur == key) { slot = (int)s; break; }
-                    if (cur == kEmptyKey) {
-                        cur = atomicCAS((unsigned long long *)&tkey[s], (unsigned long long)kEmptyKey, (unsigned long long)key);
-                        if (cur == kEmptyKey || cur == key) { slot = (int)s; break; }
+        PLAN_FORJ {
+            if (ok[j] && ps[j] < 0) {
+                const unsigned nullbits = nb[j];
+                const uint64_t key = keys[j];
+                const uint64_t grow = (uint64_t)P.row_base + r0 + (uint64_t)j * kThreads;
+                int slot = -1;
+                if (key != kEmptyKey) {
+                    unsigned s = (unsigned)mix64(key) & (kCtaSlots - 1);
+                    for (int probes = 0; probes < kCtaSlots; probes++) {
+                        uint64_t cur = tkey[s];
+                        if (cur == key) { slot = (int)s; break; }
+                        if (cur == kEmptyKey) {
+                            cur = atomicCAS((unsigned long long *)&tkey[s], (unsigned long long)kEmptyKey, (unsigned long long)key);
+                            if (cur == kEmptyKey || cur == key) { slot = (int)s; break; }
+                        }
+                        s = (s + 1) & (kCtaSlots - 1);
                     }
-                    s = (s + 1) & (kCtaSlots - 1);
                 }
-            }
-            unsigned long long *first_p = slot >= 0 ? &tfirst[slot] : nullptr, *rows_p = slot >= 0 ? &trows[slot] : nullptr;
-            double *acc_p = slot >= 0 ? &tacc[slot * naggs] : nullptr; unsigned long long *cnt_p = slot >= 0 ? &tcnt[slot * naggs] : nullptr;
-            if (slot < 0) {
-                const uint64_t gs = global_find(G, key);
-                if (gs == ~0ull) continue;
-                first_p = &G.first_row[gs]; rows_p = &G.rows[gs]; acc_p = &G.acc[gs * naggs]; cnt_p = &G.cnt[gs * naggs];
-            }
-            if (*((volatile unsigned long long *)first_p) > grow) atomicMin(first_p, (unsigned long long)grow);
-            atomicAdd(rows_p, 1ull);
-            for (int a = 0; a < naggs; a++) {
-                const int vs = P.agg[a].value;
-                if (vs < 0) { atomicAdd(&cnt_p[a], 1ull); continue; }            // COUNT(*)
-                if ((nullbits >> vs) & 1u) continue;                             // aggregates skip NULLs
-                agg_apply(P.agg[a].kind, &acc_p[a], slot_f64(my[(vs * R + j) * kThreads], vs < P.ncols && X.is_int[vs], vs < P.ncols && P.col_type[vs] == MO_T_UINT64));
-                atomicAdd(&cnt_p[a], 1ull);
+                unsigned long long *first_p = slot >= 0 ? &tfirst[slot] : nullptr, *rows_p = slot >= 0 ? &trows[slot] : nullptr;
+                double *acc_p = slot >= 0 ? &tacc[slot * naggs] : nullptr; unsigned long long *cnt_p = slot >= 0 ? &tcnt[slot * naggs] : nullptr;
+                bool have = true;
+                if (slot < 0) {
+                    const uint64_t gs = global_find(G, key);
+                    if (gs == ~0ull) have = false;
+                    else { first_p = &G.first_row[gs]; rows_p = &G.rows[gs]; acc_p = &G.acc[gs * naggs]; cnt_p = &G.cnt[gs * naggs]; }
+                }
+                if (have) {
+                    if (*((volatile unsigned long long *)first_p) > grow) atomicMin(first_p, (unsigned long long)grow);
+                    atomicAdd(rows_p, 1ull);
+                    for (int a = 0; a < naggs; a++) {
+                        const int vs = P.agg[a].value;
+                        if (vs < 0) { atomicAdd(&cnt_p[a], 1ull); continue; }            // COUNT(*)
+                        if ((nullbits >> vs) & 1u) continue;                             // aggregates skip NULLs
+                        agg_apply(P.agg[a].kind, &acc_p[a], __longlong_as_double((long long)PLAN_SLOT(vs, j)));
+                        atomicAdd(&cnt_p[a], 1ull);
+                    }
+                }
             }
         }
     }
-    // ---- retire: every thread folds its private states into the global table (at most kPriv x naggs atomics per thread, once)
+    // ---- retire: the CTA first folds its threads' private states (one thread per (group, aggregate), a fixed order), then touches the global
+    // table once per (group, aggregate) instead of once per thread
     __syncthreads();
-    for (int g = 0; g < kPriv; g++) {
+    for (int ga = threadIdx.x; ga < kPriv * naggs; ga += kThreads) {
+        const int g = ga / naggs, a = ga % naggs, kind = P.agg[a].kind;
         const unsigned long long pk = pdict[g];
-        if (pk == kEmptyKey || prows[g * kThreads] == 0u) continue;
+        if (pk == kEmptyKey) continue;
+        double acc = agg_identity(kind); unsigned long long cnt = 0;
+        for (int t = 0; t < kThreads; t++) {
+            const int ix = ga * kThreads + t;
+            const unsigned long long c = X.need_cnt ? pcnt0[ix] : prows0[g * kThreads + t];   // without per-aggregate counts every row of the group fed every aggregate
+            if (c == 0) continue;
+            cnt += c;
+            const double v = pacc0[ix];
+            if (kind == MO_AGG_SUM || kind == MO_AGG_AVG) acc = __dadd_rn(acc, v);
+            else if (kind == MO_AGG_MIN) { if ((unsigned long long)__double_as_longlong(v) < (unsigned long long)__double_as_longlong(acc)) acc = v; }
+            else if (kind == MO_AGG_MAX) { if ((unsigned long long)__double_as_longlong(v) > (unsigned long long)__double_as_longlong(acc)) acc = v; }
+        }
+        if (cnt == 0) continue;
         const uint64_t gs = global_find(G, pk);
         if (gs == ~0ull) continue;
-        atomicMin(&G.first_row[gs], pfirst[g * kThreads]);
-        atomicAdd(&G.rows[gs], (unsigned long long)prows[g * kThreads]);
-        for (int a = 0; a < naggs; a++) {
-            const int ix = (g * naggs + a) * kThreads;
-            // without per-aggregate counts (no nullable input): every row of the group fed every aggregate
-            const unsigned c = X.need_cnt ? pcnt[ix] : prows[g * kThreads];
-            if (c == 0u) continue;
-            agg_fold(P.agg[a].kind, &G.acc[gs * naggs + a], pacc[ix]);
-            atomicAdd(&G.cnt[gs * naggs + a], (unsigned long long)c);
-        }
+        agg_fold(kind, &G.acc[gs * naggs + a], acc);
+        atomicAdd(&G.cnt[gs * naggs + a], cnt);
+    }
+    for (int g = threadIdx.x; g < kPriv; g += kThreads) {
+        const unsigned long long pk = pdict[g];
+        if (pk == kEmptyKey) continue;
+        unsigned long long rows = 0, first = ~0ull;
+        for (int t = 0; t < kThreads; t++) { rows += prows0[g * kThreads + t]; const unsigned long long f = pfirst0[g * kThreads + t]; if (f < first) first = f; }
+        if (rows == 0) continue;
+        const uint64_t gs = global_find(G, pk);
+        if (gs == ~0ull) continue;
+        atomicMin(&G.first_row[gs], first);
+        atomicAdd(&G.rows[gs], rows);
     }
     // ---- and the shared CTA table
     for (int s = threadIdx.x; s < kCtaSlots; s += kThreads) {
@@ -642,18 +656,46 @@ int xcall_plan(mo_xcall_args_t *args, uint64_t len) {
     MOB_CUDA_TRY(cudaMemsetAsync(nused, 0, 16, t.stream));
     // the descriptor travels through the thread's pinned staging buffer (the caller's copy may be pageable and short-lived)
     if (sizeof(mo_plan_t) + sizeof(PlanAux) > t.pinned_sz) { st.finish(); set_error("plan: descriptor larger than the staging buffer"); return MO_RC_INTERNAL_ERROR; }
-    // decode once on the host: which columns stay in the integer domain, which predicates compare there, whether per-aggregate counts are needed
+    // decode once on the host: the domain of every column slot (raw int64 or float64), which predicates compare as integers, how the group
+    // key reads its columns, whether per-aggregate counts are needed
     PlanAux X;
     memset(&X, 0, sizeof X);
-    for (int c = 0; c < P.ncols; c++) { X.is_int[c] = !(P.col_type[c] == MO_T_FLOAT32 || P.col_type[c] == MO_T_FLOAT64); X.sz[c] = tbytes(P.col_type[c]); }
-    for (int j = 0; j < P.npreds; j++) {
-        const mo_plan_pred_t &q = P.pred[j];
-        auto integral = [](double v) { return v == std::floor(v) && std::fabs(v) < 9007199254740992.0; };
-        const bool ok = X.is_int[q.col] && P.col_type[q.col] != MO_T_UINT64 && integral(q.lo) && (q.op != 6 || integral(q.hi));
-        X.pred_int[j] = ok;
-        if (ok) { X.ilo[j] = (long long)q.lo; X.ihi[j] = q.op == 6 ? (long long)q.hi : 0; }
-    }
     {
+        auto is_float = [](int T) { return T == MO_T_FLOAT32 || T == MO_T_FLOAT64; };
+        auto integral = [](double v) { return v == std::floor(v) && std::fabs(v) < 9007199254740992.0; };
+        bool value_use[MO_PLAN_MAX_COLS] = {false}, f64dom[MO_PLAN_MAX_COLS];
+        for (int i = 0; i < P.ninstr; i++) {
+            const mo_plan_instr_t &in = P.instr[i];
+            if (in.op == MO_PLAN_OP_CONST) continue;
+            if (in.a < P.ncols) value_use[in.a] = true;
+            if (in.op >= MO_PLAN_OP_ADD && in.b < P.ncols) value_use[in.b] = true;
+        }
+        for (int a = 0; a < P.naggs; a++) if (P.agg[a].value >= 0 && P.agg[a].value < P.ncols) value_use[P.agg[a].value] = true;
+        bool intable[MO_PLAN_MAX_PREDS];
+        for (int c = 0; c < P.ncols; c++) f64dom[c] = is_float(P.col_type[c]) || value_use[c];
+        for (int j = 0; j < P.npreds; j++) {
+            const mo_plan_pred_t &q = P.pred[j];
+            intable[j] = !is_float(P.col_type[q.col]) && P.col_type[q.col] != MO_T_UINT64 && integral(q.lo) && (q.op != 6 || integral(q.hi));
+            if (!intable[j]) f64dom[q.col] = true;
+        }
+        for (int j = 0; j < P.npreds; j++) {
+            const mo_plan_pred_t &q = P.pred[j];
+            X.pred_int[j] = intable[j] && !f64dom[q.col];
+            if (X.pred_int[j]) { X.ilo[j] = (long long)q.lo; X.ihi[j] = q.op == 6 ? (long long)q.hi : 0; }
+        }
+        for (int c = 0; c < P.ncols; c++) {
+            const int T = P.col_type[c];
+            X.sz[c] = tbytes(T);
+            X.ext[c] = T == MO_T_INT8 ? 1 : T == MO_T_INT16 ? 2 : (T == MO_T_INT32 || T == MO_T_DATE) ? 3 : 0;
+            X.tof[c] = T == MO_T_FLOAT32 ? 3 : T == MO_T_FLOAT64 ? 0 : !f64dom[c] ? 0 : T == MO_T_UINT64 ? 2 : 1;
+        }
+        int shift = 0;
+        for (int k = 0; k < P.nkeys; k++) {
+            const int c = P.key_col[k], T = P.col_type[c];
+            X.key_mode[k] = T == MO_T_FLOAT32 ? 3 : T == MO_T_FLOAT64 ? 4 : !f64dom[c] ? 0 : X.sz[c] < 8 ? 1 : 2;
+            X.key_shift[k] = shift < 64 ? shift : 63;
+            shift += 8 * X.sz[c];
+        }
         // an aggregate input can be NULL iff a nullable column or a division feeds it (null-ness only flows forward through the SSA program)
         bool maybe[MO_PLAN_MAX_COLS + MO_PLAN_MAX_INSTR];
         for (int c = 0; c < P.ncols; c++) maybe[c] = args[2 + c].pnulls != nullptr;
@@ -676,8 +718,8 @@ int xcall_plan(mo_xcall_args_t *args, uint64_t len) {
     static size_t attr_smem = 0;
     if (smem > attr_smem) { MOB_CUDA_TRY(cudaFuncSetAttribute(plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; }
     if (len) {
-        int ctas = (int)((220 * 1024) / (smem + 2048));
-        if (ctas > 8) ctas = 8; if (ctas < 1) ctas = 1;
+        int ctas = 1;   // exactly the resident CTAs: the rows are dealt statically over the grid, a partial second wave would double the time
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, plan_kernel, kThreads, smem) != cudaSuccess || ctas < 1) ctas = 1;
         int grid = num_sms() * ctas;
         const uint64_t work = (len + (uint64_t)kThreads * R - 1) / ((uint64_t)kThreads * R);
         if ((uint64_t)grid > work) grid = (int)work;

@@ -763,3 +763,19 @@ def kmeans_elkan(vectors, init_centroids, max_iter=500, rnd=None):
             Vector(data=np.ascontiguousarray(rnd, dtype=np.float32), length=len(rnd)) if rnd is not None and len(rnd) else Vector(length=0)]
     xcall(capi.XCALL_KMEANS_ELKAN_F32 if v.dtype == np.float32 else capi.XCALL_KMEANS_ELKAN_F64, vecs, n)
     return cent, assign, int(iters[0])
+
+
+# ---------------------------------------------------------------------------------------------- LZ4 block decode (csrc/lz4.cu)
+def lz4_decode_blocks(blocks, sizes):
+    """compress.Decompress over many column blocks in one call: blocks = list of compressed byte strings, sizes = their decoded sizes.
+    Returns the list of decoded byte strings."""
+    src = np.frombuffer(b"".join(blocks), dtype=np.uint8) if blocks else np.zeros(0, np.uint8)
+    n = len(blocks)
+    desc = np.zeros((n, 4), dtype=np.int64)
+    so = do = 0
+    for i, (b, s) in enumerate(zip(blocks, sizes)):
+        desc[i] = (so, len(b), do, s)
+        so += len(b); do += s
+    dst = np.zeros(max(do, 1), dtype=np.uint8)
+    xcall(capi.XCALL_LZ4_DECODE, [Vector(data=dst, length=do), Vector(data=src if src.size else np.zeros(1, np.uint8), length=so), Vector(data=desc.reshape(-1), length=4 * n)], n)
+    return [dst[desc[i, 2]:desc[i, 2] + desc[i, 3]].tobytes() for i in range(n)]

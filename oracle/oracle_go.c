@@ -1575,3 +1575,26 @@ int64_t og_join_probe(const uint64_t *vals, int64_t n, const int32_t *offsets, c
     }
 KMEANS_IMPL(float, f32, 3.40282346638528859811704183484516925440e+38f)
 KMEANS_IMPL(double, f64, 1.79769313486231570814527423731704356798070e+308)
+
+/* og_lz4_decode_block: LZ4 block format decoder (what compress.Decompress / lz4.UncompressBlock does, pkg/compress/compress.go:37-47), restated
+ * from the published block format.  Returns the decoded size or -1 (malformed / does not fit).  Test infrastructure. */
+int64_t og_lz4_decode_block(const uint8_t *src, int64_t sl, uint8_t *dst, int64_t dcap) {
+    int64_t ip = 0, op = 0;
+    while (ip < sl) {
+        unsigned token = src[ip++];
+        int64_t lit = token >> 4;
+        if (lit == 15) { unsigned e; do { if (ip >= sl) return -1; e = src[ip++]; lit += e; } while (e == 255); }
+        if (ip + lit > sl || op + lit > dcap) return -1;
+        memcpy(dst + op, src + ip, (size_t)lit); ip += lit; op += lit;
+        if (ip >= sl) break;
+        if (ip + 2 > sl) return -1;
+        int64_t offset = (int64_t)src[ip] | ((int64_t)src[ip + 1] << 8); ip += 2;
+        int64_t mlen = token & 15;
+        if (mlen == 15) { unsigned e; do { if (ip >= sl) return -1; e = src[ip++]; mlen += e; } while (e == 255); }
+        mlen += 4;
+        if (offset == 0 || offset > op || op + mlen > dcap) return -1;
+        for (int64_t i = 0; i < mlen; i++) dst[op + i] = dst[op - offset + i];   /* byte-serial: overlapping matches replicate */
+        op += mlen;
+    }
+    return op;
+}

@@ -49,6 +49,8 @@ def go():
             getattr(lib, "og_km_update_bounds_" + sfx).argtypes = [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]
             getattr(lib, "og_km_cluster_" + sfx).restype = _i64
             getattr(lib, "og_km_cluster_" + sfx).argtypes = [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp]
+        lib.og_lz4_decode_block.restype = _i64
+        lib.og_lz4_decode_block.argtypes = [_vp, _i64, _vp, _i64]
         lib.og_join_sels.restype = _i64
         lib.og_join_sels.argtypes = [_vp, _i64, _i64, _vp, _vp]
         lib.og_join_find.restype = None
