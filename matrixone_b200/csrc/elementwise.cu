@@ -75,7 +75,11 @@ __device__ __forceinline__ bool arith_apply(T a, T b, R &r, unsigned &st) {
     } else {
         // AR_INTDIV: (int64_t)(A / B), arith.c:515-521
         if (b == (T)0) { st |= ST_DIVZERO; return false; }
-        r = (R)(long long)(a / b);
+        // the reference C on x86-64 converts with cvttss2si / cvttsd2si, whose out-of-range / NaN result is the "integer indefinite" INT64_MIN;
+        // a plain CUDA cast would saturate instead
+        const T q = a / b;
+        const double qd = (double)q;
+        r = (qd >= -9223372036854775808.0 && qd < 9223372036854775808.0) ? (R)(long long)q : (R)(long long)INT64_MIN;
         return true;
     }
 }

@@ -799,7 +799,7 @@ thread_local int g_last_tc_fallbacks = -1;   // queries of the last tensor-core 
 struct TcOperand { __nv_bfloat16 *bf = nullptr; float *norm = nullptr; float *lonorm = nullptr; const float *enorm = nullptr; int kprime = 0; };   // enorm: what the epilogue adds (null = norm; zeros for inner product)   // norm = |x|^2, lonorm = |x - bf16(x)|^2 per row
 
 // datasets split once by MoB200_SearchPrepare (index load); looked up by (pointer, rows, dim)
-struct PreparedOperand { const float *x; int64_t n; int dim; int device; TcOperand op; const float *cent = nullptr; int64_t nlist = 0; int normalized = 0; };   // cent != nullptr: IVF residual operand; normalized: cosine
+struct PreparedOperand { const float *x; int64_t n; int dim; int device; TcOperand op; const float *cent = nullptr; int64_t nlist = 0; int normalized = 0; const int64_t *offsets = nullptr; };   // cent != nullptr: IVF residual operand; normalized: cosine
 static std::mutex g_prepared_mu;
 static std::vector<PreparedOperand> g_prepared;
 // A search holds this shared for its whole call (the kernels it launched have finished when it returns); whoever frees or rebuilds a
@@ -836,7 +836,7 @@ static int tc_prepare_ivf_entries(ThreadCtx &t, const float *x, int64_t n, int d
                                   int *dnonfinite, TcOperand &op) {
     {
         std::lock_guard<std::mutex> lk(g_prepared_mu);
-        for (const PreparedOperand &e : g_prepared) if (e.x == x && e.n == n && e.dim == dim && e.cent == dcent && e.nlist == nlist) { op = e.op; return MO_RC_SUCCESS; }
+        for (const PreparedOperand &e : g_prepared) if (e.x == x && e.n == n && e.dim == dim && e.cent == dcent && e.nlist == nlist && e.offsets == doffsets) { op = e.op; return MO_RC_SUCCESS; }
     }
     struct Cached { const float *x = nullptr, *c = nullptr; int64_t n = 0; int dim = 0; uint64_t epoch = ~0ull; const ThreadCtx *t = nullptr; TcOperand op; };
     static thread_local Cached c;
@@ -1155,7 +1155,8 @@ void search_invalidate(const void *p, uint64_t bytes) {
         for (const PreparedOperand &e : g_prepared) {
             const char *xl = (const char *)e.x, *xh = xl + (size_t)e.n * e.dim * 4;
             const char *cl = (const char *)e.cent, *ch = e.cent ? cl + (size_t)e.nlist * e.dim * 4 : cl;
-            if ((lo0 < xh && xl < hi0) || (e.cent && lo0 < ch && cl < hi0)) hit = true;
+            const char *ol = (const char *)e.offsets, *oh = e.offsets ? ol + (size_t)(e.nlist + 1) * 8 : ol;   // the residual operand depends on the list boundaries too
+            if ((lo0 < xh && xl < hi0) || (e.cent && lo0 < ch && cl < hi0) || (e.offsets && lo0 < oh && ol < hi0)) hit = true;
         }
         if (!hit) return;
     }
@@ -1166,7 +1167,8 @@ void search_invalidate(const void *p, uint64_t bytes) {
         const PreparedOperand &e = g_prepared[i];
         const char *xl = (const char *)e.x, *xh = xl + (size_t)e.n * e.dim * 4;
         const char *cl = (const char *)e.cent, *ch = e.cent ? cl + (size_t)e.nlist * e.dim * 4 : cl;
-        if ((lo < xh && xl < hi) || (e.cent && lo < ch && cl < hi)) {
+        const char *ol = (const char *)e.offsets, *oh = e.offsets ? ol + (size_t)(e.nlist + 1) * 8 : ol;
+        if ((lo < xh && xl < hi) || (e.cent && lo < ch && cl < hi) || (e.offsets && lo < oh && ol < hi)) {
             cudaFree(e.op.bf); cudaFree(e.op.norm);
             g_prepared.erase(g_prepared.begin() + (long)i);
         } else i++;
@@ -1324,7 +1326,7 @@ int32_t MoB200_SearchPrepareIvf(const void *data, uint64_t n, int64_t dim, const
     if (!data || n == 0 || dim < 16 || n >= (1ull << 31) - BN || nlist == 0) return MO_RC_SUCCESS;
     if (!is_device_ptr(data) || !is_device_ptr(centroids) || !is_device_ptr(offsets)) { set_error("SearchPrepareIvf: entries, centroids and offsets must be device memory"); return MO_RC_INVALID_ARGUMENT; }
     release_same_kind(data, true, 0);
-    PreparedOperand e; e.x = (const float *)data; e.n = (int64_t)n; e.dim = (int)dim; e.device = 0; e.cent = (const float *)centroids; e.nlist = (int64_t)nlist;
+    PreparedOperand e; e.x = (const float *)data; e.n = (int64_t)n; e.dim = (int)dim; e.device = 0; e.cent = (const float *)centroids; e.nlist = (int64_t)nlist; e.offsets = (const int64_t *)offsets;
     e.op.kprime = ((3 * (int)dim + BK - 1) / BK) * BK;
     MOB_CUDA_TRY(cudaMalloc((void **)&e.op.bf, (size_t)n * e.op.kprime * 2 + 1024));
     if (cudaMalloc((void **)&e.op.norm, (size_t)n * 8) != cudaSuccess) { cudaFree(e.op.bf); set_error("SearchPrepareIvf: out of device memory"); return MO_RC_INTERNAL_ERROR; }

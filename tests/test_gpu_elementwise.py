@@ -92,6 +92,11 @@ def test_float_arith_vs_reference_c(gpu, n):
         r1 = np.zeros(n, dtype=np.int64); r2 = np.zeros(n, dtype=np.int64)
         assert ref.Float_VecIntegerDiv(O.p(r1), O.p(a), O.p(bb), n, None, 0, szof) == gpu.Float_VecIntegerDiv(O.p(r2), O.p(a), O.p(bb), n, None, 0, szof) == 0
         assert (r1 == r2).all()
+        # quotients outside int64 / NaN: the reference's cvttsd2si yields INT64_MIN ("integer indefinite"), not a saturated value
+        big = np.array([1e30, -1e30, np.inf, -np.inf, np.nan, 9.3e18, -9.3e18, 5.0], dtype=dt); one = np.array([1e-3, 1e-3, 1, 1, 1, 1, 1, 2], dtype=dt)
+        q1 = np.zeros(8, dtype=np.int64); q2 = np.zeros(8, dtype=np.int64)
+        assert ref.Float_VecIntegerDiv(O.p(q1), O.p(big), O.p(one), 8, None, 0, szof) == gpu.Float_VecIntegerDiv(O.p(q2), O.p(big), O.p(one), 8, None, 0, szof) == 0
+        assert (q1 == q2).all(), (q1, q2)
         # division: bit-exact against the IEEE restatement of the Go "/" operator (null on zero divisor)
         rn = np.zeros((n + 63) // 64, dtype=np.uint64); rg = np.full(n, 7, dtype=dt); r2 = np.full(n, 7, dtype=dt)
         lib.og_arith(3, 30 if szof == 4 else 31, O.p(rg), O.p(a), O.p(b), n, 0, 0, None, None, O.p(rn), 1, None)
