@@ -21,9 +21,36 @@ namespace {
 
 constexpr int kWarpsPerCta = 4;
 
+// The token stream is read through a per-warp shared-memory WINDOW of the compressed block (kWin bytes, refilled cooperatively with 16-byte loads
+// when the cursor runs past it): a sequence costs a handful of dependent byte reads (token, length extensions, offset), and from global memory each
+// of them is a full memory latency (measured: 14 MB/s per warp, 27 GB/s for 2000 blocks); from shared memory they are ~30 cycles.
+constexpr int kWin = 1024;
+
+struct SrcWin {
+    const uint8_t *src; int64_t sl; unsigned char *buf; int64_t base;   // buf holds src[base .. base + kWin) (base is 16-byte aligned in ABSOLUTE address terms)
+    __device__ __forceinline__ void fill(int64_t ip, unsigned lane) {
+        const uintptr_t a0 = (uintptr_t)(src + ip) & ~(uintptr_t)15;
+        base = (int64_t)(a0 - (uintptr_t)src);                            // may be slightly negative for the first window of an unaligned block
+        __syncwarp();
+        for (int i = lane * 16; i < kWin; i += 32 * 16) {
+            const int64_t o = base + i;
+            int4 v = make_int4(0, 0, 0, 0);
+            if (o >= 0 && o + 16 <= sl) v = *reinterpret_cast<const int4 *>(src + o);
+            else { unsigned char t[16]; for (int k = 0; k < 16; k++) t[k] = (o + k >= 0 && o + k < sl) ? src[o + k] : 0; memcpy(&v, t, 16); }
+            *reinterpret_cast<int4 *>(buf + i) = v;
+        }
+        __syncwarp();
+    }
+    __device__ __forceinline__ unsigned byte(int64_t ip, unsigned lane) {   // src[ip], ip < sl
+        if (ip - base >= kWin) fill(ip, lane);
+        return buf[ip - base];
+    }
+};
+
 __global__ void __launch_bounds__(32 * kWarpsPerCta)
 lz4_decode_kernel(uint8_t *__restrict__ dst_base, uint64_t dst_cap, const uint8_t *__restrict__ src_base, uint64_t src_cap, const int64_t *__restrict__ desc, uint64_t nblocks,
                   unsigned long long *first_bad) {
+    __shared__ __align__(16) unsigned char win[kWarpsPerCta][kWin];
     const unsigned lane = threadIdx.x & 31;
     const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t b = warp; b < nblocks; b += nwarps) {
@@ -32,21 +59,27 @@ lz4_decode_kernel(uint8_t *__restrict__ dst_base, uint64_t dst_cap, const uint8_
         if (!bad) {
             const uint8_t *src = src_base + so;
             volatile uint8_t *dst = dst_base + dof;
+            SrcWin W{src, sl, win[threadIdx.x >> 5], 0};
             int64_t ip = 0, op = 0;
             if (sl == 0) bad = dl != 0;
+            else W.fill(0, lane);
             while (!bad && ip < sl) {
-                const unsigned token = src[ip++];
+                const unsigned token = W.byte(ip++, lane);
                 int64_t lit = token >> 4;
-                if (lit == 15) { unsigned e; do { if (ip >= sl) { bad = true; break; } e = src[ip++]; lit += e; } while (e == 255); }
+                if (lit == 15) { unsigned e; do { if (ip >= sl) { bad = true; break; } e = W.byte(ip++, lane); lit += e; } while (e == 255); }
                 if (bad || ip + lit > sl || op + lit > dl) { bad = true; break; }
-                for (int64_t i = lane; i < lit; i += 32) dst[op + i] = src[ip + i];
+                if (lit) {
+                    if (ip + lit - W.base > kWin && lit <= kWin - 16) W.fill(ip, lane);           // bring the whole literal run into the window when it fits
+                    if (ip + lit - W.base <= kWin) { for (int64_t i = lane; i < lit; i += 32) dst[op + i] = W.buf[ip - W.base + i]; }
+                    else { for (int64_t i = lane; i < lit; i += 32) dst[op + i] = src[ip + i]; }   // a long run (incompressible data): straight from global memory
+                }
                 ip += lit; op += lit;
                 if (ip >= sl) break;                                   // the last sequence: literals only
                 if (ip + 2 > sl) { bad = true; break; }
-                const int64_t offset = (int64_t)src[ip] | ((int64_t)src[ip + 1] << 8);
+                const int64_t offset = (int64_t)W.byte(ip, lane) | ((int64_t)W.byte(ip + 1, lane) << 8);
                 ip += 2;
                 int64_t mlen = token & 15;
-                if (mlen == 15) { unsigned e; do { if (ip >= sl) { bad = true; break; } e = src[ip++]; mlen += e; } while (e == 255); }
+                if (mlen == 15) { unsigned e; do { if (ip >= sl) { bad = true; break; } e = W.byte(ip++, lane); mlen += e; } while (e == 255); }
                 mlen += 4;
                 if (bad || offset == 0 || offset > op || op + mlen > dl) { bad = true; break; }
                 __syncwarp();                                          // the bytes this match reads were written by other lanes
