@@ -47,10 +47,19 @@ struct SrcWin {
     }
 };
 
+// The OUTPUT goes through shared memory too: a match reads bytes the warp wrote a moment ago, and from global memory that is an L2 round trip per
+// sequence (the measured bound once the token stream was in shared memory: ~0.6 us per sequence per warp).  Every output byte is written to the
+// block in global memory AND to a per-warp ring of the last kRing bytes; matches whose source lies inside the ring (offset <= kRing: the common
+// case, LZ4 favours near matches) are served from it, farther ones from global memory.
+constexpr int kRing = 16384;
+constexpr size_t kLz4Smem = (size_t)kWarpsPerCta * (kWin + kRing);
+
 __global__ void __launch_bounds__(32 * kWarpsPerCta)
 lz4_decode_kernel(uint8_t *__restrict__ dst_base, uint64_t dst_cap, const uint8_t *__restrict__ src_base, uint64_t src_cap, const int64_t *__restrict__ desc, uint64_t nblocks,
                   unsigned long long *first_bad) {
-    __shared__ __align__(16) unsigned char win[kWarpsPerCta][kWin];
+    extern __shared__ __align__(16) unsigned char lz4_smem[];
+    unsigned char (*win)[kWin] = reinterpret_cast<unsigned char (*)[kWin]>(lz4_smem);
+    unsigned char *ring = lz4_smem + (size_t)kWarpsPerCta * kWin + (size_t)(threadIdx.x >> 5) * kRing;
     const unsigned lane = threadIdx.x & 31;
     const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t b = warp; b < nblocks; b += nwarps) {
@@ -70,8 +79,8 @@ lz4_decode_kernel(uint8_t *__restrict__ dst_base, uint64_t dst_cap, const uint8_
                 if (bad || ip + lit > sl || op + lit > dl) { bad = true; break; }
                 if (lit) {
                     if (ip + lit - W.base > kWin && lit <= kWin - 16) W.fill(ip, lane);           // bring the whole literal run into the window when it fits
-                    if (ip + lit - W.base <= kWin) { for (int64_t i = lane; i < lit; i += 32) dst[op + i] = W.buf[ip - W.base + i]; }
-                    else { for (int64_t i = lane; i < lit; i += 32) dst[op + i] = src[ip + i]; }   // a long run (incompressible data): straight from global memory
+                    if (ip + lit - W.base <= kWin) { for (int64_t i = lane; i < lit; i += 32) { const unsigned char v = W.buf[ip - W.base + i]; dst[op + i] = v; ring[(op + i) & (kRing - 1)] = v; } }
+                    else { for (int64_t i = lane; i < lit; i += 32) { const unsigned char v = src[ip + i]; dst[op + i] = v; ring[(op + i) & (kRing - 1)] = v; } }   // a long run (incompressible data): straight from global memory
                 }
                 ip += lit; op += lit;
                 if (ip >= sl) break;                                   // the last sequence: literals only
@@ -84,8 +93,15 @@ lz4_decode_kernel(uint8_t *__restrict__ dst_base, uint64_t dst_cap, const uint8_
                 if (bad || offset == 0 || offset > op || op + mlen > dl) { bad = true; break; }
                 __syncwarp();                                          // the bytes this match reads were written by other lanes
                 const int64_t from = op - offset;
-                if (offset >= mlen) { for (int64_t i = lane; i < mlen; i += 32) dst[op + i] = dst[from + i]; }
-                else { for (int64_t i = lane; i < mlen; i += 32) dst[op + i] = dst[from + (i % offset)]; }   // overlapping: periodic with period `offset`
+                // (an overlapping match, offset < length, is periodic with period `offset`: byte i is byte i mod offset of the last `offset` output bytes)
+                if (offset <= kRing && mlen <= kRing - offset) {
+                    // source [from, op) and destination [op, op + mlen) occupy disjoint ring slots (offset + mlen <= kRing): no ordering needed inside the copy
+                    if (offset >= mlen) { for (int64_t i = lane; i < mlen; i += 32) { const unsigned char v = ring[(from + i) & (kRing - 1)]; dst[op + i] = v; ring[(op + i) & (kRing - 1)] = v; } }
+                    else { for (int64_t i = lane; i < mlen; i += 32) { const unsigned char v = ring[(from + (i % offset)) & (kRing - 1)]; dst[op + i] = v; ring[(op + i) & (kRing - 1)] = v; } }
+                } else {   // a far or very long match: its source is (or would get) evicted from the ring -> read the block in global memory
+                    if (offset >= mlen) { for (int64_t i = lane; i < mlen; i += 32) { const unsigned char v = dst[from + i]; dst[op + i] = v; ring[(op + i) & (kRing - 1)] = v; } }
+                    else { for (int64_t i = lane; i < mlen; i += 32) { const unsigned char v = dst[from + (i % offset)]; dst[op + i] = v; ring[(op + i) & (kRing - 1)] = v; } }
+                }
                 op += mlen;
                 __syncwarp();
             }
@@ -114,7 +130,9 @@ int xcall_lz4_decode(mo_xcall_args_t *args, uint64_t len) {
     uint64_t ctas = (len + kWarpsPerCta - 1) / kWarpsPerCta;
     if (ctas > (uint64_t)num_sms() * 16) ctas = (uint64_t)num_sms() * 16;
     cudaEventRecord(t.kev0, t.stream);
-    lz4_decode_kernel<<<(unsigned)ctas, 32 * kWarpsPerCta, 0, t.stream>>>(dst, args[0].dataSz, src, args[1].dataSz, desc, len, dbad);
+    static bool attr = false;
+    if (!attr) { MOB_CUDA_TRY(cudaFuncSetAttribute(lz4_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLz4Smem)); attr = true; }
+    lz4_decode_kernel<<<(unsigned)ctas, 32 * kWarpsPerCta, kLz4Smem, t.stream>>>(dst, args[0].dataSz, src, args[1].dataSz, desc, len, dbad);
     cudaEventRecord(t.kev1, t.stream);
     MOB_LAUNCH_CHECK();
     unsigned long long bad = ~0ull;
