@@ -19,12 +19,12 @@
 namespace mob {
 namespace {
 
-constexpr int kWarpsPerCta = 4;
+constexpr int kWarpsPerCta = 8;
 
 // The token stream is read through a per-warp shared-memory WINDOW of the compressed block (kWin bytes, refilled cooperatively with 16-byte loads
 // when the cursor runs past it): a sequence costs a handful of dependent byte reads (token, length extensions, offset), and from global memory each
 // of them is a full memory latency (measured: 14 MB/s per warp, 27 GB/s for 2000 blocks); from shared memory they are ~30 cycles.
-constexpr int kWin = 1024;
+constexpr int kWin = 512;
 
 struct SrcWin {
     const uint8_t *src; int64_t sl; unsigned char *buf; int64_t base;   // buf holds src[base .. base + kWin) (base is 16-byte aligned in ABSOLUTE address terms)
@@ -50,8 +50,8 @@ struct SrcWin {
 // The OUTPUT goes through shared memory too: a match reads bytes the warp wrote a moment ago, and from global memory that is an L2 round trip per
 // sequence (the measured bound once the token stream was in shared memory: ~0.6 us per sequence per warp).  Every output byte is written to the
 // block in global memory AND to a per-warp ring of the last kRing bytes; matches whose source lies inside the ring (offset <= kRing: the common
-// case, LZ4 favours near matches) are served from it, farther ones from global memory.
-constexpr int kRing = 16384;
+// case in column data, where a value repeats its neighbours' bytes) are served from it, farther ones from global memory.
+constexpr int kRing = 4096;    // 4.5 KB of shared memory per warp: up to 48 warps (= blocks in flight) per SM
 constexpr size_t kLz4Smem = (size_t)kWarpsPerCta * (kWin + kRing);
 
 __global__ void __launch_bounds__(32 * kWarpsPerCta)
@@ -128,10 +128,13 @@ int xcall_lz4_decode(mo_xcall_args_t *args, uint64_t len) {
     if (st.failed) { st.finish(); return MO_RC_INTERNAL_ERROR; }
     MOB_CUDA_TRY(cudaMemsetAsync(dbad, 0xff, 8, t.stream));
     uint64_t ctas = (len + kWarpsPerCta - 1) / kWarpsPerCta;
-    if (ctas > (uint64_t)num_sms() * 16) ctas = (uint64_t)num_sms() * 16;
+
     cudaEventRecord(t.kev0, t.stream);
     static bool attr = false;
     if (!attr) { MOB_CUDA_TRY(cudaFuncSetAttribute(lz4_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLz4Smem)); attr = true; }
+    int occ = 1;   // exactly the resident CTAs: blocks are dealt statically over the warps, a partial second wave would cost a whole block time
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lz4_decode_kernel, 32 * kWarpsPerCta, kLz4Smem) != cudaSuccess || occ < 1) occ = 1;
+    if (ctas > (uint64_t)num_sms() * occ) ctas = (uint64_t)num_sms() * occ;
     lz4_decode_kernel<<<(unsigned)ctas, 32 * kWarpsPerCta, kLz4Smem, t.stream>>>(dst, args[0].dataSz, src, args[1].dataSz, desc, len, dbad);
     cudaEventRecord(t.kev1, t.stream);
     MOB_LAUNCH_CHECK();

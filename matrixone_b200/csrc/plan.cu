@@ -131,50 +131,6 @@ __device__ __forceinline__ uint64_t plan_key_bits(int mode, unsigned long long s
     }
 }
 
-// one row whose group is not in the CTA's private dictionary: shared CTA table first, the global table when that is full
-__device__ __noinline__ void plan_slow_row(const mo_plan_t &P, PlanGlobal &G, uint64_t *tkey, unsigned long long *tfirst, unsigned long long *trows, double *tacc,
-                                           unsigned long long *tcnt, const unsigned long long *my, int j, uint64_t key, unsigned nullbits, uint64_t grow) {
-    const int naggs = P.naggs;
-    int slot = -1;
-    if (key != kEmptyKey) {
-        unsigned s = (unsigned)mix64(key) & (kCtaSlots - 1);
-        for (int probes = 0; probes < kCtaSlots; probes++) {
-            uint64_t cur = tkey[s];
-            if (cur == key) { slot = (int)s; break; }
-            if (cur == kEmptyKey) {
-                cur = atomicCAS((unsigned long long *)&tkey[s], (unsigned long long)kEmptyKey, (unsigned long long)key);
-                if (cur == kEmptyKey || cur == key) { slot = (int)s; break; }
-            }
-            s = (s + 1) & (kCtaSlots - 1);
-        }
-    }
-    unsigned long long *first_p = slot >= 0 ? &tfirst[slot] : nullptr, *rows_p = slot >= 0 ? &trows[slot] : nullptr;
-    double *acc_p = slot >= 0 ? &tacc[slot * naggs] : nullptr; unsigned long long *cnt_p = slot >= 0 ? &tcnt[slot * naggs] : nullptr;
-    if (slot < 0) {
-        const uint64_t gs = global_find(G, key);
-        if (gs == ~0ull) return;
-        first_p = &G.first_row[gs]; rows_p = &G.rows[gs]; acc_p = &G.acc[gs * naggs]; cnt_p = &G.cnt[gs * naggs];
-    }
-    if (*((volatile unsigned long long *)first_p) > grow) atomicMin(first_p, (unsigned long long)grow);
-    atomicAdd(rows_p, 1ull);
-    for (int a = 0; a < naggs; a++) {
-        const int vs = P.agg[a].value;
-        if (vs < 0) { atomicAdd(&cnt_p[a], 1ull); continue; }            // COUNT(*)
-        if ((nullbits >> vs) & 1u) continue;                             // aggregates skip NULLs
-        agg_apply(P.agg[a].kind, &acc_p[a], __longlong_as_double((long long)PLAN_SLOT(vs, j)));
-        atomicAdd(&cnt_p[a], 1ull);
-    }
-}
-
-// claim (or find) `key` in the CTA's private dictionary.  Out of line: runs a handful of times per thread.
-__device__ __noinline__ void plan_dict_claim(unsigned long long *pdict, uint64_t key) {
-    bool okc = false;
-    for (int g = 0; g < kPriv && !okc; g++) {
-        const unsigned long long prev = atomicCAS(&pdict[g], (unsigned long long)kEmptyKey, (unsigned long long)key);
-        okc = prev == kEmptyKey || prev == key;
-    }
-}
-
 __global__ void __launch_bounds__(kThreads)
 plan_kernel(const mo_plan_t *__restrict__ Pg, const PlanAux *__restrict__ Ag, PlanCols C, uint64_t n, PlanGlobal G) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -331,7 +287,12 @@ plan_kernel(const mo_plan_t *__restrict__ Pg, const PlanAux *__restrict__ Ag, Pl
 #pragma unroll
                 for (int g = 0; g < kPriv; g++) if (dk[g] == key) p = g;
                 if (p < 0 && !dict_full && key != kEmptyKey) {
-                    plan_dict_claim(pdict, key);
+                    bool okc = false;
+#pragma unroll
+                    for (int g = 0; g < kPriv; g++) {
+                        const unsigned long long prev = okc ? key : atomicCAS(&pdict[g], (unsigned long long)kEmptyKey, (unsigned long long)key);
+                        okc = okc || prev == kEmptyKey || prev == key;
+                    }
                     bool full = true;
 #pragma unroll
                     for (int g = 0; g < kPriv; g++) { dk[g] = ((volatile unsigned long long *)pdict)[g]; full = full && dk[g] != kEmptyKey; if (dk[g] == key) p = g; }
@@ -364,9 +325,46 @@ plan_kernel(const mo_plan_t *__restrict__ Pg, const PlanAux *__restrict__ Ag, Pl
                 }
             }
         }
-        // ---- rows whose key is not in the private dictionary: shared CTA table, then the global table (out of line: rare for few-group plans, and
-        // four inlined copies of it made the kernel large enough to stall on instruction fetch)
-        PLAN_FORJ { if (ok[j] && ps[j] < 0) plan_slow_row(P, G, tkey, tfirst, trows, tacc, tcnt, my, j, keys[j], nb[j], (uint64_t)P.row_base + r0 + (uint64_t)j * kThreads); }
+        // ---- rows whose key is not in the private dictionary: shared CTA table, then the global table
+        PLAN_FORJ {
+            if (ok[j] && ps[j] < 0) {
+                const unsigned nullbits = nb[j];
+                const uint64_t key = keys[j];
+                const uint64_t grow = (uint64_t)P.row_base + r0 + (uint64_t)j * kThreads;
+                int slot = -1;
+                if (key != kEmptyKey) {
+                    unsigned s = (unsigned)mix64(key) & (kCtaSlots - 1);
+                    for (int probes = 0; probes < kCtaSlots; probes++) {
+                        uint64_t cur = tkey[s];
+                        if (cur == key) { slot = (int)s; break; }
+                        if (cur == kEmptyKey) {
+                            cur = atomicCAS((unsigned long long *)&tkey[s], (unsigned long long)kEmptyKey, (unsigned long long)key);
+                            if (cur == kEmptyKey || cur == key) { slot = (int)s; break; }
+                        }
+                        s = (s + 1) & (kCtaSlots - 1);
+                    }
+                }
+                unsigned long long *first_p = slot >= 0 ? &tfirst[slot] : nullptr, *rows_p = slot >= 0 ? &trows[slot] : nullptr;
+                double *acc_p = slot >= 0 ? &tacc[slot * naggs] : nullptr; unsigned long long *cnt_p = slot >= 0 ? &tcnt[slot * naggs] : nullptr;
+                bool have = true;
+                if (slot < 0) {
+                    const uint64_t gs = global_find(G, key);
+                    if (gs == ~0ull) have = false;
+                    else { first_p = &G.first_row[gs]; rows_p = &G.rows[gs]; acc_p = &G.acc[gs * naggs]; cnt_p = &G.cnt[gs * naggs]; }
+                }
+                if (have) {
+                    if (*((volatile unsigned long long *)first_p) > grow) atomicMin(first_p, (unsigned long long)grow);
+                    atomicAdd(rows_p, 1ull);
+                    for (int a = 0; a < naggs; a++) {
+                        const int vs = P.agg[a].value;
+                        if (vs < 0) { atomicAdd(&cnt_p[a], 1ull); continue; }            // COUNT(*)
+                        if ((nullbits >> vs) & 1u) continue;                             // aggregates skip NULLs
+                        agg_apply(P.agg[a].kind, &acc_p[a], __longlong_as_double((long long)PLAN_SLOT(vs, j)));
+                        atomicAdd(&cnt_p[a], 1ull);
+                    }
+                }
+            }
+        }
     }
     // ---- retire: the CTA first folds its threads' private states (one thread per (group, aggregate), a fixed order), then touches the global
     // table once per (group, aggregate) instead of once per thread

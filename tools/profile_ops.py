@@ -140,14 +140,14 @@ def main():
         lib.bloomfilter_free(bf); keys.free(); res.free()
     except Exception as e:   # keep the other numbers
         out["bloom_error"] = repr(e)
-    # ---- LZ4 block decode: 2000 column blocks (8192 int64 rows each, ~2.5x compressible) in one call vs liblz4 on one host core
+    # ---- LZ4 block decode: 16000 column blocks (8192 int64 rows each, ~2.5x compressible) in one call vs liblz4 on one host core
     try:
         import time
         import pyarrow as pa
         rng = np.random.default_rng(3)
         raws = [(rng.integers(0, 1000, 8192) + i).astype(np.int64).tobytes() for i in range(64)]
         comps = [pa.compress(r, codec="lz4_raw", asbytes=True) for r in raws]
-        nblk = 2000
+        nblk = 16000                                              # a scan's worth: the decoder keeps one block per warp in flight, up to 48 per SM
         blocks = [comps[i % 64] for i in range(nblk)]
         src = np.frombuffer(b"".join(blocks), dtype=np.uint8)
         desc = np.zeros((nblk, 4), dtype=np.int64); so = 0
@@ -167,6 +167,27 @@ def main():
         dsrc.free(); ddesc.free(); ddst.free()
     except Exception as e:
         out["lz4_error"] = repr(e)
+    # ---- Elkan k-means (index build): 100 k x 128-d vectors, 256 clusters, <= 10 iterations; the oracle port (= the reference's loop) on one host core
+    try:
+        import time
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as O
+        kn, kd, kk = 100_000, 128, 256
+        kv = datagen.vectors_f32(33, 0, kn, kd)
+        kinit = kv[:: kn // kk][:kk].copy()
+        krnd = np.random.default_rng(5).random(kd * kk * 4).astype(np.float32)
+        ops.kmeans_elkan(kv[:2000], kinit[:8], 2, krnd)                       # warm-up
+        t0 = time.perf_counter()
+        gc, ga, gi = ops.kmeans_elkan(kv, kinit, 10, krnd)
+        gpu_s = time.perf_counter() - t0
+        oc = kinit.copy(); oa = np.zeros(kn, np.int64)
+        t0 = time.perf_counter()
+        oi = O.go().og_km_cluster_f32(O.p(kv), kn, kd, O.p(oc), kk, 10, O.p(krnd), len(krnd), O.p(oa))
+        cpu_s = time.perf_counter() - t0
+        out["kmeans_elkan"] = {"n": kn, "dim": kd, "k": kk, "iterations": gi, "gpu_s_host_pointers": gpu_s, "oracle_one_core_s": cpu_s,
+                               "bit_equal": bool(gi == oi and (ga == oa).all() and gc.tobytes() == oc.tobytes())}
+    except Exception as e:
+        out["kmeans_error"] = repr(e)
     print(json.dumps(out))
 
 
