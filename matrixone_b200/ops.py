@@ -749,11 +749,20 @@ class JoinMap:
 
 # ---------------------------------------------------------------------------------------------- Elkan k-means (csrc/kmeans.cu)
 def kmeans_elkan(vectors, init_centroids, max_iter=500, rnd=None):
-    """ElkanClusterer.Cluster from given initial centroids (pkg/vectorindex/ivfflat/kmeans/elkans/clusterer.go:330-392), dense variant.
+    """ElkanClusterer.Cluster (pkg/vectorindex/ivfflat/kmeans/elkans/clusterer.go:330-392), dense variant.  init_centroids: an array [k, dim],
+    or an int k = kmeans.Random initialisation (Random.InitCentroids with Go's PCG, gorand.py) and the matching empty-cluster stream.
     Returns (centroids [k, dim], assignments int64[n], iterations)."""
     v = np.ascontiguousarray(vectors)
     assert v.dtype in (np.float32, np.float64)
     n, dim = v.shape
+    if isinstance(init_centroids, (int, np.integer)):
+        from . import gorand
+        k = int(init_centroids)
+        if n == k:                                    # Cluster(): vectorCnt == clusterCnt returns the vectors themselves (clusterer.go:337-339)
+            return v.copy(), np.arange(n, dtype=np.int64), 0
+        init_centroids = v[gorand.random_init_rows(n, k)]
+        if rnd is None:
+            rnd = np.array(gorand.empty_cluster_stream(min(dim * k * 4, 1 << 20)), dtype=np.float32)
     cent = np.ascontiguousarray(init_centroids, dtype=v.dtype).copy()
     k = cent.shape[0]
     assign = np.zeros(n, dtype=np.int64); iters = np.zeros(1, dtype=np.int64)

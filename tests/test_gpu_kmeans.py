@@ -38,6 +38,15 @@ def test_reference_table_vectors(gpu):
     np.testing.assert_allclose(c, K["recalc"]["centroids"], rtol=1e-12)          # the converged means are the recalculateCentroids table's
 
 
+def test_reference_test_cluster_expectation_with_random_init(gpu):
+    """Test_Cluster (clusterer_test.go:441-470) end to end: kmeans.Random initialisation (Go's PCG restated on the host side) + the GPU loop"""
+    v = np.array([[1, 2, 3, 4], [1, 2, 4, 5], [1, 2, 4, 5], [1, 2, 3, 4], [1, 2, 4, 5], [1, 2, 4, 5],
+                  [10, 2, 4, 5], [10, 3, 4, 5], [10, 5, 4, 5], [10, 2, 4, 5], [10, 3, 4, 5], [10, 5, 4, 5]], dtype=np.float64)
+    c, a, it = ops.kmeans_elkan(v, 2)
+    np.testing.assert_allclose(c, [[10, 3.333333333333333, 4, 5], [1, 2, 3.6666666666666665, 4.666666666666666]], rtol=1e-12)
+    assert list(a) == [1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0]
+
+
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("n,k,dim", [(3000, 16, 64), (2000, 7, 13), (5000, 64, 128), (400, 3, 1), (20_000, 128, 96)])
 def test_matches_oracle_bit_for_bit(gpu, dtype, n, k, dim):

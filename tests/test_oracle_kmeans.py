@@ -51,6 +51,24 @@ def test_update_bounds_table():
         assert _close(lower[i], m["lower"]) and _close(upper[i], m["upper"]) and bool(rec[i]) == m["recompute"]
 
 
+def test_reference_whole_run_expectations_pin_the_generator_and_the_loop():
+    """TestRandom_InitCentroids (initializer_test.go:36-59) and Test_Cluster (clusterer_test.go:441-470): kmeans.Random initialisation on 12 vectors,
+    k = 2.  The expected initial centroids are vectors 7 and 1 -- reached only if Go's PCG(1, 0) is restated correctly (gorand.py) -- and the expected
+    final centroids come out of the restated Elkan loop started from them."""
+    from matrixone_b200 import gorand
+    v = np.array([[1, 2, 3, 4], [1, 2, 4, 5], [1, 2, 4, 5], [1, 2, 3, 4], [1, 2, 4, 5], [1, 2, 4, 5],
+                  [10, 2, 4, 5], [10, 3, 4, 5], [10, 5, 4, 5], [10, 2, 4, 5], [10, 3, 4, 5], [10, 5, 4, 5]], dtype=np.float64)
+    rows = gorand.random_init_rows(12, 2)
+    assert rows == [7, 1]
+    assert v[rows].tolist() == [[10, 3, 4, 5], [1, 2, 4, 5]]                       # wantCentroids of TestRandom_InitCentroids
+    cent = v[rows].copy(); assign = np.zeros(12, np.int64)
+    iters = O.go().og_km_cluster_f64(O.p(v), 12, 4, O.p(cent), 2, 500, None, 0, O.p(assign))
+    assert iters > 0
+    assert _close(cent, [[10, 3.333333333333333, 4, 5], [1, 2, 3.6666666666666665, 4.666666666666666]])       # want of Test_Cluster
+    sse = sum(float(np.sqrt(((v[i] - cent[assign[i]]) ** 2).sum())) ** 2 for i in range(12))
+    assert abs(sse - 12) < 1e-9                                                     # wantSSE
+
+
 def test_whole_loop_agrees_with_lloyd_on_separated_clusters():
     rng = np.random.default_rng(0)
     k, dim, per = 8, 16, 200
