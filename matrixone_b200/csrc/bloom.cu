@@ -118,9 +118,16 @@ bloom_kernel(uint64_t *__restrict__ bits, uint64_t nbits, uint32_t k, uint64_t s
             }
         } else {
             bool all = true;
-            for (uint32_t j = 0; j < k && all; j++) {
-                const uint64_t pos = (h.lo + (uint64_t)j * h.hi) & (nbits - 1);
-                all = (__ldg(&bits[pos >> 6]) >> (pos & 63)) & 1ull;
+            if (k <= 4) {   // the usual k: all probes are issued before any is looked at (they are independent random reads; an early exit would serialise them)
+                uint64_t w[4];
+#pragma unroll
+                for (uint32_t j = 0; j < 4; j++) { const uint64_t pos = (h.lo + (uint64_t)j * h.hi) & (nbits - 1); w[j] = j < k ? (__ldg(&bits[pos >> 6]) >> (pos & 63)) : 1ull; }
+                all = (w[0] & w[1] & w[2] & w[3]) & 1ull;
+            } else {
+                for (uint32_t j = 0; j < k && all; j++) {
+                    const uint64_t pos = (h.lo + (uint64_t)j * h.hi) & (nbits - 1);
+                    all = (__ldg(&bits[pos >> 6]) >> (pos & 63)) & 1ull;
+                }
             }
             result[i] = all ? 1 : 0;
         }
