@@ -94,9 +94,16 @@ select_kernel(const uint8_t *__restrict__ v, const uint64_t *__restrict__ nulls,
         s_prefix = excl;
         if (tile == ntiles - 1) *total = excl + agg;
     }
+    // the selected rows of the tile are first listed in shared memory (16-bit offsets inside the tile, at their rank), then written out by the
+    // whole CTA with consecutive threads on consecutive slots: one coalesced stream instead of 256 interleaved per-thread runs
+    __shared__ unsigned short s_list[kSelTile];
+    unsigned lpos = wbase + (inc - cnt);
+    const unsigned tbase = threadIdx.x * kSelRows;
+    while (mask) { const int j = __ffs(mask) - 1; mask &= mask - 1; s_list[lpos++] = (unsigned short)(tbase + j); }
     __syncthreads();
-    unsigned long long off = s_prefix + wbase + (inc - cnt);
-    while (mask) { const int j = __ffs(mask) - 1; mask &= mask - 1; sels[off++] = (OutT)(row0 + j); }
+    const unsigned long long out0 = s_prefix;
+    const uint64_t tile_row0 = (uint64_t)tile * kSelTile;
+    for (unsigned i = threadIdx.x; i < agg; i += kSelThreads) sels[out0 + i] = (OutT)(tile_row0 + s_list[i]);
 }
 
 // launches the compaction; *dtotal (device) receives the count.  status/ticket scratch comes from the arena.

@@ -80,7 +80,7 @@ lz4_decode_kernel(uint8_t *__restrict__ dst_base, uint64_t dst_cap, const uint8_
                 if (lit) {
                     if (ip + lit - W.base > kWin && lit <= kWin - 16) W.fill(ip, lane);           // bring the whole literal run into the window when it fits
                     if (ip + lit - W.base <= kWin) { for (int64_t i = lane; i < lit; i += 32) { const unsigned char v = W.buf[ip - W.base + i]; dst[op + i] = v; ring[(op + i) & (kRing - 1)] = v; } }
-                    else { for (int64_t i = lane; i < lit; i += 32) { const unsigned char v = src[ip + i]; dst[op + i] = v; ring[(op + i) & (kRing - 1)] = v; } }   // a long run (incompressible data): straight from global memory
+                    else { __syncwarp(); for (int64_t i = lane; i < lit; i += 32) { const unsigned char v = src[ip + i]; dst[op + i] = v; ring[(op + i) & (kRing - 1)] = v; } }   // a long run (incompressible data): straight from global memory (it may wrap the ring: the previous match must be done reading)
                 }
                 ip += lit; op += lit;
                 if (ip >= sl) break;                                   // the last sequence: literals only
@@ -103,7 +103,9 @@ lz4_decode_kernel(uint8_t *__restrict__ dst_base, uint64_t dst_cap, const uint8_
                     else { for (int64_t i = lane; i < mlen; i += 32) { const unsigned char v = dst[from + (i % offset)]; dst[op + i] = v; ring[(op + i) & (kRing - 1)] = v; } }
                 }
                 op += mlen;
-                __syncwarp();
+                // the next sequence's literal copy writes ring slots that are at most kWin + its length ahead: it can only collide with this match's
+                // reads when the match reached back almost a whole ring; otherwise the __syncwarp() before the next match orders everything
+                if (offset + mlen + 2 * kWin > kRing) __syncwarp();
             }
             if (!bad && op != dl) bad = true;
         }
