@@ -250,6 +250,21 @@ typedef struct { int32_t div0_null; int32_t reserved; int64_t err_row; } mo_go_p
  * decoded size the object metadata records; a block that decodes to anything else, or is malformed, fails the call with MO_RC_INVALID_ARGUMENT and
  * the block number in the error text).  len = number of blocks. */
 #define MO_XCALL_LZ4_DECODE 0x6030
+/* ---- a decompressed column block -> a resident vector (csrc/vecdecode.cu): Vector.UnmarshalBinary (pkg/container/vector/vector.go:766-819) on the device.
+ * args: [0] mo_vector_view_t (out) ; [1] data bytes (out: capacity >= dataLen, aligned) ; [2] area bytes (out) ; [3] nulls uint64 words (out:
+ * (length + 63) / 64 words; pdata NULL when not wanted) ; [4] the marshalled bytes (dataSz = their length; when they are device memory the buffer
+ * must be readable 8 bytes past that length).  Malformed bytes or too small output buffers -> MO_RC_INVALID_ARGUMENT. */
+typedef struct mo_vector_view_t {
+    int32_t vclass;        /* 0 FLAT, 1 CONSTANT */
+    int32_t oid;           /* types.T */
+    int32_t size, width, scale;
+    uint32_t length;       /* rows */
+    uint64_t data_len, area_len;
+    int64_t null_count;    /* bitmap.count as marshalled */
+    uint64_t nulls_words;
+    int32_t sorted, bad;
+} mo_vector_view_t;
+#define MO_XCALL_VECTOR_UNMARSHAL 0x6031
 typedef struct mo_kmeans_params_t { int64_t n, dim, k, max_iter; } mo_kmeans_params_t;
 #define MO_XCALL_KMEANS_ELKAN_F32 0x6020
 #define MO_XCALL_KMEANS_ELKAN_F64 0x6021

@@ -50,6 +50,7 @@ XCALL_FILTER_SELS, XCALL_PACK_KEYS, XCALL_GROUP_IDS = 0x6000, 0x6001, 0x6002
 XCALL_JOIN_SELS, XCALL_JOIN_FIND, XCALL_JOIN_PROBE = 0x6010, 0x6011, 0x6012
 XCALL_KMEANS_ELKAN_F32, XCALL_KMEANS_ELKAN_F64 = 0x6020, 0x6021
 XCALL_LZ4_DECODE = 0x6030
+XCALL_VECTOR_UNMARSHAL = 0x6031
 JOIN_INNER, JOIN_LEFT, JOIN_SEMI, JOIN_ANTI = 0, 1, 2, 3
 
 

@@ -24,6 +24,7 @@ int xcall_group_ids(mo_xcall_args_t *args, uint64_t len);
 int xcall_join_sels(mo_xcall_args_t *args, uint64_t len);
 int xcall_kmeans(int64_t funcId, mo_xcall_args_t *args, uint64_t len);
 int xcall_lz4_decode(mo_xcall_args_t *args, uint64_t len);
+int xcall_vector_unmarshal(mo_xcall_args_t *args, uint64_t len);
 int xcall_join_find(mo_xcall_args_t *args, uint64_t len);
 int xcall_join_probe(mo_xcall_args_t *args, uint64_t len);
 int xcall_group_agg(int op, int T, mo_xcall_args_t *args, uint64_t len);
@@ -65,6 +66,7 @@ extern "C" int32_t XCall(int64_t runtimeId, int64_t funcId, uint8_t *errStr, uin
     else if (funcId == MO_XCALL_GROUP_IDS) rc = xcall_group_ids(a, len);
     else if (funcId == MO_XCALL_JOIN_SELS) rc = xcall_join_sels(a, len);
     else if (funcId == MO_XCALL_LZ4_DECODE) rc = xcall_lz4_decode(a, len);
+    else if (funcId == MO_XCALL_VECTOR_UNMARSHAL) rc = xcall_vector_unmarshal(a, len);
     else if (funcId == MO_XCALL_KMEANS_ELKAN_F32 || funcId == MO_XCALL_KMEANS_ELKAN_F64) rc = xcall_kmeans(funcId, a, len);
     else if (funcId == MO_XCALL_JOIN_FIND) rc = xcall_join_find(a, len);
     else if (funcId == MO_XCALL_JOIN_PROBE) rc = xcall_join_probe(a, len);

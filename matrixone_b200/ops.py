@@ -788,3 +788,21 @@ def lz4_decode_blocks(blocks, sizes):
     dst = np.zeros(max(do, 1), dtype=np.uint8)
     xcall(capi.XCALL_LZ4_DECODE, [Vector(data=dst, length=do), Vector(data=src if src.size else np.zeros(1, np.uint8), length=so), Vector(data=desc.reshape(-1), length=4 * n)], n)
     return [dst[desc[i, 2]:desc[i, 2] + desc[i, 3]].tobytes() for i in range(n)]
+
+
+# ---------------------------------------------------------------------------------------------- marshalled vector -> resident vector (csrc/vecdecode.cu)
+class VectorView(C.Structure):
+    _fields_ = [("vclass", C.c_int32), ("oid", C.c_int32), ("size", C.c_int32), ("width", C.c_int32), ("scale", C.c_int32), ("length", C.c_uint32),
+                ("data_len", C.c_uint64), ("area_len", C.c_uint64), ("null_count", C.c_int64), ("nulls_words", C.c_uint64), ("sorted", C.c_int32), ("bad", C.c_int32)]
+
+
+def vector_unmarshal_device(src_dev, nbytes, data_dev, area_dev, nulls_dev):
+    """Vector.UnmarshalBinary on the device: src_dev holds the marshalled bytes (e.g. straight out of lz4 decode), the sections are copied to the
+    aligned DeviceBuffers given.  Returns the VectorView."""
+    view = np.zeros(C.sizeof(VectorView), dtype=np.uint8)
+    vecs = [Vector(data=view, length=1), Vector(data_ptr=data_dev.ptr, data_nbytes=data_dev.nbytes, length=1),
+            Vector(data_ptr=area_dev.ptr, data_nbytes=area_dev.nbytes, length=1) if area_dev is not None else Vector(length=0),
+            Vector(data_ptr=nulls_dev.ptr, data_nbytes=nulls_dev.nbytes, length=1) if nulls_dev is not None else Vector(length=0),
+            Vector(data_ptr=src_dev.ptr, data_nbytes=nbytes, length=1)]
+    xcall(capi.XCALL_VECTOR_UNMARSHAL, vecs, 1)
+    return VectorView.from_buffer_copy(view.tobytes())

@@ -201,3 +201,25 @@ def xcall(func_id, vectors, length, runtime_id=1, lib=None, raise_on_error=True)
     if rc != 0 and raise_on_error:
         raise capi.MoError(rc, "xcall xfunc failed, error code %d, %s" % (rc, msg))
     return rc, msg
+
+
+# ---------------------------------------------------------------------------------------------- marshalled vectors (object blocks)
+def marshal_vector(oid, data, length, area=b"", nulls=None, size=None, width=0, scale=0, const=False, sorted_flag=False):
+    """Vector.MarshalBinary (pkg/container/vector/vector.go:718-764) for the test harness: class, types.Type (16 bytes), length, dataLen + data,
+    areaLen + area, nspLen + bitmap.Marshal (count, len, size, words; nothing when no row is NULL), sorted."""
+    data = np.ascontiguousarray(data).view(np.uint8).reshape(-1).tobytes()
+    area = bytes(area)
+    out = bytearray()
+    out += bytes([1 if const else 0])
+    out += bytes([oid & 0xFF, 0, 0, 0]) + np.array([size if size is not None else (len(data) // max(length, 1)), width, scale], dtype=np.int32).tobytes()
+    out += np.uint32(length).tobytes() + np.uint32(len(data)).tobytes() + data
+    out += np.uint32(len(area)).tobytes() + area
+    nsp = b""
+    if nulls is not None:
+        words = np.ascontiguousarray(nulls, dtype=np.uint64)
+        cnt = int(sum(bin(int(w)).count("1") for w in words))
+        if cnt:
+            nsp = np.int64(cnt).tobytes() + np.uint64(length).tobytes() + np.uint64(words.nbytes).tobytes() + words.tobytes()
+    out += np.uint32(len(nsp)).tobytes() + nsp
+    out += bytes([1 if sorted_flag else 0])
+    return bytes(out)
