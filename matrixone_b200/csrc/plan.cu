@@ -27,7 +27,7 @@ using namespace mob;
 namespace {
 
 constexpr int kThreads = 128;
-constexpr int kCtaSlots = 64;           // per-CTA group table (shared atomics)
+constexpr int kCtaSlots = 32;           // per-CTA group table (shared atomics)
 constexpr int kPriv = 4;               // groups whose state every thread keeps PRIVATELY in shared memory (no atomics, no shuffles)
 constexpr uint64_t kEmptyKey = 0xffffffffffffffffull;
 
@@ -117,6 +117,8 @@ struct PlanAux {                       // host-prepared decode of the descriptor
                                        // 3 float64 slot holding a float32 (key = its float32 bits), 4 float64 bits
     int key_shift[MO_PLAN_MAX_KEYS];   // bit offset of the column inside the packed key when has_null_keys == 0
     int need_cnt;                      // some aggregate input can be NULL (nullable column or a division): per-aggregate counts are kept
+    int phys[MO_PLAN_MAX_COLS + MO_PLAN_MAX_INSTR];   // value slot -> PHYSICAL slot of the shared-memory register file (slots are reused once dead)
+    int nphys;
 };
 
 #define PLAN_FORJ _Pragma("unroll") for (int j = 0; j < R; j++)
@@ -131,7 +133,7 @@ __device__ __forceinline__ uint64_t plan_key_bits(int mode, unsigned long long s
     }
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 plan_kernel(const mo_plan_t *__restrict__ Pg, const PlanAux *__restrict__ Ag, PlanCols C, uint64_t n, PlanGlobal G) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ mo_plan_t P;
@@ -139,8 +141,8 @@ plan_kernel(const mo_plan_t *__restrict__ Pg, const PlanAux *__restrict__ Ag, Pl
     for (int i = threadIdx.x; i < (int)(sizeof(mo_plan_t) / 4); i += kThreads) reinterpret_cast<uint32_t *>(&P)[i] = reinterpret_cast<const uint32_t *>(Pg)[i];
     for (int i = threadIdx.x; i < (int)(sizeof(PlanAux) / 4); i += kThreads) reinterpret_cast<uint32_t *>(&X)[i] = reinterpret_cast<const uint32_t *>(Ag)[i];
     __syncthreads();
-    const int nslots = P.ncols + P.ninstr, naggs = P.naggs;
-    unsigned long long *vreg = reinterpret_cast<unsigned long long *>(smem_raw);                      // [(slot * R + j) * kThreads + tid]
+    const int nslots = X.nphys, naggs = P.naggs;
+    unsigned long long *vreg = reinterpret_cast<unsigned long long *>(smem_raw);                      // [(physical slot * R + j) * kThreads + tid]
     uint64_t *tkey = reinterpret_cast<uint64_t *>(vreg + (size_t)nslots * R * kThreads);              // [kCtaSlots]
     unsigned long long *tfirst = reinterpret_cast<unsigned long long *>(tkey + kCtaSlots);
     unsigned long long *trows = tfirst + kCtaSlots;
@@ -156,12 +158,12 @@ plan_kernel(const mo_plan_t *__restrict__ Pg, const PlanAux *__restrict__ Ag, Pl
     __shared__ unsigned long long pdict[kPriv];
     double *pacc0 = reinterpret_cast<double *>(tcnt + (size_t)kCtaSlots * naggs);                     // [(g * naggs + a) * kThreads + tid]
     unsigned *pcnt0 = reinterpret_cast<unsigned *>(pacc0 + (size_t)kPriv * naggs * kThreads);
-    unsigned *prows0 = pcnt0 + (size_t)kPriv * naggs * kThreads;                                      // [g * kThreads + tid]
+    unsigned *prows0 = pcnt0 + (X.need_cnt ? (size_t)kPriv * naggs * kThreads : 0);                   // [g * kThreads + tid]  (the per-aggregate counts exist only when an input can be NULL)
     unsigned long long *pfirst0 = reinterpret_cast<unsigned long long *>(prows0 + (size_t)kPriv * kThreads);
     double *pacc = pacc0 + threadIdx.x; unsigned *pcnt = pcnt0 + threadIdx.x, *prows = prows0 + threadIdx.x; unsigned long long *pfirst = pfirst0 + threadIdx.x;
     if (threadIdx.x < kPriv) pdict[threadIdx.x] = kEmptyKey;
     for (int g = 0; g < kPriv; g++) {
-        for (int a = 0; a < naggs; a++) { pacc[(g * naggs + a) * kThreads] = agg_identity(P.agg[a].kind); pcnt[(g * naggs + a) * kThreads] = 0u; }
+        for (int a = 0; a < naggs; a++) { pacc[(g * naggs + a) * kThreads] = agg_identity(P.agg[a].kind); if (X.need_cnt) pcnt[(g * naggs + a) * kThreads] = 0u; }
         prows[g * kThreads] = 0u; pfirst[g * kThreads] = ~0ull;
     }
     unsigned long long dk[kPriv];
@@ -204,13 +206,14 @@ plan_kernel(const mo_plan_t *__restrict__ Pg, const PlanAux *__restrict__ Ag, Pl
                     if (tof == 1) { PLAN_FORJ raw[g][j] = (unsigned long long)__double_as_longlong((double)(long long)raw[g][j]); }
                     else if (tof == 2) { PLAN_FORJ raw[g][j] = (unsigned long long)__double_as_longlong((double)raw[g][j]); }
                     else if (tof == 3) { PLAN_FORJ raw[g][j] = (unsigned long long)__double_as_longlong((double)__uint_as_float((unsigned)raw[g][j])); }
-                    PLAN_FORJ { PLAN_SLOT(c, j) = raw[g][j]; nb[j] |= (unsigned)((nw[g][j] >> ((r0 + (uint64_t)j * kThreads) & 63)) & 1ull) << c; }
+                    const int pc = X.phys[c];
+                    PLAN_FORJ { PLAN_SLOT(pc, j) = raw[g][j]; nb[j] |= (unsigned)((nw[g][j] >> ((r0 + (uint64_t)j * kThreads) & 63)) & 1ull) << c; }
                 }
             }
         }
         // ---- filter: conjunction; a NULL operand makes the conjunct not-true (filter.go:125-141 keeps rows with !null && true)
         for (int q = 0; q < P.npreds; q++) {
-            const int c = P.pred[q].col, op = P.pred[q].op;
+            const int c = P.pred[q].col, op = P.pred[q].op, pc = X.phys[c];
 #define PLAN_PRED(XT, LOADX, EXPR) PLAN_FORJ { const XT x = LOADX; ok[j] = ok[j] && (EXPR) && !((nb[j] >> c) & 1u); }
 #define PLAN_PRED_SWITCH(XT, LOADX)                                       \
             switch (op) {                                                 \
@@ -224,41 +227,22 @@ plan_kernel(const mo_plan_t *__restrict__ Pg, const PlanAux *__restrict__ Ag, Pl
             }
             if (X.pred_int[q]) {
                 const long long lo = X.ilo[q], hi = X.ihi[q];
-                PLAN_PRED_SWITCH(long long, (long long)PLAN_SLOT(c, j))
+                PLAN_PRED_SWITCH(long long, (long long)PLAN_SLOT(pc, j))
             } else {
                 const double lo = P.pred[q].lo, hi = P.pred[q].hi;
-                PLAN_PRED_SWITCH(double, __longlong_as_double((long long)PLAN_SLOT(c, j)))
+                PLAN_PRED_SWITCH(double, __longlong_as_double((long long)PLAN_SLOT(pc, j)))
             }
         }
         if (!(ok[0] | ok[1] | ok[2] | ok[3])) continue;
-        // ---- projection: SSA program over float64 slots, one rounding per node (the reference evaluates one expression node at a time too)
-        for (int i = 0; i < P.ninstr; i++) {
-            const int dst = P.ncols + i, op = P.instr[i].op, sa = P.instr[i].a, sb = P.instr[i].b;
-#define PLAN_A __longlong_as_double((long long)PLAN_SLOT(sa, j))
-#define PLAN_B __longlong_as_double((long long)PLAN_SLOT(sb, j))
-#define PLAN_BIN(EXPR) PLAN_FORJ { const double a = PLAN_A, b = PLAN_B; PLAN_SLOT(dst, j) = (unsigned long long)__double_as_longlong(EXPR); \
-                                   nb[j] |= (((nb[j] >> sa) | (nb[j] >> sb)) & 1u) << dst; }
-            switch (op) {
-            case MO_PLAN_OP_CONST: { const unsigned long long imm = (unsigned long long)__double_as_longlong(P.instr[i].imm); PLAN_FORJ PLAN_SLOT(dst, j) = imm; } break;
-            case MO_PLAN_OP_COL: PLAN_FORJ { PLAN_SLOT(dst, j) = PLAN_SLOT(sa, j); nb[j] |= ((nb[j] >> sa) & 1u) << dst; } break;
-            case MO_PLAN_OP_ADD: PLAN_BIN(__dadd_rn(a, b)) break;
-            case MO_PLAN_OP_SUB: PLAN_BIN(__dsub_rn(a, b)) break;
-            case MO_PLAN_OP_MUL: PLAN_BIN(__dmul_rn(a, b)) break;
-            default:             // x / 0 -> NULL (SELECT behaviour)
-                PLAN_FORJ { const double a = PLAN_A, b = PLAN_B; const bool z = b == 0.0;
-                            PLAN_SLOT(dst, j) = (unsigned long long)__double_as_longlong(z ? 0.0 : __ddiv_rn(a, b));
-                            nb[j] |= ((((nb[j] >> sa) | (nb[j] >> sb)) & 1u) | (z ? 1u : 0u)) << dst; }
-                break;
-            }
-        }
-        // ---- group keys (fillKeys): one column at a time
+        // ---- group keys (fillKeys): one column at a time.  BEFORE the projection: keys only read column slots, which the expression nodes may reuse
         uint64_t keys[R];
         PLAN_FORJ keys[j] = 0;
         if (!P.has_null_keys) {
             for (int k = 0; k < P.nkeys; k++) {
                 const int c = P.key_col[k], mode = X.key_mode[k], sh = X.key_shift[k];
                 const uint64_t mask = X.sz[c] < 8 ? (1ull << (8 * X.sz[c])) - 1ull : ~0ull;
-                PLAN_FORJ if (ok[j]) keys[j] |= (plan_key_bits(mode, PLAN_SLOT(c, j), C.data[c], r0 + (uint64_t)j * kThreads) & mask) << sh;
+                const int pc = X.phys[c];
+                PLAN_FORJ if (ok[j]) keys[j] |= (plan_key_bits(mode, PLAN_SLOT(pc, j), C.data[c], r0 + (uint64_t)j * kThreads) & mask) << sh;
             }
         } else {   // has_null mode: a marker byte per column, a NULL contributes the marker only -> the byte offset depends on the row
             PLAN_FORJ {
@@ -268,13 +252,34 @@ plan_kernel(const mo_plan_t *__restrict__ Pg, const PlanAux *__restrict__ Ag, Pl
                         const int c = P.key_col[k], sz = X.sz[c];
                         if ((nb[j] >> c) & 1u) { key |= 1ull << (8 * off); off += 1; continue; }
                         off += 1;
-                        uint64_t raw = plan_key_bits(X.key_mode[k], PLAN_SLOT(c, j), C.data[c], r0 + (uint64_t)j * kThreads);
+                        uint64_t raw = plan_key_bits(X.key_mode[k], PLAN_SLOT(X.phys[c], j), C.data[c], r0 + (uint64_t)j * kThreads);
                         if (sz < 8) raw &= (1ull << (8 * sz)) - 1ull;
                         if (off < 8) key |= raw << (8 * off);
                         off += sz;
                     }
                     keys[j] = key;
                 }
+            }
+        }
+        // ---- projection: SSA program over float64 slots, one rounding per node (the reference evaluates one expression node at a time too)
+        for (int i = 0; i < P.ninstr; i++) {
+            const int dst = P.ncols + i, op = P.instr[i].op, sa = P.instr[i].a, sb = P.instr[i].b;
+            const int pd = X.phys[dst], pa = op != MO_PLAN_OP_CONST ? X.phys[sa] : 0, pb = op >= MO_PLAN_OP_ADD ? X.phys[sb] : 0;   // null bits are per VALUE slot, storage per physical slot
+#define PLAN_A __longlong_as_double((long long)PLAN_SLOT(pa, j))
+#define PLAN_B __longlong_as_double((long long)PLAN_SLOT(pb, j))
+#define PLAN_BIN(EXPR) PLAN_FORJ { const double a = PLAN_A, b = PLAN_B; PLAN_SLOT(pd, j) = (unsigned long long)__double_as_longlong(EXPR); \
+                                   nb[j] |= (((nb[j] >> sa) | (nb[j] >> sb)) & 1u) << dst; }
+            switch (op) {
+            case MO_PLAN_OP_CONST: { const unsigned long long imm = (unsigned long long)__double_as_longlong(P.instr[i].imm); PLAN_FORJ PLAN_SLOT(pd, j) = imm; } break;
+            case MO_PLAN_OP_COL: PLAN_FORJ { PLAN_SLOT(pd, j) = PLAN_SLOT(pa, j); nb[j] |= ((nb[j] >> sa) & 1u) << dst; } break;
+            case MO_PLAN_OP_ADD: PLAN_BIN(__dadd_rn(a, b)) break;
+            case MO_PLAN_OP_SUB: PLAN_BIN(__dsub_rn(a, b)) break;
+            case MO_PLAN_OP_MUL: PLAN_BIN(__dmul_rn(a, b)) break;
+            default:             // x / 0 -> NULL (SELECT behaviour)
+                PLAN_FORJ { const double a = PLAN_A, b = PLAN_B; const bool z = b == 0.0;
+                            PLAN_SLOT(pd, j) = (unsigned long long)__double_as_longlong(z ? 0.0 : __ddiv_rn(a, b));
+                            nb[j] |= ((((nb[j] >> sa) | (nb[j] >> sb)) & 1u) | (z ? 1u : 0u)) << dst; }
+                break;
             }
         }
         // ---- private-dictionary lookup per row (the dictionary state is sequential)
@@ -308,19 +313,19 @@ plan_kernel(const mo_plan_t *__restrict__ Pg, const PlanAux *__restrict__ Ag, Pl
         // ---- the aggregates, COLUMN AT A TIME over the thread's rows that live in private state
         for (int a = 0; a < naggs; a++) {
             const int vs = P.agg[a].value, kind = P.agg[a].kind;
-            const int ab = a * kThreads, gstride = naggs * kThreads;
+            const int ab = a * kThreads, gstride = naggs * kThreads, pv = vs >= 0 ? X.phys[vs] : 0;
             if (vs < 0) { if (X.need_cnt) { PLAN_FORJ if (ps[j] >= 0) pcnt[ps[j] * gstride + ab] += 1u; } continue; }          // COUNT(*)
             if (X.need_cnt) { PLAN_FORJ if (ps[j] >= 0 && !((nb[j] >> vs) & 1u)) pcnt[ps[j] * gstride + ab] += 1u; }
             if (kind == MO_AGG_SUM || kind == MO_AGG_AVG) {
-                PLAN_FORJ if (ps[j] >= 0 && !((nb[j] >> vs) & 1u)) { const int ix = ps[j] * gstride + ab; pacc[ix] = __dadd_rn(pacc[ix], __longlong_as_double((long long)PLAN_SLOT(vs, j))); }
+                PLAN_FORJ if (ps[j] >= 0 && !((nb[j] >> vs) & 1u)) { const int ix = ps[j] * gstride + ab; pacc[ix] = __dadd_rn(pacc[ix], __longlong_as_double((long long)PLAN_SLOT(pv, j))); }
             } else if (kind == MO_AGG_MIN) {
                 PLAN_FORJ if (ps[j] >= 0 && !((nb[j] >> vs) & 1u)) {
-                    const double v = __longlong_as_double((long long)PLAN_SLOT(vs, j)); const int ix = ps[j] * gstride + ab;
+                    const double v = __longlong_as_double((long long)PLAN_SLOT(pv, j)); const int ix = ps[j] * gstride + ab;
                     if (v == v) { const unsigned long long kv = flt_key(v); if (kv < (unsigned long long)__double_as_longlong(pacc[ix])) pacc[ix] = __longlong_as_double((long long)kv); }
                 }
             } else if (kind == MO_AGG_MAX) {
                 PLAN_FORJ if (ps[j] >= 0 && !((nb[j] >> vs) & 1u)) {
-                    const double v = __longlong_as_double((long long)PLAN_SLOT(vs, j)); const int ix = ps[j] * gstride + ab;
+                    const double v = __longlong_as_double((long long)PLAN_SLOT(pv, j)); const int ix = ps[j] * gstride + ab;
                     if (v == v) { const unsigned long long kv = flt_key(v); if (kv > (unsigned long long)__double_as_longlong(pacc[ix])) pacc[ix] = __longlong_as_double((long long)kv); }
                 }
             }
@@ -359,7 +364,7 @@ plan_kernel(const mo_plan_t *__restrict__ Pg, const PlanAux *__restrict__ Ag, Pl
                         const int vs = P.agg[a].value;
                         if (vs < 0) { atomicAdd(&cnt_p[a], 1ull); continue; }            // COUNT(*)
                         if ((nullbits >> vs) & 1u) continue;                             // aggregates skip NULLs
-                        agg_apply(P.agg[a].kind, &acc_p[a], __longlong_as_double((long long)PLAN_SLOT(vs, j)));
+                        agg_apply(P.agg[a].kind, &acc_p[a], __longlong_as_double((long long)PLAN_SLOT(X.phys[vs], j)));
                         atomicAdd(&cnt_p[a], 1ull);
                     }
                 }
@@ -705,6 +710,39 @@ int xcall_plan(mo_xcall_args_t *args, uint64_t len) {
         }
         for (int a = 0; a < P.naggs; a++) if (P.agg[a].value >= 0 && maybe[P.agg[a].value]) X.need_cnt = 1;
     }
+    {
+        // liveness-based slot allocation: the SSA program gives every node its own value slot; in shared memory a slot is reused once its value is
+        // dead.  Times: 0 load, 1 filter, 2 group keys, 3 + i expression node i, 3 + ninstr aggregates.
+        const int nv = P.ncols + P.ninstr, t_agg = 3 + P.ninstr;
+        int last[MO_PLAN_MAX_COLS + MO_PLAN_MAX_INSTR];
+        for (int v = 0; v < nv; v++) last[v] = v < P.ncols ? 0 : -1;
+        auto use = [&](int v, int when) { if (v >= 0 && v < nv && last[v] < when) last[v] = when; };
+        for (int j = 0; j < P.npreds; j++) use(P.pred[j].col, 1);
+        for (int k = 0; k < P.nkeys; k++) use(P.key_col[k], 2);
+        for (int i = 0; i < P.ninstr; i++) {
+            const mo_plan_instr_t &in = P.instr[i];
+            if (in.op != MO_PLAN_OP_CONST) use(in.a, 3 + i);
+            if (in.op >= MO_PLAN_OP_ADD) use(in.b, 3 + i);
+        }
+        for (int a = 0; a < P.naggs; a++) use(P.agg[a].value, t_agg);
+        bool busy[MO_PLAN_MAX_COLS + MO_PLAN_MAX_INSTR] = {false};
+        int nphys = P.ncols;
+        for (int c = 0; c < P.ncols; c++) { X.phys[c] = c; busy[c] = true; }
+        for (int i = 0; i < P.ninstr; i++) {
+            const int now = 3 + i, dst = P.ncols + i;
+            // values whose last reader is this node or an earlier phase give their slot back (a node may overwrite its own operand: every
+            // (thread, row) cell is read before it is written)
+            for (int v = 0; v < dst; v++) if (busy[X.phys[v]] && last[v] <= now) {
+                busy[X.phys[v]] = false; last[v] = 1 << 30;   // released once
+            }
+            int p = 0;
+            while (p < nphys && busy[p]) p++;
+            if (p == nphys) nphys++;
+            X.phys[dst] = p; busy[p] = true;
+            if (last[dst] < 0) last[dst] = now;             // a node nobody reads: its slot is free again after it
+        }
+        X.nphys = nphys;
+    }
     MOB_CUDA_TRY(cudaStreamSynchronize(t.stream));
     memcpy(t.pinned, &P, sizeof P);
     memcpy((char *)t.pinned + sizeof P, &X, sizeof X);
@@ -713,8 +751,8 @@ int xcall_plan(mo_xcall_args_t *args, uint64_t len) {
     const unsigned igrid = (unsigned)((cap + 1 + 255) / 256 > (uint64_t)num_sms() * 8 ? (uint64_t)num_sms() * 8 : (cap + 1 + 255) / 256);
     plan_init_kernel<<<igrid, 256, 0, t.stream>>>(G, P.naggs, dP);
     MOB_LAUNCH_CHECK();
-    const size_t smem = (size_t)(P.ncols + P.ninstr) * R * kThreads * 8 + (size_t)kCtaSlots * (24 + 16 * (size_t)P.naggs) +
-                        (size_t)kPriv * kThreads * ((size_t)P.naggs * 12 + 12);
+    const size_t smem = (size_t)X.nphys * R * kThreads * 8 + (size_t)kCtaSlots * (24 + 16 * (size_t)P.naggs) +
+                        (size_t)kPriv * kThreads * ((size_t)P.naggs * (X.need_cnt ? 12 : 8) + 12);
     static size_t attr_smem = 0;
     if (smem > attr_smem) { MOB_CUDA_TRY(cudaFuncSetAttribute(plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; }
     if (len) {

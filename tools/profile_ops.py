@@ -46,6 +46,8 @@ def main():
     out["plan_q6_recognised_shape"] = {"ms": ms, "gbs": 28.0 * n / ms / 1e6}
     ms = timed(lambda: p1.run([bufs[k] for k in names], n, max_groups=16, out_ptr=r1.ptr))
     out["plan_q1_recognised_shape"] = {"ms": ms, "gbs": 38.0 * n / ms / 1e6}
+    if os.environ.get("MOB_PROFILE_ONLY") == "plan":
+        print(json.dumps(out)); return
     spec6 = DeviceBuffer(16, lib)
     ms = timed(lambda: ops.q6_filter_sum_device(bufs["shipdate"], bufs["discount"], bufs["quantity"], bufs["extendedprice"], n, *datagen.q6_params(), out_ptr=spec6.ptr))
     out["q6_specialised"] = {"ms": ms, "gbs": 28.0 * n / ms / 1e6}
